@@ -505,6 +505,11 @@ int orc_read_matches(const orc_ctx *c, const char *seq, uint64_t n) {
     return !sd.terminal.empty();
 }
 
+void orc_window_floats(const uint32_t acgt[4], uint32_t size, float *gc, float *entropy) {
+    *gc = gcContent(acgt, size);
+    *entropy = shannon(acgt, size);
+}
+
 uint64_t orc_scan_many(const orc_ctx *c, const char *buf, const uint64_t *off, int count,
                        int tipsOnly, int threads) {
     std::atomic<int> next{0};

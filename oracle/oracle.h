@@ -87,6 +87,9 @@ size_t orc_result_windows(const orc_result *, const orc_window **out);
  * 42 unless -l was given; terminal_limit is overridden to UINT32_MAX/2 here. */
 int orc_read_matches(const orc_ctx *, const char *seq, uint64_t n);
 
+/* getGCContent / getShannonEntropy (include/teloscope.h:199-214) on given counters. */
+void orc_window_floats(const uint32_t acgt[4], uint32_t size, float *gc, float *entropy);
+
 /* Bulk helper for the CPU baseline: scans `count` segments laid out back to back (offsets has
  * count+1 entries) with `threads` std::threads, one job per segment like the reference's pool,
  * and returns a checksum of the results so the work cannot be optimised away. */

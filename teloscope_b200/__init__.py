@@ -1,0 +1,292 @@
+"""teloscope_b200 — B200-native telomeric motif scan (drop-in for Teloscope's scanSegment path).
+
+This package is a thin ctypes binding over the C ABI in include/teloscope_b200.h
+(libteloscope_b200.so: hand-written CUDA for sm_100a).  There is no CPU path: importing works
+anywhere (so the symbol table can be checked), but creating a Scanner without the built library
+or without a B200 raises.
+
+Reference interface mirrored here (all `path:line` relative to vgl-hub/teloscope):
+  * ScanConfig            <- UserInputTeloscope scan fields, include/input.h:31-48
+  * expand_patterns()     <- expandPatternsWithOrientation, src/tools.cpp:201-283
+  * Scanner.scan_segment  <- Teloscope::scanSegment, include/teloscope.h:260
+  * Scanner.read_matches  <- ReadTelomereFilter::matches, src/read-filter.cpp:37-45
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+__all__ = ["ScanConfig", "Scanner", "BatchResult", "expand_patterns", "load_library", "LIB_PATH",
+           "MODE_GENOME", "MODE_TIPS", "MODE_READS", "MATCH_DT", "BLOCK_DT", "WINDOW_DT", "TlsError"]
+
+LIB_PATH = Path(__file__).resolve().parent / "libteloscope_b200.so"
+ABI_VERSION = 1
+MODE_GENOME, MODE_TIPS, MODE_READS = 0, 1, 2
+OUT_ACGT, OUT_MATCHES, OUT_ITS = 1, 2, 4
+
+MATCH_DT = np.dtype([("pos", "<u8"), ("len", "<u2"), ("fwd", "u1"), ("can", "u1"), ("pad", "<u4")])
+BLOCK_DT = np.dtype([("start", "<u8"), ("len", "<u4"), ("counts", "<u4"), ("fwd_count", "<u4"),
+                     ("rev_count", "<u4"), ("can_count", "<u4"), ("noncan_count", "<u4"),
+                     ("total_cov", "<u4"), ("fwd_cov", "<u4"), ("can_cov", "<u4"),
+                     ("valid_or", "u1"), ("label", "S1"), ("pad", "<u2")])
+WINDOW_DT = np.dtype([("acgt", "<u4", (4,)), ("can_cov", "<u4"), ("noncan_cov", "<u4"),
+                      ("fwd_cov", "<u4"), ("rev_cov", "<u4")])
+assert MATCH_DT.itemsize == 16 and BLOCK_DT.itemsize == 48 and WINDOW_DT.itemsize == 32
+
+
+class TlsError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("n_patterns", C.c_uint32),
+                ("patterns", C.POINTER(C.c_char_p)), ("is_forward", C.POINTER(C.c_uint8)),
+                ("is_canonical", C.POINTER(C.c_uint8)),
+                ("window_size", C.c_uint32), ("step", C.c_uint32), ("terminal_limit", C.c_uint32),
+                ("max_match_dist", C.c_uint16), ("min_block_len", C.c_uint16),
+                ("max_block_dist", C.c_uint16), ("min_block_counts", C.c_uint16),
+                ("min_block_density", C.c_float), ("outputs", C.c_uint32)]
+
+
+class _Batch(C.Structure):
+    _fields_ = [("seq", C.c_void_p), ("offsets", C.c_void_p), ("abs_pos", C.c_void_p),
+                ("n_items", C.c_uint32), ("mode", C.c_uint32), ("seq_on_device", C.c_uint32),
+                ("pad", C.c_uint32)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_items", C.c_uint32), ("mode", C.c_uint32),
+                ("window_off", C.c_void_p), ("windows", C.c_void_p),
+                ("terminal_off", C.c_void_p), ("terminal", C.c_void_p),
+                ("its_off", C.c_void_p), ("its", C.c_void_p),
+                ("canonical_off", C.c_void_p), ("canonical", C.c_void_p),
+                ("noncanonical_off", C.c_void_p), ("noncanonical", C.c_void_p),
+                ("n_canonical", C.c_void_p), ("n_fwd", C.c_void_p), ("n_rev", C.c_void_p),
+                ("pass_", C.c_void_p),
+                ("scan_kernel_ms", C.c_float), ("device_ms", C.c_float),
+                ("n_bases_scanned", C.c_uint64), ("n_matches", C.c_uint64),
+                ("n_kernel_launches", C.c_uint32), ("pad", C.c_uint32)]
+
+
+EXPORTS = ("tls_expand_patterns", "tls_device_count", "tls_create", "tls_destroy", "tls_submit",
+           "tls_collect", "tls_release", "tls_last_error")
+
+_lib = None
+
+
+def load_library():
+    """dlopen libteloscope_b200.so (built in-tree by `make -C teloscope_b200/csrc` or
+    __graft_entry__.build()).  Raises if it is missing — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise TlsError(f"{LIB_PATH} not built; run `make -C {LIB_PATH.parent / 'csrc'}` "
+                       "(this package has no CPU implementation)")
+    L = C.CDLL(str(LIB_PATH))
+    L.tls_last_error.restype = C.c_char_p
+    L.tls_expand_patterns.restype = C.c_int
+    L.tls_expand_patterns.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t,
+                                      C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                      C.POINTER(C.c_size_t)]
+    L.tls_device_count.restype = C.c_int
+    L.tls_create.restype = C.c_int
+    L.tls_create.argtypes = [C.POINTER(_Config), C.c_int, C.POINTER(C.c_void_p)]
+    L.tls_destroy.argtypes = [C.c_void_p]
+    L.tls_submit.restype = C.c_int
+    L.tls_submit.argtypes = [C.c_void_p, C.POINTER(_Batch), C.POINTER(C.c_int)]
+    L.tls_collect.restype = C.c_int
+    L.tls_collect.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Result)]
+    L.tls_release.restype = C.c_int
+    L.tls_release.argtypes = [C.c_void_p, C.c_int]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise TlsError(f"tls error {rc}: {load_library().tls_last_error().decode()}")
+
+
+def revcomp(s: str) -> str:
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+def expand_patterns(raw: list[str], edit_distance: int, canonical_fwd: str):
+    """-> list of (pattern, is_forward, is_canonical) exactly as the reference's
+    expandPatternsWithOrientation + Teloscope ctor produce them."""
+    L = load_library()
+    n, need = C.c_uint32(), C.c_size_t()
+    csv = ",".join(raw).encode()
+    _check(L.tls_expand_patterns(csv, edit_distance, canonical_fwd.encode(), None, 0, None, None, 0,
+                                 C.byref(n), C.byref(need)))
+    text = C.create_string_buffer(max(need.value, 1))
+    fwd = (C.c_uint8 * max(n.value, 1))()
+    can = (C.c_uint8 * max(n.value, 1))()
+    _check(L.tls_expand_patterns(csv, edit_distance, canonical_fwd.encode(), text, need.value, fwd, can,
+                                 n.value, C.byref(n), C.byref(need)))
+    pats = text.raw[:need.value].split(b"\0")[:n.value]
+    return [(p.decode(), bool(fwd[i]), bool(can[i])) for i, p in enumerate(pats)]
+
+
+@dataclass
+class ScanConfig:
+    """Scan-relevant fields of UserInputTeloscope after main() processed the flags
+    (include/input.h:31-48, src/main.cpp:287-296 for -c, :617-643 for the pattern table)."""
+    canonical: str = "TTAGGG"                 # -c (either strand; the lexicographically smaller is Fwd)
+    patterns: list[str] | None = None         # -p seeds; None = canonical pair
+    edit_distance: int = 1                    # -x
+    window_size: int = 1000                   # -w
+    step: int = 1000                          # -s
+    terminal_limit: int = 50000               # -t
+    max_match_dist: int = 50                  # -k
+    min_block_len: int = 300                  # -l (42 in read modes unless given)
+    max_block_dist: int = 500                 # -d
+    min_block_counts: int = 2
+    min_block_density: float = 0.5            # -y
+    out_acgt: bool = True                     # -g or -e
+    out_matches: bool = True                  # -m
+    canonical_fwd: str = field(init=False)
+    canonical_rev: str = field(init=False)
+
+    def __post_init__(self):
+        c = self.canonical.upper()
+        rc = revcomp(c)
+        self.canonical_fwd, self.canonical_rev = (c, rc) if c <= rc else (rc, c)
+
+    def raw_patterns(self) -> list[str]:
+        if self.patterns:
+            return [p.upper() for p in self.patterns]
+        return [self.canonical_fwd, self.canonical_rev]
+
+
+class BatchResult:
+    """Per-item views of one collected batch (numpy copies; independent of the ctx)."""
+
+    def __init__(self, r: _Result):
+        n = r.n_items
+        self.n_items, self.mode = n, r.mode
+
+        def arr(ptr, count, dt):
+            if not ptr or count == 0:
+                return np.zeros(0, dtype=dt)
+            return np.frombuffer(C.string_at(ptr, int(count) * np.dtype(dt).itemsize), dtype=dt).copy()
+
+        def off(ptr):
+            return arr(ptr, n + 1, "<u8") if ptr else np.zeros(n + 1, dtype="<u8")
+
+        self.window_off = off(r.window_off)
+        self.windows = arr(r.windows, self.window_off[-1] if r.mode == MODE_GENOME else 0, WINDOW_DT)
+        self.terminal_off = off(r.terminal_off)
+        self.terminal = arr(r.terminal, self.terminal_off[-1], BLOCK_DT)
+        self.its_off = off(r.its_off)
+        self.its = arr(r.its, self.its_off[-1], BLOCK_DT)
+        self.canonical_off = off(r.canonical_off)
+        self.canonical = arr(r.canonical, self.canonical_off[-1], MATCH_DT)
+        self.noncanonical_off = off(r.noncanonical_off)
+        self.noncanonical = arr(r.noncanonical, self.noncanonical_off[-1], MATCH_DT)
+        self.n_canonical = arr(r.n_canonical, n, "<u4")
+        self.n_fwd = arr(r.n_fwd, n, "<u4")
+        self.n_rev = arr(r.n_rev, n, "<u4")
+        self.passed = arr(r.pass_, n, "u1").astype(bool)
+        self.scan_kernel_ms = float(r.scan_kernel_ms)
+        self.device_ms = float(r.device_ms)
+        self.n_bases_scanned = int(r.n_bases_scanned)
+        self.n_matches = int(r.n_matches)
+        self.n_kernel_launches = int(r.n_kernel_launches)
+
+    def item(self, i: int) -> dict:
+        """What SegmentData holds for item i (include/teloscope.h:139-148)."""
+        s = lambda a, o: a[int(o[i]):int(o[i + 1])]
+        return {"windows": s(self.windows, self.window_off), "terminal": s(self.terminal, self.terminal_off),
+                "its": s(self.its, self.its_off), "canonical": s(self.canonical, self.canonical_off),
+                "noncanonical": s(self.noncanonical, self.noncanonical_off),
+                "n_canonical": int(self.n_canonical[i]) if len(self.n_canonical) else 0}
+
+
+class Scanner:
+    """One pattern table + parameter set bound to one GPU (a `Teloscope` instance)."""
+
+    def __init__(self, cfg: ScanConfig, device: int = 0):
+        L = load_library()
+        self.cfg = cfg
+        self.table = expand_patterns(cfg.raw_patterns(), cfg.edit_distance, cfg.canonical_fwd)
+        n = len(self.table)
+        pats = (C.c_char_p * n)(*[p.encode() for p, _, _ in self.table])
+        fwd = (C.c_uint8 * n)(*[int(f) for _, f, _ in self.table])
+        can = (C.c_uint8 * n)(*[int(c) for _, _, c in self.table])
+        outputs = (OUT_ACGT if cfg.out_acgt else 0) | (OUT_MATCHES if cfg.out_matches else 0) | OUT_ITS
+        c = _Config(ABI_VERSION, n, pats, fwd, can, cfg.window_size, cfg.step, cfg.terminal_limit,
+                    cfg.max_match_dist, cfg.min_block_len, cfg.max_block_dist, cfg.min_block_counts,
+                    float(np.float32(cfg.min_block_density)), outputs)
+        h = C.c_void_p()
+        _check(L.tls_create(C.byref(c), device, C.byref(h)))
+        self._h, self._L = h, L
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tls_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- batch interface (the C ABI, one call per batch) ------------------------------------
+    def submit(self, seq, offsets: np.ndarray, abs_pos: np.ndarray | None = None, mode: int = MODE_GENOME,
+               device_ptr: int | None = None) -> int:
+        """seq: bytes / numpy uint8 array on the host, or pass device_ptr (a CUDA address on this
+        scanner's device, e.g. torch_tensor.data_ptr()) for a device-resident batch."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        keep = [offsets]
+        b = _Batch()
+        if device_ptr is not None:
+            b.seq, b.seq_on_device = device_ptr, 1
+        else:
+            if isinstance(seq, (bytes, bytearray)):
+                seq = np.frombuffer(seq, dtype=np.uint8)
+            seq = np.ascontiguousarray(seq, dtype=np.uint8)
+            keep.append(seq)
+            b.seq, b.seq_on_device = seq.ctypes.data, 0
+        b.offsets = offsets.ctypes.data
+        if abs_pos is not None:
+            abs_pos = np.ascontiguousarray(abs_pos, dtype=np.uint64)
+            keep.append(abs_pos)
+            b.abs_pos = abs_pos.ctypes.data
+        b.n_items, b.mode = n, mode
+        t = C.c_int()
+        _check(self._L.tls_submit(self._h, C.byref(b), C.byref(t)))
+        self._keep[t.value] = keep
+        return t.value
+
+    def collect(self, ticket: int) -> BatchResult:
+        r = _Result()
+        _check(self._L.tls_collect(self._h, ticket, C.byref(r)))
+        out = BatchResult(r)
+        _check(self._L.tls_release(self._h, ticket))
+        self._keep.pop(ticket, None)
+        return out
+
+    def scan_batch(self, seqs: list[bytes], abs_pos=None, mode: int = MODE_GENOME) -> BatchResult:
+        offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum([len(s) for s in seqs], out=offsets[1:])
+        buf = np.frombuffer(b"".join(seqs), dtype=np.uint8) if seqs else np.zeros(0, dtype=np.uint8)
+        return self.collect(self.submit(buf, offsets, abs_pos, mode))
+
+    # ---- the reference's per-call interface ----------------------------------------------------
+    def scan_segment(self, sequence: bytes, abs_pos: int = 0, tips_only: bool = False) -> dict:
+        """Teloscope::scanSegment(sequence, absPos, tipsOnly) -> SegmentData (as a dict of arrays)."""
+        r = self.scan_batch([sequence], np.array([abs_pos], dtype=np.uint64), MODE_TIPS if tips_only else MODE_GENOME)
+        return r.item(0)
+
+    def read_matches(self, sequence: bytes) -> bool:
+        """ReadTelomereFilter::matches(sequence)."""
+        return bool(self.scan_batch([sequence], None, MODE_READS).passed[0])

@@ -1,0 +1,676 @@
+// C ABI of the B200-native scan (include/teloscope_b200.h): context, pinned double-buffered
+// staging, tiling of the batch into scan regions, kernel sequencing, result assembly.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/teloscope_b200.h"
+#include "kernels.hpp"
+#include "patterns.hpp"
+
+namespace tls {
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define TLS_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(TLS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// Growable device / pinned-host buffers -----------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Slot {
+    bool busy = false, collected = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evScan0 = nullptr, evScan1 = nullptr, evAll0 = nullptr, evAll1 = nullptr;
+    // inputs
+    uint32_t nItems = 0, mode = 0;
+    uint64_t seqBytes = 0, nBases = 0, nWindows = 0;
+    std::vector<uint64_t> absPos;
+    std::vector<uint32_t> itemLen;
+    std::vector<uint64_t> winOff;            // per item window offsets (n+1)
+    std::vector<DevRegion> regions;
+    std::vector<DevTile> tiles;
+    const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
+    HostBuf hSeq, hMeta;                      // pinned staging
+    DevBuf dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dStatus,
+        dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
+    // device counters block: [0] tileCounter(u32) [8] totalMatches(u64) [16] blockCount(u32) [24] selTotals(2 x u64)
+    HostBuf hCounters, hWindows, hItemCounts, hBlocks, hPass, hSelCan, hSelNon;
+    uint64_t matchCap = 0;
+    uint32_t blockCap = 0;
+    uint32_t launches = 0;
+    // assembled results
+    std::vector<uint64_t> terminalOff, itsOff, canOff, nonOff;
+    std::vector<tls_block> terminal, its;
+    std::vector<tls_match> canonical, noncanonical;
+    std::vector<uint32_t> nCan, nFwd, nRev;
+    std::vector<uint8_t> pass;
+    uint64_t nMatches = 0;
+    float scanMs = 0, allMs = 0;
+};
+
+}  // namespace
+}  // namespace tls
+
+using namespace tls;
+
+struct tls_ctx {
+    int device = 0;
+    int smCount = 0;
+    tls_config cfg{};
+    std::vector<Pattern> patterns;
+    ScanTables tables;
+    DevConfig dcfg{};
+    DevBuf dIndex, dFlags, dKeys, dKeyFlags, dScratch;
+    uint32_t scratchPerWarp = 0;
+    Slot slot[2];
+};
+
+namespace {
+
+void fillDivider(DevConfig &c, uint32_t d) {
+    // Granlund-Montgomery round-up method for u32 / invariant d >= 1
+    uint32_t L = 0;
+    while ((1ull << L) < d) ++L;
+    const uint64_t m = ((1ull << 32) * ((1ull << L) - d)) / d + 1;
+    c.winMagic = static_cast<uint32_t>(m);
+    c.winSh1 = L < 1 ? L : 1;
+    c.winSh2 = L > 1 ? L - 1 : 0;
+}
+
+int buildDevConfig(tls_ctx *ctx) {
+    const ScanTables &t = ctx->tables;
+    DevConfig &c = ctx->dcfg;
+    c = DevConfig{};
+    c.nClasses = static_cast<uint32_t>(t.classes.size());
+    c.minLen = t.minLen; c.maxLen = t.maxLen; c.npos = t.npos;
+    for (size_t i = 0; i < t.classes.size(); ++i) {
+        c.cls[i].len = t.classes[i].len;
+        c.cls[i].direct = t.classes[i].direct ? 1u : 0u;
+        c.cls[i].flagOffset = t.classes[i].flagOffset;
+        c.cls[i].sortedBegin = t.classes[i].sortedBegin;
+        c.cls[i].sortedCount = t.classes[i].sortedCount;
+    }
+    c.flagTabBytes = static_cast<uint32_t>((t.flagTables.size() + 15) & ~size_t(15));
+    if (c.flagTabBytes > static_cast<uint32_t>(kFlagTabBytes))
+        return fail(TLS_ERR_INVALID, "direct pattern tables need %u bytes (> %d)", c.flagTabBytes, kFlagTabBytes);
+    const tls_config &u = ctx->cfg;
+    c.windowSize = u.window_size; c.step = u.step; c.terminalLimit = u.terminal_limit;
+    c.maxMatchDist = u.max_match_dist; c.minBlockLen = u.min_block_len; c.maxBlockDist = u.max_block_dist;
+    c.minBlockCounts = u.min_block_counts; c.itsMinLen = t.itsMinLen; c.minBlockDensity = u.min_block_density;
+    c.countAcgt = (u.outputs & TLS_OUT_ACGT) ? 1u : 0u;
+    fillDivider(c, u.window_size);
+    return TLS_OK;
+}
+
+int upload(DevBuf &b, const void *src, size_t bytes) {
+    TLS_CUDA(b.reserve(std::max<size_t>(bytes, 16)));
+    if (bytes) TLS_CUDA(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return TLS_OK;
+}
+
+// Split the batch into scan regions and tiles (host, O(items + bases/48K)).
+int planBatch(const tls_ctx *ctx, const tls_batch *b, Slot &s) {
+    const uint32_t n = b->n_items;
+    (void)ctx;
+    s.regions.clear(); s.tiles.clear();
+    s.itemLen.assign(n, 0);
+    s.absPos.assign(n, 0);
+    s.winOff.assign(n + 1, 0);
+    s.nBases = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t a = b->offsets[i], e = b->offsets[i + 1];
+        if (e < a) return fail(TLS_ERR_INVALID, "offsets not monotone at item %u", i);
+        uint64_t len = e - a;
+        if (len > 0xFFFFFFFFull) return fail(TLS_ERR_INVALID, "item %u longer than 2^32-1 bases", i);
+        s.absPos[i] = b->abs_pos ? b->abs_pos[i] : 0;
+        s.itemLen[i] = static_cast<uint32_t>(len);    // read mode '\r' trim happens in submit (host) below
+    }
+    return TLS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tls_last_error(void) { return g_err.c_str(); }
+
+int tls_expand_patterns(const char *raw_csv, int edit_distance, const char *canonical_fwd, char *text,
+                        size_t text_len, uint8_t *is_forward, uint8_t *is_canonical, uint32_t cap,
+                        uint32_t *n_out, size_t *text_need) {
+    if (!raw_csv || !canonical_fwd || !n_out) return fail(TLS_ERR_INVALID, "null argument");
+    std::vector<std::string> raw;
+    std::string cur;
+    for (const char *p = raw_csv;; ++p) {
+        if (*p == ',' || *p == 0) {
+            if (!cur.empty()) raw.push_back(cur);
+            cur.clear();
+            if (!*p) break;
+        } else {
+            cur.push_back(*p);
+        }
+    }
+    std::vector<Pattern> pats;
+    std::string err;
+    if (!expandPatterns(raw, edit_distance, canonical_fwd, pats, err)) return fail(TLS_ERR_INVALID, "%s", err.c_str());
+    size_t need = 0;
+    for (const Pattern &p : pats) need += p.text.size() + 1;
+    *n_out = static_cast<uint32_t>(pats.size());
+    if (text_need) *text_need = need;
+    if (!text) return TLS_OK;
+    if (need > text_len || pats.size() > cap) return fail(TLS_ERR_INVALID, "output buffers too small");
+    char *w = text;
+    for (size_t i = 0; i < pats.size(); ++i) {
+        std::memcpy(w, pats[i].text.c_str(), pats[i].text.size() + 1);
+        w += pats[i].text.size() + 1;
+        if (is_forward) is_forward[i] = pats[i].isForward;
+        if (is_canonical) is_canonical[i] = pats[i].isCanonical;
+    }
+    return TLS_OK;
+}
+
+int tls_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp pr;
+        if (cudaGetDeviceProperties(&pr, i) == cudaSuccess && pr.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
+    if (!cfg || !out) return fail(TLS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != TLS_ABI_VERSION) return fail(TLS_ERR_INVALID, "ABI version mismatch");
+    if (cfg->n_patterns == 0 || !cfg->patterns || !cfg->is_forward || !cfg->is_canonical)
+        return fail(TLS_ERR_INVALID, "empty pattern table");
+    if (cfg->window_size == 0 || cfg->step == 0 || cfg->step > cfg->window_size)
+        return fail(TLS_ERR_INVALID, "need 0 < step <= window_size");
+    if (cfg->step != cfg->window_size)
+        return fail(TLS_ERR_INVALID, "overlapping windows (step < window) are not implemented on the device yet");
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
+        cudaGetLastError();
+        return fail(TLS_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU path)");
+    }
+    if (device < 0 || device >= nDev) return fail(TLS_ERR_INVALID, "device %d out of range", device);
+    cudaDeviceProp prop;
+    TLS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(TLS_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    TLS_CUDA(cudaSetDevice(device));
+
+    std::unique_ptr<tls_ctx> ctx(new (std::nothrow) tls_ctx);
+    if (!ctx) return fail(TLS_ERR_NOMEM, "out of memory");
+    ctx->device = device;
+    ctx->smCount = prop.multiProcessorCount;
+    ctx->cfg = *cfg;
+    for (uint32_t i = 0; i < cfg->n_patterns; ++i) {
+        Pattern p;
+        p.text = cfg->patterns[i] ? cfg->patterns[i] : "";
+        p.isForward = cfg->is_forward[i] != 0;
+        p.isCanonical = cfg->is_canonical[i] != 0;
+        ctx->patterns.push_back(std::move(p));
+    }
+    ctx->cfg.patterns = nullptr; ctx->cfg.is_forward = nullptr; ctx->cfg.is_canonical = nullptr;
+    std::string err;
+    if (!buildScanTables(ctx->patterns, ctx->tables, err)) return fail(TLS_ERR_INVALID, "%s", err.c_str());
+    int rc = buildDevConfig(ctx.get());
+    if (rc) return rc;
+    const ScanTables &t = ctx->tables;
+    if ((rc = upload(ctx->dIndex, t.index8.data(), t.index8.size()))) return rc;
+    {
+        std::vector<uint8_t> padded(ctx->dcfg.flagTabBytes, 0);
+        std::copy(t.flagTables.begin(), t.flagTables.end(), padded.begin());
+        if ((rc = upload(ctx->dFlags, padded.data(), padded.size()))) return rc;
+    }
+    if ((rc = upload(ctx->dKeys, t.sortedKeys.data(), t.sortedKeys.size() * 8))) return rc;
+    if ((rc = upload(ctx->dKeyFlags, t.sortedFlags.data(), t.sortedFlags.size()))) return rc;
+    ctx->scratchPerWarp = static_cast<uint32_t>(kRowsPerWarp * kRowBytes) * ctx->dcfg.nClasses;
+    TLS_CUDA(ctx->dScratch.reserve(static_cast<size_t>(ctx->smCount) * kScanWarps * ctx->scratchPerWarp * sizeof(DevMatch)));
+    for (Slot &s : ctx->slot) {
+        TLS_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        TLS_CUDA(cudaEventCreate(&s.evScan0)); TLS_CUDA(cudaEventCreate(&s.evScan1));
+        TLS_CUDA(cudaEventCreate(&s.evAll0)); TLS_CUDA(cudaEventCreate(&s.evAll1));
+        TLS_CUDA(s.dCounters.reserve(64));
+        TLS_CUDA(s.hCounters.reserve(64));
+    }
+    *out = ctx.release();
+    return TLS_OK;
+}
+
+void tls_destroy(tls_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (Slot &s : ctx->slot) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        for (DevBuf *b : {&s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
+                          &s.dMatches, &s.dStatus, &s.dCounters, &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch,
+                          &s.dSelCan, &s.dSelNon})
+            b->release();
+        for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
+                           &s.hSelCan, &s.hSelNon})
+            b->release();
+        if (s.evScan0) cudaEventDestroy(s.evScan0);
+        if (s.evScan1) cudaEventDestroy(s.evScan1);
+        if (s.evAll0) cudaEventDestroy(s.evAll0);
+        if (s.evAll1) cudaEventDestroy(s.evAll1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (DevBuf *b : {&ctx->dIndex, &ctx->dFlags, &ctx->dKeys, &ctx->dKeyFlags, &ctx->dScratch}) b->release();
+    delete ctx;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Enqueue the fused scan for the slot (memsets + kernel + copy of the counters).
+int enqueueScan(tls_ctx *ctx, Slot &s) {
+    const uint32_t nTiles = static_cast<uint32_t>(s.tiles.size());
+    TLS_CUDA(s.dMatches.reserve(std::max<uint64_t>(s.matchCap, 1) * sizeof(DevMatch)));
+    TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 64, s.stream));
+    TLS_CUDA(cudaMemsetAsync(s.dStatus.p, 0, std::max<size_t>(nTiles, 1) * 8, s.stream));
+    TLS_CUDA(cudaMemsetAsync(s.dItemCounts.p, 0, std::max<size_t>(s.nItems, 1) * sizeof(DevItemCounts), s.stream));
+    if (s.nWindows) TLS_CUDA(cudaMemsetAsync(s.dWindows.p, 0, s.nWindows * 32, s.stream));
+    s.launches = 0;
+    if (nTiles) {
+        ScanParams p{};
+        p.seq = s.devSeq;
+        p.tiles = s.dTiles.as<DevTile>();
+        p.regions = s.dRegions.as<DevRegion>();
+        p.nTiles = nTiles;
+        p.nRegions = static_cast<uint32_t>(s.regions.size());
+        p.index8 = ctx->dIndex.as<uint8_t>();
+        p.flagTabs = ctx->dFlags.as<uint8_t>();
+        p.sortedKeys = ctx->dKeys.as<uint64_t>();
+        p.sortedFlags = ctx->dKeyFlags.as<uint8_t>();
+        p.matches = s.dMatches.as<DevMatch>();
+        p.matchCap = s.matchCap;
+        p.scratch = ctx->dScratch.as<DevMatch>();
+        p.scratchPerWarp = ctx->scratchPerWarp;
+        uint8_t *cnt = s.dCounters.as<uint8_t>();
+        p.tileCounter = reinterpret_cast<unsigned int *>(cnt);
+        p.totalMatches = reinterpret_cast<unsigned long long *>(cnt + 8);
+        p.tileStatus = s.dStatus.as<unsigned long long>();
+        p.windows = s.dWindows.as<uint32_t>();
+        p.itemCounts = s.dItemCounts.as<DevItemCounts>();
+        p.cfg = ctx->dcfg;
+        p.cfg.mode = s.mode;
+        if (s.mode != TLS_MODE_GENOME) p.cfg.countAcgt = 0;
+        TLS_CUDA(cudaEventRecord(s.evScan0, s.stream));
+        TLS_CUDA(launchScan(p, std::min<int>(ctx->smCount, static_cast<int>(nTiles)), s.stream));
+        TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
+        s.launches++;
+    }
+    TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 64, cudaMemcpyDeviceToHost, s.stream));
+    return TLS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
+    if (!ctx || !b || !ticket) return fail(TLS_ERR_INVALID, "null argument");
+    if (b->n_items && (!b->seq || !b->offsets)) return fail(TLS_ERR_INVALID, "null batch arrays");
+    if (b->mode > TLS_MODE_READS) return fail(TLS_ERR_INVALID, "bad mode %u", b->mode);
+    int si = -1;
+    for (int i = 0; i < 2; ++i) if (!ctx->slot[i].busy) { si = i; break; }
+    if (si < 0) return fail(TLS_ERR_STATE, "two tickets already in flight");
+    TLS_CUDA(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slot[si];
+    const uint32_t n = b->n_items;
+    const uint32_t T = ctx->cfg.terminal_limit, S = ctx->cfg.step;
+    s.nItems = n; s.mode = b->mode; s.collected = false;
+    int rc = planBatch(ctx, b, s);
+    if (rc) return rc;
+    const uint64_t base = n ? b->offsets[0] : 0;
+    s.seqBytes = n ? b->offsets[n] - base : 0;
+
+    // ---- stage the sequence -----------------------------------------------------------------
+    if (b->seq_on_device) {
+        s.devSeq = b->seq;
+    } else {
+        TLS_CUDA(s.dSeq.reserve(s.seqBytes + 512));
+        cudaPointerAttributes attr{};
+        const bool pinned = cudaPointerGetAttributes(&attr, b->seq) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const uint8_t *src = b->seq + base;
+        if (!pinned && s.seqBytes) {
+            TLS_CUDA(s.hSeq.reserve(s.seqBytes));
+            std::memcpy(s.hSeq.p, src, s.seqBytes);
+            src = s.hSeq.as<uint8_t>();
+        }
+        if (s.seqBytes) TLS_CUDA(cudaMemcpyAsync(s.dSeq.p, src, s.seqBytes, cudaMemcpyHostToDevice, s.stream));
+        TLS_CUDA(cudaMemsetAsync(s.dSeq.as<uint8_t>() + s.seqBytes, 0, 256, s.stream));
+        s.devSeq = s.dSeq.as<uint8_t>();
+    }
+    const uint64_t devBase = b->seq_on_device ? 0 : base;   // offsets are relative to devSeq after this shift
+
+    // ---- read mode: drop one trailing '\r' per read (src/read-filter.cpp:38-40) -------------------
+    if (b->mode == TLS_MODE_READS && !b->seq_on_device) {
+        for (uint32_t i = 0; i < n; ++i)
+            if (s.itemLen[i] && b->seq[b->offsets[i + 1] - 1] == '\r') --s.itemLen[i];
+    }
+
+    // ---- regions ------------------------------------------------------------------------------
+    uint64_t nWin = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t a = b->offsets[i] - devBase;
+        const uint32_t len = s.itemLen[i];
+        s.winOff[i] = nWin;
+        auto add = [&](uint32_t rs, uint32_t rl) {
+            DevRegion r{};
+            r.bufStart = a + rs; r.len = rl; r.item = i; r.relStart = rs; r.itemLen = len;
+            r.winBase = static_cast<uint32_t>(s.winOff[i]);
+            s.regions.push_back(r);
+            s.nBases += rl;
+        };
+        if (len == 0) continue;
+        if (b->mode == TLS_MODE_GENOME) {
+            nWin += (static_cast<uint64_t>(len) + S - 1) / S;          // src/teloscope.cpp:608-637
+            add(0, len);
+        } else if (b->mode == TLS_MODE_TIPS && len > static_cast<uint32_t>(2u * T)) {   // :576 (uint32 product)
+            add(0, T);
+            add(len - T, T);
+        } else {
+            add(0, len);
+        }
+    }
+    s.winOff[n] = nWin;
+    s.nWindows = nWin;
+    if (nWin > 0xFFFFFFFFull) return fail(TLS_ERR_INVALID, "more than 2^32 windows in one batch");
+
+    // ---- tiles: cut runs of (nearly) adjacent regions into pieces of <= kTileMaxLen bytes ------------
+    {
+        size_t r = 0;
+        const size_t nr = s.regions.size();
+        while (r < nr) {
+            uint64_t spanStart = s.regions[r].bufStart, spanEnd = spanStart + s.regions[r].len;
+            size_t e = r + 1;
+            while (e < nr && s.regions[e].bufStart - spanEnd <= 4096) { spanEnd = s.regions[e].bufStart + s.regions[e].len; ++e; }
+            size_t fr = r;
+            for (uint64_t p = spanStart; p < spanEnd; p += kTileMaxLen) {
+                DevTile t{};
+                t.bufStart = p;
+                t.len = static_cast<uint32_t>(std::min<uint64_t>(kTileMaxLen, spanEnd - p));
+                while (fr + 1 < e && s.regions[fr].bufStart + s.regions[fr].len <= p) ++fr;
+                t.firstRegion = static_cast<uint32_t>(fr);
+                s.tiles.push_back(t);
+            }
+            r = e;
+        }
+    }
+
+    // ---- upload metadata ------------------------------------------------------------------------
+    const size_t bRegions = s.regions.size() * sizeof(DevRegion), bTiles = s.tiles.size() * sizeof(DevTile),
+                 bLen = static_cast<size_t>(n) * 4;
+    TLS_CUDA(s.hMeta.reserve(bRegions + bTiles + bLen + 64));
+    uint8_t *hm = s.hMeta.as<uint8_t>();
+    if (bRegions) std::memcpy(hm, s.regions.data(), bRegions);
+    if (bTiles) std::memcpy(hm + bRegions, s.tiles.data(), bTiles);
+    if (bLen) std::memcpy(hm + bRegions + bTiles, s.itemLen.data(), bLen);
+    TLS_CUDA(s.dRegions.reserve(std::max<size_t>(bRegions, 16)));
+    TLS_CUDA(s.dTiles.reserve(std::max<size_t>(bTiles, 16)));
+    TLS_CUDA(s.dItemLen.reserve(std::max<size_t>(bLen, 16)));
+    if (bRegions) TLS_CUDA(cudaMemcpyAsync(s.dRegions.p, hm, bRegions, cudaMemcpyHostToDevice, s.stream));
+    if (bTiles) TLS_CUDA(cudaMemcpyAsync(s.dTiles.p, hm + bRegions, bTiles, cudaMemcpyHostToDevice, s.stream));
+    if (bLen) TLS_CUDA(cudaMemcpyAsync(s.dItemLen.p, hm + bRegions + bTiles, bLen, cudaMemcpyHostToDevice, s.stream));
+    TLS_CUDA(s.dStatus.reserve(std::max<size_t>(s.tiles.size(), 1) * 8));
+    TLS_CUDA(s.dItemCounts.reserve(std::max<size_t>(n, 1) * sizeof(DevItemCounts)));
+    TLS_CUDA(s.dItemBegin.reserve((static_cast<size_t>(n) + 1) * 8));
+    TLS_CUDA(s.dWindows.reserve(std::max<uint64_t>(nWin, 1) * 32));
+    TLS_CUDA(s.dBoundaries.reserve(std::max<size_t>(n, 1) * 8));
+    TLS_CUDA(s.dPass.reserve(std::max<size_t>(n, 1)));
+    s.matchCap = std::max<uint64_t>(s.matchCap, s.nBases / 8 + 65536);
+
+    TLS_CUDA(cudaEventRecord(s.evAll0, s.stream));
+    if (b->mode == TLS_MODE_READS && b->seq_on_device)
+        TLS_CUDA(launchTrimCr(s.devSeq, s.dRegions.as<DevRegion>(), static_cast<uint32_t>(s.regions.size()),
+                              s.dItemLen.as<uint32_t>(), s.stream));
+    if ((rc = enqueueScan(ctx, s))) return rc;
+    s.busy = true;
+    *ticket = si;
+    return TLS_OK;
+}
+
+int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
+    if (!ctx || !res || ticket < 0 || ticket > 1 || !ctx->slot[ticket].busy)
+        return fail(TLS_ERR_STATE, "bad ticket");
+    TLS_CUDA(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slot[ticket];
+    const uint32_t n = s.nItems;
+    int rc;
+    if (!s.collected) {
+        // ---- wait for the scan; grow the match list and rerun if it overflowed ---------------------
+        for (;;) {
+            TLS_CUDA(cudaStreamSynchronize(s.stream));
+            s.nMatches = *reinterpret_cast<unsigned long long *>(s.hCounters.as<uint8_t>() + 8);
+            if (s.nMatches <= s.matchCap) break;
+            s.matchCap = s.nMatches + s.nMatches / 16 + 1024;
+            if ((rc = enqueueScan(ctx, s))) return rc;
+        }
+        if (!s.tiles.empty()) TLS_CUDA(cudaEventElapsedTime(&s.scanMs, s.evScan0, s.evScan1));
+        else s.scanMs = 0;
+
+        // ---- blocks -------------------------------------------------------------------------------
+        const bool genome = s.mode == TLS_MODE_GENOME, reads = s.mode == TLS_MODE_READS;
+        const bool wantSel = genome && (ctx->cfg.outputs & TLS_OUT_MATCHES) && s.nMatches > 0;
+        uint32_t nBlocks = 0;
+        s.blockCap = std::max<uint32_t>(s.blockCap, 4096);
+        for (;;) {
+            TLS_CUDA(s.dBlocks.reserve(static_cast<size_t>(s.blockCap) * sizeof(DevBlock)));
+            uint8_t *cnt = s.dCounters.as<uint8_t>();
+            TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 4, s.stream));
+            if (reads && n) TLS_CUDA(cudaMemsetAsync(s.dPass.p, 0, n, s.stream));
+            if (n) {
+                TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), n, s.dItemBegin.as<unsigned long long>(), s.stream));
+                BlockParams bp{};
+                bp.matches = s.dMatches.as<DevMatch>();
+                bp.itemBegin = s.dItemBegin.as<unsigned long long>();
+                bp.itemCounts = s.dItemCounts.as<DevItemCounts>();
+                bp.itemLen = s.dItemLen.as<uint32_t>();
+                bp.nItems = n;
+                bp.blocks = s.dBlocks.as<DevBlock>();
+                bp.blockCap = reads ? 0 : s.blockCap;       // read mode only needs the pass flag
+                bp.blockCount = reinterpret_cast<unsigned int *>(cnt + 16);
+                bp.fwdBoundary = s.dBoundaries.as<uint32_t>();
+                bp.revBoundary = s.dBoundaries.as<uint32_t>() + n;
+                bp.pass = s.dPass.as<uint8_t>();
+                bp.cfg = ctx->dcfg;
+                bp.cfg.mode = s.mode;
+                TLS_CUDA(launchTerminal(bp, s.stream));
+                s.launches += 2;
+                if (genome && s.nMatches >= 2) { TLS_CUDA(launchIts(bp, s.nMatches, s.stream)); s.launches++; }
+            }
+            TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 64, cudaMemcpyDeviceToHost, s.stream));
+            TLS_CUDA(cudaStreamSynchronize(s.stream));
+            nBlocks = *reinterpret_cast<unsigned int *>(s.hCounters.as<uint8_t>() + 16);
+            if (reads || nBlocks <= s.blockCap) break;
+            s.blockCap = nBlocks + nBlocks / 8 + 64;
+        }
+        if (reads) nBlocks = 0;
+
+        // ---- -m lists --------------------------------------------------------------------------------
+        unsigned long long selTotals[2] = {0, 0};
+        if (wantSel) {
+            const uint32_t capSel = static_cast<uint32_t>(std::min<uint64_t>(s.nMatches, 0xFFFFFFFFull));
+            TLS_CUDA(s.dSelScratch.reserve(static_cast<size_t>(selectChunks(s.nMatches)) * 8 + 16));
+            TLS_CUDA(s.dSelCan.reserve(static_cast<size_t>(capSel) * sizeof(DevMatch)));
+            TLS_CUDA(s.dSelNon.reserve(static_cast<size_t>(capSel) * sizeof(DevMatch)));
+            uint8_t *cnt = s.dCounters.as<uint8_t>();
+            TLS_CUDA(launchSelect(s.dMatches.as<DevMatch>(), s.nMatches, s.dSelScratch.as<uint32_t>(),
+                                  reinterpret_cast<unsigned long long *>(cnt + 24), s.dSelCan.as<DevMatch>(), capSel,
+                                  s.dSelNon.as<DevMatch>(), capSel, s.stream));
+            s.launches += 3;
+            TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 64, cudaMemcpyDeviceToHost, s.stream));
+            TLS_CUDA(cudaStreamSynchronize(s.stream));
+            std::memcpy(selTotals, s.hCounters.as<uint8_t>() + 24, 16);
+        }
+        TLS_CUDA(cudaEventRecord(s.evAll1, s.stream));
+
+        // ---- copy results back ------------------------------------------------------------------------
+        if (genome && s.nWindows) {
+            TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
+            TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows.p, s.nWindows * 32, cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (!reads && n) {
+            TLS_CUDA(s.hItemCounts.reserve(static_cast<size_t>(n) * sizeof(DevItemCounts)));
+            TLS_CUDA(cudaMemcpyAsync(s.hItemCounts.p, s.dItemCounts.p, static_cast<size_t>(n) * sizeof(DevItemCounts),
+                                     cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (nBlocks) {
+            TLS_CUDA(s.hBlocks.reserve(static_cast<size_t>(nBlocks) * sizeof(DevBlock)));
+            TLS_CUDA(cudaMemcpyAsync(s.hBlocks.p, s.dBlocks.p, static_cast<size_t>(nBlocks) * sizeof(DevBlock),
+                                     cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (reads && n) {
+            TLS_CUDA(s.hPass.reserve(n));
+            TLS_CUDA(cudaMemcpyAsync(s.hPass.p, s.dPass.p, n, cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (selTotals[0]) {
+            TLS_CUDA(s.hSelCan.reserve(selTotals[0] * sizeof(DevMatch)));
+            TLS_CUDA(cudaMemcpyAsync(s.hSelCan.p, s.dSelCan.p, selTotals[0] * sizeof(DevMatch), cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (selTotals[1]) {
+            TLS_CUDA(s.hSelNon.reserve(selTotals[1] * sizeof(DevMatch)));
+            TLS_CUDA(cudaMemcpyAsync(s.hSelNon.p, s.dSelNon.p, selTotals[1] * sizeof(DevMatch), cudaMemcpyDeviceToHost, s.stream));
+        }
+        TLS_CUDA(cudaStreamSynchronize(s.stream));
+        TLS_CUDA(cudaEventElapsedTime(&s.allMs, s.evAll0, s.evAll1));
+
+        // ---- assemble per-item views ----------------------------------------------------------------------
+        s.terminalOff.assign(n + 1, 0); s.itsOff.assign(n + 1, 0); s.canOff.assign(n + 1, 0); s.nonOff.assign(n + 1, 0);
+        s.terminal.clear(); s.its.clear(); s.canonical.clear(); s.noncanonical.clear();
+        s.nCan.assign(n, 0); s.nFwd.assign(n, 0); s.nRev.assign(n, 0);
+        s.pass.assign(n, 0);
+        if (reads && n) std::memcpy(s.pass.data(), s.hPass.p, n);
+        const DevItemCounts *ic = s.hItemCounts.as<DevItemCounts>();
+        if (!reads)
+            for (uint32_t i = 0; i < n; ++i) { s.nCan[i] = ic[i].can; s.nFwd[i] = ic[i].fwd; s.nRev[i] = ic[i].rev; }
+        if (nBlocks) {
+            std::vector<DevBlock> blk(s.hBlocks.as<DevBlock>(), s.hBlocks.as<DevBlock>() + nBlocks);
+            // terminal blocks keep the reference's order (p walk then q walk, each in emission order);
+            // ITS blocks are emitted by independent threads -> order by start
+            std::sort(blk.begin(), blk.end(), [](const DevBlock &a, const DevBlock &b2) {
+                if (a.item != b2.item) return a.item < b2.item;
+                if (a.order != b2.order) return a.order < b2.order;
+                return a.start < b2.start;
+            });
+            auto conv = [&](const DevBlock &d) {
+                tls_block o{};
+                o.start = s.absPos[d.item] + d.start; o.len = d.len; o.counts = d.counts; o.fwd_count = d.fwdCount;
+                o.rev_count = d.counts - d.fwdCount; o.can_count = d.canCount; o.noncan_count = d.counts - d.canCount;
+                o.total_cov = d.totalCov; o.fwd_cov = d.fwdCov; o.can_cov = d.canCov;
+                o.has_valid_or = d.validOr; o.label = d.label;
+                return o;
+            };
+            for (const DevBlock &d : blk) {
+                if (d.kind == 1) { s.its.push_back(conv(d)); s.itsOff[d.item + 1]++; }
+                else { s.terminal.push_back(conv(d)); s.terminalOff[d.item + 1]++; }
+            }
+        }
+        for (uint32_t i = 0; i < n; ++i) { s.terminalOff[i + 1] += s.terminalOff[i]; s.itsOff[i + 1] += s.itsOff[i]; }
+        auto convMatches = [&](const DevMatch *src, uint64_t cnt, std::vector<tls_match> &dst, std::vector<uint64_t> &off,
+                               bool canon) -> int {
+            dst.resize(cnt);
+            uint64_t k = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                off[i] = k;
+                const uint64_t c = canon ? ic[i].can : ic[i].nonCanTerm;
+                if (k + c > cnt) return fail(TLS_ERR_STATE, "internal: match list shorter than per-item counts");
+                for (uint64_t j = 0; j < c; ++j, ++k) {
+                    tls_match m{};
+                    m.pos = s.absPos[i] + src[k].pos; m.len = src[k].len;
+                    m.is_forward = src[k].flags & kMatchFwd ? 1 : 0; m.is_canonical = src[k].flags & kMatchCan ? 1 : 0;
+                    dst[k] = m;
+                }
+            }
+            off[n] = k;
+            return TLS_OK;
+        };
+        if (wantSel) {
+            if ((rc = convMatches(s.hSelCan.as<DevMatch>(), selTotals[0], s.canonical, s.canOff, true))) return rc;
+            if ((rc = convMatches(s.hSelNon.as<DevMatch>(), selTotals[1], s.noncanonical, s.nonOff, false))) return rc;
+        }
+        s.collected = true;
+    }
+    std::memset(res, 0, sizeof *res);
+    res->n_items = n; res->mode = s.mode;
+    res->window_off = s.winOff.data();
+    res->windows = s.hWindows.as<tls_window>();
+    res->terminal_off = s.terminalOff.data(); res->terminal = s.terminal.data();
+    res->its_off = s.itsOff.data(); res->its = s.its.data();
+    res->canonical_off = s.canOff.data(); res->canonical = s.canonical.data();
+    res->noncanonical_off = s.nonOff.data(); res->noncanonical = s.noncanonical.data();
+    res->n_canonical = s.nCan.data(); res->n_fwd = s.nFwd.data(); res->n_rev = s.nRev.data();
+    res->pass = s.pass.data();
+    res->scan_kernel_ms = s.scanMs; res->device_ms = s.allMs;
+    res->n_bases_scanned = s.nBases; res->n_matches = s.nMatches; res->n_kernel_launches = s.launches;
+    return TLS_OK;
+}
+
+int tls_release(tls_ctx *ctx, int ticket) {
+    if (!ctx || ticket < 0 || ticket > 1 || !ctx->slot[ticket].busy) return fail(TLS_ERR_STATE, "bad ticket");
+    ctx->slot[ticket].busy = false;
+    return TLS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,367 @@
+// Kernels that turn the ordered match list into what SegmentData holds besides the matches:
+//   itemOffsetsKernel   exclusive scan of per-item match counts
+//   terminalKernel      Teloscope::getTerminalBlocks (src/teloscope.cpp:29-176), one walk per
+//                       (item, strand), Phase 2 merged on the fly
+//   itsKernel           Teloscope::getInterstitialBlocks (src/teloscope.cpp:179-256): every run
+//                       start walks its run
+//   selectKernels       ordered selection of canonical / terminal non-canonical matches (-m)
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.hpp"
+
+namespace tls {
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan of itemCounts[i].all -> itemBegin[0..n]   (single block, n up to millions)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *counts, uint32_t n,
+                                                          unsigned long long *itemBegin) {
+    __shared__ unsigned long long warpSums[32];
+    __shared__ unsigned long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + tid;
+        const unsigned long long v = i < n ? counts[i].all : 0;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) warpSums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warpSums[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if (lane >= d) wi += u;
+            }
+            warpSums[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned long long excl = carry + warpSums[warp] + incl - v;
+        if (i < n) itemBegin[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) itemBegin[n] = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Terminal blocks
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Run {
+    uint32_t start, end, prev, n, nFwd, nCan, cov, fwdCov, canCov;
+    __device__ void begin(const DevMatch &m) {
+        const uint32_t f = m.flags & kMatchFwd ? 1u : 0u, c = m.flags & kMatchCan ? 1u : 0u;
+        start = m.pos; end = m.pos + m.len; prev = m.pos; n = 1; nFwd = f; nCan = c;
+        cov = m.len; fwdCov = f * m.len; canCov = c * m.len;
+    }
+    __device__ void absorb(const DevMatch &m) {
+        const uint32_t f = m.flags & kMatchFwd ? 1u : 0u, c = m.flags & kMatchCan ? 1u : 0u;
+        ++n; nFwd += f; nCan += c; cov += m.len; fwdCov += f * m.len; canCov += c * m.len; prev = m.pos;
+    }
+};
+
+__device__ void emitBlock(const BlockParams &p, const DevBlock &b) {
+    const unsigned int slot = atomicAdd(p.blockCount, 1u);
+    if (slot < p.blockCap) p.blocks[slot] = b;
+}
+
+}  // namespace
+
+// One thread per (item, arm).  arm 0 = p (forward-strand matches from the start),
+// arm 1 = q (reverse-strand matches from the end).
+__global__ void terminalKernel(const BlockParams p) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= 2u * p.nItems) return;
+    const uint32_t item = gid >> 1;
+    const bool fromStart = (gid & 1u) == 0;
+    const DevConfig &c = p.cfg;
+    const uint32_t n = p.itemLen[item];
+    const bool readMode = c.mode == 2;
+    const uint32_t T = readMode ? 0x7FFFFFFFu : c.terminalLimit;      // UINT32_MAX / 2, src/read-filter.cpp:19
+    uint32_t boundary = fromStart ? 0u : n;
+    const DevItemCounts cnt = p.itemCounts[item];
+    const uint32_t strandCount = fromStart ? cnt.fwd : cnt.rev;
+    uint32_t emitted = 0;
+
+    if (strandCount >= 2) {                                           // src/teloscope.cpp:646,649
+        const long long begin = static_cast<long long>(p.itemBegin[item]);
+        const long long end = static_cast<long long>(p.itemBegin[item + 1]);
+        const uint8_t want = fromStart ? kMatchFwd : 0;
+        auto inZone = [&](uint32_t rel) {                             // :48-52
+            if (n <= T) return true;
+            return fromStart ? rel < T : rel >= n - T;
+        };
+        // Phase 2 state: the block being extended
+        bool haveCur = false;
+        DevBlock cur{};
+        auto finishCur = [&]() {                                      // :132-145
+            if (cur.len >= c.minBlockLen) {
+                cur.item = item;
+                cur.order = (fromStart ? 0u : 0x80000000u) | emitted;
+                cur.label = fromStart ? 'p' : 'q';
+                const uint64_t relEnd = static_cast<uint64_t>(cur.start) + cur.len;
+                const uint64_t left = cur.start, right = relEnd <= n ? n - relEnd : 0;
+                cur.validOr = fromStart ? left <= right : left >= right;
+                emitBlock(p, cur);
+                ++emitted;
+                boundary = fromStart ? cur.start + cur.len : cur.start;
+            }
+        };
+        auto feedSub = [&](const Run &r) {                            // Phase 1 filter :75-92, Phase 2 :147-172
+            const float rhs = __fmul_rn(c.minBlockDensity, __ull2float_rn(static_cast<unsigned long long>(r.end - r.start)));
+            if (!(r.n >= c.minBlockCounts && r.nCan > 0 && __uint2float_rn(r.canCov) >= rhs)) return;
+            DevBlock nx{};
+            nx.start = r.start; nx.len = r.end - r.start; nx.counts = r.n; nx.fwdCount = r.nFwd;
+            nx.canCount = r.nCan; nx.totalCov = r.cov; nx.fwdCov = r.fwdCov; nx.canCov = r.canCov;
+            if (!haveCur) { cur = nx; haveCur = true; return; }
+            const uint64_t gap = fromStart ? static_cast<uint64_t>(nx.start) - (static_cast<uint64_t>(cur.start) + cur.len)
+                                           : static_cast<uint64_t>(cur.start) - (static_cast<uint64_t>(nx.start) + nx.len);
+            if (gap <= c.maxBlockDist) {
+                if (fromStart) cur.len = nx.start + nx.len - cur.start;
+                else { cur.len = cur.start + cur.len - nx.start; cur.start = nx.start; }
+                cur.counts += nx.counts; cur.fwdCount += nx.fwdCount; cur.canCount += nx.canCount;
+                cur.totalCov += nx.totalCov; cur.fwdCov += nx.fwdCov; cur.canCov += nx.canCov;
+            } else {
+                finishCur();
+                cur = nx;
+            }
+        };
+
+        Run run{};
+        bool inRun = false;
+        const long long step = fromStart ? 1 : -1;
+        for (long long i = fromStart ? begin : end - 1; i != (fromStart ? end : begin - 1); i += step) {
+            const DevMatch m = p.matches[i];
+            if ((m.flags & kMatchFwd) != want) continue;
+            if (!inRun) {
+                if (!inZone(m.pos)) break;
+                run.begin(m);
+                inRun = true;
+                continue;
+            }
+            const uint32_t gap = fromStart ? m.pos - run.prev : run.prev - m.pos;
+            if (gap <= c.maxMatchDist) {
+                if (fromStart) run.end = m.pos + m.len; else run.start = m.pos;
+                run.absorb(m);
+            } else {
+                feedSub(run);
+                inRun = false;
+                if (!inZone(m.pos)) break;
+                run.begin(m);
+                inRun = true;
+            }
+        }
+        if (inRun) feedSub(run);
+        if (haveCur) finishCur();
+    }
+    if (fromStart) p.fwdBoundary[item] = boundary; else p.revBoundary[item] = boundary;
+    if (readMode && emitted) p.pass[item] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interstitial blocks.  One thread per 64 consecutive matches; a thread that finds a run start
+// among its matches walks that run to its end.
+// ------------------------------------------------------------------------------------------------
+__global__ void itsKernel(const BlockParams p, unsigned long long nMatches) {
+    const unsigned long long first = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 64ull;
+    if (first >= nMatches) return;
+    const DevConfig &c = p.cfg;
+    // item of the first match: last i with itemBegin[i] <= first
+    uint32_t lo = 0, hi = p.nItems;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.itemBegin[mid] <= first) lo = mid + 1; else hi = mid;
+    }
+    uint32_t item = lo - 1;
+    unsigned long long itemEnd = p.itemBegin[item + 1];
+    const unsigned long long last = first + 64 < nMatches ? first + 64 : nMatches;
+    for (unsigned long long i = first; i < last; ++i) {
+        while (i >= itemEnd) { ++item; itemEnd = p.itemBegin[item + 1]; }
+        const unsigned long long itemBegin = p.itemBegin[item];
+        const uint32_t fwdB = p.fwdBoundary[item], revB = p.revBoundary[item];
+        // src/teloscope.cpp:653: needs fwdBoundary < revBoundary and >= 2 matches in the segment
+        if (!(fwdB < revB) || itemEnd - itemBegin < 2) { i = itemEnd - 1; continue; }
+        const DevMatch m = p.matches[i];
+        if (m.pos < fwdB || m.pos >= revB) continue;
+        bool isStart = true;                                  // first match at/after fwdBoundary starts a run
+        if (i > itemBegin) {
+            const DevMatch prev = p.matches[i - 1];
+            if (prev.pos >= fwdB) isStart = m.pos - prev.pos > c.maxMatchDist;
+        }
+        if (!isStart) continue;
+        Run r{};
+        r.begin(m);
+        for (unsigned long long j = i + 1; j < itemEnd; ++j) {
+            const DevMatch x = p.matches[j];
+            if (x.pos >= revB || x.pos - r.prev > c.maxMatchDist) break;
+            r.end = x.pos + x.len;
+            r.absorb(x);
+        }
+        const uint32_t len = r.end - r.start;
+        // computeBlockLabel, include/teloscope.h:217-222 (float32)
+        const float ratio = __fdiv_rn(__fmul_rn(__uint2float_rn(r.nFwd), 100.0f), __uint2float_rn(r.n));
+        const char label = ratio > 66.6f ? 'p' : (ratio < 33.3f ? 'q' : 'b');
+        if (len >= c.itsMinLen && r.nCan >= 4 && !(label == 'b' && r.nFwd < 2 && (r.n - r.nFwd) < 2)) {
+            DevBlock b{};
+            b.item = item; b.order = 0; b.start = r.start; b.len = len; b.counts = r.n; b.fwdCount = r.nFwd;
+            b.canCount = r.nCan; b.totalCov = r.cov; b.fwdCov = r.fwdCov; b.canCov = r.canCov;
+            b.validOr = 1; b.label = label; b.kind = 1;
+            emitBlock(p, b);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ordered selection for -m: canonical matches, and non-canonical matches flagged terminal.
+// Pass 1 counts per 2048-match chunk, a single block scans the chunk counts, pass 2 writes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelChunk = 2048;
+
+__global__ void __launch_bounds__(256) selectCountKernel(const DevMatch *m, unsigned long long n, uint32_t *chunkCounts) {
+    const unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * kSelChunk;
+    uint32_t nc = 0, nn = 0;
+    for (int i = threadIdx.x; i < kSelChunk; i += 256) {
+        const unsigned long long k = base + i;
+        if (k < n) {
+            const uint8_t f = m[k].flags;
+            nc += (f & kMatchCan) != 0;
+            nn += (f & (kMatchCan | kMatchTerm)) == kMatchTerm;
+        }
+    }
+    nc = __reduce_add_sync(0xFFFFFFFFu, nc);
+    nn = __reduce_add_sync(0xFFFFFFFFu, nn);
+    __shared__ uint32_t s[2];
+    if (threadIdx.x < 2) s[threadIdx.x] = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s[0], nc); atomicAdd(&s[1], nn); }
+    __syncthreads();
+    if (threadIdx.x < 2) chunkCounts[2 * blockIdx.x + threadIdx.x] = s[threadIdx.x];
+}
+
+// in place: chunkCounts[2*i+k] -> exclusive prefix; totals[k] = sum
+__global__ void __launch_bounds__(1024) selectScanKernel(uint32_t *chunkCounts, uint32_t nChunks, unsigned long long *totals) {
+    __shared__ unsigned long long warpSums[2][32];
+    __shared__ unsigned long long carry[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 2) carry[tid] = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nChunks; base += 1024) {
+        const uint32_t i = base + tid;
+        unsigned long long v[2], incl[2];
+        for (int k = 0; k < 2; ++k) {
+            v[k] = i < nChunks ? chunkCounts[2 * i + k] : 0;
+            incl[k] = v[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl[k], d);
+                if (lane >= d) incl[k] += u;
+            }
+            if (lane == 31) warpSums[k][warp] = incl[k];
+        }
+        __syncthreads();
+        if (warp < 2) {
+            unsigned long long w = warpSums[warp][lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if (lane >= d) wi += u;
+            }
+            warpSums[warp][lane] = wi - w;
+        }
+        __syncthreads();
+        unsigned long long excl[2];
+        for (int k = 0; k < 2; ++k) {
+            excl[k] = carry[k] + warpSums[k][warp] + incl[k] - v[k];
+            // prefix fits 32 bits only if the list does; keep 32-bit chunk offsets relative to 0
+            if (i < nChunks) chunkCounts[2 * i + k] = static_cast<uint32_t>(excl[k]);
+        }
+        __syncthreads();
+        if (tid == 1023) { carry[0] = excl[0] + v[0]; carry[1] = excl[1] + v[1]; }
+        __syncthreads();
+    }
+    if (tid < 2) totals[tid] = carry[tid];
+}
+
+__global__ void __launch_bounds__(32) selectWriteKernel(const DevMatch *m, unsigned long long n, const uint32_t *chunkOffsets,
+                                                         DevMatch *outCan, uint32_t capCan, DevMatch *outNon, uint32_t capNon) {
+    // one warp walks the chunk in order so the output order equals the input order
+    const unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * kSelChunk;
+    const int lane = threadIdx.x;
+    uint32_t oc = chunkOffsets[2 * blockIdx.x], on = chunkOffsets[2 * blockIdx.x + 1];
+    for (int i = 0; i < kSelChunk; i += 32) {
+        const unsigned long long k = base + i + lane;
+        DevMatch x{};
+        bool isC = false, isN = false;
+        if (k < n) {
+            x = m[k];
+            isC = (x.flags & kMatchCan) != 0;
+            isN = (x.flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
+        }
+        const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
+        const uint32_t below = (1u << lane) - 1u;
+        if (isC) { const uint32_t o = oc + __popc(bc & below); if (o < capCan) outCan[o] = x; }
+        if (isN) { const uint32_t o = on + __popc(bn & below); if (o < capNon) outNon[o] = x; }
+        oc += __popc(bc);
+        on += __popc(bn);
+    }
+}
+
+cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned long long *itemBegin, cudaStream_t s) {
+    itemOffsetsKernel<<<1, 1024, 0, s>>>(counts, n, itemBegin);
+    return cudaGetLastError();
+}
+cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s) {
+    const uint32_t threads = 2u * p.nItems;
+    if (threads == 0) return cudaSuccess;
+    terminalKernel<<<(threads + 127) / 128, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launchIts(const BlockParams &p, unsigned long long nMatches, cudaStream_t s) {
+    if (nMatches == 0) return cudaSuccess;
+    const unsigned long long threads = (nMatches + 63) / 64;
+    itsKernel<<<static_cast<unsigned int>((threads + 127) / 128), 128, 0, s>>>(p, nMatches);
+    return cudaGetLastError();
+}
+
+uint32_t selectChunks(unsigned long long n) { return static_cast<uint32_t>((n + kSelChunk - 1) / kSelChunk); }
+
+cudaError_t launchSelect(const DevMatch *m, unsigned long long n, uint32_t *chunkScratch, unsigned long long *totals,
+                         DevMatch *outCan, uint32_t capCan, DevMatch *outNon, uint32_t capNon, cudaStream_t s) {
+    const uint32_t chunks = selectChunks(n);
+    if (chunks == 0) return cudaSuccess;
+    selectCountKernel<<<chunks, 256, 0, s>>>(m, n, chunkScratch);
+    selectScanKernel<<<1, 1024, 0, s>>>(chunkScratch, chunks, totals);
+    selectWriteKernel<<<chunks, 32, 0, s>>>(m, n, chunkScratch, outCan, capCan, outNon, capNon);
+    return cudaGetLastError();
+}
+
+// Read mode with a device-resident batch: drop one trailing '\r' per read (src/read-filter.cpp:38-40).
+__global__ void trimCrKernel(const uint8_t *seq, DevRegion *regions, uint32_t nRegions, uint32_t *itemLen) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nRegions) return;
+    DevRegion reg = regions[r];
+    if (reg.len && seq[reg.bufStart + reg.len - 1] == '\r') {
+        regions[r].len = reg.len - 1;
+        regions[r].itemLen = reg.itemLen - 1;
+        itemLen[reg.item] = reg.itemLen - 1;
+    }
+}
+
+cudaError_t launchTrimCr(const uint8_t *seq, DevRegion *regions, uint32_t nRegions, uint32_t *itemLen, cudaStream_t s) {
+    if (nRegions == 0) return cudaSuccess;
+    trimCrKernel<<<(nRegions + 255) / 256, 256, 0, s>>>(seq, regions, nRegions, itemLen);
+    return cudaGetLastError();
+}
+
+}  // namespace tls

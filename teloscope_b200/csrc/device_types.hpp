@@ -1,0 +1,120 @@
+// Plain structs shared between the host side of the library (api.cu) and the kernels.
+#pragma once
+
+#include <cstdint>
+
+namespace tls {
+
+// ---- geometry of the fused scan kernel ------------------------------------------------------
+constexpr int kScanThreads = 512;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kSpanBytes = 48;                    // bases per lane per row (3 x 16-byte chunks)
+constexpr int kRowBytes = 32 * kSpanBytes;        // 1536
+constexpr int kRowsPerWarp = 2;
+constexpr int kTileRows = kScanWarps * kRowsPerWarp;          // 32
+constexpr int kTileSmemBytes = kTileRows * kRowBytes;         // 49152
+constexpr int kTileHalo = 64;                     // bytes staged after the tile for k-mer tails
+constexpr int kTileMaxLen = kTileSmemBytes - 16;  // leaves room for the alignment skew
+constexpr int kQueueCap = 544;                    // per-warp candidate queue (u16 entries)
+constexpr int kRegionCache = 32;                  // regions of a tile kept in shared memory
+constexpr int kWindowSlots = 128;                 // per-tile window counter slots in shared memory
+constexpr int kFlagTabBytes = 24576;              // direct stage-2 tables (sum 4^len, len<=7)
+
+// A maximal stretch of one item inside which matches must lie entirely
+// (genome mode: the whole contig; tips mode: [0,T) and [n-T,n); reads: the whole read).
+struct DevRegion {
+    uint64_t bufStart;     // offset of the region's first base in the sequence buffer
+    uint32_t len;
+    uint32_t item;
+    uint32_t relStart;     // position of the region's first base inside the item
+    uint32_t itemLen;
+    uint32_t winBase;      // global index of the item's first window (genome mode)
+    uint32_t pad;
+};
+
+struct DevTile {
+    uint64_t bufStart;     // first base of the tile
+    uint32_t len;          // <= kTileMaxLen
+    uint32_t firstRegion;  // first region that overlaps the tile
+};
+
+struct DevMatch {          // 8 bytes, ordered by (item, pos, len)
+    uint32_t pos;          // relative to the item start
+    uint16_t len;
+    uint8_t flags;         // bit0 forward, bit1 canonical, bit2 terminal (src/teloscope.cpp:451-459)
+    uint8_t pad;
+};
+enum : uint8_t { kMatchFwd = 1, kMatchCan = 2, kMatchTerm = 4 };
+
+struct DevItemCounts {     // per item, filled by the scan kernel
+    uint32_t all, fwd, rev, can, nonCanTerm, pad[3];
+};
+
+struct DevBlock {          // 48 bytes
+    uint32_t item;
+    uint32_t order;        // terminal: bit31 = q-arm walk, low bits = emission order; ITS: 0
+    uint32_t start;        // relative to the item start
+    uint32_t len, counts, fwdCount, canCount, totalCov, fwdCov, canCov;
+    uint8_t validOr;
+    char label;
+    uint16_t kind;         // 0 terminal, 1 interstitial
+    uint32_t pad2;
+};
+
+struct DevLenClass {
+    uint32_t len;
+    uint32_t direct;       // 1: flag table in shared memory at flagOffset
+    uint32_t flagOffset;
+    uint32_t sortedBegin, sortedCount;
+};
+
+struct DevConfig {
+    uint32_t nClasses, minLen, maxLen, npos;
+    DevLenClass cls[8];
+    uint32_t flagTabBytes;
+    uint32_t mode;                 // tls_mode
+    uint32_t windowSize, step, terminalLimit;
+    uint32_t maxMatchDist, minBlockLen, maxBlockDist, minBlockCounts, itsMinLen;
+    float minBlockDensity;
+    uint32_t countAcgt;
+    // rel / windowSize by multiply-high (Granlund-Montgomery, exact for every u32 rel):
+    //   t = umulhi(winMagic, rel);  q = (t + ((rel - t) >> winSh1)) >> winSh2
+    uint32_t winMagic, winSh1, winSh2;
+};
+
+struct ScanParams {
+    const uint8_t *seq;            // device sequence buffer
+    const DevTile *tiles;
+    const DevRegion *regions;
+    uint32_t nTiles, nRegions;
+    const uint8_t *index8;         // 65536-byte stage-1 table
+    const uint8_t *flagTabs;       // direct stage-2 tables
+    const uint64_t *sortedKeys;    // long patterns (len > 7)
+    const uint8_t *sortedFlags;
+    DevMatch *matches;             // ordered output
+    uint64_t matchCap;
+    DevMatch *scratch;             // per-CTA staging, scratchPerWarp records per warp
+    uint32_t scratchPerWarp;
+    unsigned long long *tileStatus;   // decoupled look-back words, zeroed per launch
+    unsigned int *tileCounter;        // dynamic tile scheduler, zeroed per launch
+    unsigned long long *totalMatches; // written by the last tile
+    uint32_t *windows;             // [nWindows][8], zeroed per launch
+    DevItemCounts *itemCounts;     // zeroed per launch
+    DevConfig cfg;
+};
+
+struct BlockParams {
+    const DevMatch *matches;
+    const unsigned long long *itemBegin;   // nItems + 1
+    const DevItemCounts *itemCounts;
+    const uint32_t *itemLen;               // per item (after the read-mode '\r' trim)
+    uint32_t nItems;
+    DevBlock *blocks;                      // output, unordered; the host sorts by (item, order)
+    uint32_t blockCap;
+    unsigned int *blockCount;              // keeps counting past the capacity
+    uint32_t *fwdBoundary, *revBoundary;   // per item, relative to the item start
+    uint8_t *pass;                         // read mode: per item, 1 = some terminal block
+    DevConfig cfg;
+};
+
+}  // namespace tls

@@ -1,0 +1,23 @@
+// Launchers of the CUDA kernels (scan_kernel.cu, block_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "device_types.hpp"
+
+namespace tls {
+
+size_t scanSmemBytes();
+cudaError_t launchScan(const ScanParams &p, int grid, cudaStream_t stream);
+
+cudaError_t launchTrimCr(const uint8_t *seq, DevRegion *regions, uint32_t nRegions, uint32_t *itemLen, cudaStream_t s);
+cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned long long *itemBegin, cudaStream_t s);
+cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s);
+cudaError_t launchIts(const BlockParams &p, unsigned long long nMatches, cudaStream_t s);
+
+uint32_t selectChunks(unsigned long long nMatches);
+// chunkScratch: 2 * selectChunks(n) u32; totals: 2 u64 (canonical, terminal non-canonical)
+cudaError_t launchSelect(const DevMatch *m, unsigned long long n, uint32_t *chunkScratch, unsigned long long *totals,
+                         DevMatch *outCan, uint32_t capCan, DevMatch *outNon, uint32_t capNon, cudaStream_t s);
+
+}  // namespace tls

@@ -105,8 +105,16 @@ def lib():
         L.orc_read_matches.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
         L.orc_scan_many.restype = C.c_uint64
         L.orc_scan_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_window_floats.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         _lib = L
     return _lib
+
+
+def window_floats(acgt, size: int) -> tuple[float, float]:
+    a = (C.c_uint32 * 4)(*[int(x) for x in acgt])
+    gc, ent = C.c_float(), C.c_float()
+    lib().orc_window_floats(a, int(size), C.byref(gc), C.byref(ent))
+    return gc.value, ent.value
 
 
 def expand_patterns(raw: list[str], x: int, canonical_fwd: str) -> list[tuple[str, bool]]:

@@ -1,0 +1,93 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and against the files the
+unmodified reference binary wrote.  Bit-exact: everything here is integer / byte / index work;
+the float window tracks are derived from the integer counters with the reference's expressions
+and compared as the text the reference prints."""
+import numpy as np
+import pytest
+
+import golden_cmp
+import oracle_lib as ol
+import product_adapter as pa
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import teloscope_b200
+    if teloscope_b200.load_library().tls_device_count() < 1:
+        pytest.fail("no sm_100 device visible: GPU tests must run on a B200")
+    return teloscope_b200
+
+
+def _same_blocks(a, b):
+    assert len(a) == len(b)
+    for name in ("start", "len", "counts", "fwd_count", "rev_count", "can_count", "noncan_count",
+                 "total_cov", "fwd_cov", "can_cov", "valid_or", "label"):
+        assert np.array_equal(a[name], b[name]), name
+
+
+def test_golden_fasta_cases(tb, golden):
+    """Every FASTA case with step == window: product == reference files, and product == oracle
+    record by record (block order included)."""
+    cases, fixtures = golden
+    done = 0
+    for c in cases:
+        if c["kind"] != "fasta":
+            continue
+        cfg, flags = ol.config_from_args(c["args"])
+        if cfg.step != cfg.window_size:
+            continue
+        data = fixtures[c["fixture"]].tobytes()
+        paths = ol.parse_fasta(data)
+        tips = not flags["genome"]
+        scanner = tb.Scanner(pa.scan_config(cfg, flags))
+        try:
+            prod = pa.BatchedProduct(scanner, cfg, paths, tips)
+            golden_cmp.check_fasta_case(c, data, prod.scan_fn, cfg, flags)
+            # record-level comparison with the oracle
+            orc = ol.Oracle(cfg)
+            i = 0
+            for _, comps, _ in paths:
+                for kind, a, payload in comps:
+                    if kind != "seg":
+                        continue
+                    want = orc.scan_segment(payload.upper(), a, tips)
+                    got = prod.item_as_oracle(i, a)
+                    _same_blocks(got["terminal"], want["terminal"])
+                    _same_blocks(got["its"], want["its"])
+                    if not tips:
+                        assert got["n_canonical"] == len(want["canonical"])
+                        for k in ("canonical", "noncanonical"):
+                            assert np.array_equal(got[k][["pos", "len", "fwd", "can"]], want[k][["pos", "len", "fwd", "can"]]), k
+                        w1, w2 = got["windows"], want["windows"]
+                        assert len(w1) == len(w2)
+                        for k in ("start", "size", "can_cov", "noncan_cov", "fwd_cov", "rev_cov"):
+                            assert np.array_equal(w1[k], w2[k]), k
+                        if cfg.count_acgt:
+                            assert np.array_equal(w1["acgt"], w2["acgt"])
+                    assert prod.res.n_fwd[i] == len(want["fwd"]) and prod.res.n_rev[i] == len(want["rev"])
+                    i += 1
+        finally:
+            scanner.close()
+        done += 1
+    assert done >= 170
+
+
+def test_golden_fastq_cases(tb, golden):
+    cases, fixtures = golden
+    done = 0
+    for c in cases:
+        if c["kind"] != "fastq":
+            continue
+        cfg, flags = ol.config_from_args(c["args"], read_mode=True)
+        reads = ol.parse_fastq(fixtures[c["fixture"]].tobytes())
+        scanner = tb.Scanner(pa.scan_config(cfg))
+        try:
+            res = scanner.scan_batch([s for _, s in reads], None, tb.MODE_READS)
+            kept = [name for (name, _), ok in zip(reads, res.passed) if ok]
+            assert kept == c["kept"], (c["fixture"], c["args"])
+        finally:
+            scanner.close()
+        done += 1
+    assert done >= 15

@@ -85,9 +85,10 @@ struct Slot {
     std::vector<DevTile> tiles;
     const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
     HostBuf hSeq, hMeta;                      // pinned staging
-    DevBuf dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dStatus,
-        dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
-    // device counters block: [0] tileCounter(u32) [8] totalMatches(u64) [16] blockCount(u32) [24] selTotals(2 x u64)
+    DevBuf dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotCounts,
+        dSlotOv, dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
+    uint32_t ovCap = 0;
+    // device counters block: [0] ovCursor(u32) [16] blockCount(u32) [24] selTotals(2 x u64)
     HostBuf hCounters, hWindows, hItemCounts, hBlocks, hPass, hSelCan, hSelNon;
     uint64_t matchCap = 0;
     uint32_t blockCap = 0;
@@ -114,8 +115,8 @@ struct tls_ctx {
     std::vector<Pattern> patterns;
     ScanTables tables;
     DevConfig dcfg{};
-    DevBuf dIndex, dFlags, dKeys, dKeyFlags, dScratch;
-    uint32_t scratchPerWarp = 0;
+    DevBuf dIndex, dFlags, dKeys, dKeyFlags;
+    uint32_t slotCap = 0, ovChunk = 0;
     Slot slot[2];
 };
 
@@ -282,8 +283,17 @@ int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
     }
     if ((rc = upload(ctx->dKeys, t.sortedKeys.data(), t.sortedKeys.size() * 8))) return rc;
     if ((rc = upload(ctx->dKeyFlags, t.sortedFlags.data(), t.sortedFlags.size()))) return rc;
-    ctx->scratchPerWarp = static_cast<uint32_t>(kRowsPerWarp * kRowBytes) * ctx->dcfg.nClasses;
-    TLS_CUDA(ctx->dScratch.reserve(static_cast<size_t>(ctx->smCount) * kScanWarps * ctx->scratchPerWarp * sizeof(DevMatch)));
+    {
+        // expected matches per (tile, warp) on random sequence = bases per warp * pattern density;
+        // slots hold twice that (power of two), denser stretches spill into overflow chunks
+        double density = 0;
+        for (const LenClass &c : t.classes) density += static_cast<double>(c.sortedCount) / static_cast<double>(1ull << (2 * std::min<uint32_t>(c.len, 31)));
+        const uint32_t perWarp = static_cast<uint32_t>(kRowsPerWarp * kRowBytes);
+        ctx->ovChunk = perWarp * ctx->dcfg.nClasses;
+        uint32_t want = static_cast<uint32_t>(2.0 * perWarp * density) + 64, cap = 64;
+        while (cap < want) cap <<= 1;
+        ctx->slotCap = std::min(cap, ctx->ovChunk);
+    }
     for (Slot &s : ctx->slot) {
         TLS_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         TLS_CUDA(cudaEventCreate(&s.evScan0)); TLS_CUDA(cudaEventCreate(&s.evScan1));
@@ -301,8 +311,8 @@ void tls_destroy(tls_ctx *ctx) {
     for (Slot &s : ctx->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         for (DevBuf *b : {&s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
-                          &s.dMatches, &s.dStatus, &s.dCounters, &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch,
-                          &s.dSelCan, &s.dSelNon})
+                          &s.dMatches, &s.dSlots, &s.dSlotCounts, &s.dSlotOv, &s.dOvArena, &s.dTileBase, &s.dCounters,
+                          &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch, &s.dSelCan, &s.dSelNon})
             b->release();
         for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
                            &s.hSelCan, &s.hSelNon})
@@ -313,7 +323,7 @@ void tls_destroy(tls_ctx *ctx) {
         if (s.evAll1) cudaEventDestroy(s.evAll1);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    for (DevBuf *b : {&ctx->dIndex, &ctx->dFlags, &ctx->dKeys, &ctx->dKeyFlags, &ctx->dScratch}) b->release();
+    for (DevBuf *b : {&ctx->dIndex, &ctx->dFlags, &ctx->dKeys, &ctx->dKeyFlags}) b->release();
     delete ctx;
 }
 
@@ -321,12 +331,32 @@ void tls_destroy(tls_ctx *ctx) {
 
 namespace {
 
-// Enqueue the fused scan for the slot (memsets + kernel + copy of the counters).
+GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
+    GatherParams g{};
+    g.tiles = s.dTiles.as<DevTile>(); g.regions = s.dRegions.as<DevRegion>();
+    g.nRegions = static_cast<uint32_t>(s.regions.size());
+    g.windows = s.dWindows.as<uint32_t>(); g.itemCounts = s.dItemCounts.as<DevItemCounts>();
+    g.cfg = ctx->dcfg; g.cfg.mode = s.mode;
+    g.slots = s.dSlots.as<DevMatch>(); g.slotCap = ctx->slotCap;
+    g.slotCounts = s.dSlotCounts.as<uint32_t>(); g.slotOv = s.dSlotOv.as<uint32_t>();
+    g.ovArena = s.dOvArena.as<DevMatch>(); g.ovCap = s.ovCap;
+    g.nTiles = static_cast<uint32_t>(s.tiles.size());
+    g.tileBase = s.dTileBase.as<unsigned long long>();
+    g.matches = s.dMatches.as<DevMatch>(); g.matchCap = s.matchCap;
+    return g;
+}
+
+// Enqueue the fused scan for the slot: memsets, kernel, per-tile prefix, copy of the counters.
 int enqueueScan(tls_ctx *ctx, Slot &s) {
     const uint32_t nTiles = static_cast<uint32_t>(s.tiles.size());
-    TLS_CUDA(s.dMatches.reserve(std::max<uint64_t>(s.matchCap, 1) * sizeof(DevMatch)));
+    const size_t nSlots = static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * kScanWarps;
+    TLS_CUDA(s.dSlots.reserve(nSlots * ctx->slotCap * sizeof(DevMatch)));
+    TLS_CUDA(s.dSlotCounts.reserve(nSlots * 4));
+    TLS_CUDA(s.dSlotOv.reserve(nSlots * 4));
+    TLS_CUDA(s.dTileBase.reserve((static_cast<size_t>(nTiles) + 1) * 8));
+    s.ovCap = std::max<uint32_t>(s.ovCap, 256u * ctx->ovChunk);
+    TLS_CUDA(s.dOvArena.reserve(static_cast<size_t>(s.ovCap) * sizeof(DevMatch)));
     TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 64, s.stream));
-    TLS_CUDA(cudaMemsetAsync(s.dStatus.p, 0, std::max<size_t>(nTiles, 1) * 8, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dItemCounts.p, 0, std::max<size_t>(s.nItems, 1) * sizeof(DevItemCounts), s.stream));
     if (s.nWindows) TLS_CUDA(cudaMemsetAsync(s.dWindows.p, 0, s.nWindows * 32, s.stream));
     s.launches = 0;
@@ -341,14 +371,10 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         p.flagTabs = ctx->dFlags.as<uint8_t>();
         p.sortedKeys = ctx->dKeys.as<uint64_t>();
         p.sortedFlags = ctx->dKeyFlags.as<uint8_t>();
-        p.matches = s.dMatches.as<DevMatch>();
-        p.matchCap = s.matchCap;
-        p.scratch = ctx->dScratch.as<DevMatch>();
-        p.scratchPerWarp = ctx->scratchPerWarp;
-        uint8_t *cnt = s.dCounters.as<uint8_t>();
-        p.tileCounter = reinterpret_cast<unsigned int *>(cnt);
-        p.totalMatches = reinterpret_cast<unsigned long long *>(cnt + 8);
-        p.tileStatus = s.dStatus.as<unsigned long long>();
+        p.slots = s.dSlots.as<DevMatch>(); p.slotCap = ctx->slotCap;
+        p.slotCounts = s.dSlotCounts.as<uint32_t>(); p.slotOv = s.dSlotOv.as<uint32_t>();
+        p.ovArena = s.dOvArena.as<DevMatch>(); p.ovCap = s.ovCap; p.ovChunk = ctx->ovChunk;
+        p.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
         p.windows = s.dWindows.as<uint32_t>();
         p.itemCounts = s.dItemCounts.as<DevItemCounts>();
         p.cfg = ctx->dcfg;
@@ -357,9 +383,15 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         TLS_CUDA(cudaEventRecord(s.evScan0, s.stream));
         TLS_CUDA(launchScan(p, std::min<int>(ctx->smCount, static_cast<int>(nTiles)), s.stream));
         TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
-        s.launches++;
+        TLS_CUDA(launchTileScan(gatherParams(ctx, s), s.stream));
+        s.launches += 2;
+    } else {
+        TLS_CUDA(cudaMemsetAsync(s.dTileBase.p, 0, 8, s.stream));
     }
-    TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 64, cudaMemcpyDeviceToHost, s.stream));
+    // counters: [0] ovCursor; total matches = tileBase[nTiles]
+    TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 8, cudaMemcpyDeviceToHost, s.stream));
+    TLS_CUDA(cudaMemcpyAsync(s.hCounters.as<uint8_t>() + 8, s.dTileBase.as<unsigned long long>() + nTiles, 8,
+                             cudaMemcpyDeviceToHost, s.stream));
     return TLS_OK;
 }
 
@@ -473,13 +505,11 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     if (bRegions) TLS_CUDA(cudaMemcpyAsync(s.dRegions.p, hm, bRegions, cudaMemcpyHostToDevice, s.stream));
     if (bTiles) TLS_CUDA(cudaMemcpyAsync(s.dTiles.p, hm + bRegions, bTiles, cudaMemcpyHostToDevice, s.stream));
     if (bLen) TLS_CUDA(cudaMemcpyAsync(s.dItemLen.p, hm + bRegions + bTiles, bLen, cudaMemcpyHostToDevice, s.stream));
-    TLS_CUDA(s.dStatus.reserve(std::max<size_t>(s.tiles.size(), 1) * 8));
     TLS_CUDA(s.dItemCounts.reserve(std::max<size_t>(n, 1) * sizeof(DevItemCounts)));
     TLS_CUDA(s.dItemBegin.reserve((static_cast<size_t>(n) + 1) * 8));
     TLS_CUDA(s.dWindows.reserve(std::max<uint64_t>(nWin, 1) * 32));
     TLS_CUDA(s.dBoundaries.reserve(std::max<size_t>(n, 1) * 8));
     TLS_CUDA(s.dPass.reserve(std::max<size_t>(n, 1)));
-    s.matchCap = std::max<uint64_t>(s.matchCap, s.nBases / 8 + 65536);
 
     TLS_CUDA(cudaEventRecord(s.evAll0, s.stream));
     if (b->mode == TLS_MODE_READS && b->seq_on_device)
@@ -499,14 +529,19 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
     const uint32_t n = s.nItems;
     int rc;
     if (!s.collected) {
-        // ---- wait for the scan; grow the match list and rerun if it overflowed ---------------------
+        // ---- wait for the scan; grow the overflow arena and rerun if it ran out --------------------
         for (;;) {
             TLS_CUDA(cudaStreamSynchronize(s.stream));
+            const uint32_t ovUsed = *s.hCounters.as<uint32_t>();
             s.nMatches = *reinterpret_cast<unsigned long long *>(s.hCounters.as<uint8_t>() + 8);
-            if (s.nMatches <= s.matchCap) break;
-            s.matchCap = s.nMatches + s.nMatches / 16 + 1024;
+            if (ovUsed <= s.ovCap) break;
+            s.ovCap = ovUsed + ovUsed / 4;
             if ((rc = enqueueScan(ctx, s))) return rc;
         }
+        // ---- slots -> one ordered list ------------------------------------------------------------------
+        s.matchCap = std::max<uint64_t>(s.matchCap, s.nMatches);
+        TLS_CUDA(s.dMatches.reserve(std::max<uint64_t>(s.matchCap, 1) * sizeof(DevMatch)));
+        if (!s.tiles.empty()) { TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream)); s.launches++; }
         if (!s.tiles.empty()) TLS_CUDA(cudaEventElapsedTime(&s.scanMs, s.evScan0, s.evScan1));
         else s.scanMs = 0;
 

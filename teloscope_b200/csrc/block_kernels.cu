@@ -9,6 +9,7 @@
 
 #include <cstdint>
 
+#include "device_common.cuh"
 #include "kernels.hpp"
 
 namespace tls {
@@ -51,6 +52,180 @@ __global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *c
         __syncthreads();
     }
     if (tid == 0) itemBegin[n] = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Slot arena -> one ordered match list.
+//   tileScanKernel: per-tile totals (sum of the 16 warp slots) and their exclusive prefix
+//   gatherKernel:   one block per tile copies its slots (and overflow chunks) to the list
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) tileScanKernel(const GatherParams g) {
+    __shared__ unsigned long long warpSums[32];
+    __shared__ unsigned long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < g.nTiles; base += 1024) {
+        const uint32_t i = base + tid;
+        unsigned long long v = 0;
+        if (i < g.nTiles) {
+            const uint4 *c = reinterpret_cast<const uint4 *>(g.slotCounts + static_cast<size_t>(i) * kScanWarps);
+#pragma unroll
+            for (int k = 0; k < kScanWarps / 4; ++k) { const uint4 x = c[k]; v += x.x; v += x.y; v += x.z; v += x.w; }
+        }
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) warpSums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warpSums[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if (lane >= d) wi += u;
+            }
+            warpSums[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned long long excl = carry + warpSums[warp] + incl - v;
+        if (i < g.nTiles) g.tileBase[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) g.tileBase[g.nTiles] = carry;
+}
+
+// One block per tile.  Thread k walks the k-th contiguous share of the tile's records in genome
+// order: copies them to the ordered list (adding the terminal flag) and accumulates, while the
+// key stays the same, per-item counters and per-window covered bp; shared atomics on key change,
+// one flush to global memory at the end.
+constexpr int kGatherThreads = 128;
+constexpr int kGatherSlots = 128;
+
+__global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParams g) {
+    const uint32_t tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ uint32_t sOff[kScanWarps + 1];
+    __shared__ DevRegion sRegion[kRegionCache];
+    __shared__ uint32_t sRegCnt[kRegionCache][5];
+    __shared__ uint32_t sWin[kGatherSlots][4];
+    __shared__ uint32_t sFirstWin, sNReg;
+    const DevConfig &c = g.cfg;
+    const DevTile dt = g.tiles[tile];
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int w = 0; w < kScanWarps; ++w) { sOff[w] = acc; acc += g.slotCounts[static_cast<size_t>(tile) * kScanWarps + w]; }
+        sOff[kScanWarps] = acc;
+    }
+    if (tid < 32) {
+        const uint64_t tileEnd = dt.bufStart + dt.len;
+        const uint32_t idx = min(dt.firstRegion + static_cast<uint32_t>(tid), g.nRegions - 1);
+        const DevRegion r = g.regions[idx];
+        const bool in = dt.firstRegion + tid < g.nRegions && r.bufStart < tileEnd;
+        const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, in));
+        if (in) sRegion[tid] = r;
+        if (tid == 0) {
+            sNReg = n;
+            const uint64_t s = dt.bufStart > r.bufStart ? dt.bufStart : r.bufStart;
+            sFirstWin = (c.mode == 0 && n > 0) ? r.winBase + divWindow(c, r.relStart + static_cast<uint32_t>(s - r.bufStart)) : 0;
+        }
+    }
+    for (int i = tid; i < kRegionCache * 5; i += kGatherThreads) (&sRegCnt[0][0])[i] = 0;
+    for (int i = tid; i < kGatherSlots * 4; i += kGatherThreads) (&sWin[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t total = sOff[kScanWarps];
+    if (total == 0) return;
+    const unsigned long long base = g.tileBase[tile];
+    const uint32_t firstWin = sFirstWin;
+    const uint32_t share = (total + kGatherThreads - 1) / kGatherThreads;
+    uint32_t i = tid * share;
+    const uint32_t end = min(total, i + share);
+
+    // running accumulators
+    uint32_t curReg = 0xFFFFFFFFu, nAll = 0, nFwd = 0, nCan = 0, nNct = 0;
+    uint32_t curWin = 0xFFFFFFFFu, canCov = 0, nonCov = 0, fwdCov = 0, revCov = 0;
+    auto flushReg = [&]() {
+        if (curReg != 0xFFFFFFFFu && nAll) {
+            uint32_t *r = sRegCnt[curReg];
+            atomicAdd(r + 0, nAll); atomicAdd(r + 1, nFwd); atomicAdd(r + 2, nAll - nFwd);
+            if (nCan) atomicAdd(r + 3, nCan);
+            if (nNct) atomicAdd(r + 4, nNct);
+        }
+        nAll = nFwd = nCan = nNct = 0;
+    };
+    auto flushWin = [&]() {
+        if (curWin != 0xFFFFFFFFu) {
+            const uint32_t s = curWin - firstWin;
+            uint32_t *w = s < kGatherSlots ? sWin[s] : g.windows + static_cast<size_t>(curWin) * 8 + 4;
+            if (canCov) atomicAdd(w + 0, canCov);
+            if (nonCov) atomicAdd(w + 1, nonCov);
+            if (fwdCov) atomicAdd(w + 2, fwdCov);
+            if (revCov) atomicAdd(w + 3, revCov);
+        }
+        canCov = nonCov = fwdCov = revCov = 0;
+    };
+
+    if (i < end) {
+        int w = 0;
+        while (sOff[w + 1] <= i) ++w;
+        for (; i < end; ++i) {
+            while (sOff[w + 1] <= i) ++w;
+            const size_t slotIdx = static_cast<size_t>(tile) * kScanWarps + w;
+            const uint32_t k = i - sOff[w];
+            DevMatch m;
+            if (k < g.slotCap) m = g.slots[slotIdx * g.slotCap + k];
+            else {
+                const unsigned long long o = static_cast<unsigned long long>(g.slotOv[slotIdx]) + (k - g.slotCap);
+                if (o >= g.ovCap) continue;                     // overflow arena exhausted: the host reruns
+                m = g.ovArena[o];
+            }
+            if (m.region != kRegionAccounted) {
+                const DevRegion &r = sRegion[m.region];
+                const bool fwd = m.flags & kMatchFwd, can = m.flags & kMatchCan;
+                bool term = false;
+                if (c.mode == 0) {
+                    const uint32_t winIdx = divWindow(c, m.pos);
+                    term = isTerminalMatch(c, m.pos, winIdx, r.itemLen);
+                    const uint32_t win = r.winBase + winIdx;
+                    if (win != curWin) { flushWin(); curWin = win; }
+                    if (can) canCov += m.len; else nonCov += m.len;
+                    if (fwd) fwdCov += m.len; else revCov += m.len;
+                }
+                if (m.region != curReg) { flushReg(); curReg = m.region; }
+                ++nAll; nFwd += fwd; nCan += can; nNct += (!can && term);
+                if (term) m.flags |= kMatchTerm;
+            }
+            m.region = 0;
+            const unsigned long long o = base + i;
+            if (o < g.matchCap) g.matches[o] = m;
+        }
+    }
+    flushReg();
+    flushWin();
+    __syncthreads();
+    for (int k = tid; k < kGatherSlots * 4; k += kGatherThreads) {
+        const uint32_t v = (&sWin[0][0])[k];
+        if (v) atomicAdd(&g.windows[static_cast<size_t>(firstWin + (k >> 2)) * 8 + 4 + (k & 3)], v);
+    }
+    for (int k = tid; k < static_cast<int>(sNReg) * 5; k += kGatherThreads) {
+        const uint32_t v = (&sRegCnt[0][0])[k];
+        if (v) atomicAdd(reinterpret_cast<uint32_t *>(g.itemCounts + sRegion[k / 5].item) + (k % 5), v);
+    }
+}
+
+cudaError_t launchTileScan(const GatherParams &g, cudaStream_t s) {
+    tileScanKernel<<<1, 1024, 0, s>>>(g);
+    return cudaGetLastError();
+}
+cudaError_t launchGather(const GatherParams &g, cudaStream_t s) {
+    if (g.nTiles == 0) return cudaSuccess;
+    gatherKernel<<<g.nTiles, kGatherThreads, 0, s>>>(g);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

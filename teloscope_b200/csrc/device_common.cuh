@@ -1,0 +1,28 @@
+// Small device helpers shared by the scan and the gather kernels.
+#pragma once
+
+#include <cstdint>
+
+#include "device_types.hpp"
+
+namespace tls {
+
+__device__ __forceinline__ uint32_t divWindow(const DevConfig &c, uint32_t rel) {
+    const uint32_t t = __umulhi(c.winMagic, rel);
+    return (t + ((rel - t) >> c.winSh1)) >> c.winSh2;
+}
+
+// "Terminal" status of a match that starts at item-relative position rel in window winIdx of an
+// item of n bases (src/teloscope.cpp:403-406 and :451-459; note the <= in the per-match test).
+__device__ __forceinline__ bool isTerminalMatch(const DevConfig &c, uint32_t rel, uint32_t winIdx, uint32_t n) {
+    const uint32_t T = c.terminalLimit;
+    const uint64_t wStart = static_cast<uint64_t>(winIdx) * c.windowSize;
+    uint64_t wEnd = wStart + c.windowSize;
+    if (wEnd > n) wEnd = n;
+    const uint32_t termEnd = n > T ? n - T : 0;
+    if (wEnd <= T || wStart >= termEnd) return true;
+    if (wStart > T && wEnd < termEnd) return false;
+    return rel <= T || rel >= termEnd;
+}
+
+}  // namespace tls

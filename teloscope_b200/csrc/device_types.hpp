@@ -17,6 +17,7 @@ constexpr int kTileHalo = 64;                     // bytes staged after the tile
 constexpr int kTileMaxLen = kTileSmemBytes - 16;  // leaves room for the alignment skew
 constexpr int kQueueCap = 544;                    // per-warp candidate queue (u16 entries)
 constexpr int kRegionCache = 32;                  // regions of a tile kept in shared memory
+constexpr uint32_t kNoOverflow = 0xFFFFFFFFu;
 constexpr int kWindowSlots = 128;                 // per-tile window counter slots in shared memory
 constexpr int kFlagTabBytes = 24576;              // direct stage-2 tables (sum 4^len, len<=7)
 
@@ -42,9 +43,11 @@ struct DevMatch {          // 8 bytes, ordered by (item, pos, len)
     uint32_t pos;          // relative to the item start
     uint16_t len;
     uint8_t flags;         // bit0 forward, bit1 canonical, bit2 terminal (src/teloscope.cpp:451-459)
-    uint8_t pad;
+    uint8_t region;        // scan -> gather only: index of the match's region in its tile's region
+                           // list, or kRegionAccounted when the scan kernel already did the counting
 };
 enum : uint8_t { kMatchFwd = 1, kMatchCan = 2, kMatchTerm = 4 };
+constexpr uint8_t kRegionAccounted = 0xFF;
 
 struct DevItemCounts {     // per item, filled by the scan kernel
     uint32_t all, fwd, rev, can, nonCanTerm, pad[3];
@@ -91,16 +94,36 @@ struct ScanParams {
     const uint8_t *flagTabs;       // direct stage-2 tables
     const uint64_t *sortedKeys;    // long patterns (len > 7)
     const uint8_t *sortedFlags;
-    DevMatch *matches;             // ordered output
-    uint64_t matchCap;
-    DevMatch *scratch;             // per-CTA staging, scratchPerWarp records per warp
-    uint32_t scratchPerWarp;
-    unsigned long long *tileStatus;   // decoupled look-back words, zeroed per launch
-    unsigned int *tileCounter;        // dynamic tile scheduler, zeroed per launch
-    unsigned long long *totalMatches; // written by the last tile
+    // Match output: every (tile, warp) owns a slot of slotCap records; a warp that needs more
+    // takes one overflow chunk of ovChunk records from ovArena (bump allocation).
+    DevMatch *slots;               // [nTiles * kScanWarps][slotCap]
+    uint32_t slotCap;
+    uint32_t *slotCounts;          // [nTiles * kScanWarps] records produced
+    uint32_t *slotOv;              // [nTiles * kScanWarps] overflow chunk base or 0xFFFFFFFF
+    DevMatch *ovArena;
+    uint32_t ovCap, ovChunk;
+    unsigned int *ovCursor;        // zeroed per launch; > ovCap afterwards means "grow and rerun"
     uint32_t *windows;             // [nWindows][8], zeroed per launch
     DevItemCounts *itemCounts;     // zeroed per launch
     DevConfig cfg;
+};
+
+struct GatherParams {
+    const DevTile *tiles;
+    const DevRegion *regions;
+    uint32_t nRegions;
+    uint32_t *windows;             // [nWindows][8]: fields 4..7 (covered bp) are added here
+    DevItemCounts *itemCounts;
+    DevConfig cfg;
+    const DevMatch *slots;
+    uint32_t slotCap;
+    const uint32_t *slotCounts, *slotOv;
+    const DevMatch *ovArena;
+    uint32_t ovCap;
+    uint32_t nTiles;
+    unsigned long long *tileBase;  // [nTiles + 1] exclusive prefix of per-tile totals
+    DevMatch *matches;             // ordered output
+    unsigned long long matchCap;
 };
 
 struct BlockParams {

@@ -10,6 +10,10 @@ namespace tls {
 size_t scanSmemBytes();
 cudaError_t launchScan(const ScanParams &p, int grid, cudaStream_t stream);
 
+// exclusive scan of per-tile match totals (tileBase[nTiles] = total), then ordered copy
+cudaError_t launchTileScan(const GatherParams &g, cudaStream_t s);
+cudaError_t launchGather(const GatherParams &g, cudaStream_t s);
+
 cudaError_t launchTrimCr(const uint8_t *seq, DevRegion *regions, uint32_t nRegions, uint32_t *itemLen, cudaStream_t s);
 cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned long long *itemBegin, cudaStream_t s);
 cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s);

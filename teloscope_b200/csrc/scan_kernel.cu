@@ -1,9 +1,10 @@
 // Fused telomeric motif scan for sm_100a.
 //
-// One persistent CTA per SM pulls tiles (<= 49136 bases of the staged sequence buffer) from a
-// dynamic scheduler.  Per tile:
+// One persistent CTA per SM walks tiles (<= 49136 bases of the staged sequence buffer), tile
+// index = blockIdx.x + k * gridDim.x.  Nothing in the kernel waits on another CTA.  Per tile:
 //   1. the raw ASCII bytes are staged into shared memory with cp.async.bulk (TMA bulk copy,
-//      mbarrier completion), double buffered so the next tile loads while this one is scanned;
+//      mbarrier completion), double buffered; the next tile's descriptor and regions are
+//      prefetched into registers one iteration ahead so no global latency sits on the tile path;
 //   2. every lane packs its 48-base span to 2-bit codes in registers (SWAR multiply-gather) and
 //      probes a 64 KiB shared-memory table with the 8-mer at every NPOS-th offset; one byte of
 //      the table answers NPOS start positions at once (replaces the reference's Trie walk,
@@ -13,14 +14,14 @@
 //      (src/teloscope.cpp:439,:549), orientation + canonical flags, per-window covered-bp and
 //      per-item counters;
 //   4. A/C/G/T window counts come from popcounts on the packed codes (src/teloscope.cpp:418-435);
-//   5. the tile's match records are written in genome order to one compact list: per-warp staging
-//      in an L2-resident scratch, then a decoupled look-back over tile totals gives the tile's
-//      base offset and the warps copy their records out.
+//   5. match records go, in genome order, to the (tile, warp) slot of a global arena; a later
+//      scan + gather pass (block_kernels.cu) compacts the slots into one ordered list.
 // No tensor cores: this is byte/integer streaming work bound by instruction issue and HBM.
 #include <cuda_runtime.h>
 
 #include <cstdint>
 
+#include "device_common.cuh"
 #include "kernels.hpp"
 
 namespace tls {
@@ -60,18 +61,6 @@ __device__ __forceinline__ void bulkLoad(void *dst, const void *src, uint32_t by
         "l"(src), "r"(bytes), "r"(smemAddr(bar))
         : "memory");
 }
-__device__ __forceinline__ unsigned long long ldAcquire(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stRelease(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-constexpr unsigned long long kFlagAgg = 1ull << 62;     // tile total published
-constexpr unsigned long long kFlagPrefix = 2ull << 62;  // inclusive prefix published
-constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
 // ------------------------------------------------------------------------------------------------
 // SWAR helpers on 4 ASCII bytes per 32-bit word
@@ -91,13 +80,21 @@ __device__ __forceinline__ uint32_t pack16(const uint4 &v) {
     return __byte_perm(__byte_perm(a, b, 0x0073), __byte_perm(c, d, 0x0073), 0x5410);
 }
 
-// Nonzero iff some byte of w is not one of ACGTacgt.  Per byte (b7..b0), after ignoring the case
-// bit b5, the four letters are exactly: b7=0, b6=1, b3=0, b0 != b4, (b2 & ~b1) == b4.
-// The two relations are evaluated at bit 4 of every byte from left-shifted copies.
-__device__ __forceinline__ uint32_t badBytes(uint32_t w) {
+// Bit 4 of a byte of the result is set iff that byte violates b0 != b4 or (b2 & ~b1) == b4; with
+// b7=0, b6=1, b3=0 (checked separately on OR/AND aggregates) these relations single out ACGTacgt.
+__device__ __forceinline__ uint32_t relBits(uint32_t w) {
     const uint32_t l2 = w << 2, l3 = w << 3, l4 = w << 4;
-    const uint32_t rel = (~(l4 ^ w)) | ((l2 & ~l3) ^ w);          // bit 4: any relation violated
-    return (rel & 0x10101010u) | ((w ^ 0x40404040u) & 0xC8C8C8C8u);
+    return (~(l4 ^ w)) | ((l2 & ~l3) ^ w);
+}
+// Nonzero iff some byte of w is not one of ACGTacgt; flagged bytes carry a bit in 0xD8.
+__device__ __forceinline__ uint32_t badBytes(uint32_t w) {
+    return (relBits(w) & 0x10101010u) | ((w ^ 0x40404040u) & 0xC8C8C8C8u);
+}
+// Same predicate for 16 bytes at once (only "any bad byte", no positions).
+__device__ __forceinline__ uint32_t badChunk(const uint4 &v) {
+    const uint32_t rel = relBits(v.x) | relBits(v.y) | relBits(v.z) | relBits(v.w);
+    const uint32_t anyOr = v.x | v.y | v.z | v.w, allAnd = v.x & v.y & v.z & v.w;
+    return (rel & 0x10101010u) | (anyOr & 0x88888888u) | (~allAnd & 0x40404040u);
 }
 
 __device__ __forceinline__ bool isBase(uint32_t c) {
@@ -105,22 +102,20 @@ __device__ __forceinline__ bool isBase(uint32_t c) {
     return c == 'A' || c == 'C' || c == 'G' || c == 'T';
 }
 
-__device__ __forceinline__ uint32_t evenMaskBelow(int n) {   // even bits 0,2,..,2(n-1); n in [0,16]
+__device__ __forceinline__ uint32_t evenMaskBelow(int n) {   // even bits 0,2,..,2(n-1); n clamped to [0,16]
+    n = n < 0 ? 0 : n;
     return n >= 16 ? 0x55555555u : (((1u << (2 * n)) - 1u) & 0x55555555u);
 }
 
-__device__ __forceinline__ uint32_t divWindow(const DevConfig &c, uint32_t rel) {
-    const uint32_t t = __umulhi(c.winMagic, rel);
-    return (t + ((rel - t) >> c.winSh1)) >> c.winSh2;
-}
-
-struct TileCtx {
+// Per-tile facts every thread needs, written to shared memory by warp 0 before the tile starts.
+struct TileMeta {
     uint64_t bufStart;
     uint32_t len;
-    uint32_t skew;          // tile byte 0 sits at shared-memory byte `skew`
     uint32_t firstRegion;
     uint32_t nCached;       // regions of this tile in shared memory
-    uint32_t firstWin;      // window index of the first slot
+    uint32_t firstWin;      // window index of shared counter slot 0
+    uint32_t single;        // 1: region 0 covers the whole tile
+    uint32_t relBase;       // single: item-relative position of tile byte 0
 };
 
 struct Located {
@@ -129,12 +124,17 @@ struct Located {
     uint32_t item, rel, itemLen, regionEndRel, winBase;
 };
 
-__device__ __forceinline__ Located locate(const ScanParams &p, const TileCtx &t, const DevRegion *sRegions,
-                                          int q) {
+__device__ __forceinline__ Located locate(const ScanParams &p, const TileMeta &t, const DevRegion *sRegions, int q) {
     Located r;
     r.ok = false;
     r.cacheIdx = 0xFFFFFFFFu;
     if (q < 0 || q >= static_cast<int>(t.len)) return r;
+    if (t.single) {
+        const DevRegion &c = sRegions[0];
+        r.ok = true; r.cacheIdx = 0; r.item = c.item; r.rel = t.relBase + static_cast<uint32_t>(q);
+        r.itemLen = c.itemLen; r.regionEndRel = c.relStart + c.len; r.winBase = c.winBase;
+        return r;
+    }
     const uint64_t pos = t.bufStart + static_cast<uint32_t>(q);
     const DevRegion *reg = nullptr;
     for (uint32_t k = 0; k < t.nCached; ++k) {
@@ -163,8 +163,7 @@ __device__ __forceinline__ Located locate(const ScanParams &p, const TileCtx &t,
     return r;
 }
 
-// Warp-level "add by key" for keys that are non-decreasing across the active lanes: one leader
-// per distinct key receives the sums.  f(key, sum0, sum1) runs on the leader lane only.
+// Warp-level "add by key": one leader per distinct key among the active lanes receives the sums.
 template <typename F>
 __device__ __forceinline__ void warpAddByKey(uint32_t active, uint32_t key, uint32_t v0, uint32_t v1, F f) {
     const int lane = threadIdx.x & 31;
@@ -172,11 +171,22 @@ __device__ __forceinline__ void warpAddByKey(uint32_t active, uint32_t key, uint
         const int leader = __ffs(active) - 1;
         const uint32_t k0 = __shfl_sync(0xFFFFFFFFu, key, leader);
         const uint32_t grp = __ballot_sync(0xFFFFFFFFu, key == k0) & active;
-        const uint32_t s0 = __reduce_add_sync(0xFFFFFFFFu, (grp >> lane) & 1u ? v0 : 0u);
-        const uint32_t s1 = __reduce_add_sync(0xFFFFFFFFu, (grp >> lane) & 1u ? v1 : 0u);
+        const bool mine = (grp >> lane) & 1u;
+        const uint32_t s0 = __reduce_add_sync(0xFFFFFFFFu, mine ? v0 : 0u);
+        const uint32_t s1 = __reduce_add_sync(0xFFFFFFFFu, mine ? v1 : 0u);
         if (lane == leader) f(k0, s0, s1);
         active &= ~grp;
     }
+}
+
+__device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= d) v += u;
+    }
+    return v;
 }
 
 }  // namespace
@@ -192,18 +202,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
     uint8_t *sTile = sFlags + kFlagTabBytes;
     constexpr int kTileStride = kTileSmemBytes + kTileHalo;
     uint16_t *sQueueAll = reinterpret_cast<uint16_t *>(sTile + 2 * kTileStride);
-    DevRegion *sRegions = reinterpret_cast<DevRegion *>(sQueueAll + kScanWarps * kQueueCap);
-    uint32_t *sRegCnt = reinterpret_cast<uint32_t *>(sRegions + kRegionCache);        // [cache][5]
-    uint32_t *sWin = sRegCnt + kRegionCache * 5;                                        // [slots][8]
-    uint32_t *sWarpCount = sWin + kWindowSlots * 8;                                     // [warps]
-    uint64_t *sBar = reinterpret_cast<uint64_t *>(sWarpCount + kScanWarps);            // [2]
-    unsigned long long *sTileBase = reinterpret_cast<unsigned long long *>(sBar + 2);
-    uint32_t *sNext = reinterpret_cast<uint32_t *>(sTileBase + 1);
+    DevRegion *sRegionsAll = reinterpret_cast<DevRegion *>(sQueueAll + kScanWarps * kQueueCap);   // [2][cache]
+    uint32_t *sWinAll = reinterpret_cast<uint32_t *>(sRegionsAll + 2 * kRegionCache);              // [2][slots][4]
+    TileMeta *sMetaAll = reinterpret_cast<TileMeta *>(sWinAll + 2 * kWindowSlots * 4);             // [2]
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(sMetaAll + 2);                                   // [2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t laneLt = (1u << lane) - 1u;
     const DevConfig &cfg = p.cfg;
     uint16_t *sQueue = sQueueAll + warp * kQueueCap;
-    DevMatch *warpScratch = p.scratch + (static_cast<size_t>(blockIdx.x) * kScanWarps + warp) * p.scratchPerWarp;
 
     // ---- one-time setup: tables to shared memory, barriers --------------------------------------
     for (int i = tid; i < 65536 / 16; i += kScanThreads)
@@ -217,8 +224,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
     }
     __syncthreads();
 
-    auto issueLoad = [&](uint32_t tileIdx, int buf) {   // one thread
-        const DevTile t = p.tiles[tileIdx];
+    auto issueLoad = [&](const DevTile &t, int buf) {   // one thread
         const uint64_t a = t.bufStart & ~15ull;
         const uint32_t bytes = (static_cast<uint32_t>(t.bufStart - a) + t.len + kTileHalo + 15u) & ~15u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -227,236 +233,211 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
         for (uint32_t off = 0; off < bytes; off += 16384u)
             bulkLoad(dst + off, p.seq + a + off, min(16384u, bytes - off), &sBar[buf]);
     };
+    auto loadRegion = [&](const DevTile &t) {           // threads of warp 0: candidate region `lane`
+        const uint32_t idx = min(t.firstRegion + static_cast<uint32_t>(lane), p.nRegions - 1);
+        return p.regions[idx];
+    };
 
-    if (tid == 0) {
-        const uint32_t first = atomicAdd(p.tileCounter, 1u);
-        *sNext = first;
-        if (first < p.nTiles) issueLoad(first, 0);
-    }
-    __syncthreads();
-    uint32_t cur = *sNext;
+    const uint32_t G = gridDim.x;
+    uint32_t tileIdx = blockIdx.x;
+    if (tileIdx >= p.nTiles) return;
+    // software pipeline registers: descriptors of tile k (cur), k+1 (next); regions of cur
+    DevTile tCur = p.tiles[tileIdx];
+    DevTile tNext = tileIdx + G < p.nTiles ? p.tiles[tileIdx + G] : DevTile{};
+    DevRegion rCur{};
+    if (warp == 0) rCur = loadRegion(tCur);
+    if (tid == 0) issueLoad(tCur, 0);
 
-    for (uint32_t iter = 0; cur < p.nTiles; ++iter) {
+    for (uint32_t iter = 0; tileIdx < p.nTiles; ++iter, tileIdx += G) {
         const int buf = iter & 1;
-        uint8_t *tile = sTile + buf * kTileStride;
-        __syncthreads();                                   // everyone has read *sNext
-        if (tid == 0) {
-            const uint32_t nxt = atomicAdd(p.tileCounter, 1u);
-            *sNext = nxt;
-            if (nxt < p.nTiles) issueLoad(nxt, buf ^ 1);
-        }
-        // ---- tile metadata --------------------------------------------------------------------
-        TileCtx t;
-        {
-            const DevTile dt = p.tiles[cur];
-            t.bufStart = dt.bufStart;
-            t.len = dt.len;
-            t.skew = static_cast<uint32_t>(dt.bufStart & 15ull);
-            t.firstRegion = dt.firstRegion;
-            const uint64_t tileEnd = dt.bufStart + dt.len;
-            uint32_t n = 0;
-            while (n < kRegionCache && dt.firstRegion + n < p.nRegions &&
-                   p.regions[dt.firstRegion + n].bufStart < tileEnd)
-                ++n;
-            t.nCached = n;
-            t.firstWin = 0;
-            if (cfg.mode == 0 && n > 0) {
-                const DevRegion r0 = p.regions[dt.firstRegion];
-                const uint64_t s = dt.bufStart > r0.bufStart ? dt.bufStart : r0.bufStart;
-                t.firstWin = r0.winBase + divWindow(cfg, r0.relStart + static_cast<uint32_t>(s - r0.bufStart));
+        const uint8_t *tile = sTile + buf * kTileStride;
+        DevRegion *sRegions = sRegionsAll + buf * kRegionCache;
+        uint32_t *sWin = sWinAll + buf * kWindowSlots * 4;
+        const bool hasNext = tileIdx + G < p.nTiles;
+
+        // ---- prefetch: data of tile k+1, descriptor of k+2, regions of k+1 (all consumed later) ----
+        if (tid == 0 && hasNext) issueLoad(tNext, buf ^ 1);
+        DevTile tNext2{};
+        if (tileIdx + 2 * G < p.nTiles) tNext2 = p.tiles[tileIdx + 2 * G];
+        DevRegion rNext{};
+        if (warp == 0 && hasNext) rNext = loadRegion(tNext);
+
+        // ---- publish this tile's metadata (registers -> shared) ----------------------------------------
+        if (warp == 0) {
+            const uint64_t tileEnd = tCur.bufStart + tCur.len;
+            const bool in = tCur.firstRegion + lane < p.nRegions && rCur.bufStart < tileEnd;
+            const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, in));   // regions are sorted: a prefix
+            if (in) sRegions[lane] = rCur;
+            if (lane == 0) {
+                TileMeta m;
+                m.bufStart = tCur.bufStart; m.len = tCur.len; m.firstRegion = tCur.firstRegion; m.nCached = n;
+                m.single = n >= 1 && rCur.bufStart <= tCur.bufStart && tileEnd <= rCur.bufStart + rCur.len;
+                const uint64_t s = tCur.bufStart > rCur.bufStart ? tCur.bufStart : rCur.bufStart;
+                const uint32_t relFirst = rCur.relStart + static_cast<uint32_t>(s - rCur.bufStart);
+                m.relBase = rCur.relStart + static_cast<uint32_t>(tCur.bufStart - rCur.bufStart);   // valid if single
+                m.firstWin = (cfg.mode == 0 && n > 0) ? rCur.winBase + divWindow(cfg, relFirst) : 0;
+                sMetaAll[buf] = m;
             }
         }
-        if (tid < static_cast<int>(t.nCached)) sRegions[tid] = p.regions[t.firstRegion + tid];
-        for (int i = tid; i < kRegionCache * 5; i += kScanThreads) sRegCnt[i] = 0;
-        for (int i = tid; i < kWindowSlots * 8; i += kScanThreads) sWin[i] = 0;
+        if (COUNT)
+            for (int i = tid; i < kWindowSlots * 4; i += kScanThreads) sWin[i] = 0;
         __syncthreads();
-        const uint32_t nextTile = *sNext;
+        const TileMeta t = sMetaAll[buf];
+        const uint32_t skew = static_cast<uint32_t>(t.bufStart & 15ull);
+        const uint32_t regionEnd0 = sRegions[0].relStart + sRegions[0].len;   // single tiles
+        const uint32_t winBase0 = sRegions[0].winBase;
         mbarWait(&sBar[buf], (iter >> 1) & 1u);
 
         // ---- per-warp state -----------------------------------------------------------------
-        uint32_t qCount = 0;        // candidates pending in this warp's queue
-        uint32_t wMatches = 0;      // match records this warp has staged for the tile
+        uint32_t wMatches = 0;      // match records this warp has produced for the tile
+        uint32_t ovBase = kNoOverflow;
+        const size_t slotIdx = static_cast<size_t>(tileIdx) * kScanWarps + warp;
+        DevMatch *slot = p.slots + slotIdx * p.slotCap;
 
-        auto addWindow = [&](uint32_t win, int field, uint32_t v) {
-            if (v == 0) return;
-            const uint32_t slot = win - t.firstWin;
-            if (slot < kWindowSlots) atomicAdd(&sWin[slot * 8 + field], v);
-            else atomicAdd(&p.windows[static_cast<size_t>(win) * 8 + field], v);
+        auto addAcgt = [&](uint32_t win, uint32_t a, uint32_t c, uint32_t g, uint32_t tt) {   // one lane
+            const uint32_t s = win - t.firstWin;
+            if (s < kWindowSlots) {
+                uint32_t *w = sWin + s * 4;
+                if (a) atomicAdd(w + 0, a);
+                if (c) atomicAdd(w + 1, c);
+                if (g) atomicAdd(w + 2, g);
+                if (tt) atomicAdd(w + 3, tt);
+            } else {
+                uint32_t *w = p.windows + static_cast<size_t>(win) * 8;
+                if (a) atomicAdd(w + 0, a);
+                if (c) atomicAdd(w + 1, c);
+                if (g) atomicAdd(w + 2, g);
+                if (tt) atomicAdd(w + 3, tt);
+            }
         };
 
-        // ---- stage 2: resolve up to 32 queued candidates (entries [from, from+count)) -----------
+        // ---- stage 2: verify up to 32 queued candidates and emit match records ---------------------
         auto resolveBatch = [&](uint32_t from, uint32_t count) {
-            const bool active = lane < static_cast<int>(count);
-            int sb = 0;
-            Located loc;
-            loc.ok = false;
-            if (active) {
-                sb = sQueue[from + lane];
-                loc = locate(p, t, sRegions, sb - static_cast<int>(t.skew));
-            }
-            uint32_t hitMask = 0, flagBits = 0;   // per class: hit bit, 3 flag bits
-            uint32_t winIdx = 0;
-            bool terminal = false;
-            if (loc.ok) {
-                // how far a match starting here may extend
-                uint32_t limit = loc.regionEndRel;
-                if (cfg.mode == 0) {
-                    winIdx = divWindow(cfg, loc.rel);
-                    const uint64_t wEnd = static_cast<uint64_t>(winIdx + 1) * cfg.windowSize;
-                    if (wEnd < limit) limit = static_cast<uint32_t>(wEnd);
-                    // terminal status for non-canonical matches (src/teloscope.cpp:403-406,451-459)
-                    const uint32_t T = cfg.terminalLimit, n = loc.itemLen;
-                    const uint64_t wStart = static_cast<uint64_t>(winIdx) * cfg.windowSize;
-                    const uint64_t wEndC = wEnd < n ? wEnd : n;
-                    const uint32_t termEnd = n > T ? n - T : 0;
-                    if (wEndC <= T || wStart >= termEnd) terminal = true;
-                    else if (wStart > T && wEndC < termEnd) terminal = false;
-                    else terminal = loc.rel <= T || loc.rel >= termEnd;
+            uint32_t hitMask = 0, flagBits = 0, rel = 0, region = 0, termBit = 0;
+            if (lane < static_cast<int>(count)) {
+                const uint32_t sb = sQueue[from + lane];
+                const uint32_t q = sb - skew;                       // tile position (wraps if before the tile)
+                bool ok = q < t.len;
+                uint32_t limit = 0, item = 0, itemLen = 0, winBaseLoc = 0;
+                if (t.single) {
+                    rel = t.relBase + q;
+                    limit = regionEnd0;
+                } else if (ok) {
+                    const Located loc = locate(p, t, sRegions, static_cast<int>(q));
+                    ok = loc.ok;
+                    rel = loc.rel; limit = loc.regionEndRel; item = loc.item; itemLen = loc.itemLen; winBaseLoc = loc.winBase;
+                    region = loc.cacheIdx == 0xFFFFFFFFu ? kRegionAccounted : loc.cacheIdx;
                 }
-                const uint32_t room = limit - loc.rel;          // >= 1
-                if (room >= cfg.minLen) {
-                    // read 8 bytes at sb (unaligned) as two words
-                    const uint32_t a = static_cast<uint32_t>(sb) & ~3u, sh = (static_cast<uint32_t>(sb) & 3u) * 8u;
-                    const uint32_t w0 = *reinterpret_cast<const uint32_t *>(tile + a);
-                    const uint32_t w1 = *reinterpret_cast<const uint32_t *>(tile + a + 4);
-                    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(tile + a + 8);
-                    const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
-                    uint64_t key = pack4(x0) | (pack4(x1) << 8);
-                    // number of leading valid bases among the first 8
-                    const uint32_t b0 = badBytes(x0), b1 = badBytes(x1);
-                    uint32_t nValid = b0 ? (__ffs(b0) - 1) >> 3 : (b1 ? 4 + ((__ffs(b1) - 1) >> 3) : 8);
-                    if (nValid == 8 && cfg.maxLen > 8 && room > 8) {   // long patterns: byte loop
-                        const uint32_t need = min(cfg.maxLen, room);
-                        for (uint32_t j = 8; j < need; ++j) {
-                            const uint32_t c = tile[sb + j];
-                            if (!isBase(c)) break;
-                            key |= static_cast<uint64_t>((c >> 1) & 3u) << (2 * j);
-                            ++nValid;
-                        }
+                if (ok) {
+                    if (cfg.mode == 0) {     // matches never cross the window end (src/teloscope.cpp:439)
+                        const uint64_t wEnd = static_cast<uint64_t>(divWindow(cfg, rel) + 1) * cfg.windowSize;
+                        if (wEnd < limit) limit = static_cast<uint32_t>(wEnd);
                     }
-                    const uint32_t usable = min(nValid, room);
-                    for (uint32_t ci = 0; ci < cfg.nClasses; ++ci) {
-                        const DevLenClass &lc = cfg.cls[ci];
-                        if (lc.len > usable) break;
-                        const uint64_t k = lc.len >= 32 ? key : (key & ((1ull << (2 * lc.len)) - 1ull));
-                        uint32_t f = 0;
-                        if (lc.direct) {
-                            f = sFlags[lc.flagOffset + static_cast<uint32_t>(k)];
-                        } else {
-                            uint32_t lo = lc.sortedBegin, hi = lc.sortedBegin + lc.sortedCount;
-                            while (lo < hi) {
-                                const uint32_t mid = (lo + hi) >> 1;
-                                const uint64_t mk = p.sortedKeys[mid];
-                                if (mk < k) lo = mid + 1; else hi = mid;
+                    const uint32_t room = limit - rel;              // >= 1
+                    if (room >= cfg.minLen) {
+                        // 8 bytes at sb (unaligned) as two words
+                        const uint32_t a = sb & ~3u, sh = (sb & 3u) * 8u;
+                        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(tile + a);
+                        const uint32_t w1 = *reinterpret_cast<const uint32_t *>(tile + a + 4);
+                        const uint32_t w2 = *reinterpret_cast<const uint32_t *>(tile + a + 8);
+                        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+                        uint64_t key = pack4(x0) | (pack4(x1) << 8);
+                        const uint32_t b0 = badBytes(x0), b1 = badBytes(x1);
+                        uint32_t nValid = b0 ? (__ffs(b0) - 1) >> 3 : (b1 ? 4 + ((__ffs(b1) - 1) >> 3) : 8);
+                        if (nValid == 8 && cfg.maxLen > 8 && room > 8) {   // long patterns: byte loop
+                            const uint32_t need = min(cfg.maxLen, room);
+                            for (uint32_t j = 8; j < need; ++j) {
+                                const uint32_t c = tile[sb + j];
+                                if (!isBase(c)) break;
+                                key |= static_cast<uint64_t>((c >> 1) & 3u) << (2 * j);
+                                ++nValid;
                             }
-                            if (lo < lc.sortedBegin + lc.sortedCount && p.sortedKeys[lo] == k) f = p.sortedFlags[lo];
                         }
-                        if (f & 1u) {
-                            hitMask |= 1u << ci;
-                            flagBits |= ((f >> 1) & 3u) << (2 * ci);
+                        const uint32_t usable = min(nValid, room);
+                        for (uint32_t ci = 0; ci < cfg.nClasses; ++ci) {
+                            const DevLenClass &lc = cfg.cls[ci];
+                            if (lc.len > usable) break;
+                            const uint64_t k = lc.len >= 32 ? key : (key & ((1ull << (2 * lc.len)) - 1ull));
+                            uint32_t f = 0;
+                            if (lc.direct) {
+                                f = sFlags[lc.flagOffset + static_cast<uint32_t>(k)];
+                            } else {
+                                uint32_t lo = lc.sortedBegin, hi = lc.sortedBegin + lc.sortedCount;
+                                while (lo < hi) {
+                                    const uint32_t mid = (lo + hi) >> 1;
+                                    if (p.sortedKeys[mid] < k) lo = mid + 1; else hi = mid;
+                                }
+                                if (lo < lc.sortedBegin + lc.sortedCount && p.sortedKeys[lo] == k) f = p.sortedFlags[lo];
+                            }
+                            if (f & 1u) {
+                                hitMask |= 1u << ci;
+                                flagBits |= ((f >> 1) & 3u) << (2 * ci);
+                            }
+                        }
+                    }
+                }
+                if (hitMask && region == kRegionAccounted && !t.single) {
+                    // region beyond the shared cache (> 32 regions in one tile): do the gather pass's
+                    // accounting here, with global atomics
+                    DevItemCounts *c = p.itemCounts + item;
+                    const uint32_t winIdx = cfg.mode == 0 ? divWindow(cfg, rel) : 0;
+                    const bool term = cfg.mode == 0 && isTerminalMatch(cfg, rel, winIdx, itemLen);
+                    if (term) termBit = kMatchTerm;
+                    for (uint32_t hm = hitMask; hm; hm &= hm - 1) {
+                        const int ci = __ffs(hm) - 1;
+                        const uint32_t fl = (flagBits >> (2 * ci)) & 3u, len = cfg.cls[ci].len;
+                        atomicAdd(&c->all, 1u);
+                        atomicAdd((fl & 1u) ? &c->fwd : &c->rev, 1u);
+                        if (fl & 2u) atomicAdd(&c->can, 1u);
+                        else if (term) atomicAdd(&c->nonCanTerm, 1u);
+                        if (cfg.mode == 0) {
+                            uint32_t *w = p.windows + static_cast<size_t>(winBaseLoc + winIdx) * 8;
+                            atomicAdd(w + ((fl & 2u) ? 4 : 5), len);
+                            atomicAdd(w + ((fl & 1u) ? 6 : 7), len);
                         }
                     }
                 }
             }
-            // ---- ordered emission into the warp's staging area ------------------------------------
+            // ---- ordered emission into the warp's slot ---------------------------------------------
             const uint32_t nHit = __popc(hitMask);
-            uint32_t incl = nHit;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += v;
+            const uint32_t have = __ballot_sync(0xFFFFFFFFu, nHit != 0);
+            if (have == 0) return;
+            uint32_t excl, total;
+            if (cfg.nClasses == 1) {
+                excl = __popc(have & laneLt);
+                total = __popc(have);
+            } else {
+                const uint32_t incl = warpInclusiveScan(nHit);
+                total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                excl = incl - nHit;
             }
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (total == 0) return;
-            uint32_t nFwd = 0, nCan = 0, nNct = 0, canLen = 0, nonCanLen = 0, fwdLen = 0, revLen = 0;
-            {
-                uint32_t o = wMatches + incl - nHit;
-                uint32_t hm = hitMask;
-                while (hm) {
-                    const int ci = __ffs(hm) - 1;
-                    hm &= hm - 1;
-                    const uint32_t fl = (flagBits >> (2 * ci)) & 3u;      // bit0 fwd, bit1 canonical
-                    const uint32_t len = cfg.cls[ci].len;
-                    const bool fwd = fl & 1u, can = fl & 2u;
-                    DevMatch m;
-                    m.pos = loc.rel;
-                    m.len = static_cast<uint16_t>(len);
-                    m.flags = static_cast<uint8_t>((fwd ? kMatchFwd : 0) | (can ? kMatchCan : 0) |
-                                                   (terminal ? kMatchTerm : 0));
-                    m.pad = 0;
-                    if (o < p.scratchPerWarp) warpScratch[o] = m;
-                    ++o;
-                    nFwd += fwd; nCan += can; nNct += (!can && terminal);
-                    if (can) canLen += len; else nonCanLen += len;
-                    if (fwd) fwdLen += len; else revLen += len;
-                }
+            if (wMatches + total > p.slotCap && ovBase == kNoOverflow) {
+                if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
+                ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
+            }
+            uint32_t o = wMatches + excl;
+            for (uint32_t hm = hitMask; hm; hm &= hm - 1, ++o) {
+                const int ci = __ffs(hm) - 1;
+                DevMatch m;
+                m.pos = rel;
+                m.len = static_cast<uint16_t>(cfg.cls[ci].len);
+                m.flags = static_cast<uint8_t>(((flagBits >> (2 * ci)) & 3u) | termBit);   // kMatchFwd | kMatchCan
+                m.region = static_cast<uint8_t>(region);
+                if (o < p.slotCap) slot[o] = m;
+                else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap) p.ovArena[ovBase + (o - p.slotCap)] = m;
             }
             wMatches += total;
-            const uint32_t have = __ballot_sync(0xFFFFFFFFu, nHit != 0);
-            // per-item counters (aggregated per distinct region, then one shared atomic each)
-            {
-                const uint32_t key = loc.cacheIdx != 0xFFFFFFFFu ? loc.cacheIdx : (0x80000000u | loc.item);
-                warpAddByKey(have, key, nHit | (nFwd << 10) | (nCan << 20), nNct,
-                             [&](uint32_t k, uint32_t s0, uint32_t s1) {
-                                 const uint32_t all = s0 & 1023u, fw = (s0 >> 10) & 1023u, cn = s0 >> 20;
-                                 if (!(k & 0x80000000u)) {
-                                     uint32_t *c = sRegCnt + k * 5;
-                                     atomicAdd(c + 0, all); atomicAdd(c + 1, fw); atomicAdd(c + 2, all - fw);
-                                     atomicAdd(c + 3, cn); atomicAdd(c + 4, s1);
-                                 } else {
-                                     DevItemCounts *c = p.itemCounts + (k & 0x7FFFFFFFu);
-                                     atomicAdd(&c->all, all); atomicAdd(&c->fwd, fw); atomicAdd(&c->rev, all - fw);
-                                     atomicAdd(&c->can, cn); atomicAdd(&c->nonCanTerm, s1);
-                                 }
-                             });
-            }
-            if (cfg.mode == 0) {   // per-window covered bp (src/teloscope.cpp:486-507)
-                const uint32_t win = loc.winBase + winIdx;
-                warpAddByKey(have, win, canLen | (nonCanLen << 16), fwdLen | (revLen << 16),
-                             [&](uint32_t k, uint32_t s0, uint32_t s1) {
-                                 addWindow(k, 4, s0 & 0xFFFFu); addWindow(k, 5, s0 >> 16);
-                                 addWindow(k, 6, s1 & 0xFFFFu); addWindow(k, 7, s1 >> 16);
-                             });
-            }
-        };
-
-        auto drain = [&](bool all) {
-            uint32_t from = 0;
-            while (qCount - from >= 32u) { resolveBatch(from, 32); from += 32; }
-            if (all && qCount > from) { resolveBatch(from, qCount - from); from = qCount; }
-            const uint32_t rem = qCount - from;
-            if (from > 0 && rem > 0) {
-                uint16_t v = 0;
-                if (lane < static_cast<int>(rem)) v = sQueue[from + lane];
-                __syncwarp();
-                if (lane < static_cast<int>(rem)) sQueue[lane] = v;
-            }
-            __syncwarp();
-            qCount = rem;
-        };
-
-        // push the candidates (bit i = span position i) of every lane, lane order = genome order
-        auto push = [&](uint32_t lo, uint32_t hi, uint32_t spanByte) {
-            const uint32_t n = __popc(lo) + __popc(hi);
-            uint32_t incl = n;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            uint32_t o = qCount + incl - n;
-            while (lo) { const int b = __ffs(lo) - 1; lo &= lo - 1; sQueue[o++] = static_cast<uint16_t>(spanByte + b); }
-            while (hi) { const int b = __ffs(hi) - 1; hi &= hi - 1; sQueue[o++] = static_cast<uint16_t>(spanByte + 32 + b); }
-            __syncwarp();
-            qCount += total;
         };
 
         // ---- main loop over this warp's rows ------------------------------------------------------
-        const uint32_t usedBytes = t.skew + t.len;
+        const uint32_t usedBytes = skew + t.len;
+        uint32_t cand[kRowsPerWarp][2];
+        uint32_t nCand = 0;                                  // packed per-row candidate counts of this lane
+#pragma unroll
         for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+            cand[rr][0] = cand[rr][1] = 0;
             const uint32_t row = warp * kRowsPerWarp + rr;
-            if (row * kRowBytes >= usedBytes) break;
+            if (row * kRowBytes >= usedBytes) continue;      // warp-uniform
             const uint32_t spanByte = row * kRowBytes + lane * kSpanBytes;
             const uint4 *src = reinterpret_cast<const uint4 *>(tile + spanByte);
             const uint4 c0 = src[0], c1 = src[1], c2 = src[2], c3 = src[3];
@@ -464,34 +445,45 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
             W[0] = pack16(c0); W[1] = pack16(c1); W[2] = pack16(c2); W[3] = pack16(c3); W[4] = 0;
 
             if (COUNT) {
-                // ---- A/C/G/T counts of this span, split at a window / region boundary -----------
-                const int q0 = static_cast<int>(spanByte) - static_cast<int>(t.skew);
-                int lo = q0 < 0 ? -q0 : 0;                                   // first span position inside the tile
-                int hi = static_cast<int>(t.len) - q0; hi = hi > kSpanBytes ? kSpanBytes : hi;   // one past last
+                // ---- A/C/G/T counts of this span, split at a window boundary -------------------------
+                const int q0 = static_cast<int>(spanByte) - static_cast<int>(skew);
+                const int lo = q0 < 0 ? -q0 : 0;                                  // first span position inside the tile
+                int hi = static_cast<int>(t.len) - q0; hi = hi > kSpanBytes ? kSpanBytes : hi;   // one past the last
                 uint32_t winA = 0xFFFFFFFFu, winB = 0xFFFFFFFFu;
-                uint32_t acA = 0, gtA = 0, acB = 0, gtB = 0;                 // packed A|C<<16, G|T<<16
+                uint32_t acA = 0, gtA = 0, acB = 0, gtB = 0;                      // packed A|C<<16, G|T<<16
                 if (lo < hi) {
-                    const Located a = locate(p, t, sRegions, q0 + lo);
-                    const Located z = locate(p, t, sRegions, q0 + hi - 1);
-                    const bool simple = a.ok && z.ok && a.item == z.item &&
-                                        z.rel - a.rel == static_cast<uint32_t>(hi - 1 - lo);
-                    const uint32_t bad = badBytes(c0.x) | badBytes(c0.y) | badBytes(c0.z) | badBytes(c0.w) |
-                                         badBytes(c1.x) | badBytes(c1.y) | badBytes(c1.z) | badBytes(c1.w) |
-                                         badBytes(c2.x) | badBytes(c2.y) | badBytes(c2.z) | badBytes(c2.w);
-                    const uint32_t wa = simple ? divWindow(cfg, a.rel) : 0, wz = simple ? divWindow(cfg, z.rel) : 0;
-                    if (simple && bad == 0 && wz - wa <= 1u) {
-                        // fast path: all 48 bytes are bases, one item, at most one window boundary
-                        int split = kSpanBytes;                                  // span position of the boundary
-                        if (wz != wa) split = lo + static_cast<int>(static_cast<uint64_t>(wz) * cfg.windowSize - a.rel);
-                        winA = a.winBase + wa;
-                        if (wz != wa) winB = a.winBase + wz;
+                    bool fast = false;
+                    uint32_t relA = 0, wa = 0, winBase = winBase0;
+                    int split = kSpanBytes;
+                    const uint32_t bad = badChunk(c0) | badChunk(c1) | badChunk(c2);
+                    if (bad == 0) {
+                        if (t.single) {
+                            relA = t.relBase + static_cast<uint32_t>(q0 + lo);
+                            fast = true;
+                        } else {
+                            const Located a = locate(p, t, sRegions, q0 + lo);
+                            const Located z = locate(p, t, sRegions, q0 + hi - 1);
+                            fast = a.ok && z.ok && a.item == z.item && z.rel - a.rel == static_cast<uint32_t>(hi - 1 - lo);
+                            relA = a.rel; winBase = a.winBase;
+                        }
+                    }
+                    if (fast) {
+                        wa = divWindow(cfg, relA);
+                        const uint64_t toNext = static_cast<uint64_t>(wa + 1) * cfg.windowSize - relA;   // >= 1
+                        if (toNext < static_cast<uint64_t>(hi - lo)) {
+                            split = lo + static_cast<int>(toNext);
+                            // a second boundary inside the span (window < 48 bases) -> slow path
+                            if (static_cast<uint64_t>(hi - split) > cfg.windowSize) fast = false;
+                        }
+                    }
+                    if (fast) {
+                        winA = winBase + wa;
+                        if (split < hi) winB = winA + 1;
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
                             const uint32_t w = W[j], h = w >> 1;
-                            const int l = lo - 16 * j, r = hi - 16 * j, s = split - 16 * j;
-                            const uint32_t inc = evenMaskBelow(r < 0 ? 0 : (r > 16 ? 16 : r)) &
-                                                 ~evenMaskBelow(l < 0 ? 0 : (l > 16 ? 16 : l));
-                            const uint32_t mA = inc & evenMaskBelow(s < 0 ? 0 : (s > 16 ? 16 : s));
+                            const uint32_t inc = evenMaskBelow(hi - 16 * j) & ~evenMaskBelow(lo - 16 * j);
+                            const uint32_t mA = inc & evenMaskBelow(split - 16 * j);
                             const uint32_t xC = w & ~h, xG = w & h, xT = ~w & h;
                             const uint32_t nC = __popc(xC & mA), nG = __popc(xG & mA), nT = __popc(xT & mA);
                             acA += (__popc(mA) - nC - nG - nT) | (nC << 16);
@@ -504,36 +496,48 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                             }
                         }
                     } else {
-                        // slow path: region edge, several windows, or a non-ACGT byte in the span
+                        // slow path: region edge, tiny windows, or a non-ACGT byte in the span
                         for (int i = lo; i < hi; ++i) {
                             const uint32_t c = tile[spanByte + i];
                             if (!isBase(c)) continue;
                             const Located m = locate(p, t, sRegions, q0 + i);
                             if (!m.ok) continue;
                             const uint32_t code = (c >> 1) & 3u;                // A0 C1 T2 G3
-                            const int field = code == 0 ? 0 : (code == 1 ? 1 : (code == 3 ? 2 : 3));
-                            addWindow(m.winBase + divWindow(cfg, m.rel), field, 1);
+                            addAcgt(m.winBase + divWindow(cfg, m.rel), code == 0, code == 1, code == 3, code == 2);
                         }
                     }
                 }
-                // reduce per window across the warp (window ids are non-decreasing in lane order)
-                const uint32_t hasA = __ballot_sync(0xFFFFFFFFu, winA != 0xFFFFFFFFu);
-                warpAddByKey(hasA, winA, acA, gtA, [&](uint32_t k, uint32_t s0, uint32_t s1) {
-                    addWindow(k, 0, s0 & 0xFFFFu); addWindow(k, 1, s0 >> 16);
-                    addWindow(k, 2, s1 & 0xFFFFu); addWindow(k, 3, s1 >> 16);
-                });
-                const uint32_t hasB = __ballot_sync(0xFFFFFFFFu, winB != 0xFFFFFFFFu);
-                warpAddByKey(hasB, winB, acB, gtB, [&](uint32_t k, uint32_t s0, uint32_t s1) {
-                    addWindow(k, 0, s0 & 0xFFFFu); addWindow(k, 1, s0 >> 16);
-                    addWindow(k, 2, s1 & 0xFFFFu); addWindow(k, 3, s1 >> 16);
-                });
+                // ---- reduce across the warp: windows touched by a row are consecutive ------------------
+                const uint32_t act = __ballot_sync(0xFFFFFFFFu, winA != 0xFFFFFFFFu);
+                if (act) {
+                    const uint32_t wFirst = __shfl_sync(0xFFFFFFFFu, winA, __ffs(act) - 1);
+                    const uint32_t lastWin = winB != 0xFFFFFFFFu ? winB : winA;
+                    const uint32_t wLast = __shfl_sync(0xFFFFFFFFu, lastWin, 31 - __clz(act));
+                    const uint32_t groups = wLast - wFirst + 1;
+                    if (groups <= 4) {
+                        for (uint32_t g = 0; g < groups; ++g) {
+                            const uint32_t wg = wFirst + g;
+                            const uint32_t v0 = (winA == wg ? acA : 0u) + (winB == wg ? acB : 0u);
+                            const uint32_t v1 = (winA == wg ? gtA : 0u) + (winB == wg ? gtB : 0u);
+                            const uint32_t s0 = __reduce_add_sync(0xFFFFFFFFu, v0), s1 = __reduce_add_sync(0xFFFFFFFFu, v1);
+                            if (lane == 0) addAcgt(wg, s0 & 0xFFFFu, s0 >> 16, s1 & 0xFFFFu, s1 >> 16);
+                        }
+                    } else {       // several items in one row: window ids are not consecutive
+                        warpAddByKey(act, winA, acA, gtA, [&](uint32_t k, uint32_t s0, uint32_t s1) {
+                            addAcgt(k, s0 & 0xFFFFu, s0 >> 16, s1 & 0xFFFFu, s1 >> 16);
+                        });
+                        const uint32_t hasB = __ballot_sync(0xFFFFFFFFu, winB != 0xFFFFFFFFu);
+                        warpAddByKey(hasB, winB, acB, gtB, [&](uint32_t k, uint32_t s0, uint32_t s1) {
+                            addAcgt(k, s0 & 0xFFFFu, s0 >> 16, s1 & 0xFFFFu, s1 >> 16);
+                        });
+                    }
+                }
             }
 
             // ---- stage 1: one table byte per NPOS start positions ---------------------------------
             uint32_t candLo = 0, candHi = 0;
 #pragma unroll
             for (int tl = 0; tl < kSpanBytes / NPOS; ++tl) {
-                constexpr int dummy = 0; (void)dummy;
                 const int bit = 2 * NPOS * tl, wi = bit >> 5, sh = bit & 31;
                 const uint32_t x = sh == 0 ? W[wi] : __funnelshift_r(W[wi], W[wi + 1], sh);
                 const uint32_t e = sIndex[x & 0xFFFFu];
@@ -546,85 +550,73 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                 }
             }
             candHi &= 0xFFFFu;
+            cand[rr][0] = candLo; cand[rr][1] = candHi;
+            nCand |= (__popc(candLo) + __popc(candHi)) << (16 * rr);
+        }
 
-            const uint32_t rowTotal = __reduce_add_sync(0xFFFFFFFFu, __popc(candLo) + __popc(candHi));
-            if (qCount + rowTotal <= static_cast<uint32_t>(kQueueCap)) {
-                push(candLo, candHi, spanByte);
-            } else {
-                // dense row: one 16-position chunk at a time (<= 512 candidates each)
-                drain(false);
-                push(candLo & 0xFFFFu, 0, spanByte);
-                drain(false);
-                push(candLo & 0xFFFF0000u, 0, spanByte);
-                drain(false);
-                push(0, candHi, spanByte);
-            }
-            drain(false);
-        }
-        drain(true);
-
-        // ---- tile epilogue: ordered output -----------------------------------------------------
-        if (lane == 0) sWarpCount[warp] = wMatches;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t c = lane < kScanWarps ? sWarpCount[lane] : 0;
-            uint32_t incl = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            const unsigned long long tileTotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (lane < kScanWarps) sWarpCount[lane] = incl - c;          // exclusive offsets
-            if (lane == 0) {
-                unsigned long long excl = 0;
-                if (cur == 0) {
-                    stRelease(&p.tileStatus[0], kFlagPrefix | tileTotal);
-                } else {
-                    stRelease(&p.tileStatus[cur], kFlagAgg | tileTotal);
-                    for (int j = static_cast<int>(cur) - 1; j >= 0;) {
-                        const unsigned long long s = ldAcquire(&p.tileStatus[j]);
-                        if ((s >> 62) == 2) { excl += s & kValueMask; break; }
-                        if ((s >> 62) == 1) { excl += s & kValueMask; --j; }
-                    }
-                    stRelease(&p.tileStatus[cur], kFlagPrefix | (excl + tileTotal));
-                }
-                *sTileBase = excl;
-                if (cur == p.nTiles - 1) *p.totalMatches = excl + tileTotal;
-            }
-        }
-        // flush shared counters while the look-back spins
-        for (int i = tid; i < kWindowSlots * 8; i += kScanThreads) {
-            const uint32_t v = sWin[i];
-            if (v) atomicAdd(&p.windows[static_cast<size_t>(t.firstWin + (i >> 3)) * 8 + (i & 7)], v);
-        }
-        for (int i = tid; i < static_cast<int>(t.nCached) * 5; i += kScanThreads) {
-            const uint32_t v = sRegCnt[i];
-            if (v) atomicAdd(reinterpret_cast<uint32_t *>(p.itemCounts + sRegions[i / 5].item) + (i % 5), v);
-        }
-        __syncthreads();
+        // ---- compaction: one scan for all rows of the warp, then scatter into the queue ------------------
+        static_assert(kRowsPerWarp == 2, "candidate counts of the rows are scanned as two 16-bit fields");
+        uint32_t rowTotal[kRowsPerWarp], rowExcl[kRowsPerWarp];
+        uint32_t allTotal;
         {
-            const unsigned long long base = *sTileBase + sWarpCount[warp];
-            const uint32_t n = wMatches < p.scratchPerWarp ? wMatches : p.scratchPerWarp;
-            for (uint32_t i = lane; i < n; i += 32) {
-                const unsigned long long o = base + i;
-                if (o < p.matchCap) p.matches[o] = warpScratch[i];
+            const uint32_t incl = warpInclusiveScan(nCand);             // fields: row0 | row1 << 16 (<= 1536 each)
+            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), ex = incl - nCand;
+            rowTotal[0] = tot & 0xFFFFu; rowTotal[1] = tot >> 16;
+            rowExcl[0] = ex & 0xFFFFu; rowExcl[1] = ex >> 16;
+            allTotal = rowTotal[0] + rowTotal[1];
+        }
+        auto scatter = [&](uint32_t lo, uint32_t hi, uint32_t spanByte, uint32_t o) {
+            while (lo) { const int b = __ffs(lo) - 1; lo &= lo - 1; sQueue[o++] = static_cast<uint16_t>(spanByte + b); }
+            while (hi) { const int b = __ffs(hi) - 1; hi &= hi - 1; sQueue[o++] = static_cast<uint16_t>(spanByte + 32 + b); }
+        };
+        if (allTotal <= static_cast<uint32_t>(kQueueCap)) {
+            uint32_t base = 0;
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+                const uint32_t spanByte = (warp * kRowsPerWarp + rr) * kRowBytes + lane * kSpanBytes;
+                scatter(cand[rr][0], cand[rr][1], spanByte, base + rowExcl[rr]);
+                base += rowTotal[rr];
+            }
+            __syncwarp();
+            for (uint32_t from = 0; from < allTotal; from += 32) resolveBatch(from, min(32u, allTotal - from));
+        } else {
+            // dense tile: 11 lanes at a time (<= 528 candidates per step); lane groups keep genome order
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+                const uint32_t spanByte = (warp * kRowsPerWarp + rr) * kRowBytes + lane * kSpanBytes;
+                for (int part = 0; part < 3; ++part) {
+                    const bool mine = lane >= 11 * part && lane < 11 * (part + 1);
+                    const uint32_t lo = mine ? cand[rr][0] : 0u, hi = mine ? cand[rr][1] : 0u;
+                    const uint32_t n = __popc(lo) + __popc(hi);
+                    const uint32_t incl = warpInclusiveScan(n);
+                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    __syncwarp();
+                    scatter(lo, hi, spanByte, incl - n);
+                    __syncwarp();
+                    for (uint32_t from = 0; from < total; from += 32) resolveBatch(from, min(32u, total - from));
+                }
             }
         }
-        cur = nextTile;
+        if (lane == 0) {
+            p.slotCounts[slotIdx] = wMatches;
+            p.slotOv[slotIdx] = ovBase;
+        }
+
+        // ---- tile epilogue: flush the shared A/C/G/T counters ---------------------------------------------
+        __syncthreads();
+        if (COUNT) {
+            for (int i = tid; i < kWindowSlots * 4; i += kScanThreads) {
+                const uint32_t v = sWin[i];
+                if (v) atomicAdd(&p.windows[static_cast<size_t>(t.firstWin + (i >> 2)) * 8 + (i & 3)], v);
+            }
+        }
+        tCur = tNext; tNext = tNext2; rCur = rNext;
     }
 }
 
-// Explicit instantiations used by api.cu
-#define TLS_INST(N, C) template __global__ void scanKernel<N, C>(const ScanParams);
-TLS_INST(1, false) TLS_INST(1, true) TLS_INST(2, false) TLS_INST(2, true)
-TLS_INST(3, false) TLS_INST(3, true) TLS_INST(4, false) TLS_INST(4, true)
-#undef TLS_INST
-
 size_t scanSmemBytes() {
     return 65536 + kFlagTabBytes + 2 * (kTileSmemBytes + kTileHalo) + kScanWarps * kQueueCap * 2 +
-           kRegionCache * sizeof(DevRegion) + kRegionCache * 5 * 4 + kWindowSlots * 8 * 4 + kScanWarps * 4 +
-           2 * 8 + 8 + 16;
+           2 * kRegionCache * sizeof(DevRegion) + 2 * kWindowSlots * 4 * 4 + 2 * sizeof(TileMeta) + 2 * 8 + 64;
 }
 
 cudaError_t launchScan(const ScanParams &p, int grid, cudaStream_t stream) {

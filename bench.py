@@ -1,0 +1,393 @@
+#!/usr/bin/env python3
+"""bench.py — genome-wide telomeric motif scan throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale F]
+
+One "step" = one pass of the hot path (Teloscope::scanSegment in genome-wide mode, flags
+-r -g -e -m -i, -c TTAGGG -p TTAGGG,TCAGGG,TGAGGG,TTGGGG) over one synthetic human-shaped
+assembly: 24 chromosomes with GRCh38 lengths (3.09 Gbp), N-gaps (which split them into contigs),
+telomere caps + TVR, ITS islands, 10 % soft-masked.  Every rank scans its own assembly (weak
+scaling, no data-path collective); rank 0 prints ONE JSON line.
+
+  value    Gbp/s with the assembly already resident in HBM (device pointer handed to the C ABI),
+           everything else of the job included (kernels, result copies, host-side assembly)
+  e2e      same call with the sequence in pinned HOST memory: H2D + kernels + D2H in the timed region
+  roofline scan kernel only: algorithmic bytes / CUDA-event duration against the measured HBM peak
+  cpu_baseline  the unmodified reference binary (oracle/_ref/teloscope) on the box's host cores on
+           a 1/16-scale assembly of the same generator (file parsing and writers included: it has
+           no other entry point); falls back to the oracle port when the binary is absent
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "Gbp/s scanned (genome-wide mode)"
+PATTERNS = ["TTAGGG", "TCAGGG", "TGAGGG", "TTGGGG"]
+REF_FLAGS = ["-c", "TTAGGG", "-p", ",".join(PATTERNS), "-r", "-g", "-e", "-m", "-i"]
+GRCH38_MBP = [248.96, 242.19, 198.30, 190.21, 181.54, 170.81, 159.35, 145.14, 138.39, 133.80, 135.09, 133.28,
+              114.36, 107.04, 101.99, 90.34, 83.26, 80.37, 58.62, 64.44, 46.71, 50.82, 156.04, 57.23]
+CHR_NAMES = [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY"]
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic assembly (SURVEY.md §8d, S-human)
+# --------------------------------------------------------------------------------------------------
+def plan_assembly(seed: int, scale: float):
+    """Host-side plan: per chromosome the contig intervals (N-gaps removed) and the patches
+    (telomere caps, TVR, ITS) to stamp onto random sequence."""
+    rng = np.random.default_rng(seed)
+    variants = PATTERNS + [revcomp(p) for p in PATTERNS]
+    chroms = []
+    for name, mbp in zip(CHR_NAMES, GRCH38_MBP):
+        n = max(200_000, int(mbp * 1e6 * scale))
+        gaps = []
+        n_gaps = int(rng.integers(5, 31))
+        cen = int(rng.integers(1_000_000, 3_000_001) * min(1.0, scale * 4))
+        cen_start = int(n * rng.uniform(0.3, 0.6))
+        gaps.append((cen_start, max(1000, cen)))
+        for _ in range(n_gaps):
+            gaps.append((int(rng.integers(100_000, n - 100_000)), int(rng.integers(100, 50_001))))
+        gaps.sort()
+        contigs, pos = [], 0
+        for g, ln in gaps:
+            if g <= pos + 1000:
+                continue
+            contigs.append((pos, g))
+            pos = min(n, g + ln)
+        if pos < n - 1000:
+            contigs.append((pos, n))
+        patches = []   # (chromosome position, bytes)
+        def tvr(unit, bp):
+            out = bytearray()
+            while len(out) < bp:
+                u = bytearray(unit)
+                u[int(rng.integers(0, len(u)))] = b"ACGT"[int(rng.integers(0, 4))]
+                out += u
+            return bytes(out)
+        cap = int(rng.integers(2000, 15001)); tv = int(rng.integers(500, 2001))
+        patches.append((0, b"CCCTAA" * (cap // 6) + tvr(b"CCCTAA", tv)))
+        cap = int(rng.integers(2000, 15001)); tv = int(rng.integers(500, 2001))
+        tail = tvr(b"TTAGGG", tv) + b"TTAGGG" * (cap // 6)
+        patches.append((n - len(tail), tail))
+        for _ in range(int(rng.integers(20, 61))):
+            unit = variants[int(rng.integers(0, len(variants)))].encode()
+            reps = int(rng.integers(4, 41))
+            patches.append((int(rng.integers(200_000, n - 200_000)), unit * reps))
+        chroms.append({"name": name, "len": n, "contigs": contigs, "patches": patches})
+    return chroms
+
+
+def revcomp(s: str) -> str:
+    return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+
+
+def build_assembly(chroms, device, seed: int):
+    """-> (seq uint8 CUDA tensor with 4 KiB of slack, offsets[n+1], abs_pos[n]) : the contigs of all
+    chromosomes back to back, exactly what the reference's walkPath hands to scanSegment."""
+    import torch
+    offsets, abs_pos = [0], []
+    for c in chroms:
+        for a, b in c["contigs"]:
+            abs_pos.append(a)
+            offsets.append(offsets[-1] + (b - a))
+    total = offsets[-1]
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    seq = torch.empty(total + 4096, dtype=torch.uint8, device=device)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    step = 1 << 26
+    for s in range(0, total + 4096, step):
+        e = min(total + 4096, s + step)
+        seq[s:e] = lut[torch.randint(0, 4, (e - s,), device=device, generator=g, dtype=torch.int64)]
+    # stamp patches: translate chromosome coordinates to buffer coordinates (skip parts in gaps)
+    pos_list, val_list = [], []
+    k = 0
+    for c in chroms:
+        starts = np.array([a for a, _ in c["contigs"]]); ends = np.array([b for _, b in c["contigs"]])
+        base = np.array(offsets[k:k + len(starts)])
+        for p, data in c["patches"]:
+            idx = np.arange(p, p + len(data))
+            ci = np.searchsorted(starts, idx, side="right") - 1
+            ok = (ci >= 0) & (idx < ends[np.clip(ci, 0, len(ends) - 1)])
+            pos_list.append((base[ci[ok]] + (idx[ok] - starts[ci[ok]])).astype(np.int64))
+            val_list.append(np.frombuffer(data, dtype=np.uint8)[ok])
+        k += len(starts)
+    pos = torch.from_numpy(np.concatenate(pos_list)).to(device)
+    val = torch.from_numpy(np.concatenate(val_list)).to(device)
+    seq[pos] = val
+    # soft-mask ~10 % in stretches of 1-50 kb
+    rng = np.random.default_rng(seed + 1)
+    masked, target = 0, total // 10
+    while masked < target:
+        ln = int(rng.integers(1000, 50001)); a = int(rng.integers(0, max(1, total - ln)))
+        seq[a:a + ln] |= 0x20
+        masked += ln
+    return seq, np.array(offsets, dtype=np.uint64), np.array(abs_pos, dtype=np.uint64)
+
+
+def write_fasta(chroms, seq_host: np.ndarray, offsets: np.ndarray, path: Path) -> int:
+    """The same assembly as a FASTA file with its N-gaps (80-column lines) for the reference."""
+    k, bases = 0, 0
+    with open(path, "wb") as fh:
+        for c in chroms:
+            rec = np.full(c["len"], ord("N"), dtype=np.uint8)
+            for a, b in c["contigs"]:
+                rec[a:b] = seq_host[int(offsets[k]):int(offsets[k + 1])]
+                bases += b - a
+                k += 1
+            fh.write(b">" + c["name"].encode() + b"\n")
+            full = (len(rec) // 80) * 80
+            if full:
+                lines = np.empty((full // 80, 81), dtype=np.uint8)
+                lines[:, :80] = rec[:full].reshape(-1, 80)
+                lines[:, 80] = ord("\n")
+                fh.write(lines.tobytes())
+            if full < len(rec):
+                fh.write(rec[full:].tobytes() + b"\n")
+    return bases
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_run(sample_scale: float, steps: int, warmup: int, seed: int = 1234):
+    """Times the reference's own CPU implementation on a scaled-down assembly of the same generator.
+    Returns (Gbp/s, description dict)."""
+    import torch
+    cores = os.cpu_count() or 1
+    chroms = plan_assembly(seed, sample_scale)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    seq, offsets, abs_pos = build_assembly(chroms, dev, seed)
+    seq_host = seq.cpu().numpy()
+    del seq
+    ref_bin = ROOT / "oracle" / "_ref" / "teloscope"
+    tmp = Path(tempfile.mkdtemp(prefix="telo_ref_", dir="/dev/shm" if Path("/dev/shm").exists() else None))
+    try:
+        if ref_bin.exists():
+            fa = tmp / "sample.fa"
+            bases = write_fasta(chroms, seq_host, offsets, fa)
+            times = []
+            for i in range(warmup + steps):
+                out = tmp / f"out{i}"
+                out.mkdir()
+                t0 = time.perf_counter()
+                subprocess.run([str(ref_bin), "-f", str(fa), *REF_FLAGS, "-j", str(cores), "-o", str(out)],
+                               check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                dt = time.perf_counter() - t0
+                shutil.rmtree(out)
+                if i >= warmup:
+                    times.append(dt)
+            kind = "reference"
+            how = (f"oracle/_ref/teloscope (unmodified reference, g++ -O3) -j {cores} on a {sample_scale:g}-scale "
+                   f"assembly of the same generator: {bases / 1e6:.0f} Mbp in 24 records, page-cache-warm FASTA in "
+                   f"/dev/shm; wall time of the whole run (parse + scan + writers)")
+        else:
+            sys.path.insert(0, str(ROOT / "tests"))
+            import oracle_lib as ol
+            orc = ol.Oracle(ol.Config(patterns=PATTERNS))
+            bases = int(offsets[-1])
+            up = np.where((seq_host >= 97) & (seq_host <= 122), seq_host - 32, seq_host).astype(np.uint8)
+            times = []
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                orc.scan_many(up, offsets, False, cores)
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+            kind = "port"
+            how = (f"oracle port (oracle/oracle.cpp scanSegment) with {cores} threads, one job per contig, on a "
+                   f"{sample_scale:g}-scale assembly: {bases / 1e6:.0f} Mbp")
+        per_step = float(np.mean(times))
+        return bases / per_step / 1e9, per_step, {"kind": kind, "cores": cores, "sample": how}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.path = Path(tempfile.mkstemp(prefix="clocks_", suffix=".csv")[1])
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [l.split(", ") for l in self.path.read_text().splitlines() if l.count(",") >= 6]
+        self.path.unlink(missing_ok=True)
+        if rows:
+            sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+            out["sm_mhz"] = float(np.median(sm)) if sm else None
+            out["sm_max_mhz"] = float(rows[0][1]) if rows[0][1].replace(".", "").isdigit() else None
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = [n for i, n in enumerate(names) if any(r[3 + i].strip() == "Active" for r in rows)]
+            out["samples"] = len(rows)
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="assembly size factor (1.0 = 3.09 Gbp; tests use less)")
+    ap.add_argument("--cpu-scale", type=float, default=1.0 / 16, help="size factor of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=42)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"synthetic human-shaped assembly x{args.scale:g} (24 chromosomes, GRCh38 lengths, N-gaps, telomere caps, "
+                f"ITS, 10% soft-masked), -c TTAGGG -p {','.join(PATTERNS)} -r -g -e -m -i (124 patterns, w=s=1000)")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        gbps, per_step, desc = cpu_reference_run(args.cpu_scale, args.steps, args.warmup)
+        print(json.dumps({"metric": METRIC, "value": gbps, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "impl": "reference", "config": {"workload": workload},
+                          "cpu_baseline": {"value": gbps, "unit": "Gbp/s", **desc},
+                          "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import teloscope_b200 as tb
+    if not torch.cuda.is_available():
+        sys.exit("bench.py needs a B200; there is no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload: one assembly per rank --------------------------------------------------------------
+    chroms = plan_assembly(args.seed + rank, args.scale)
+    seq, offsets, abs_pos = build_assembly(chroms, f"cuda:{local}", args.seed + rank)
+    n_bases = int(offsets[-1])
+    host = torch.empty(seq.numel(), dtype=torch.uint8, pin_memory=True)
+    host.copy_(seq)
+    host_np = host.numpy()
+    sc = tb.Scanner(tb.ScanConfig(canonical="TTAGGG", patterns=PATTERNS, out_acgt=True, out_matches=True), device=local)
+
+    # collect(copy=False): results are read in place from the ctx's pinned buffers (what a C++ host
+    # would do through the C ABI); release() hands the ticket back
+    def step_device():
+        r = sc.collect(sc.submit(None, offsets, abs_pos, tb.MODE_GENOME, device_ptr=seq.data_ptr()), copy=False)
+        r.release()
+        return r
+
+    def step_host():
+        r = sc.collect(sc.submit(host_np[:n_bases], offsets, abs_pos, tb.MODE_GENOME), copy=False)
+        r.release()
+        return r
+
+    for _ in range(max(3, args.warmup)):
+        r = step_device()
+    n_windows, n_matches = int(r.window_off[-1]), r.n_matches
+
+    # ---- timed: device-resident input -------------------------------------------------------------------
+    clocks = ClockSampler(local) if rank == 0 else None
+    barrier()
+    t0 = time.perf_counter()
+    scan_ms, launches = [], 0
+    for _ in range(args.steps):
+        r = step_device()
+        scan_ms.append(r.scan_kernel_ms)
+        launches += r.n_kernel_launches
+    barrier()
+    elapsed = time.perf_counter() - t0
+    # ---- timed: end to end from pinned host memory ----------------------------------------------------
+    for _ in range(1):
+        r = step_host()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        r = step_host()
+    barrier()
+    elapsed_e2e = time.perf_counter() - t1
+    clk = clocks.stop() if clocks else None
+    d2h = n_windows * 32 + (len(r.canonical) + len(r.noncanonical)) * 16 + (len(r.terminal) + len(r.its)) * 48 + \
+        r.n_items * 32 + 192
+    h2d = n_bases + len(offsets) * 40 + (n_bases // 49136 + len(offsets)) * 16
+
+    t = torch.tensor([elapsed, elapsed_e2e, float(n_bases)], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        elapsed, elapsed_e2e, total_bases = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        total_bases = float(n_bases)
+    if rank == 0:
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        algo_bytes = n_bases + 32 * n_windows + 8 * n_matches
+        kern_s = float(np.mean(scan_ms)) * 1e-3
+        achieved = algo_bytes / kern_s / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": total_bases * args.steps / elapsed / 1e9, "unit": "Gbp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload, "bases_per_gpu": n_bases, "contigs_per_gpu": len(offsets) - 1,
+                       "windows_per_gpu": n_windows, "matches_per_gpu": n_matches, "sharding": "one assembly per GPU, no collective",
+                       "l2": "input (>= 3 GB at scale 1) is larger than the 126 MB L2; no flush needed"},
+            "e2e": {"value": total_bases * args.steps / elapsed_e2e / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "kernel_only": {"scan_kernel_ms": float(np.mean(scan_ms)), "Gbp_per_s": n_bases / kern_s / 1e9},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "tls::scanKernel<3,true>",
+                         "algorithmic_bytes": algo_bytes, "peak_source": peak_src},
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            gbps, _, desc = cpu_reference_run(args.cpu_scale, 1, 1)
+            line["cpu_baseline"] = {"value": gbps, "unit": "Gbp/s", **desc}
+        print(json.dumps(line))
+    sc.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

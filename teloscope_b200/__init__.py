@@ -165,16 +165,21 @@ class ScanConfig:
 
 
 class BatchResult:
-    """Per-item views of one collected batch (numpy copies; independent of the ctx)."""
+    """Per-item views of one collected batch.  With copy=True (default) the arrays are numpy copies
+    independent of the ctx; with copy=False they alias ctx-owned pinned memory and stay valid until
+    release() — the zero-copy path a host pipeline would use."""
 
-    def __init__(self, r: _Result):
+    def __init__(self, r: _Result, copy: bool = True, on_release=None):
         n = r.n_items
         self.n_items, self.mode = n, r.mode
+        self._on_release = on_release
 
         def arr(ptr, count, dt):
             if not ptr or count == 0:
                 return np.zeros(0, dtype=dt)
-            return np.frombuffer(C.string_at(ptr, int(count) * np.dtype(dt).itemsize), dtype=dt).copy()
+            nbytes = int(count) * np.dtype(dt).itemsize
+            view = np.frombuffer((C.c_char * nbytes).from_address(ptr), dtype=dt)
+            return view.copy() if copy else view
 
         def off(ptr):
             return arr(ptr, n + 1, "<u8") if ptr else np.zeros(n + 1, dtype="<u8")
@@ -198,6 +203,12 @@ class BatchResult:
         self.n_bases_scanned = int(r.n_bases_scanned)
         self.n_matches = int(r.n_matches)
         self.n_kernel_launches = int(r.n_kernel_launches)
+
+    def release(self):
+        """Give the ticket's buffers back to the ctx (only needed after collect(copy=False))."""
+        if self._on_release is not None:
+            self._on_release()
+            self._on_release = None
 
     def item(self, i: int) -> dict:
         """What SegmentData holds for item i (include/teloscope.h:139-148)."""
@@ -267,12 +278,18 @@ class Scanner:
         self._keep[t.value] = keep
         return t.value
 
-    def collect(self, ticket: int) -> BatchResult:
+    def collect(self, ticket: int, copy: bool = True) -> BatchResult:
         r = _Result()
         _check(self._L.tls_collect(self._h, ticket, C.byref(r)))
-        out = BatchResult(r)
-        _check(self._L.tls_release(self._h, ticket))
-        self._keep.pop(ticket, None)
+
+        def rel():
+            if self._h:
+                _check(self._L.tls_release(self._h, ticket))
+            self._keep.pop(ticket, None)
+
+        out = BatchResult(r, copy=copy, on_release=None if copy else rel)
+        if copy:
+            rel()
         return out
 
     def scan_batch(self, seqs: list[bytes], abs_pos=None, mode: int = MODE_GENOME) -> BatchResult:

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -30,6 +32,22 @@ int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+
+// TLS_TRACE=1 prints host-side phase timings of submit/collect to stderr (diagnostics only).
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(const char *what) : on(std::getenv("TLS_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {
+        if (on) fprintf(stderr, "[tls] %s:", what);
+    }
+    void mark(const char *phase) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, " %s=%.2fms", phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+    ~Trace() { if (on) fprintf(stderr, "\n"); }
+};
 
 #define TLS_CUDA(expr)                                                                         \
     do {                                                                                       \
@@ -85,7 +103,7 @@ struct Slot {
     std::vector<DevTile> tiles;
     const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
     HostBuf hSeq, hMeta;                      // pinned staging
-    DevBuf dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotCounts,
+    DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotCounts,
         dSlotOv, dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
     uint32_t ovCap = 0;
     // device counters block: [0] ovCursor(u32) [16] blockCount(u32) [24] selTotals(2 x u64)
@@ -96,7 +114,7 @@ struct Slot {
     // assembled results
     std::vector<uint64_t> terminalOff, itsOff, canOff, nonOff;
     std::vector<tls_block> terminal, its;
-    std::vector<tls_match> canonical, noncanonical;
+    uint64_t nSelCan = 0, nSelNon = 0;
     std::vector<uint32_t> nCan, nFwd, nRev;
     std::vector<uint8_t> pass;
     uint64_t nMatches = 0;
@@ -310,7 +328,7 @@ void tls_destroy(tls_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (Slot &s : ctx->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        for (DevBuf *b : {&s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
+        for (DevBuf *b : {&s.dAbsPos, &s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
                           &s.dMatches, &s.dSlots, &s.dSlotCounts, &s.dSlotOv, &s.dOvArena, &s.dTileBase, &s.dCounters,
                           &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch, &s.dSelCan, &s.dSelNon})
             b->release();
@@ -408,6 +426,7 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     if (si < 0) return fail(TLS_ERR_STATE, "two tickets already in flight");
     TLS_CUDA(cudaSetDevice(ctx->device));
     Slot &s = ctx->slot[si];
+    Trace tr("submit");
     const uint32_t n = b->n_items;
     const uint32_t T = ctx->cfg.terminal_limit, S = ctx->cfg.step;
     s.nItems = n; s.mode = b->mode; s.collected = false;
@@ -434,6 +453,7 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
         TLS_CUDA(cudaMemsetAsync(s.dSeq.as<uint8_t>() + s.seqBytes, 0, 256, s.stream));
         s.devSeq = s.dSeq.as<uint8_t>();
     }
+    tr.mark("stage_seq");
     const uint64_t devBase = b->seq_on_device ? 0 : base;   // offsets are relative to devSeq after this shift
 
     // ---- read mode: drop one trailing '\r' per read (src/read-filter.cpp:38-40) -------------------
@@ -491,14 +511,19 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
         }
     }
 
+    tr.mark("plan");
     // ---- upload metadata ------------------------------------------------------------------------
     const size_t bRegions = s.regions.size() * sizeof(DevRegion), bTiles = s.tiles.size() * sizeof(DevTile),
-                 bLen = static_cast<size_t>(n) * 4;
-    TLS_CUDA(s.hMeta.reserve(bRegions + bTiles + bLen + 64));
+                 bLen = static_cast<size_t>(n) * 4, bAbs = static_cast<size_t>(n) * 8;
+    TLS_CUDA(s.hMeta.reserve(bRegions + bTiles + bLen + bAbs + 64));
     uint8_t *hm = s.hMeta.as<uint8_t>();
     if (bRegions) std::memcpy(hm, s.regions.data(), bRegions);
     if (bTiles) std::memcpy(hm + bRegions, s.tiles.data(), bTiles);
     if (bLen) std::memcpy(hm + bRegions + bTiles, s.itemLen.data(), bLen);
+    const size_t absOff = (bRegions + bTiles + bLen + 7) & ~size_t(7);
+    if (bAbs) std::memcpy(hm + absOff, s.absPos.data(), bAbs);
+    TLS_CUDA(s.dAbsPos.reserve(std::max<size_t>(bAbs, 16)));
+    if (bAbs) TLS_CUDA(cudaMemcpyAsync(s.dAbsPos.p, hm + absOff, bAbs, cudaMemcpyHostToDevice, s.stream));
     TLS_CUDA(s.dRegions.reserve(std::max<size_t>(bRegions, 16)));
     TLS_CUDA(s.dTiles.reserve(std::max<size_t>(bTiles, 16)));
     TLS_CUDA(s.dItemLen.reserve(std::max<size_t>(bLen, 16)));
@@ -515,7 +540,9 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     if (b->mode == TLS_MODE_READS && b->seq_on_device)
         TLS_CUDA(launchTrimCr(s.devSeq, s.dRegions.as<DevRegion>(), static_cast<uint32_t>(s.regions.size()),
                               s.dItemLen.as<uint32_t>(), s.stream));
+    tr.mark("alloc_meta");
     if ((rc = enqueueScan(ctx, s))) return rc;
+    tr.mark("enqueue");
     s.busy = true;
     *ticket = si;
     return TLS_OK;
@@ -528,6 +555,7 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
     Slot &s = ctx->slot[ticket];
     const uint32_t n = s.nItems;
     int rc;
+    Trace tr("collect");
     if (!s.collected) {
         // ---- wait for the scan; grow the overflow arena and rerun if it ran out --------------------
         for (;;) {
@@ -538,6 +566,7 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             s.ovCap = ovUsed + ovUsed / 4;
             if ((rc = enqueueScan(ctx, s))) return rc;
         }
+        tr.mark("wait_scan");
         // ---- slots -> one ordered list ------------------------------------------------------------------
         s.matchCap = std::max<uint64_t>(s.matchCap, s.nMatches);
         TLS_CUDA(s.dMatches.reserve(std::max<uint64_t>(s.matchCap, 1) * sizeof(DevMatch)));
@@ -582,23 +611,27 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             s.blockCap = nBlocks + nBlocks / 8 + 64;
         }
         if (reads) nBlocks = 0;
+        tr.mark("gather_blocks");
 
         // ---- -m lists --------------------------------------------------------------------------------
         unsigned long long selTotals[2] = {0, 0};
         if (wantSel) {
             const uint32_t capSel = static_cast<uint32_t>(std::min<uint64_t>(s.nMatches, 0xFFFFFFFFull));
             TLS_CUDA(s.dSelScratch.reserve(static_cast<size_t>(selectChunks(s.nMatches)) * 8 + 16));
-            TLS_CUDA(s.dSelCan.reserve(static_cast<size_t>(capSel) * sizeof(DevMatch)));
-            TLS_CUDA(s.dSelNon.reserve(static_cast<size_t>(capSel) * sizeof(DevMatch)));
+            // exact sizes are known from the per-item counters only after a copy; bound them instead:
+            // canonical + terminal non-canonical records never exceed the match count
+            TLS_CUDA(s.dSelCan.reserve(static_cast<size_t>(capSel) * sizeof(tls_match)));
+            TLS_CUDA(s.dSelNon.reserve(static_cast<size_t>(capSel) * sizeof(tls_match)));
             uint8_t *cnt = s.dCounters.as<uint8_t>();
             TLS_CUDA(launchSelect(s.dMatches.as<DevMatch>(), s.nMatches, s.dSelScratch.as<uint32_t>(),
-                                  reinterpret_cast<unsigned long long *>(cnt + 24), s.dSelCan.as<DevMatch>(), capSel,
-                                  s.dSelNon.as<DevMatch>(), capSel, s.stream));
+                                  reinterpret_cast<unsigned long long *>(cnt + 24), s.dItemBegin.as<unsigned long long>(),
+                                  s.dAbsPos.as<unsigned long long>(), n, s.dSelCan.p, capSel, s.dSelNon.p, capSel, s.stream));
             s.launches += 3;
             TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 64, cudaMemcpyDeviceToHost, s.stream));
             TLS_CUDA(cudaStreamSynchronize(s.stream));
             std::memcpy(selTotals, s.hCounters.as<uint8_t>() + 24, 16);
         }
+        tr.mark("select");
         TLS_CUDA(cudaEventRecord(s.evAll1, s.stream));
 
         // ---- copy results back ------------------------------------------------------------------------
@@ -620,20 +653,22 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             TLS_CUDA(s.hPass.reserve(n));
             TLS_CUDA(cudaMemcpyAsync(s.hPass.p, s.dPass.p, n, cudaMemcpyDeviceToHost, s.stream));
         }
+        s.nSelCan = selTotals[0]; s.nSelNon = selTotals[1];
         if (selTotals[0]) {
-            TLS_CUDA(s.hSelCan.reserve(selTotals[0] * sizeof(DevMatch)));
-            TLS_CUDA(cudaMemcpyAsync(s.hSelCan.p, s.dSelCan.p, selTotals[0] * sizeof(DevMatch), cudaMemcpyDeviceToHost, s.stream));
+            TLS_CUDA(s.hSelCan.reserve(selTotals[0] * sizeof(tls_match)));
+            TLS_CUDA(cudaMemcpyAsync(s.hSelCan.p, s.dSelCan.p, selTotals[0] * sizeof(tls_match), cudaMemcpyDeviceToHost, s.stream));
         }
         if (selTotals[1]) {
-            TLS_CUDA(s.hSelNon.reserve(selTotals[1] * sizeof(DevMatch)));
-            TLS_CUDA(cudaMemcpyAsync(s.hSelNon.p, s.dSelNon.p, selTotals[1] * sizeof(DevMatch), cudaMemcpyDeviceToHost, s.stream));
+            TLS_CUDA(s.hSelNon.reserve(selTotals[1] * sizeof(tls_match)));
+            TLS_CUDA(cudaMemcpyAsync(s.hSelNon.p, s.dSelNon.p, selTotals[1] * sizeof(tls_match), cudaMemcpyDeviceToHost, s.stream));
         }
         TLS_CUDA(cudaStreamSynchronize(s.stream));
         TLS_CUDA(cudaEventElapsedTime(&s.allMs, s.evAll0, s.evAll1));
+        tr.mark("d2h");
 
         // ---- assemble per-item views ----------------------------------------------------------------------
         s.terminalOff.assign(n + 1, 0); s.itsOff.assign(n + 1, 0); s.canOff.assign(n + 1, 0); s.nonOff.assign(n + 1, 0);
-        s.terminal.clear(); s.its.clear(); s.canonical.clear(); s.noncanonical.clear();
+        s.terminal.clear(); s.its.clear();
         s.nCan.assign(n, 0); s.nFwd.assign(n, 0); s.nRev.assign(n, 0);
         s.pass.assign(n, 0);
         if (reads && n) std::memcpy(s.pass.data(), s.hPass.p, n);
@@ -663,28 +698,15 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             }
         }
         for (uint32_t i = 0; i < n; ++i) { s.terminalOff[i + 1] += s.terminalOff[i]; s.itsOff[i + 1] += s.itsOff[i]; }
-        auto convMatches = [&](const DevMatch *src, uint64_t cnt, std::vector<tls_match> &dst, std::vector<uint64_t> &off,
-                               bool canon) -> int {
-            dst.resize(cnt);
-            uint64_t k = 0;
-            for (uint32_t i = 0; i < n; ++i) {
-                off[i] = k;
-                const uint64_t c = canon ? ic[i].can : ic[i].nonCanTerm;
-                if (k + c > cnt) return fail(TLS_ERR_STATE, "internal: match list shorter than per-item counts");
-                for (uint64_t j = 0; j < c; ++j, ++k) {
-                    tls_match m{};
-                    m.pos = s.absPos[i] + src[k].pos; m.len = src[k].len;
-                    m.is_forward = src[k].flags & kMatchFwd ? 1 : 0; m.is_canonical = src[k].flags & kMatchCan ? 1 : 0;
-                    dst[k] = m;
-                }
-            }
-            off[n] = k;
-            return TLS_OK;
-        };
         if (wantSel) {
-            if ((rc = convMatches(s.hSelCan.as<DevMatch>(), selTotals[0], s.canonical, s.canOff, true))) return rc;
-            if ((rc = convMatches(s.hSelNon.as<DevMatch>(), selTotals[1], s.noncanonical, s.nonOff, false))) return rc;
+            // the device wrote final records; only the per-item offsets are left to the host
+            uint64_t kc = 0, kn = 0;
+            for (uint32_t i = 0; i < n; ++i) { s.canOff[i] = kc; s.nonOff[i] = kn; kc += ic[i].can; kn += ic[i].nonCanTerm; }
+            s.canOff[n] = kc; s.nonOff[n] = kn;
+            if (kc != s.nSelCan || kn != s.nSelNon)
+                return fail(TLS_ERR_STATE, "internal: selected match lists disagree with the per-item counters");
         }
+        tr.mark("assemble");
         s.collected = true;
     }
     std::memset(res, 0, sizeof *res);
@@ -693,8 +715,8 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
     res->windows = s.hWindows.as<tls_window>();
     res->terminal_off = s.terminalOff.data(); res->terminal = s.terminal.data();
     res->its_off = s.itsOff.data(); res->its = s.its.data();
-    res->canonical_off = s.canOff.data(); res->canonical = s.canonical.data();
-    res->noncanonical_off = s.nonOff.data(); res->noncanonical = s.noncanonical.data();
+    res->canonical_off = s.canOff.data(); res->canonical = s.nSelCan ? s.hSelCan.as<tls_match>() : nullptr;
+    res->noncanonical_off = s.nonOff.data(); res->noncanonical = s.nSelNon ? s.hSelNon.as<tls_match>() : nullptr;
     res->n_canonical = s.nCan.data(); res->n_fwd = s.nFwd.data(); res->n_rev = s.nRev.data();
     res->pass = s.pass.data();
     res->scan_kernel_ms = s.scanMs; res->device_ms = s.allMs;

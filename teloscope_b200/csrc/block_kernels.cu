@@ -468,27 +468,56 @@ __global__ void __launch_bounds__(1024) selectScanKernel(uint32_t *chunkCounts, 
     if (tid < 2) totals[tid] = carry[tid];
 }
 
+// Final host-visible match record (same layout as tls_match in include/teloscope_b200.h).
+struct OutMatch {
+    unsigned long long pos;
+    uint16_t len;
+    uint8_t isForward, isCanonical;
+    uint32_t pad;
+};
+static_assert(sizeof(OutMatch) == 16, "tls_match layout");
+
 __global__ void __launch_bounds__(32) selectWriteKernel(const DevMatch *m, unsigned long long n, const uint32_t *chunkOffsets,
-                                                         DevMatch *outCan, uint32_t capCan, DevMatch *outNon, uint32_t capNon) {
+                                                        const unsigned long long *itemBegin, const unsigned long long *absPos,
+                                                        uint32_t nItems, OutMatch *outCan, uint32_t capCan, OutMatch *outNon,
+                                                        uint32_t capNon) {
     // one warp walks the chunk in order so the output order equals the input order
     const unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * kSelChunk;
     const int lane = threadIdx.x;
     uint32_t oc = chunkOffsets[2 * blockIdx.x], on = chunkOffsets[2 * blockIdx.x + 1];
+    // item of the chunk's first match: last i with itemBegin[i] <= base
+    uint32_t lo = 0, hi = nItems;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (itemBegin[mid] <= base) lo = mid + 1; else hi = mid;
+    }
+    uint32_t item = lo - 1;
     for (int i = 0; i < kSelChunk; i += 32) {
         const unsigned long long k = base + i + lane;
         DevMatch x{};
         bool isC = false, isN = false;
+        unsigned long long ap = 0;
         if (k < n) {
             x = m[k];
             isC = (x.flags & kMatchCan) != 0;
             isN = (x.flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
+            if (isC || isN) {
+                uint32_t it = item;
+                while (k >= itemBegin[it + 1]) ++it;
+                ap = absPos[it];
+            }
         }
         const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
         const uint32_t below = (1u << lane) - 1u;
-        if (isC) { const uint32_t o = oc + __popc(bc & below); if (o < capCan) outCan[o] = x; }
-        if (isN) { const uint32_t o = on + __popc(bn & below); if (o < capNon) outNon[o] = x; }
+        OutMatch o;
+        o.pos = ap + x.pos; o.len = x.len; o.isForward = x.flags & kMatchFwd ? 1 : 0; o.isCanonical = isC ? 1 : 0; o.pad = 0;
+        if (isC) { const uint32_t q = oc + __popc(bc & below); if (q < capCan) outCan[q] = o; }
+        if (isN) { const uint32_t q = on + __popc(bn & below); if (q < capNon) outNon[q] = o; }
         oc += __popc(bc);
         on += __popc(bn);
+        // advance the chunk's item cursor past items that end before the next 32 matches
+        const unsigned long long nextK = base + i + 32;
+        while (item + 1 < nItems && nextK >= itemBegin[item + 1]) ++item;
     }
 }
 
@@ -512,12 +541,14 @@ cudaError_t launchIts(const BlockParams &p, unsigned long long nMatches, cudaStr
 uint32_t selectChunks(unsigned long long n) { return static_cast<uint32_t>((n + kSelChunk - 1) / kSelChunk); }
 
 cudaError_t launchSelect(const DevMatch *m, unsigned long long n, uint32_t *chunkScratch, unsigned long long *totals,
-                         DevMatch *outCan, uint32_t capCan, DevMatch *outNon, uint32_t capNon, cudaStream_t s) {
+                         const unsigned long long *itemBegin, const unsigned long long *absPos, uint32_t nItems,
+                         void *outCan, uint32_t capCan, void *outNon, uint32_t capNon, cudaStream_t s) {
     const uint32_t chunks = selectChunks(n);
     if (chunks == 0) return cudaSuccess;
     selectCountKernel<<<chunks, 256, 0, s>>>(m, n, chunkScratch);
     selectScanKernel<<<1, 1024, 0, s>>>(chunkScratch, chunks, totals);
-    selectWriteKernel<<<chunks, 32, 0, s>>>(m, n, chunkScratch, outCan, capCan, outNon, capNon);
+    selectWriteKernel<<<chunks, 32, 0, s>>>(m, n, chunkScratch, itemBegin, absPos, nItems, static_cast<OutMatch *>(outCan),
+                                            capCan, static_cast<OutMatch *>(outNon), capNon);
     return cudaGetLastError();
 }
 

@@ -20,8 +20,10 @@ cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s);
 cudaError_t launchIts(const BlockParams &p, unsigned long long nMatches, cudaStream_t s);
 
 uint32_t selectChunks(unsigned long long nMatches);
-// chunkScratch: 2 * selectChunks(n) u32; totals: 2 u64 (canonical, terminal non-canonical)
+// chunkScratch: 2 * selectChunks(n) u32; totals: 2 u64 (canonical, terminal non-canonical);
+// outCan / outNon receive final 16-byte tls_match records (absPos of the item added)
 cudaError_t launchSelect(const DevMatch *m, unsigned long long n, uint32_t *chunkScratch, unsigned long long *totals,
-                         DevMatch *outCan, uint32_t capCan, DevMatch *outNon, uint32_t capNon, cudaStream_t s);
+                         const unsigned long long *itemBegin, const unsigned long long *absPos, uint32_t nItems,
+                         void *outCan, uint32_t capCan, void *outNon, uint32_t capNon, cudaStream_t s);
 
 }  // namespace tls

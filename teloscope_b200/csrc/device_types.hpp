@@ -18,7 +18,9 @@ constexpr int kTileMaxLen = kTileSmemBytes - 16;  // leaves room for the alignme
 constexpr int kQueueCap = 544;                    // per-warp candidate queue (u16 entries)
 constexpr int kRegionCache = 32;                  // regions of a tile kept in shared memory
 constexpr uint32_t kNoOverflow = 0xFFFFFFFFu;
-constexpr int kWindowSlots = 128;                 // per-tile window counter slots in shared memory
+constexpr int kWindowSlots = 128;                 // per-tile window counter slots in shared memory (8 counters each)
+constexpr int kPackedWords = kRowsPerWarp * (kRowBytes / 16) + 8;   // per-warp 2-bit copy of its rows + halo
+constexpr uint32_t kMinFastWindow = 64;           // fast path: at most one window boundary per lane span
 constexpr int kFlagTabBytes = 24576;              // direct stage-2 tables (sum 4^len, len<=7)
 
 // A maximal stretch of one item inside which matches must lie entirely

@@ -16,6 +16,12 @@
 //   4. A/C/G/T window counts come from popcounts on the packed codes (src/teloscope.cpp:418-435);
 //   5. match records go, in genome order, to the (tile, warp) slot of a global arena; a later
 //      scan + gather pass (block_kernels.cu) compacts the slots into one ordered list.
+// Tiles that lie inside one contig of a genome-mode batch with a single pattern length (the
+// north-star configuration) take a lean path: span validity is established once per lane with
+// two multiplies per word, candidates are therefore exact matches, window-end / region-end
+// truncation is applied to the candidate bitmap of the few lanes that straddle a boundary, the
+// 2-bit codes are kept per warp in shared memory for the flag lookup, and window / item
+// accounting is done on warp ballots.  Everything else takes the general path.
 // No tensor cores: this is byte/integer streaming work bound by instruction issue and HBM.
 #include <cuda_runtime.h>
 
@@ -97,6 +103,33 @@ __device__ __forceinline__ uint32_t badChunk(const uint4 &v) {
     return (rel & 0x10101010u) | (anyOr & 0x88888888u) | (~allAnd & 0x40404040u);
 }
 
+// Lean validity accumulators for the fast path.  For a byte c in ACGTacgt: bit7=0, bit6=1, bit3=0,
+// bit4 = (bit2 & ~bit1) ("is T") and bit0 = ~bit4.  With m = c & 6 in {0,2,4,6} the product
+// 6*m + 0x40 has bit7=0, bit6=1 and bit4 set only for m == 4 (T), so (y ^ w) must be zero in
+// bits 7,6,4; (w<<4) ^ w must have bit4 set (bit0 != bit4); bit3 is OR-accumulated.
+struct ValidAcc {
+    uint32_t a1 = 0, a2 = 0xFFFFFFFFu, any = 0;
+    __device__ __forceinline__ void add(uint32_t w, uint32_t m) {
+        const uint32_t y = m * 6u + 0x40404040u;
+        const uint32_t z = w * 16u;
+        a1 |= y ^ w;
+        a2 &= z ^ w;
+        any |= w;
+    }
+    __device__ __forceinline__ uint32_t bad() const {
+        return (a1 & 0xD0D0D0D0u) | (~a2 & 0x10101010u) | (any & 0x08080808u);
+    }
+};
+__device__ __forceinline__ uint32_t packWord(uint32_t w, ValidAcc &v) {
+    const uint32_t m = w & 0x06060606u;
+    v.add(w, m);
+    return m * 0x00820820u;
+}
+__device__ __forceinline__ uint32_t pack16v(const uint4 &q, ValidAcc &v) {
+    const uint32_t a = packWord(q.x, v), b = packWord(q.y, v), c = packWord(q.z, v), d = packWord(q.w, v);
+    return __byte_perm(__byte_perm(a, b, 0x0073), __byte_perm(c, d, 0x0073), 0x5410);
+}
+
 __device__ __forceinline__ bool isBase(uint32_t c) {
     c &= 0xDFu;
     return c == 'A' || c == 'C' || c == 'G' || c == 'T';
@@ -116,6 +149,10 @@ struct TileMeta {
     uint32_t firstWin;      // window index of shared counter slot 0
     uint32_t single;        // 1: region 0 covers the whole tile
     uint32_t relBase;       // single: item-relative position of tile byte 0
+    uint32_t fast;          // 1: lean path (single region, genome mode, one direct pattern length)
+    uint32_t termMixed;     // fast: 1 when matches of this tile can be "terminal" (src/teloscope.cpp:451-459)
+    uint32_t regionEndQ;    // fast: tile position one past the region's last base
+    uint32_t item, itemLen, winBase;
 };
 
 struct Located {
@@ -202,9 +239,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
     uint8_t *sTile = sFlags + kFlagTabBytes;
     constexpr int kTileStride = kTileSmemBytes + kTileHalo;
     uint16_t *sQueueAll = reinterpret_cast<uint16_t *>(sTile + 2 * kTileStride);
-    DevRegion *sRegionsAll = reinterpret_cast<DevRegion *>(sQueueAll + kScanWarps * kQueueCap);   // [2][cache]
-    uint32_t *sWinAll = reinterpret_cast<uint32_t *>(sRegionsAll + 2 * kRegionCache);              // [2][slots][4]
-    TileMeta *sMetaAll = reinterpret_cast<TileMeta *>(sWinAll + 2 * kWindowSlots * 4);             // [2]
+    uint32_t *sPackedAll = reinterpret_cast<uint32_t *>(sQueueAll + kScanWarps * kQueueCap);      // [warps][kPackedWords]
+    DevRegion *sRegionsAll = reinterpret_cast<DevRegion *>(sPackedAll + kScanWarps * kPackedWords);  // [2][cache]
+    uint32_t *sWinAll = reinterpret_cast<uint32_t *>(sRegionsAll + 2 * kRegionCache);              // [2][slots][8]
+    uint32_t *sItemAll = sWinAll + 2 * kWindowSlots * 8;                                           // [2][8]
+    TileMeta *sMetaAll = reinterpret_cast<TileMeta *>(sItemAll + 2 * 8);                           // [2]
     uint64_t *sBar = reinterpret_cast<uint64_t *>(sMetaAll + 2);                                   // [2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -237,6 +276,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
         const uint32_t idx = min(t.firstRegion + static_cast<uint32_t>(lane), p.nRegions - 1);
         return p.regions[idx];
     };
+    const bool fastConfig = cfg.mode == 0 && cfg.nClasses == 1 && cfg.cls[0].direct != 0 &&
+                            cfg.windowSize >= kMinFastWindow && cfg.cls[0].len + NPOS <= 9;
 
     const uint32_t G = gridDim.x;
     uint32_t tileIdx = blockIdx.x;
@@ -252,7 +293,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
         const int buf = iter & 1;
         const uint8_t *tile = sTile + buf * kTileStride;
         DevRegion *sRegions = sRegionsAll + buf * kRegionCache;
-        uint32_t *sWin = sWinAll + buf * kWindowSlots * 4;
+        uint32_t *sWin = sWinAll + buf * kWindowSlots * 8;
+        uint32_t *sItem = sItemAll + buf * 8;
         const bool hasNext = tileIdx + G < p.nTiles;
 
         // ---- prefetch: data of tile k+1, descriptor of k+2, regions of k+1 (all consumed later) ----
@@ -276,11 +318,19 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                 const uint32_t relFirst = rCur.relStart + static_cast<uint32_t>(s - rCur.bufStart);
                 m.relBase = rCur.relStart + static_cast<uint32_t>(tCur.bufStart - rCur.bufStart);   // valid if single
                 m.firstWin = (cfg.mode == 0 && n > 0) ? rCur.winBase + divWindow(cfg, relFirst) : 0;
+                m.fast = fastConfig && m.single;
+                m.item = rCur.item; m.itemLen = rCur.itemLen; m.winBase = rCur.winBase;
+                m.regionEndQ = rCur.relStart + rCur.len - m.relBase;
+                // no position of the tile is <= T or >= n - T  ->  no match of it is "terminal"
+                const uint32_t T = cfg.terminalLimit, nIt = rCur.itemLen;
+                const uint32_t termEnd = nIt > T ? nIt - T : 0;
+                m.termMixed = !(m.relBase > T && static_cast<uint64_t>(m.relBase) + m.len <= termEnd);
                 sMetaAll[buf] = m;
             }
         }
-        if (COUNT)
-            for (int i = tid; i < kWindowSlots * 4; i += kScanThreads) sWin[i] = 0;
+        for (int i = tid; i < kWindowSlots * 8 + 8; i += kScanThreads) {
+            if (i < kWindowSlots * 8) sWin[i] = 0; else sItem[i - kWindowSlots * 8] = 0;
+        }
         __syncthreads();
         const TileMeta t = sMetaAll[buf];
         const uint32_t skew = static_cast<uint32_t>(t.bufStart & 15ull);
@@ -296,22 +346,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
 
         auto addAcgt = [&](uint32_t win, uint32_t a, uint32_t c, uint32_t g, uint32_t tt) {   // one lane
             const uint32_t s = win - t.firstWin;
-            if (s < kWindowSlots) {
-                uint32_t *w = sWin + s * 4;
-                if (a) atomicAdd(w + 0, a);
-                if (c) atomicAdd(w + 1, c);
-                if (g) atomicAdd(w + 2, g);
-                if (tt) atomicAdd(w + 3, tt);
-            } else {
-                uint32_t *w = p.windows + static_cast<size_t>(win) * 8;
-                if (a) atomicAdd(w + 0, a);
-                if (c) atomicAdd(w + 1, c);
-                if (g) atomicAdd(w + 2, g);
-                if (tt) atomicAdd(w + 3, tt);
-            }
+            uint32_t *w = s < kWindowSlots ? sWin + s * 8 : p.windows + static_cast<size_t>(win) * 8;
+            if (a) atomicAdd(w + 0, a);
+            if (c) atomicAdd(w + 1, c);
+            if (g) atomicAdd(w + 2, g);
+            if (tt) atomicAdd(w + 3, tt);
         };
 
-        // ---- stage 2: verify up to 32 queued candidates and emit match records ---------------------
+        // ---- stage 2 (general): verify up to 32 queued candidates and emit match records -------------
         auto resolveBatch = [&](uint32_t from, uint32_t count) {
             uint32_t hitMask = 0, flagBits = 0, rel = 0, region = 0, termBit = 0;
             if (lane < static_cast<int>(count)) {
@@ -429,10 +471,196 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
             wMatches += total;
         };
 
-        // ---- main loop over this warp's rows ------------------------------------------------------
         const uint32_t usedBytes = skew + t.len;
         uint32_t cand[kRowsPerWarp][2];
-        uint32_t nCand = 0;                                  // packed per-row candidate counts of this lane
+        static_assert(kRowsPerWarp == 2, "candidate counts of the rows are scanned as two 16-bit fields");
+        bool fastResolve = false;
+
+        if (t.fast) {
+            // =====================================================================================
+            // Lean path: the tile lies inside one contig (genome mode, one direct pattern length)
+            // =====================================================================================
+            const uint32_t L = cfg.cls[0].len;
+            const uint32_t blockByte = warp * (kRowsPerWarp * kRowBytes);
+            uint32_t *sPk = sPackedAll + warp * kPackedWords;
+            // match starts are allowed at tile positions [0, candLimitQ): inside the tile and with
+            // the whole match inside the region (src/teloscope.cpp:439 scanLimit)
+            const uint32_t candLimitQ = min(t.len, t.regionEndQ >= L ? t.regionEndQ - (L - 1) : 0u);
+            uint32_t W[kRowsPerWarp][4];
+            uint32_t totAC[kRowsPerWarp], totGT[kRowsPerWarp];     // A | C << 16, G | T << 16 of the whole span
+            uint32_t notPlain = 0;                                   // bit rr: span of row rr needs the fix-up pass
+            bool laneBad = false;
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+                cand[rr][0] = cand[rr][1] = 0;
+                W[rr][0] = W[rr][1] = W[rr][2] = W[rr][3] = 0;
+                totAC[rr] = totGT[rr] = 0;
+                const uint32_t rowByte = blockByte + rr * kRowBytes;
+                if (rowByte >= usedBytes + kTileHalo) continue;              // warp-uniform
+                const uint32_t spanByte = rowByte + lane * kSpanBytes;
+                const uint4 *src = reinterpret_cast<const uint4 *>(tile + spanByte);
+                const uint4 c0 = src[0], c1 = src[1], c2 = src[2];
+                ValidAcc va;
+                W[rr][0] = pack16v(c0, va); W[rr][1] = pack16v(c1, va); W[rr][2] = pack16v(c2, va);
+                const bool inRange = spanByte < usedBytes + kTileHalo;
+                if (inRange && va.bad()) { laneBad = true; notPlain |= 1u << rr; }
+                sPk[rr * (kRowBytes / 16) + lane * 3 + 0] = W[rr][0];
+                sPk[rr * (kRowBytes / 16) + lane * 3 + 1] = W[rr][1];
+                sPk[rr * (kRowBytes / 16) + lane * 3 + 2] = W[rr][2];
+            }
+            // ---- halo word of every span: the next lane's first word; the block's last span reads ahead
+            {
+                uint32_t tail = 0;
+                if (lane == 31) {
+                    const uint32_t endByte = blockByte + kRowsPerWarp * kRowBytes;   // 8-byte aligned
+                    if (endByte < usedBytes + kTileHalo) {
+                        const uint2 h = *reinterpret_cast<const uint2 *>(tile + endByte);
+                        ValidAcc va;
+                        tail = (packWord(h.x, va) >> 24) | ((packWord(h.y, va) >> 24) << 8);
+                        if (va.bad()) laneBad = true;
+                    }
+                    sPk[kRowsPerWarp * (kRowBytes / 16)] = tail;
+                }
+                const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, lane == 0 ? W[1][0] : W[0][0], (lane + 1) & 31);
+                const uint32_t n1 = __shfl_down_sync(0xFFFFFFFFu, W[1][0], 1);
+                W[0][3] = n0;
+                W[1][3] = lane == 31 ? tail : n1;
+            }
+            const bool warpBad = __any_sync(0xFFFFFFFFu, laneBad);
+
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+                const uint32_t rowByte = blockByte + rr * kRowBytes;
+                if (rowByte >= usedBytes) continue;                            // warp-uniform
+                // ---- stage 1: one table byte per NPOS start positions ---------------------------------
+                uint32_t candLo = 0, candHi = 0;
+#pragma unroll
+                for (int tl = 0; tl < kSpanBytes / NPOS; ++tl) {
+                    const int bit = 2 * NPOS * tl, wi = bit >> 5, sh = bit & 31;
+                    const uint32_t x = sh == 0 ? W[rr][wi] : (sh <= 16 ? W[rr][wi] >> sh : __funnelshift_r(W[rr][wi], W[rr][wi + 1], sh));
+                    const uint32_t e = sIndex[x & 0xFFFFu];
+                    const int pos = NPOS * tl;
+                    if (pos < 32) {
+                        candLo |= e << pos;
+                        if (pos + NPOS > 32) candHi |= e >> (32 - pos);
+                    } else {
+                        candHi |= e << (pos - 32);
+                    }
+                }
+                candHi &= 0xFFFFu;
+                // ---- lane classification -----------------------------------------------------------------
+                const int q0 = static_cast<int>(rowByte + lane * kSpanBytes) - static_cast<int>(skew);
+                const uint32_t relA = t.relBase + static_cast<uint32_t>(q0);
+                const uint32_t winA = divWindow(cfg, relA);
+                const uint32_t toNext = (winA + 1) * cfg.windowSize - relA;    // exact in 32-bit wrap arithmetic
+                const bool plain = q0 >= 0 && q0 + kSpanBytes <= static_cast<int>(candLimitQ) &&
+                                   toNext >= static_cast<uint32_t>(kSpanBytes) + L - 1 && !((notPlain >> rr) & 1u);
+                if (!plain) notPlain |= 1u << rr;
+                cand[rr][0] = candLo; cand[rr][1] = candHi;
+                if (COUNT) {
+                    // ---- A/C/G/T of the whole span: bit planes of 32 + 16 bases ----------------------------
+                    const uint32_t w0 = W[rr][0], w1 = W[rr][1], w2 = W[rr][2];
+                    const uint32_t e01 = (w0 & 0x55555555u) | ((w1 << 1) & 0xAAAAAAAAu);   // bit1 of the codes: C or G
+                    const uint32_t o01 = ((w0 >> 1) & 0x55555555u) | (w1 & 0xAAAAAAAAu);   // bit2 of the codes: G or T
+                    const uint32_t e2 = w2 & 0x55555555u, o2 = (w2 >> 1) & 0x55555555u;
+                    const uint32_t nE = __popc(e01) + __popc(e2), nO = __popc(o01) + __popc(o2);
+                    const uint32_t nG = __popc(e01 & o01) + __popc(e2 & o2);
+                    totAC[rr] = (kSpanBytes - nE - nO + nG) | ((nE - nG) << 16);
+                    totGT[rr] = nG | ((nO - nG) << 16);
+                    // ---- plain spans: whole-span counts go to one window; reduce over the warp -------------
+                    const uint32_t ws = t.winBase + winA - t.firstWin;
+                    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, plain);
+                    if (pm) {
+                        const uint32_t gFirst = __shfl_sync(0xFFFFFFFFu, ws, __ffs(pm) - 1);
+                        const uint32_t gLast = __shfl_sync(0xFFFFFFFFu, ws, 31 - __clz(pm));
+                        for (uint32_t g = gFirst; g <= gLast; ++g) {
+                            const bool mine = plain && ws == g;
+                            const uint32_t s0 = __reduce_add_sync(0xFFFFFFFFu, mine ? totAC[rr] : 0u);
+                            const uint32_t s1 = __reduce_add_sync(0xFFFFFFFFu, mine ? totGT[rr] : 0u);
+                            if (lane < 4) {
+                                const uint32_t v = ((lane & 2) ? s1 : s0) >> ((lane & 1) * 16) & 0xFFFFu;
+                                if (v) {
+                                    if (g < kWindowSlots) atomicAdd(sWin + g * 8 + lane, v);
+                                    else atomicAdd(p.windows + static_cast<size_t>(t.firstWin + g) * 8 + lane, v);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+
+            // ---- fix-up pass: spans that touch the tile / region edge, a window end or a non-ACGT byte ----
+            for (uint32_t pend = notPlain; pend; pend &= pend - 1) {
+                const int rr = __ffs(pend) - 1;
+                const uint32_t rowByte = blockByte + rr * kRowBytes;
+                if (rowByte >= usedBytes) { if (rr == 0) cand[0][0] = cand[0][1] = 0; else cand[1][0] = cand[1][1] = 0; continue; }
+                const uint32_t spanByte = rowByte + lane * kSpanBytes;
+                const int q0 = static_cast<int>(spanByte) - static_cast<int>(skew);
+                const int lo = q0 < 0 ? -q0 : 0;
+                int hi = static_cast<int>(t.len) - q0; hi = hi > kSpanBytes ? kSpanBytes : hi;
+                int keepHi = static_cast<int>(candLimitQ) - q0; keepHi = keepHi > kSpanBytes ? kSpanBytes : keepHi;
+                uint64_t keep = 0;
+                uint32_t relLo = 0, winLo = 0;
+                int pb = 1 << 20;                                   // span position of the next window's first base
+                if (lo < hi) {
+                    relLo = t.relBase + static_cast<uint32_t>(q0 + lo);
+                    winLo = divWindow(cfg, relLo);
+                    const uint32_t toNext = (winLo + 1) * cfg.windowSize - relLo;
+                    if (toNext < 4096u) pb = lo + static_cast<int>(toNext);
+                    if (keepHi > lo) keep = ((1ull << keepHi) - 1ull) & ~((1ull << lo) - 1ull);
+                    // matches never cross the window end (src/teloscope.cpp:439): starts in [pb-L+1, pb) are dead
+                    const int ds = pb - static_cast<int>(L) + 1 < 0 ? 0 : pb - static_cast<int>(L) + 1;
+                    if (ds < kSpanBytes) {
+                        const int de = pb > kSpanBytes ? kSpanBytes : pb;
+                        keep &= ~(((1ull << de) - 1ull) & ~((1ull << ds) - 1ull));
+                    }
+                }
+                const uint32_t kLo = static_cast<uint32_t>(keep), kHi = static_cast<uint32_t>(keep >> 32);
+                if (rr == 0) { cand[0][0] &= kLo; cand[0][1] &= kHi; } else { cand[1][0] &= kLo; cand[1][1] &= kHi; }
+                if (COUNT && lo < hi) {
+                    const uint32_t wsLo = t.winBase + winLo;        // global window index of position lo
+                    const bool spanBad = [&]() {
+                        // recheck this span only (laneBad may come from the other row)
+                        const uint4 *src = reinterpret_cast<const uint4 *>(tile + spanByte);
+                        ValidAcc va;
+                        (void)pack16v(src[0], va); (void)pack16v(src[1], va); (void)pack16v(src[2], va);
+                        return va.bad() != 0;
+                    }();
+                    if (spanBad) {
+                        for (int i = lo; i < hi; ++i) {
+                            const uint32_t c = tile[spanByte + i];
+                            if (!isBase(c)) continue;
+                            const uint32_t code = (c >> 1) & 3u;                // A0 C1 T2 G3
+                            addAcgt(wsLo + (i >= pb ? 1u : 0u), code == 0, code == 1, code == 3, code == 2);
+                        }
+                    } else {
+                        const uint32_t *wp = sPk + rr * (kRowBytes / 16) + lane * 3;
+                        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+                        auto prefix = [&](int x, uint32_t &ac, uint32_t &gt) {   // counts of span positions [0, x)
+                            const uint32_t m0 = evenMaskBelow(x), m1 = evenMaskBelow(x - 16), m2 = evenMaskBelow(x - 32);
+                            const uint32_t e0 = w0 & m0, e1 = w1 & m1, e2 = w2 & m2;
+                            const uint32_t o0 = (w0 >> 1) & m0, o1 = (w1 >> 1) & m1, o2 = (w2 >> 1) & m2;
+                            const uint32_t nE = __popc(e0) + __popc(e1) + __popc(e2), nO = __popc(o0) + __popc(o1) + __popc(o2);
+                            const uint32_t nG = __popc(e0 & o0) + __popc(e1 & o1) + __popc(e2 & o2);
+                            ac = (static_cast<uint32_t>(x) - nE - nO + nG) | ((nE - nG) << 16);
+                            gt = nG | ((nO - nG) << 16);
+                        };
+                        const int split = pb < hi ? pb : hi;
+                        uint32_t acLo = 0, gtLo = 0, acSp, gtSp, acHi, gtHi;
+                        if (lo > 0) prefix(lo, acLo, gtLo);
+                        if (hi == kSpanBytes) { acHi = rr == 0 ? totAC[0] : totAC[1]; gtHi = rr == 0 ? totGT[0] : totGT[1]; }
+                        else prefix(hi, acHi, gtHi);
+                        if (split == hi) { acSp = acHi; gtSp = gtHi; } else prefix(split, acSp, gtSp);
+                        const uint32_t aAC = acSp - acLo, aGT = gtSp - gtLo, bAC = acHi - acSp, bGT = gtHi - gtSp;
+                        addAcgt(wsLo, aAC & 0xFFFFu, aAC >> 16, aGT & 0xFFFFu, aGT >> 16);
+                        if (bAC | bGT) addAcgt(wsLo + 1, bAC & 0xFFFFu, bAC >> 16, bGT & 0xFFFFu, bGT >> 16);
+                    }
+                }
+            }
+            __syncwarp();
+            fastResolve = !warpBad;
+        } else {
+        // ---- general path: main loop over this warp's rows ------------------------------------------
 #pragma unroll
         for (int rr = 0; rr < kRowsPerWarp; ++rr) {
             cand[rr][0] = cand[rr][1] = 0;
@@ -551,14 +779,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
             }
             candHi &= 0xFFFFu;
             cand[rr][0] = candLo; cand[rr][1] = candHi;
-            nCand |= (__popc(candLo) + __popc(candHi)) << (16 * rr);
+        }
         }
 
         // ---- compaction: one scan for all rows of the warp, then scatter into the queue ------------------
-        static_assert(kRowsPerWarp == 2, "candidate counts of the rows are scanned as two 16-bit fields");
         uint32_t rowTotal[kRowsPerWarp], rowExcl[kRowsPerWarp];
         uint32_t allTotal;
         {
+            const uint32_t nCand = (__popc(cand[0][0]) + __popc(cand[0][1])) | ((__popc(cand[1][0]) + __popc(cand[1][1])) << 16);
             const uint32_t incl = warpInclusiveScan(nCand);             // fields: row0 | row1 << 16 (<= 1536 each)
             const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), ex = incl - nCand;
             rowTotal[0] = tot & 0xFFFFu; rowTotal[1] = tot >> 16;
@@ -578,7 +806,83 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                 base += rowTotal[rr];
             }
             __syncwarp();
-            for (uint32_t from = 0; from < allTotal; from += 32) resolveBatch(from, min(32u, allTotal - from));
+            if (fastResolve) {
+                // ---- stage 2 (lean): every queue entry is a match; flags from the 2-bit copy ------------
+                const uint32_t L = cfg.cls[0].len;
+                const uint32_t keyMask = (1u << (2 * L)) - 1u;
+                const uint8_t *sFl = sFlags + cfg.cls[0].flagOffset;
+                const uint32_t *sPk = sPackedAll + warp * kPackedWords;
+                const uint32_t blockByte = warp * (kRowsPerWarp * kRowBytes);
+                const uint32_t blockRel0 = t.relBase + blockByte - skew;
+                if (allTotal > p.slotCap) {
+                    if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
+                    ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
+                }
+                // running accumulators of the current window (warp-uniform)
+                uint32_t curWs = 0xFFFFFFFFu, accAll = 0, accCan = 0, accFwd = 0;
+                uint32_t itAll = 0, itFwd = 0, itCan = 0, itNct = 0;
+                auto flushAcc = [&]() {
+                    if (accAll) {
+                        if (lane < 4) {
+                            const uint32_t n = lane == 0 ? accCan : lane == 1 ? accAll - accCan : lane == 2 ? accFwd : accAll - accFwd;
+                            if (n) {
+                                if (curWs < kWindowSlots) atomicAdd(sWin + curWs * 8 + 4 + lane, n * L);
+                                else atomicAdd(p.windows + static_cast<size_t>(t.firstWin + curWs) * 8 + 4 + lane, n * L);
+                            }
+                        }
+                        itAll += accAll; itFwd += accFwd; itCan += accCan;
+                    }
+                    accAll = accCan = accFwd = 0;
+                };
+                for (uint32_t from = 0; from < allTotal; from += 32) {
+                    const uint32_t idx = from + lane;
+                    const bool act = idx < allTotal;
+                    uint32_t f = 0, ws = 0xFFFFFFFFu;
+                    bool term = false;
+                    if (act) {
+                        const uint32_t qq = static_cast<uint32_t>(sQueue[idx]) - blockByte;
+                        const uint32_t wi = qq >> 4, sh = (qq & 15u) * 2u;
+                        const uint32_t key = __funnelshift_r(sPk[wi], sPk[wi + 1], sh) & keyMask;
+                        f = sFl[key];
+                        const uint32_t rel = blockRel0 + qq;
+                        const uint32_t winIdx = divWindow(cfg, rel);
+                        ws = t.winBase + winIdx - t.firstWin;
+                        if (t.termMixed) term = isTerminalMatch(cfg, rel, winIdx, t.itemLen);
+                        DevMatch m;
+                        m.pos = rel;
+                        m.len = static_cast<uint16_t>(L);
+                        m.flags = static_cast<uint8_t>(((f >> 1) & 3u) | (term ? kMatchTerm : 0));
+                        m.region = kRegionAccounted;
+                        if (idx < p.slotCap) slot[idx] = m;
+                        else if (static_cast<uint64_t>(ovBase) + (idx - p.slotCap) < p.ovCap) p.ovArena[ovBase + (idx - p.slotCap)] = m;
+                    }
+                    const uint32_t actB = __ballot_sync(0xFFFFFFFFu, act);
+                    const uint32_t canB = __ballot_sync(0xFFFFFFFFu, (f & 4u) != 0);
+                    const uint32_t fwdB = __ballot_sync(0xFFFFFFFFu, (f & 2u) != 0);
+                    if (t.termMixed) itNct += __popc(__ballot_sync(0xFFFFFFFFu, term && !(f & 4u)));
+                    const uint32_t chg = __ballot_sync(0xFFFFFFFFu, act && ws != curWs);
+                    if (chg == 0) {
+                        accAll += __popc(actB); accCan += __popc(canB); accFwd += __popc(fwdB);
+                    } else {
+                        uint32_t rest = actB;
+                        while (rest) {
+                            const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, ws, __ffs(rest) - 1);
+                            const uint32_t grp = __ballot_sync(0xFFFFFFFFu, ws == w0) & rest;
+                            if (w0 != curWs) { flushAcc(); curWs = w0; }
+                            accAll += __popc(grp); accCan += __popc(grp & canB); accFwd += __popc(grp & fwdB);
+                            rest &= ~grp;
+                        }
+                    }
+                }
+                flushAcc();
+                if (lane < 5 && itAll) {
+                    const uint32_t v = lane == 0 ? itAll : lane == 1 ? itFwd : lane == 2 ? itAll - itFwd : lane == 3 ? itCan : itNct;
+                    if (v) atomicAdd(sItem + lane, v);
+                }
+                wMatches = allTotal;
+            } else {
+                for (uint32_t from = 0; from < allTotal; from += 32) resolveBatch(from, min(32u, allTotal - from));
+            }
         } else {
             // dense tile: 11 lanes at a time (<= 528 candidates per step); lane groups keep genome order
 #pragma unroll
@@ -602,13 +906,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
             p.slotOv[slotIdx] = ovBase;
         }
 
-        // ---- tile epilogue: flush the shared A/C/G/T counters ---------------------------------------------
+        // ---- tile epilogue: flush the shared window and item counters ---------------------------------------
         __syncthreads();
-        if (COUNT) {
-            for (int i = tid; i < kWindowSlots * 4; i += kScanThreads) {
-                const uint32_t v = sWin[i];
-                if (v) atomicAdd(&p.windows[static_cast<size_t>(t.firstWin + (i >> 2)) * 8 + (i & 3)], v);
-            }
+        for (int i = tid; i < kWindowSlots * 8; i += kScanThreads) {
+            const uint32_t v = sWin[i];
+            if (v) atomicAdd(&p.windows[static_cast<size_t>(t.firstWin + (i >> 3)) * 8 + (i & 7)], v);
+        }
+        if (tid < 5 && t.fast) {
+            const uint32_t v = sItem[tid];
+            if (v) atomicAdd(reinterpret_cast<uint32_t *>(p.itemCounts + t.item) + tid, v);
         }
         tCur = tNext; tNext = tNext2; rCur = rNext;
     }
@@ -616,7 +922,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
 
 size_t scanSmemBytes() {
     return 65536 + kFlagTabBytes + 2 * (kTileSmemBytes + kTileHalo) + kScanWarps * kQueueCap * 2 +
-           2 * kRegionCache * sizeof(DevRegion) + 2 * kWindowSlots * 4 * 4 + 2 * sizeof(TileMeta) + 2 * 8 + 64;
+           kScanWarps * kPackedWords * 4 + 2 * kRegionCache * sizeof(DevRegion) + 2 * kWindowSlots * 8 * 4 + 2 * 8 * 4 +
+           2 * sizeof(TileMeta) + 2 * 8 + 64;
 }
 
 cudaError_t launchScan(const ScanParams &p, int grid, cudaStream_t stream) {

@@ -92,7 +92,8 @@ struct HostBuf {
 struct Slot {
     bool busy = false, collected = false;
     cudaStream_t stream = nullptr;
-    cudaEvent_t evScan0 = nullptr, evScan1 = nullptr, evAll0 = nullptr, evAll1 = nullptr;
+    cudaEvent_t evScan0 = nullptr, evScan1 = nullptr, evFast1 = nullptr, evAll0 = nullptr, evAll1 = nullptr;
+    float fastMs = 0;
     // inputs
     uint32_t nItems = 0, mode = 0;
     uint64_t seqBytes = 0, nBases = 0, nWindows = 0;
@@ -101,8 +102,11 @@ struct Slot {
     std::vector<uint64_t> winOff;            // per item window offsets (n+1)
     std::vector<DevRegion> regions;
     std::vector<DevTile> tiles;
+    std::vector<DevFastTile> fastTiles;      // tiles for the lean kernel
+    std::vector<uint32_t> generalTiles;      // indices of the tiles the general kernel takes entirely
     const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
-    HostBuf hSeq, hMeta;                      // pinned staging
+    HostBuf hSeq, hMeta, hMeta2;              // pinned staging
+    DevBuf dFastTiles, dGeneralTiles, dRedo;
     DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotCounts,
         dSlotOv, dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
     uint32_t ovCap = 0;
@@ -135,6 +139,7 @@ struct tls_ctx {
     DevConfig dcfg{};
     DevBuf dIndex, dFlags, dKeys, dKeyFlags;
     uint32_t slotCap = 0, ovChunk = 0;
+    bool forceGeneral = false;               // TLS_FORCE_GENERAL=1 or a lean-kernel layout failure
     Slot slot[2];
 };
 
@@ -306,19 +311,20 @@ int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
         // slots hold twice that (power of two), denser stretches spill into overflow chunks
         double density = 0;
         for (const LenClass &c : t.classes) density += static_cast<double>(c.sortedCount) / static_cast<double>(1ull << (2 * std::min<uint32_t>(c.len, 31)));
-        const uint32_t perWarp = static_cast<uint32_t>(kRowsPerWarp * kRowBytes);
-        ctx->ovChunk = perWarp * ctx->dcfg.nClasses;
-        uint32_t want = static_cast<uint32_t>(2.0 * perWarp * density) + 64, cap = 64;
+        const uint32_t perRow = static_cast<uint32_t>(kRowBytes);          // every tile row owns one slot
+        ctx->ovChunk = perRow * ctx->dcfg.nClasses;
+        uint32_t want = static_cast<uint32_t>(1.5 * perRow * density) + 48, cap = 64;
         while (cap < want) cap <<= 1;
         ctx->slotCap = std::min(cap, ctx->ovChunk);
     }
     for (Slot &s : ctx->slot) {
         TLS_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        TLS_CUDA(cudaEventCreate(&s.evScan0)); TLS_CUDA(cudaEventCreate(&s.evScan1));
+        TLS_CUDA(cudaEventCreate(&s.evScan0)); TLS_CUDA(cudaEventCreate(&s.evScan1)); TLS_CUDA(cudaEventCreate(&s.evFast1));
         TLS_CUDA(cudaEventCreate(&s.evAll0)); TLS_CUDA(cudaEventCreate(&s.evAll1));
         TLS_CUDA(s.dCounters.reserve(64));
         TLS_CUDA(s.hCounters.reserve(64));
     }
+    ctx->forceGeneral = std::getenv("TLS_FORCE_GENERAL") != nullptr;
     *out = ctx.release();
     return TLS_OK;
 }
@@ -328,15 +334,17 @@ void tls_destroy(tls_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (Slot &s : ctx->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
+        for (DevBuf *b : {&s.dFastTiles, &s.dGeneralTiles, &s.dRedo}) b->release();
         for (DevBuf *b : {&s.dAbsPos, &s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
                           &s.dMatches, &s.dSlots, &s.dSlotCounts, &s.dSlotOv, &s.dOvArena, &s.dTileBase, &s.dCounters,
                           &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch, &s.dSelCan, &s.dSelNon})
             b->release();
-        for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
+        for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hMeta2, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
                            &s.hSelCan, &s.hSelNon})
             b->release();
         if (s.evScan0) cudaEventDestroy(s.evScan0);
         if (s.evScan1) cudaEventDestroy(s.evScan1);
+        if (s.evFast1) cudaEventDestroy(s.evFast1);
         if (s.evAll0) cudaEventDestroy(s.evAll0);
         if (s.evAll1) cudaEventDestroy(s.evAll1);
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -364,52 +372,89 @@ GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
     return g;
 }
 
-// Enqueue the fused scan for the slot: memsets, kernel, per-tile prefix, copy of the counters.
+// Enqueue the scan for the slot: memsets, lean kernel over the single-contig tiles, general kernel
+// over the rest and over the rows the lean kernel handed back, per-tile prefix, copy of the counters.
 int enqueueScan(tls_ctx *ctx, Slot &s) {
     const uint32_t nTiles = static_cast<uint32_t>(s.tiles.size());
-    const size_t nSlots = static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * kScanWarps;
+    const size_t nSlots = static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * kTileRows;
     TLS_CUDA(s.dSlots.reserve(nSlots * ctx->slotCap * sizeof(DevMatch)));
     TLS_CUDA(s.dSlotCounts.reserve(nSlots * 4));
     TLS_CUDA(s.dSlotOv.reserve(nSlots * 4));
     TLS_CUDA(s.dTileBase.reserve((static_cast<size_t>(nTiles) + 1) * 8));
     s.ovCap = std::max<uint32_t>(s.ovCap, 256u * ctx->ovChunk);
     TLS_CUDA(s.dOvArena.reserve(static_cast<size_t>(s.ovCap) * sizeof(DevMatch)));
+    const uint32_t nFast = static_cast<uint32_t>(s.fastTiles.size());
+    const uint32_t redoCap = std::max<uint32_t>(nFast, 1) * kTileRows;
+    TLS_CUDA(s.dRedo.reserve(16 + static_cast<size_t>(redoCap) * 4));       // [0] count, [1] status, [4..] entries
+    TLS_CUDA(cudaMemsetAsync(s.dRedo.p, 0, 16, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 64, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dItemCounts.p, 0, std::max<size_t>(s.nItems, 1) * sizeof(DevItemCounts), s.stream));
     if (s.nWindows) TLS_CUDA(cudaMemsetAsync(s.dWindows.p, 0, s.nWindows * 32, s.stream));
     s.launches = 0;
     if (nTiles) {
-        ScanParams p{};
-        p.seq = s.devSeq;
-        p.tiles = s.dTiles.as<DevTile>();
-        p.regions = s.dRegions.as<DevRegion>();
-        p.nTiles = nTiles;
-        p.nRegions = static_cast<uint32_t>(s.regions.size());
-        p.index8 = ctx->dIndex.as<uint8_t>();
-        p.flagTabs = ctx->dFlags.as<uint8_t>();
-        p.sortedKeys = ctx->dKeys.as<uint64_t>();
-        p.sortedFlags = ctx->dKeyFlags.as<uint8_t>();
-        p.slots = s.dSlots.as<DevMatch>(); p.slotCap = ctx->slotCap;
-        p.slotCounts = s.dSlotCounts.as<uint32_t>(); p.slotOv = s.dSlotOv.as<uint32_t>();
-        p.ovArena = s.dOvArena.as<DevMatch>(); p.ovCap = s.ovCap; p.ovChunk = ctx->ovChunk;
-        p.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
-        p.windows = s.dWindows.as<uint32_t>();
-        p.itemCounts = s.dItemCounts.as<DevItemCounts>();
-        p.cfg = ctx->dcfg;
-        p.cfg.mode = s.mode;
-        if (s.mode != TLS_MODE_GENOME) p.cfg.countAcgt = 0;
+        DevConfig cfg = ctx->dcfg;
+        cfg.mode = s.mode;
+        if (s.mode != TLS_MODE_GENOME) cfg.countAcgt = 0;
+        unsigned int *redo = s.dRedo.as<unsigned int>();
         TLS_CUDA(cudaEventRecord(s.evScan0, s.stream));
-        TLS_CUDA(launchScan(p, std::min<int>(ctx->smCount, static_cast<int>(nTiles)), s.stream));
+        if (nFast) {
+            FastParams f{};
+            f.seq = s.devSeq;
+            f.tiles = s.dFastTiles.as<DevFastTile>(); f.nTiles = nFast;
+            f.index8 = ctx->dIndex.as<uint8_t>();
+            f.flagTab = ctx->dFlags.as<uint8_t>() + cfg.cls[0].flagOffset;
+            f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
+            f.patLen = cfg.cls[0].len;
+            f.slots = s.dSlots.as<DevMatch>(); f.slotCap = ctx->slotCap;
+            f.slotCounts = s.dSlotCounts.as<uint32_t>(); f.slotOv = s.dSlotOv.as<uint32_t>();
+            f.ovArena = s.dOvArena.as<DevMatch>(); f.ovCap = s.ovCap; f.ovChunk = ctx->ovChunk;
+            f.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
+            f.windows = s.dWindows.as<uint32_t>();
+            f.itemCounts = s.dItemCounts.as<DevItemCounts>();
+            f.redoList = redo + 4; f.redoCount = redo; f.redoCap = redoCap;
+            f.cfg = cfg;
+            TLS_CUDA(launchFastScan(f, std::min<int>(ctx->smCount, static_cast<int>(nFast)), s.stream));
+            s.launches++;
+        }
+        TLS_CUDA(cudaEventRecord(s.evFast1, s.stream));
+        const uint32_t nGeneral = static_cast<uint32_t>(s.generalTiles.size());
+        if (nGeneral || nFast) {
+            ScanParams p{};
+            p.seq = s.devSeq;
+            p.tiles = s.dTiles.as<DevTile>();
+            p.regions = s.dRegions.as<DevRegion>();
+            p.nTiles = nTiles;
+            p.nRegions = static_cast<uint32_t>(s.regions.size());
+            p.workTiles = s.dGeneralTiles.as<uint32_t>(); p.nWork = nGeneral;
+            p.redoList = redo + 4; p.redoCount = nFast ? redo : nullptr; p.redoCap = redoCap;
+            p.index8 = ctx->dIndex.as<uint8_t>();
+            p.flagTabs = ctx->dFlags.as<uint8_t>();
+            p.sortedKeys = ctx->dKeys.as<uint64_t>();
+            p.sortedFlags = ctx->dKeyFlags.as<uint8_t>();
+            p.slots = s.dSlots.as<DevMatch>(); p.slotCap = ctx->slotCap;
+            p.slotCounts = s.dSlotCounts.as<uint32_t>(); p.slotOv = s.dSlotOv.as<uint32_t>();
+            p.ovArena = s.dOvArena.as<DevMatch>(); p.ovCap = s.ovCap; p.ovChunk = ctx->ovChunk;
+            p.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
+            p.windows = s.dWindows.as<uint32_t>();
+            p.itemCounts = s.dItemCounts.as<DevItemCounts>();
+            p.cfg = cfg;
+            // rows handed back by the lean kernel are only known on the device: when there are lean
+            // tiles every SM gets a CTA, which exits at once if the work list turns out empty
+            const int grid = nFast ? ctx->smCount : std::min<int>(ctx->smCount, static_cast<int>(nGeneral));
+            TLS_CUDA(launchScan(p, grid, s.stream));
+            s.launches++;
+        }
         TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
         TLS_CUDA(launchTileScan(gatherParams(ctx, s), s.stream));
-        s.launches += 2;
+        s.launches++;
     } else {
         TLS_CUDA(cudaMemsetAsync(s.dTileBase.p, 0, 8, s.stream));
     }
-    // counters: [0] ovCursor; total matches = tileBase[nTiles]
+    // counters: [0] ovCursor; total matches = tileBase[nTiles]; lean kernel status
     TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 8, cudaMemcpyDeviceToHost, s.stream));
     TLS_CUDA(cudaMemcpyAsync(s.hCounters.as<uint8_t>() + 8, s.dTileBase.as<unsigned long long>() + nTiles, 8,
                              cudaMemcpyDeviceToHost, s.stream));
+    TLS_CUDA(cudaMemcpyAsync(s.hCounters.as<uint8_t>() + 32, s.dRedo.p, 8, cudaMemcpyDeviceToHost, s.stream));
     return TLS_OK;
 }
 
@@ -511,8 +556,44 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
         }
     }
 
+    // ---- which kernel takes which tile: the lean kernel wants tiles inside one region ------------------
+    s.fastTiles.clear(); s.generalTiles.clear();
+    {
+        DevConfig probe = ctx->dcfg;
+        probe.mode = b->mode;
+        const bool fastOk = fastConfigOk(probe) && !ctx->forceGeneral;
+        const uint32_t W = ctx->cfg.window_size;
+        for (size_t ti = 0; ti < s.tiles.size(); ++ti) {
+            const DevTile &t = s.tiles[ti];
+            const DevRegion &r = s.regions[t.firstRegion];
+            const bool single = r.bufStart <= t.bufStart && t.bufStart + t.len <= r.bufStart + r.len;
+            if (!(fastOk && single)) { s.generalTiles.push_back(static_cast<uint32_t>(ti)); continue; }
+            DevFastTile f{};
+            f.bufStart = t.bufStart; f.len = t.len; f.tile = static_cast<uint32_t>(ti);
+            f.relBase = r.relStart + static_cast<uint32_t>(t.bufStart - r.bufStart);
+            f.regionEndQ = r.relStart + r.len - f.relBase;
+            f.item = r.item; f.itemLen = r.itemLen;
+            f.firstWin = r.winBase + f.relBase / W;
+            f.winDelta = r.winBase - f.firstWin;                   // mod 2^32
+            const uint32_t termEnd = r.itemLen > T ? r.itemLen - T : 0;
+            // no position of the tile is <= T or >= n - T  ->  none of its matches is "terminal"
+            f.termMixed = !(f.relBase > T && static_cast<uint64_t>(f.relBase) + f.len <= termEnd);
+            s.fastTiles.push_back(f);
+        }
+    }
     tr.mark("plan");
     // ---- upload metadata ------------------------------------------------------------------------
+    {
+        const size_t bFast = s.fastTiles.size() * sizeof(DevFastTile), bGen = s.generalTiles.size() * 4;
+        TLS_CUDA(s.hMeta2.reserve(bFast + bGen + 64));
+        uint8_t *h2 = s.hMeta2.as<uint8_t>();
+        if (bFast) std::memcpy(h2, s.fastTiles.data(), bFast);
+        if (bGen) std::memcpy(h2 + bFast, s.generalTiles.data(), bGen);
+        TLS_CUDA(s.dFastTiles.reserve(std::max<size_t>(bFast, 16)));
+        TLS_CUDA(s.dGeneralTiles.reserve(std::max<size_t>(bGen, 16)));
+        if (bFast) TLS_CUDA(cudaMemcpyAsync(s.dFastTiles.p, h2, bFast, cudaMemcpyHostToDevice, s.stream));
+        if (bGen) TLS_CUDA(cudaMemcpyAsync(s.dGeneralTiles.p, h2 + bFast, bGen, cudaMemcpyHostToDevice, s.stream));
+    }
     const size_t bRegions = s.regions.size() * sizeof(DevRegion), bTiles = s.tiles.size() * sizeof(DevTile),
                  bLen = static_cast<size_t>(n) * 4, bAbs = static_cast<size_t>(n) * 8;
     TLS_CUDA(s.hMeta.reserve(bRegions + bTiles + bLen + bAbs + 64));
@@ -560,6 +641,11 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
         // ---- wait for the scan; grow the overflow arena and rerun if it ran out --------------------
         for (;;) {
             TLS_CUDA(cudaStreamSynchronize(s.stream));
+            if (s.hCounters.as<uint32_t>()[9] != 0)
+                return fail(TLS_ERR_STATE, "lean scan kernel could not lay out its shared memory (window base %% 64 KiB); "
+                                           "set TLS_FORCE_GENERAL=1");
+            const uint32_t nRedo = s.hCounters.as<uint32_t>()[8];
+            if (tr.on) fprintf(stderr, " lean_tiles=%zu/%zu redo_rows=%u", s.fastTiles.size(), s.tiles.size(), nRedo);
             const uint32_t ovUsed = *s.hCounters.as<uint32_t>();
             s.nMatches = *reinterpret_cast<unsigned long long *>(s.hCounters.as<uint8_t>() + 8);
             if (ovUsed <= s.ovCap) break;
@@ -571,8 +657,10 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
         s.matchCap = std::max<uint64_t>(s.matchCap, s.nMatches);
         TLS_CUDA(s.dMatches.reserve(std::max<uint64_t>(s.matchCap, 1) * sizeof(DevMatch)));
         if (!s.tiles.empty()) { TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream)); s.launches++; }
-        if (!s.tiles.empty()) TLS_CUDA(cudaEventElapsedTime(&s.scanMs, s.evScan0, s.evScan1));
-        else s.scanMs = 0;
+        if (!s.tiles.empty()) {
+            TLS_CUDA(cudaEventElapsedTime(&s.scanMs, s.evScan0, s.evScan1));
+            TLS_CUDA(cudaEventElapsedTime(&s.fastMs, s.evScan0, s.evFast1));
+        } else s.scanMs = s.fastMs = 0;
 
         // ---- blocks -------------------------------------------------------------------------------
         const bool genome = s.mode == TLS_MODE_GENOME, reads = s.mode == TLS_MODE_READS;

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *c
 
 // ------------------------------------------------------------------------------------------------
 // Slot arena -> one ordered match list.
-//   tileScanKernel: per-tile totals (sum of the 16 warp slots) and their exclusive prefix
+//   tileScanKernel: per-tile totals (sum of the 32 row slots) and their exclusive prefix
 //   gatherKernel:   one block per tile copies its slots (and overflow chunks) to the list
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) tileScanKernel(const GatherParams g) {
@@ -69,9 +69,9 @@ __global__ void __launch_bounds__(1024) tileScanKernel(const GatherParams g) {
         const uint32_t i = base + tid;
         unsigned long long v = 0;
         if (i < g.nTiles) {
-            const uint4 *c = reinterpret_cast<const uint4 *>(g.slotCounts + static_cast<size_t>(i) * kScanWarps);
+            const uint4 *c = reinterpret_cast<const uint4 *>(g.slotCounts + static_cast<size_t>(i) * kTileRows);
 #pragma unroll
-            for (int k = 0; k < kScanWarps / 4; ++k) { const uint4 x = c[k]; v += x.x; v += x.y; v += x.z; v += x.w; }
+            for (int k = 0; k < kTileRows / 4; ++k) { const uint4 x = c[k]; v += x.x; v += x.y; v += x.z; v += x.w; }
         }
         unsigned long long incl = v;
 #pragma unroll
@@ -110,7 +110,7 @@ constexpr int kGatherSlots = 128;
 __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParams g) {
     const uint32_t tile = blockIdx.x;
     const int tid = threadIdx.x;
-    __shared__ uint32_t sOff[kScanWarps + 1];
+    __shared__ uint32_t sOff[kTileRows + 1];
     __shared__ DevRegion sRegion[kRegionCache];
     __shared__ uint32_t sRegCnt[kRegionCache][5];
     __shared__ uint32_t sWin[kGatherSlots][4];
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
     const DevTile dt = g.tiles[tile];
     if (tid == 0) {
         uint32_t acc = 0;
-        for (int w = 0; w < kScanWarps; ++w) { sOff[w] = acc; acc += g.slotCounts[static_cast<size_t>(tile) * kScanWarps + w]; }
-        sOff[kScanWarps] = acc;
+        for (int w = 0; w < kTileRows; ++w) { sOff[w] = acc; acc += g.slotCounts[static_cast<size_t>(tile) * kTileRows + w]; }
+        sOff[kTileRows] = acc;
     }
     if (tid < 32) {
         const uint64_t tileEnd = dt.bufStart + dt.len;
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
     for (int i = tid; i < kRegionCache * 5; i += kGatherThreads) (&sRegCnt[0][0])[i] = 0;
     for (int i = tid; i < kGatherSlots * 4; i += kGatherThreads) (&sWin[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t total = sOff[kScanWarps];
+    const uint32_t total = sOff[kTileRows];
     if (total == 0) return;
     const unsigned long long base = g.tileBase[tile];
     const uint32_t firstWin = sFirstWin;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
         while (sOff[w + 1] <= i) ++w;
         for (; i < end; ++i) {
             while (sOff[w + 1] <= i) ++w;
-            const size_t slotIdx = static_cast<size_t>(tile) * kScanWarps + w;
+            const size_t slotIdx = static_cast<size_t>(tile) * kTileRows + w;
             const uint32_t k = i - sOff[w];
             DevMatch m;
             if (k < g.slotCap) m = g.slots[slotIdx * g.slotCap + k];

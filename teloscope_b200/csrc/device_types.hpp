@@ -18,10 +18,16 @@ constexpr int kTileMaxLen = kTileSmemBytes - 16;  // leaves room for the alignme
 constexpr int kQueueCap = 544;                    // per-warp candidate queue (u16 entries)
 constexpr int kRegionCache = 32;                  // regions of a tile kept in shared memory
 constexpr uint32_t kNoOverflow = 0xFFFFFFFFu;
-constexpr int kWindowSlots = 128;                 // per-tile window counter slots in shared memory (8 counters each)
-constexpr int kPackedWords = kRowsPerWarp * (kRowBytes / 16) + 8;   // per-warp 2-bit copy of its rows + halo
-constexpr uint32_t kMinFastWindow = 64;           // fast path: at most one window boundary per lane span
+constexpr int kWindowSlots = 128;                 // per-tile window counter slots in shared memory
 constexpr int kFlagTabBytes = 24576;              // direct stage-2 tables (sum 4^len, len<=7)
+
+// ---- geometry of the lean kernel (scan_fast.cu): same tiles and rows, one warp per row -------------
+constexpr int kFastThreads = 1024;
+constexpr int kFastWarps = kFastThreads / 32;     // == kTileRows
+constexpr int kFastQueueCap = 288;                // per-warp candidate queue (u16 entries), 6 spans
+constexpr int kFastPackedWords = kRowBytes / 16 + 4;   // per-warp 2-bit copy of its row + halo word
+constexpr int kFastFlagBytes = 16384;             // one direct table, pattern length <= 7
+constexpr uint32_t kFastMinWindow = 512;          // <= 98 windows per tile, <= 1 window end per span
 
 // A maximal stretch of one item inside which matches must lie entirely
 // (genome mode: the whole contig; tips mode: [0,T) and [n-T,n); reads: the whole read).
@@ -39,6 +45,21 @@ struct DevTile {
     uint64_t bufStart;     // first base of the tile
     uint32_t len;          // <= kTileMaxLen
     uint32_t firstRegion;  // first region that overlaps the tile
+};
+
+// Descriptor of a tile for the lean kernel, precomputed on the host: the tile lies inside one
+// region (= one contig in genome mode).
+struct DevFastTile {
+    uint64_t bufStart;     // first base of the tile in the sequence buffer
+    uint32_t len;          // <= kTileMaxLen
+    uint32_t tile;         // index in the batch's tile table (slot addressing)
+    uint32_t relBase;      // item-relative position of the tile's first base
+    uint32_t regionEndQ;   // tile position one past the region's last base (>= len)
+    uint32_t item, itemLen;
+    uint32_t firstWin;     // global index of the window that holds the tile's first base
+    uint32_t winDelta;     // item's first window - firstWin (mod 2^32): slot = rel / window + winDelta
+    uint32_t termMixed;    // 1: matches of this tile may be "terminal" (src/teloscope.cpp:451-459)
+    uint32_t pad;
 };
 
 struct DevMatch {          // 8 bytes, ordered by (item, pos, len)
@@ -98,15 +119,43 @@ struct ScanParams {
     const uint8_t *sortedFlags;
     // Match output: every (tile, warp) owns a slot of slotCap records; a warp that needs more
     // takes one overflow chunk of ovChunk records from ovArena (bump allocation).
-    DevMatch *slots;               // [nTiles * kScanWarps][slotCap]
+    // work list: whole tiles (workTiles[nWork], or tiles 0..nWork-1 when null), then the rows the
+    // lean kernel handed back (redoList[*redoCount] entries tile << 5 | row)
+    const uint32_t *workTiles;
+    uint32_t nWork, redoCap;
+    const uint32_t *redoList;
+    const unsigned int *redoCount;
+    DevMatch *slots;               // [nTiles * kTileRows][slotCap]: one slot per tile row
     uint32_t slotCap;
-    uint32_t *slotCounts;          // [nTiles * kScanWarps] records produced
-    uint32_t *slotOv;              // [nTiles * kScanWarps] overflow chunk base or 0xFFFFFFFF
+    uint32_t *slotCounts;          // [nTiles * kTileRows] records produced
+    uint32_t *slotOv;              // [nTiles * kTileRows] overflow chunk base or 0xFFFFFFFF
     DevMatch *ovArena;
     uint32_t ovCap, ovChunk;
     unsigned int *ovCursor;        // zeroed per launch; > ovCap afterwards means "grow and rerun"
     uint32_t *windows;             // [nWindows][8], zeroed per launch
     DevItemCounts *itemCounts;     // zeroed per launch
+    DevConfig cfg;
+};
+
+struct FastParams {
+    const uint8_t *seq;
+    const DevFastTile *tiles;
+    uint32_t nTiles;
+    const uint8_t *index8;         // 65536-byte stage-1 table
+    const uint8_t *flagTab;        // direct table of the single length class (4^len bytes)
+    uint32_t flagTabBytes;         // rounded up to 16
+    uint32_t patLen;
+    DevMatch *slots;
+    uint32_t slotCap;
+    uint32_t *slotCounts, *slotOv;
+    DevMatch *ovArena;
+    uint32_t ovCap, ovChunk;
+    unsigned int *ovCursor;
+    uint32_t *windows;             // [nWindows][8]
+    DevItemCounts *itemCounts;
+    uint32_t *redoList;            // rows with a non-ACGT byte: tile << 5 | row, redone by the general kernel
+    unsigned int *redoCount;
+    uint32_t redoCap;
     DevConfig cfg;
 };
 

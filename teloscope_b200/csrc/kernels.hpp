@@ -10,6 +10,11 @@ namespace tls {
 size_t scanSmemBytes();
 cudaError_t launchScan(const ScanParams &p, int grid, cudaStream_t stream);
 
+// lean kernel (scan_fast.cu): genome mode, one direct pattern length, window >= kFastMinWindow
+size_t fastSmemBytes();
+bool fastConfigOk(const DevConfig &c);
+cudaError_t launchFastScan(const FastParams &p, int grid, cudaStream_t stream);
+
 // exclusive scan of per-tile match totals (tileBase[nTiles] = total), then ordered copy
 cudaError_t launchTileScan(const GatherParams &g, cudaStream_t s);
 cudaError_t launchGather(const GatherParams &g, cudaStream_t s);

@@ -1,6 +1,9 @@
-// Fused telomeric motif scan for sm_100a.
+// General telomeric motif scan kernel for sm_100a (any mode, any pattern set, any window size).
+// Tiles of a genome-mode batch that lie inside one contig and use one short pattern length go to
+// the lean kernel in scan_fast.cu instead; this kernel takes every other tile plus the rows the
+// lean kernel handed back (rows holding a non-ACGT byte).
 //
-// One persistent CTA per SM walks tiles (<= 49136 bases of the staged sequence buffer), tile
+// One persistent CTA per SM walks its work items (<= 49136 bases of the staged sequence buffer), tile
 // index = blockIdx.x + k * gridDim.x.  Nothing in the kernel waits on another CTA.  Per tile:
 //   1. the raw ASCII bytes are staged into shared memory with cp.async.bulk (TMA bulk copy,
 //      mbarrier completion), double buffered; the next tile's descriptor and regions are
@@ -16,12 +19,6 @@
 //   4. A/C/G/T window counts come from popcounts on the packed codes (src/teloscope.cpp:418-435);
 //   5. match records go, in genome order, to the (tile, warp) slot of a global arena; a later
 //      scan + gather pass (block_kernels.cu) compacts the slots into one ordered list.
-// Tiles that lie inside one contig of a genome-mode batch with a single pattern length (the
-// north-star configuration) take a lean path: span validity is established once per lane with
-// two multiplies per word, candidates are therefore exact matches, window-end / region-end
-// truncation is applied to the candidate bitmap of the few lanes that straddle a boundary, the
-// 2-bit codes are kept per warp in shared memory for the flag lookup, and window / item
-// accounting is done on warp ballots.  Everything else takes the general path.
 // No tensor cores: this is byte/integer streaming work bound by instruction issue and HBM.
 #include <cuda_runtime.h>
 
@@ -103,33 +100,6 @@ __device__ __forceinline__ uint32_t badChunk(const uint4 &v) {
     return (rel & 0x10101010u) | (anyOr & 0x88888888u) | (~allAnd & 0x40404040u);
 }
 
-// Lean validity accumulators for the fast path.  For a byte c in ACGTacgt: bit7=0, bit6=1, bit3=0,
-// bit4 = (bit2 & ~bit1) ("is T") and bit0 = ~bit4.  With m = c & 6 in {0,2,4,6} the product
-// 6*m + 0x40 has bit7=0, bit6=1 and bit4 set only for m == 4 (T), so (y ^ w) must be zero in
-// bits 7,6,4; (w<<4) ^ w must have bit4 set (bit0 != bit4); bit3 is OR-accumulated.
-struct ValidAcc {
-    uint32_t a1 = 0, a2 = 0xFFFFFFFFu, any = 0;
-    __device__ __forceinline__ void add(uint32_t w, uint32_t m) {
-        const uint32_t y = m * 6u + 0x40404040u;
-        const uint32_t z = w * 16u;
-        a1 |= y ^ w;
-        a2 &= z ^ w;
-        any |= w;
-    }
-    __device__ __forceinline__ uint32_t bad() const {
-        return (a1 & 0xD0D0D0D0u) | (~a2 & 0x10101010u) | (any & 0x08080808u);
-    }
-};
-__device__ __forceinline__ uint32_t packWord(uint32_t w, ValidAcc &v) {
-    const uint32_t m = w & 0x06060606u;
-    v.add(w, m);
-    return m * 0x00820820u;
-}
-__device__ __forceinline__ uint32_t pack16v(const uint4 &q, ValidAcc &v) {
-    const uint32_t a = packWord(q.x, v), b = packWord(q.y, v), c = packWord(q.z, v), d = packWord(q.w, v);
-    return __byte_perm(__byte_perm(a, b, 0x0073), __byte_perm(c, d, 0x0073), 0x5410);
-}
-
 __device__ __forceinline__ bool isBase(uint32_t c) {
     c &= 0xDFu;
     return c == 'A' || c == 'C' || c == 'G' || c == 'T';
@@ -149,10 +119,6 @@ struct TileMeta {
     uint32_t firstWin;      // window index of shared counter slot 0
     uint32_t single;        // 1: region 0 covers the whole tile
     uint32_t relBase;       // single: item-relative position of tile byte 0
-    uint32_t fast;          // 1: lean path (single region, genome mode, one direct pattern length)
-    uint32_t termMixed;     // fast: 1 when matches of this tile can be "terminal" (src/teloscope.cpp:451-459)
-    uint32_t regionEndQ;    // fast: tile position one past the region's last base
-    uint32_t item, itemLen, winBase;
 };
 
 struct Located {
@@ -239,17 +205,28 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
     uint8_t *sTile = sFlags + kFlagTabBytes;
     constexpr int kTileStride = kTileSmemBytes + kTileHalo;
     uint16_t *sQueueAll = reinterpret_cast<uint16_t *>(sTile + 2 * kTileStride);
-    uint32_t *sPackedAll = reinterpret_cast<uint32_t *>(sQueueAll + kScanWarps * kQueueCap);      // [warps][kPackedWords]
-    DevRegion *sRegionsAll = reinterpret_cast<DevRegion *>(sPackedAll + kScanWarps * kPackedWords);  // [2][cache]
-    uint32_t *sWinAll = reinterpret_cast<uint32_t *>(sRegionsAll + 2 * kRegionCache);              // [2][slots][8]
-    uint32_t *sItemAll = sWinAll + 2 * kWindowSlots * 8;                                           // [2][8]
-    TileMeta *sMetaAll = reinterpret_cast<TileMeta *>(sItemAll + 2 * 8);                           // [2]
+    DevRegion *sRegionsAll = reinterpret_cast<DevRegion *>(sQueueAll + kScanWarps * kQueueCap);   // [2][cache]
+    uint32_t *sWinAll = reinterpret_cast<uint32_t *>(sRegionsAll + 2 * kRegionCache);              // [2][slots][4]
+    TileMeta *sMetaAll = reinterpret_cast<TileMeta *>(sWinAll + 2 * kWindowSlots * 4);             // [2]
     uint64_t *sBar = reinterpret_cast<uint64_t *>(sMetaAll + 2);                                   // [2]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t laneLt = (1u << lane) - 1u;
     const DevConfig &cfg = p.cfg;
     uint16_t *sQueue = sQueueAll + warp * kQueueCap;
+
+    // ---- work list: whole tiles, then single rows handed back by the lean kernel ---------------------
+    const uint32_t nRedo = p.redoCount ? min(*p.redoCount, p.redoCap) : 0u;
+    const uint32_t nWorkItems = p.nWork + nRedo;
+    const uint32_t G = gridDim.x;
+    uint32_t work = blockIdx.x;
+    if (work >= nWorkItems) return;
+    auto workTile = [&](uint32_t i, uint32_t &rows) -> uint32_t {
+        if (i < p.nWork) { rows = 0xFFFFFFFFu; return p.workTiles ? p.workTiles[i] : i; }
+        const uint32_t e = p.redoList[i - p.nWork];
+        rows = 1u << (e & 31u);
+        return e >> 5;
+    };
 
     // ---- one-time setup: tables to shared memory, barriers --------------------------------------
     for (int i = tid; i < 65536 / 16; i += kScanThreads)
@@ -276,31 +253,29 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
         const uint32_t idx = min(t.firstRegion + static_cast<uint32_t>(lane), p.nRegions - 1);
         return p.regions[idx];
     };
-    const bool fastConfig = cfg.mode == 0 && cfg.nClasses == 1 && cfg.cls[0].direct != 0 &&
-                            cfg.windowSize >= kMinFastWindow && cfg.cls[0].len + NPOS <= 9;
 
-    const uint32_t G = gridDim.x;
-    uint32_t tileIdx = blockIdx.x;
-    if (tileIdx >= p.nTiles) return;
-    // software pipeline registers: descriptors of tile k (cur), k+1 (next); regions of cur
-    DevTile tCur = p.tiles[tileIdx];
-    DevTile tNext = tileIdx + G < p.nTiles ? p.tiles[tileIdx + G] : DevTile{};
+    // software pipeline registers: descriptors of work item k (cur), k+1 (next); regions of cur
+    uint32_t rowsCur, rowsNext = 0, rowsNext2 = 0;
+    uint32_t tileCur = workTile(work, rowsCur), tileNext = 0, tileNext2 = 0;
+    DevTile tCur = p.tiles[tileCur];
+    DevTile tNext{};
+    if (work + G < nWorkItems) { tileNext = workTile(work + G, rowsNext); tNext = p.tiles[tileNext]; }
     DevRegion rCur{};
     if (warp == 0) rCur = loadRegion(tCur);
     if (tid == 0) issueLoad(tCur, 0);
 
-    for (uint32_t iter = 0; tileIdx < p.nTiles; ++iter, tileIdx += G) {
+    for (uint32_t iter = 0; work < nWorkItems; ++iter, work += G) {
         const int buf = iter & 1;
         const uint8_t *tile = sTile + buf * kTileStride;
         DevRegion *sRegions = sRegionsAll + buf * kRegionCache;
-        uint32_t *sWin = sWinAll + buf * kWindowSlots * 8;
-        uint32_t *sItem = sItemAll + buf * 8;
-        const bool hasNext = tileIdx + G < p.nTiles;
+        uint32_t *sWin = sWinAll + buf * kWindowSlots * 4;
+        const bool hasNext = work + G < nWorkItems;
+        const uint32_t tileIdx = tileCur, rowMask = rowsCur;
 
-        // ---- prefetch: data of tile k+1, descriptor of k+2, regions of k+1 (all consumed later) ----
+        // ---- prefetch: data of item k+1, descriptor of k+2, regions of k+1 (all consumed later) ----
         if (tid == 0 && hasNext) issueLoad(tNext, buf ^ 1);
         DevTile tNext2{};
-        if (tileIdx + 2 * G < p.nTiles) tNext2 = p.tiles[tileIdx + 2 * G];
+        if (work + 2 * G < nWorkItems) { tileNext2 = workTile(work + 2 * G, rowsNext2); tNext2 = p.tiles[tileNext2]; }
         DevRegion rNext{};
         if (warp == 0 && hasNext) rNext = loadRegion(tNext);
 
@@ -318,19 +293,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                 const uint32_t relFirst = rCur.relStart + static_cast<uint32_t>(s - rCur.bufStart);
                 m.relBase = rCur.relStart + static_cast<uint32_t>(tCur.bufStart - rCur.bufStart);   // valid if single
                 m.firstWin = (cfg.mode == 0 && n > 0) ? rCur.winBase + divWindow(cfg, relFirst) : 0;
-                m.fast = fastConfig && m.single;
-                m.item = rCur.item; m.itemLen = rCur.itemLen; m.winBase = rCur.winBase;
-                m.regionEndQ = rCur.relStart + rCur.len - m.relBase;
-                // no position of the tile is <= T or >= n - T  ->  no match of it is "terminal"
-                const uint32_t T = cfg.terminalLimit, nIt = rCur.itemLen;
-                const uint32_t termEnd = nIt > T ? nIt - T : 0;
-                m.termMixed = !(m.relBase > T && static_cast<uint64_t>(m.relBase) + m.len <= termEnd);
                 sMetaAll[buf] = m;
             }
         }
-        for (int i = tid; i < kWindowSlots * 8 + 8; i += kScanThreads) {
-            if (i < kWindowSlots * 8) sWin[i] = 0; else sItem[i - kWindowSlots * 8] = 0;
-        }
+        if (COUNT)
+            for (int i = tid; i < kWindowSlots * 4; i += kScanThreads) sWin[i] = 0;
         __syncthreads();
         const TileMeta t = sMetaAll[buf];
         const uint32_t skew = static_cast<uint32_t>(t.bufStart & 15ull);
@@ -338,335 +305,147 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
         const uint32_t winBase0 = sRegions[0].winBase;
         mbarWait(&sBar[buf], (iter >> 1) & 1u);
 
-        // ---- per-warp state -----------------------------------------------------------------
-        uint32_t wMatches = 0;      // match records this warp has produced for the tile
-        uint32_t ovBase = kNoOverflow;
-        const size_t slotIdx = static_cast<size_t>(tileIdx) * kScanWarps + warp;
-        DevMatch *slot = p.slots + slotIdx * p.slotCap;
-
         auto addAcgt = [&](uint32_t win, uint32_t a, uint32_t c, uint32_t g, uint32_t tt) {   // one lane
             const uint32_t s = win - t.firstWin;
-            uint32_t *w = s < kWindowSlots ? sWin + s * 8 : p.windows + static_cast<size_t>(win) * 8;
+            uint32_t *w = s < kWindowSlots ? sWin + s * 4 : p.windows + static_cast<size_t>(win) * 8;
             if (a) atomicAdd(w + 0, a);
             if (c) atomicAdd(w + 1, c);
             if (g) atomicAdd(w + 2, g);
             if (tt) atomicAdd(w + 3, tt);
         };
 
-        // ---- stage 2 (general): verify up to 32 queued candidates and emit match records -------------
-        auto resolveBatch = [&](uint32_t from, uint32_t count) {
-            uint32_t hitMask = 0, flagBits = 0, rel = 0, region = 0, termBit = 0;
-            if (lane < static_cast<int>(count)) {
-                const uint32_t sb = sQueue[from + lane];
-                const uint32_t q = sb - skew;                       // tile position (wraps if before the tile)
-                bool ok = q < t.len;
-                uint32_t limit = 0, item = 0, itemLen = 0, winBaseLoc = 0;
-                if (t.single) {
-                    rel = t.relBase + q;
-                    limit = regionEnd0;
-                } else if (ok) {
-                    const Located loc = locate(p, t, sRegions, static_cast<int>(q));
-                    ok = loc.ok;
-                    rel = loc.rel; limit = loc.regionEndRel; item = loc.item; itemLen = loc.itemLen; winBaseLoc = loc.winBase;
-                    region = loc.cacheIdx == 0xFFFFFFFFu ? kRegionAccounted : loc.cacheIdx;
-                }
-                if (ok) {
-                    if (cfg.mode == 0) {     // matches never cross the window end (src/teloscope.cpp:439)
-                        const uint64_t wEnd = static_cast<uint64_t>(divWindow(cfg, rel) + 1) * cfg.windowSize;
-                        if (wEnd < limit) limit = static_cast<uint32_t>(wEnd);
-                    }
-                    const uint32_t room = limit - rel;              // >= 1
-                    if (room >= cfg.minLen) {
-                        // 8 bytes at sb (unaligned) as two words
-                        const uint32_t a = sb & ~3u, sh = (sb & 3u) * 8u;
-                        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(tile + a);
-                        const uint32_t w1 = *reinterpret_cast<const uint32_t *>(tile + a + 4);
-                        const uint32_t w2 = *reinterpret_cast<const uint32_t *>(tile + a + 8);
-                        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
-                        uint64_t key = pack4(x0) | (pack4(x1) << 8);
-                        const uint32_t b0 = badBytes(x0), b1 = badBytes(x1);
-                        uint32_t nValid = b0 ? (__ffs(b0) - 1) >> 3 : (b1 ? 4 + ((__ffs(b1) - 1) >> 3) : 8);
-                        if (nValid == 8 && cfg.maxLen > 8 && room > 8) {   // long patterns: byte loop
-                            const uint32_t need = min(cfg.maxLen, room);
-                            for (uint32_t j = 8; j < need; ++j) {
-                                const uint32_t c = tile[sb + j];
-                                if (!isBase(c)) break;
-                                key |= static_cast<uint64_t>((c >> 1) & 3u) << (2 * j);
-                                ++nValid;
-                            }
-                        }
-                        const uint32_t usable = min(nValid, room);
-                        for (uint32_t ci = 0; ci < cfg.nClasses; ++ci) {
-                            const DevLenClass &lc = cfg.cls[ci];
-                            if (lc.len > usable) break;
-                            const uint64_t k = lc.len >= 32 ? key : (key & ((1ull << (2 * lc.len)) - 1ull));
-                            uint32_t f = 0;
-                            if (lc.direct) {
-                                f = sFlags[lc.flagOffset + static_cast<uint32_t>(k)];
-                            } else {
-                                uint32_t lo = lc.sortedBegin, hi = lc.sortedBegin + lc.sortedCount;
-                                while (lo < hi) {
-                                    const uint32_t mid = (lo + hi) >> 1;
-                                    if (p.sortedKeys[mid] < k) lo = mid + 1; else hi = mid;
-                                }
-                                if (lo < lc.sortedBegin + lc.sortedCount && p.sortedKeys[lo] == k) f = p.sortedFlags[lo];
-                            }
-                            if (f & 1u) {
-                                hitMask |= 1u << ci;
-                                flagBits |= ((f >> 1) & 3u) << (2 * ci);
-                            }
-                        }
-                    }
-                }
-                if (hitMask && region == kRegionAccounted && !t.single) {
-                    // region beyond the shared cache (> 32 regions in one tile): do the gather pass's
-                    // accounting here, with global atomics
-                    DevItemCounts *c = p.itemCounts + item;
-                    const uint32_t winIdx = cfg.mode == 0 ? divWindow(cfg, rel) : 0;
-                    const bool term = cfg.mode == 0 && isTerminalMatch(cfg, rel, winIdx, itemLen);
-                    if (term) termBit = kMatchTerm;
-                    for (uint32_t hm = hitMask; hm; hm &= hm - 1) {
-                        const int ci = __ffs(hm) - 1;
-                        const uint32_t fl = (flagBits >> (2 * ci)) & 3u, len = cfg.cls[ci].len;
-                        atomicAdd(&c->all, 1u);
-                        atomicAdd((fl & 1u) ? &c->fwd : &c->rev, 1u);
-                        if (fl & 2u) atomicAdd(&c->can, 1u);
-                        else if (term) atomicAdd(&c->nonCanTerm, 1u);
-                        if (cfg.mode == 0) {
-                            uint32_t *w = p.windows + static_cast<size_t>(winBaseLoc + winIdx) * 8;
-                            atomicAdd(w + ((fl & 2u) ? 4 : 5), len);
-                            atomicAdd(w + ((fl & 1u) ? 6 : 7), len);
-                        }
-                    }
-                }
-            }
-            // ---- ordered emission into the warp's slot ---------------------------------------------
-            const uint32_t nHit = __popc(hitMask);
-            const uint32_t have = __ballot_sync(0xFFFFFFFFu, nHit != 0);
-            if (have == 0) return;
-            uint32_t excl, total;
-            if (cfg.nClasses == 1) {
-                excl = __popc(have & laneLt);
-                total = __popc(have);
-            } else {
-                const uint32_t incl = warpInclusiveScan(nHit);
-                total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                excl = incl - nHit;
-            }
-            if (wMatches + total > p.slotCap && ovBase == kNoOverflow) {
-                if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
-                ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
-            }
-            uint32_t o = wMatches + excl;
-            for (uint32_t hm = hitMask; hm; hm &= hm - 1, ++o) {
-                const int ci = __ffs(hm) - 1;
-                DevMatch m;
-                m.pos = rel;
-                m.len = static_cast<uint16_t>(cfg.cls[ci].len);
-                m.flags = static_cast<uint8_t>(((flagBits >> (2 * ci)) & 3u) | termBit);   // kMatchFwd | kMatchCan
-                m.region = static_cast<uint8_t>(region);
-                if (o < p.slotCap) slot[o] = m;
-                else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap) p.ovArena[ovBase + (o - p.slotCap)] = m;
-            }
-            wMatches += total;
-        };
-
         const uint32_t usedBytes = skew + t.len;
-        uint32_t cand[kRowsPerWarp][2];
-        static_assert(kRowsPerWarp == 2, "candidate counts of the rows are scanned as two 16-bit fields");
-        bool fastResolve = false;
+#pragma unroll 1
+        for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+            const uint32_t row = warp * kRowsPerWarp + rr;
+            if (!((rowMask >> row) & 1u)) continue;            // warp-uniform
+            // ---- per-row state: every row owns one output slot ------------------------------------------
+            uint32_t wMatches = 0;      // match records this row has produced
+            uint32_t ovBase = kNoOverflow;
+            const size_t slotIdx = static_cast<size_t>(tileIdx) * kTileRows + row;
+            DevMatch *slot = p.slots + slotIdx * p.slotCap;
+            uint32_t candLo = 0, candHi = 0;
 
-        if (t.fast) {
-            // =====================================================================================
-            // Lean path: the tile lies inside one contig (genome mode, one direct pattern length)
-            // =====================================================================================
-            const uint32_t L = cfg.cls[0].len;
-            const uint32_t blockByte = warp * (kRowsPerWarp * kRowBytes);
-            uint32_t *sPk = sPackedAll + warp * kPackedWords;
-            // match starts are allowed at tile positions [0, candLimitQ): inside the tile and with
-            // the whole match inside the region (src/teloscope.cpp:439 scanLimit)
-            const uint32_t candLimitQ = min(t.len, t.regionEndQ >= L ? t.regionEndQ - (L - 1) : 0u);
-            uint32_t W[kRowsPerWarp][4];
-            uint32_t totAC[kRowsPerWarp], totGT[kRowsPerWarp];     // A | C << 16, G | T << 16 of the whole span
-            uint32_t notPlain = 0;                                   // bit rr: span of row rr needs the fix-up pass
-            bool laneBad = false;
-#pragma unroll
-            for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-                cand[rr][0] = cand[rr][1] = 0;
-                W[rr][0] = W[rr][1] = W[rr][2] = W[rr][3] = 0;
-                totAC[rr] = totGT[rr] = 0;
-                const uint32_t rowByte = blockByte + rr * kRowBytes;
-                if (rowByte >= usedBytes + kTileHalo) continue;              // warp-uniform
-                const uint32_t spanByte = rowByte + lane * kSpanBytes;
-                const uint4 *src = reinterpret_cast<const uint4 *>(tile + spanByte);
-                const uint4 c0 = src[0], c1 = src[1], c2 = src[2];
-                ValidAcc va;
-                W[rr][0] = pack16v(c0, va); W[rr][1] = pack16v(c1, va); W[rr][2] = pack16v(c2, va);
-                const bool inRange = spanByte < usedBytes + kTileHalo;
-                if (inRange && va.bad()) { laneBad = true; notPlain |= 1u << rr; }
-                sPk[rr * (kRowBytes / 16) + lane * 3 + 0] = W[rr][0];
-                sPk[rr * (kRowBytes / 16) + lane * 3 + 1] = W[rr][1];
-                sPk[rr * (kRowBytes / 16) + lane * 3 + 2] = W[rr][2];
-            }
-            // ---- halo word of every span: the next lane's first word; the block's last span reads ahead
-            {
-                uint32_t tail = 0;
-                if (lane == 31) {
-                    const uint32_t endByte = blockByte + kRowsPerWarp * kRowBytes;   // 8-byte aligned
-                    if (endByte < usedBytes + kTileHalo) {
-                        const uint2 h = *reinterpret_cast<const uint2 *>(tile + endByte);
-                        ValidAcc va;
-                        tail = (packWord(h.x, va) >> 24) | ((packWord(h.y, va) >> 24) << 8);
-                        if (va.bad()) laneBad = true;
+            // ---- stage 2: verify up to 32 queued candidates and emit match records ---------------------
+            auto resolveBatch = [&](uint32_t from, uint32_t count) {
+                uint32_t hitMask = 0, flagBits = 0, rel = 0, region = 0, termBit = 0;
+                if (lane < static_cast<int>(count)) {
+                    const uint32_t sb = sQueue[from + lane];
+                    const uint32_t q = sb - skew;                       // tile position (wraps if before the tile)
+                    bool ok = q < t.len;
+                    uint32_t limit = 0, item = 0, itemLen = 0, winBaseLoc = 0;
+                    if (t.single) {
+                        rel = t.relBase + q;
+                        limit = regionEnd0;
+                    } else if (ok) {
+                        const Located loc = locate(p, t, sRegions, static_cast<int>(q));
+                        ok = loc.ok;
+                        rel = loc.rel; limit = loc.regionEndRel; item = loc.item; itemLen = loc.itemLen; winBaseLoc = loc.winBase;
+                        region = loc.cacheIdx == 0xFFFFFFFFu ? kRegionAccounted : loc.cacheIdx;
                     }
-                    sPk[kRowsPerWarp * (kRowBytes / 16)] = tail;
-                }
-                const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, lane == 0 ? W[1][0] : W[0][0], (lane + 1) & 31);
-                const uint32_t n1 = __shfl_down_sync(0xFFFFFFFFu, W[1][0], 1);
-                W[0][3] = n0;
-                W[1][3] = lane == 31 ? tail : n1;
-            }
-            const bool warpBad = __any_sync(0xFFFFFFFFu, laneBad);
-
-#pragma unroll
-            for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-                const uint32_t rowByte = blockByte + rr * kRowBytes;
-                if (rowByte >= usedBytes) continue;                            // warp-uniform
-                // ---- stage 1: one table byte per NPOS start positions ---------------------------------
-                uint32_t candLo = 0, candHi = 0;
-#pragma unroll
-                for (int tl = 0; tl < kSpanBytes / NPOS; ++tl) {
-                    const int bit = 2 * NPOS * tl, wi = bit >> 5, sh = bit & 31;
-                    const uint32_t x = sh == 0 ? W[rr][wi] : (sh <= 16 ? W[rr][wi] >> sh : __funnelshift_r(W[rr][wi], W[rr][wi + 1], sh));
-                    const uint32_t e = sIndex[x & 0xFFFFu];
-                    const int pos = NPOS * tl;
-                    if (pos < 32) {
-                        candLo |= e << pos;
-                        if (pos + NPOS > 32) candHi |= e >> (32 - pos);
-                    } else {
-                        candHi |= e << (pos - 32);
-                    }
-                }
-                candHi &= 0xFFFFu;
-                // ---- lane classification -----------------------------------------------------------------
-                const int q0 = static_cast<int>(rowByte + lane * kSpanBytes) - static_cast<int>(skew);
-                const uint32_t relA = t.relBase + static_cast<uint32_t>(q0);
-                const uint32_t winA = divWindow(cfg, relA);
-                const uint32_t toNext = (winA + 1) * cfg.windowSize - relA;    // exact in 32-bit wrap arithmetic
-                const bool plain = q0 >= 0 && q0 + kSpanBytes <= static_cast<int>(candLimitQ) &&
-                                   toNext >= static_cast<uint32_t>(kSpanBytes) + L - 1 && !((notPlain >> rr) & 1u);
-                if (!plain) notPlain |= 1u << rr;
-                cand[rr][0] = candLo; cand[rr][1] = candHi;
-                if (COUNT) {
-                    // ---- A/C/G/T of the whole span: bit planes of 32 + 16 bases ----------------------------
-                    const uint32_t w0 = W[rr][0], w1 = W[rr][1], w2 = W[rr][2];
-                    const uint32_t e01 = (w0 & 0x55555555u) | ((w1 << 1) & 0xAAAAAAAAu);   // bit1 of the codes: C or G
-                    const uint32_t o01 = ((w0 >> 1) & 0x55555555u) | (w1 & 0xAAAAAAAAu);   // bit2 of the codes: G or T
-                    const uint32_t e2 = w2 & 0x55555555u, o2 = (w2 >> 1) & 0x55555555u;
-                    const uint32_t nE = __popc(e01) + __popc(e2), nO = __popc(o01) + __popc(o2);
-                    const uint32_t nG = __popc(e01 & o01) + __popc(e2 & o2);
-                    totAC[rr] = (kSpanBytes - nE - nO + nG) | ((nE - nG) << 16);
-                    totGT[rr] = nG | ((nO - nG) << 16);
-                    // ---- plain spans: whole-span counts go to one window; reduce over the warp -------------
-                    const uint32_t ws = t.winBase + winA - t.firstWin;
-                    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, plain);
-                    if (pm) {
-                        const uint32_t gFirst = __shfl_sync(0xFFFFFFFFu, ws, __ffs(pm) - 1);
-                        const uint32_t gLast = __shfl_sync(0xFFFFFFFFu, ws, 31 - __clz(pm));
-                        for (uint32_t g = gFirst; g <= gLast; ++g) {
-                            const bool mine = plain && ws == g;
-                            const uint32_t s0 = __reduce_add_sync(0xFFFFFFFFu, mine ? totAC[rr] : 0u);
-                            const uint32_t s1 = __reduce_add_sync(0xFFFFFFFFu, mine ? totGT[rr] : 0u);
-                            if (lane < 4) {
-                                const uint32_t v = ((lane & 2) ? s1 : s0) >> ((lane & 1) * 16) & 0xFFFFu;
-                                if (v) {
-                                    if (g < kWindowSlots) atomicAdd(sWin + g * 8 + lane, v);
-                                    else atomicAdd(p.windows + static_cast<size_t>(t.firstWin + g) * 8 + lane, v);
+                    if (ok) {
+                        if (cfg.mode == 0) {     // matches never cross the window end (src/teloscope.cpp:439)
+                            const uint64_t wEnd = static_cast<uint64_t>(divWindow(cfg, rel) + 1) * cfg.windowSize;
+                            if (wEnd < limit) limit = static_cast<uint32_t>(wEnd);
+                        }
+                        const uint32_t room = limit - rel;              // >= 1
+                        if (room >= cfg.minLen) {
+                            // 8 bytes at sb (unaligned) as two words
+                            const uint32_t a = sb & ~3u, sh = (sb & 3u) * 8u;
+                            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(tile + a);
+                            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(tile + a + 4);
+                            const uint32_t w2 = *reinterpret_cast<const uint32_t *>(tile + a + 8);
+                            const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+                            uint64_t key = pack4(x0) | (pack4(x1) << 8);
+                            const uint32_t b0 = badBytes(x0), b1 = badBytes(x1);
+                            uint32_t nValid = b0 ? (__ffs(b0) - 1) >> 3 : (b1 ? 4 + ((__ffs(b1) - 1) >> 3) : 8);
+                            if (nValid == 8 && cfg.maxLen > 8 && room > 8) {   // long patterns: byte loop
+                                const uint32_t need = min(cfg.maxLen, room);
+                                for (uint32_t j = 8; j < need; ++j) {
+                                    const uint32_t c = tile[sb + j];
+                                    if (!isBase(c)) break;
+                                    key |= static_cast<uint64_t>((c >> 1) & 3u) << (2 * j);
+                                    ++nValid;
+                                }
+                            }
+                            const uint32_t usable = min(nValid, room);
+                            for (uint32_t ci = 0; ci < cfg.nClasses; ++ci) {
+                                const DevLenClass &lc = cfg.cls[ci];
+                                if (lc.len > usable) break;
+                                const uint64_t k = lc.len >= 32 ? key : (key & ((1ull << (2 * lc.len)) - 1ull));
+                                uint32_t f = 0;
+                                if (lc.direct) {
+                                    f = sFlags[lc.flagOffset + static_cast<uint32_t>(k)];
+                                } else {
+                                    uint32_t lo = lc.sortedBegin, hi = lc.sortedBegin + lc.sortedCount;
+                                    while (lo < hi) {
+                                        const uint32_t mid = (lo + hi) >> 1;
+                                        if (p.sortedKeys[mid] < k) lo = mid + 1; else hi = mid;
+                                    }
+                                    if (lo < lc.sortedBegin + lc.sortedCount && p.sortedKeys[lo] == k) f = p.sortedFlags[lo];
+                                }
+                                if (f & 1u) {
+                                    hitMask |= 1u << ci;
+                                    flagBits |= ((f >> 1) & 3u) << (2 * ci);
                                 }
                             }
                         }
                     }
-                }
-            }
-
-            // ---- fix-up pass: spans that touch the tile / region edge, a window end or a non-ACGT byte ----
-            for (uint32_t pend = notPlain; pend; pend &= pend - 1) {
-                const int rr = __ffs(pend) - 1;
-                const uint32_t rowByte = blockByte + rr * kRowBytes;
-                if (rowByte >= usedBytes) { if (rr == 0) cand[0][0] = cand[0][1] = 0; else cand[1][0] = cand[1][1] = 0; continue; }
-                const uint32_t spanByte = rowByte + lane * kSpanBytes;
-                const int q0 = static_cast<int>(spanByte) - static_cast<int>(skew);
-                const int lo = q0 < 0 ? -q0 : 0;
-                int hi = static_cast<int>(t.len) - q0; hi = hi > kSpanBytes ? kSpanBytes : hi;
-                int keepHi = static_cast<int>(candLimitQ) - q0; keepHi = keepHi > kSpanBytes ? kSpanBytes : keepHi;
-                uint64_t keep = 0;
-                uint32_t relLo = 0, winLo = 0;
-                int pb = 1 << 20;                                   // span position of the next window's first base
-                if (lo < hi) {
-                    relLo = t.relBase + static_cast<uint32_t>(q0 + lo);
-                    winLo = divWindow(cfg, relLo);
-                    const uint32_t toNext = (winLo + 1) * cfg.windowSize - relLo;
-                    if (toNext < 4096u) pb = lo + static_cast<int>(toNext);
-                    if (keepHi > lo) keep = ((1ull << keepHi) - 1ull) & ~((1ull << lo) - 1ull);
-                    // matches never cross the window end (src/teloscope.cpp:439): starts in [pb-L+1, pb) are dead
-                    const int ds = pb - static_cast<int>(L) + 1 < 0 ? 0 : pb - static_cast<int>(L) + 1;
-                    if (ds < kSpanBytes) {
-                        const int de = pb > kSpanBytes ? kSpanBytes : pb;
-                        keep &= ~(((1ull << de) - 1ull) & ~((1ull << ds) - 1ull));
-                    }
-                }
-                const uint32_t kLo = static_cast<uint32_t>(keep), kHi = static_cast<uint32_t>(keep >> 32);
-                if (rr == 0) { cand[0][0] &= kLo; cand[0][1] &= kHi; } else { cand[1][0] &= kLo; cand[1][1] &= kHi; }
-                if (COUNT && lo < hi) {
-                    const uint32_t wsLo = t.winBase + winLo;        // global window index of position lo
-                    const bool spanBad = [&]() {
-                        // recheck this span only (laneBad may come from the other row)
-                        const uint4 *src = reinterpret_cast<const uint4 *>(tile + spanByte);
-                        ValidAcc va;
-                        (void)pack16v(src[0], va); (void)pack16v(src[1], va); (void)pack16v(src[2], va);
-                        return va.bad() != 0;
-                    }();
-                    if (spanBad) {
-                        for (int i = lo; i < hi; ++i) {
-                            const uint32_t c = tile[spanByte + i];
-                            if (!isBase(c)) continue;
-                            const uint32_t code = (c >> 1) & 3u;                // A0 C1 T2 G3
-                            addAcgt(wsLo + (i >= pb ? 1u : 0u), code == 0, code == 1, code == 3, code == 2);
+                    if (hitMask && region == kRegionAccounted && !t.single) {
+                        // region beyond the shared cache (> 32 regions in one tile): do the gather pass's
+                        // accounting here, with global atomics
+                        DevItemCounts *c = p.itemCounts + item;
+                        const uint32_t winIdx = cfg.mode == 0 ? divWindow(cfg, rel) : 0;
+                        const bool term = cfg.mode == 0 && isTerminalMatch(cfg, rel, winIdx, itemLen);
+                        if (term) termBit = kMatchTerm;
+                        for (uint32_t hm = hitMask; hm; hm &= hm - 1) {
+                            const int ci = __ffs(hm) - 1;
+                            const uint32_t fl = (flagBits >> (2 * ci)) & 3u, len = cfg.cls[ci].len;
+                            atomicAdd(&c->all, 1u);
+                            atomicAdd((fl & 1u) ? &c->fwd : &c->rev, 1u);
+                            if (fl & 2u) atomicAdd(&c->can, 1u);
+                            else if (term) atomicAdd(&c->nonCanTerm, 1u);
+                            if (cfg.mode == 0) {
+                                uint32_t *w = p.windows + static_cast<size_t>(winBaseLoc + winIdx) * 8;
+                                atomicAdd(w + ((fl & 2u) ? 4 : 5), len);
+                                atomicAdd(w + ((fl & 1u) ? 6 : 7), len);
+                            }
                         }
-                    } else {
-                        const uint32_t *wp = sPk + rr * (kRowBytes / 16) + lane * 3;
-                        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-                        auto prefix = [&](int x, uint32_t &ac, uint32_t &gt) {   // counts of span positions [0, x)
-                            const uint32_t m0 = evenMaskBelow(x), m1 = evenMaskBelow(x - 16), m2 = evenMaskBelow(x - 32);
-                            const uint32_t e0 = w0 & m0, e1 = w1 & m1, e2 = w2 & m2;
-                            const uint32_t o0 = (w0 >> 1) & m0, o1 = (w1 >> 1) & m1, o2 = (w2 >> 1) & m2;
-                            const uint32_t nE = __popc(e0) + __popc(e1) + __popc(e2), nO = __popc(o0) + __popc(o1) + __popc(o2);
-                            const uint32_t nG = __popc(e0 & o0) + __popc(e1 & o1) + __popc(e2 & o2);
-                            ac = (static_cast<uint32_t>(x) - nE - nO + nG) | ((nE - nG) << 16);
-                            gt = nG | ((nO - nG) << 16);
-                        };
-                        const int split = pb < hi ? pb : hi;
-                        uint32_t acLo = 0, gtLo = 0, acSp, gtSp, acHi, gtHi;
-                        if (lo > 0) prefix(lo, acLo, gtLo);
-                        if (hi == kSpanBytes) { acHi = rr == 0 ? totAC[0] : totAC[1]; gtHi = rr == 0 ? totGT[0] : totGT[1]; }
-                        else prefix(hi, acHi, gtHi);
-                        if (split == hi) { acSp = acHi; gtSp = gtHi; } else prefix(split, acSp, gtSp);
-                        const uint32_t aAC = acSp - acLo, aGT = gtSp - gtLo, bAC = acHi - acSp, bGT = gtHi - gtSp;
-                        addAcgt(wsLo, aAC & 0xFFFFu, aAC >> 16, aGT & 0xFFFFu, aGT >> 16);
-                        if (bAC | bGT) addAcgt(wsLo + 1, bAC & 0xFFFFu, bAC >> 16, bGT & 0xFFFFu, bGT >> 16);
                     }
                 }
-            }
-            __syncwarp();
-            fastResolve = !warpBad;
-        } else {
-        // ---- general path: main loop over this warp's rows ------------------------------------------
-#pragma unroll
-        for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-            cand[rr][0] = cand[rr][1] = 0;
-            const uint32_t row = warp * kRowsPerWarp + rr;
-            if (row * kRowBytes >= usedBytes) continue;      // warp-uniform
+                // ---- ordered emission into the row's slot ---------------------------------------------
+                const uint32_t nHit = __popc(hitMask);
+                const uint32_t have = __ballot_sync(0xFFFFFFFFu, nHit != 0);
+                if (have == 0) return;
+                uint32_t excl, total;
+                if (cfg.nClasses == 1) {
+                    excl = __popc(have & laneLt);
+                    total = __popc(have);
+                } else {
+                    const uint32_t incl = warpInclusiveScan(nHit);
+                    total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    excl = incl - nHit;
+                }
+                if (wMatches + total > p.slotCap && ovBase == kNoOverflow) {
+                    if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
+                    ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
+                }
+                uint32_t o = wMatches + excl;
+                for (uint32_t hm = hitMask; hm; hm &= hm - 1, ++o) {
+                    const int ci = __ffs(hm) - 1;
+                    DevMatch m;
+                    m.pos = rel;
+                    m.len = static_cast<uint16_t>(cfg.cls[ci].len);
+                    m.flags = static_cast<uint8_t>(((flagBits >> (2 * ci)) & 3u) | termBit);   // kMatchFwd | kMatchCan
+                    m.region = static_cast<uint8_t>(region);
+                    if (o < p.slotCap) slot[o] = m;
+                    else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap) p.ovArena[ovBase + (o - p.slotCap)] = m;
+                }
+                wMatches += total;
+            };
+
             const uint32_t spanByte = row * kRowBytes + lane * kSpanBytes;
+            if (row * kRowBytes < usedBytes) {                   // warp-uniform
             const uint4 *src = reinterpret_cast<const uint4 *>(tile + spanByte);
             const uint4 c0 = src[0], c1 = src[1], c2 = src[2], c3 = src[3];
             uint32_t W[5];
@@ -763,7 +542,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
             }
 
             // ---- stage 1: one table byte per NPOS start positions ---------------------------------
-            uint32_t candLo = 0, candHi = 0;
 #pragma unroll
             for (int tl = 0; tl < kSpanBytes / NPOS; ++tl) {
                 const int bit = 2 * NPOS * tl, wi = bit >> 5, sh = bit & 31;
@@ -778,152 +556,57 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                 }
             }
             candHi &= 0xFFFFu;
-            cand[rr][0] = candLo; cand[rr][1] = candHi;
-        }
-        }
+            }
 
-        // ---- compaction: one scan for all rows of the warp, then scatter into the queue ------------------
-        uint32_t rowTotal[kRowsPerWarp], rowExcl[kRowsPerWarp];
-        uint32_t allTotal;
-        {
-            const uint32_t nCand = (__popc(cand[0][0]) + __popc(cand[0][1])) | ((__popc(cand[1][0]) + __popc(cand[1][1])) << 16);
-            const uint32_t incl = warpInclusiveScan(nCand);             // fields: row0 | row1 << 16 (<= 1536 each)
-            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), ex = incl - nCand;
-            rowTotal[0] = tot & 0xFFFFu; rowTotal[1] = tot >> 16;
-            rowExcl[0] = ex & 0xFFFFu; rowExcl[1] = ex >> 16;
-            allTotal = rowTotal[0] + rowTotal[1];
-        }
-        auto scatter = [&](uint32_t lo, uint32_t hi, uint32_t spanByte, uint32_t o) {
-            while (lo) { const int b = __ffs(lo) - 1; lo &= lo - 1; sQueue[o++] = static_cast<uint16_t>(spanByte + b); }
-            while (hi) { const int b = __ffs(hi) - 1; hi &= hi - 1; sQueue[o++] = static_cast<uint16_t>(spanByte + 32 + b); }
-        };
-        if (allTotal <= static_cast<uint32_t>(kQueueCap)) {
-            uint32_t base = 0;
-#pragma unroll
-            for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-                const uint32_t spanByte = (warp * kRowsPerWarp + rr) * kRowBytes + lane * kSpanBytes;
-                scatter(cand[rr][0], cand[rr][1], spanByte, base + rowExcl[rr]);
-                base += rowTotal[rr];
-            }
+            // ---- compaction: scan the row's candidate counts, scatter into the queue ----------------------
+            auto scatter = [&](uint32_t lo, uint32_t hi, uint32_t o) {
+                while (lo) { const int b = __ffs(lo) - 1; lo &= lo - 1; sQueue[o++] = static_cast<uint16_t>(spanByte + b); }
+                while (hi) { const int b = __ffs(hi) - 1; hi &= hi - 1; sQueue[o++] = static_cast<uint16_t>(spanByte + 32 + b); }
+            };
+            const uint32_t nCand = __popc(candLo) + __popc(candHi);
+            const uint32_t incl = warpInclusiveScan(nCand);
+            const uint32_t allTotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
             __syncwarp();
-            if (fastResolve) {
-                // ---- stage 2 (lean): every queue entry is a match; flags from the 2-bit copy ------------
-                const uint32_t L = cfg.cls[0].len;
-                const uint32_t keyMask = (1u << (2 * L)) - 1u;
-                const uint8_t *sFl = sFlags + cfg.cls[0].flagOffset;
-                const uint32_t *sPk = sPackedAll + warp * kPackedWords;
-                const uint32_t blockByte = warp * (kRowsPerWarp * kRowBytes);
-                const uint32_t blockRel0 = t.relBase + blockByte - skew;
-                if (allTotal > p.slotCap) {
-                    if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
-                    ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
-                }
-                // running accumulators of the current window (warp-uniform)
-                uint32_t curWs = 0xFFFFFFFFu, accAll = 0, accCan = 0, accFwd = 0;
-                uint32_t itAll = 0, itFwd = 0, itCan = 0, itNct = 0;
-                auto flushAcc = [&]() {
-                    if (accAll) {
-                        if (lane < 4) {
-                            const uint32_t n = lane == 0 ? accCan : lane == 1 ? accAll - accCan : lane == 2 ? accFwd : accAll - accFwd;
-                            if (n) {
-                                if (curWs < kWindowSlots) atomicAdd(sWin + curWs * 8 + 4 + lane, n * L);
-                                else atomicAdd(p.windows + static_cast<size_t>(t.firstWin + curWs) * 8 + 4 + lane, n * L);
-                            }
-                        }
-                        itAll += accAll; itFwd += accFwd; itCan += accCan;
-                    }
-                    accAll = accCan = accFwd = 0;
-                };
-                for (uint32_t from = 0; from < allTotal; from += 32) {
-                    const uint32_t idx = from + lane;
-                    const bool act = idx < allTotal;
-                    uint32_t f = 0, ws = 0xFFFFFFFFu;
-                    bool term = false;
-                    if (act) {
-                        const uint32_t qq = static_cast<uint32_t>(sQueue[idx]) - blockByte;
-                        const uint32_t wi = qq >> 4, sh = (qq & 15u) * 2u;
-                        const uint32_t key = __funnelshift_r(sPk[wi], sPk[wi + 1], sh) & keyMask;
-                        f = sFl[key];
-                        const uint32_t rel = blockRel0 + qq;
-                        const uint32_t winIdx = divWindow(cfg, rel);
-                        ws = t.winBase + winIdx - t.firstWin;
-                        if (t.termMixed) term = isTerminalMatch(cfg, rel, winIdx, t.itemLen);
-                        DevMatch m;
-                        m.pos = rel;
-                        m.len = static_cast<uint16_t>(L);
-                        m.flags = static_cast<uint8_t>(((f >> 1) & 3u) | (term ? kMatchTerm : 0));
-                        m.region = kRegionAccounted;
-                        if (idx < p.slotCap) slot[idx] = m;
-                        else if (static_cast<uint64_t>(ovBase) + (idx - p.slotCap) < p.ovCap) p.ovArena[ovBase + (idx - p.slotCap)] = m;
-                    }
-                    const uint32_t actB = __ballot_sync(0xFFFFFFFFu, act);
-                    const uint32_t canB = __ballot_sync(0xFFFFFFFFu, (f & 4u) != 0);
-                    const uint32_t fwdB = __ballot_sync(0xFFFFFFFFu, (f & 2u) != 0);
-                    if (t.termMixed) itNct += __popc(__ballot_sync(0xFFFFFFFFu, term && !(f & 4u)));
-                    const uint32_t chg = __ballot_sync(0xFFFFFFFFu, act && ws != curWs);
-                    if (chg == 0) {
-                        accAll += __popc(actB); accCan += __popc(canB); accFwd += __popc(fwdB);
-                    } else {
-                        uint32_t rest = actB;
-                        while (rest) {
-                            const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, ws, __ffs(rest) - 1);
-                            const uint32_t grp = __ballot_sync(0xFFFFFFFFu, ws == w0) & rest;
-                            if (w0 != curWs) { flushAcc(); curWs = w0; }
-                            accAll += __popc(grp); accCan += __popc(grp & canB); accFwd += __popc(grp & fwdB);
-                            rest &= ~grp;
-                        }
-                    }
-                }
-                flushAcc();
-                if (lane < 5 && itAll) {
-                    const uint32_t v = lane == 0 ? itAll : lane == 1 ? itFwd : lane == 2 ? itAll - itFwd : lane == 3 ? itCan : itNct;
-                    if (v) atomicAdd(sItem + lane, v);
-                }
-                wMatches = allTotal;
-            } else {
+            if (allTotal <= static_cast<uint32_t>(kQueueCap)) {
+                scatter(candLo, candHi, incl - nCand);
+                __syncwarp();
                 for (uint32_t from = 0; from < allTotal; from += 32) resolveBatch(from, min(32u, allTotal - from));
-            }
-        } else {
-            // dense tile: 11 lanes at a time (<= 528 candidates per step); lane groups keep genome order
-#pragma unroll
-            for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-                const uint32_t spanByte = (warp * kRowsPerWarp + rr) * kRowBytes + lane * kSpanBytes;
+            } else {
+                // dense row: 11 lanes at a time (<= 528 candidates per step); lane groups keep genome order
                 for (int part = 0; part < 3; ++part) {
                     const bool mine = lane >= 11 * part && lane < 11 * (part + 1);
-                    const uint32_t lo = mine ? cand[rr][0] : 0u, hi = mine ? cand[rr][1] : 0u;
+                    const uint32_t lo = mine ? candLo : 0u, hi = mine ? candHi : 0u;
                     const uint32_t n = __popc(lo) + __popc(hi);
-                    const uint32_t incl = warpInclusiveScan(n);
-                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    const uint32_t in2 = warpInclusiveScan(n);
+                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, in2, 31);
                     __syncwarp();
-                    scatter(lo, hi, spanByte, incl - n);
+                    scatter(lo, hi, in2 - n);
                     __syncwarp();
                     for (uint32_t from = 0; from < total; from += 32) resolveBatch(from, min(32u, total - from));
                 }
             }
-        }
-        if (lane == 0) {
-            p.slotCounts[slotIdx] = wMatches;
-            p.slotOv[slotIdx] = ovBase;
+            if (lane == 0) {
+                p.slotCounts[slotIdx] = wMatches;
+                p.slotOv[slotIdx] = ovBase;
+            }
         }
 
-        // ---- tile epilogue: flush the shared window and item counters ---------------------------------------
+        // ---- tile epilogue: flush the shared A/C/G/T counters ---------------------------------------------
         __syncthreads();
-        for (int i = tid; i < kWindowSlots * 8; i += kScanThreads) {
-            const uint32_t v = sWin[i];
-            if (v) atomicAdd(&p.windows[static_cast<size_t>(t.firstWin + (i >> 3)) * 8 + (i & 7)], v);
-        }
-        if (tid < 5 && t.fast) {
-            const uint32_t v = sItem[tid];
-            if (v) atomicAdd(reinterpret_cast<uint32_t *>(p.itemCounts + t.item) + tid, v);
+        if (COUNT) {
+            for (int i = tid; i < kWindowSlots * 4; i += kScanThreads) {
+                const uint32_t v = sWin[i];
+                if (v) atomicAdd(&p.windows[static_cast<size_t>(t.firstWin + (i >> 2)) * 8 + (i & 3)], v);
+            }
         }
         tCur = tNext; tNext = tNext2; rCur = rNext;
+        tileCur = tileNext; tileNext = tileNext2; rowsCur = rowsNext; rowsNext = rowsNext2;
     }
 }
 
 size_t scanSmemBytes() {
     return 65536 + kFlagTabBytes + 2 * (kTileSmemBytes + kTileHalo) + kScanWarps * kQueueCap * 2 +
-           kScanWarps * kPackedWords * 4 + 2 * kRegionCache * sizeof(DevRegion) + 2 * kWindowSlots * 8 * 4 + 2 * 8 * 4 +
-           2 * sizeof(TileMeta) + 2 * 8 + 64;
+           2 * kRegionCache * sizeof(DevRegion) + 2 * kWindowSlots * 4 * 4 + 2 * sizeof(TileMeta) + 2 * 8 + 64;
 }
 
 cudaError_t launchScan(const ScanParams &p, int grid, cudaStream_t stream) {

@@ -1,6 +1,7 @@
 """CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol
 the header declares, the pattern table producer equals the oracle's (row P of SURVEY §8a), and
 the library refuses to run without a B200 (no CPU fallback)."""
+import numpy as np
 import ctypes as C
 import itertools
 import re
@@ -63,3 +64,36 @@ def test_golden_case_pattern_counts(golden):
         seen.add(key)
         n = len(tb.expand_patterns(cfg.raw_patterns(), cfg.edit_distance, cfg.canonical_fwd))
         assert f"Scanning {n} telomeric variants" in c["stderr"]
+
+
+def test_validity_formula():
+    """The lean kernel's span validity test (scan_fast.cu ValidAcc): exact on all 256 byte values in
+    every byte lane, and over random multi-word spans."""
+    valid = set(b"ACGTacgt")
+    M = 0xFFFFFFFF
+
+    def bad(words):
+        a1, a2, any_ = 0, M, 0
+        for w in words:
+            m = w & 0x06060606
+            y = (m * 6 + 0x40404040) & M
+            z = (w * 16) & M
+            a1 |= y ^ w
+            a2 &= z ^ w
+            any_ |= w
+        return ((a1 & 0xD0D0D0D0) | (~a2 & 0x10101010) | (any_ & 0x08080808)) & M
+
+    for pos in range(4):
+        for b in range(256):
+            for other in (0x41, 0x74, 0x47, 0x63):
+                by = [other] * 4
+                by[pos] = b
+                assert (bad([int.from_bytes(bytes(by), "little")]) != 0) == (b not in valid), (pos, b)
+    rng = np.random.default_rng(3)
+    pool = np.frombuffer(b"ACGTacgt", dtype=np.uint8)
+    for _ in range(20000):
+        by = rng.choice(pool, size=12)
+        if rng.random() < 0.5:
+            by[rng.integers(0, 12)] = rng.integers(0, 256)
+        words = [int.from_bytes(bytes(by[i:i + 4].tolist()), "little") for i in range(0, 12, 4)]
+        assert (bad(words) != 0) == any(int(x) not in valid for x in by)

@@ -106,12 +106,13 @@ struct Slot {
     std::vector<uint32_t> generalTiles;      // indices of the tiles the general kernel takes entirely
     const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
     HostBuf hSeq, hMeta, hMeta2;              // pinned staging
-    DevBuf dFastTiles, dGeneralTiles, dRedo;
+    DevBuf dFastTiles, dGeneralTiles, dRedo, dSlotCan, dSlotNct, dTileTot, dCanIdx, dNctIdx, dRunStarts;
+    uint64_t nCanAll = 0, nNctAll = 0;       // canonical / terminal non-canonical records of the batch
     DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotCounts,
         dSlotOv, dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
     uint32_t ovCap = 0;
     // device counters block: [0] ovCursor(u32) [16] blockCount(u32) [24] selTotals(2 x u64)
-    HostBuf hCounters, hWindows, hItemCounts, hBlocks, hPass, hSelCan, hSelNon;
+    HostBuf hScan, hCounters, hWindows, hItemCounts, hBlocks, hPass, hSelCan, hSelNon;
     uint64_t matchCap = 0;
     uint32_t blockCap = 0;
     uint32_t launches = 0;
@@ -323,6 +324,7 @@ int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
         TLS_CUDA(cudaEventCreate(&s.evAll0)); TLS_CUDA(cudaEventCreate(&s.evAll1));
         TLS_CUDA(s.dCounters.reserve(64));
         TLS_CUDA(s.hCounters.reserve(64));
+        TLS_CUDA(s.hScan.reserve(64));
     }
     ctx->forceGeneral = std::getenv("TLS_FORCE_GENERAL") != nullptr;
     *out = ctx.release();
@@ -334,12 +336,14 @@ void tls_destroy(tls_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (Slot &s : ctx->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        for (DevBuf *b : {&s.dFastTiles, &s.dGeneralTiles, &s.dRedo}) b->release();
+        for (DevBuf *b : {&s.dFastTiles, &s.dGeneralTiles, &s.dRedo, &s.dSlotCan, &s.dSlotNct, &s.dTileTot, &s.dCanIdx,
+                          &s.dNctIdx, &s.dRunStarts})
+            b->release();
         for (DevBuf *b : {&s.dAbsPos, &s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
                           &s.dMatches, &s.dSlots, &s.dSlotCounts, &s.dSlotOv, &s.dOvArena, &s.dTileBase, &s.dCounters,
                           &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch, &s.dSelCan, &s.dSelNon})
             b->release();
-        for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hMeta2, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
+        for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hMeta2, &s.hScan, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
                            &s.hSelCan, &s.hSelNon})
             b->release();
         if (s.evScan0) cudaEventDestroy(s.evScan0);
@@ -365,10 +369,13 @@ GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
     g.cfg = ctx->dcfg; g.cfg.mode = s.mode;
     g.slots = s.dSlots.as<DevMatch>(); g.slotCap = ctx->slotCap;
     g.slotCounts = s.dSlotCounts.as<uint32_t>(); g.slotOv = s.dSlotOv.as<uint32_t>();
+    g.slotCan = s.dSlotCan.as<uint32_t>(); g.slotNct = s.dSlotNct.as<uint32_t>();
     g.ovArena = s.dOvArena.as<DevMatch>(); g.ovCap = s.ovCap;
     g.nTiles = static_cast<uint32_t>(s.tiles.size());
     g.tileBase = s.dTileBase.as<unsigned long long>();
     g.matches = s.dMatches.as<DevMatch>(); g.matchCap = s.matchCap;
+    g.canIdx = s.dCanIdx.as<uint32_t>(); g.nctIdx = s.dNctIdx.as<uint32_t>();
+    g.selCap = std::max<uint64_t>(s.nCanAll, s.nNctAll);
     return g;
 }
 
@@ -380,7 +387,11 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
     TLS_CUDA(s.dSlots.reserve(nSlots * ctx->slotCap * sizeof(DevMatch)));
     TLS_CUDA(s.dSlotCounts.reserve(nSlots * 4));
     TLS_CUDA(s.dSlotOv.reserve(nSlots * 4));
-    TLS_CUDA(s.dTileBase.reserve((static_cast<size_t>(nTiles) + 1) * 8));
+    TLS_CUDA(s.dSlotCan.reserve(nSlots * 4));
+    TLS_CUDA(s.dSlotNct.reserve(nSlots * 4));
+    TLS_CUDA(s.dTileTot.reserve(static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * 12));
+    TLS_CUDA(s.dTileBase.reserve((static_cast<size_t>(nTiles) + 1) * 24));
+    TLS_CUDA(cudaMemsetAsync(s.dTileTot.p, 0, static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * 12, s.stream));
     s.ovCap = std::max<uint32_t>(s.ovCap, 256u * ctx->ovChunk);
     TLS_CUDA(s.dOvArena.reserve(static_cast<size_t>(s.ovCap) * sizeof(DevMatch)));
     const uint32_t nFast = static_cast<uint32_t>(s.fastTiles.size());
@@ -407,6 +418,8 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             f.patLen = cfg.cls[0].len;
             f.slots = s.dSlots.as<DevMatch>(); f.slotCap = ctx->slotCap;
             f.slotCounts = s.dSlotCounts.as<uint32_t>(); f.slotOv = s.dSlotOv.as<uint32_t>();
+            f.slotCan = s.dSlotCan.as<uint32_t>(); f.slotNct = s.dSlotNct.as<uint32_t>();
+            f.tileTot = s.dTileTot.as<uint32_t>(); f.nTilesAll = nTiles;
             f.ovArena = s.dOvArena.as<DevMatch>(); f.ovCap = s.ovCap; f.ovChunk = ctx->ovChunk;
             f.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
             f.windows = s.dWindows.as<uint32_t>();
@@ -433,6 +446,8 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             p.sortedFlags = ctx->dKeyFlags.as<uint8_t>();
             p.slots = s.dSlots.as<DevMatch>(); p.slotCap = ctx->slotCap;
             p.slotCounts = s.dSlotCounts.as<uint32_t>(); p.slotOv = s.dSlotOv.as<uint32_t>();
+            p.slotCan = s.dSlotCan.as<uint32_t>(); p.slotNct = s.dSlotNct.as<uint32_t>();
+            p.tileTot = s.dTileTot.as<uint32_t>();
             p.ovArena = s.dOvArena.as<DevMatch>(); p.ovCap = s.ovCap; p.ovChunk = ctx->ovChunk;
             p.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
             p.windows = s.dWindows.as<uint32_t>();
@@ -445,16 +460,18 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             s.launches++;
         }
         TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
-        TLS_CUDA(launchTileScan(gatherParams(ctx, s), s.stream));
+        TLS_CUDA(launchTileScan(s.dTileTot.as<uint32_t>(), nTiles, s.dTileBase.as<unsigned long long>(), s.stream));
         s.launches++;
     } else {
-        TLS_CUDA(cudaMemsetAsync(s.dTileBase.p, 0, 8, s.stream));
+        TLS_CUDA(cudaMemsetAsync(s.dTileBase.p, 0, 24, s.stream));
     }
-    // counters: [0] ovCursor; total matches = tileBase[nTiles]; lean kernel status
-    TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 8, cudaMemcpyDeviceToHost, s.stream));
-    TLS_CUDA(cudaMemcpyAsync(s.hCounters.as<uint8_t>() + 8, s.dTileBase.as<unsigned long long>() + nTiles, 8,
-                             cudaMemcpyDeviceToHost, s.stream));
-    TLS_CUDA(cudaMemcpyAsync(s.hCounters.as<uint8_t>() + 32, s.dRedo.p, 8, cudaMemcpyDeviceToHost, s.stream));
+    // host copy: [0] ovCursor; [8],[16],[24] totals (all, canonical, terminal non-canonical); [32] redo count, status
+    unsigned long long *tb = s.dTileBase.as<unsigned long long>();
+    uint8_t *hc = s.hScan.as<uint8_t>();
+    TLS_CUDA(cudaMemcpyAsync(hc, s.dCounters.p, 8, cudaMemcpyDeviceToHost, s.stream));
+    for (int k = 0; k < 3; ++k)
+        TLS_CUDA(cudaMemcpyAsync(hc + 8 + 8 * k, tb + static_cast<size_t>(k) * (nTiles + 1) + nTiles, 8, cudaMemcpyDeviceToHost, s.stream));
+    TLS_CUDA(cudaMemcpyAsync(hc + 32, s.dRedo.p, 8, cudaMemcpyDeviceToHost, s.stream));
     return TLS_OK;
 }
 
@@ -641,39 +658,48 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
         // ---- wait for the scan; grow the overflow arena and rerun if it ran out --------------------
         for (;;) {
             TLS_CUDA(cudaStreamSynchronize(s.stream));
-            if (s.hCounters.as<uint32_t>()[9] != 0)
+            const uint32_t *hs = s.hScan.as<uint32_t>();
+            if (hs[9] != 0)
                 return fail(TLS_ERR_STATE, "lean scan kernel could not lay out its shared memory (window base %% 64 KiB); "
                                            "set TLS_FORCE_GENERAL=1");
-            const uint32_t nRedo = s.hCounters.as<uint32_t>()[8];
-            if (tr.on) fprintf(stderr, " lean_tiles=%zu/%zu redo_rows=%u", s.fastTiles.size(), s.tiles.size(), nRedo);
-            const uint32_t ovUsed = *s.hCounters.as<uint32_t>();
-            s.nMatches = *reinterpret_cast<unsigned long long *>(s.hCounters.as<uint8_t>() + 8);
+            if (tr.on) fprintf(stderr, " lean_tiles=%zu/%zu redo_rows=%u", s.fastTiles.size(), s.tiles.size(), hs[8]);
+            const uint32_t ovUsed = hs[0];
+            const unsigned long long *tot = reinterpret_cast<const unsigned long long *>(s.hScan.as<uint8_t>() + 8);
+            s.nMatches = tot[0]; s.nCanAll = tot[1]; s.nNctAll = tot[2];
             if (ovUsed <= s.ovCap) break;
             s.ovCap = ovUsed + ovUsed / 4;
             if ((rc = enqueueScan(ctx, s))) return rc;
         }
+        if (s.nMatches > 0xFFFFFFF0ull) return fail(TLS_ERR_INVALID, "more than 2^32 matches in one batch; submit smaller batches");
         tr.mark("wait_scan");
-        // ---- slots -> one ordered list ------------------------------------------------------------------
-        s.matchCap = std::max<uint64_t>(s.matchCap, s.nMatches);
-        TLS_CUDA(s.dMatches.reserve(std::max<uint64_t>(s.matchCap, 1) * sizeof(DevMatch)));
-        if (!s.tiles.empty()) { TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream)); s.launches++; }
         if (!s.tiles.empty()) {
             TLS_CUDA(cudaEventElapsedTime(&s.scanMs, s.evScan0, s.evScan1));
             TLS_CUDA(cudaEventElapsedTime(&s.fastMs, s.evScan0, s.evFast1));
         } else s.scanMs = s.fastMs = 0;
-
-        // ---- blocks -------------------------------------------------------------------------------
         const bool genome = s.mode == TLS_MODE_GENOME, reads = s.mode == TLS_MODE_READS;
         const bool wantSel = genome && (ctx->cfg.outputs & TLS_OUT_MATCHES) && s.nMatches > 0;
+
+        // ---- slots -> one ordered list, blocks, -m lists: one enqueue, one synchronisation ------------------
+        s.matchCap = std::max<uint64_t>(s.matchCap, s.nMatches);
+        TLS_CUDA(s.dMatches.reserve(std::max<uint64_t>(s.matchCap, 1) * sizeof(DevMatch)));
+        TLS_CUDA(s.dCanIdx.reserve(std::max<uint64_t>(s.nCanAll, 1) * 4));
+        TLS_CUDA(s.dNctIdx.reserve(std::max<uint64_t>(s.nNctAll, 1) * 4));
         uint32_t nBlocks = 0;
         s.blockCap = std::max<uint32_t>(s.blockCap, 4096);
-        for (;;) {
+        const uint32_t runCap = static_cast<uint32_t>(std::min<uint64_t>(s.nCanAll / 4 + 64, 0x7FFFFFFFull));
+        TLS_CUDA(s.dRunStarts.reserve(static_cast<size_t>(runCap) * 8));
+        if (wantSel) {
+            TLS_CUDA(s.dSelCan.reserve(std::max<uint64_t>(s.nCanAll, 1) * sizeof(tls_match)));
+            TLS_CUDA(s.dSelNon.reserve(std::max<uint64_t>(s.nNctAll, 1) * sizeof(tls_match)));
+        }
+        for (bool first = true;; first = false) {
             TLS_CUDA(s.dBlocks.reserve(static_cast<size_t>(s.blockCap) * sizeof(DevBlock)));
             uint8_t *cnt = s.dCounters.as<uint8_t>();
-            TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 4, s.stream));
+            TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 8, s.stream));            // [16] block count, [20] ITS run count
+            if (first && !s.tiles.empty()) { TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream)); s.launches++; }
             if (reads && n) TLS_CUDA(cudaMemsetAsync(s.dPass.p, 0, n, s.stream));
             if (n) {
-                TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), n, s.dItemBegin.as<unsigned long long>(), s.stream));
+                if (first) { TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), n, s.dItemBegin.as<unsigned long long>(), s.stream)); s.launches++; }
                 BlockParams bp{};
                 bp.matches = s.dMatches.as<DevMatch>();
                 bp.itemBegin = s.dItemBegin.as<unsigned long long>();
@@ -689,9 +715,23 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
                 bp.cfg = ctx->dcfg;
                 bp.cfg.mode = s.mode;
                 TLS_CUDA(launchTerminal(bp, s.stream));
-                s.launches += 2;
-                if (genome && s.nMatches >= 2) { TLS_CUDA(launchIts(bp, s.nMatches, s.stream)); s.launches++; }
+                s.launches++;
+                if (genome && s.nMatches >= 2 && s.nCanAll >= 4) {
+                    TLS_CUDA(launchIts(bp, s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dRunStarts.as<unsigned long long>(),
+                                       reinterpret_cast<unsigned int *>(cnt + 20), runCap, s.stream));
+                    s.launches += 2;
+                }
+                if (first && wantSel) {
+                    TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll,
+                                                  s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
+                                                  s.dSelCan.p, s.stream));
+                    TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll,
+                                                  s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
+                                                  s.dSelNon.p, s.stream));
+                    s.launches += (s.nCanAll ? 1 : 0) + (s.nNctAll ? 1 : 0);
+                }
             }
+            TLS_CUDA(cudaEventRecord(s.evAll1, s.stream));
             TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 64, cudaMemcpyDeviceToHost, s.stream));
             TLS_CUDA(cudaStreamSynchronize(s.stream));
             nBlocks = *reinterpret_cast<unsigned int *>(s.hCounters.as<uint8_t>() + 16);
@@ -699,28 +739,8 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             s.blockCap = nBlocks + nBlocks / 8 + 64;
         }
         if (reads) nBlocks = 0;
-        tr.mark("gather_blocks");
-
-        // ---- -m lists --------------------------------------------------------------------------------
-        unsigned long long selTotals[2] = {0, 0};
-        if (wantSel) {
-            const uint32_t capSel = static_cast<uint32_t>(std::min<uint64_t>(s.nMatches, 0xFFFFFFFFull));
-            TLS_CUDA(s.dSelScratch.reserve(static_cast<size_t>(selectChunks(s.nMatches)) * 8 + 16));
-            // exact sizes are known from the per-item counters only after a copy; bound them instead:
-            // canonical + terminal non-canonical records never exceed the match count
-            TLS_CUDA(s.dSelCan.reserve(static_cast<size_t>(capSel) * sizeof(tls_match)));
-            TLS_CUDA(s.dSelNon.reserve(static_cast<size_t>(capSel) * sizeof(tls_match)));
-            uint8_t *cnt = s.dCounters.as<uint8_t>();
-            TLS_CUDA(launchSelect(s.dMatches.as<DevMatch>(), s.nMatches, s.dSelScratch.as<uint32_t>(),
-                                  reinterpret_cast<unsigned long long *>(cnt + 24), s.dItemBegin.as<unsigned long long>(),
-                                  s.dAbsPos.as<unsigned long long>(), n, s.dSelCan.p, capSel, s.dSelNon.p, capSel, s.stream));
-            s.launches += 3;
-            TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 64, cudaMemcpyDeviceToHost, s.stream));
-            TLS_CUDA(cudaStreamSynchronize(s.stream));
-            std::memcpy(selTotals, s.hCounters.as<uint8_t>() + 24, 16);
-        }
-        tr.mark("select");
-        TLS_CUDA(cudaEventRecord(s.evAll1, s.stream));
+        tr.mark("gather_blocks_select");
+        unsigned long long selTotals[2] = {wantSel ? s.nCanAll : 0, wantSel ? s.nNctAll : 0};
 
         // ---- copy results back ------------------------------------------------------------------------
         if (genome && s.nWindows) {

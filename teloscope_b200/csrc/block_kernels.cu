@@ -1,18 +1,56 @@
-// Kernels that turn the ordered match list into what SegmentData holds besides the matches:
+// Kernels that turn the per-row match slots into what SegmentData holds besides the window counters:
+//   tileScanKernel      exclusive prefixes over tiles of (all, canonical, terminal non-canonical) matches
+//   gatherKernel        slot arena -> one ordered match list + index lists of the -m selections
+//                       (+ window / item accounting of the records the general scan kernel left to it)
 //   itemOffsetsKernel   exclusive scan of per-item match counts
-//   terminalKernel      Teloscope::getTerminalBlocks (src/teloscope.cpp:29-176), one walk per
-//                       (item, strand), Phase 2 merged on the fly
-//   itsKernel           Teloscope::getInterstitialBlocks (src/teloscope.cpp:179-256): every run
-//                       start walks its run
-//   selectKernels       ordered selection of canonical / terminal non-canonical matches (-m)
+//   terminalKernel      Teloscope::getTerminalBlocks (src/teloscope.cpp:29-176), one warp per
+//                       (item, arm), Phase 2 merged on the fly
+//   itsSeedKernel /     Teloscope::getInterstitialBlocks (src/teloscope.cpp:179-256): a block needs
+//   itsRunKernel        >= 4 canonical matches, so only runs that hold canonical matches are walked
+//   selectFinalizeKernel  final 16-byte records of the canonical / terminal non-canonical lists (-m)
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "device_common.cuh"
 #include "kernels.hpp"
 
 namespace tls {
+
+namespace {
+
+// Exclusive scan of up to 1024 values per call inside one block of 1024 threads; returns the
+// exclusive prefix of `v` (carry included) and advances the carry.  warpSums: 32 entries.
+__device__ __forceinline__ unsigned long long blockExclusive1024(unsigned long long v, unsigned long long *warpSums,
+                                                                 unsigned long long *carry) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += u;
+    }
+    if (lane == 31) warpSums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = warpSums[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= d) wi += u;
+        }
+        warpSums[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned long long excl = *carry + warpSums[warp] + incl - v;
+    __syncthreads();
+    if (tid == 1023) *carry = excl + v;
+    __syncthreads();
+    return excl;
+}
+
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // Exclusive scan of itemCounts[i].all -> itemBegin[0..n]   (single block, n up to millions)
@@ -21,116 +59,80 @@ __global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *c
                                                           unsigned long long *itemBegin) {
     __shared__ unsigned long long warpSums[32];
     __shared__ unsigned long long carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + tid;
+        const uint32_t i = base + threadIdx.x;
         const unsigned long long v = i < n ? counts[i].all : 0;
-        unsigned long long incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += u;
-        }
-        if (lane == 31) warpSums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warpSums[lane], wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-                if (lane >= d) wi += u;
-            }
-            warpSums[lane] = wi - w;
-        }
-        __syncthreads();
-        const unsigned long long excl = carry + warpSums[warp] + incl - v;
+        const unsigned long long excl = blockExclusive1024(v, warpSums, &carry);
         if (i < n) itemBegin[i] = excl;
-        __syncthreads();
-        if (tid == 1023) carry = excl + v;
-        __syncthreads();
     }
-    if (tid == 0) itemBegin[n] = carry;
+    if (threadIdx.x == 0) itemBegin[n] = carry;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Slot arena -> one ordered match list.
-//   tileScanKernel: per-tile totals (sum of the 32 row slots) and their exclusive prefix
-//   gatherKernel:   one block per tile copies its slots (and overflow chunks) to the list
+// Per-tile totals (written by the scan kernels with atomics) -> exclusive prefixes.
+// tileTot / tileBase hold three arrays back to back: all matches, canonical, terminal non-canonical.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tileScanKernel(const GatherParams g) {
+__global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase) {
     __shared__ unsigned long long warpSums[32];
     __shared__ unsigned long long carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < g.nTiles; base += 1024) {
-        const uint32_t i = base + tid;
-        unsigned long long v = 0;
-        if (i < g.nTiles) {
-            const uint4 *c = reinterpret_cast<const uint4 *>(g.slotCounts + static_cast<size_t>(i) * kTileRows);
-#pragma unroll
-            for (int k = 0; k < kTileRows / 4; ++k) { const uint4 x = c[k]; v += x.x; v += x.y; v += x.z; v += x.w; }
-        }
-        unsigned long long incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += u;
-        }
-        if (lane == 31) warpSums[warp] = incl;
+    for (int k = 0; k < 3; ++k) {
+        if (threadIdx.x == 0) carry = 0;
         __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warpSums[lane], wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-                if (lane >= d) wi += u;
-            }
-            warpSums[lane] = wi - w;
+        const uint32_t *in = tileTot + static_cast<size_t>(k) * nTiles;
+        unsigned long long *out = tileBase + static_cast<size_t>(k) * (nTiles + 1);
+        for (uint32_t base = 0; base < nTiles; base += 1024) {
+            const uint32_t i = base + threadIdx.x;
+            const unsigned long long v = i < nTiles ? in[i] : 0;
+            const unsigned long long excl = blockExclusive1024(v, warpSums, &carry);
+            if (i < nTiles) out[i] = excl;
         }
-        __syncthreads();
-        const unsigned long long excl = carry + warpSums[warp] + incl - v;
-        if (i < g.nTiles) g.tileBase[i] = excl;
-        __syncthreads();
-        if (tid == 1023) carry = excl + v;
+        if (threadIdx.x == 0) out[nTiles] = carry;
         __syncthreads();
     }
-    if (tid == 0) g.tileBase[g.nTiles] = carry;
 }
 
-// One block per tile.  Thread k walks the k-th contiguous share of the tile's records in genome
-// order: copies them to the ordered list (adding the terminal flag) and accumulates, while the
-// key stays the same, per-item counters and per-window covered bp; shared atomics on key change,
-// one flush to global memory at the end.
-constexpr int kGatherThreads = 128;
+// ------------------------------------------------------------------------------------------------
+// Slot arena -> ordered match list.  One block per tile, one warp per row slot at a time; fully
+// coalesced 8-byte copies.  Records the scan kernels did not account for (general kernel, regions
+// held in the tile's region cache) are accounted here with shared-memory atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGatherThreads = 256;
 constexpr int kGatherSlots = 128;
 
 __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParams g) {
     const uint32_t tile = blockIdx.x;
-    const int tid = threadIdx.x;
-    __shared__ uint32_t sOff[kTileRows + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ uint32_t sOff[3][kTileRows + 1];
     __shared__ DevRegion sRegion[kRegionCache];
     __shared__ uint32_t sRegCnt[kRegionCache][5];
     __shared__ uint32_t sWin[kGatherSlots][4];
-    __shared__ uint32_t sFirstWin, sNReg;
+    __shared__ uint32_t sFirstWin, sNReg, sDirty;
     const DevConfig &c = g.cfg;
     const DevTile dt = g.tiles[tile];
-    if (tid == 0) {
-        uint32_t acc = 0;
-        for (int w = 0; w < kTileRows; ++w) { sOff[w] = acc; acc += g.slotCounts[static_cast<size_t>(tile) * kTileRows + w]; }
-        sOff[kTileRows] = acc;
-    }
-    if (tid < 32) {
+    if (warp < 3) {
+        // exclusive prefix over the 32 row slots of this tile (warp k handles array k)
+        const uint32_t *src = warp == 0 ? g.slotCounts : warp == 1 ? g.slotCan : g.slotNct;
+        const uint32_t v = src[static_cast<size_t>(tile) * kTileRows + lane];
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        sOff[warp][lane] = incl - v;
+        if (lane == 31) sOff[warp][kTileRows] = incl;
+    } else if (warp == 3) {
         const uint64_t tileEnd = dt.bufStart + dt.len;
-        const uint32_t idx = min(dt.firstRegion + static_cast<uint32_t>(tid), g.nRegions - 1);
+        const uint32_t idx = min(dt.firstRegion + static_cast<uint32_t>(lane), g.nRegions - 1);
         const DevRegion r = g.regions[idx];
-        const bool in = dt.firstRegion + tid < g.nRegions && r.bufStart < tileEnd;
+        const bool in = dt.firstRegion + lane < g.nRegions && r.bufStart < tileEnd;
         const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, in));
-        if (in) sRegion[tid] = r;
-        if (tid == 0) {
+        if (in) sRegion[lane] = r;
+        if (lane == 0) {
             sNReg = n;
+            sDirty = 0;
             const uint64_t s = dt.bufStart > r.bufStart ? dt.bufStart : r.bufStart;
             sFirstWin = (c.mode == 0 && n > 0) ? r.winBase + divWindow(c, r.relStart + static_cast<uint32_t>(s - r.bufStart)) : 0;
         }
@@ -138,76 +140,62 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
     for (int i = tid; i < kRegionCache * 5; i += kGatherThreads) (&sRegCnt[0][0])[i] = 0;
     for (int i = tid; i < kGatherSlots * 4; i += kGatherThreads) (&sWin[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t total = sOff[kTileRows];
-    if (total == 0) return;
+    if (sOff[0][kTileRows] == 0) return;
     const unsigned long long base = g.tileBase[tile];
+    const unsigned long long baseCan = g.tileBase[static_cast<size_t>(g.nTiles) + 1 + tile];
+    const unsigned long long baseNct = g.tileBase[2 * (static_cast<size_t>(g.nTiles) + 1) + tile];
     const uint32_t firstWin = sFirstWin;
-    const uint32_t share = (total + kGatherThreads - 1) / kGatherThreads;
-    uint32_t i = tid * share;
-    const uint32_t end = min(total, i + share);
+    const uint32_t laneLt = (1u << lane) - 1u;
 
-    // running accumulators
-    uint32_t curReg = 0xFFFFFFFFu, nAll = 0, nFwd = 0, nCan = 0, nNct = 0;
-    uint32_t curWin = 0xFFFFFFFFu, canCov = 0, nonCov = 0, fwdCov = 0, revCov = 0;
-    auto flushReg = [&]() {
-        if (curReg != 0xFFFFFFFFu && nAll) {
-            uint32_t *r = sRegCnt[curReg];
-            atomicAdd(r + 0, nAll); atomicAdd(r + 1, nFwd); atomicAdd(r + 2, nAll - nFwd);
-            if (nCan) atomicAdd(r + 3, nCan);
-            if (nNct) atomicAdd(r + 4, nNct);
-        }
-        nAll = nFwd = nCan = nNct = 0;
-    };
-    auto flushWin = [&]() {
-        if (curWin != 0xFFFFFFFFu) {
-            const uint32_t s = curWin - firstWin;
-            uint32_t *w = s < kGatherSlots ? sWin[s] : g.windows + static_cast<size_t>(curWin) * 8 + 4;
-            if (canCov) atomicAdd(w + 0, canCov);
-            if (nonCov) atomicAdd(w + 1, nonCov);
-            if (fwdCov) atomicAdd(w + 2, fwdCov);
-            if (revCov) atomicAdd(w + 3, revCov);
-        }
-        canCov = nonCov = fwdCov = revCov = 0;
-    };
-
-    if (i < end) {
-        int w = 0;
-        while (sOff[w + 1] <= i) ++w;
-        for (; i < end; ++i) {
-            while (sOff[w + 1] <= i) ++w;
-            const size_t slotIdx = static_cast<size_t>(tile) * kTileRows + w;
-            const uint32_t k = i - sOff[w];
-            DevMatch m;
-            if (k < g.slotCap) m = g.slots[slotIdx * g.slotCap + k];
-            else {
-                const unsigned long long o = static_cast<unsigned long long>(g.slotOv[slotIdx]) + (k - g.slotCap);
-                if (o >= g.ovCap) continue;                     // overflow arena exhausted: the host reruns
-                m = g.ovArena[o];
+    for (int s = warp; s < kTileRows; s += kGatherThreads / 32) {
+        const uint32_t cnt = sOff[0][s + 1] - sOff[0][s];
+        if (cnt == 0) continue;
+        const size_t slotIdx = static_cast<size_t>(tile) * kTileRows + s;
+        const uint2 *src = reinterpret_cast<const uint2 *>(g.slots) + slotIdx * g.slotCap;
+        const unsigned long long ov = g.slotOv[slotIdx];
+        const unsigned long long o = base + sOff[0][s];
+        unsigned long long oc = baseCan + sOff[1][s], on = baseNct + sOff[2][s];
+        for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            uint2 rec = make_uint2(0u, 0u);
+            bool have = k < cnt;
+            if (have) {
+                if (k < g.slotCap) rec = src[k];
+                else if (ov + (k - g.slotCap) < g.ovCap) rec = reinterpret_cast<const uint2 *>(g.ovArena)[ov + (k - g.slotCap)];
+                else have = false;                              // overflow arena exhausted: the host reruns the scan
             }
-            if (m.region != kRegionAccounted) {
-                const DevRegion &r = sRegion[m.region];
-                const bool fwd = m.flags & kMatchFwd, can = m.flags & kMatchCan;
-                bool term = false;
+            const uint32_t flags = (rec.y >> 16) & 0xFFu, region = rec.y >> 24;
+            if (have && region != kRegionAccounted) {
+                // general-kernel record: window coverage and per-item counters
+                const DevRegion &r = sRegion[region];
+                const uint32_t len = rec.y & 0xFFFFu;
+                const bool fwd = flags & kMatchFwd, can = flags & kMatchCan;
                 if (c.mode == 0) {
-                    const uint32_t winIdx = divWindow(c, m.pos);
-                    term = isTerminalMatch(c, m.pos, winIdx, r.itemLen);
-                    const uint32_t win = r.winBase + winIdx;
-                    if (win != curWin) { flushWin(); curWin = win; }
-                    if (can) canCov += m.len; else nonCov += m.len;
-                    if (fwd) fwdCov += m.len; else revCov += m.len;
+                    const uint32_t win = r.winBase + divWindow(c, rec.x), sl = win - firstWin;
+                    uint32_t *w = sl < kGatherSlots ? sWin[sl] : g.windows + static_cast<size_t>(win) * 8 + 4;
+                    atomicAdd(w + (can ? 0 : 1), len);
+                    atomicAdd(w + (fwd ? 2 : 3), len);
                 }
-                if (m.region != curReg) { flushReg(); curReg = m.region; }
-                ++nAll; nFwd += fwd; nCan += can; nNct += (!can && term);
-                if (term) m.flags |= kMatchTerm;
+                uint32_t *rc = sRegCnt[region];
+                atomicAdd(rc + 0, 1u);
+                atomicAdd(rc + (fwd ? 1 : 2), 1u);
+                if (can) atomicAdd(rc + 3, 1u);
+                else if (flags & kMatchTerm) atomicAdd(rc + 4, 1u);
+                sDirty = 1;
             }
-            m.region = 0;
-            const unsigned long long o = base + i;
-            if (o < g.matchCap) g.matches[o] = m;
+            if (have && o + k < g.matchCap) reinterpret_cast<uint2 *>(g.matches)[o + k] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
+            // index lists of the -m selections, in genome order
+            const bool isC = have && (flags & kMatchCan);
+            const bool isN = have && (flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
+            const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
+            if (isC && oc + __popc(bc & laneLt) < g.selCap) g.canIdx[oc + __popc(bc & laneLt)] = static_cast<uint32_t>(o + k);
+            if (isN && on + __popc(bn & laneLt) < g.selCap) g.nctIdx[on + __popc(bn & laneLt)] = static_cast<uint32_t>(o + k);
+            oc += __popc(bc);
+            on += __popc(bn);
         }
     }
-    flushReg();
-    flushWin();
     __syncthreads();
+    if (!sDirty) return;
     for (int k = tid; k < kGatherSlots * 4; k += kGatherThreads) {
         const uint32_t v = (&sWin[0][0])[k];
         if (v) atomicAdd(&g.windows[static_cast<size_t>(firstWin + (k >> 2)) * 8 + 4 + (k & 3)], v);
@@ -218,8 +206,8 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
     }
 }
 
-cudaError_t launchTileScan(const GatherParams &g, cudaStream_t s) {
-    tileScanKernel<<<1, 1024, 0, s>>>(g);
+cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, cudaStream_t s) {
+    tileScanKernel<<<1, 1024, 0, s>>>(tileTot, nTiles, tileBase);
     return cudaGetLastError();
 }
 cudaError_t launchGather(const GatherParams &g, cudaStream_t s) {
@@ -235,14 +223,14 @@ namespace {
 
 struct Run {
     uint32_t start, end, prev, n, nFwd, nCan, cov, fwdCov, canCov;
-    __device__ void begin(const DevMatch &m) {
-        const uint32_t f = m.flags & kMatchFwd ? 1u : 0u, c = m.flags & kMatchCan ? 1u : 0u;
-        start = m.pos; end = m.pos + m.len; prev = m.pos; n = 1; nFwd = f; nCan = c;
-        cov = m.len; fwdCov = f * m.len; canCov = c * m.len;
+    __device__ void begin(uint32_t pos, uint32_t len, uint32_t flags) {
+        const uint32_t f = flags & kMatchFwd ? 1u : 0u, c = flags & kMatchCan ? 1u : 0u;
+        start = pos; end = pos + len; prev = pos; n = 1; nFwd = f; nCan = c;
+        cov = len; fwdCov = f * len; canCov = c * len;
     }
-    __device__ void absorb(const DevMatch &m) {
-        const uint32_t f = m.flags & kMatchFwd ? 1u : 0u, c = m.flags & kMatchCan ? 1u : 0u;
-        ++n; nFwd += f; nCan += c; cov += m.len; fwdCov += f * m.len; canCov += c * m.len; prev = m.pos;
+    __device__ void absorb(uint32_t pos, uint32_t len, uint32_t flags) {
+        const uint32_t f = flags & kMatchFwd ? 1u : 0u, c = flags & kMatchCan ? 1u : 0u;
+        ++n; nFwd += f; nCan += c; cov += len; fwdCov += f * len; canCov += c * len; prev = pos;
     }
 };
 
@@ -253,13 +241,16 @@ __device__ void emitBlock(const BlockParams &p, const DevBlock &b) {
 
 }  // namespace
 
-// One thread per (item, arm).  arm 0 = p (forward-strand matches from the start),
-// arm 1 = q (reverse-strand matches from the end).
-__global__ void terminalKernel(const BlockParams p) {
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= 2u * p.nItems) return;
-    const uint32_t item = gid >> 1;
-    const bool fromStart = (gid & 1u) == 0;
+// One warp per (item, arm).  arm 0 = p (forward-strand matches from the start), arm 1 = q
+// (reverse-strand matches from the end).  The warp loads 32 records at a time (coalesced) and
+// all lanes run the same sequential state machine on the records of the wanted strand, handed
+// round by shuffles; the walk stops at the first run start outside the terminal zone.
+__global__ void __launch_bounds__(128) terminalKernel(const BlockParams p) {
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= 2u * p.nItems) return;
+    const uint32_t item = gw >> 1;
+    const bool fromStart = (gw & 1u) == 0;
     const DevConfig &c = p.cfg;
     const uint32_t n = p.itemLen[item];
     const bool readMode = c.mode == 2;
@@ -272,7 +263,7 @@ __global__ void terminalKernel(const BlockParams p) {
     if (strandCount >= 2) {                                           // src/teloscope.cpp:646,649
         const long long begin = static_cast<long long>(p.itemBegin[item]);
         const long long end = static_cast<long long>(p.itemBegin[item + 1]);
-        const uint8_t want = fromStart ? kMatchFwd : 0;
+        const uint32_t want = fromStart ? kMatchFwd : 0;
         auto inZone = [&](uint32_t rel) {                             // :48-52
             if (n <= T) return true;
             return fromStart ? rel < T : rel >= n - T;
@@ -288,7 +279,7 @@ __global__ void terminalKernel(const BlockParams p) {
                 const uint64_t relEnd = static_cast<uint64_t>(cur.start) + cur.len;
                 const uint64_t left = cur.start, right = relEnd <= n ? n - relEnd : 0;
                 cur.validOr = fromStart ? left <= right : left >= right;
-                emitBlock(p, cur);
+                if (lane == 0) emitBlock(p, cur);
                 ++emitted;
                 boundary = fromStart ? cur.start + cur.len : cur.start;
             }
@@ -314,161 +305,159 @@ __global__ void terminalKernel(const BlockParams p) {
         };
 
         Run run{};
-        bool inRun = false;
-        const long long step = fromStart ? 1 : -1;
-        for (long long i = fromStart ? begin : end - 1; i != (fromStart ? end : begin - 1); i += step) {
-            const DevMatch m = p.matches[i];
-            if ((m.flags & kMatchFwd) != want) continue;
-            if (!inRun) {
-                if (!inZone(m.pos)) break;
-                run.begin(m);
-                inRun = true;
-                continue;
-            }
-            const uint32_t gap = fromStart ? m.pos - run.prev : run.prev - m.pos;
-            if (gap <= c.maxMatchDist) {
-                if (fromStart) run.end = m.pos + m.len; else run.start = m.pos;
-                run.absorb(m);
-            } else {
-                feedSub(run);
-                inRun = false;
-                if (!inZone(m.pos)) break;
-                run.begin(m);
-                inRun = true;
+        bool inRun = false, done = false;
+        const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
+        for (long long off = 0; off < end - begin && !done; off += 32) {
+            // lane l holds the l-th next record in walk order
+            const long long i = fromStart ? begin + off + lane : end - 1 - off - lane;
+            const bool valid = fromStart ? i < end : i >= begin;
+            const uint2 rec = valid ? recs[i] : make_uint2(0u, 0u);
+            uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && ((rec.y >> 16) & kMatchFwd) == want);
+            while (mask && !done) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const uint32_t pos = __shfl_sync(0xFFFFFFFFu, rec.x, b), hi = __shfl_sync(0xFFFFFFFFu, rec.y, b);
+                const uint32_t len = hi & 0xFFFFu, flags = (hi >> 16) & 0xFFu;
+                if (!inRun) {
+                    if (!inZone(pos)) { done = true; break; }
+                    run.begin(pos, len, flags);
+                    inRun = true;
+                    continue;
+                }
+                const uint32_t gap = fromStart ? pos - run.prev : run.prev - pos;
+                if (gap <= c.maxMatchDist) {
+                    if (fromStart) run.end = pos + len; else run.start = pos;
+                    run.absorb(pos, len, flags);
+                } else {
+                    feedSub(run);
+                    inRun = false;
+                    if (!inZone(pos)) { done = true; break; }
+                    run.begin(pos, len, flags);
+                    inRun = true;
+                }
             }
         }
         if (inRun) feedSub(run);
         if (haveCur) finishCur();
     }
-    if (fromStart) p.fwdBoundary[item] = boundary; else p.revBoundary[item] = boundary;
-    if (readMode && emitted) p.pass[item] = 1;
+    if (lane == 0) {
+        if (fromStart) p.fwdBoundary[item] = boundary; else p.revBoundary[item] = boundary;
+        if (readMode && emitted) p.pass[item] = 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Interstitial blocks.  One thread per 64 consecutive matches; a thread that finds a run start
-// among its matches walks that run to its end.
+// Interstitial blocks.  A block needs canonicalCount >= 4 (src/teloscope.cpp:186), so runs are found
+// from the canonical matches: a seed thread per canonical match decides whether it is the first
+// canonical match of its run and whether the run reaches 4 of them; a warp then walks each such run.
+// Runs start afresh at the first match at or after fwdBoundary and stop before revBoundary (:188-191,235).
 // ------------------------------------------------------------------------------------------------
-__global__ void itsKernel(const BlockParams p, unsigned long long nMatches) {
-    const unsigned long long first = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 64ull;
-    if (first >= nMatches) return;
+__global__ void __launch_bounds__(256) itsSeedKernel(const BlockParams p, const uint32_t *canIdx, unsigned long long nCan,
+                                                     unsigned long long *runStarts, unsigned int *runCount, uint32_t runCap) {
+    const unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= nCan) return;
     const DevConfig &c = p.cfg;
-    // item of the first match: last i with itemBegin[i] <= first
-    uint32_t lo = 0, hi = p.nItems;
+    const unsigned long long idx = canIdx[j];
+    uint32_t lo = 0, hi = p.nItems;                               // item: last i with itemBegin[i] <= idx
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (p.itemBegin[mid] <= first) lo = mid + 1; else hi = mid;
+        if (p.itemBegin[mid] <= idx) lo = mid + 1; else hi = mid;
     }
-    uint32_t item = lo - 1;
-    unsigned long long itemEnd = p.itemBegin[item + 1];
-    const unsigned long long last = first + 64 < nMatches ? first + 64 : nMatches;
-    for (unsigned long long i = first; i < last; ++i) {
-        while (i >= itemEnd) { ++item; itemEnd = p.itemBegin[item + 1]; }
-        const unsigned long long itemBegin = p.itemBegin[item];
-        const uint32_t fwdB = p.fwdBoundary[item], revB = p.revBoundary[item];
-        // src/teloscope.cpp:653: needs fwdBoundary < revBoundary and >= 2 matches in the segment
-        if (!(fwdB < revB) || itemEnd - itemBegin < 2) { i = itemEnd - 1; continue; }
-        const DevMatch m = p.matches[i];
-        if (m.pos < fwdB || m.pos >= revB) continue;
-        bool isStart = true;                                  // first match at/after fwdBoundary starts a run
-        if (i > itemBegin) {
-            const DevMatch prev = p.matches[i - 1];
-            if (prev.pos >= fwdB) isStart = m.pos - prev.pos > c.maxMatchDist;
+    const uint32_t item = lo - 1;
+    const unsigned long long itemBegin = p.itemBegin[item], itemEnd = p.itemBegin[item + 1];
+    const uint32_t fwdB = p.fwdBoundary[item], revB = p.revBoundary[item];
+    if (!(fwdB < revB) || itemEnd - itemBegin < 2) return;        // src/teloscope.cpp:653
+    const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
+    const uint32_t pos0 = recs[idx].x;
+    if (pos0 < fwdB || pos0 >= revB) return;
+    // walk left to the run start; give up if an earlier canonical match of the same run exists
+    unsigned long long i = idx;
+    uint32_t pos = pos0;
+    while (i > itemBegin) {
+        const uint2 pr = recs[i - 1];
+        if (pr.x < fwdB || pos - pr.x > c.maxMatchDist) break;
+        if ((pr.y >> 16) & kMatchCan) return;
+        --i;
+        pos = pr.x;
+    }
+    // walk right until the run holds 4 canonical matches (or ends)
+    uint32_t nCanRun = 1;
+    unsigned long long k = idx;
+    pos = pos0;
+    while (nCanRun < 4 && k + 1 < itemEnd) {
+        const uint2 nx = recs[k + 1];
+        if (nx.x >= revB || nx.x - pos > c.maxMatchDist) break;
+        if ((nx.y >> 16) & kMatchCan) ++nCanRun;
+        ++k;
+        pos = nx.x;
+    }
+    if (nCanRun < 4) return;
+    const unsigned int slot = atomicAdd(runCount, 1u);
+    if (slot < runCap) runStarts[slot] = (static_cast<unsigned long long>(item) << 32) | i;   // i < 2^32
+}
+
+__global__ void __launch_bounds__(128) itsRunKernel(const BlockParams p, const unsigned long long *runStarts,
+                                                    const unsigned int *runCount, uint32_t runCap) {
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nRuns = min(*runCount, runCap);
+    if (gw >= nRuns) return;
+    const DevConfig &c = p.cfg;
+    const unsigned long long e = runStarts[gw];
+    const uint32_t item = static_cast<uint32_t>(e >> 32);
+    const unsigned long long first = e & 0xFFFFFFFFull;
+    const unsigned long long itemEnd = p.itemBegin[item + 1];
+    const uint32_t revB = p.revBoundary[item];
+    const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
+    uint32_t n = 0, nFwd = 0, nCan = 0, cov = 0, fwdCov = 0, canCov = 0, start = 0, end = 0;
+    uint32_t prevPos = 0;
+    bool open = true;
+    for (unsigned long long base = first; open && base < itemEnd; base += 32) {
+        const unsigned long long i = base + lane;
+        const bool valid = i < itemEnd;
+        const uint2 rec = valid ? recs[i] : make_uint2(0u, 0u);
+        uint32_t before = __shfl_up_sync(0xFFFFFFFFu, rec.x, 1);
+        if (lane == 0) before = prevPos;
+        // the run's first record always belongs; the others need pos < revB and a start gap <= maxMatchDist
+        const bool isFirst = base == first && lane == 0;
+        const bool ok = valid && (isFirst || (rec.x < revB && rec.x - before <= c.maxMatchDist));
+        const uint32_t bad = ~__ballot_sync(0xFFFFFFFFu, ok);
+        const uint32_t take = bad ? (1u << (__ffs(bad) - 1)) - 1u : 0xFFFFFFFFu;     // lanes before the first break
+        const bool mine = (take >> lane) & 1u;
+        const uint32_t len = rec.y & 0xFFFFu, flags = (rec.y >> 16) & 0xFFu;
+        const uint32_t f = (mine && (flags & kMatchFwd)) ? 1u : 0u, cn = (mine && (flags & kMatchCan)) ? 1u : 0u;
+        const uint32_t cntTake = __popc(take);
+        n += cntTake;
+        nFwd += __popc(__ballot_sync(0xFFFFFFFFu, f != 0));
+        nCan += __popc(__ballot_sync(0xFFFFFFFFu, cn != 0));
+        cov += __reduce_add_sync(0xFFFFFFFFu, mine ? len : 0u);
+        fwdCov += __reduce_add_sync(0xFFFFFFFFu, f ? len : 0u);
+        canCov += __reduce_add_sync(0xFFFFFFFFu, cn ? len : 0u);
+        if (base == first) start = __shfl_sync(0xFFFFFFFFu, rec.x, 0);
+        if (cntTake) {
+            const int last = static_cast<int>(cntTake) - 1;
+            prevPos = __shfl_sync(0xFFFFFFFFu, rec.x, last);
+            end = prevPos + __shfl_sync(0xFFFFFFFFu, len, last);
         }
-        if (!isStart) continue;
-        Run r{};
-        r.begin(m);
-        for (unsigned long long j = i + 1; j < itemEnd; ++j) {
-            const DevMatch x = p.matches[j];
-            if (x.pos >= revB || x.pos - r.prev > c.maxMatchDist) break;
-            r.end = x.pos + x.len;
-            r.absorb(x);
-        }
-        const uint32_t len = r.end - r.start;
-        // computeBlockLabel, include/teloscope.h:217-222 (float32)
-        const float ratio = __fdiv_rn(__fmul_rn(__uint2float_rn(r.nFwd), 100.0f), __uint2float_rn(r.n));
-        const char label = ratio > 66.6f ? 'p' : (ratio < 33.3f ? 'q' : 'b');
-        if (len >= c.itsMinLen && r.nCan >= 4 && !(label == 'b' && r.nFwd < 2 && (r.n - r.nFwd) < 2)) {
-            DevBlock b{};
-            b.item = item; b.order = 0; b.start = r.start; b.len = len; b.counts = r.n; b.fwdCount = r.nFwd;
-            b.canCount = r.nCan; b.totalCov = r.cov; b.fwdCov = r.fwdCov; b.canCov = r.canCov;
-            b.validOr = 1; b.label = label; b.kind = 1;
-            emitBlock(p, b);
-        }
+        open = bad == 0;
+    }
+    if (lane != 0) return;
+    const uint32_t len = end - start;
+    // computeBlockLabel, include/teloscope.h:217-222 (float32)
+    const float ratio = __fdiv_rn(__fmul_rn(__uint2float_rn(nFwd), 100.0f), __uint2float_rn(n));
+    const char label = ratio > 66.6f ? 'p' : (ratio < 33.3f ? 'q' : 'b');
+    if (len >= c.itsMinLen && nCan >= 4 && !(label == 'b' && nFwd < 2 && (n - nFwd) < 2)) {
+        DevBlock b{};
+        b.item = item; b.order = 0; b.start = start; b.len = len; b.counts = n; b.fwdCount = nFwd;
+        b.canCount = nCan; b.totalCov = cov; b.fwdCov = fwdCov; b.canCov = canCov;
+        b.validOr = 1; b.label = label; b.kind = 1;
+        emitBlock(p, b);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Ordered selection for -m: canonical matches, and non-canonical matches flagged terminal.
-// Pass 1 counts per 2048-match chunk, a single block scans the chunk counts, pass 2 writes.
+// -m lists: final host-visible records (same layout as tls_match in include/teloscope_b200.h)
 // ------------------------------------------------------------------------------------------------
-constexpr int kSelChunk = 2048;
-
-__global__ void __launch_bounds__(256) selectCountKernel(const DevMatch *m, unsigned long long n, uint32_t *chunkCounts) {
-    const unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * kSelChunk;
-    uint32_t nc = 0, nn = 0;
-    for (int i = threadIdx.x; i < kSelChunk; i += 256) {
-        const unsigned long long k = base + i;
-        if (k < n) {
-            const uint8_t f = m[k].flags;
-            nc += (f & kMatchCan) != 0;
-            nn += (f & (kMatchCan | kMatchTerm)) == kMatchTerm;
-        }
-    }
-    nc = __reduce_add_sync(0xFFFFFFFFu, nc);
-    nn = __reduce_add_sync(0xFFFFFFFFu, nn);
-    __shared__ uint32_t s[2];
-    if (threadIdx.x < 2) s[threadIdx.x] = 0;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&s[0], nc); atomicAdd(&s[1], nn); }
-    __syncthreads();
-    if (threadIdx.x < 2) chunkCounts[2 * blockIdx.x + threadIdx.x] = s[threadIdx.x];
-}
-
-// in place: chunkCounts[2*i+k] -> exclusive prefix; totals[k] = sum
-__global__ void __launch_bounds__(1024) selectScanKernel(uint32_t *chunkCounts, uint32_t nChunks, unsigned long long *totals) {
-    __shared__ unsigned long long warpSums[2][32];
-    __shared__ unsigned long long carry[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 2) carry[tid] = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < nChunks; base += 1024) {
-        const uint32_t i = base + tid;
-        unsigned long long v[2], incl[2];
-        for (int k = 0; k < 2; ++k) {
-            v[k] = i < nChunks ? chunkCounts[2 * i + k] : 0;
-            incl[k] = v[k];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, incl[k], d);
-                if (lane >= d) incl[k] += u;
-            }
-            if (lane == 31) warpSums[k][warp] = incl[k];
-        }
-        __syncthreads();
-        if (warp < 2) {
-            unsigned long long w = warpSums[warp][lane], wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-                if (lane >= d) wi += u;
-            }
-            warpSums[warp][lane] = wi - w;
-        }
-        __syncthreads();
-        unsigned long long excl[2];
-        for (int k = 0; k < 2; ++k) {
-            excl[k] = carry[k] + warpSums[k][warp] + incl[k] - v[k];
-            // prefix fits 32 bits only if the list does; keep 32-bit chunk offsets relative to 0
-            if (i < nChunks) chunkCounts[2 * i + k] = static_cast<uint32_t>(excl[k]);
-        }
-        __syncthreads();
-        if (tid == 1023) { carry[0] = excl[0] + v[0]; carry[1] = excl[1] + v[1]; }
-        __syncthreads();
-    }
-    if (tid < 2) totals[tid] = carry[tid];
-}
-
-// Final host-visible match record (same layout as tls_match in include/teloscope_b200.h).
 struct OutMatch {
     unsigned long long pos;
     uint16_t len;
@@ -477,48 +466,22 @@ struct OutMatch {
 };
 static_assert(sizeof(OutMatch) == 16, "tls_match layout");
 
-__global__ void __launch_bounds__(32) selectWriteKernel(const DevMatch *m, unsigned long long n, const uint32_t *chunkOffsets,
-                                                        const unsigned long long *itemBegin, const unsigned long long *absPos,
-                                                        uint32_t nItems, OutMatch *outCan, uint32_t capCan, OutMatch *outNon,
-                                                        uint32_t capNon) {
-    // one warp walks the chunk in order so the output order equals the input order
-    const unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * kSelChunk;
-    const int lane = threadIdx.x;
-    uint32_t oc = chunkOffsets[2 * blockIdx.x], on = chunkOffsets[2 * blockIdx.x + 1];
-    // item of the chunk's first match: last i with itemBegin[i] <= base
-    uint32_t lo = 0, hi = nItems;
+__global__ void __launch_bounds__(256) selectFinalizeKernel(const DevMatch *m, const uint32_t *idxList, unsigned long long n,
+                                                            const unsigned long long *itemBegin, const unsigned long long *absPos,
+                                                            uint32_t nItems, OutMatch *out) {
+    const unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long idx = idxList[j];
+    uint32_t lo = 0, hi = nItems;                                  // item: last i with itemBegin[i] <= idx
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (itemBegin[mid] <= base) lo = mid + 1; else hi = mid;
+        if (itemBegin[mid] <= idx) lo = mid + 1; else hi = mid;
     }
-    uint32_t item = lo - 1;
-    for (int i = 0; i < kSelChunk; i += 32) {
-        const unsigned long long k = base + i + lane;
-        DevMatch x{};
-        bool isC = false, isN = false;
-        unsigned long long ap = 0;
-        if (k < n) {
-            x = m[k];
-            isC = (x.flags & kMatchCan) != 0;
-            isN = (x.flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
-            if (isC || isN) {
-                uint32_t it = item;
-                while (k >= itemBegin[it + 1]) ++it;
-                ap = absPos[it];
-            }
-        }
-        const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
-        const uint32_t below = (1u << lane) - 1u;
-        OutMatch o;
-        o.pos = ap + x.pos; o.len = x.len; o.isForward = x.flags & kMatchFwd ? 1 : 0; o.isCanonical = isC ? 1 : 0; o.pad = 0;
-        if (isC) { const uint32_t q = oc + __popc(bc & below); if (q < capCan) outCan[q] = o; }
-        if (isN) { const uint32_t q = on + __popc(bn & below); if (q < capNon) outNon[q] = o; }
-        oc += __popc(bc);
-        on += __popc(bn);
-        // advance the chunk's item cursor past items that end before the next 32 matches
-        const unsigned long long nextK = base + i + 32;
-        while (item + 1 < nItems && nextK >= itemBegin[item + 1]) ++item;
-    }
+    const DevMatch x = m[idx];
+    OutMatch o;
+    o.pos = absPos[lo - 1] + x.pos; o.len = x.len;
+    o.isForward = x.flags & kMatchFwd ? 1 : 0; o.isCanonical = x.flags & kMatchCan ? 1 : 0; o.pad = 0;
+    out[j] = o;
 }
 
 cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned long long *itemBegin, cudaStream_t s) {
@@ -526,29 +489,28 @@ cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned 
     return cudaGetLastError();
 }
 cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s) {
-    const uint32_t threads = 2u * p.nItems;
+    const unsigned long long threads = 64ull * p.nItems;              // one warp per (item, arm)
     if (threads == 0) return cudaSuccess;
-    terminalKernel<<<(threads + 127) / 128, 128, 0, s>>>(p);
+    terminalKernel<<<static_cast<unsigned int>((threads + 127) / 128), 128, 0, s>>>(p);
     return cudaGetLastError();
 }
-cudaError_t launchIts(const BlockParams &p, unsigned long long nMatches, cudaStream_t s) {
-    if (nMatches == 0) return cudaSuccess;
-    const unsigned long long threads = (nMatches + 63) / 64;
-    itsKernel<<<static_cast<unsigned int>((threads + 127) / 128), 128, 0, s>>>(p, nMatches);
+cudaError_t launchIts(const BlockParams &p, const uint32_t *canIdx, unsigned long long nCan, unsigned long long *runStarts,
+                      unsigned int *runCount, uint32_t runCap, cudaStream_t s) {
+    if (nCan == 0) return cudaSuccess;
+    itsSeedKernel<<<static_cast<unsigned int>((nCan + 255) / 256), 256, 0, s>>>(p, canIdx, nCan, runStarts, runCount, runCap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // the number of runs is only known on the device: enough warps for the capacity, surplus warps exit
+    const unsigned long long warps = std::min<unsigned long long>(runCap, nCan / 4 + 1);
+    itsRunKernel<<<static_cast<unsigned int>((warps * 32 + 127) / 128), 128, 0, s>>>(p, runStarts, runCount, runCap);
     return cudaGetLastError();
 }
-
-uint32_t selectChunks(unsigned long long n) { return static_cast<uint32_t>((n + kSelChunk - 1) / kSelChunk); }
-
-cudaError_t launchSelect(const DevMatch *m, unsigned long long n, uint32_t *chunkScratch, unsigned long long *totals,
-                         const unsigned long long *itemBegin, const unsigned long long *absPos, uint32_t nItems,
-                         void *outCan, uint32_t capCan, void *outNon, uint32_t capNon, cudaStream_t s) {
-    const uint32_t chunks = selectChunks(n);
-    if (chunks == 0) return cudaSuccess;
-    selectCountKernel<<<chunks, 256, 0, s>>>(m, n, chunkScratch);
-    selectScanKernel<<<1, 1024, 0, s>>>(chunkScratch, chunks, totals);
-    selectWriteKernel<<<chunks, 32, 0, s>>>(m, n, chunkScratch, itemBegin, absPos, nItems, static_cast<OutMatch *>(outCan),
-                                            capCan, static_cast<OutMatch *>(outNon), capNon);
+cudaError_t launchSelectFinalize(const DevMatch *m, const uint32_t *idxList, unsigned long long n,
+                                 const unsigned long long *itemBegin, const unsigned long long *absPos, uint32_t nItems,
+                                 void *out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    selectFinalizeKernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(m, idxList, n, itemBegin, absPos, nItems,
+                                                                                   static_cast<OutMatch *>(out));
     return cudaGetLastError();
 }
 

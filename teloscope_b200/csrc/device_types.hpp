@@ -129,6 +129,8 @@ struct ScanParams {
     uint32_t slotCap;
     uint32_t *slotCounts;          // [nTiles * kTileRows] records produced
     uint32_t *slotOv;              // [nTiles * kTileRows] overflow chunk base or 0xFFFFFFFF
+    uint32_t *slotCan, *slotNct;   // [nTiles * kTileRows] canonical / terminal non-canonical records among them
+    uint32_t *tileTot;             // [3][nTiles] per-tile totals (all, canonical, terminal non-canonical), atomics
     DevMatch *ovArena;
     uint32_t ovCap, ovChunk;
     unsigned int *ovCursor;        // zeroed per launch; > ovCap afterwards means "grow and rerun"
@@ -147,7 +149,9 @@ struct FastParams {
     uint32_t patLen;
     DevMatch *slots;
     uint32_t slotCap;
-    uint32_t *slotCounts, *slotOv;
+    uint32_t *slotCounts, *slotOv, *slotCan, *slotNct;
+    uint32_t *tileTot;             // [3][nTilesAll]
+    uint32_t nTilesAll;            // tiles of the batch (lean + general)
     DevMatch *ovArena;
     uint32_t ovCap, ovChunk;
     unsigned int *ovCursor;
@@ -163,18 +167,20 @@ struct GatherParams {
     const DevTile *tiles;
     const DevRegion *regions;
     uint32_t nRegions;
-    uint32_t *windows;             // [nWindows][8]: fields 4..7 (covered bp) are added here
+    uint32_t *windows;             // [nWindows][8]: fields 4..7 (covered bp) of general-kernel records are added here
     DevItemCounts *itemCounts;
     DevConfig cfg;
     const DevMatch *slots;
     uint32_t slotCap;
-    const uint32_t *slotCounts, *slotOv;
+    const uint32_t *slotCounts, *slotOv, *slotCan, *slotNct;
     const DevMatch *ovArena;
     uint32_t ovCap;
     uint32_t nTiles;
-    unsigned long long *tileBase;  // [nTiles + 1] exclusive prefix of per-tile totals
+    const unsigned long long *tileBase;   // [3][nTiles + 1] exclusive prefixes of the per-tile totals
     DevMatch *matches;             // ordered output
     unsigned long long matchCap;
+    uint32_t *canIdx, *nctIdx;     // positions in `matches` of the canonical / terminal non-canonical records
+    unsigned long long selCap;     // capacity of each index list
 };
 
 struct BlockParams {

@@ -15,20 +15,19 @@ size_t fastSmemBytes();
 bool fastConfigOk(const DevConfig &c);
 cudaError_t launchFastScan(const FastParams &p, int grid, cudaStream_t stream);
 
-// exclusive scan of per-tile match totals (tileBase[nTiles] = total), then ordered copy
-cudaError_t launchTileScan(const GatherParams &g, cudaStream_t s);
+// exclusive scans of the per-tile totals (3 arrays: tileBase[k][nTiles] = total), then ordered copy
+cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, cudaStream_t s);
 cudaError_t launchGather(const GatherParams &g, cudaStream_t s);
 
 cudaError_t launchTrimCr(const uint8_t *seq, DevRegion *regions, uint32_t nRegions, uint32_t *itemLen, cudaStream_t s);
 cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned long long *itemBegin, cudaStream_t s);
 cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s);
-cudaError_t launchIts(const BlockParams &p, unsigned long long nMatches, cudaStream_t s);
-
-uint32_t selectChunks(unsigned long long nMatches);
-// chunkScratch: 2 * selectChunks(n) u32; totals: 2 u64 (canonical, terminal non-canonical);
-// outCan / outNon receive final 16-byte tls_match records (absPos of the item added)
-cudaError_t launchSelect(const DevMatch *m, unsigned long long n, uint32_t *chunkScratch, unsigned long long *totals,
-                         const unsigned long long *itemBegin, const unsigned long long *absPos, uint32_t nItems,
-                         void *outCan, uint32_t capCan, void *outNon, uint32_t capNon, cudaStream_t s);
+// runStarts: runCap entries; runCount: device counter, zeroed by the caller
+cudaError_t launchIts(const BlockParams &p, const uint32_t *canIdx, unsigned long long nCan, unsigned long long *runStarts,
+                      unsigned int *runCount, uint32_t runCap, cudaStream_t s);
+// out receives n final 16-byte tls_match records (absPos of the item added) for the records idxList points at
+cudaError_t launchSelectFinalize(const DevMatch *m, const uint32_t *idxList, unsigned long long n,
+                                 const unsigned long long *itemBegin, const unsigned long long *absPos, uint32_t nItems,
+                                 void *out, cudaStream_t s);
 
 }  // namespace tls

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
     static_assert(kWindowSlots * 8 == kFastThreads, "one thread per window-slot word");
     DevFastTile *sMetaAll = reinterpret_cast<DevFastTile *>(smem + kMetaOff);
     uint64_t *sBar = reinterpret_cast<uint64_t *>(smem + kMiscOff);             // [2]
-    uint32_t *sNct = reinterpret_cast<uint32_t *>(smem + kMiscOff + 16);        // [2]
+    uint32_t *sTot = reinterpret_cast<uint32_t *>(smem + kMiscOff + 16);        // [2][4] tile totals: all, canonical, nct
 
     const uint32_t G = gridDim.x;
     uint32_t tileI = blockIdx.x;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
             asyncWaitAll();                                                // descriptor of tile k+1 has landed
             if (tileI + G < p.nTiles) issueLoad(sMetaAll[(iter + 1) & 3], buf ^ 1);
             if (tileI + 2 * G < p.nTiles) copyDescAsync(&sMetaAll[(iter + 2) & 3], &p.tiles[tileI + 2 * G]);
-            sNct[buf] = 0;
+            sTot[buf * 4 + 0] = sTot[buf * 4 + 1] = sTot[buf * 4 + 2] = 0;
         }
         sWin[tid] = 0;                                                    // 1024 threads = 128 slots x 8 words
         __syncthreads();
@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
         const uint32_t rowByte = warp * kRowBytes;
         const size_t slotIdx = static_cast<size_t>(t.tile) * kTileRows + warp;
         uint32_t wMatches = 0, ovBase = kNoOverflow;
+        uint32_t rowCan = 0, rowNct = 0;                                 // canonical / terminal non-canonical among them
 
         if (rowByte < usedBytes) {                                       // warp-uniform: the row holds tile positions
             const uint32_t spanByte = rowByte + lane * kSpanBytes;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
                     uint2 *out = reinterpret_cast<uint2 *>(slot) + wMatches;
                     for (uint32_t from = 0; from < total; from += 32) {
                         const uint32_t idx = from + lane;
-                        bool nct = false;
+                        bool nct = false, can = false;
                         if (idx < total) {
                             const uint32_t qq = sQueue[idx];
                             const uint32_t wi = qq >> 4, sh = (qq & 15u) * 2u;
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
                             const uint32_t rel = rowRel0 + qq;
                             const uint32_t winIdx = divWindow(cfg, rel);
                             uint32_t fl = (f >> 1) & 3u;
+                            can = (f & 4u) != 0;
                             atomicAdd(sWin + (winIdx + winDelta) * 8 + 2 + fl, 1u);
                             if (termMixed && isTerminalMatch(cfg, rel, winIdx, itemLen)) { fl |= kMatchTerm; nct = !(f & 4u); }
                             // DevMatch {pos, len:16, flags:8, region:8}
@@ -422,10 +424,8 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
                                     reinterpret_cast<uint2 *>(p.ovArena)[ovBase + (o - p.slotCap)] = rec;
                             }
                         }
-                        if (termMixed) {
-                            const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, nct));
-                            if (n && lane == 0) atomicAdd(&sNct[buf], n);
-                        }
+                        rowCan += __popc(__ballot_sync(0xFFFFFFFFu, can));
+                        if (termMixed) rowNct += __popc(__ballot_sync(0xFFFFFFFFu, nct));
                     }
                     wMatches += total;
                 };
@@ -461,6 +461,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
         if (lane == 0) {
             p.slotCounts[slotIdx] = wMatches;
             p.slotOv[slotIdx] = ovBase;
+            p.slotCan[slotIdx] = rowCan;
+            p.slotNct[slotIdx] = rowNct;
+            if (wMatches) atomicAdd(&sTot[buf * 4 + 0], wMatches);
+            if (rowCan) atomicAdd(&sTot[buf * 4 + 1], rowCan);
+            if (rowNct) atomicAdd(&sTot[buf * 4 + 2], rowNct);
         }
 
         // ---- tile epilogue: shared window slots -> global counters -----------------------------------------
@@ -488,7 +493,11 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
                 else if (lane == 6) atomicAdd(ic + 1, n);
                 else atomicAdd(ic + 2, n);
             }
-            if (tid == 0 && sNct[buf]) atomicAdd(reinterpret_cast<uint32_t *>(p.itemCounts + t.item) + 4, sNct[buf]);
+            if (tid < 3) {
+                const uint32_t v = sTot[buf * 4 + tid];
+                if (v) atomicAdd(p.tileTot + static_cast<size_t>(tid) * p.nTilesAll + t.tile, v);
+                if (tid == 2 && v) atomicAdd(reinterpret_cast<uint32_t *>(p.itemCounts + t.item) + 4, v);
+            }
         }
     }
 }

@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
             if (!((rowMask >> row) & 1u)) continue;            // warp-uniform
             // ---- per-row state: every row owns one output slot ------------------------------------------
             uint32_t wMatches = 0;      // match records this row has produced
+            uint32_t rowCan = 0, rowNct = 0;   // canonical / terminal non-canonical records among them
             uint32_t ovBase = kNoOverflow;
             const size_t slotIdx = static_cast<size_t>(tileIdx) * kTileRows + row;
             DevMatch *slot = p.slots + slotIdx * p.slotCap;
@@ -391,13 +392,16 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                             }
                         }
                     }
+                    if (hitMask && cfg.mode == 0) {          // "terminal" status, src/teloscope.cpp:451-459
+                        const uint32_t nIt = t.single ? sRegions[0].itemLen : itemLen;
+                        if (isTerminalMatch(cfg, rel, divWindow(cfg, rel), nIt)) termBit = kMatchTerm;
+                    }
                     if (hitMask && region == kRegionAccounted && !t.single) {
                         // region beyond the shared cache (> 32 regions in one tile): do the gather pass's
                         // accounting here, with global atomics
                         DevItemCounts *c = p.itemCounts + item;
                         const uint32_t winIdx = cfg.mode == 0 ? divWindow(cfg, rel) : 0;
-                        const bool term = cfg.mode == 0 && isTerminalMatch(cfg, rel, winIdx, itemLen);
-                        if (term) termBit = kMatchTerm;
+                        const bool term = termBit != 0;
                         for (uint32_t hm = hitMask; hm; hm &= hm - 1) {
                             const int ci = __ffs(hm) - 1;
                             const uint32_t fl = (flagBits >> (2 * ci)) & 3u, len = cfg.cls[ci].len;
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                     if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
                     ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
                 }
-                uint32_t o = wMatches + excl;
+                uint32_t o = wMatches + excl, nCanLane = 0, nNctLane = 0;
                 for (uint32_t hm = hitMask; hm; hm &= hm - 1, ++o) {
                     const int ci = __ffs(hm) - 1;
                     DevMatch m;
@@ -438,10 +442,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                     m.len = static_cast<uint16_t>(cfg.cls[ci].len);
                     m.flags = static_cast<uint8_t>(((flagBits >> (2 * ci)) & 3u) | termBit);   // kMatchFwd | kMatchCan
                     m.region = static_cast<uint8_t>(region);
+                    if (m.flags & kMatchCan) ++nCanLane; else if (termBit) ++nNctLane;
                     if (o < p.slotCap) slot[o] = m;
                     else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap) p.ovArena[ovBase + (o - p.slotCap)] = m;
                 }
                 wMatches += total;
+                rowCan += __reduce_add_sync(0xFFFFFFFFu, nCanLane);
+                rowNct += __reduce_add_sync(0xFFFFFFFFu, nNctLane);
             };
 
             const uint32_t spanByte = row * kRowBytes + lane * kSpanBytes;
@@ -588,6 +595,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
             if (lane == 0) {
                 p.slotCounts[slotIdx] = wMatches;
                 p.slotOv[slotIdx] = ovBase;
+                p.slotCan[slotIdx] = rowCan;
+                p.slotNct[slotIdx] = rowNct;
+                if (wMatches) atomicAdd(p.tileTot + tileIdx, wMatches);
+                if (rowCan) atomicAdd(p.tileTot + static_cast<size_t>(p.nTiles) + tileIdx, rowCan);
+                if (rowNct) atomicAdd(p.tileTot + 2 * static_cast<size_t>(p.nTiles) + tileIdx, rowNct);
             }
         }
 

@@ -124,12 +124,12 @@ typedef struct {
     const uint32_t *n_fwd, *n_rev;    /* per item: fwdMatches.size(), revMatches.size()           */
     const uint8_t *pass;              /* read mode: 1 = terminalBlocks non-empty                  */
     /* measurement (CUDA events on the ctx's stream) */
-    float scan_kernel_ms;             /* fused scan kernel only                                   */
+    float scan_kernel_ms;             /* scan kernels (lean + general), CUDA events                */
     float device_ms;                  /* all kernels of the batch                                 */
     uint64_t n_bases_scanned;         /* bases staged through the scan kernel                     */
     uint64_t n_matches;               /* match records the scan emitted                           */
     uint32_t n_kernel_launches;
-    uint32_t pad_;
+    float lean_kernel_ms;             /* lean scan kernel alone (0 when the batch has no lean tiles) */
 } tls_result;
 
 typedef struct tls_ctx tls_ctx;

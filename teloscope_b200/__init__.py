@@ -69,7 +69,7 @@ class _Result(C.Structure):
                 ("pass_", C.c_void_p),
                 ("scan_kernel_ms", C.c_float), ("device_ms", C.c_float),
                 ("n_bases_scanned", C.c_uint64), ("n_matches", C.c_uint64),
-                ("n_kernel_launches", C.c_uint32), ("pad", C.c_uint32)]
+                ("n_kernel_launches", C.c_uint32), ("lean_kernel_ms", C.c_float)]
 
 
 EXPORTS = ("tls_expand_patterns", "tls_device_count", "tls_create", "tls_destroy", "tls_submit",
@@ -203,6 +203,7 @@ class BatchResult:
         self.n_bases_scanned = int(r.n_bases_scanned)
         self.n_matches = int(r.n_matches)
         self.n_kernel_launches = int(r.n_kernel_launches)
+        self.lean_kernel_ms = float(r.lean_kernel_ms)
 
     def release(self):
         """Give the ticket's buffers back to the ctx (only needed after collect(copy=False))."""

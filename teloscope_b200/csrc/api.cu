@@ -92,6 +92,9 @@ struct HostBuf {
 struct Slot {
     bool busy = false, collected = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;       // window / item counters go home while the block kernels run
+    cudaEvent_t evScanDone = nullptr, evCopyDone = nullptr;
+    unsigned long long *hScanDev = nullptr;   // device view of hScan (mapped): scan totals without a copy
     cudaEvent_t evScan0 = nullptr, evScan1 = nullptr, evFast1 = nullptr, evAll0 = nullptr, evAll1 = nullptr;
     float fastMs = 0;
     // inputs
@@ -320,11 +323,16 @@ int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
     }
     for (Slot &s : ctx->slot) {
         TLS_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        TLS_CUDA(cudaStreamCreateWithFlags(&s.copyStream, cudaStreamNonBlocking));
+        TLS_CUDA(cudaEventCreateWithFlags(&s.evScanDone, cudaEventDisableTiming));
+        TLS_CUDA(cudaEventCreateWithFlags(&s.evCopyDone, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreate(&s.evScan0)); TLS_CUDA(cudaEventCreate(&s.evScan1)); TLS_CUDA(cudaEventCreate(&s.evFast1));
         TLS_CUDA(cudaEventCreate(&s.evAll0)); TLS_CUDA(cudaEventCreate(&s.evAll1));
         TLS_CUDA(s.dCounters.reserve(64));
         TLS_CUDA(s.hCounters.reserve(64));
-        TLS_CUDA(s.hScan.reserve(64));
+        TLS_CUDA(cudaHostAlloc(&s.hScan.p, 4096, cudaHostAllocMapped));
+        s.hScan.cap = 4096;
+        TLS_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.hScanDev), s.hScan.p, 0));
     }
     ctx->forceGeneral = std::getenv("TLS_FORCE_GENERAL") != nullptr;
     *out = ctx.release();
@@ -351,6 +359,9 @@ void tls_destroy(tls_ctx *ctx) {
         if (s.evFast1) cudaEventDestroy(s.evFast1);
         if (s.evAll0) cudaEventDestroy(s.evAll0);
         if (s.evAll1) cudaEventDestroy(s.evAll1);
+        if (s.copyStream) { cudaStreamSynchronize(s.copyStream); cudaStreamDestroy(s.copyStream); }
+        if (s.evScanDone) cudaEventDestroy(s.evScanDone);
+        if (s.evCopyDone) cudaEventDestroy(s.evCopyDone);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (DevBuf *b : {&ctx->dIndex, &ctx->dFlags, &ctx->dKeys, &ctx->dKeyFlags}) b->release();
@@ -397,6 +408,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
     const uint32_t nFast = static_cast<uint32_t>(s.fastTiles.size());
     const uint32_t redoCap = std::max<uint32_t>(nFast, 1) * kTileRows;
     TLS_CUDA(s.dRedo.reserve(16 + static_cast<size_t>(redoCap) * 4));       // [0] count, [1] status, [4..] entries
+    TLS_CUDA(cudaStreamWaitEvent(s.stream, s.evCopyDone, 0));               // a rerun must not clear what is still being copied
     TLS_CUDA(cudaMemsetAsync(s.dRedo.p, 0, 16, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 64, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dItemCounts.p, 0, std::max<size_t>(s.nItems, 1) * sizeof(DevItemCounts), s.stream));
@@ -460,18 +472,27 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             s.launches++;
         }
         TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
-        TLS_CUDA(launchTileScan(s.dTileTot.as<uint32_t>(), nTiles, s.dTileBase.as<unsigned long long>(), s.stream));
+        // window and per-item counters are final now: copy them home on the side stream
+        TLS_CUDA(cudaEventRecord(s.evScanDone, s.stream));
+        TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evScanDone, 0));
+        if (s.mode == TLS_MODE_GENOME && s.nWindows) {
+            TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
+            TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows.p, s.nWindows * 32, cudaMemcpyDeviceToHost, s.copyStream));
+        }
+        if (s.mode != TLS_MODE_READS && s.nItems) {
+            TLS_CUDA(s.hItemCounts.reserve(static_cast<size_t>(s.nItems) * sizeof(DevItemCounts)));
+            TLS_CUDA(cudaMemcpyAsync(s.hItemCounts.p, s.dItemCounts.p, static_cast<size_t>(s.nItems) * sizeof(DevItemCounts),
+                                     cudaMemcpyDeviceToHost, s.copyStream));
+        }
+        TLS_CUDA(cudaEventRecord(s.evCopyDone, s.copyStream));
+        TLS_CUDA(launchTileScan(s.dTileTot.as<uint32_t>(), nTiles, s.dTileBase.as<unsigned long long>(),
+                                reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>()), nFast ? redo : nullptr,
+                                s.hScanDev, s.stream));
         s.launches++;
     } else {
         TLS_CUDA(cudaMemsetAsync(s.dTileBase.p, 0, 24, s.stream));
+        std::memset(s.hScan.p, 0, 64);
     }
-    // host copy: [0] ovCursor; [8],[16],[24] totals (all, canonical, terminal non-canonical); [32] redo count, status
-    unsigned long long *tb = s.dTileBase.as<unsigned long long>();
-    uint8_t *hc = s.hScan.as<uint8_t>();
-    TLS_CUDA(cudaMemcpyAsync(hc, s.dCounters.p, 8, cudaMemcpyDeviceToHost, s.stream));
-    for (int k = 0; k < 3; ++k)
-        TLS_CUDA(cudaMemcpyAsync(hc + 8 + 8 * k, tb + static_cast<size_t>(k) * (nTiles + 1) + nTiles, 8, cudaMemcpyDeviceToHost, s.stream));
-    TLS_CUDA(cudaMemcpyAsync(hc + 32, s.dRedo.p, 8, cudaMemcpyDeviceToHost, s.stream));
     return TLS_OK;
 }
 
@@ -553,6 +574,7 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     if (nWin > 0xFFFFFFFFull) return fail(TLS_ERR_INVALID, "more than 2^32 windows in one batch");
 
     // ---- tiles: cut runs of (nearly) adjacent regions into pieces of <= kTileMaxLen bytes ------------
+    s.tiles.reserve(static_cast<size_t>(s.nBases / kTileMaxLen) + s.regions.size() + 1);
     {
         size_t r = 0;
         const size_t nr = s.regions.size();
@@ -575,6 +597,7 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
 
     // ---- which kernel takes which tile: the lean kernel wants tiles inside one region ------------------
     s.fastTiles.clear(); s.generalTiles.clear();
+    s.fastTiles.reserve(s.tiles.size());
     {
         DevConfig probe = ctx->dcfg;
         probe.mode = b->mode;
@@ -658,14 +681,14 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
         // ---- wait for the scan; grow the overflow arena and rerun if it ran out --------------------
         for (;;) {
             TLS_CUDA(cudaStreamSynchronize(s.stream));
-            const uint32_t *hs = s.hScan.as<uint32_t>();
-            if (hs[9] != 0)
+            const volatile unsigned long long *hs = s.hScan.as<unsigned long long>();   // ovCursor, totals[3], redo | status << 32
+            if ((hs[4] >> 32) != 0)
                 return fail(TLS_ERR_STATE, "lean scan kernel could not lay out its shared memory (window base %% 64 KiB); "
                                            "set TLS_FORCE_GENERAL=1");
-            if (tr.on) fprintf(stderr, " lean_tiles=%zu/%zu redo_rows=%u", s.fastTiles.size(), s.tiles.size(), hs[8]);
-            const uint32_t ovUsed = hs[0];
-            const unsigned long long *tot = reinterpret_cast<const unsigned long long *>(s.hScan.as<uint8_t>() + 8);
-            s.nMatches = tot[0]; s.nCanAll = tot[1]; s.nNctAll = tot[2];
+            if (tr.on) fprintf(stderr, " lean_tiles=%zu/%zu redo_rows=%u", s.fastTiles.size(), s.tiles.size(),
+                               static_cast<uint32_t>(hs[4]));
+            const uint32_t ovUsed = static_cast<uint32_t>(hs[0]);
+            s.nMatches = hs[1]; s.nCanAll = hs[2]; s.nNctAll = hs[3];
             if (ovUsed <= s.ovCap) break;
             s.ovCap = ovUsed + ovUsed / 4;
             if ((rc = enqueueScan(ctx, s))) return rc;
@@ -743,15 +766,6 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
         unsigned long long selTotals[2] = {wantSel ? s.nCanAll : 0, wantSel ? s.nNctAll : 0};
 
         // ---- copy results back ------------------------------------------------------------------------
-        if (genome && s.nWindows) {
-            TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
-            TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows.p, s.nWindows * 32, cudaMemcpyDeviceToHost, s.stream));
-        }
-        if (!reads && n) {
-            TLS_CUDA(s.hItemCounts.reserve(static_cast<size_t>(n) * sizeof(DevItemCounts)));
-            TLS_CUDA(cudaMemcpyAsync(s.hItemCounts.p, s.dItemCounts.p, static_cast<size_t>(n) * sizeof(DevItemCounts),
-                                     cudaMemcpyDeviceToHost, s.stream));
-        }
         if (nBlocks) {
             TLS_CUDA(s.hBlocks.reserve(static_cast<size_t>(nBlocks) * sizeof(DevBlock)));
             TLS_CUDA(cudaMemcpyAsync(s.hBlocks.p, s.dBlocks.p, static_cast<size_t>(nBlocks) * sizeof(DevBlock),
@@ -771,6 +785,7 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             TLS_CUDA(cudaMemcpyAsync(s.hSelNon.p, s.dSelNon.p, selTotals[1] * sizeof(tls_match), cudaMemcpyDeviceToHost, s.stream));
         }
         TLS_CUDA(cudaStreamSynchronize(s.stream));
+        TLS_CUDA(cudaStreamSynchronize(s.copyStream));
         TLS_CUDA(cudaEventElapsedTime(&s.allMs, s.evAll0, s.evAll1));
         tr.mark("d2h");
 
@@ -829,6 +844,7 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
     res->pass = s.pass.data();
     res->scan_kernel_ms = s.scanMs; res->device_ms = s.allMs;
     res->n_bases_scanned = s.nBases; res->n_matches = s.nMatches; res->n_kernel_launches = s.launches;
+    res->lean_kernel_ms = s.fastMs;
     return TLS_OK;
 }
 

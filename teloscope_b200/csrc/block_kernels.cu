@@ -1,7 +1,6 @@
 // Kernels that turn the per-row match slots into what SegmentData holds besides the window counters:
 //   tileScanKernel      exclusive prefixes over tiles of (all, canonical, terminal non-canonical) matches
 //   gatherKernel        slot arena -> one ordered match list + index lists of the -m selections
-//                       (+ window / item accounting of the records the general scan kernel left to it)
 //   itemOffsetsKernel   exclusive scan of per-item match counts
 //   terminalKernel      Teloscope::getTerminalBlocks (src/teloscope.cpp:29-176), one warp per
 //                       (item, arm), Phase 2 merged on the fly
@@ -74,9 +73,18 @@ __global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *c
 // Per-tile totals (written by the scan kernels with atomics) -> exclusive prefixes.
 // tileTot / tileBase hold three arrays back to back: all matches, canonical, terminal non-canonical.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase) {
+// The totals, the overflow cursor and the redo counters are also published to `hostOut` (mapped
+// pinned host memory: [0] ovCursor, [1..3] totals, [4] redo count | status << 32), so that the host
+// needs no copy-engine transfer (which would queue behind the window counters going home).
+__global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase,
+                                                       const unsigned int *ovCursor, const unsigned int *redo,
+                                                       unsigned long long *hostOut) {
     __shared__ unsigned long long warpSums[32];
     __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) {
+        hostOut[0] = *ovCursor;
+        hostOut[4] = redo ? (static_cast<unsigned long long>(redo[0]) | (static_cast<unsigned long long>(redo[1]) << 32)) : 0ull;
+    }
     for (int k = 0; k < 3; ++k) {
         if (threadIdx.x == 0) carry = 0;
         __syncthreads();
@@ -88,29 +96,22 @@ __global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, 
             const unsigned long long excl = blockExclusive1024(v, warpSums, &carry);
             if (i < nTiles) out[i] = excl;
         }
-        if (threadIdx.x == 0) out[nTiles] = carry;
+        if (threadIdx.x == 0) { out[nTiles] = carry; hostOut[1 + k] = carry; }
         __syncthreads();
     }
+    if (threadIdx.x == 0) __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
 // Slot arena -> ordered match list.  One block per tile, one warp per row slot at a time; fully
-// coalesced 8-byte copies.  Records the scan kernels did not account for (general kernel, regions
-// held in the tile's region cache) are accounted here with shared-memory atomics.
+// coalesced 8-byte copies (all window / item accounting was done by the scan kernels).
 // ------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
-constexpr int kGatherSlots = 128;
 
 __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParams g) {
     const uint32_t tile = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ uint32_t sOff[3][kTileRows + 1];
-    __shared__ DevRegion sRegion[kRegionCache];
-    __shared__ uint32_t sRegCnt[kRegionCache][5];
-    __shared__ uint32_t sWin[kGatherSlots][4];
-    __shared__ uint32_t sFirstWin, sNReg, sDirty;
-    const DevConfig &c = g.cfg;
-    const DevTile dt = g.tiles[tile];
     if (warp < 3) {
         // exclusive prefix over the 32 row slots of this tile (warp k handles array k)
         const uint32_t *src = warp == 0 ? g.slotCounts : warp == 1 ? g.slotCan : g.slotNct;
@@ -123,28 +124,12 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
         }
         sOff[warp][lane] = incl - v;
         if (lane == 31) sOff[warp][kTileRows] = incl;
-    } else if (warp == 3) {
-        const uint64_t tileEnd = dt.bufStart + dt.len;
-        const uint32_t idx = min(dt.firstRegion + static_cast<uint32_t>(lane), g.nRegions - 1);
-        const DevRegion r = g.regions[idx];
-        const bool in = dt.firstRegion + lane < g.nRegions && r.bufStart < tileEnd;
-        const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, in));
-        if (in) sRegion[lane] = r;
-        if (lane == 0) {
-            sNReg = n;
-            sDirty = 0;
-            const uint64_t s = dt.bufStart > r.bufStart ? dt.bufStart : r.bufStart;
-            sFirstWin = (c.mode == 0 && n > 0) ? r.winBase + divWindow(c, r.relStart + static_cast<uint32_t>(s - r.bufStart)) : 0;
-        }
     }
-    for (int i = tid; i < kRegionCache * 5; i += kGatherThreads) (&sRegCnt[0][0])[i] = 0;
-    for (int i = tid; i < kGatherSlots * 4; i += kGatherThreads) (&sWin[0][0])[i] = 0;
     __syncthreads();
     if (sOff[0][kTileRows] == 0) return;
     const unsigned long long base = g.tileBase[tile];
     const unsigned long long baseCan = g.tileBase[static_cast<size_t>(g.nTiles) + 1 + tile];
     const unsigned long long baseNct = g.tileBase[2 * (static_cast<size_t>(g.nTiles) + 1) + tile];
-    const uint32_t firstWin = sFirstWin;
     const uint32_t laneLt = (1u << lane) - 1u;
 
     for (int s = warp; s < kTileRows; s += kGatherThreads / 32) {
@@ -155,6 +140,7 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
         const unsigned long long ov = g.slotOv[slotIdx];
         const unsigned long long o = base + sOff[0][s];
         unsigned long long oc = baseCan + sOff[1][s], on = baseNct + sOff[2][s];
+        const bool anySel = sOff[1][s + 1] != sOff[1][s] || sOff[2][s + 1] != sOff[2][s];     // warp-uniform
         for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
             const uint32_t k = k0 + lane;
             uint2 rec = make_uint2(0u, 0u);
@@ -164,27 +150,10 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
                 else if (ov + (k - g.slotCap) < g.ovCap) rec = reinterpret_cast<const uint2 *>(g.ovArena)[ov + (k - g.slotCap)];
                 else have = false;                              // overflow arena exhausted: the host reruns the scan
             }
-            const uint32_t flags = (rec.y >> 16) & 0xFFu, region = rec.y >> 24;
-            if (have && region != kRegionAccounted) {
-                // general-kernel record: window coverage and per-item counters
-                const DevRegion &r = sRegion[region];
-                const uint32_t len = rec.y & 0xFFFFu;
-                const bool fwd = flags & kMatchFwd, can = flags & kMatchCan;
-                if (c.mode == 0) {
-                    const uint32_t win = r.winBase + divWindow(c, rec.x), sl = win - firstWin;
-                    uint32_t *w = sl < kGatherSlots ? sWin[sl] : g.windows + static_cast<size_t>(win) * 8 + 4;
-                    atomicAdd(w + (can ? 0 : 1), len);
-                    atomicAdd(w + (fwd ? 2 : 3), len);
-                }
-                uint32_t *rc = sRegCnt[region];
-                atomicAdd(rc + 0, 1u);
-                atomicAdd(rc + (fwd ? 1 : 2), 1u);
-                if (can) atomicAdd(rc + 3, 1u);
-                else if (flags & kMatchTerm) atomicAdd(rc + 4, 1u);
-                sDirty = 1;
-            }
             if (have && o + k < g.matchCap) reinterpret_cast<uint2 *>(g.matches)[o + k] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
+            if (!anySel) continue;
             // index lists of the -m selections, in genome order
+            const uint32_t flags = (rec.y >> 16) & 0xFFu;
             const bool isC = have && (flags & kMatchCan);
             const bool isN = have && (flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
             const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
@@ -194,20 +163,11 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
             on += __popc(bn);
         }
     }
-    __syncthreads();
-    if (!sDirty) return;
-    for (int k = tid; k < kGatherSlots * 4; k += kGatherThreads) {
-        const uint32_t v = (&sWin[0][0])[k];
-        if (v) atomicAdd(&g.windows[static_cast<size_t>(firstWin + (k >> 2)) * 8 + 4 + (k & 3)], v);
-    }
-    for (int k = tid; k < static_cast<int>(sNReg) * 5; k += kGatherThreads) {
-        const uint32_t v = (&sRegCnt[0][0])[k];
-        if (v) atomicAdd(reinterpret_cast<uint32_t *>(g.itemCounts + sRegion[k / 5].item) + (k % 5), v);
-    }
 }
 
-cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, cudaStream_t s) {
-    tileScanKernel<<<1, 1024, 0, s>>>(tileTot, nTiles, tileBase);
+cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, const unsigned int *ovCursor,
+                           const unsigned int *redo, unsigned long long *hostOut, cudaStream_t s) {
+    tileScanKernel<<<1, 1024, 0, s>>>(tileTot, nTiles, tileBase, ovCursor, redo, hostOut);
     return cudaGetLastError();
 }
 cudaError_t launchGather(const GatherParams &g, cudaStream_t s) {

@@ -16,7 +16,9 @@ bool fastConfigOk(const DevConfig &c);
 cudaError_t launchFastScan(const FastParams &p, int grid, cudaStream_t stream);
 
 // exclusive scans of the per-tile totals (3 arrays: tileBase[k][nTiles] = total), then ordered copy
-cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, cudaStream_t s);
+// hostOut: 5 u64 in mapped pinned host memory: ovCursor, totals[3], redo count | status << 32
+cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, const unsigned int *ovCursor,
+                           const unsigned int *redo, unsigned long long *hostOut, cudaStream_t s);
 cudaError_t launchGather(const GatherParams &g, cudaStream_t s);
 
 cudaError_t launchTrimCr(const uint8_t *seq, DevRegion *regions, uint32_t nRegions, uint32_t *itemLen, cudaStream_t s);

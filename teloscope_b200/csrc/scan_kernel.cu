@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
 
             // ---- stage 2: verify up to 32 queued candidates and emit match records ---------------------
             auto resolveBatch = [&](uint32_t from, uint32_t count) {
-                uint32_t hitMask = 0, flagBits = 0, rel = 0, region = 0, termBit = 0;
+                uint32_t hitMask = 0, flagBits = 0, rel = 0, termBit = 0;
                 if (lane < static_cast<int>(count)) {
                     const uint32_t sb = sQueue[from + lane];
                     const uint32_t q = sb - skew;                       // tile position (wraps if before the tile)
@@ -342,7 +342,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                         const Located loc = locate(p, t, sRegions, static_cast<int>(q));
                         ok = loc.ok;
                         rel = loc.rel; limit = loc.regionEndRel; item = loc.item; itemLen = loc.itemLen; winBaseLoc = loc.winBase;
-                        region = loc.cacheIdx == 0xFFFFFFFFu ? kRegionAccounted : loc.cacheIdx;
                     }
                     if (ok) {
                         if (cfg.mode == 0) {     // matches never cross the window end (src/teloscope.cpp:439)
@@ -396,9 +395,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                         const uint32_t nIt = t.single ? sRegions[0].itemLen : itemLen;
                         if (isTerminalMatch(cfg, rel, divWindow(cfg, rel), nIt)) termBit = kMatchTerm;
                     }
-                    if (hitMask && region == kRegionAccounted && !t.single) {
-                        // region beyond the shared cache (> 32 regions in one tile): do the gather pass's
-                        // accounting here, with global atomics
+                    if (hitMask) {
+                        // window coverage (src/teloscope.cpp:470-510) and per-item counters of this position's matches
+                        if (t.single) { item = sRegions[0].item; winBaseLoc = winBase0; }
                         DevItemCounts *c = p.itemCounts + item;
                         const uint32_t winIdx = cfg.mode == 0 ? divWindow(cfg, rel) : 0;
                         const bool term = termBit != 0;
@@ -441,7 +440,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                     m.pos = rel;
                     m.len = static_cast<uint16_t>(cfg.cls[ci].len);
                     m.flags = static_cast<uint8_t>(((flagBits >> (2 * ci)) & 3u) | termBit);   // kMatchFwd | kMatchCan
-                    m.region = static_cast<uint8_t>(region);
+                    m.region = kRegionAccounted;
                     if (m.flags & kMatchCan) ++nCanLane; else if (termBit) ++nNctLane;
                     if (o < p.slotCap) slot[o] = m;
                     else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap) p.ovArena[ovBase + (o - p.slotCap)] = m;

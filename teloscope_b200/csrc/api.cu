@@ -106,10 +106,12 @@ struct Slot {
     std::vector<DevRegion> regions;
     std::vector<DevTile> tiles;
     std::vector<DevFastTile> fastTiles;      // tiles for the lean kernel
+    std::vector<DevRowTile> rowTiles;        // tiles for the window-row kernel
+    std::vector<uint8_t> tileIsRow;          // per tile: 1 = made of whole windows for the window-row kernel
     std::vector<uint32_t> generalTiles;      // indices of the tiles the general kernel takes entirely
     const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
     HostBuf hSeq, hMeta, hMeta2;              // pinned staging
-    DevBuf dFastTiles, dGeneralTiles, dRedo, dSlotCan, dSlotNct, dTileTot, dCanIdx, dNctIdx, dRunStarts;
+    DevBuf dRowTiles, dFastTiles, dGeneralTiles, dRedo, dSlotCan, dSlotNct, dTileTot, dCanIdx, dNctIdx, dRunStarts;
     uint64_t nCanAll = 0, nNctAll = 0;       // canonical / terminal non-canonical records of the batch
     DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotCounts,
         dSlotOv, dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
@@ -144,6 +146,8 @@ struct tls_ctx {
     DevBuf dIndex, dFlags, dKeys, dKeyFlags;
     uint32_t slotCap = 0, ovChunk = 0;
     bool forceGeneral = false;               // TLS_FORCE_GENERAL=1 or a lean-kernel layout failure
+    bool noRowKernel = false;                // TLS_NO_ROW_KERNEL=1: 1536-base-row lean kernel instead of the window-row kernel
+    uint32_t rowMinWindows = kRowMinWindows; // TLS_ROW_MIN_WINDOWS=n: shortest contig (in windows) the window-row kernel takes
     Slot slot[2];
 };
 
@@ -335,6 +339,8 @@ int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
         TLS_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.hScanDev), s.hScan.p, 0));
     }
     ctx->forceGeneral = std::getenv("TLS_FORCE_GENERAL") != nullptr;
+    ctx->noRowKernel = std::getenv("TLS_NO_ROW_KERNEL") != nullptr;
+    if (const char *e = std::getenv("TLS_ROW_MIN_WINDOWS")) ctx->rowMinWindows = std::max(1, std::atoi(e));
     *out = ctx.release();
     return TLS_OK;
 }
@@ -344,7 +350,7 @@ void tls_destroy(tls_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (Slot &s : ctx->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        for (DevBuf *b : {&s.dFastTiles, &s.dGeneralTiles, &s.dRedo, &s.dSlotCan, &s.dSlotNct, &s.dTileTot, &s.dCanIdx,
+        for (DevBuf *b : {&s.dRowTiles, &s.dFastTiles, &s.dGeneralTiles, &s.dRedo, &s.dSlotCan, &s.dSlotNct, &s.dTileTot, &s.dCanIdx,
                           &s.dNctIdx, &s.dRunStarts})
             b->release();
         for (DevBuf *b : {&s.dAbsPos, &s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
@@ -403,6 +409,12 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
     TLS_CUDA(s.dTileTot.reserve(static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * 12));
     TLS_CUDA(s.dTileBase.reserve((static_cast<size_t>(nTiles) + 1) * 24));
     TLS_CUDA(cudaMemsetAsync(s.dTileTot.p, 0, static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * 12, s.stream));
+    if (!s.rowTiles.empty()) {
+        // the last tile of a contig has fewer than 32 windows: its other row slots must read as empty
+        TLS_CUDA(cudaMemsetAsync(s.dSlotCounts.p, 0, nSlots * 4, s.stream));
+        TLS_CUDA(cudaMemsetAsync(s.dSlotCan.p, 0, nSlots * 4, s.stream));
+        TLS_CUDA(cudaMemsetAsync(s.dSlotNct.p, 0, nSlots * 4, s.stream));
+    }
     s.ovCap = std::max<uint32_t>(s.ovCap, 256u * ctx->ovChunk);
     TLS_CUDA(s.dOvArena.reserve(static_cast<size_t>(s.ovCap) * sizeof(DevMatch)));
     const uint32_t nFast = static_cast<uint32_t>(s.fastTiles.size());
@@ -420,6 +432,30 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         if (s.mode != TLS_MODE_GENOME) cfg.countAcgt = 0;
         unsigned int *redo = s.dRedo.as<unsigned int>();
         TLS_CUDA(cudaEventRecord(s.evScan0, s.stream));
+        const uint32_t nRow = static_cast<uint32_t>(s.rowTiles.size());
+        if (nRow) {
+            RowParams f{};
+            f.seq = s.devSeq;
+            f.tiles = s.dRowTiles.as<DevRowTile>(); f.nTiles = nRow;
+            f.index8 = ctx->dIndex.as<uint8_t>();
+            f.flagTab = ctx->dFlags.as<uint8_t>() + cfg.cls[0].flagOffset;
+            f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
+            f.patLen = cfg.cls[0].len;
+            f.slots = s.dSlots.as<DevMatch>(); f.slotCap = ctx->slotCap;
+            f.slotCounts = s.dSlotCounts.as<uint32_t>(); f.slotOv = s.dSlotOv.as<uint32_t>();
+            f.slotCan = s.dSlotCan.as<uint32_t>(); f.slotNct = s.dSlotNct.as<uint32_t>();
+            f.tileTot = s.dTileTot.as<uint32_t>(); f.nTilesAll = nTiles;
+            f.ovArena = s.dOvArena.as<DevMatch>(); f.ovCap = s.ovCap; f.ovChunk = ctx->ovChunk;
+            f.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
+            f.windows = s.dWindows.as<uint32_t>();
+            f.itemCounts = s.dItemCounts.as<DevItemCounts>();
+            f.status = redo + 1;
+            f.cfg = cfg;
+            const uint32_t nUnits = nRow * (kTileRows / kRowsPerUnit);
+            const int grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (nUnits + kRowWarps - 1) / kRowWarps));
+            TLS_CUDA(launchRowScan(f, grid, s.stream));
+            s.launches++;
+        }
         if (nFast) {
             FastParams f{};
             f.seq = s.devSeq;
@@ -486,7 +522,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         }
         TLS_CUDA(cudaEventRecord(s.evCopyDone, s.copyStream));
         TLS_CUDA(launchTileScan(s.dTileTot.as<uint32_t>(), nTiles, s.dTileBase.as<unsigned long long>(),
-                                reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>()), nFast ? redo : nullptr,
+                                reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>()), (nFast || nRow) ? redo : nullptr,
                                 s.hScanDev, s.stream));
         s.launches++;
     } else {
@@ -573,15 +609,50 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     s.nWindows = nWin;
     if (nWin > 0xFFFFFFFFull) return fail(TLS_ERR_INVALID, "more than 2^32 windows in one batch");
 
-    // ---- tiles: cut runs of (nearly) adjacent regions into pieces of <= kTileMaxLen bytes ------------
-    s.tiles.reserve(static_cast<size_t>(s.nBases / kTileMaxLen) + s.regions.size() + 1);
+    // ---- tiles ------------------------------------------------------------------------------------
+    // Genome mode with a window-row configuration: every contig of >= kRowMinWindows windows becomes
+    // tiles of 32 whole windows (one window per tile row).  Everything else: runs of (nearly) adjacent
+    // regions are cut into pieces of <= kTileMaxLen bytes; of those the lean kernel takes the tiles that
+    // lie inside one region, the general kernel the rest.
+    s.tiles.clear(); s.tileIsRow.clear(); s.rowTiles.clear();
+    s.tiles.reserve(static_cast<size_t>(s.nBases / 32000) + s.regions.size() + 1);
     {
+        DevConfig probe = ctx->dcfg;
+        probe.mode = b->mode;
+        const bool rowOk = rowConfigOk(probe) && !ctx->forceGeneral && !ctx->noRowKernel;
+        const uint32_t W = ctx->cfg.window_size;
+        const uint64_t rowMinLen = static_cast<uint64_t>(W) * (ctx->rowMinWindows - 1) + 1;   // at least rowMinWindows windows
         size_t r = 0;
         const size_t nr = s.regions.size();
         while (r < nr) {
-            uint64_t spanStart = s.regions[r].bufStart, spanEnd = spanStart + s.regions[r].len;
+            const DevRegion &reg = s.regions[r];
+            if (rowOk && reg.len >= rowMinLen) {
+                const uint32_t nWinReg = (reg.len + W - 1) / W;
+                for (uint32_t w0 = 0; w0 < nWinReg; w0 += kTileRows) {
+                    DevRowTile rt{};
+                    rt.nRows = std::min<uint32_t>(kTileRows, nWinReg - w0);
+                    rt.relBase = reg.relStart + w0 * W;
+                    rt.bufStart = reg.bufStart + static_cast<uint64_t>(w0) * W;
+                    rt.tile = static_cast<uint32_t>(s.tiles.size());
+                    rt.item = reg.item; rt.itemLen = reg.itemLen;
+                    rt.firstWin = reg.winBase + w0;
+                    s.rowTiles.push_back(rt);
+                    DevTile t{};
+                    t.bufStart = rt.bufStart;
+                    t.len = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(rt.nRows) * W, reg.len - static_cast<uint64_t>(w0) * W));
+                    t.firstRegion = static_cast<uint32_t>(r);
+                    s.tiles.push_back(t);
+                    s.tileIsRow.push_back(1);
+                }
+                ++r;
+                continue;
+            }
+            uint64_t spanStart = reg.bufStart, spanEnd = spanStart + reg.len;
             size_t e = r + 1;
-            while (e < nr && s.regions[e].bufStart - spanEnd <= 4096) { spanEnd = s.regions[e].bufStart + s.regions[e].len; ++e; }
+            while (e < nr && !(rowOk && s.regions[e].len >= rowMinLen) && s.regions[e].bufStart - spanEnd <= 4096) {
+                spanEnd = s.regions[e].bufStart + s.regions[e].len;
+                ++e;
+            }
             size_t fr = r;
             for (uint64_t p = spanStart; p < spanEnd; p += kTileMaxLen) {
                 DevTile t{};
@@ -590,20 +661,22 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
                 while (fr + 1 < e && s.regions[fr].bufStart + s.regions[fr].len <= p) ++fr;
                 t.firstRegion = static_cast<uint32_t>(fr);
                 s.tiles.push_back(t);
+                s.tileIsRow.push_back(0);
             }
             r = e;
         }
     }
 
-    // ---- which kernel takes which tile: the lean kernel wants tiles inside one region ------------------
+    // ---- which kernel takes the other tiles: the lean kernel wants tiles inside one region -------------
     s.fastTiles.clear(); s.generalTiles.clear();
-    s.fastTiles.reserve(s.tiles.size());
+    s.fastTiles.reserve(s.tiles.size() - s.rowTiles.size());
     {
         DevConfig probe = ctx->dcfg;
         probe.mode = b->mode;
         const bool fastOk = fastConfigOk(probe) && !ctx->forceGeneral;
         const uint32_t W = ctx->cfg.window_size;
         for (size_t ti = 0; ti < s.tiles.size(); ++ti) {
+            if (s.tileIsRow[ti]) continue;
             const DevTile &t = s.tiles[ti];
             const DevRegion &r = s.regions[t.firstRegion];
             const bool single = r.bufStart <= t.bufStart && t.bufStart + t.len <= r.bufStart + r.len;
@@ -624,15 +697,19 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     tr.mark("plan");
     // ---- upload metadata ------------------------------------------------------------------------
     {
-        const size_t bFast = s.fastTiles.size() * sizeof(DevFastTile), bGen = s.generalTiles.size() * 4;
-        TLS_CUDA(s.hMeta2.reserve(bFast + bGen + 64));
+        const size_t bFast = s.fastTiles.size() * sizeof(DevFastTile), bGen = s.generalTiles.size() * 4,
+                     bRow = s.rowTiles.size() * sizeof(DevRowTile);
+        TLS_CUDA(s.hMeta2.reserve(bFast + bGen + bRow + 64));
         uint8_t *h2 = s.hMeta2.as<uint8_t>();
-        if (bFast) std::memcpy(h2, s.fastTiles.data(), bFast);
-        if (bGen) std::memcpy(h2 + bFast, s.generalTiles.data(), bGen);
+        if (bRow) std::memcpy(h2, s.rowTiles.data(), bRow);
+        if (bFast) std::memcpy(h2 + bRow, s.fastTiles.data(), bFast);
+        if (bGen) std::memcpy(h2 + bRow + bFast, s.generalTiles.data(), bGen);
+        TLS_CUDA(s.dRowTiles.reserve(std::max<size_t>(bRow, 16)));
         TLS_CUDA(s.dFastTiles.reserve(std::max<size_t>(bFast, 16)));
         TLS_CUDA(s.dGeneralTiles.reserve(std::max<size_t>(bGen, 16)));
-        if (bFast) TLS_CUDA(cudaMemcpyAsync(s.dFastTiles.p, h2, bFast, cudaMemcpyHostToDevice, s.stream));
-        if (bGen) TLS_CUDA(cudaMemcpyAsync(s.dGeneralTiles.p, h2 + bFast, bGen, cudaMemcpyHostToDevice, s.stream));
+        if (bRow) TLS_CUDA(cudaMemcpyAsync(s.dRowTiles.p, h2, bRow, cudaMemcpyHostToDevice, s.stream));
+        if (bFast) TLS_CUDA(cudaMemcpyAsync(s.dFastTiles.p, h2 + bRow, bFast, cudaMemcpyHostToDevice, s.stream));
+        if (bGen) TLS_CUDA(cudaMemcpyAsync(s.dGeneralTiles.p, h2 + bRow + bFast, bGen, cudaMemcpyHostToDevice, s.stream));
     }
     const size_t bRegions = s.regions.size() * sizeof(DevRegion), bTiles = s.tiles.size() * sizeof(DevTile),
                  bLen = static_cast<size_t>(n) * 4, bAbs = static_cast<size_t>(n) * 8;
@@ -685,7 +762,7 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             if ((hs[4] >> 32) != 0)
                 return fail(TLS_ERR_STATE, "lean scan kernel could not lay out its shared memory (window base %% 64 KiB); "
                                            "set TLS_FORCE_GENERAL=1");
-            if (tr.on) fprintf(stderr, " lean_tiles=%zu/%zu redo_rows=%u", s.fastTiles.size(), s.tiles.size(),
+            if (tr.on) fprintf(stderr, " row_tiles=%zu lean_tiles=%zu/%zu redo_rows=%u", s.rowTiles.size(), s.fastTiles.size(), s.tiles.size(),
                                static_cast<uint32_t>(hs[4]));
             const uint32_t ovUsed = static_cast<uint32_t>(hs[0]);
             s.nMatches = hs[1]; s.nCanAll = hs[2]; s.nNctAll = hs[3];

@@ -29,6 +29,17 @@ constexpr int kFastPackedWords = kRowBytes / 16 + 4;   // per-warp 2-bit copy of
 constexpr int kFastFlagBytes = 16384;             // one direct table, pattern length <= 7
 constexpr uint32_t kFastMinWindow = 512;          // <= 98 windows per tile, <= 1 window end per span
 
+// ---- geometry of the window-row kernel (scan_rows.cu): a row is one window, a lane owns 32 bases ----
+constexpr int kRowThreads = 1024;
+constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kRowSpan = 32;                      // bases per lane
+constexpr int kRowStage = 32 * kRowSpan;          // bytes of one staging buffer (1024)
+constexpr int kRowMaxLen = kRowStage - 15 - 7;    // longest window: alignment skew <= 15, 7 bases of k-mer tail
+constexpr uint32_t kRowMinWindow = 600;           // below this more than 40 % of the lanes would idle
+constexpr uint32_t kRowMinWindows = 8;            // shorter contigs go to the general kernel
+constexpr int kRowQueueCap = 256;                 // per-warp match queue (u16 entries), 8 lanes' worth
+constexpr int kRowsPerUnit = 8;                   // consecutive windows one warp takes at a time
+
 // A maximal stretch of one item inside which matches must lie entirely
 // (genome mode: the whole contig; tips mode: [0,T) and [n-T,n); reads: the whole read).
 struct DevRegion {
@@ -60,6 +71,17 @@ struct DevFastTile {
     uint32_t winDelta;     // item's first window - firstWin (mod 2^32): slot = rel / window + winDelta
     uint32_t termMixed;    // 1: matches of this tile may be "terminal" (src/teloscope.cpp:451-459)
     uint32_t pad;
+};
+
+// 32 consecutive windows (rows) of one contig for the window-row kernel; row r is window firstWin + r,
+// starts at item position relBase + r * windowSize and at buffer offset bufStart + r * windowSize.
+struct DevRowTile {        // 32 bytes, read as two uint4
+    uint64_t bufStart;
+    uint32_t tile;         // index in the batch's tile table (slot addressing)
+    uint32_t relBase;      // multiple of windowSize
+    uint32_t item, itemLen;
+    uint32_t firstWin;
+    uint32_t nRows;        // 1..32
 };
 
 struct DevMatch {          // 8 bytes, ordered by (item, pos, len)
@@ -160,6 +182,28 @@ struct FastParams {
     uint32_t *redoList;            // rows with a non-ACGT byte: tile << 5 | row, redone by the general kernel
     unsigned int *redoCount;
     uint32_t redoCap;
+    DevConfig cfg;
+};
+
+struct RowParams {
+    const uint8_t *seq;
+    const DevRowTile *tiles;
+    uint32_t nTiles;
+    const uint8_t *index8;         // 65536-byte stage-1 table
+    const uint8_t *flagTab;        // direct table of the single length class (4^len bytes)
+    uint32_t flagTabBytes;         // rounded up to 16
+    uint32_t patLen;
+    DevMatch *slots;
+    uint32_t slotCap;
+    uint32_t *slotCounts, *slotOv, *slotCan, *slotNct;
+    uint32_t *tileTot;             // [3][nTilesAll]
+    uint32_t nTilesAll;
+    DevMatch *ovArena;
+    uint32_t ovCap, ovChunk;
+    unsigned int *ovCursor;
+    uint32_t *windows;             // [nWindows][8]
+    DevItemCounts *itemCounts;
+    unsigned int *status;          // set to 1 when the shared memory layout assumption fails
     DevConfig cfg;
 };
 

@@ -15,6 +15,11 @@ size_t fastSmemBytes();
 bool fastConfigOk(const DevConfig &c);
 cudaError_t launchFastScan(const FastParams &p, int grid, cudaStream_t stream);
 
+// window-row kernel (scan_rows.cu): genome mode, one direct pattern length, kRowMinWindow <= window <= kRowMaxLen
+size_t rowSmemBytes();
+bool rowConfigOk(const DevConfig &c);
+cudaError_t launchRowScan(const RowParams &p, int grid, cudaStream_t stream);
+
 // exclusive scans of the per-tile totals (3 arrays: tileBase[k][nTiles] = total), then ordered copy
 // hostOut: 5 u64 in mapped pinned host memory: ovCursor, totals[3], redo count | status << 32
 cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, const unsigned int *ovCursor,

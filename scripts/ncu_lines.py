@@ -64,6 +64,9 @@ def main():
     ap.add_argument("--top", type=int, default=60)
     ap.add_argument("--cubin")
     ap.add_argument("--lib", default=str(ROOT / "teloscope_b200" / "libteloscope_b200.so"))
+    ap.add_argument("--by-line", action="store_true", help="list every line of the kernel's own file in source order")
+    ap.add_argument("--per", type=float, default=0, help="divide executed instructions by this (e.g. rows processed)")
+    ap.add_argument("--sass", action="store_true", help="dump the SASS with executed counts and line numbers")
     args = ap.parse_args()
     name, rows = sass_rows(args.report, args.kernel)
     cubins = [args.cubin] if args.cubin else []
@@ -102,6 +105,17 @@ def main():
         if f not in src_cache:
             src_cache[f] = f.read_text().splitlines()
         return src_cache[f][l[1] - 1].strip()[:100] if l[1] - 1 < len(src_cache[f]) else ""
+    if args.sass:
+        for r, l in zip(rows, lines):
+            n = r["inst"] / args.per if args.per else r["inst"]
+            print(f"{n:10.2f} {r['samples']:6.0f}  {(l[0] + ':' + str(l[1])) if l else '?':28s} {r['sass']}")
+        return
+    if args.by_line:
+        print(f"{'inst':>8} {'samp%':>6}  line")
+        for l, (i, sm, c) in sorted(per.items(), key=lambda kv: (kv[0][0] if kv[0] else '', kv[0][1] if kv[0] else 0)):
+            n = i / args.per if args.per else i
+            print(f"{n:8.2f} {100*sm/tot_s:6.2f}  {l[0] if l else '?'}:{l[1] if l else 0}  {src(l)}")
+        return
     print(f"{'inst%':>6} {'samp%':>6} {'smem-excess':>11}  line")
     for l, (i, s, c) in sorted(per.items(), key=lambda kv: -kv[1][0])[:args.top]:
         print(f"{100*i/tot_i:6.2f} {100*s/tot_s:6.2f} {c:11.0f}  {l[0] if l else '?'}:{l[1] if l else 0}  {src(l)}")

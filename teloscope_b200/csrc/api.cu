@@ -106,15 +106,16 @@ struct Slot {
     std::vector<DevRegion> regions;
     std::vector<DevTile> tiles;
     std::vector<DevFastTile> fastTiles;      // tiles for the lean kernel
-    std::vector<DevRowTile> rowTiles;        // tiles for the window-row kernel
+    std::vector<DevRowUnit> rowUnits;        // work units of the window-row kernel
+    size_t nRowTiles = 0;
     std::vector<uint8_t> tileIsRow;          // per tile: 1 = made of whole windows for the window-row kernel
     std::vector<uint32_t> generalTiles;      // indices of the tiles the general kernel takes entirely
     const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
     HostBuf hSeq, hMeta, hMeta2;              // pinned staging
-    DevBuf dRowTiles, dFastTiles, dGeneralTiles, dRedo, dSlotCan, dSlotNct, dTileTot, dCanIdx, dNctIdx, dRunStarts;
+    DevBuf dRowTiles, dFastTiles, dGeneralTiles, dRedo, dTileTot, dCanIdx, dNctIdx, dRunStarts;
     uint64_t nCanAll = 0, nNctAll = 0;       // canonical / terminal non-canonical records of the batch
-    DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotCounts,
-        dSlotOv, dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
+    DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotMeta,
+        dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
     uint32_t ovCap = 0;
     // device counters block: [0] ovCursor(u32) [16] blockCount(u32) [24] selTotals(2 x u64)
     HostBuf hScan, hCounters, hWindows, hItemCounts, hBlocks, hPass, hSelCan, hSelNon;
@@ -350,11 +351,11 @@ void tls_destroy(tls_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (Slot &s : ctx->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        for (DevBuf *b : {&s.dRowTiles, &s.dFastTiles, &s.dGeneralTiles, &s.dRedo, &s.dSlotCan, &s.dSlotNct, &s.dTileTot, &s.dCanIdx,
+        for (DevBuf *b : {&s.dRowTiles, &s.dFastTiles, &s.dGeneralTiles, &s.dRedo, &s.dTileTot, &s.dCanIdx,
                           &s.dNctIdx, &s.dRunStarts})
             b->release();
         for (DevBuf *b : {&s.dAbsPos, &s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
-                          &s.dMatches, &s.dSlots, &s.dSlotCounts, &s.dSlotOv, &s.dOvArena, &s.dTileBase, &s.dCounters,
+                          &s.dMatches, &s.dSlots, &s.dSlotMeta, &s.dOvArena, &s.dTileBase, &s.dCounters,
                           &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch, &s.dSelCan, &s.dSelNon})
             b->release();
         for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hMeta2, &s.hScan, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
@@ -385,8 +386,7 @@ GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
     g.windows = s.dWindows.as<uint32_t>(); g.itemCounts = s.dItemCounts.as<DevItemCounts>();
     g.cfg = ctx->dcfg; g.cfg.mode = s.mode;
     g.slots = s.dSlots.as<DevMatch>(); g.slotCap = ctx->slotCap;
-    g.slotCounts = s.dSlotCounts.as<uint32_t>(); g.slotOv = s.dSlotOv.as<uint32_t>();
-    g.slotCan = s.dSlotCan.as<uint32_t>(); g.slotNct = s.dSlotNct.as<uint32_t>();
+    g.slotMeta = s.dSlotMeta.as<uint4>();
     g.ovArena = s.dOvArena.as<DevMatch>(); g.ovCap = s.ovCap;
     g.nTiles = static_cast<uint32_t>(s.tiles.size());
     g.tileBase = s.dTileBase.as<unsigned long long>();
@@ -402,18 +402,13 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
     const uint32_t nTiles = static_cast<uint32_t>(s.tiles.size());
     const size_t nSlots = static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * kTileRows;
     TLS_CUDA(s.dSlots.reserve(nSlots * ctx->slotCap * sizeof(DevMatch)));
-    TLS_CUDA(s.dSlotCounts.reserve(nSlots * 4));
-    TLS_CUDA(s.dSlotOv.reserve(nSlots * 4));
-    TLS_CUDA(s.dSlotCan.reserve(nSlots * 4));
-    TLS_CUDA(s.dSlotNct.reserve(nSlots * 4));
+    TLS_CUDA(s.dSlotMeta.reserve(nSlots * 16));
     TLS_CUDA(s.dTileTot.reserve(static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * 12));
     TLS_CUDA(s.dTileBase.reserve((static_cast<size_t>(nTiles) + 1) * 24));
     TLS_CUDA(cudaMemsetAsync(s.dTileTot.p, 0, static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * 12, s.stream));
-    if (!s.rowTiles.empty()) {
+    if (!s.rowUnits.empty()) {
         // the last tile of a contig has fewer than 32 windows: its other row slots must read as empty
-        TLS_CUDA(cudaMemsetAsync(s.dSlotCounts.p, 0, nSlots * 4, s.stream));
-        TLS_CUDA(cudaMemsetAsync(s.dSlotCan.p, 0, nSlots * 4, s.stream));
-        TLS_CUDA(cudaMemsetAsync(s.dSlotNct.p, 0, nSlots * 4, s.stream));
+        TLS_CUDA(cudaMemsetAsync(s.dSlotMeta.p, 0, nSlots * 16, s.stream));
     }
     s.ovCap = std::max<uint32_t>(s.ovCap, 256u * ctx->ovChunk);
     TLS_CUDA(s.dOvArena.reserve(static_cast<size_t>(s.ovCap) * sizeof(DevMatch)));
@@ -432,27 +427,25 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         if (s.mode != TLS_MODE_GENOME) cfg.countAcgt = 0;
         unsigned int *redo = s.dRedo.as<unsigned int>();
         TLS_CUDA(cudaEventRecord(s.evScan0, s.stream));
-        const uint32_t nRow = static_cast<uint32_t>(s.rowTiles.size());
+        const uint32_t nRow = static_cast<uint32_t>(s.rowUnits.size());
         if (nRow) {
             RowParams f{};
             f.seq = s.devSeq;
-            f.tiles = s.dRowTiles.as<DevRowTile>(); f.nTiles = nRow;
+            f.units = s.dRowTiles.as<DevRowUnit>(); f.nUnits = nRow;
             f.index8 = ctx->dIndex.as<uint8_t>();
             f.flagTab = ctx->dFlags.as<uint8_t>() + cfg.cls[0].flagOffset;
             f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
             f.patLen = cfg.cls[0].len;
             f.slots = s.dSlots.as<DevMatch>(); f.slotCap = ctx->slotCap;
-            f.slotCounts = s.dSlotCounts.as<uint32_t>(); f.slotOv = s.dSlotOv.as<uint32_t>();
-            f.slotCan = s.dSlotCan.as<uint32_t>(); f.slotNct = s.dSlotNct.as<uint32_t>();
+            f.slotMeta = s.dSlotMeta.as<uint4>();
             f.tileTot = s.dTileTot.as<uint32_t>(); f.nTilesAll = nTiles;
             f.ovArena = s.dOvArena.as<DevMatch>(); f.ovCap = s.ovCap; f.ovChunk = ctx->ovChunk;
             f.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
-            f.windows = s.dWindows.as<uint32_t>();
+            f.windows = s.dWindows.as<uint4>();
             f.itemCounts = s.dItemCounts.as<DevItemCounts>();
             f.status = redo + 1;
             f.cfg = cfg;
-            const uint32_t nUnits = nRow * (kTileRows / kRowsPerUnit);
-            const int grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (nUnits + kRowWarps - 1) / kRowWarps));
+            const int grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (nRow + kRowWarps - 1) / kRowWarps));
             TLS_CUDA(launchRowScan(f, grid, s.stream));
             s.launches++;
         }
@@ -465,8 +458,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
             f.patLen = cfg.cls[0].len;
             f.slots = s.dSlots.as<DevMatch>(); f.slotCap = ctx->slotCap;
-            f.slotCounts = s.dSlotCounts.as<uint32_t>(); f.slotOv = s.dSlotOv.as<uint32_t>();
-            f.slotCan = s.dSlotCan.as<uint32_t>(); f.slotNct = s.dSlotNct.as<uint32_t>();
+            f.slotMeta = s.dSlotMeta.as<uint4>();
             f.tileTot = s.dTileTot.as<uint32_t>(); f.nTilesAll = nTiles;
             f.ovArena = s.dOvArena.as<DevMatch>(); f.ovCap = s.ovCap; f.ovChunk = ctx->ovChunk;
             f.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
@@ -493,8 +485,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             p.sortedKeys = ctx->dKeys.as<uint64_t>();
             p.sortedFlags = ctx->dKeyFlags.as<uint8_t>();
             p.slots = s.dSlots.as<DevMatch>(); p.slotCap = ctx->slotCap;
-            p.slotCounts = s.dSlotCounts.as<uint32_t>(); p.slotOv = s.dSlotOv.as<uint32_t>();
-            p.slotCan = s.dSlotCan.as<uint32_t>(); p.slotNct = s.dSlotNct.as<uint32_t>();
+            p.slotMeta = s.dSlotMeta.as<uint4>();
             p.tileTot = s.dTileTot.as<uint32_t>();
             p.ovArena = s.dOvArena.as<DevMatch>(); p.ovCap = s.ovCap; p.ovChunk = ctx->ovChunk;
             p.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
@@ -614,7 +605,7 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     // tiles of 32 whole windows (one window per tile row).  Everything else: runs of (nearly) adjacent
     // regions are cut into pieces of <= kTileMaxLen bytes; of those the lean kernel takes the tiles that
     // lie inside one region, the general kernel the rest.
-    s.tiles.clear(); s.tileIsRow.clear(); s.rowTiles.clear();
+    s.tiles.clear(); s.tileIsRow.clear(); s.rowUnits.clear(); s.nRowTiles = 0;
     s.tiles.reserve(static_cast<size_t>(s.nBases / 32000) + s.regions.size() + 1);
     {
         DevConfig probe = ctx->dcfg;
@@ -629,20 +620,26 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
             if (rowOk && reg.len >= rowMinLen) {
                 const uint32_t nWinReg = (reg.len + W - 1) / W;
                 for (uint32_t w0 = 0; w0 < nWinReg; w0 += kTileRows) {
-                    DevRowTile rt{};
-                    rt.nRows = std::min<uint32_t>(kTileRows, nWinReg - w0);
-                    rt.relBase = reg.relStart + w0 * W;
-                    rt.bufStart = reg.bufStart + static_cast<uint64_t>(w0) * W;
-                    rt.tile = static_cast<uint32_t>(s.tiles.size());
-                    rt.item = reg.item; rt.itemLen = reg.itemLen;
-                    rt.firstWin = reg.winBase + w0;
-                    s.rowTiles.push_back(rt);
+                    const uint32_t nRows = std::min<uint32_t>(kTileRows, nWinReg - w0);
+                    const uint32_t tile = static_cast<uint32_t>(s.tiles.size());
+                    for (uint32_t k = 0; k < nRows; k += kRowsPerUnit) {
+                        DevRowUnit u{};
+                        u.bufStart = reg.bufStart + static_cast<uint64_t>(w0 + k) * W;
+                        u.rel = reg.relStart + (w0 + k) * W;
+                        u.itemLen = reg.itemLen;
+                        u.firstWin = reg.winBase + w0 + k;
+                        u.slot0 = tile * kTileRows + k;
+                        u.nRows = std::min<uint32_t>(kRowsPerUnit, nRows - k);
+                        u.item = reg.item;
+                        s.rowUnits.push_back(u);
+                    }
                     DevTile t{};
-                    t.bufStart = rt.bufStart;
-                    t.len = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(rt.nRows) * W, reg.len - static_cast<uint64_t>(w0) * W));
+                    t.bufStart = reg.bufStart + static_cast<uint64_t>(w0) * W;
+                    t.len = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(nRows) * W, reg.len - static_cast<uint64_t>(w0) * W));
                     t.firstRegion = static_cast<uint32_t>(r);
                     s.tiles.push_back(t);
                     s.tileIsRow.push_back(1);
+                    ++s.nRowTiles;
                 }
                 ++r;
                 continue;
@@ -669,7 +666,7 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
 
     // ---- which kernel takes the other tiles: the lean kernel wants tiles inside one region -------------
     s.fastTiles.clear(); s.generalTiles.clear();
-    s.fastTiles.reserve(s.tiles.size() - s.rowTiles.size());
+    s.fastTiles.reserve(s.tiles.size() - s.nRowTiles);
     {
         DevConfig probe = ctx->dcfg;
         probe.mode = b->mode;
@@ -698,10 +695,10 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     // ---- upload metadata ------------------------------------------------------------------------
     {
         const size_t bFast = s.fastTiles.size() * sizeof(DevFastTile), bGen = s.generalTiles.size() * 4,
-                     bRow = s.rowTiles.size() * sizeof(DevRowTile);
+                     bRow = s.rowUnits.size() * sizeof(DevRowUnit);
         TLS_CUDA(s.hMeta2.reserve(bFast + bGen + bRow + 64));
         uint8_t *h2 = s.hMeta2.as<uint8_t>();
-        if (bRow) std::memcpy(h2, s.rowTiles.data(), bRow);
+        if (bRow) std::memcpy(h2, s.rowUnits.data(), bRow);
         if (bFast) std::memcpy(h2 + bRow, s.fastTiles.data(), bFast);
         if (bGen) std::memcpy(h2 + bRow + bFast, s.generalTiles.data(), bGen);
         TLS_CUDA(s.dRowTiles.reserve(std::max<size_t>(bRow, 16)));
@@ -762,7 +759,7 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             if ((hs[4] >> 32) != 0)
                 return fail(TLS_ERR_STATE, "lean scan kernel could not lay out its shared memory (window base %% 64 KiB); "
                                            "set TLS_FORCE_GENERAL=1");
-            if (tr.on) fprintf(stderr, " row_tiles=%zu lean_tiles=%zu/%zu redo_rows=%u", s.rowTiles.size(), s.fastTiles.size(), s.tiles.size(),
+            if (tr.on) fprintf(stderr, " row_tiles=%zu lean_tiles=%zu/%zu redo_rows=%u", s.nRowTiles, s.fastTiles.size(), s.tiles.size(),
                                static_cast<uint32_t>(hs[4]));
             const uint32_t ovUsed = static_cast<uint32_t>(hs[0]);
             s.nMatches = hs[1]; s.nCanAll = hs[2]; s.nNctAll = hs[3];

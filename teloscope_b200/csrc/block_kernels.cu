@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
     __shared__ uint32_t sOff[3][kTileRows + 1];
     if (warp < 3) {
         // exclusive prefix over the 32 row slots of this tile (warp k handles array k)
-        const uint32_t *src = warp == 0 ? g.slotCounts : warp == 1 ? g.slotCan : g.slotNct;
-        const uint32_t v = src[static_cast<size_t>(tile) * kTileRows + lane];
+        const uint4 meta = g.slotMeta[static_cast<size_t>(tile) * kTileRows + lane];
+        const uint32_t v = warp == 0 ? meta.x : warp == 1 ? meta.z : meta.w;
         uint32_t incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
         if (cnt == 0) continue;
         const size_t slotIdx = static_cast<size_t>(tile) * kTileRows + s;
         const uint2 *src = reinterpret_cast<const uint2 *>(g.slots) + slotIdx * g.slotCap;
-        const unsigned long long ov = g.slotOv[slotIdx];
+        const unsigned long long ov = g.slotMeta[slotIdx].y;
         const unsigned long long o = base + sOff[0][s];
         unsigned long long oc = baseCan + sOff[1][s], on = baseNct + sOff[2][s];
         const bool anySel = sOff[1][s + 1] != sOff[1][s] || sOff[2][s + 1] != sOff[2][s];     // warp-uniform

@@ -3,6 +3,8 @@
 
 #include <cstdint>
 
+#include <vector_types.h>
+
 namespace tls {
 
 // ---- geometry of the fused scan kernel ------------------------------------------------------
@@ -73,15 +75,17 @@ struct DevFastTile {
     uint32_t pad;
 };
 
-// 32 consecutive windows (rows) of one contig for the window-row kernel; row r is window firstWin + r,
-// starts at item position relBase + r * windowSize and at buffer offset bufStart + r * windowSize.
-struct DevRowTile {        // 32 bytes, read as two uint4
+// Up to kRowsPerUnit consecutive windows of one contig: the unit of work of the window-row kernel.
+// Window k of the unit is global window firstWin + k, row slot slot0 + k, starts at item position
+// rel + k * windowSize and at buffer offset bufStart + k * windowSize.
+struct DevRowUnit {        // 32 bytes, read as two uint4
     uint64_t bufStart;
-    uint32_t tile;         // index in the batch's tile table (slot addressing)
-    uint32_t relBase;      // multiple of windowSize
-    uint32_t item, itemLen;
+    uint32_t rel;          // multiple of windowSize
+    uint32_t itemLen;
     uint32_t firstWin;
-    uint32_t nRows;        // 1..32
+    uint32_t slot0;        // tile * kTileRows + row of the first window
+    uint32_t nRows;        // 1..kRowsPerUnit
+    uint32_t item;
 };
 
 struct DevMatch {          // 8 bytes, ordered by (item, pos, len)
@@ -149,9 +153,8 @@ struct ScanParams {
     const unsigned int *redoCount;
     DevMatch *slots;               // [nTiles * kTileRows][slotCap]: one slot per tile row
     uint32_t slotCap;
-    uint32_t *slotCounts;          // [nTiles * kTileRows] records produced
-    uint32_t *slotOv;              // [nTiles * kTileRows] overflow chunk base or 0xFFFFFFFF
-    uint32_t *slotCan, *slotNct;   // [nTiles * kTileRows] canonical / terminal non-canonical records among them
+    uint4 *slotMeta;               // [nTiles * kTileRows] x = records produced, y = overflow chunk base or 0xFFFFFFFF,
+                                   // z / w = canonical / terminal non-canonical records among them
     uint32_t *tileTot;             // [3][nTiles] per-tile totals (all, canonical, terminal non-canonical), atomics
     DevMatch *ovArena;
     uint32_t ovCap, ovChunk;
@@ -171,7 +174,7 @@ struct FastParams {
     uint32_t patLen;
     DevMatch *slots;
     uint32_t slotCap;
-    uint32_t *slotCounts, *slotOv, *slotCan, *slotNct;
+    uint4 *slotMeta;               // per row slot: count, overflow base, canonical, terminal non-canonical
     uint32_t *tileTot;             // [3][nTilesAll]
     uint32_t nTilesAll;            // tiles of the batch (lean + general)
     DevMatch *ovArena;
@@ -187,21 +190,21 @@ struct FastParams {
 
 struct RowParams {
     const uint8_t *seq;
-    const DevRowTile *tiles;
-    uint32_t nTiles;
+    const DevRowUnit *units;
+    uint32_t nUnits;
     const uint8_t *index8;         // 65536-byte stage-1 table
     const uint8_t *flagTab;        // direct table of the single length class (4^len bytes)
     uint32_t flagTabBytes;         // rounded up to 16
     uint32_t patLen;
     DevMatch *slots;
     uint32_t slotCap;
-    uint32_t *slotCounts, *slotOv, *slotCan, *slotNct;
+    uint4 *slotMeta;               // per row slot: count, overflow base, canonical, terminal non-canonical
     uint32_t *tileTot;             // [3][nTilesAll]
     uint32_t nTilesAll;
     DevMatch *ovArena;
     uint32_t ovCap, ovChunk;
     unsigned int *ovCursor;
-    uint32_t *windows;             // [nWindows][8]
+    uint4 *windows;                // [nWindows][2]: A, C, G, T | canonical, non-canonical, forward, reverse covered bp
     DevItemCounts *itemCounts;
     unsigned int *status;          // set to 1 when the shared memory layout assumption fails
     DevConfig cfg;
@@ -216,7 +219,7 @@ struct GatherParams {
     DevConfig cfg;
     const DevMatch *slots;
     uint32_t slotCap;
-    const uint32_t *slotCounts, *slotOv, *slotCan, *slotNct;
+    const uint4 *slotMeta;
     const DevMatch *ovArena;
     uint32_t ovCap;
     uint32_t nTiles;

@@ -459,10 +459,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
             }
         }
         if (lane == 0) {
-            p.slotCounts[slotIdx] = wMatches;
-            p.slotOv[slotIdx] = ovBase;
-            p.slotCan[slotIdx] = rowCan;
-            p.slotNct[slotIdx] = rowNct;
+            p.slotMeta[slotIdx] = make_uint4(wMatches, ovBase, rowCan, rowNct);
             if (wMatches) atomicAdd(&sTot[buf * 4 + 0], wMatches);
             if (rowCan) atomicAdd(&sTot[buf * 4 + 1], rowCan);
             if (rowNct) atomicAdd(&sTot[buf * 4 + 2], rowNct);

@@ -592,10 +592,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                 }
             }
             if (lane == 0) {
-                p.slotCounts[slotIdx] = wMatches;
-                p.slotOv[slotIdx] = ovBase;
-                p.slotCan[slotIdx] = rowCan;
-                p.slotNct[slotIdx] = rowNct;
+                p.slotMeta[slotIdx] = make_uint4(wMatches, ovBase, rowCan, rowNct);
                 if (wMatches) atomicAdd(p.tileTot + tileIdx, wMatches);
                 if (rowCan) atomicAdd(p.tileTot + static_cast<size_t>(p.nTiles) + tileIdx, rowCan);
                 if (rowNct) atomicAdd(p.tileTot + 2 * static_cast<size_t>(p.nTiles) + tileIdx, rowNct);

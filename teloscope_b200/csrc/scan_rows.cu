@@ -71,13 +71,20 @@ __device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {      // the tables ne
     asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ uint32_t shlClamp(uint32_t v, uint32_t n) {   // v << n, 0 for n >= 32 (PTX semantics)
-    uint32_t r;
-    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
-    return r;
+__device__ __forceinline__ uint32_t ldsU16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
-__device__ __forceinline__ uint32_t maskBelow(int n) {   // bits [0, n), n in [0, 32]
-    return shlClamp(1u, static_cast<uint32_t>(n)) - 1u;
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t bmskClamp(int n) {   // bits [0, min(n, 32)), n >= 0 (BMSK)
+    uint32_t r;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(0u), "r"(static_cast<uint32_t>(n)));
+    return r;
 }
 __device__ __forceinline__ int clamp32(int v) { return min(max(v, 0), 32); }
 
@@ -153,20 +160,20 @@ __device__ __noinline__ uint32_t slowRow(const uint8_t *row, int nValid, uint32_
 template <int NPOS, bool COUNT>
 __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const DevConfig &cfg = p.cfg;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if ((smemAddr(smem) & 0xFFFFu) != kWindowBase) {       // the table must sit on a 64 KiB boundary of the window
         if (tid == 0 && blockIdx.x == 0) atomicExch(p.status, 1u);
         return;
     }
-    const uint32_t idxBase = smemAddr(smem) + kIdxOff;          // low 16 bits are zero
-    const uint32_t flagBase = smemAddr(smem) + kFlagOff;
-    uint32_t *sPk = reinterpret_cast<uint32_t *>(smem + kPkOff) + warp * kPkWords;
-    uint16_t *sQueue = reinterpret_cast<uint16_t *>(smem + kQueueOff) + warp * kRowQueueCap;
-    uint8_t *sStage = smem + kStageOff + warp * 2 * kRowStage;
-    const uint32_t stageAddr = smemAddr(sStage);
-    const uint32_t barAddr = smemAddr(smem + kBarOff) + warp * 16;
+    // shared-window addresses (the dynamic block starts at kWindowBase of this CTA's window)
+    const uint32_t winBase = smemAddr(smem) - kWindowBase;      // 0 unless the CTA's window is offset (clusters)
+    const uint32_t idxBase = winBase + kWindowBase + kIdxOff;   // low 16 bits are zero
+    const uint32_t flagBase = winBase + kWindowBase + kFlagOff;
+    const uint32_t pkAddr = winBase + kWindowBase + kPkOff + warp * (kPkWords * 4);
+    const uint32_t qAddr = winBase + kWindowBase + kQueueOff + warp * (kRowQueueCap * 2);
+    const uint32_t stageAddr = winBase + kWindowBase + kStageOff + warp * (2 * kRowStage);
+    const uint32_t barAddr = winBase + kWindowBase + kBarOff + warp * 16;
 
     // ---- one-time setup ---------------------------------------------------------------------------
     for (int i = tid; i < 65536 / 16; i += kRowThreads)
@@ -174,7 +181,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     for (uint32_t i = tid; i < p.flagTabBytes / 16; i += kRowThreads)
         reinterpret_cast<uint4 *>(smem + kFlagOff)[i] = reinterpret_cast<const uint4 *>(p.flagTab)[i];
     for (int i = lane; i < 2 * kRowStage / 16; i += 32)        // bytes a short row leaves untouched must be harmless
-        reinterpret_cast<uint4 *>(sStage)[i] = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+        reinterpret_cast<uint4 *>(smem + kStageOff + warp * (2 * kRowStage))[i] =
+            make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
     if (lane == 0) {
         mbarInit(barAddr, 1);
         mbarInit(barAddr + 8, 1);
@@ -182,71 +190,63 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     }
     __syncthreads();
 
-    const uint32_t L = p.patLen, W = cfg.windowSize, T = cfg.terminalLimit;
+    const uint32_t L = p.patLen, W = p.cfg.windowSize, T = p.cfg.terminalLimit;
     const uint32_t keyMask = (1u << (2 * L)) - 1u;
+    const uint32_t recHi = L | (static_cast<uint32_t>(kRegionAccounted) << 24);    // DevMatch {pos, len:16, flags:8, region:8}
     const uint32_t totalWarps = gridDim.x * kRowWarps;
-    const uint32_t nUnits = p.nTiles * (kTileRows / kRowsPerUnit);
-    const uint8_t *seqBase = p.seq;
+    const uint32_t nUnits = p.nUnits;
+    const uint32_t laneOff = lane * kRowSpan;
 
-    // stage row `r` of tile `d` into buffer `buf` (lane 0 only)
-    auto issueRow = [&](const DevRowTile &d, uint32_t r, int buf) {
-        const uint64_t g = d.bufStart + static_cast<uint64_t>(r) * W;             // first base of the row
-        const uint32_t rel = d.relBase + r * W;
-        const uint32_t rowLen = min(W, d.itemLen - rel);
-        const uint64_t addr = reinterpret_cast<uint64_t>(seqBase) + g;
+    // stage the row that starts at global address `addr` into buffer `b` (one lane)
+    auto issueRow = [&](uint64_t addr, uint32_t rowLen, uint32_t b) {
         const uint32_t skew = static_cast<uint32_t>(addr) & 15u;
         const uint32_t bytes = (skew + rowLen + 15u) & ~15u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbarExpectTx(barAddr + buf * 8, bytes);
-        bulkLoad(stageAddr + buf * kRowStage, reinterpret_cast<const void *>(addr - skew), bytes, barAddr + buf * 8);
+        mbarExpectTx(barAddr + b * 8, bytes);
+        bulkLoad(stageAddr + b * kRowStage, reinterpret_cast<const void *>(addr - skew), bytes, barAddr + b * 8);
     };
-    auto loadTile = [&](uint32_t u) {
-        DevRowTile d;
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.tiles + (u / (kTileRows / kRowsPerUnit)));
-        const uint4 a = __ldg(src), b = __ldg(src + 1);
-        d.bufStart = static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32);
-        d.tile = a.z; d.relBase = a.w; d.item = b.x; d.itemLen = b.y; d.firstWin = b.z; d.nRows = b.w;
-        return d;
+    auto loadUnit = [&](uint32_t u, uint4 &a, uint4 &b) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.units + u);
+        a = __ldg(src); b = __ldg(src + 1);
     };
 
-    uint32_t phase = 0;                                        // bit b: parity to wait for on buffer b
-    int buf = 0;
+    uint32_t phase = 0, buf = 0;                               // phase bit b: parity to wait for on buffer b
     uint32_t u = blockIdx.x * kRowWarps + warp;
-    // skip units that lie past the last row of their tile
-    DevRowTile d{};
-    uint32_t r0 = 0, r1 = 0;
-    auto settle = [&]() {                                      // find the next non-empty unit at or after u
-        while (u < nUnits) {
-            d = loadTile(u);
-            r0 = (u % (kTileRows / kRowsPerUnit)) * kRowsPerUnit;
-            r1 = min(r0 + kRowsPerUnit, d.nRows);
-            if (r0 < r1) return;
-            u += totalWarps;
-        }
-    };
-    settle();
-    if (u < nUnits && lane == 0) issueRow(d, r0, 0);
+    if (u >= nUnits) return;
+    if (lane == 0) {
+        uint4 a, b;
+        loadUnit(u, a, b);
+        issueRow(reinterpret_cast<uint64_t>(p.seq) + (static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32)),
+                 min(W, a.w - a.z), 0);
+    }
 
-    while (u < nUnits) {
-        const DevRowTile cur = d;
-        const uint32_t rBeg = r0, rEnd = r1;
-        // the unit after this one (descriptor loaded now, used for the look-ahead of the last row)
-        u += totalWarps;
-        settle();
+    for (; u < nUnits; u += totalWarps) {
+        uint4 da, db;
+        loadUnit(u, da, db);
+        uint64_t rowAddr = reinterpret_cast<uint64_t>(p.seq) + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32));
+        uint32_t rel = da.z;                                   // item position of the window start
+        uint32_t remaining = da.w - da.z;                      // bases from the window start to the end of the contig
+        const uint32_t termEnd = da.w > T ? da.w - T : 0u;     // "terminal": pos <= T || pos >= n - T (src/teloscope.cpp:403-406,451-459)
+        uint32_t win = db.x, slotIdx = db.y;
+        const uint32_t nRows = db.z;
         uint32_t uAll = 0, uCan = 0, uFwd = 0, uNct = 0;
 
-        for (uint32_t r = rBeg; r < rEnd; ++r) {
+#pragma unroll 1
+        for (uint32_t r = 0; r < nRows; ++r) {
+            const uint32_t rowLen = min(W, remaining);
             // ---- look-ahead: stage the next row of this warp ----------------------------------------------
-            __syncwarp();                                       // every lane is done with the other buffer
+            __syncwarp();                                       // every lane is done with the other buffer, the queue and the 2-bit copy
             if (lane == 0) {
-                if (r + 1 < rEnd) issueRow(cur, r + 1, buf ^ 1);
-                else if (u < nUnits) issueRow(d, r0, buf ^ 1);
+                if (r + 1 < nRows) issueRow(rowAddr + W, min(W, remaining - W), buf ^ 1u);
+                else if (u + totalWarps < nUnits) {
+                    uint4 a, b;
+                    loadUnit(u + totalWarps, a, b);
+                    issueRow(reinterpret_cast<uint64_t>(p.seq) + (static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32)),
+                             min(W, a.w - a.z), buf ^ 1u);
+                }
             }
-            const uint32_t rel = cur.relBase + r * W;                      // item position of the window start
-            const uint32_t rowLen = min(W, cur.itemLen - rel);
-            const uint32_t skew = static_cast<uint32_t>(reinterpret_cast<uint64_t>(seqBase) + cur.bufStart +
-                                                        static_cast<uint64_t>(r) * W) & 15u;
-            const uint8_t *stage = sStage + buf * kRowStage;
+            const uint32_t skew = static_cast<uint32_t>(rowAddr) & 15u;
+            const uint32_t stage = stageAddr + buf * kRowStage;
             mbarWait(barAddr + buf * 8, (phase >> buf) & 1u);
             phase ^= 1u << buf;
 
@@ -254,11 +254,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
             uint32_t X0, X1, X2;
             bool bad;
             {
-                const uint4 *src = reinterpret_cast<const uint4 *>(stage + lane * kRowSpan);
-                const uint4 c0 = src[0], c1 = src[1];
+                uint4 c0, c1;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0.x), "=r"(c0.y), "=r"(c0.z), "=r"(c0.w) : "r"(stage + laneOff));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(c1.x), "=r"(c1.y), "=r"(c1.z), "=r"(c1.w) : "r"(stage + laneOff));
                 ValidAcc va;
                 const uint32_t P0 = pack16v(c0, va), P1 = pack16v(c1, va);
-                bad = va.bad() != 0 && static_cast<uint32_t>(lane * kRowSpan) < rowLen + skew;
+                bad = va.bad() != 0 && laneOff < rowLen + skew;
                 uint32_t P2 = __shfl_down_sync(0xFFFFFFFFu, P0, 1), P3 = __shfl_down_sync(0xFFFFFFFFu, P1, 1);
                 if (lane == 31) { P2 = 0; P3 = 0; }
                 const uint32_t sh = 2u * skew;
@@ -266,11 +267,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 X1 = __funnelshift_r(P1, P2, sh);
                 X2 = __funnelshift_r(P2, P3, sh);
             }
-            const int nValid = clamp32(static_cast<int>(rowLen) - lane * kRowSpan);       // row bases of this lane
+            const int nLeft = static_cast<int>(rowLen) - static_cast<int>(laneOff);        // row bases from this lane's first on
             const bool anyBad = __any_sync(0xFFFFFFFFu, bad);
             uint32_t inv = 0, slowAC = 0, slowGT = 0;
-            if (anyBad) inv = slowRow(stage + skew + lane * kRowSpan, nValid, &slowAC, &slowGT);
-            *reinterpret_cast<uint2 *>(sPk + 2 * lane) = make_uint2(X0, X1);
+            if (anyBad) inv = slowRow(smem + (stage - winBase - kWindowBase) + skew + laneOff, clamp32(nLeft), &slowAC, &slowGT);
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pkAddr + lane * 8), "r"(X0), "r"(X1) : "memory");
 
             // ---- 2. one table byte per NPOS start positions ---------------------------------------------------
             uint32_t H = 0;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 }
             }
             // ---- 3. matches never cross the window end (src/teloscope.cpp:439) --------------------------------
-            H &= maskBelow(clamp32(static_cast<int>(rowLen) - static_cast<int>(L) + 1 - lane * kRowSpan));
+            H &= bmskClamp(max(nLeft - static_cast<int>(L) + 1, 0));
             if (anyBad) {
                 uint32_t invN = __shfl_down_sync(0xFFFFFFFFu, inv, 1);
                 if (lane == 31) invN = 0;
@@ -298,80 +299,77 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
             // ---- 4. A/C/G/T of the window ---------------------------------------------------------------------
             uint32_t sumAC = 0, sumGT = 0;
             if (COUNT) {
-                uint32_t totAC, totGT;
-                const uint32_t Y0 = X0 & (shlClamp(1u, 2u * static_cast<uint32_t>(min(nValid, 16))) - 1u);
-                const uint32_t Y1 = X1 & (shlClamp(1u, 2u * static_cast<uint32_t>(max(nValid - 16, 0))) - 1u);
+                const int n2 = 2 * nLeft;
+                const uint32_t Y0 = X0 & bmskClamp(max(n2, 0));
+                const uint32_t Y1 = X1 & bmskClamp(max(n2 - 32, 0));
                 const uint32_t e = (Y0 & 0x55555555u) | ((Y1 << 1) & 0xAAAAAAAAu);    // code bit 0: C or G
                 const uint32_t o = ((Y0 >> 1) & 0x55555555u) | (Y1 & 0xAAAAAAAAu);    // code bit 1: G or T
                 const uint32_t nE = __popc(e), nO = __popc(o), nG = __popc(e & o);
-                totAC = (static_cast<uint32_t>(nValid) - nE - nO + nG) | ((nE - nG) << 16);
-                totGT = nG | ((nO - nG) << 16);
+                uint32_t totAC = (static_cast<uint32_t>(clamp32(nLeft)) - nE - nO + nG) | ((nE - nG) << 16);
+                uint32_t totGT = nG | ((nO - nG) << 16);
                 if (anyBad) { totAC = slowAC; totGT = slowGT; }
                 sumAC = __reduce_add_sync(0xFFFFFFFFu, totAC);
                 sumGT = __reduce_add_sync(0xFFFFFFFFu, totGT);
             }
 
             // ---- 5. compaction and emission -------------------------------------------------------------------
-            const size_t slotIdx = static_cast<size_t>(cur.tile) * kTileRows + r;
-            DevMatch *slot = p.slots + slotIdx * p.slotCap;
-            // "terminal" status (src/teloscope.cpp:403-406,451-459) is a property of the window, except for
-            // the window that straddles T or n - T
-            const uint32_t termEnd = cur.itemLen > T ? cur.itemLen - T : 0u;
-            const uint32_t wEnd = rel + rowLen;
-            const uint32_t termMode = (wEnd <= T || rel >= termEnd) ? 1u : ((rel > T && wEnd < termEnd) ? 0u : 2u);
-            uint32_t wMatches = 0, ovBase = kNoOverflow, rowNct = 0;
-            uint32_t cls = 0;                                   // per lane: 4 x 8-bit counters by class (bit0 forward, bit1 canonical)
+            uint2 *slot = reinterpret_cast<uint2 *>(p.slots) + static_cast<size_t>(slotIdx) * p.slotCap;
+            const bool rowHasTerm = rel <= T || rel + rowLen > termEnd;          // warp-uniform
+            uint32_t wMatches = 0, ovBase = kNoOverflow, rowNct = 0, nCan = 0, nFwd = 0;
             auto emitRange = [&](uint32_t total) {              // queue[0, total) holds row positions, ascending
                 const bool roomy = wMatches + total <= p.slotCap;           // warp-uniform
                 if (!roomy && ovBase == kNoOverflow) {
                     if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
                     ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
                 }
-                uint2 *out = reinterpret_cast<uint2 *>(slot) + wMatches;
+                uint2 *out = slot + wMatches;
+#pragma unroll 1
                 for (uint32_t from = 0; from < total; from += 32) {
                     const uint32_t idx = from + lane;
-                    bool nct = false;
+                    uint32_t f = 0;
+                    bool term = false;
                     if (idx < total) {
-                        const uint32_t qq = sQueue[idx];
-                        const uint32_t wi = qq >> 4, sh = (qq & 15u) * 2u;
-                        const uint32_t key = __funnelshift_r(sPk[wi], sPk[wi + 1], sh) & keyMask;
-                        const uint32_t f = ldsU8(flagBase + key);        // bit0 hit, bit1 forward, bit2 canonical
+                        const uint32_t qq = ldsU16(qAddr + idx * 2);
+                        const uint32_t wa = pkAddr + ((qq >> 2) & ~3u), sh = (qq & 15u) * 2u;
+                        const uint32_t key = __funnelshift_r(lds32(wa), lds32(wa + 4), sh) & keyMask;
+                        f = ldsU8(flagBase + key);        // bit0 hit, bit1 forward, bit2 canonical
                         const uint32_t pos = rel + qq;
-                        uint32_t fl = (f >> 1) & 3u;
-                        cls += 1u << (8u * fl);
-                        if (termMode == 1u || (termMode == 2u && (pos <= T || pos >= termEnd))) {
-                            fl |= kMatchTerm;
-                            nct = !(f & 4u);
-                        }
-                        // DevMatch {pos, len:16, flags:8, region:8}
-                        const uint2 rec = make_uint2(pos, L | (fl << 16) | (static_cast<uint32_t>(kRegionAccounted) << 24));
+                        term = pos <= T || pos >= termEnd;
+                        const uint32_t fl = ((f >> 1) & 3u) | (term ? static_cast<uint32_t>(kMatchTerm) : 0u);
+                        const uint2 rec = make_uint2(pos, fl * 65536u + recHi);
                         if (roomy) out[idx] = rec;
                         else {
                             const uint32_t o = wMatches + idx;
-                            if (o < p.slotCap) reinterpret_cast<uint2 *>(slot)[o] = rec;
+                            if (o < p.slotCap) slot[o] = rec;
                             else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap)
                                 reinterpret_cast<uint2 *>(p.ovArena)[ovBase + (o - p.slotCap)] = rec;
                         }
                     }
-                    if (termMode) rowNct += __popc(__ballot_sync(0xFFFFFFFFu, nct));
+                    nFwd += __popc(__ballot_sync(0xFFFFFFFFu, (f & 2u) != 0));
+                    nCan += __popc(__ballot_sync(0xFFFFFFFFu, (f & 4u) != 0));
+                    if (rowHasTerm) rowNct += __popc(__ballot_sync(0xFFFFFFFFu, term && (f & 5u) == 1u));
                 }
                 wMatches += total;
             };
             auto scatter = [&](uint32_t bits, uint32_t o) {
-                const uint32_t base = lane * kRowSpan;
-                while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; sQueue[o++] = static_cast<uint16_t>(base + b); }
+                uint32_t a = qAddr + o * 2;
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(laneOff + b) : "memory");
+                    a += 2;
+                }
             };
             const uint32_t nH = __popc(H);
             const uint32_t incl = warpInclusiveScan(nH, lane);
             const uint32_t allTotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            __syncwarp();                                       // the 2-bit copy of the row is in place
             if (allTotal <= static_cast<uint32_t>(kRowQueueCap)) {
                 scatter(H, incl - nH);
                 __syncwarp();
                 emitRange(allTotal);
             } else {
                 // dense row: 8 lanes (<= 256 starts) at a time, lane groups keep genome order
-                for (int part = 0; part < 4; ++part) {
+                for (uint32_t part = 0; part < 4; ++part) {
                     const uint32_t bits = (lane >> 3) == part ? H : 0u;
                     const uint32_t n = __popc(bits);
                     const uint32_t in2 = warpInclusiveScan(n, lane);
@@ -383,37 +381,25 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 }
             }
 
-            // ---- 6. the window's 8 counters: one 32-byte store -----------------------------------------------
-            const uint32_t cEven = __reduce_add_sync(0xFFFFFFFFu, cls & 0x00FF00FFu);            // rev-non | rev-can << 16
-            const uint32_t cOdd = __reduce_add_sync(0xFFFFFFFFu, (cls >> 8) & 0x00FF00FFu);      // fwd-non | fwd-can << 16
-            const uint32_t nCan = (cEven >> 16) + (cOdd >> 16), nFwd = (cOdd & 0xFFFFu) + (cOdd >> 16);
-            if (lane < 8) {
-                uint32_t v;
-                if (lane < 4) {
-                    const uint32_t pk = lane < 2 ? sumAC : sumGT;
-                    v = (lane & 1) ? pk >> 16 : pk & 0xFFFFu;
-                } else {
-                    const uint32_t n = lane == 4 ? nCan : lane == 5 ? wMatches - nCan : lane == 6 ? nFwd : wMatches - nFwd;
-                    v = n * L;                                   // canonical, non-canonical, forward, reverse covered bp
-                }
-                p.windows[static_cast<size_t>(cur.firstWin + r) * 8 + lane] = v;
-            }
+            // ---- 6. the window's 8 counters and the slot's bookkeeping: three 16-byte stores -----------------------
             if (lane == 0) {
-                p.slotCounts[slotIdx] = wMatches;
-                p.slotOv[slotIdx] = ovBase;
-                p.slotCan[slotIdx] = nCan;
-                p.slotNct[slotIdx] = rowNct;
+                const uint32_t covAll = wMatches * L, covCan = nCan * L, covFwd = nFwd * L;
+                p.windows[2 * static_cast<size_t>(win)] = make_uint4(sumAC & 0xFFFFu, sumAC >> 16, sumGT & 0xFFFFu, sumGT >> 16);
+                p.windows[2 * static_cast<size_t>(win) + 1] = make_uint4(covCan, covAll - covCan, covFwd, covAll - covFwd);
+                p.slotMeta[slotIdx] = make_uint4(wMatches, ovBase, nCan, rowNct);
             }
             uAll += wMatches; uCan += nCan; uFwd += nFwd; uNct += rowNct;
-            buf ^= 1;
+            buf ^= 1u;
+            rowAddr += W; rel += W; remaining -= W; ++win; ++slotIdx;
         }
         // ---- unit epilogue: per-tile and per-item totals ----------------------------------------------------
         if (uAll) {
+            const uint32_t tile = db.y / kTileRows;
             if (lane < 3) {
                 const uint32_t v = lane == 0 ? uAll : lane == 1 ? uCan : uNct;
-                if (v) atomicAdd(p.tileTot + static_cast<size_t>(lane) * p.nTilesAll + cur.tile, v);
+                if (v) atomicAdd(p.tileTot + static_cast<size_t>(lane) * p.nTilesAll + tile, v);
             } else if (lane < 8) {
-                uint32_t *ic = reinterpret_cast<uint32_t *>(p.itemCounts + cur.item);     // all, fwd, rev, can, nonCanTerm
+                uint32_t *ic = reinterpret_cast<uint32_t *>(p.itemCounts + db.w);     // all, fwd, rev, can, nonCanTerm
                 const uint32_t v = lane == 3 ? uAll : lane == 4 ? uFwd : lane == 5 ? uAll - uFwd : lane == 6 ? uCan : uNct;
                 if (v) atomicAdd(ic + (lane - 3), v);
             }

@@ -106,13 +106,14 @@ struct Slot {
     std::vector<DevRegion> regions;
     std::vector<DevTile> tiles;
     std::vector<DevFastTile> fastTiles;      // tiles for the lean kernel
-    std::vector<DevRowUnit> rowUnits;        // work units of the window-row kernel
+    std::vector<DevRowRegion> rowRegions;    // contigs of the window-row kernel (units are laid out on the device)
+    uint32_t nRowUnits = 0;
     size_t nRowTiles = 0;
     std::vector<uint8_t> tileIsRow;          // per tile: 1 = made of whole windows for the window-row kernel
     std::vector<uint32_t> generalTiles;      // indices of the tiles the general kernel takes entirely
     const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
     HostBuf hSeq, hMeta, hMeta2;              // pinned staging
-    DevBuf dRowTiles, dFastTiles, dGeneralTiles, dRedo, dTileTot, dCanIdx, dNctIdx, dRunStarts;
+    DevBuf dRowTiles, dRowRegions, dFastTiles, dGeneralTiles, dRedo, dTileTot, dCanIdx, dNctIdx, dRunStarts;
     uint64_t nCanAll = 0, nNctAll = 0;       // canonical / terminal non-canonical records of the batch
     DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotMeta,
         dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
@@ -351,7 +352,7 @@ void tls_destroy(tls_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (Slot &s : ctx->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
-        for (DevBuf *b : {&s.dRowTiles, &s.dFastTiles, &s.dGeneralTiles, &s.dRedo, &s.dTileTot, &s.dCanIdx,
+        for (DevBuf *b : {&s.dRowTiles, &s.dRowRegions, &s.dFastTiles, &s.dGeneralTiles, &s.dRedo, &s.dTileTot, &s.dCanIdx,
                           &s.dNctIdx, &s.dRunStarts})
             b->release();
         for (DevBuf *b : {&s.dAbsPos, &s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
@@ -406,7 +407,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
     TLS_CUDA(s.dTileTot.reserve(static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * 12));
     TLS_CUDA(s.dTileBase.reserve((static_cast<size_t>(nTiles) + 1) * 24));
     TLS_CUDA(cudaMemsetAsync(s.dTileTot.p, 0, static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * 12, s.stream));
-    if (!s.rowUnits.empty()) {
+    if (s.nRowUnits) {
         // the last tile of a contig has fewer than 32 windows: its other row slots must read as empty
         TLS_CUDA(cudaMemsetAsync(s.dSlotMeta.p, 0, nSlots * 16, s.stream));
     }
@@ -427,7 +428,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         if (s.mode != TLS_MODE_GENOME) cfg.countAcgt = 0;
         unsigned int *redo = s.dRedo.as<unsigned int>();
         TLS_CUDA(cudaEventRecord(s.evScan0, s.stream));
-        const uint32_t nRow = static_cast<uint32_t>(s.rowUnits.size());
+        const uint32_t nRow = s.nRowUnits;
         if (nRow) {
             RowParams f{};
             f.seq = s.devSeq;
@@ -605,7 +606,7 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     // tiles of 32 whole windows (one window per tile row).  Everything else: runs of (nearly) adjacent
     // regions are cut into pieces of <= kTileMaxLen bytes; of those the lean kernel takes the tiles that
     // lie inside one region, the general kernel the rest.
-    s.tiles.clear(); s.tileIsRow.clear(); s.rowUnits.clear(); s.nRowTiles = 0;
+    s.tiles.clear(); s.tileIsRow.clear(); s.rowRegions.clear(); s.nRowUnits = 0; s.nRowTiles = 0;
     s.tiles.reserve(static_cast<size_t>(s.nBases / 32000) + s.regions.size() + 1);
     {
         DevConfig probe = ctx->dcfg;
@@ -619,28 +620,21 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
             const DevRegion &reg = s.regions[r];
             if (rowOk && reg.len >= rowMinLen) {
                 const uint32_t nWinReg = (reg.len + W - 1) / W;
-                for (uint32_t w0 = 0; w0 < nWinReg; w0 += kTileRows) {
-                    const uint32_t nRows = std::min<uint32_t>(kTileRows, nWinReg - w0);
-                    const uint32_t tile = static_cast<uint32_t>(s.tiles.size());
-                    for (uint32_t k = 0; k < nRows; k += kRowsPerUnit) {
-                        DevRowUnit u{};
-                        u.bufStart = reg.bufStart + static_cast<uint64_t>(w0 + k) * W;
-                        u.rel = reg.relStart + (w0 + k) * W;
-                        u.itemLen = reg.itemLen;
-                        u.firstWin = reg.winBase + w0 + k;
-                        u.slot0 = tile * kTileRows + k;
-                        u.nRows = std::min<uint32_t>(kRowsPerUnit, nRows - k);
-                        u.item = reg.item;
-                        s.rowUnits.push_back(u);
-                    }
-                    DevTile t{};
-                    t.bufStart = reg.bufStart + static_cast<uint64_t>(w0) * W;
-                    t.len = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(nRows) * W, reg.len - static_cast<uint64_t>(w0) * W));
-                    t.firstRegion = static_cast<uint32_t>(r);
-                    s.tiles.push_back(t);
-                    s.tileIsRow.push_back(1);
-                    ++s.nRowTiles;
-                }
+                const uint32_t nTilesReg = (nWinReg + kTileRows - 1) / kTileRows;
+                DevRowRegion rr{};
+                rr.bufStart = reg.bufStart; rr.len = reg.len; rr.relStart = reg.relStart; rr.itemLen = reg.itemLen;
+                rr.winBase = reg.winBase; rr.item = reg.item;
+                rr.tile0 = static_cast<uint32_t>(s.tiles.size());
+                rr.unit0 = s.nRowUnits;
+                rr.nUnits = (nWinReg + kRowsPerUnit - 1) / kRowsPerUnit;      // kTileRows is a multiple of kRowsPerUnit
+                s.rowRegions.push_back(rr);
+                s.nRowUnits += rr.nUnits;
+                // the tile table entries of these tiles are not read by any kernel (only general tiles are)
+                DevTile t{};
+                t.firstRegion = static_cast<uint32_t>(r);
+                s.tiles.resize(s.tiles.size() + nTilesReg, t);
+                s.tileIsRow.resize(s.tileIsRow.size() + nTilesReg, 1);
+                s.nRowTiles += nTilesReg;
                 ++r;
                 continue;
             }
@@ -695,16 +689,21 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     // ---- upload metadata ------------------------------------------------------------------------
     {
         const size_t bFast = s.fastTiles.size() * sizeof(DevFastTile), bGen = s.generalTiles.size() * 4,
-                     bRow = s.rowUnits.size() * sizeof(DevRowUnit);
+                     bRow = s.rowRegions.size() * sizeof(DevRowRegion);
         TLS_CUDA(s.hMeta2.reserve(bFast + bGen + bRow + 64));
         uint8_t *h2 = s.hMeta2.as<uint8_t>();
-        if (bRow) std::memcpy(h2, s.rowUnits.data(), bRow);
+        if (bRow) std::memcpy(h2, s.rowRegions.data(), bRow);
         if (bFast) std::memcpy(h2 + bRow, s.fastTiles.data(), bFast);
         if (bGen) std::memcpy(h2 + bRow + bFast, s.generalTiles.data(), bGen);
-        TLS_CUDA(s.dRowTiles.reserve(std::max<size_t>(bRow, 16)));
+        TLS_CUDA(s.dRowRegions.reserve(std::max<size_t>(bRow, 16)));
+        TLS_CUDA(s.dRowTiles.reserve(std::max<size_t>(static_cast<size_t>(s.nRowUnits) * sizeof(DevRowUnit), 16)));
         TLS_CUDA(s.dFastTiles.reserve(std::max<size_t>(bFast, 16)));
         TLS_CUDA(s.dGeneralTiles.reserve(std::max<size_t>(bGen, 16)));
-        if (bRow) TLS_CUDA(cudaMemcpyAsync(s.dRowTiles.p, h2, bRow, cudaMemcpyHostToDevice, s.stream));
+        if (bRow) {
+            TLS_CUDA(cudaMemcpyAsync(s.dRowRegions.p, h2, bRow, cudaMemcpyHostToDevice, s.stream));
+            TLS_CUDA(launchRowPlan(s.dRowRegions.as<DevRowRegion>(), static_cast<uint32_t>(s.rowRegions.size()), ctx->cfg.window_size,
+                                   s.dRowTiles.as<DevRowUnit>(), s.nRowUnits, s.stream));
+        }
         if (bFast) TLS_CUDA(cudaMemcpyAsync(s.dFastTiles.p, h2 + bRow, bFast, cudaMemcpyHostToDevice, s.stream));
         if (bGen) TLS_CUDA(cudaMemcpyAsync(s.dGeneralTiles.p, h2 + bRow + bFast, bGen, cudaMemcpyHostToDevice, s.stream));
     }

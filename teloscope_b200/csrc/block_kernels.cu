@@ -79,27 +79,38 @@ __global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *c
 __global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase,
                                                        const unsigned int *ovCursor, const unsigned int *redo,
                                                        unsigned long long *hostOut) {
+    // one block per array; a thread takes 4 consecutive tiles per round
     __shared__ unsigned long long warpSums[32];
     __shared__ unsigned long long carry;
+    const uint32_t k = blockIdx.x;
     if (threadIdx.x == 0) {
-        hostOut[0] = *ovCursor;
-        hostOut[4] = redo ? (static_cast<unsigned long long>(redo[0]) | (static_cast<unsigned long long>(redo[1]) << 32)) : 0ull;
-    }
-    for (int k = 0; k < 3; ++k) {
-        if (threadIdx.x == 0) carry = 0;
-        __syncthreads();
-        const uint32_t *in = tileTot + static_cast<size_t>(k) * nTiles;
-        unsigned long long *out = tileBase + static_cast<size_t>(k) * (nTiles + 1);
-        for (uint32_t base = 0; base < nTiles; base += 1024) {
-            const uint32_t i = base + threadIdx.x;
-            const unsigned long long v = i < nTiles ? in[i] : 0;
-            const unsigned long long excl = blockExclusive1024(v, warpSums, &carry);
-            if (i < nTiles) out[i] = excl;
+        carry = 0;
+        if (k == 0) {
+            hostOut[0] = *ovCursor;
+            hostOut[4] = redo ? (static_cast<unsigned long long>(redo[0]) | (static_cast<unsigned long long>(redo[1]) << 32)) : 0ull;
         }
-        if (threadIdx.x == 0) { out[nTiles] = carry; hostOut[1 + k] = carry; }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) __threadfence_system();
+    __syncthreads();
+    const uint32_t *in = tileTot + static_cast<size_t>(k) * nTiles;
+    unsigned long long *out = tileBase + static_cast<size_t>(k) * (nTiles + 1);
+    for (uint32_t base = 0; base < nTiles; base += 4096) {
+        const uint32_t i = base + threadIdx.x * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = i + j < nTiles ? in[i + j] : 0u;
+        const unsigned long long sum = static_cast<unsigned long long>(v[0]) + v[1] + v[2] + v[3];
+        unsigned long long excl = blockExclusive1024(sum, warpSums, &carry);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i + j < nTiles) out[i + j] = excl;
+            excl += v[j];
+        }
+    }
+    if (threadIdx.x == 0) {
+        out[nTiles] = carry;
+        hostOut[1 + k] = carry;
+        __threadfence_system();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
 
 cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, const unsigned int *ovCursor,
                            const unsigned int *redo, unsigned long long *hostOut, cudaStream_t s) {
-    tileScanKernel<<<1, 1024, 0, s>>>(tileTot, nTiles, tileBase, ovCursor, redo, hostOut);
+    tileScanKernel<<<3, 1024, 0, s>>>(tileTot, nTiles, tileBase, ovCursor, redo, hostOut);
     return cudaGetLastError();
 }
 cudaError_t launchGather(const GatherParams &g, cudaStream_t s) {

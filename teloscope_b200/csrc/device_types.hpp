@@ -88,6 +88,17 @@ struct DevRowUnit {        // 32 bytes, read as two uint4
     uint32_t item;
 };
 
+// A contig the window-row kernel takes: its units and tiles are laid out on the device by
+// rowPlanKernel (4 units per tile of 32 windows; the last tile of a contig may hold fewer).
+struct DevRowRegion {      // 48 bytes
+    uint64_t bufStart;
+    uint32_t len, relStart, itemLen, winBase, item;
+    uint32_t tile0;        // index of the contig's first tile in the batch's tile table
+    uint32_t unit0;        // index of its first unit
+    uint32_t nUnits;
+    uint32_t pad[2];
+};
+
 struct DevMatch {          // 8 bytes, ordered by (item, pos, len)
     uint32_t pos;          // relative to the item start
     uint16_t len;

@@ -19,6 +19,9 @@ cudaError_t launchFastScan(const FastParams &p, int grid, cudaStream_t stream);
 size_t rowSmemBytes();
 bool rowConfigOk(const DevConfig &c);
 cudaError_t launchRowScan(const RowParams &p, int grid, cudaStream_t stream);
+// fills units[0, nUnits) from the per-contig table (regions sorted by unit0)
+cudaError_t launchRowPlan(const DevRowRegion *regions, uint32_t nRegions, uint32_t windowSize, DevRowUnit *units,
+                          uint32_t nUnits, cudaStream_t stream);
 
 // exclusive scans of the per-tile totals (3 arrays: tileBase[k][nTiles] = total), then ordered copy
 // hostOut: 5 u64 in mapped pinned host memory: ovCursor, totals[3], redo count | status << 32

@@ -11,7 +11,7 @@
 //   * warps are autonomous: every warp owns a double-buffered 1 KiB staging area and two mbarriers,
 //     stages its next row with cp.async.bulk (TMA bulk copy) while it works on the current one, and
 //     never meets another warp at a barrier.  Work = units of 8 consecutive windows, unit u goes to
-//     warp u mod (warps in the grid);
+//     warp u mod (warps in the grid); lane r precomputes the copy of row r once per unit and issues it;
 //   * a lane owns 32 bases: 2 x LDS.128 of the 16-byte-aligned staging area, SWAR pack to 2-bit codes
 //     (one multiply per 4 bases) fused with the exact "all bytes are ACGTacgt" test; the row's
 //     alignment skew is removed on the packed words (one funnel shift per word);
@@ -22,8 +22,9 @@
 //   * matches: warp prefix sum, scatter into a per-warp queue, then 32 at a time: orientation /
 //     canonical flags from the 4^L table, per-lane class counters (covered bp = count * L,
 //     :470-510), one coalesced 8-byte store into the row's slot of the match arena;
-//   * the 8 window counters leave as one 32-byte store; per-tile / per-item totals as a handful of
-//     atomics per unit.
+//   * a row's results (8 window counters, slot bookkeeping) wait in shared memory until the unit is
+//     done; then lane r writes row r's three 16-byte stores, and the per-tile / per-item totals leave
+//     as a handful of atomics per unit.
 //   * a row that holds a byte outside ACGTacgt takes a slow exact path in the same kernel (per-byte
 //     validity bitmap: dead starts, bases not counted), so nothing is handed to another kernel.
 // Integer / byte streaming work: no tensor cores; the bound is instruction issue, then HBM.
@@ -130,8 +131,10 @@ constexpr uint32_t kPkOff = 0;
 constexpr uint32_t kQueueOff = kPkOff + kRowWarps * kPkWords * 4;         // 8448
 constexpr uint32_t kFlagOff = kQueueOff + kRowWarps * kRowQueueCap * 2;   // + 16384
 constexpr uint32_t kBarOff = kFlagOff + kFastFlagBytes;                   // + 16384
+constexpr uint32_t kRecOff = kBarOff + kRowWarps * 2 * 8;                  // per warp: row results of the unit in flight
+constexpr uint32_t kRecBytes = kRowsPerUnit * 16 + kRowsPerUnit * 4;      //   8 x {A|C<<16, G|T<<16, all|can<<16, fwd|nct<<16} + 8 overflow bases
 constexpr uint32_t kIdxOff = 0x10000u - kWindowBase;
-static_assert(kBarOff + kRowWarps * 2 * 8 <= kIdxOff, "front region must end before the 8-mer table");
+static_assert(kRecOff + kRowWarps * kRecBytes <= kIdxOff, "front region must end before the 8-mer table");
 constexpr uint32_t kStageOff = kIdxOff + 65536u;
 constexpr uint32_t kRowSmemTotal = kStageOff + kRowWarps * 2 * kRowStage;
 static_assert(kRowSmemTotal <= 232448u, "shared memory budget of one SM");
@@ -140,7 +143,7 @@ static_assert(kRowSmemTotal <= 232448u, "shared memory budget of one SM");
 // bitmap of such bases in row coordinates and the A/C/G/T counts of the lane's valid bases.  The
 // reference's Trie stops at such a byte (include/teloscope.h:27-35,63-66) and analyzeWindow does not
 // count it (src/teloscope.cpp:418-435).
-__device__ __noinline__ uint32_t slowRow(const uint8_t *row, int nValid, uint32_t *ac, uint32_t *gt) {
+__device__ __noinline__ uint4 slowRow(const uint8_t *row, int nValid) {
     uint32_t inv = 0, a = 0, c = 0, g = 0, t = 0;
     for (int i = 0; i < nValid; ++i) {
         const uint32_t ch = row[i] & 0xDFu;
@@ -150,9 +153,7 @@ __device__ __noinline__ uint32_t slowRow(const uint8_t *row, int nValid, uint32_
         else if (ch == 'T') ++t;
         else inv |= 1u << i;
     }
-    *ac = a | (c << 16);
-    *gt = g | (t << 16);
-    return inv;
+    return make_uint4(inv, a | (c << 16), g | (t << 16), 0u);
 }
 
 }  // namespace
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     const uint32_t qAddr = winBase + kWindowBase + kQueueOff + warp * (kRowQueueCap * 2);
     const uint32_t stageAddr = winBase + kWindowBase + kStageOff + warp * (2 * kRowStage);
     const uint32_t barAddr = winBase + kWindowBase + kBarOff + warp * 16;
+    const uint32_t recAddr = winBase + kWindowBase + kRecOff + warp * kRecBytes;
 
     // ---- one-time setup ---------------------------------------------------------------------------
     for (int i = tid; i < 65536 / 16; i += kRowThreads)
@@ -196,54 +198,72 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     const uint32_t totalWarps = gridDim.x * kRowWarps;
     const uint32_t nUnits = p.nUnits;
     const uint32_t laneOff = lane * kRowSpan;
+    const uint64_t seqBase = reinterpret_cast<uint64_t>(p.seq);
 
-    // stage the row that starts at global address `addr` into buffer `b` (one lane)
-    auto issueRow = [&](uint64_t addr, uint32_t rowLen, uint32_t b) {
-        const uint32_t skew = static_cast<uint32_t>(addr) & 15u;
-        const uint32_t bytes = (skew + rowLen + 15u) & ~15u;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // Per-lane masks of a row of rowLen bases: the lane's valid 2-bit fields in X0 / X1, its valid match
+    // starts (a match never crosses the window end, src/teloscope.cpp:439) and its number of bases.
+    // A full window has the same masks in every row, so they are computed once (only the last window of
+    // a contig is shorter).
+    struct LaneMasks { uint32_t m0, m1, hm, nv; };
+    auto laneMasks = [&](uint32_t rowLen) {
+        const int nLeft = static_cast<int>(rowLen) - static_cast<int>(laneOff);
+        LaneMasks m;
+        m.m0 = bmskClamp(max(2 * nLeft, 0));
+        m.m1 = bmskClamp(max(2 * nLeft - 32, 0));
+        m.hm = bmskClamp(max(nLeft - static_cast<int>(L) + 1, 0));
+        m.nv = static_cast<uint32_t>(clamp32(nLeft));
+        return m;
+    };
+    const LaneMasks fullMasks = laneMasks(W);
+
+    // One lane stages a row: 16-byte aligned source, whole 16-byte pieces.  No proxy fence is needed for
+    // the reuse of the buffer: every lane's reads of it were consumed before the __syncwarp that precedes
+    // the issue, and the mbarrier orders the copy's writes before the next reads.
+    auto issueCopy = [&](uint64_t src, uint32_t bytes, uint32_t b) {
         mbarExpectTx(barAddr + b * 8, bytes);
-        bulkLoad(stageAddr + b * kRowStage, reinterpret_cast<const void *>(addr - skew), bytes, barAddr + b * 8);
+        bulkLoad(stageAddr + b * kRowStage, reinterpret_cast<const void *>(src), bytes, barAddr + b * 8);
     };
     auto loadUnit = [&](uint32_t u, uint4 &a, uint4 &b) {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.units + u);
         a = __ldg(src); b = __ldg(src + 1);
     };
+    auto issueFirstRow = [&](uint32_t u, uint32_t b) {          // row 0 of unit u (one lane)
+        uint4 da, db;
+        loadUnit(u, da, db);
+        const uint64_t addr = seqBase + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32));
+        const uint32_t skew = static_cast<uint32_t>(addr) & 15u;
+        issueCopy(addr - skew, (skew + min(W, da.w - da.z) + 15u) & ~15u, b);
+    };
 
     uint32_t phase = 0, buf = 0;                               // phase bit b: parity to wait for on buffer b
     uint32_t u = blockIdx.x * kRowWarps + warp;
     if (u >= nUnits) return;
-    if (lane == 0) {
-        uint4 a, b;
-        loadUnit(u, a, b);
-        issueRow(reinterpret_cast<uint64_t>(p.seq) + (static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32)),
-                 min(W, a.w - a.z), 0);
-    }
+    if (lane == 0) issueFirstRow(u, 0);
 
     for (; u < nUnits; u += totalWarps) {
         uint4 da, db;
         loadUnit(u, da, db);
-        uint64_t rowAddr = reinterpret_cast<uint64_t>(p.seq) + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32));
+        uint64_t rowAddr = seqBase + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32));
         uint32_t rel = da.z;                                   // item position of the window start
         uint32_t remaining = da.w - da.z;                      // bases from the window start to the end of the contig
         const uint32_t termEnd = da.w > T ? da.w - T : 0u;     // "terminal": pos <= T || pos >= n - T (src/teloscope.cpp:403-406,451-459)
-        uint32_t win = db.x, slotIdx = db.y;
         const uint32_t nRows = db.z;
-        uint32_t uAll = 0, uCan = 0, uFwd = 0, uNct = 0;
+        // lane r holds the staging parameters of row r of this unit (rows are W bases apart)
+        const uint64_t myAddr = rowAddr + static_cast<uint64_t>(lane) * W;
+        const uint32_t mySkew = static_cast<uint32_t>(myAddr) & 15u;
+        const uint32_t myBytes = (mySkew + min(W, remaining - lane * W) + 15u) & ~15u;
+        const uint64_t mySrc = myAddr - mySkew;
+        uint32_t ovRows = 0;                                   // bit r: row r spilled into an overflow chunk
 
 #pragma unroll 1
         for (uint32_t r = 0; r < nRows; ++r) {
             const uint32_t rowLen = min(W, remaining);
             // ---- look-ahead: stage the next row of this warp ----------------------------------------------
             __syncwarp();                                       // every lane is done with the other buffer, the queue and the 2-bit copy
-            if (lane == 0) {
-                if (r + 1 < nRows) issueRow(rowAddr + W, min(W, remaining - W), buf ^ 1u);
-                else if (u + totalWarps < nUnits) {
-                    uint4 a, b;
-                    loadUnit(u + totalWarps, a, b);
-                    issueRow(reinterpret_cast<uint64_t>(p.seq) + (static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32)),
-                             min(W, a.w - a.z), buf ^ 1u);
-                }
+            if (r + 1 < nRows) {
+                if (lane == r + 1) issueCopy(mySrc, myBytes, buf ^ 1u);
+            } else if (lane == 0 && u + totalWarps < nUnits) {
+                issueFirstRow(u + totalWarps, buf ^ 1u);
             }
             const uint32_t skew = static_cast<uint32_t>(rowAddr) & 15u;
             const uint32_t stage = stageAddr + buf * kRowStage;
@@ -267,10 +287,11 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 X1 = __funnelshift_r(P1, P2, sh);
                 X2 = __funnelshift_r(P2, P3, sh);
             }
-            const int nLeft = static_cast<int>(rowLen) - static_cast<int>(laneOff);        // row bases from this lane's first on
+            LaneMasks lm = fullMasks;
+            if (rowLen != W) lm = laneMasks(rowLen);            // warp-uniform: the last window of a contig
             const bool anyBad = __any_sync(0xFFFFFFFFu, bad);
-            uint32_t inv = 0, slowAC = 0, slowGT = 0;
-            if (anyBad) inv = slowRow(smem + (stage - winBase - kWindowBase) + skew + laneOff, clamp32(nLeft), &slowAC, &slowGT);
+            uint4 slow = make_uint4(0u, 0u, 0u, 0u);            // x: bitmap of the lane's bases outside ACGTacgt, y / z: A|C<<16, G|T<<16
+            if (anyBad) slow = slowRow(smem + (stage - winBase - kWindowBase) + skew + laneOff, static_cast<int>(lm.nv));
             asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pkAddr + lane * 8), "r"(X0), "r"(X1) : "memory");
 
             // ---- 2. one table byte per NPOS start positions ---------------------------------------------------
@@ -287,33 +308,31 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 }
             }
             // ---- 3. matches never cross the window end (src/teloscope.cpp:439) --------------------------------
-            H &= bmskClamp(max(nLeft - static_cast<int>(L) + 1, 0));
+            H &= lm.hm;
             if (anyBad) {
-                uint32_t invN = __shfl_down_sync(0xFFFFFFFFu, inv, 1);
+                uint32_t invN = __shfl_down_sync(0xFFFFFFFFu, slow.x, 1);
                 if (lane == 31) invN = 0;
-                uint32_t dead = inv;
-                for (uint32_t j = 1; j < L; ++j) dead |= __funnelshift_r(inv, invN, j);
+                uint32_t dead = slow.x;
+                for (uint32_t j = 1; j < L; ++j) dead |= __funnelshift_r(slow.x, invN, j);
                 H &= ~dead;
             }
 
             // ---- 4. A/C/G/T of the window ---------------------------------------------------------------------
             uint32_t sumAC = 0, sumGT = 0;
             if (COUNT) {
-                const int n2 = 2 * nLeft;
-                const uint32_t Y0 = X0 & bmskClamp(max(n2, 0));
-                const uint32_t Y1 = X1 & bmskClamp(max(n2 - 32, 0));
+                const uint32_t Y0 = X0 & lm.m0, Y1 = X1 & lm.m1;
                 const uint32_t e = (Y0 & 0x55555555u) | ((Y1 << 1) & 0xAAAAAAAAu);    // code bit 0: C or G
                 const uint32_t o = ((Y0 >> 1) & 0x55555555u) | (Y1 & 0xAAAAAAAAu);    // code bit 1: G or T
                 const uint32_t nE = __popc(e), nO = __popc(o), nG = __popc(e & o);
-                uint32_t totAC = (static_cast<uint32_t>(clamp32(nLeft)) - nE - nO + nG) | ((nE - nG) << 16);
+                uint32_t totAC = (lm.nv - nE - nO + nG) | ((nE - nG) << 16);
                 uint32_t totGT = nG | ((nO - nG) << 16);
-                if (anyBad) { totAC = slowAC; totGT = slowGT; }
+                if (anyBad) { totAC = slow.y; totGT = slow.z; }
                 sumAC = __reduce_add_sync(0xFFFFFFFFu, totAC);
                 sumGT = __reduce_add_sync(0xFFFFFFFFu, totGT);
             }
 
             // ---- 5. compaction and emission -------------------------------------------------------------------
-            uint2 *slot = reinterpret_cast<uint2 *>(p.slots) + static_cast<size_t>(slotIdx) * p.slotCap;
+            uint2 *slot = reinterpret_cast<uint2 *>(p.slots) + static_cast<size_t>(db.y + r) * p.slotCap;
             const bool rowHasTerm = rel <= T || rel + rowLen > termEnd;          // warp-uniform
             uint32_t wMatches = 0, ovBase = kNoOverflow, rowNct = 0, nCan = 0, nFwd = 0;
             auto emitRange = [&](uint32_t total) {              // queue[0, total) holds row positions, ascending
@@ -381,18 +400,34 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 }
             }
 
-            // ---- 6. the window's 8 counters and the slot's bookkeeping: three 16-byte stores -----------------------
+            // ---- 6. the row's results wait in shared memory for the unit epilogue ----------------------------------
             if (lane == 0) {
-                const uint32_t covAll = wMatches * L, covCan = nCan * L, covFwd = nFwd * L;
-                p.windows[2 * static_cast<size_t>(win)] = make_uint4(sumAC & 0xFFFFu, sumAC >> 16, sumGT & 0xFFFFu, sumGT >> 16);
-                p.windows[2 * static_cast<size_t>(win) + 1] = make_uint4(covCan, covAll - covCan, covFwd, covAll - covFwd);
-                p.slotMeta[slotIdx] = make_uint4(wMatches, ovBase, nCan, rowNct);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(recAddr + r * 16), "r"(sumAC), "r"(sumGT),
+                             "r"(wMatches | (nCan << 16)), "r"(nFwd | (rowNct << 16)) : "memory");
+                if (ovBase != kNoOverflow) asm volatile("st.shared.u32 [%0], %1;" ::"r"(recAddr + kRowsPerUnit * 16 + r * 4), "r"(ovBase) : "memory");
             }
-            uAll += wMatches; uCan += nCan; uFwd += nFwd; uNct += rowNct;
+            if (ovBase != kNoOverflow) ovRows |= 1u << r;
             buf ^= 1u;
-            rowAddr += W; rel += W; remaining -= W; ++win; ++slotIdx;
+            rowAddr += W; rel += W; remaining -= W;
         }
-        // ---- unit epilogue: per-tile and per-item totals ----------------------------------------------------
+        // ---- unit epilogue: lane r writes row r's window counters and slot bookkeeping (three 16-byte stores);
+        //      per-tile and per-item totals as a handful of atomics ------------------------------------------------
+        __syncwarp();
+        uint32_t k2 = 0, k3 = 0;                               // all | canonical << 16, forward | terminal non-canonical << 16
+        if (lane < nRows) {
+            uint32_t ac, gt;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ac), "=r"(gt), "=r"(k2), "=r"(k3) : "r"(recAddr + lane * 16));
+            uint32_t ov = kNoOverflow;
+            if ((ovRows >> lane) & 1u) ov = lds32(recAddr + kRowsPerUnit * 16 + lane * 4);
+            const uint32_t all = k2 & 0xFFFFu, can = k2 >> 16, fwd = k3 & 0xFFFFu, nct = k3 >> 16;
+            uint4 *wp = p.windows + 2 * static_cast<size_t>(db.x + lane);
+            wp[0] = make_uint4(ac & 0xFFFFu, ac >> 16, gt & 0xFFFFu, gt >> 16);
+            wp[1] = make_uint4(can * L, (all - can) * L, fwd * L, (all - fwd) * L);
+            p.slotMeta[db.y + lane] = make_uint4(all, ov, can, nct);
+        }
+        k2 = __reduce_add_sync(0xFFFFFFFFu, k2);               // <= 8 rows x 1002 per half: no carry between the halves
+        k3 = __reduce_add_sync(0xFFFFFFFFu, k3);
+        const uint32_t uAll = k2 & 0xFFFFu, uCan = k2 >> 16, uFwd = k3 & 0xFFFFu, uNct = k3 >> 16;
         if (uAll) {
             const uint32_t tile = db.y / kTileRows;
             if (lane < 3) {
@@ -405,6 +440,39 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
             }
         }
     }
+}
+
+// Work units of the window-row kernel, one thread per unit: unit j of a contig covers its windows
+// [8j, 8j + 8), tile j / 4, row slots (j % 4) * 8 ... of that tile.
+__global__ void __launch_bounds__(256) rowPlanKernel(const DevRowRegion *regions, uint32_t nRegions, uint32_t W,
+                                                     DevRowUnit *units, uint32_t nUnits) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nUnits) return;
+    uint32_t lo = 0, hi = nRegions;                               // last region with unit0 <= u
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (regions[mid].unit0 <= u) lo = mid; else hi = mid;
+    }
+    const DevRowRegion r = regions[lo];
+    const uint32_t j = u - r.unit0;
+    const uint32_t w0 = j * kRowsPerUnit;
+    const uint32_t nWin = (r.len + W - 1) / W;
+    DevRowUnit o;
+    o.bufStart = r.bufStart + static_cast<uint64_t>(w0) * W;
+    o.rel = r.relStart + w0 * W;
+    o.itemLen = r.itemLen;
+    o.firstWin = r.winBase + w0;
+    o.slot0 = (r.tile0 + w0 / kTileRows) * kTileRows + w0 % kTileRows;
+    o.nRows = min(static_cast<uint32_t>(kRowsPerUnit), nWin - w0);
+    o.item = r.item;
+    units[u] = o;
+}
+
+cudaError_t launchRowPlan(const DevRowRegion *regions, uint32_t nRegions, uint32_t windowSize, DevRowUnit *units,
+                          uint32_t nUnits, cudaStream_t stream) {
+    if (nUnits == 0) return cudaSuccess;
+    rowPlanKernel<<<(nUnits + 255) / 256, 256, 0, stream>>>(regions, nRegions, windowSize, units, nUnits);
+    return cudaGetLastError();
 }
 
 size_t rowSmemBytes() { return kRowSmemTotal; }

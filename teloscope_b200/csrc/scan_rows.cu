@@ -8,26 +8,30 @@
 // crosses a window end and windows tile the contig from its start (:604-637), so a window is an
 // independent row: no halo, no boundary inside a row, its 8 counters belong to exactly one warp.
 //
-//   * warps are autonomous: every warp owns a double-buffered 1 KiB staging area and two mbarriers,
-//     stages its next row with cp.async.bulk (TMA bulk copy) while it works on the current one, and
-//     never meets another warp at a barrier.  Work = units of 8 consecutive windows, unit u goes to
-//     warp u mod (warps in the grid); lane r precomputes the copy of row r once per unit and issues it;
-//   * a lane owns 32 bases: 2 x LDS.128 of the 16-byte-aligned staging area, SWAR pack to 2-bit codes
-//     (one multiply per 4 bases) fused with the exact "all bytes are ACGTacgt" test; the row's
-//     alignment skew is removed on the packed words (one funnel shift per word);
-//   * 11 probes of the 64 KiB 8-mer table (one byte answers NPOS start offsets, table on a 64 KiB
-//     boundary of the shared window so that masking + addressing is one LOP3) give the 32-bit bitmap
-//     of match starts; starts whose match would cross the window end are masked (:439);
-//   * A/C/G/T: 3 popcounts on bit planes + 2 REDUX per window (:418-435);
+//   * warps are autonomous and never meet at a barrier.  Work = units of 8 consecutive windows, unit u
+//     goes to warp u mod (warps in the grid);
+//   * a lane owns 32 bases of the row: two 16-byte streaming loads (ld.global.nc, no L1 allocation)
+//     from the 16-byte aligned span of the row straight into registers.  They are packed at the top of
+//     the row's iteration and the same registers are re-armed at once with the NEXT row's loads, which
+//     then have the whole iteration to land (software pipeline of depth one row per warp, 32 KiB in
+//     flight per SM); no shared-memory staging, no mbarrier;
+//   * SWAR pack to 2-bit codes (one multiply per 4 bases) fused with the exact "all bytes are ACGTacgt"
+//     test; the row's alignment skew is removed on the packed words (one funnel shift per word);
+//   * 11 probes of the 64 KiB 8-mer table (one byte answers NPOS start offsets; the table sits at
+//     shared address 0x10000, so the probe is mask + LDS with an immediate) give the 32-bit bitmap of
+//     match starts; starts whose match would cross the window end are masked (:439);
+//   * A/C/G/T: 3 popcounts on bit planes, 2 REDUX per window on packed partial sums; the four counts
+//     are derived from them once per row in the unit epilogue (:418-435);
 //   * matches: warp prefix sum, scatter into a per-warp queue, then 32 at a time: orientation /
-//     canonical flags from the 4^L table, per-lane class counters (covered bp = count * L,
-//     :470-510), one coalesced 8-byte store into the row's slot of the match arena;
+//     canonical flags from the 4^L table, class counts by one REDUX on a packed value (covered bp =
+//     count * L, :470-510), one coalesced 8-byte store into the row's slot of the match arena;
 //   * a row's results (8 window counters, slot bookkeeping) wait in shared memory until the unit is
 //     done; then lane r writes row r's three 16-byte stores, and the per-tile / per-item totals leave
-//     as a handful of atomics per unit.
+//     as a handful of atomics per unit;
 //   * a row that holds a byte outside ACGTacgt takes a slow exact path in the same kernel (per-byte
 //     validity bitmap: dead starts, bases not counted), so nothing is handed to another kernel.
-// Integer / byte streaming work: no tensor cores; the bound is instruction issue, then HBM.
+// Integer / byte streaming work: no tensor cores; the bound is instruction issue and the shared-memory
+// data pipe (random table probes), then HBM.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -42,30 +46,10 @@ namespace {
 __device__ __forceinline__ uint32_t smemAddr(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulkLoad(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-        "l"(src), "r"(bytes), "r"(bar)
-        : "memory");
+// streaming 16-byte load: every base is read once, nothing of it belongs in L1
+__device__ __forceinline__ void ldStream(uint4 &v, uint64_t addr) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr));
 }
 __device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {      // the tables never change during the kernel
     uint32_t v;
@@ -123,37 +107,38 @@ __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane) {
     return v;
 }
 
-// ---- shared memory layout (offsets inside the dynamic block, which starts kWindowBase bytes into the
-// shared window on sm_100; checked at run time) ----------------------------------------------------------
+// ---- shared memory layout: ABSOLUTE addresses in the CTA's shared window.  The dynamic block starts
+// kWindowBase bytes into it on sm_100 (checked at run time: status 1 otherwise), so every address below
+// is a compile-time constant and goes into the instruction as an immediate. -------------------------------
 constexpr uint32_t kWindowBase = 0x400;
-constexpr uint32_t kPkWords = 66;                                         // 2-bit copy of a row: 64 words + pad
-constexpr uint32_t kPkOff = 0;
-constexpr uint32_t kQueueOff = kPkOff + kRowWarps * kPkWords * 4;         // 8448
-constexpr uint32_t kFlagOff = kQueueOff + kRowWarps * kRowQueueCap * 2;   // + 16384
-constexpr uint32_t kBarOff = kFlagOff + kFastFlagBytes;                   // + 16384
-constexpr uint32_t kRecOff = kBarOff + kRowWarps * 2 * 8;                  // per warp: row results of the unit in flight
-constexpr uint32_t kRecBytes = kRowsPerUnit * 16 + kRowsPerUnit * 4;      //   8 x {A|C<<16, G|T<<16, all|can<<16, fwd|nct<<16} + 8 overflow bases
-constexpr uint32_t kIdxOff = 0x10000u - kWindowBase;
-static_assert(kRecOff + kRowWarps * kRecBytes <= kIdxOff, "front region must end before the 8-mer table");
-constexpr uint32_t kStageOff = kIdxOff + 65536u;
-constexpr uint32_t kRowSmemTotal = kStageOff + kRowWarps * 2 * kRowStage;
+constexpr uint32_t kWarpBlk = 1024;                        // per warp: 2-bit copy of the row | row results of the unit | match queue
+constexpr uint32_t kPkOff = 0;                             //   66 words (64 + pad)
+constexpr uint32_t kRecOff = 272;                          //   8 x 16 bytes of window / slot results + 8 overflow bases
+constexpr uint32_t kQueueOff = 512;                        //   kRowQueueCap u16 entries
+static_assert(kRecOff + kRowsPerUnit * 20 <= kQueueOff && kQueueOff + kRowQueueCap * 2 <= kWarpBlk, "per-warp block");
+constexpr uint32_t kWarpBase = kWindowBase;                               // 32 KiB of warp blocks (1 KiB aligned)
+constexpr uint32_t kFlagBase = kWarpBase + kRowWarps * kWarpBlk;          // 16 KiB flag table
+constexpr uint32_t kIdxBase = 0x10000u;                                   // 64 KiB 8-mer table on a 64 KiB boundary
+static_assert(kFlagBase + kFastFlagBytes <= kIdxBase, "front region must end before the 8-mer table");
+constexpr uint32_t kRowSmemTotal = kIdxBase + 65536u - kWindowBase;
 static_assert(kRowSmemTotal <= 232448u, "shared memory budget of one SM");
 
 // Slow exact path of a row that holds a byte outside ACGTacgt (IUPAC letters, '\r', ...): per-lane
-// bitmap of such bases in row coordinates and the A/C/G/T counts of the lane's valid bases.  The
-// reference's Trie stops at such a byte (include/teloscope.h:27-35,63-66) and analyzeWindow does not
-// count it (src/teloscope.cpp:418-435).
+// bitmap of such bases in row coordinates and the counts of the lane's valid bases, in the packed form
+// the fast path reduces (x: invalid bitmap, y: nE | nO << 16, z: nG | nValid << 16 with nE = C + G,
+// nO = G + T).  The reference's Trie stops at such a byte (include/teloscope.h:27-35,63-66) and
+// analyzeWindow does not count it (src/teloscope.cpp:418-435).
 __device__ __noinline__ uint4 slowRow(const uint8_t *row, int nValid) {
     uint32_t inv = 0, a = 0, c = 0, g = 0, t = 0;
     for (int i = 0; i < nValid; ++i) {
-        const uint32_t ch = row[i] & 0xDFu;
+        const uint32_t ch = __ldg(row + i) & 0xDFu;
         if (ch == 'A') ++a;
         else if (ch == 'C') ++c;
         else if (ch == 'G') ++g;
         else if (ch == 'T') ++t;
         else inv |= 1u << i;
     }
-    return make_uint4(inv, a | (c << 16), g | (t << 16), 0u);
+    return make_uint4(inv, (c + g) | ((g + t) << 16), g | ((a + c + g + t) << 16), 0u);
 }
 
 }  // namespace
@@ -163,33 +148,17 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-    if ((smemAddr(smem) & 0xFFFFu) != kWindowBase) {       // the table must sit on a 64 KiB boundary of the window
+    if (smemAddr(smem) != kWindowBase) {                   // the layout above is in absolute shared addresses
         if (tid == 0 && blockIdx.x == 0) atomicExch(p.status, 1u);
         return;
     }
-    // shared-window addresses (the dynamic block starts at kWindowBase of this CTA's window)
-    const uint32_t winBase = smemAddr(smem) - kWindowBase;      // 0 unless the CTA's window is offset (clusters)
-    const uint32_t idxBase = winBase + kWindowBase + kIdxOff;   // low 16 bits are zero
-    const uint32_t flagBase = winBase + kWindowBase + kFlagOff;
-    const uint32_t pkAddr = winBase + kWindowBase + kPkOff + warp * (kPkWords * 4);
-    const uint32_t qAddr = winBase + kWindowBase + kQueueOff + warp * (kRowQueueCap * 2);
-    const uint32_t stageAddr = winBase + kWindowBase + kStageOff + warp * (2 * kRowStage);
-    const uint32_t barAddr = winBase + kWindowBase + kBarOff + warp * 16;
-    const uint32_t recAddr = winBase + kWindowBase + kRecOff + warp * kRecBytes;
+    const uint32_t wb = kWarpBase + warp * kWarpBlk;       // this warp's block (1 KiB aligned: offsets can be OR-ed in)
 
     // ---- one-time setup ---------------------------------------------------------------------------
     for (int i = tid; i < 65536 / 16; i += kRowThreads)
-        reinterpret_cast<uint4 *>(smem + kIdxOff)[i] = reinterpret_cast<const uint4 *>(p.index8)[i];
+        reinterpret_cast<uint4 *>(smem + (kIdxBase - kWindowBase))[i] = reinterpret_cast<const uint4 *>(p.index8)[i];
     for (uint32_t i = tid; i < p.flagTabBytes / 16; i += kRowThreads)
-        reinterpret_cast<uint4 *>(smem + kFlagOff)[i] = reinterpret_cast<const uint4 *>(p.flagTab)[i];
-    for (int i = lane; i < 2 * kRowStage / 16; i += 32)        // bytes a short row leaves untouched must be harmless
-        reinterpret_cast<uint4 *>(smem + kStageOff + warp * (2 * kRowStage))[i] =
-            make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-    if (lane == 0) {
-        mbarInit(barAddr, 1);
-        mbarInit(barAddr + 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+        reinterpret_cast<uint4 *>(smem + (kFlagBase - kWindowBase))[i] = reinterpret_cast<const uint4 *>(p.flagTab)[i];
     __syncthreads();
 
     const uint32_t L = p.patLen, W = p.cfg.windowSize, T = p.cfg.terminalLimit;
@@ -199,6 +168,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     const uint32_t nUnits = p.nUnits;
     const uint32_t laneOff = lane * kRowSpan;
     const uint64_t seqBase = reinterpret_cast<uint64_t>(p.seq);
+    const uint32_t slotBytes = p.slotCap * 8u;
 
     // Per-lane masks of a row of rowLen bases: the lane's valid 2-bit fields in X0 / X1, its valid match
     // starts (a match never crosses the window end, src/teloscope.cpp:439) and its number of bases.
@@ -211,103 +181,94 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
         m.m0 = bmskClamp(max(2 * nLeft, 0));
         m.m1 = bmskClamp(max(2 * nLeft - 32, 0));
         m.hm = bmskClamp(max(nLeft - static_cast<int>(L) + 1, 0));
-        m.nv = static_cast<uint32_t>(clamp32(nLeft));
+        m.nv = static_cast<uint32_t>(clamp32(nLeft)) << 16;
         return m;
     };
     const LaneMasks fullMasks = laneMasks(W);
 
-    // One lane stages a row: 16-byte aligned source, whole 16-byte pieces.  No proxy fence is needed for
-    // the reuse of the buffer: every lane's reads of it were consumed before the __syncwarp that precedes
-    // the issue, and the mbarrier orders the copy's writes before the next reads.
-    auto issueCopy = [&](uint64_t src, uint32_t bytes, uint32_t b) {
-        mbarExpectTx(barAddr + b * 8, bytes);
-        bulkLoad(stageAddr + b * kRowStage, reinterpret_cast<const void *>(src), bytes, barAddr + b * 8);
-    };
     auto loadUnit = [&](uint32_t u, uint4 &a, uint4 &b) {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.units + u);
         a = __ldg(src); b = __ldg(src + 1);
     };
-    auto issueFirstRow = [&](uint32_t u, uint32_t b) {          // row 0 of unit u (one lane)
-        uint4 da, db;
-        loadUnit(u, da, db);
-        const uint64_t addr = seqBase + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32));
+    // the lane's 32 bytes of the 16-byte aligned span of a row; lanes past the row keep what they hold
+    // (everything past the row is masked), so nothing is read more than 32 bytes past a row's end
+    uint4 c0 = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u), c1 = c0;
+    auto loadRow = [&](uint64_t addr, uint32_t len) {
         const uint32_t skew = static_cast<uint32_t>(addr) & 15u;
-        issueCopy(addr - skew, (skew + min(W, da.w - da.z) + 15u) & ~15u, b);
+        if (laneOff < skew + len) {
+            const uint64_t src = addr - skew + laneOff;
+            ldStream(c0, src);
+            ldStream(c1, src + 16);
+        }
     };
 
-    uint32_t phase = 0, buf = 0;                               // phase bit b: parity to wait for on buffer b
     uint32_t u = blockIdx.x * kRowWarps + warp;
     if (u >= nUnits) return;
-    if (lane == 0) issueFirstRow(u, 0);
+    uint4 da, db;
+    loadUnit(u, da, db);
+    loadRow(seqBase + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32)), min(W, da.w - da.z));
 
-    for (; u < nUnits; u += totalWarps) {
-        uint4 da, db;
-        loadUnit(u, da, db);
+    for (;;) {
         uint64_t rowAddr = seqBase + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32));
         uint32_t rel = da.z;                                   // item position of the window start
         uint32_t remaining = da.w - da.z;                      // bases from the window start to the end of the contig
         const uint32_t termEnd = da.w > T ? da.w - T : 0u;     // "terminal": pos <= T || pos >= n - T (src/teloscope.cpp:403-406,451-459)
         const uint32_t nRows = db.z;
-        // lane r holds the staging parameters of row r of this unit (rows are W bases apart)
-        const uint64_t myAddr = rowAddr + static_cast<uint64_t>(lane) * W;
-        const uint32_t mySkew = static_cast<uint32_t>(myAddr) & 15u;
-        const uint32_t myBytes = (mySkew + min(W, remaining - lane * W) + 15u) & ~15u;
-        const uint64_t mySrc = myAddr - mySkew;
+        const uint32_t uNext = u + totalWarps;
+        uint64_t nextAddr = 0;                                 // first row of this warp's next unit
+        uint32_t nextLen = 0;
+        if (uNext < nUnits) {
+            const uint4 na = __ldg(reinterpret_cast<const uint4 *>(p.units + uNext));
+            nextAddr = seqBase + (static_cast<uint64_t>(na.x) | (static_cast<uint64_t>(na.y) << 32));
+            nextLen = min(W, na.w - na.z);
+        }
+        uint8_t *slotBytesPtr = reinterpret_cast<uint8_t *>(p.slots) + static_cast<size_t>(db.y) * slotBytes;
         uint32_t ovRows = 0;                                   // bit r: row r spilled into an overflow chunk
 
 #pragma unroll 1
         for (uint32_t r = 0; r < nRows; ++r) {
             const uint32_t rowLen = min(W, remaining);
-            // ---- look-ahead: stage the next row of this warp ----------------------------------------------
-            __syncwarp();                                       // every lane is done with the other buffer, the queue and the 2-bit copy
-            if (r + 1 < nRows) {
-                if (lane == r + 1) issueCopy(mySrc, myBytes, buf ^ 1u);
-            } else if (lane == 0 && u + totalWarps < nUnits) {
-                issueFirstRow(u + totalWarps, buf ^ 1u);
-            }
             const uint32_t skew = static_cast<uint32_t>(rowAddr) & 15u;
-            const uint32_t stage = stageAddr + buf * kRowStage;
-            mbarWait(barAddr + buf * 8, (phase >> buf) & 1u);
-            phase ^= 1u << buf;
 
-            // ---- 1. load, pack, validate, remove the skew -----------------------------------------------------
-            uint32_t X0, X1, X2;
+            // ---- 1. pack + validate the row that has landed, then re-arm the registers with the next row -------
+            uint32_t P0, P1;
             bool bad;
             {
-                uint4 c0, c1;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0.x), "=r"(c0.y), "=r"(c0.z), "=r"(c0.w) : "r"(stage + laneOff));
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(c1.x), "=r"(c1.y), "=r"(c1.z), "=r"(c1.w) : "r"(stage + laneOff));
                 ValidAcc va;
-                const uint32_t P0 = pack16v(c0, va), P1 = pack16v(c1, va);
+                P0 = pack16v(c0, va);
+                P1 = pack16v(c1, va);
                 bad = va.bad() != 0 && laneOff < rowLen + skew;
-                uint32_t P2 = __shfl_down_sync(0xFFFFFFFFu, P0, 1), P3 = __shfl_down_sync(0xFFFFFFFFu, P1, 1);
-                if (lane == 31) { P2 = 0; P3 = 0; }
-                const uint32_t sh = 2u * skew;
-                X0 = __funnelshift_r(P0, P1, sh);
-                X1 = __funnelshift_r(P1, P2, sh);
-                X2 = __funnelshift_r(P2, P3, sh);
             }
+            if (r + 1 < nRows) loadRow(rowAddr + W, min(W, remaining - W));
+            else if (nextLen) loadRow(nextAddr, nextLen);
+
+            // ---- 2. remove the skew: X0 X1 X2 = the lane's 32 bases and the 16 that follow -------------------
+            const uint32_t sh = 2u * skew;
+            const uint32_t X0 = __funnelshift_r(P0, P1, sh);
+            const uint32_t X1 = __funnelshift_r(P1, __shfl_down_sync(0xFFFFFFFFu, P0, 1), sh);
+            const uint32_t X2 = __shfl_down_sync(0xFFFFFFFFu, X0, 1);      // lane 31: bases past any row, masked below
             LaneMasks lm = fullMasks;
             if (rowLen != W) lm = laneMasks(rowLen);            // warp-uniform: the last window of a contig
             const bool anyBad = __any_sync(0xFFFFFFFFu, bad);
-            uint4 slow = make_uint4(0u, 0u, 0u, 0u);            // x: bitmap of the lane's bases outside ACGTacgt, y / z: A|C<<16, G|T<<16
-            if (anyBad) slow = slowRow(smem + (stage - winBase - kWindowBase) + skew + laneOff, static_cast<int>(lm.nv));
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pkAddr + lane * 8), "r"(X0), "r"(X1) : "memory");
+            uint4 slow = make_uint4(0u, 0u, 0u, 0u);
+            if (anyBad) slow = slowRow(reinterpret_cast<const uint8_t *>(rowAddr + laneOff), static_cast<int>(lm.nv >> 16));
+            __syncwarp();                                       // the previous row's emission has read the queue and the 2-bit copy
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(wb + kPkOff + lane * 8), "r"(X0), "r"(X1) : "memory");
 
-            // ---- 2. one table byte per NPOS start positions ---------------------------------------------------
+            // ---- 3. one table byte per NPOS start positions ---------------------------------------------------
             uint32_t H = 0;
             {
                 const uint32_t Xv[4] = {X0, X1, X2, 0u};
                 constexpr int kProbes = (kRowSpan + NPOS - 1) / NPOS;
 #pragma unroll
                 for (int tl = 0; tl < kProbes; ++tl) {
-                    const int bit = 2 * NPOS * tl, wi = bit >> 5, sh = bit & 31;
-                    const uint32_t x = sh == 0 ? Xv[wi] : (sh <= 16 ? Xv[wi] >> sh : __funnelshift_r(Xv[wi], Xv[wi + 1], sh));
-                    const uint32_t e = ldsU8((x & 0xFFFFu) | idxBase);
+                    const int bit = 2 * NPOS * tl, wi = bit >> 5, s = bit & 31;
+                    const uint32_t x = s == 0 ? Xv[wi] : (s <= 16 ? Xv[wi] >> s : __funnelshift_r(Xv[wi], Xv[wi + 1], s));
+                    const uint32_t e = ldsU8((x & 0xFFFFu) + kIdxBase);
                     H = e * (1u << (NPOS * tl)) + H;              // disjoint bit fields: add == or (bits >= 32 drop out)
                 }
             }
-            // ---- 3. matches never cross the window end (src/teloscope.cpp:439) --------------------------------
+            // ---- 4. matches never cross the window end (src/teloscope.cpp:439) --------------------------------
             H &= lm.hm;
             if (anyBad) {
                 uint32_t invN = __shfl_down_sync(0xFFFFFFFFu, slow.x, 1);
@@ -317,65 +278,81 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 H &= ~dead;
             }
 
-            // ---- 4. A/C/G/T of the window ---------------------------------------------------------------------
-            uint32_t sumAC = 0, sumGT = 0;
+            // ---- 5. A/C/G/T of the window: packed partial sums (nE = C + G, nO = G + T, nG, bases) -------------
+            uint32_t sum1 = 0, sum2 = 0;
             if (COUNT) {
                 const uint32_t Y0 = X0 & lm.m0, Y1 = X1 & lm.m1;
                 const uint32_t e = (Y0 & 0x55555555u) | ((Y1 << 1) & 0xAAAAAAAAu);    // code bit 0: C or G
                 const uint32_t o = ((Y0 >> 1) & 0x55555555u) | (Y1 & 0xAAAAAAAAu);    // code bit 1: G or T
-                const uint32_t nE = __popc(e), nO = __popc(o), nG = __popc(e & o);
-                uint32_t totAC = (lm.nv - nE - nO + nG) | ((nE - nG) << 16);
-                uint32_t totGT = nG | ((nO - nG) << 16);
-                if (anyBad) { totAC = slow.y; totGT = slow.z; }
-                sumAC = __reduce_add_sync(0xFFFFFFFFu, totAC);
-                sumGT = __reduce_add_sync(0xFFFFFFFFu, totGT);
+                uint32_t t1 = __popc(e) + (__popc(o) << 16);
+                uint32_t t2 = __popc(e & o) + lm.nv;
+                if (anyBad) { t1 = slow.y; t2 = slow.z; }
+                sum1 = __reduce_add_sync(0xFFFFFFFFu, t1);
+                sum2 = __reduce_add_sync(0xFFFFFFFFu, t2);
             }
 
-            // ---- 5. compaction and emission -------------------------------------------------------------------
-            uint2 *slot = reinterpret_cast<uint2 *>(p.slots) + static_cast<size_t>(db.y + r) * p.slotCap;
-            const bool rowHasTerm = rel <= T || rel + rowLen > termEnd;          // warp-uniform
-            uint32_t wMatches = 0, ovBase = kNoOverflow, rowNct = 0, nCan = 0, nFwd = 0;
+            // ---- 6. compaction and emission -------------------------------------------------------------------
+            uint2 *slot = reinterpret_cast<uint2 *>(slotBytesPtr);
+            const bool rowHasTerm = rel <= T || rel + rowLen > termEnd;                         // warp-uniform
+            const bool rowAllTerm = rel + rowLen <= T + 1u || rel >= termEnd;                   // warp-uniform
+            const uint32_t recHiRow = recHi | (rowAllTerm ? static_cast<uint32_t>(kMatchTerm) << 16 : 0u);
+            uint32_t wMatches = 0, ovBase = kNoOverflow, rowNct = 0, flagSum = 0;               // flagSum: 2 * forward + (canonical << 17)
             auto emitRange = [&](uint32_t total) {              // queue[0, total) holds row positions, ascending
+                if (wMatches + total <= p.slotCap && (rowAllTerm || !rowHasTerm)) {
+                    // common case: the slot has room and "terminal" is the same for the whole row
+                    uint32_t qa = wb + kQueueOff + lane * 2;
+                    uint2 *out = slot + wMatches + lane;
+                    int left = static_cast<int>(total) - static_cast<int>(lane);
+#pragma unroll 1
+                    for (uint32_t from = 0; from < total; from += 32, left -= 32, qa += 64, out += 32) {
+                        uint32_t f = 0;
+                        if (left > 0) {
+                            const uint32_t qq = ldsU16(qa);
+                            const uint32_t wa = ((qq >> 2) & 0xFCu) | wb;
+                            const uint32_t key = __funnelshift_r(lds32(wa + kPkOff), lds32(wa + kPkOff + 4), qq * 2u) & keyMask;
+                            f = ldsU8(key + kFlagBase);      // bit0 hit, bit1 forward, bit2 canonical
+                            *out = make_uint2(rel + qq, (f & 6u) * 32768u + recHiRow);
+                        }
+                        flagSum += __reduce_add_sync(0xFFFFFFFFu, (f * 0x8001u) & 0x20002u);
+                    }
+                    wMatches += total;
+                    return;
+                }
                 const bool roomy = wMatches + total <= p.slotCap;           // warp-uniform
                 if (!roomy && ovBase == kNoOverflow) {
                     if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
                     ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
                 }
-                uint2 *out = slot + wMatches;
 #pragma unroll 1
                 for (uint32_t from = 0; from < total; from += 32) {
                     const uint32_t idx = from + lane;
                     uint32_t f = 0;
                     bool term = false;
                     if (idx < total) {
-                        const uint32_t qq = ldsU16(qAddr + idx * 2);
-                        const uint32_t wa = pkAddr + ((qq >> 2) & ~3u), sh = (qq & 15u) * 2u;
-                        const uint32_t key = __funnelshift_r(lds32(wa), lds32(wa + 4), sh) & keyMask;
-                        f = ldsU8(flagBase + key);        // bit0 hit, bit1 forward, bit2 canonical
+                        const uint32_t qq = ldsU16(wb + kQueueOff + idx * 2);
+                        const uint32_t wa = ((qq >> 2) & 0xFCu) | wb;
+                        const uint32_t key = __funnelshift_r(lds32(wa + kPkOff), lds32(wa + kPkOff + 4), qq * 2u) & keyMask;
+                        f = ldsU8(key + kFlagBase);
                         const uint32_t pos = rel + qq;
                         term = pos <= T || pos >= termEnd;
-                        const uint32_t fl = ((f >> 1) & 3u) | (term ? static_cast<uint32_t>(kMatchTerm) : 0u);
-                        const uint2 rec = make_uint2(pos, fl * 65536u + recHi);
-                        if (roomy) out[idx] = rec;
-                        else {
-                            const uint32_t o = wMatches + idx;
-                            if (o < p.slotCap) slot[o] = rec;
-                            else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap)
-                                reinterpret_cast<uint2 *>(p.ovArena)[ovBase + (o - p.slotCap)] = rec;
-                        }
+                        const uint2 rec = make_uint2(pos, (f & 6u) * 32768u + (term ? static_cast<uint32_t>(kMatchTerm) << 16 : 0u) + recHi);
+                        const uint32_t o = wMatches + idx;
+                        if (o < p.slotCap) slot[o] = rec;
+                        else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap)
+                            reinterpret_cast<uint2 *>(p.ovArena)[ovBase + (o - p.slotCap)] = rec;
                     }
-                    nFwd += __popc(__ballot_sync(0xFFFFFFFFu, (f & 2u) != 0));
-                    nCan += __popc(__ballot_sync(0xFFFFFFFFu, (f & 4u) != 0));
-                    if (rowHasTerm) rowNct += __popc(__ballot_sync(0xFFFFFFFFu, term && (f & 5u) == 1u));
+                    flagSum += __reduce_add_sync(0xFFFFFFFFu, (f * 0x8001u) & 0x20002u);
+                    rowNct += __popc(__ballot_sync(0xFFFFFFFFu, term && (f & 5u) == 1u));
                 }
                 wMatches += total;
             };
-            auto scatter = [&](uint32_t bits, uint32_t o) {
-                uint32_t a = qAddr + o * 2;
-                while (bits) {
-                    const int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(laneOff + b) : "memory");
+            auto scatter = [&](uint32_t bits, uint32_t o) {     // the lane's starts, ascending, to queue[o ...)
+                uint32_t a = wb + kQueueOff + o * 2;
+                uint32_t rb = __brev(bits);                     // leading bit of the reversed map = lowest start
+                while (rb) {
+                    const uint32_t c = __clz(rb);
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(laneOff + c) : "memory");
+                    rb &= ~(0x80000000u >> c);
                     a += 2;
                 }
             };
@@ -400,28 +377,31 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 }
             }
 
-            // ---- 6. the row's results wait in shared memory for the unit epilogue ----------------------------------
+            // ---- 7. the row's results wait in shared memory for the unit epilogue ----------------------------------
+            const uint32_t nFwd = (flagSum & 0x1FFFFu) >> 1, nCan = flagSum >> 17;
+            if (rowAllTerm) rowNct = wMatches - nCan;
             if (lane == 0) {
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(recAddr + r * 16), "r"(sumAC), "r"(sumGT),
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sum1), "r"(sum2),
                              "r"(wMatches | (nCan << 16)), "r"(nFwd | (rowNct << 16)) : "memory");
-                if (ovBase != kNoOverflow) asm volatile("st.shared.u32 [%0], %1;" ::"r"(recAddr + kRowsPerUnit * 16 + r * 4), "r"(ovBase) : "memory");
+                if (ovBase != kNoOverflow) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wb + kRecOff + kRowsPerUnit * 16 + r * 4), "r"(ovBase) : "memory");
             }
             if (ovBase != kNoOverflow) ovRows |= 1u << r;
-            buf ^= 1u;
             rowAddr += W; rel += W; remaining -= W;
+            slotBytesPtr += slotBytes;
         }
         // ---- unit epilogue: lane r writes row r's window counters and slot bookkeeping (three 16-byte stores);
         //      per-tile and per-item totals as a handful of atomics ------------------------------------------------
         __syncwarp();
         uint32_t k2 = 0, k3 = 0;                               // all | canonical << 16, forward | terminal non-canonical << 16
         if (lane < nRows) {
-            uint32_t ac, gt;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ac), "=r"(gt), "=r"(k2), "=r"(k3) : "r"(recAddr + lane * 16));
+            uint32_t s1, s2;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(s1), "=r"(s2), "=r"(k2), "=r"(k3) : "r"(wb + kRecOff + lane * 16));
             uint32_t ov = kNoOverflow;
-            if ((ovRows >> lane) & 1u) ov = lds32(recAddr + kRowsPerUnit * 16 + lane * 4);
+            if ((ovRows >> lane) & 1u) ov = lds32(wb + kRecOff + kRowsPerUnit * 16 + lane * 4);
             const uint32_t all = k2 & 0xFFFFu, can = k2 >> 16, fwd = k3 & 0xFFFFu, nct = k3 >> 16;
+            const uint32_t nE = s1 & 0xFFFFu, nO = s1 >> 16, nG = s2 & 0xFFFFu, nV = s2 >> 16;
             uint4 *wp = p.windows + 2 * static_cast<size_t>(db.x + lane);
-            wp[0] = make_uint4(ac & 0xFFFFu, ac >> 16, gt & 0xFFFFu, gt >> 16);
+            wp[0] = make_uint4(nV - nE - nO + nG, nE - nG, nG, nO - nG);        // A, C, G, T
             wp[1] = make_uint4(can * L, (all - can) * L, fwd * L, (all - fwd) * L);
             p.slotMeta[db.y + lane] = make_uint4(all, ov, can, nct);
         }
@@ -439,6 +419,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 if (v) atomicAdd(ic + (lane - 3), v);
             }
         }
+        if (uNext >= nUnits) break;
+        u = uNext;
+        loadUnit(u, da, db);
     }
 }
 

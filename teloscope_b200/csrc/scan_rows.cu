@@ -46,20 +46,23 @@ namespace {
 __device__ __forceinline__ uint32_t smemAddr(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-// streaming 16-byte load: every base is read once, nothing of it belongs in L1
-__device__ __forceinline__ void ldStream(uint4 &v, uint64_t addr) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(addr));
+// Streaming loads of a lane's 32 bytes (every base is read once, nothing of it belongs in L1), done only
+// when a < b; otherwise the registers keep what they hold.
+__device__ __forceinline__ void ldStream32If(uint4 &v0, uint4 &v1, uint64_t addr, uint32_t a, uint32_t b) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.lt.u32 p, %9, %10;\n"
+        "@p ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%8];\n"
+        "@p ld.global.nc.L1::no_allocate.v4.u32 {%4,%5,%6,%7}, [%8+16];\n"
+        "}\n"
+        : "+r"(v0.x), "+r"(v0.y), "+r"(v0.z), "+r"(v0.w), "+r"(v1.x), "+r"(v1.y), "+r"(v1.z), "+r"(v1.w)
+        : "l"(addr), "r"(a), "r"(b));
 }
-__device__ __forceinline__ uint32_t ldsU8(uint32_t addr) {      // the tables never change during the kernel
-    uint32_t v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t ldsU16(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
+__device__ __forceinline__ uint32_t bfind(uint32_t v) {         // position of the highest set bit (FLO)
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
@@ -111,17 +114,27 @@ __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane) {
 // kWindowBase bytes into it on sm_100 (checked at run time: status 1 otherwise), so every address below
 // is a compile-time constant and goes into the instruction as an immediate. -------------------------------
 constexpr uint32_t kWindowBase = 0x400;
-constexpr uint32_t kWarpBlk = 1024;                        // per warp: 2-bit copy of the row | row results of the unit | match queue
-constexpr uint32_t kPkOff = 0;                             //   66 words (64 + pad)
-constexpr uint32_t kRecOff = 272;                          //   8 x 16 bytes of window / slot results + 8 overflow bases
-constexpr uint32_t kQueueOff = 512;                        //   kRowQueueCap u16 entries
-static_assert(kRecOff + kRowsPerUnit * 20 <= kQueueOff && kQueueOff + kRowQueueCap * 2 <= kWarpBlk, "per-warp block");
-constexpr uint32_t kWarpBase = kWindowBase;                               // 32 KiB of warp blocks (1 KiB aligned)
+constexpr uint32_t kWarpBlk = 256;                         // per warp: row results of the unit in flight
+constexpr uint32_t kRecOff = 0;                            //   8 x 16 bytes of window / slot results + 8 overflow bases
+static_assert(kRecOff + kRowsPerUnit * 20 <= kWarpBlk, "per-warp block");
+constexpr uint32_t kWarpBase = kWindowBase;                               // 8 KiB of warp blocks
 constexpr uint32_t kFlagBase = kWarpBase + kRowWarps * kWarpBlk;          // 16 KiB flag table
-constexpr uint32_t kIdxBase = 0x10000u;                                   // 64 KiB 8-mer table on a 64 KiB boundary
+constexpr uint32_t kIdxBase = 0x10000u;                                   // 64 KiB 8-mer table
 static_assert(kFlagBase + kFastFlagBytes <= kIdxBase, "front region must end before the 8-mer table");
 constexpr uint32_t kRowSmemTotal = kIdxBase + 65536u - kWindowBase;
 static_assert(kRowSmemTotal <= 232448u, "shared memory budget of one SM");
+
+// the tables never change during the kernel: plain asm (may be scheduled freely), address = index + immediate
+__device__ __forceinline__ uint32_t ldsU8Idx(uint32_t key) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(key), "n"(kIdxBase));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldsU8Flag(uint32_t key) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(key), "n"(kFlagBase));
+    return v;
+}
 
 // Slow exact path of a row that holds a byte outside ACGTacgt (IUPAC letters, '\r', ...): per-lane
 // bitmap of such bases in row coordinates and the counts of the lane's valid bases, in the packed form
@@ -141,6 +154,35 @@ __device__ __noinline__ uint4 slowRow(const uint8_t *row, int nValid) {
     return make_uint4(inv, (c + g) | ((g + t) << 16), g | ((a + c + g + t) << 16), 0u);
 }
 
+// A row that is shorter than the window (the last one of a contig) and / or holds a byte outside ACGTacgt:
+// the lane's match starts H (computed with the masks of a full window) and its packed A/C/G/T partial sums
+// are redone exactly.  Called by the whole warp.
+__device__ __noinline__ uint4 fixRow(uint32_t H, uint32_t X0, uint32_t X1, const uint8_t *laneRow, uint32_t rowLen, uint32_t L,
+                                     bool anyBad, bool count) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const int nLeft = static_cast<int>(rowLen) - static_cast<int>(lane * kRowSpan);
+    const uint32_t nv = static_cast<uint32_t>(clamp32(nLeft));
+    H &= bmskClamp(max(nLeft - static_cast<int>(L) + 1, 0));
+    uint32_t t1 = 0, t2 = 0;
+    if (count) {
+        const uint32_t Y0 = X0 & bmskClamp(max(2 * nLeft, 0)), Y1 = X1 & bmskClamp(max(2 * nLeft - 32, 0));
+        const uint32_t e = (Y0 & 0x55555555u) | ((Y1 << 1) & 0xAAAAAAAAu);
+        const uint32_t o = ((Y0 >> 1) & 0x55555555u) | (Y1 & 0xAAAAAAAAu);
+        t1 = __popc(e) + (__popc(o) << 16);
+        t2 = __popc(e & o) + (nv << 16);
+    }
+    if (anyBad) {
+        const uint4 slow = slowRow(laneRow, static_cast<int>(nv));
+        uint32_t invN = __shfl_down_sync(0xFFFFFFFFu, slow.x, 1);
+        if (lane == 31) invN = 0;
+        uint32_t dead = slow.x;
+        for (uint32_t j = 1; j < L; ++j) dead |= __funnelshift_r(slow.x, invN, j);
+        H &= ~dead;
+        t1 = slow.y; t2 = slow.z;
+    }
+    return make_uint4(H, t1, t2, 0u);
+}
+
 }  // namespace
 
 template <int NPOS, bool COUNT>
@@ -152,13 +194,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
         if (tid == 0 && blockIdx.x == 0) atomicExch(p.status, 1u);
         return;
     }
-    const uint32_t wb = kWarpBase + warp * kWarpBlk;       // this warp's block (1 KiB aligned: offsets can be OR-ed in)
+    const uint32_t wb = kWarpBase + warp * kWarpBlk;       // this warp's block of row results
 
-    // ---- one-time setup ---------------------------------------------------------------------------
+    // ---- one-time setup: the 8-mer table as it is; the flag table re-coded for the emission loop:
+    //      bit0 forward, bit1 canonical (= DevMatch flags), bit7 canonical again (count field, see below) ------
     for (int i = tid; i < 65536 / 16; i += kRowThreads)
         reinterpret_cast<uint4 *>(smem + (kIdxBase - kWindowBase))[i] = reinterpret_cast<const uint4 *>(p.index8)[i];
-    for (uint32_t i = tid; i < p.flagTabBytes / 16; i += kRowThreads)
-        reinterpret_cast<uint4 *>(smem + (kFlagBase - kWindowBase))[i] = reinterpret_cast<const uint4 *>(p.flagTab)[i];
+    for (uint32_t i = tid; i < p.flagTabBytes / 4; i += kRowThreads) {
+        const uint32_t f = reinterpret_cast<const uint32_t *>(p.flagTab)[i];   // per byte: bit0 hit, bit1 forward, bit2 canonical
+        reinterpret_cast<uint32_t *>(smem + (kFlagBase - kWindowBase))[i] = ((f >> 1) & 0x03030303u) | ((f & 0x04040404u) << 5);
+    }
     __syncthreads();
 
     const uint32_t L = p.patLen, W = p.cfg.windowSize, T = p.cfg.terminalLimit;
@@ -169,11 +214,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     const uint32_t laneOff = lane * kRowSpan;
     const uint64_t seqBase = reinterpret_cast<uint64_t>(p.seq);
     const uint32_t slotBytes = p.slotCap * 8u;
+    const bool lane0 = lane == 0;
 
     // Per-lane masks of a row of rowLen bases: the lane's valid 2-bit fields in X0 / X1, its valid match
-    // starts (a match never crosses the window end, src/teloscope.cpp:439) and its number of bases.
-    // A full window has the same masks in every row, so they are computed once (only the last window of
-    // a contig is shorter).
+    // starts (a match never crosses the window end, src/teloscope.cpp:439) and its number of bases << 16.
+    // A full window has the same masks in every row; the last window of a contig is shorter and applies
+    // its own (a subset) on top.
     struct LaneMasks { uint32_t m0, m1, hm, nv; };
     auto laneMasks = [&](uint32_t rowLen) {
         const int nLeft = static_cast<int>(rowLen) - static_cast<int>(laneOff);
@@ -184,76 +230,71 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
         m.nv = static_cast<uint32_t>(clamp32(nLeft)) << 16;
         return m;
     };
-    const LaneMasks fullMasks = laneMasks(W);
+    const LaneMasks fm = laneMasks(W);
 
     auto loadUnit = [&](uint32_t u, uint4 &a, uint4 &b) {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.units + u);
         a = __ldg(src); b = __ldg(src + 1);
     };
-    // the lane's 32 bytes of the 16-byte aligned span of a row; lanes past the row keep what they hold
-    // (everything past the row is masked), so nothing is read more than 32 bytes past a row's end
+    // The lane's 32 bytes of the 16-byte aligned span of a row whose first base is at rowAddr:
+    // ((rowAddr + laneOff) & ~15) since laneOff is a multiple of 16.  Lanes past the row keep what they
+    // hold (everything past the row is masked); nothing is read more than 47 bytes past a row's end.
     uint4 c0 = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u), c1 = c0;
-    auto loadRow = [&](uint64_t addr, uint32_t len) {
-        const uint32_t skew = static_cast<uint32_t>(addr) & 15u;
-        if (laneOff < skew + len) {
-            const uint64_t src = addr - skew + laneOff;
-            ldStream(c0, src);
-            ldStream(c1, src + 16);
-        }
+    auto loadRow = [&](uint64_t laneRowAddr, uint32_t len) {
+        ldStream32If(c0, c1, laneRowAddr & ~static_cast<uint64_t>(15), laneOff, len + 15u);
     };
 
     uint32_t u = blockIdx.x * kRowWarps + warp;
     if (u >= nUnits) return;
     uint4 da, db;
     loadUnit(u, da, db);
-    loadRow(seqBase + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32)), min(W, da.w - da.z));
+    loadRow(seqBase + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32)) + laneOff, min(W, da.w - da.z));
 
     for (;;) {
-        uint64_t rowAddr = seqBase + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32));
+        // laneAddr: address of the lane's first base of the current row (its low 4 bits are the row's skew)
+        uint64_t laneAddr = seqBase + (static_cast<uint64_t>(da.x) | (static_cast<uint64_t>(da.y) << 32)) + laneOff;
         uint32_t rel = da.z;                                   // item position of the window start
-        uint32_t remaining = da.w - da.z;                      // bases from the window start to the end of the contig
-        const uint32_t termEnd = da.w > T ? da.w - T : 0u;     // "terminal": pos <= T || pos >= n - T (src/teloscope.cpp:403-406,451-459)
+        const uint32_t itemLen = da.w;
+        const uint32_t termEnd = itemLen > T ? itemLen - T : 0u;   // "terminal": pos <= T || pos >= n - T (src/teloscope.cpp:403-406,451-459)
         const uint32_t nRows = db.z;
         const uint32_t uNext = u + totalWarps;
-        uint64_t nextAddr = 0;                                 // first row of this warp's next unit
-        uint32_t nextLen = 0;
+        uint64_t nextAddr = 0;                                 // the lane's first base of the first row of this warp's next unit
+        uint32_t nextLim = 0;                                  // its length + 15 (lanes below it load), 0: there is none
         if (uNext < nUnits) {
             const uint4 na = __ldg(reinterpret_cast<const uint4 *>(p.units + uNext));
-            nextAddr = seqBase + (static_cast<uint64_t>(na.x) | (static_cast<uint64_t>(na.y) << 32));
-            nextLen = min(W, na.w - na.z);
+            nextAddr = seqBase + (static_cast<uint64_t>(na.x) | (static_cast<uint64_t>(na.y) << 32)) + laneOff;
+            nextLim = min(W, na.w - na.z) + 15u;
         }
-        uint8_t *slotBytesPtr = reinterpret_cast<uint8_t *>(p.slots) + static_cast<size_t>(db.y) * slotBytes;
+        uint8_t *slotPtr = reinterpret_cast<uint8_t *>(p.slots) + static_cast<size_t>(db.y) * slotBytes;
         uint32_t ovRows = 0;                                   // bit r: row r spilled into an overflow chunk
 
 #pragma unroll 1
         for (uint32_t r = 0; r < nRows; ++r) {
-            const uint32_t rowLen = min(W, remaining);
-            const uint32_t skew = static_cast<uint32_t>(rowAddr) & 15u;
+            const uint32_t remaining = itemLen - rel;
+            const bool partial = remaining < W;                 // warp-uniform: the last window of a contig
+            const uint32_t skew = static_cast<uint32_t>(laneAddr) & 15u;
 
             // ---- 1. pack + validate the row that has landed, then re-arm the registers with the next row -------
-            uint32_t P0, P1;
-            bool bad;
+            uint32_t P0, P1, badBits;
             {
                 ValidAcc va;
                 P0 = pack16v(c0, va);
                 P1 = pack16v(c1, va);
-                bad = va.bad() != 0 && laneOff < rowLen + skew;
+                badBits = va.bad();                             // stale lanes past a short row hold bytes that were valid or already took the slow path
             }
-            if (r + 1 < nRows) loadRow(rowAddr + W, min(W, remaining - W));
-            else if (nextLen) loadRow(nextAddr, nextLen);
+            {
+                const bool inUnit = r + 1 < nRows;
+                const uint64_t na = inUnit ? laneAddr + W : nextAddr;
+                const uint32_t nl = inUnit ? min(W, remaining - W) + 15u : nextLim;
+                ldStream32If(c0, c1, na & ~static_cast<uint64_t>(15), laneOff, nl);
+            }
 
             // ---- 2. remove the skew: X0 X1 X2 = the lane's 32 bases and the 16 that follow -------------------
             const uint32_t sh = 2u * skew;
             const uint32_t X0 = __funnelshift_r(P0, P1, sh);
             const uint32_t X1 = __funnelshift_r(P1, __shfl_down_sync(0xFFFFFFFFu, P0, 1), sh);
             const uint32_t X2 = __shfl_down_sync(0xFFFFFFFFu, X0, 1);      // lane 31: bases past any row, masked below
-            LaneMasks lm = fullMasks;
-            if (rowLen != W) lm = laneMasks(rowLen);            // warp-uniform: the last window of a contig
-            const bool anyBad = __any_sync(0xFFFFFFFFu, bad);
-            uint4 slow = make_uint4(0u, 0u, 0u, 0u);
-            if (anyBad) slow = slowRow(reinterpret_cast<const uint8_t *>(rowAddr + laneOff), static_cast<int>(lm.nv >> 16));
-            __syncwarp();                                       // the previous row's emission has read the queue and the 2-bit copy
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(wb + kPkOff + lane * 8), "r"(X0), "r"(X1) : "memory");
+            const bool anyBad = __any_sync(0xFFFFFFFFu, badBits != 0);
 
             // ---- 3. one table byte per NPOS start positions ---------------------------------------------------
             uint32_t H = 0;
@@ -264,146 +305,117 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 for (int tl = 0; tl < kProbes; ++tl) {
                     const int bit = 2 * NPOS * tl, wi = bit >> 5, s = bit & 31;
                     const uint32_t x = s == 0 ? Xv[wi] : (s <= 16 ? Xv[wi] >> s : __funnelshift_r(Xv[wi], Xv[wi + 1], s));
-                    const uint32_t e = ldsU8((x & 0xFFFFu) + kIdxBase);
+                    const uint32_t e = ldsU8Idx(x & 0xFFFFu);
                     H = e * (1u << (NPOS * tl)) + H;              // disjoint bit fields: add == or (bits >= 32 drop out)
                 }
             }
             // ---- 4. matches never cross the window end (src/teloscope.cpp:439) --------------------------------
-            H &= lm.hm;
-            if (anyBad) {
-                uint32_t invN = __shfl_down_sync(0xFFFFFFFFu, slow.x, 1);
-                if (lane == 31) invN = 0;
-                uint32_t dead = slow.x;
-                for (uint32_t j = 1; j < L; ++j) dead |= __funnelshift_r(slow.x, invN, j);
-                H &= ~dead;
-            }
+            H &= fm.hm;
 
             // ---- 5. A/C/G/T of the window: packed partial sums (nE = C + G, nO = G + T, nG, bases) -------------
-            uint32_t sum1 = 0, sum2 = 0;
+            uint32_t t1 = 0, t2 = 0;
             if (COUNT) {
-                const uint32_t Y0 = X0 & lm.m0, Y1 = X1 & lm.m1;
+                const uint32_t Y0 = X0 & fm.m0, Y1 = X1 & fm.m1;
                 const uint32_t e = (Y0 & 0x55555555u) | ((Y1 << 1) & 0xAAAAAAAAu);    // code bit 0: C or G
                 const uint32_t o = ((Y0 >> 1) & 0x55555555u) | (Y1 & 0xAAAAAAAAu);    // code bit 1: G or T
-                uint32_t t1 = __popc(e) + (__popc(o) << 16);
-                uint32_t t2 = __popc(e & o) + lm.nv;
-                if (anyBad) { t1 = slow.y; t2 = slow.z; }
+                t1 = __popc(e) + (__popc(o) << 16);
+                t2 = __popc(e & o) + fm.nv;
+            }
+            if (partial || anyBad) {                            // rare, warp-uniform: the exact path redoes H, t1, t2
+                const uint4 fx = fixRow(H, X0, X1, reinterpret_cast<const uint8_t *>(laneAddr), min(W, remaining), L, anyBad, COUNT);
+                H = fx.x; t1 = fx.y; t2 = fx.z;
+            }
+            uint32_t sum1 = 0, sum2 = 0;
+            if (COUNT) {
                 sum1 = __reduce_add_sync(0xFFFFFFFFu, t1);
                 sum2 = __reduce_add_sync(0xFFFFFFFFu, t2);
             }
 
-            // ---- 6. compaction and emission -------------------------------------------------------------------
-            uint2 *slot = reinterpret_cast<uint2 *>(slotBytesPtr);
-            const bool rowHasTerm = rel <= T || rel + rowLen > termEnd;                         // warp-uniform
-            const bool rowAllTerm = rel + rowLen <= T + 1u || rel >= termEnd;                   // warp-uniform
-            const uint32_t recHiRow = recHi | (rowAllTerm ? static_cast<uint32_t>(kMatchTerm) << 16 : 0u);
-            uint32_t wMatches = 0, ovBase = kNoOverflow, rowNct = 0, flagSum = 0;               // flagSum: 2 * forward + (canonical << 17)
-            auto emitRange = [&](uint32_t total) {              // queue[0, total) holds row positions, ascending
-                if (wMatches + total <= p.slotCap && (rowAllTerm || !rowHasTerm)) {
-                    // common case: the slot has room and "terminal" is the same for the whole row
-                    uint32_t qa = wb + kQueueOff + lane * 2;
-                    uint2 *out = slot + wMatches + lane;
-                    int left = static_cast<int>(total) - static_cast<int>(lane);
-#pragma unroll 1
-                    for (uint32_t from = 0; from < total; from += 32, left -= 32, qa += 64, out += 32) {
-                        uint32_t f = 0;
-                        if (left > 0) {
-                            const uint32_t qq = ldsU16(qa);
-                            const uint32_t wa = ((qq >> 2) & 0xFCu) | wb;
-                            const uint32_t key = __funnelshift_r(lds32(wa + kPkOff), lds32(wa + kPkOff + 4), qq * 2u) & keyMask;
-                            f = ldsU8(key + kFlagBase);      // bit0 hit, bit1 forward, bit2 canonical
-                            *out = make_uint2(rel + qq, (f & 6u) * 32768u + recHiRow);
-                        }
-                        flagSum += __reduce_add_sync(0xFFFFFFFFu, (f * 0x8001u) & 0x20002u);
-                    }
-                    wMatches += total;
-                    return;
-                }
-                const bool roomy = wMatches + total <= p.slotCap;           // warp-uniform
-                if (!roomy && ovBase == kNoOverflow) {
-                    if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
-                    ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
-                }
-#pragma unroll 1
-                for (uint32_t from = 0; from < total; from += 32) {
-                    const uint32_t idx = from + lane;
-                    uint32_t f = 0;
-                    bool term = false;
-                    if (idx < total) {
-                        const uint32_t qq = ldsU16(wb + kQueueOff + idx * 2);
-                        const uint32_t wa = ((qq >> 2) & 0xFCu) | wb;
-                        const uint32_t key = __funnelshift_r(lds32(wa + kPkOff), lds32(wa + kPkOff + 4), qq * 2u) & keyMask;
-                        f = ldsU8(key + kFlagBase);
-                        const uint32_t pos = rel + qq;
-                        term = pos <= T || pos >= termEnd;
-                        const uint2 rec = make_uint2(pos, (f & 6u) * 32768u + (term ? static_cast<uint32_t>(kMatchTerm) << 16 : 0u) + recHi);
-                        const uint32_t o = wMatches + idx;
-                        if (o < p.slotCap) slot[o] = rec;
-                        else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap)
-                            reinterpret_cast<uint2 *>(p.ovArena)[ovBase + (o - p.slotCap)] = rec;
-                    }
-                    flagSum += __reduce_add_sync(0xFFFFFFFFu, (f * 0x8001u) & 0x20002u);
-                    rowNct += __popc(__ballot_sync(0xFFFFFFFFu, term && (f & 5u) == 1u));
-                }
-                wMatches += total;
-            };
-            auto scatter = [&](uint32_t bits, uint32_t o) {     // the lane's starts, ascending, to queue[o ...)
-                uint32_t a = wb + kQueueOff + o * 2;
-                uint32_t rb = __brev(bits);                     // leading bit of the reversed map = lowest start
-                while (rb) {
-                    const uint32_t c = __clz(rb);
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(laneOff + c) : "memory");
-                    rb &= ~(0x80000000u >> c);
-                    a += 2;
-                }
-            };
+            // ---- 6. emission: every lane writes its own matches, in order, behind those of the lanes before it.
+            //      The match's 2L-bit key comes out of the lane's registers, the flag byte g (bit0 forward, bit1
+            //      canonical, bit7 canonical) goes into the record as it is and is summed per lane: a lane has at
+            //      most 32 matches, so forward + 2 canonical < 128 stays below the canonical count at bit 7. ----------
+            const uint32_t rowEnd = rel + min(W, remaining);
+            const bool rowHasTerm = rel <= T || rowEnd > termEnd;                               // warp-uniform
+            const bool rowAllTerm = rowEnd <= T + 1u || rel >= termEnd;                         // warp-uniform
             const uint32_t nH = __popc(H);
             const uint32_t incl = warpInclusiveScan(nH, lane);
-            const uint32_t allTotal = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (allTotal <= static_cast<uint32_t>(kRowQueueCap)) {
-                scatter(H, incl - nH);
-                __syncwarp();
-                emitRange(allTotal);
-            } else {
-                // dense row: 8 lanes (<= 256 starts) at a time, lane groups keep genome order
-                for (uint32_t part = 0; part < 4; ++part) {
-                    const uint32_t bits = (lane >> 3) == part ? H : 0u;
-                    const uint32_t n = __popc(bits);
-                    const uint32_t in2 = warpInclusiveScan(n, lane);
-                    const uint32_t total = __shfl_sync(0xFFFFFFFFu, in2, 31);
-                    __syncwarp();
-                    scatter(bits, in2 - n);
-                    __syncwarp();
-                    emitRange(total);
+            const uint32_t wMatches = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            const uint32_t relLane = rel + laneOff;
+            uint32_t acc = 0, rowNct = 0;
+            if (wMatches <= p.slotCap && (rowAllTerm || !rowHasTerm)) {
+                // common case: the slot has room and "terminal" is the same for the whole row
+                const uint32_t recHiRow = recHi | (rowAllTerm ? static_cast<uint32_t>(kMatchTerm) << 16 : 0u);
+                uint2 *out = reinterpret_cast<uint2 *>(slotPtr) + (incl - nH);
+                uint32_t bits = H;
+                while (bits) {
+                    const uint32_t t = bits & (0u - bits);
+                    const uint32_t c = bfind(t);
+                    bits ^= t;
+                    const bool lowHalf = c < 16u;
+                    const uint32_t key = __funnelshift_r(lowHalf ? X0 : X1, lowHalf ? X1 : X2, 2u * c) & keyMask;
+                    const uint32_t g = ldsU8Flag(key);
+                    *out++ = make_uint2(relLane + c, g * 65536u + recHiRow);
+                    acc += g;
                 }
+            } else {
+                uint32_t ovBase = kNoOverflow;
+                if (wMatches > p.slotCap) {
+                    if (lane0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
+                    ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
+                    if (lane0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wb + kRecOff + kRowsPerUnit * 16 + r * 4), "r"(ovBase) : "memory");
+                    ovRows |= 1u << r;
+                }
+                uint32_t o = incl - nH;
+                uint32_t bits = H;
+                while (bits) {
+                    const uint32_t t = bits & (0u - bits);
+                    const uint32_t c = bfind(t);
+                    bits ^= t;
+                    const bool lowHalf = c < 16u;
+                    const uint32_t key = __funnelshift_r(lowHalf ? X0 : X1, lowHalf ? X1 : X2, 2u * c) & keyMask;
+                    const uint32_t g = ldsU8Flag(key);
+                    const uint32_t pos = relLane + c;
+                    const bool term = pos <= T || pos >= termEnd;
+                    const uint2 rec = make_uint2(pos, g * 65536u + (term ? static_cast<uint32_t>(kMatchTerm) << 16 : 0u) + recHi);
+                    if (o < p.slotCap) reinterpret_cast<uint2 *>(slotPtr)[o] = rec;
+                    else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap)
+                        reinterpret_cast<uint2 *>(p.ovArena)[ovBase + (o - p.slotCap)] = rec;
+                    ++o;
+                    acc += g;
+                    if (term && !(g & 2u)) ++rowNct;
+                }
+                rowNct = __reduce_add_sync(0xFFFFFFFFu, rowNct);
             }
+            // forward + 2 canonical | canonical << 16, summed over the lanes
+            const uint32_t flagSum = __reduce_add_sync(0xFFFFFFFFu, (acc & 127u) | ((acc >> 7) << 16));
 
             // ---- 7. the row's results wait in shared memory for the unit epilogue ----------------------------------
-            const uint32_t nFwd = (flagSum & 0x1FFFFu) >> 1, nCan = flagSum >> 17;
-            if (rowAllTerm) rowNct = wMatches - nCan;
-            if (lane == 0) {
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sum1), "r"(sum2),
-                             "r"(wMatches | (nCan << 16)), "r"(nFwd | (rowNct << 16)) : "memory");
-                if (ovBase != kNoOverflow) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wb + kRecOff + kRowsPerUnit * 16 + r * 4), "r"(ovBase) : "memory");
+            if (lane0) {
+                const uint32_t w2 = wMatches | (rowNct << 12) | (rowAllTerm ? 0x80000000u : 0u);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sum1), "r"(sum2), "r"(w2), "r"(flagSum) : "memory");
             }
-            if (ovBase != kNoOverflow) ovRows |= 1u << r;
-            rowAddr += W; rel += W; remaining -= W;
-            slotBytesPtr += slotBytes;
+            laneAddr += W; rel += W;
+            slotPtr += slotBytes;
         }
         // ---- unit epilogue: lane r writes row r's window counters and slot bookkeeping (three 16-byte stores);
         //      per-tile and per-item totals as a handful of atomics ------------------------------------------------
         __syncwarp();
         uint32_t k2 = 0, k3 = 0;                               // all | canonical << 16, forward | terminal non-canonical << 16
         if (lane < nRows) {
-            uint32_t s1, s2;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(s1), "=r"(s2), "=r"(k2), "=r"(k3) : "r"(wb + kRecOff + lane * 16));
+            uint32_t s1, s2, w2, fs;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(s1), "=r"(s2), "=r"(w2), "=r"(fs) : "r"(wb + kRecOff + lane * 16));
             uint32_t ov = kNoOverflow;
             if ((ovRows >> lane) & 1u) ov = lds32(wb + kRecOff + kRowsPerUnit * 16 + lane * 4);
-            const uint32_t all = k2 & 0xFFFFu, can = k2 >> 16, fwd = k3 & 0xFFFFu, nct = k3 >> 16;
+            const uint32_t all = w2 & 0xFFFu, can = fs >> 16, fwd = (fs & 0xFFFFu) - 2u * can;
+            const uint32_t nct = (w2 >> 31) ? all - can : (w2 >> 12) & 0xFFFu;
             const uint32_t nE = s1 & 0xFFFFu, nO = s1 >> 16, nG = s2 & 0xFFFFu, nV = s2 >> 16;
             uint4 *wp = p.windows + 2 * static_cast<size_t>(db.x + lane);
             wp[0] = make_uint4(nV - nE - nO + nG, nE - nG, nG, nO - nG);        // A, C, G, T
             wp[1] = make_uint4(can * L, (all - can) * L, fwd * L, (all - fwd) * L);
             p.slotMeta[db.y + lane] = make_uint4(all, ov, can, nct);
+            k2 = all | (can << 16);
+            k3 = fwd | (nct << 16);
         }
         k2 = __reduce_add_sync(0xFFFFFFFFu, k2);               // <= 8 rows x 1002 per half: no carry between the halves
         k3 = __reduce_add_sync(0xFFFFFFFFu, k3);

@@ -381,10 +381,15 @@ def main():
         moved_bytes = n_bases + 32 * n_windows + 8 * n_matches
         kern_s = float(np.mean(scan_ms)) * 1e-3
         achieved = algo_bytes / kern_s / 1e9
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
+        # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the
+        # committed `ncu --set full` capture (taken on a 0.25-scale assembly of the same generator; the kernel
+        # streams, so bytes per base carry over), scaled to the bases one launch processes here.
+        traffic, traffic_src = None, None
+        tp = ROOT / "profiles" / "rows_kernel_traffic.json"
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tp.read_text())
+            traffic = int(tj["dram_bytes_per_base"] * n_bases)
+            traffic_src = f"{tj['dram_bytes_per_base']:.3f} B/base x {n_bases} bases; {tj['source']}"
         line = {
             "metric": METRIC, "value": total_bases * args.steps / elapsed / 1e9, "unit": "Gbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed / args.steps * 1e3,
@@ -399,7 +404,7 @@ def main():
             "kernel_only": {"scan_kernels_ms": float(np.mean(scan_ms)), "lean_kernel_ms": float(np.mean(stats["lean_ms"])),
                             "Gbp_per_s": n_bases / kern_s / 1e9},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "tls::rowScanKernel<3,true> (+ the two small launches that take "
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "tls::rowScanKernel<3,true> (+ the two small launches that take "
                          "contigs shorter than 8 windows); duration = all three, CUDA events on the ctx stream, mean over "
                          "the timed steps", "algorithmic_bytes": algo_bytes, "bytes_per_base": algo_bytes / n_bases,
                          "achieved_incl_intermediate_match_records": moved_bytes / kern_s / 1e9,

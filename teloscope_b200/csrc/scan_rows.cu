@@ -22,9 +22,13 @@
 //     match starts; starts whose match would cross the window end are masked (:439);
 //   * A/C/G/T: 3 popcounts on bit planes, 2 REDUX per window on packed partial sums; the four counts
 //     are derived from them once per row in the unit epilogue (:418-435);
-//   * matches: warp prefix sum, scatter into a per-warp queue, then 32 at a time: orientation /
-//     canonical flags from the 4^L table, class counts by one REDUX on a packed value (covered bp =
-//     count * L, :470-510), one coalesced 8-byte store into the row's slot of the match arena;
+//   * matches: warp prefix sum of the per-lane counts, then every lane writes its own 8-byte records,
+//     in order, behind those of the lanes before it, straight into the row's slot of the match arena
+//     (no queue, no shared copy of the row): the 2L-bit key comes out of the lane's registers, the
+//     flag byte from the re-coded 4^L table goes into the record as it is and is summed per lane; one
+//     REDUX per row turns the sums into the class counts (covered bp = count * L, :470-510).  A bulk
+//     (TMA) store of shared-staged records was measured and is slower at this granularity (about 40
+//     extra instructions per row for the fence / elect / uniform-register traffic);
 //   * a row's results (8 window counters, slot bookkeeping) wait in shared memory until the unit is
 //     done; then lane r writes row r's three 16-byte stores, and the per-tile / per-item totals leave
 //     as a handful of atomics per unit;

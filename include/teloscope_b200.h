@@ -85,6 +85,11 @@ typedef struct {
     const uint8_t *is_forward;
     const uint8_t *is_canonical;
     /* UserInputTeloscope scan parameters (include/input.h:36-48) */
+    /* 0 < step <= window_size.  step < window_size (overlapping windows, src/teloscope.cpp:409-434,
+       485,512-529) is supported for pattern tables of ONE length L with step >= L and window_size -
+       step >= L; otherwise the reference's uint32 scan start wraps (:413-415) or its match vectors
+       are not position-ordered, and tls_submit refuses TLS_MODE_GENOME batches (other modes have no
+       windows and run). */
     uint32_t window_size, step, terminal_limit;
     uint16_t max_match_dist, min_block_len, max_block_dist, min_block_counts;
     float min_block_density;

@@ -147,6 +147,7 @@ struct tls_ctx {
     DevConfig dcfg{};
     DevBuf dIndex, dFlags, dKeys, dKeyFlags;
     uint32_t slotCap = 0, ovChunk = 0;
+    std::string overlapRefusal;              // non-empty: genome-mode batches are refused (see buildDevConfig)
     bool forceGeneral = false;               // TLS_FORCE_GENERAL=1 or a lean-kernel layout failure
     bool noRowKernel = false;                // TLS_NO_ROW_KERNEL=1: 1536-base-row lean kernel instead of the window-row kernel
     uint32_t rowMinWindows = kRowMinWindows; // TLS_ROW_MIN_WINDOWS=n: shortest contig (in windows) the window-row kernel takes
@@ -186,6 +187,21 @@ int buildDevConfig(tls_ctx *ctx) {
     c.maxMatchDist = u.max_match_dist; c.minBlockLen = u.min_block_len; c.maxBlockDist = u.max_block_dist;
     c.minBlockCounts = u.min_block_counts; c.itsMinLen = t.itsMinLen; c.minBlockDensity = u.min_block_density;
     c.countAcgt = (u.outputs & TLS_OUT_ACGT) ? 1u : 0u;
+    c.overlapWindows = u.step < u.window_size ? 1u : 0u;
+    if (c.overlapWindows) {
+        // src/teloscope.cpp:413-415 computes the scan start of a non-first window as min(step - L, overlap - L) in
+        // uint32: with step < L or overlap < L it wraps and whole windows go unscanned; with several pattern lengths
+        // the reference's match vectors are ordered by the window a match ENDS in, not by position.  Neither is
+        // reproduced on the device; everything else (one pattern length, step >= L, window - step >= L) is.
+        // Windows only exist in genome mode, so the refusal waits for a genome-mode batch (tls_submit).
+        char why[160] = "";
+        if (c.nClasses != 1)
+            snprintf(why, sizeof why, "overlapping windows (step < window) need patterns of one length on the device");
+        else if (u.step < c.maxLen || u.window_size - u.step < c.maxLen)
+            snprintf(why, sizeof why, "overlapping windows need step >= %u and window - step >= %u (the pattern length)",
+                     c.maxLen, c.maxLen);
+        ctx->overlapRefusal = why;
+    }
     fillDivider(c, u.window_size);
     return TLS_OK;
 }
@@ -275,8 +291,6 @@ int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
         return fail(TLS_ERR_INVALID, "empty pattern table");
     if (cfg->window_size == 0 || cfg->step == 0 || cfg->step > cfg->window_size)
         return fail(TLS_ERR_INVALID, "need 0 < step <= window_size");
-    if (cfg->step != cfg->window_size)
-        return fail(TLS_ERR_INVALID, "overlapping windows (step < window) are not implemented on the device yet");
     int nDev = 0;
     if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0) {
         cudaGetLastError();
@@ -425,7 +439,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
     if (nTiles) {
         DevConfig cfg = ctx->dcfg;
         cfg.mode = s.mode;
-        if (s.mode != TLS_MODE_GENOME) cfg.countAcgt = 0;
+        if (s.mode != TLS_MODE_GENOME || cfg.overlapWindows) cfg.countAcgt = 0;   // overlapping windows: counted by overlapWindowsKernel
         unsigned int *redo = s.dRedo.as<unsigned int>();
         TLS_CUDA(cudaEventRecord(s.evScan0, s.stream));
         const uint32_t nRow = s.nRowUnits;
@@ -503,7 +517,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         // window and per-item counters are final now: copy them home on the side stream
         TLS_CUDA(cudaEventRecord(s.evScanDone, s.stream));
         TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evScanDone, 0));
-        if (s.mode == TLS_MODE_GENOME && s.nWindows) {
+        if (s.mode == TLS_MODE_GENOME && s.nWindows && !cfg.overlapWindows) {
             TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
             TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows.p, s.nWindows * 32, cudaMemcpyDeviceToHost, s.copyStream));
         }
@@ -532,6 +546,7 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     if (!ctx || !b || !ticket) return fail(TLS_ERR_INVALID, "null argument");
     if (b->n_items && (!b->seq || !b->offsets)) return fail(TLS_ERR_INVALID, "null batch arrays");
     if (b->mode > TLS_MODE_READS) return fail(TLS_ERR_INVALID, "bad mode %u", b->mode);
+    if (b->mode == TLS_MODE_GENOME && !ctx->overlapRefusal.empty()) return fail(TLS_ERR_INVALID, "%s", ctx->overlapRefusal.c_str());
     int si = -1;
     for (int i = 0; i < 2; ++i) if (!ctx->slot[i].busy) { si = i; break; }
     if (si < 0) return fail(TLS_ERR_STATE, "two tickets already in flight");
@@ -796,6 +811,15 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             if (reads && n) TLS_CUDA(cudaMemsetAsync(s.dPass.p, 0, n, s.stream));
             if (n) {
                 if (first) { TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), n, s.dItemBegin.as<unsigned long long>(), s.stream)); s.launches++; }
+                if (first && genome && ctx->dcfg.overlapWindows && s.nWindows) {
+                    // step < window: the window table comes from the ordered list (block_kernels.cu), then goes home
+                    TLS_CUDA(launchOverlapWindows(s.devSeq, s.dRegions.as<DevRegion>(), static_cast<uint32_t>(s.regions.size()),
+                                                  s.dMatches.as<DevMatch>(), s.dItemBegin.as<unsigned long long>(),
+                                                  static_cast<uint32_t>(s.nWindows), ctx->dcfg, s.dWindows.as<uint32_t>(), s.stream));
+                    s.launches++;
+                    TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
+                    TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows.p, s.nWindows * 32, cudaMemcpyDeviceToHost, s.stream));
+                }
                 BlockParams bp{};
                 bp.matches = s.dMatches.as<DevMatch>();
                 bp.itemBegin = s.dItemBegin.as<unsigned long long>();

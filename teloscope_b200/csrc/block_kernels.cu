@@ -455,6 +455,79 @@ __global__ void __launch_bounds__(256) selectFinalizeKernel(const DevMatch *m, c
     out[j] = o;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Window table for overlapping windows (step < window; src/teloscope.cpp:409-434,485,512-529,600-637).
+// Window k of a contig starts at k * step and has min(window, n - k * step) bases; its counters are
+// what the reference builds from two pieces: the carry of window k - 1 (everything found at i >= step
+// there: start inside [k * step, ...) and end inside window k - 1) and its own part (match END index
+// j >= overlap).  For step >= L and overlap >= L (L = the pattern length; tls_create refuses anything
+// else) the two pieces add up to: every match that lies entirely inside the window, and every A/C/G/T
+// base of the window; and across windows every match of the contig is reported exactly once (by the
+// window its end falls into), so the scan kernels run without window truncation and this kernel builds
+// the table from the sequence and the ordered match list.  One warp per window.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) overlapWindowsKernel(const uint8_t *seq, const DevRegion *regions, uint32_t nRegions,
+                                                            const DevMatch *matches, const unsigned long long *itemBegin,
+                                                            uint32_t nWindows, uint32_t W, uint32_t S, uint32_t countAcgt,
+                                                            uint4 *windows) {
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (g >= nWindows) return;
+    uint32_t lo = 0, hi = nRegions;                                  // last region with winBase <= g
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (regions[mid].winBase <= g) lo = mid; else hi = mid;
+    }
+    const DevRegion r = regions[lo];
+    const uint32_t ws = (g - r.winBase) * S;                         // < r.len
+    const uint32_t cw = min(W, r.len - ws), wEnd = ws + cw;
+    uint32_t a = 0, c = 0, gg = 0, t = 0;
+    if (countAcgt) {
+        const uint8_t *row = seq + r.bufStart + ws;
+        for (uint32_t i = lane; i < cw; i += 32) {
+            const uint32_t ch = row[i] & 0xDFu;
+            a += ch == 'A'; c += ch == 'C'; gg += ch == 'G'; t += ch == 'T';
+        }
+    }
+    // first record of the item with pos >= ws
+    unsigned long long b = itemBegin[r.item], e = itemBegin[r.item + 1];
+    const unsigned long long itemEnd = e;
+    while (b < e) {
+        const unsigned long long mid = (b + e) >> 1;
+        if (matches[mid].pos < ws) b = mid + 1; else e = mid;
+    }
+    uint32_t can = 0, non = 0, fwd = 0, rev = 0;
+    for (unsigned long long base = b; base < itemEnd; base += 32) {
+        const unsigned long long i = base + lane;
+        bool inside = false;
+        if (i < itemEnd) {
+            const DevMatch m = matches[i];
+            inside = m.pos < wEnd;
+            if (inside && m.pos + m.len <= wEnd) {                   // entirely inside the window
+                if (m.flags & kMatchCan) can += m.len; else non += m.len;
+                if (m.flags & kMatchFwd) fwd += m.len; else rev += m.len;
+            }
+        }
+        if (!__all_sync(0xFFFFFFFFu, inside)) break;
+    }
+    a = __reduce_add_sync(0xFFFFFFFFu, a); c = __reduce_add_sync(0xFFFFFFFFu, c);
+    gg = __reduce_add_sync(0xFFFFFFFFu, gg); t = __reduce_add_sync(0xFFFFFFFFu, t);
+    can = __reduce_add_sync(0xFFFFFFFFu, can); non = __reduce_add_sync(0xFFFFFFFFu, non);
+    fwd = __reduce_add_sync(0xFFFFFFFFu, fwd); rev = __reduce_add_sync(0xFFFFFFFFu, rev);
+    if (lane == 0) {
+        windows[2 * static_cast<size_t>(g)] = make_uint4(a, c, gg, t);
+        windows[2 * static_cast<size_t>(g) + 1] = make_uint4(can, non, fwd, rev);
+    }
+}
+
+cudaError_t launchOverlapWindows(const uint8_t *seq, const DevRegion *regions, uint32_t nRegions, const DevMatch *matches,
+                                 const unsigned long long *itemBegin, uint32_t nWindows, const DevConfig &cfg, uint32_t *windows,
+                                 cudaStream_t s) {
+    if (nWindows == 0 || nRegions == 0) return cudaSuccess;
+    const unsigned long long threads = 32ull * nWindows;
+    overlapWindowsKernel<<<static_cast<unsigned int>((threads + 255) / 256), 256, 0, s>>>(
+        seq, regions, nRegions, matches, itemBegin, nWindows, cfg.windowSize, cfg.step, cfg.countAcgt, reinterpret_cast<uint4 *>(windows));
+    return cudaGetLastError();
+}
 cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned long long *itemBegin, cudaStream_t s) {
     itemOffsetsKernel<<<1, 1024, 0, s>>>(counts, n, itemBegin);
     return cudaGetLastError();

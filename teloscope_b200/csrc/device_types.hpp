@@ -140,6 +140,9 @@ struct DevConfig {
     uint32_t maxMatchDist, minBlockLen, maxBlockDist, minBlockCounts, itsMinLen;
     float minBlockDensity;
     uint32_t countAcgt;
+    uint32_t overlapWindows;       // 1: step < windowSize.  The scan kernels then neither cut matches at window ends nor
+                                   // account windows (every match of the contig is reported exactly once, see
+                                   // overlapWindowsKernel in block_kernels.cu); the window table is built from the ordered list
     // rel / windowSize by multiply-high (Granlund-Montgomery, exact for every u32 rel):
     //   t = umulhi(winMagic, rel);  q = (t + ((rel - t) >> winSh1)) >> winSh2
     uint32_t winMagic, winSh1, winSh2;

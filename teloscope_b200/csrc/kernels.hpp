@@ -31,6 +31,11 @@ cudaError_t launchGather(const GatherParams &g, cudaStream_t s);
 
 cudaError_t launchTrimCr(const uint8_t *seq, DevRegion *regions, uint32_t nRegions, uint32_t *itemLen, cudaStream_t s);
 cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned long long *itemBegin, cudaStream_t s);
+// step < window: the whole window table from the sequence and the ordered match list (regions: one per non-empty
+// contig, ascending winBase)
+cudaError_t launchOverlapWindows(const uint8_t *seq, const DevRegion *regions, uint32_t nRegions, const DevMatch *matches,
+                                 const unsigned long long *itemBegin, uint32_t nWindows, const DevConfig &cfg, uint32_t *windows,
+                                 cudaStream_t s);
 cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s);
 // runStarts: runCap entries; runCount: device counter, zeroed by the caller
 cudaError_t launchIts(const BlockParams &p, const uint32_t *canIdx, unsigned long long nCan, unsigned long long *runStarts,

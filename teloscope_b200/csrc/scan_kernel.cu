@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                         rel = loc.rel; limit = loc.regionEndRel; item = loc.item; itemLen = loc.itemLen; winBaseLoc = loc.winBase;
                     }
                     if (ok) {
-                        if (cfg.mode == 0) {     // matches never cross the window end (src/teloscope.cpp:439)
+                        if (cfg.mode == 0 && !cfg.overlapWindows) {     // matches never cross the window end (src/teloscope.cpp:439)
                             const uint64_t wEnd = static_cast<uint64_t>(divWindow(cfg, rel) + 1) * cfg.windowSize;
                             if (wEnd < limit) limit = static_cast<uint32_t>(wEnd);
                         }
@@ -393,7 +393,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                     }
                     if (hitMask && cfg.mode == 0) {          // "terminal" status, src/teloscope.cpp:451-459
                         const uint32_t nIt = t.single ? sRegions[0].itemLen : itemLen;
-                        if (isTerminalMatch(cfg, rel, divWindow(cfg, rel), nIt)) termBit = kMatchTerm;
+                        if (cfg.overlapWindows) {            // the window-level shortcuts of :403-406 agree with the per-match test
+                            const uint32_t termEnd = nIt > cfg.terminalLimit ? nIt - cfg.terminalLimit : 0u;
+                            if (rel <= cfg.terminalLimit || rel >= termEnd) termBit = kMatchTerm;
+                        } else if (isTerminalMatch(cfg, rel, divWindow(cfg, rel), nIt)) termBit = kMatchTerm;
                     }
                     if (hitMask) {
                         // window coverage (src/teloscope.cpp:470-510) and per-item counters of this position's matches
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                             atomicAdd((fl & 1u) ? &c->fwd : &c->rev, 1u);
                             if (fl & 2u) atomicAdd(&c->can, 1u);
                             else if (term) atomicAdd(&c->nonCanTerm, 1u);
-                            if (cfg.mode == 0) {
+                            if (cfg.mode == 0 && !cfg.overlapWindows) {
                                 uint32_t *w = p.windows + static_cast<size_t>(winBaseLoc + winIdx) * 8;
                                 atomicAdd(w + ((fl & 2u) ? 4 : 5), len);
                                 atomicAdd(w + ((fl & 1u) ? 6 : 7), len);

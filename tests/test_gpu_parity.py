@@ -27,17 +27,29 @@ def _same_blocks(a, b):
         assert np.array_equal(a[name], b[name]), name
 
 
+def device_supports(cfg, genome: bool = True) -> bool:
+    """step == window always (and windows do not exist outside genome mode); overlapping windows for one
+    pattern length L with step >= L and window - step >= L (what tls_submit accepts, see buildDevConfig
+    in csrc/api.cu)."""
+    if cfg.step == cfg.window_size or not genome:
+        return True
+    lens = {len(p) for p, _ in ol.expand_patterns(cfg.raw_patterns(), cfg.edit_distance, cfg.canonical_fwd)}
+    L = max(lens)
+    return len(lens) == 1 and cfg.step >= L and cfg.window_size - cfg.step >= L
+
+
 def test_golden_fasta_cases(tb, golden):
-    """Every FASTA case with step == window: product == reference files, and product == oracle
-    record by record (block order included)."""
+    """Every FASTA case the device supports (all with step == window, and the overlapping-window cases):
+    product == reference files, and product == oracle record by record (block order included)."""
     cases, fixtures = golden
-    done = 0
+    done = overlapping = 0
     for c in cases:
         if c["kind"] != "fasta":
             continue
         cfg, flags = ol.config_from_args(c["args"])
-        if cfg.step != cfg.window_size:
+        if not device_supports(cfg, flags["genome"]):
             continue
+        overlapping += flags["genome"] and cfg.step != cfg.window_size
         data = fixtures[c["fixture"]].tobytes()
         paths = ol.parse_fasta(data)
         tips = not flags["genome"]
@@ -72,6 +84,7 @@ def test_golden_fasta_cases(tb, golden):
             scanner.close()
         done += 1
     assert done >= 170
+    assert overlapping >= 3          # -w 500 -s 250 (the reference's own .tst flag set, with the genome-wide outputs), -w 100 -s 30, chr33 -w 2000 -s 500
 
 
 def test_golden_fastq_cases(tb, golden):

@@ -45,13 +45,16 @@ CHR_NAMES = [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY"]
 # --------------------------------------------------------------------------------------------------
 # synthetic assembly (SURVEY.md §8d, S-human)
 # --------------------------------------------------------------------------------------------------
-def plan_assembly(seed: int, scale: float):
+def plan_assembly(seed: int, scale: float, names=None, mbps=None, patterns=None, cap_unit: str = "TTAGGG"):
     """Host-side plan: per chromosome the contig intervals (N-gaps removed) and the patches
-    (telomere caps, TVR, ITS) to stamp onto random sequence."""
+    (telomere caps, TVR, ITS) to stamp onto random sequence.  Defaults: the human-shaped assembly
+    (SURVEY.md 8d S-human); names / mbps / patterns / cap_unit give the plant-shaped one (S-plant)."""
     rng = np.random.default_rng(seed)
-    variants = PATTERNS + [revcomp(p) for p in PATTERNS]
+    patterns = patterns or PATTERNS
+    variants = patterns + [revcomp(p) for p in patterns]
+    cap_fwd, cap_rev = cap_unit.encode(), revcomp(cap_unit).encode()
     chroms = []
-    for name, mbp in zip(CHR_NAMES, GRCH38_MBP):
+    for name, mbp in zip(names or CHR_NAMES, mbps or GRCH38_MBP):
         n = max(200_000, int(mbp * 1e6 * scale))
         gaps = []
         n_gaps = int(rng.integers(5, 31))
@@ -78,9 +81,9 @@ def plan_assembly(seed: int, scale: float):
                 out += u
             return bytes(out)
         cap = int(rng.integers(2000, 15001)); tv = int(rng.integers(500, 2001))
-        patches.append((0, b"CCCTAA" * (cap // 6) + tvr(b"CCCTAA", tv)))
+        patches.append((0, cap_rev * (cap // len(cap_rev)) + tvr(cap_rev, tv)))
         cap = int(rng.integers(2000, 15001)); tv = int(rng.integers(500, 2001))
-        tail = tvr(b"TTAGGG", tv) + b"TTAGGG" * (cap // 6)
+        tail = tvr(cap_fwd, tv) + cap_fwd * (cap // len(cap_fwd))
         patches.append((n - len(tail), tail))
         for _ in range(int(rng.integers(20, 61))):
             unit = variants[int(rng.integers(0, len(variants)))].encode()
@@ -158,6 +161,98 @@ def write_fasta(chroms, seq_host: np.ndarray, offsets: np.ndarray, path: Path) -
             if full < len(rec):
                 fh.write(rec[full:].tobytes() + b"\n")
     return bases
+
+
+# --------------------------------------------------------------------------------------------------
+# other BASELINE.json configs, measured beside the headline one (rank 0, N = 1): device-resident input
+# --------------------------------------------------------------------------------------------------
+PLANT_PATTERNS = ["CCCTAAA", "CCCTAAG", "CCCTAAC", "CCCTAAT", "CCCTAGA"]
+
+
+def build_reads(device, seed: int, total_bp: int):
+    """S-reads: HiFi-shaped reads, length ~N(15000, 3000) clipped at 1 kb, i.i.d. ACGT,
+    2 % with a 120 bp - 5 kb telomeric prefix or suffix.  -> (seq CUDA tensor, offsets, n_telomeric)"""
+    import torch
+    rng = np.random.default_rng(seed)
+    lens = np.maximum(1000, rng.normal(15000, 3000, size=int(total_bp / 15000 * 1.05) + 8).astype(np.int64))
+    lens = lens[: int(np.searchsorted(np.cumsum(lens), total_bp)) + 1]
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    total = int(offsets[-1])
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    seq = torch.empty(total + 4096, dtype=torch.uint8, device=device)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    for s0 in range(0, total + 4096, 1 << 26):
+        e = min(total + 4096, s0 + (1 << 26))
+        seq[s0:e] = lut[torch.randint(0, 4, (e - s0,), device=device, generator=g, dtype=torch.int64)]
+    telo = rng.choice(len(lens), size=max(1, len(lens) // 50), replace=False)
+    pos_list, val_list = [], []
+    for i in telo:
+        ln = int(min(rng.integers(120, 5001), lens[i]))
+        if rng.integers(0, 2):
+            unit, a = b"CCCTAA", int(offsets[i])
+        else:
+            unit, a = b"TTAGGG", int(offsets[i + 1]) - ln
+        pos_list.append(np.arange(a, a + ln, dtype=np.int64))
+        val_list.append(np.frombuffer((unit * (ln // 6 + 1))[:ln], dtype=np.uint8))
+    seq[torch.from_numpy(np.concatenate(pos_list)).to(device)] = torch.from_numpy(np.concatenate(val_list)).to(device)
+    return seq, offsets, len(telo)
+
+
+def time_workload(tb, cfg, seq, offsets, abs_pos, mode, steps: int, warmup: int, device: int):
+    """-> (seconds per step, mean scan-kernel ms, last result summary) with the input resident in HBM."""
+    import torch
+    sc = tb.Scanner(cfg, device=device)
+    try:
+        scan_ms, last = [], None
+        for k in range(warmup + steps):
+            if k == warmup:
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+            res = sc.collect(sc.submit(None, offsets, abs_pos, mode, device_ptr=seq.data_ptr()), copy=False)
+            if k >= warmup:
+                scan_ms.append(res.scan_kernel_ms)
+            if k == warmup + steps - 1:
+                last = {"matches": int(res.n_matches), "launches_per_step": int(res.n_kernel_launches)}
+                if mode == tb.MODE_READS:
+                    last["reads_passed"] = int(np.count_nonzero(res.passed))
+                else:
+                    last["windows"] = int(res.window_off[-1]); last["terminal_blocks"] = len(res.terminal); last["its_blocks"] = len(res.its)
+            res.release()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps, float(np.mean(scan_ms)), last
+    finally:
+        sc.close()
+
+
+def other_workloads(tb, device: int, seed: int, scale: float, peak: float):
+    """configs[3] (plant-shaped assembly, 7-mers) and configs[4] (read subset scorer) of BASELINE.json,
+    a few steps each; rooflines by the same byte accounting as the headline workload."""
+    import torch
+    out = []
+    dev = f"cuda:{device}"
+    # ---- S-plant: 2.5 Gbp in 12 records, -c CCCTAAA + 4 variants, genome-wide ----------------------------
+    chroms = plan_assembly(seed + 100, scale, [f"chr{i}" for i in range(1, 13)], [2500.0 / 12] * 12, PLANT_PATTERNS, "TTTAGGG")
+    seq, offsets, abs_pos = build_assembly(chroms, dev, seed + 100)
+    nb = int(offsets[-1])
+    cfg = tb.ScanConfig(canonical="CCCTAAA", patterns=PLANT_PATTERNS, out_acgt=True, out_matches=True)
+    per, kms, info = time_workload(tb, cfg, seq, offsets, abs_pos, tb.MODE_GENOME, 3, 2, device)
+    algo = nb + 32 * info["windows"]
+    out.append({"workload": f"synthetic plant-shaped assembly x{scale:g} (12 records, TTTAGGG caps), -c CCCTAAA -p {','.join(PLANT_PATTERNS)} "
+                            f"-r -g -e -m -i ({len(tb.expand_patterns(PLANT_PATTERNS, 1, 'CCCTAAA'))} 7-mer patterns)",
+                "bases": nb, "value": nb / per / 1e9, "unit": "Gbp/s", "ms_per_step": per * 1e3, "scan_kernels_ms": kms,
+                "roofline_frac": (algo / (kms * 1e-3) / 1e9) / peak, **info})
+    del seq
+    torch.cuda.empty_cache()
+    # ---- S-reads: HiFi-shaped reads through the read scorer (--fastq-subset / --bam-subset path, -l 42) ----------
+    total = int(2.0e9 * min(1.0, scale))
+    seq, offsets, n_telo = build_reads(dev, seed + 200, total)
+    nb = int(offsets[-1])
+    cfg = tb.ScanConfig(min_block_len=42)
+    per, kms, info = time_workload(tb, cfg, seq, offsets, None, tb.MODE_READS, 3, 2, device)
+    out.append({"workload": f"{len(offsets) - 1} synthetic HiFi reads (15 kb mean, {n_telo} with a telomeric end), read subset scorer, -l 42, default motif",
+                "bases": nb, "reads": len(offsets) - 1, "value": nb / per / 1e9, "unit": "Gbp/s", "reads_per_s": (len(offsets) - 1) / per,
+                "ms_per_step": per * 1e3, "scan_kernels_ms": kms,
+                "roofline_frac": ((nb + len(offsets) - 1) / (kms * 1e-3) / 1e9) / peak, **info})
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -260,6 +355,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="assembly size factor (1.0 = 3.09 Gbp; tests use less)")
     ap.add_argument("--cpu-scale", type=float, default=1.0 / 16, help="size factor of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the plant-assembly and read-scorer measurements")
     ap.add_argument("--seed", type=int, default=42)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -414,8 +510,16 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             gbps, _, desc = cpu_reference_run(args.cpu_scale, 1, 1)
             line["cpu_baseline"] = {"value": gbps, "unit": "Gbp/s", **desc}
-        print(json.dumps(line))
     sc.close()
+    if rank == 0:
+        if world == 1 and not args.no_extra:
+            del seq, host, host_np
+            torch.cuda.empty_cache()
+            try:
+                line["other_workloads"] = other_workloads(tb, local, args.seed, args.scale, peak)
+            except Exception as exc:           # the headline line must not be lost to a side measurement
+                line["other_workloads"] = {"error": repr(exc)}
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -1,0 +1,727 @@
+// teloscope-b200 — host pipeline around the C ABI for FASTA / FASTA.gz assemblies.
+//
+// What the reference does around scanSegment for a FASTA input, restated in C++17 on top of
+// include/teloscope_b200.h so that the output files, stdout and stderr are byte-identical:
+//   * flags of the scan (src/main.cpp:149-190 getopt table, :287-506 handlers, :590-674 messages);
+//   * FASTA ingest with gfalibs' semantics (gfalibs/src/input-gfa.cpp:41-72, gfalibs/src/gfa.cpp:88-239):
+//     header = text up to the first space, only '\n' leaves the sequence, maximal runs of N/n/X/x are gaps,
+//     every other byte stays in its contig;
+//   * Teloscope::walkPath (src/input.cpp:942-1041): every contig of a path is one scanSegment call with its
+//     absPos — here: one item of a batch that goes to the GPU through tls_submit / tls_collect, two batches
+//     in flight;
+//   * labelTerminalBlocks (src/teloscope.cpp:259-383), the writers (:661-859), file set (:886-920), the path
+//     and assembly summaries (:950-1055), getStats (src/tools.cpp:22-51), computeN50 (include/teloscope.h:224).
+// Not here (the reference's other front ends; this binary says so and exits with status 2): GFA input,
+// --fastq-subset / --bam-subset, the record filters (--include-bed ...), --plot-report, stdin.
+//
+// The float tracks are computed on the host from the device's integer window counters with the reference's
+// own expressions (include/teloscope.h:199-214, src/teloscope.cpp:788-803): compiled with -ffp-contract=off.
+#include <getopt.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cctype>
+#include <cstdarg>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "teloscope_b200.h"
+
+namespace {
+
+struct Options {
+    std::string inSequence, inSequenceName, inSequencePrefix, outRoute;
+    bool outRouteSet = false;
+    std::string canonicalFwd = "CCCTAA", canonicalRev = "TTAGGG";
+    std::vector<std::string> rawPatterns;
+    bool hasInputPatterns = false;
+    uint32_t windowSize = 1000, step = 1000, terminalLimit = 50000;
+    uint8_t editDistance = 1;
+    unsigned short maxMatchDist = 50, minBlockLen = 300, maxBlockDist = 500, minBlockCounts = 2;
+    float minBlockDensity = 0.5f;
+    bool outWinRepeats = false, outGC = false, outEntropy = false, outMatches = false, outITS = false;
+    bool ultraFastMode = true, manualCuration = false;
+    int cmdFlag = 0;
+};
+
+[[noreturn]] void die(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+void die(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    exit(EXIT_FAILURE);
+}
+[[noreturn]] void unsupported(const char *what) {
+    fprintf(stderr, "teloscope-b200: %s is not part of the B200 FASTA pipeline (use the reference binary for it).\n", what);
+    exit(2);
+}
+
+std::string upper(std::string s) {
+    for (char &c : s) c = static_cast<char>(std::toupper(static_cast<unsigned char>(c)));
+    return s;
+}
+std::string revCom(const std::string &s) {          // gfalibs revCom: complement of ACGT (either case), other bytes kept
+    std::string r(s.rbegin(), s.rend());
+    for (char &c : r) {
+        switch (c) {
+            case 'A': c = 'T'; break; case 'C': c = 'G'; break; case 'G': c = 'C'; break; case 'T': c = 'A'; break;
+            case 'a': c = 't'; break; case 'c': c = 'g'; break; case 'g': c = 'c'; break; case 't': c = 'a'; break;
+            default: break;
+        }
+    }
+    return r;
+}
+bool hasDigit(const std::string &s) { return std::any_of(s.begin(), s.end(), [](unsigned char c) { return std::isdigit(c); }); }
+
+int parseInt(const char *arg, const char *invalidMsg, const char *rangeMsg) {      // std::stoi + "> 0" of the reference's handlers
+    try {
+        const int v = std::stoi(arg);
+        if (v <= 0) die("%s", rangeMsg);
+        return v;
+    } catch (const std::exception &) {
+        die(invalidMsg, arg);
+    }
+}
+
+void setInputFile(Options &o, const char *path) {                                    // src/main.cpp:92-101
+    std::error_code ec;
+    if (!std::filesystem::exists(path, ec)) die("Error: Input file '%s' does not exist.\n", path);
+    const std::filesystem::path real = std::filesystem::canonical(path);
+    o.inSequence = real.string();
+    o.inSequencePrefix = real.parent_path().string();
+    o.inSequenceName = real.filename().string();
+    if (!o.outRouteSet) o.outRoute = o.inSequencePrefix;
+}
+
+Options parseArgs(int argc, char **argv) {
+    Options o;
+    static int cmdFlag = 0, verboseFlag = 0;
+    static struct option longOptions[] = {
+        {"input-sequence", required_argument, 0, 'f'}, {"output", required_argument, 0, 'o'},
+        {"include-bed", required_argument, 0, 0}, {"exclude-bed", required_argument, 0, 0},
+        {"include-prefix", required_argument, 0, 0}, {"exclude-prefix", required_argument, 0, 0},
+        {"patterns", required_argument, 0, 'p'}, {"window", required_argument, 0, 'w'}, {"step", required_argument, 0, 's'},
+        {"canonical", required_argument, 0, 'c'}, {"threads", required_argument, 0, 'j'},
+        {"terminal-limit", required_argument, 0, 't'}, {"max-match-distance", required_argument, 0, 'k'},
+        {"max-block-distance", required_argument, 0, 'd'}, {"min-block-length", required_argument, 0, 'l'},
+        {"min-block-density", required_argument, 0, 'y'}, {"edit-distance", required_argument, 0, 'x'},
+        {"out-fasta", no_argument, 0, 'a'}, {"out-win-repeats", no_argument, 0, 'r'}, {"out-gc", no_argument, 0, 'g'},
+        {"out-entropy", no_argument, 0, 'e'}, {"out-matches", no_argument, 0, 'm'}, {"out-its", no_argument, 0, 'i'},
+        {"ultra-fast", no_argument, 0, 'u'}, {"manual-curation", no_argument, 0, 'n'}, {"plot-report", no_argument, 0, 0},
+        {"fastq-subset", no_argument, 0, 0}, {"bam-subset", no_argument, 0, 0}, {"verbose", no_argument, &verboseFlag, 1},
+        {"cmd", no_argument, &cmdFlag, 1}, {"version", no_argument, 0, 'v'}, {"help", no_argument, 0, 'h'}, {0, 0, 0, 0}};
+    for (;;) {
+        int idx = 0;
+        const int c = getopt_long(argc, argv, "-:f:j:o:p:s:w:c:t:k:d:l:y:x:argemivhun", longOptions, &idx);
+        if (c == -1) break;
+        switch (c) {
+            case ':':
+                if (optopt == 0 && optind > 0 && optind <= argc && strncmp(argv[optind - 1], "--", 2) == 0)
+                    fprintf(stderr, "Error: Option %s is missing a required argument\n", argv[optind - 1]);
+                else
+                    fprintf(stderr, "Error: Option -%c is missing a required argument\n", optopt);
+                exit(EXIT_FAILURE);
+            case 0: {
+                const char *name = longOptions[idx].name;
+                if (longOptions[idx].flag) break;                      // --verbose / --cmd
+                if (!strcmp(name, "plot-report")) unsupported("--plot-report");
+                if (!strcmp(name, "fastq-subset")) unsupported("--fastq-subset");
+                if (!strcmp(name, "bam-subset")) unsupported("--bam-subset");
+                unsupported("record filtering (--include-bed / --exclude-bed / --include-prefix / --exclude-prefix)");
+            }
+            case 1:
+                if (o.inSequence.empty()) setInputFile(o, optarg);
+                else fprintf(stderr, "Warning: Ignoring extra positional argument '%s'\n", optarg);
+                break;
+            case 'f': setInputFile(o, optarg); break;
+            case 'o':
+                o.outRoute = optarg;
+                o.outRouteSet = true;
+                if (o.outRoute.empty()) exit(EXIT_FAILURE);
+                try {
+                    if (!std::filesystem::exists(o.outRoute)) std::filesystem::create_directories(o.outRoute);
+                } catch (const std::filesystem::filesystem_error &e) {
+                    die("Error: Cannot create output directory '%s': %s\n", o.outRoute.c_str(), e.code().message().c_str());
+                }
+                break;
+            case 'j': break;                                           // host threads of the reference; the scan runs on the GPU
+            case 'c': {
+                if (!optarg || !*optarg) {
+                    fprintf(stderr, "Warning: Empty canonical pattern provided, using default vertebrate TTAGGG.\n");
+                    break;
+                }
+                const std::string can = upper(optarg);
+                if (hasDigit(can)) die("Error: Canonical pattern '%s' contains numerical characters.\n", can.c_str());
+                const std::string rc = revCom(can);
+                if (can <= rc) { o.canonicalFwd = can; o.canonicalRev = rc; }
+                else { o.canonicalFwd = rc; o.canonicalRev = can; }
+                fprintf(stderr, "Setting canonical pattern: %s and its reverse complement: %s\n", o.canonicalFwd.c_str(),
+                        o.canonicalRev.c_str());
+                break;
+            }
+            case 'p': {
+                o.hasInputPatterns = true;
+                if (!optarg || !*optarg) {
+                    fprintf(stderr, "Warning: Empty pattern list provided, using default: TTAGGG, CCCTAA\n");
+                    o.rawPatterns = {"TTAGGG", "CCCTAA"};
+                    break;
+                }
+                o.rawPatterns.clear();
+                std::istringstream ps(optarg);
+                std::string pat;
+                while (std::getline(ps, pat, ',')) {
+                    if (pat.empty()) continue;
+                    if (hasDigit(pat)) die("Error: Pattern '%s' contains numerical characters.\n", pat.c_str());
+                    o.rawPatterns.push_back(upper(pat));
+                }
+                break;
+            }
+            case 'w':
+                o.windowSize = parseInt(optarg, "Error: Invalid window size '%s'. Must be a number.\n",
+                                        "Error: Window size (-w or --window) must be > 0.\n");
+                break;
+            case 's':
+                o.step = parseInt(optarg, "Error: Invalid step size '%s'. Must be a number.\n",
+                                  "Error: Step size (-s or --step) must be > 0.\n");
+                break;
+            case 't':
+                o.terminalLimit = parseInt(optarg, "Error: Invalid terminal limit '%s'. Must be a number.\n",
+                                           "Error: Terminal limit (-t or --terminal-limit) must be > 0.\n");
+                break;
+            case 'k':
+                o.maxMatchDist = static_cast<unsigned short>(parseInt(optarg, "Error: Invalid max match distance '%s'. Must be a number.\n",
+                                                                        "Error: Max match distance (-k/--max-match-distance) must be > 0.\n"));
+                break;
+            case 'l':
+                o.minBlockLen = static_cast<unsigned short>(parseInt(optarg, "Error: Invalid min block length '%s'. Must be a number.\n",
+                                                                       "Error: Min block length (-l or --min-block-length) must be > 0.\n"));
+                break;
+            case 'd':
+                o.maxBlockDist = static_cast<unsigned short>(parseInt(optarg, "Error: Invalid max block distance '%s'. Must be a number.\n",
+                                                                        "Error: Max block distance (-d or --max-block-distance) must be > 0.\n"));
+                break;
+            case 'y':
+                try {
+                    const float v = std::stof(optarg);
+                    if (v < 0.0f || v > 1.0f) die("Error: Min block density (-y/--min-block-density) must be in the range [0,1].\n");
+                    o.minBlockDensity = v;
+                } catch (const std::exception &) {
+                    die("Error: Invalid min block density '%s'. Must be a number [0,1].\n", optarg);
+                }
+                break;
+            case 'x':
+                try {
+                    const int v = std::stoi(optarg);
+                    if (v < 0 || v > 2) die("Error: Edit distance (-x/--edit-distance) must be in the range [0,2].\n");
+                    o.editDistance = static_cast<uint8_t>(v);
+                } catch (const std::exception &) {
+                    die("Error: Invalid edit distance '%s'. Must be a number [0,2].\n", optarg);
+                }
+                break;
+            case 'a': o.ultraFastMode = false; break;
+            case 'r': o.outWinRepeats = true; o.ultraFastMode = false; break;
+            case 'g': o.outGC = true; o.ultraFastMode = false; break;
+            case 'e': o.outEntropy = true; o.ultraFastMode = false; break;
+            case 'm': o.outMatches = true; o.ultraFastMode = false; break;
+            case 'i': o.outITS = true; o.ultraFastMode = false; break;
+            case 'u':
+                if (o.outWinRepeats || o.outGC || o.outEntropy || o.outITS || o.outMatches) {
+                    o.ultraFastMode = false;
+                    fprintf(stderr, "Ignoring -u: -r/-g/-e/-i/-m request genome-wide scanning.\n");
+                } else {
+                    o.ultraFastMode = true;
+                    fprintf(stderr, "Fast mode: Only scanning terminal regions.\n");
+                }
+                break;
+            case 'n': o.manualCuration = true; break;
+            case 'v': printf("/// teloscope-b200 (B200 FASTA pipeline of Teloscope's scan path)\n"); exit(0);
+            case 'h':
+                printf("teloscope-b200 input.[fa|fa.gz] [options]\n"
+                       "Scan flags as in teloscope: -f -o -c -p -x -w -s -t -k -d -l -y -r -g -e -m -i -u -n -j (ignored).\n");
+                exit(0);
+            default:
+                fprintf(stderr, "Error: Unknown option.\n");
+                exit(EXIT_FAILURE);
+        }
+    }
+    o.cmdFlag = cmdFlag;
+    return o;
+}
+
+// ---- FASTA ingest -------------------------------------------------------------------------------------
+struct Gap { uint64_t start; uint32_t length; };
+struct PathRec {
+    uint32_t seqPos = 0;
+    std::string header;
+    uint64_t pathSize = 0;
+    std::vector<Gap> gaps;
+    std::vector<tls_block> terminal, its;
+    uint64_t nCanonical = 0, nWindows = 0;
+    std::string terminalLabel;
+    int scaffoldType = 6;                       // index into kTypeNames: none
+    std::vector<uint8_t> isLongest;
+};
+struct Item { uint32_t path; uint64_t absPos, offset; uint32_t len; };
+
+std::string slurp(const std::string &path) {                 // plain or gzip: zlib reads both
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) die("Error: Cannot open input file '%s'.\n", path.c_str());
+    gzbuffer(f, 1 << 20);
+    std::string data;
+    std::vector<char> buf(1 << 24);
+    for (;;) {
+        const int n = gzread(f, buf.data(), static_cast<unsigned>(buf.size()));
+        if (n < 0) die("Error: Cannot read input file '%s'.\n", path.c_str());
+        if (n == 0) break;
+        data.append(buf.data(), static_cast<size_t>(n));
+    }
+    gzclose(f);
+    return data;
+}
+
+void parseFasta(const std::string &data, std::vector<PathRec> &paths, std::vector<Item> &items, std::vector<uint8_t> &seq) {
+    if (data.empty() || data[0] != '>') die("Error: '%s' does not look like a FASTA file (GFA input is not part of this pipeline).\n", "input");
+    seq.reserve(data.size() + 4096);
+    size_t p = 1;
+    while (p <= data.size()) {
+        size_t end = data.find('>', p);                       // a record runs to the next '>' wherever it stands
+        if (end == std::string::npos) end = data.size();
+        size_t nl = data.find('\n', p);
+        if (nl == std::string::npos || nl > end) nl = end;
+        PathRec rec;
+        rec.seqPos = static_cast<uint32_t>(paths.size());
+        const size_t sp = data.find(' ', p);
+        rec.header = data.substr(p, (sp != std::string::npos && sp < nl ? sp : nl) - p);
+        rec.header.erase(std::remove(rec.header.begin(), rec.header.end(), '\r'), rec.header.end());   // walkPath, src/input.cpp:950
+        const uint32_t pathIdx = static_cast<uint32_t>(paths.size());
+        uint64_t pos = 0, runStart = 0;
+        int state = -1;                                       // -1 nothing yet, 0 in a contig, 1 in a gap
+        const size_t segOffset0 = seq.size();
+        size_t segOffset = segOffset0;
+        auto closeRun = [&]() {
+            if (state == 1) rec.gaps.push_back({runStart, static_cast<uint32_t>(pos - runStart)});
+            else if (state == 0) items.push_back({pathIdx, runStart, segOffset, static_cast<uint32_t>(pos - runStart)});
+        };
+        for (size_t i = nl < end ? nl + 1 : end; i < end; ++i) {
+            const uint8_t c = static_cast<uint8_t>(data[i]);
+            if (c == '\n') continue;
+            const int st = (c == 'N' || c == 'n' || c == 'X' || c == 'x') ? 1 : 0;
+            if (st != state) {
+                closeRun();
+                state = st; runStart = pos; segOffset = seq.size();
+            }
+            if (st == 0) seq.push_back(c);
+            ++pos;
+        }
+        closeRun();
+        rec.pathSize = pos;
+        paths.push_back(std::move(rec));
+        p = end + 1;
+        if (end == data.size()) break;
+    }
+}
+
+// ---- output ---------------------------------------------------------------------------------------------
+struct OutFile {
+    std::string path, buf;
+    FILE *fh = nullptr;
+    bool open(const std::string &p) {
+        path = p;
+        fh = fopen(p.c_str(), "wb");
+        if (!fh) die("Error: Could not open '%s' for writing.\n", p.c_str());
+        buf.reserve(1 << 22);
+        return true;
+    }
+    void flushIfBig() { if (buf.size() > (1u << 22) - 4096) flush(); }
+    void flush() { if (fh && !buf.empty()) { fwrite(buf.data(), 1, buf.size(), fh); buf.clear(); } }
+    void close() { flush(); if (fh) { fclose(fh); fh = nullptr; } }
+};
+inline void appendU64(std::string &s, uint64_t v) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = static_cast<char>('0' + v % 10); v /= 10; } while (v);
+    while (n) s.push_back(tmp[--n]);
+}
+inline void appendFloat(std::string &s, float v) {              // std::ostream << float, default precision
+    char tmp[40];
+    const int n = snprintf(tmp, sizeof tmp, "%g", static_cast<double>(v));
+    s.append(tmp, static_cast<size_t>(n));
+}
+inline void windowLine(std::string &s, const std::string &header, uint64_t a, uint64_t b, float v) {
+    s += header; s.push_back('\t'); appendU64(s, a); s.push_back('\t'); appendU64(s, b); s.push_back('\t'); appendFloat(s, v);
+    s.push_back('\n');
+}
+float shannonEntropy(const uint32_t nt[4], uint32_t windowSize) {         // include/teloscope.h:199-208
+    float entropy = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        if (nt[i] > 0) {
+            const float probability = static_cast<float>(nt[i]) / windowSize;
+            entropy -= probability * std::log2(probability);
+        }
+    }
+    return std::round(entropy * 1000.0f) / 1000.0f;
+}
+float gcContent(const uint32_t nt[4], uint32_t windowSize) {               // include/teloscope.h:211-214
+    const uint32_t gcCount = nt[1] + nt[2];
+    return static_cast<float>(gcCount) / windowSize * 100.0;
+}
+
+const char *kTypeNames[] = {"t2t", "gapped_t2t", "misassembly", "gapped_misassembly", "incomplete", "gapped_incomplete",
+                            "none", "gapped_none", "discordant", "gapped_discordant"};
+enum { T2T = 0, MISASSEMBLY = 2, INCOMPLETE = 4, NONE = 6, DISCORDANT = 8 };
+
+void labelTerminalBlocks(PathRec &p, uint32_t terminalLimit) {             // src/teloscope.cpp:259-383
+    auto &blocks = p.terminal;
+    const int gapped = p.gaps.empty() ? 0 : 1;
+    p.isLongest.assign(blocks.size(), 0);
+    p.terminalLabel.clear();
+    if (blocks.empty()) { p.scaffoldType = NONE + gapped; return; }
+    std::sort(blocks.begin(), blocks.end(), [](const tls_block &a, const tls_block &b) { return a.start < b.start; });
+    std::vector<size_t> scaffold;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+        const uint64_t blockEnd = blocks[i].start + blocks[i].len;
+        if (blocks[i].start < terminalLimit || blockEnd > p.pathSize - terminalLimit) scaffold.push_back(i);
+    }
+    for (const auto &b : blocks) {
+        p.terminalLabel += b.label;
+        if (!b.has_valid_or) p.terminalLabel += '*';
+    }
+    long longestP = -1, longestQ = -1;
+    uint64_t maxP = 0, maxQ = 0;
+    for (size_t i : scaffold) {
+        if (blocks[i].label == 'p' && blocks[i].can_cov > maxP) { longestP = static_cast<long>(i); maxP = blocks[i].can_cov; }
+        else if (blocks[i].label == 'q' && blocks[i].can_cov > maxQ) { longestQ = static_cast<long>(i); maxQ = blocks[i].can_cov; }
+    }
+    if (longestP >= 0) p.isLongest[longestP] = 1;
+    if (longestQ >= 0) p.isLongest[longestQ] = 1;
+    for (size_t i = 0, j = 0; i < blocks.size(); ++i) {
+        if (p.isLongest[i]) p.terminalLabel[j] = static_cast<char>(std::toupper(static_cast<unsigned char>(p.terminalLabel[j])));
+        ++j;
+        if (j < p.terminalLabel.size() && p.terminalLabel[j] == '*') ++j;
+    }
+    const bool hasP = longestP >= 0, hasQ = longestQ >= 0;
+    if ((hasP && !blocks[longestP].has_valid_or) || (hasQ && !blocks[longestQ].has_valid_or)) { p.scaffoldType = DISCORDANT + gapped; return; }
+    if (hasP && hasQ) {
+        p.scaffoldType = (blocks[longestP].start < blocks[longestQ].start ? T2T : MISASSEMBLY) + gapped;
+        return;
+    }
+    for (int arm = 0; arm < 2; ++arm) {
+        const long longest = arm == 0 ? longestP : longestQ;
+        if (longest < 0) continue;
+        const char lab = arm == 0 ? 'p' : 'q';
+        for (size_t i : scaffold)
+            if (blocks[i].label == lab && static_cast<long>(i) != longest && blocks[i].has_valid_or) { p.scaffoldType = MISASSEMBLY + gapped; return; }
+    }
+    if (!hasP && !hasQ) { p.scaffoldType = NONE + gapped; return; }
+    p.scaffoldType = INCOMPLETE + gapped;
+}
+
+uint64_t computeN50(std::vector<uint64_t> &lengths) {                       // include/teloscope.h:224-236
+    if (lengths.empty()) return 0;
+    std::sort(lengths.begin(), lengths.end(), [](uint64_t a, uint64_t b) { return a > b; });
+    uint64_t total = 0;
+    for (uint64_t l : lengths) total += l;
+    uint64_t cum = 0;
+    for (uint64_t l : lengths) {
+        cum += l;
+        if (cum * 2 >= total) return l;
+    }
+    return lengths.back();
+}
+
+void blockRow(std::string &s, const std::string &header, const tls_block &b, uint64_t pathSize) {
+    s += header; s.push_back('\t'); appendU64(s, b.start); s.push_back('\t'); appendU64(s, b.start + b.len); s.push_back('\t');
+    appendU64(s, b.len); s.push_back('\t'); s.push_back(b.label); s.push_back('\t'); appendU64(s, b.fwd_count); s.push_back('\t');
+    appendU64(s, b.rev_count); s.push_back('\t'); appendU64(s, b.can_count); s.push_back('\t'); appendU64(s, b.noncan_count);
+    s.push_back('\t'); appendU64(s, pathSize);
+}
+
+void check(int rc, const char *what) {
+    if (rc != TLS_OK) die("Error: %s failed: %s\n", what, tls_last_error());
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc == 1) {
+        printf("teloscope-b200 input.[fa|fa.gz] [options]\nUse -h for additional help.\n");
+        return 0;
+    }
+    Options o = parseArgs(argc, argv);
+    if (o.inSequence.empty()) die("Error: No input file provided. Use -f or pass as positional argument.\n");
+    if (o.step > o.windowSize) die("Error: Step size (%d) cannot be larger than window size (%d).\n", o.step, o.windowSize);
+    if (o.step < o.windowSize) fprintf(stderr, "Sliding with window size (%d) and step size (%d).\n", o.windowSize, o.step);
+    {   // writable check, src/main.cpp:611-622
+        const std::string testPath = o.outRoute + "/.teloscope_write_test";
+        std::ofstream test(testPath);
+        if (!test.is_open()) die("Error: Output directory '%s' is not writable.\n", o.outRoute.c_str());
+        test.close();
+        std::filesystem::remove(testPath);
+    }
+    if (!o.hasInputPatterns) o.rawPatterns = {o.canonicalFwd, o.canonicalRev};
+    if (o.rawPatterns.empty()) {
+        fprintf(stderr, "Warning: No valid patterns supplied via -p. Using canonical: %s, %s\n", o.canonicalFwd.c_str(), o.canonicalRev.c_str());
+        o.rawPatterns = {o.canonicalFwd, o.canonicalRev};
+    }
+
+    // ---- pattern table (expandPatternsWithOrientation through the C ABI) ------------------------------------
+    std::string csv;
+    for (const auto &p : o.rawPatterns) { if (!csv.empty()) csv += ','; csv += p; }
+    uint32_t nPat = 0;
+    size_t textNeed = 0;
+    check(tls_expand_patterns(csv.c_str(), o.editDistance, o.canonicalFwd.c_str(), nullptr, 0, nullptr, nullptr, 0, &nPat, &textNeed),
+          "pattern expansion");
+    std::vector<char> text(std::max<size_t>(textNeed, 1));
+    std::vector<uint8_t> isFwd(std::max<uint32_t>(nPat, 1)), isCan(std::max<uint32_t>(nPat, 1));
+    check(tls_expand_patterns(csv.c_str(), o.editDistance, o.canonicalFwd.c_str(), text.data(), text.size(), isFwd.data(), isCan.data(),
+                              nPat, &nPat, &textNeed), "pattern expansion");
+    std::vector<const char *> patPtr;
+    for (size_t off = 0, i = 0; i < nPat; ++i) { patPtr.push_back(text.data() + off); off += strlen(text.data() + off) + 1; }
+    fprintf(stderr, "Scanning %zu telomeric variants (includes reverse complements).\n", static_cast<size_t>(nPat));
+    if (o.editDistance > 0)
+        fprintf(stderr, "Edit distance enabled: up to %u substitution%s per seed.\n", o.editDistance, o.editDistance > 1 ? "s" : "");
+    if (nPat > 500) {
+        fprintf(stderr, "Warning: %zu patterns is unusually high and may be slow on large genomes.\n", static_cast<size_t>(nPat));
+        fprintf(stderr, "  Consider fewer IUPAC wildcards or a lower -x value.\n");
+    }
+    {
+        std::string summary;
+        auto add = [&](bool on, const char *label) { if (on) { if (!summary.empty()) summary += ", "; summary += label; } };
+        add(o.outGC, "GC windows"); add(o.outWinRepeats, "repeat density"); add(o.outEntropy, "Shannon entropy");
+        add(o.outMatches, "genome-wide matches"); add(o.outITS, "ITS blocks");
+        if (!summary.empty()) fprintf(stderr, "Outputs: %s.\n", summary.c_str());
+    }
+    if (o.cmdFlag) {
+        for (int i = 0; i < argc; ++i) printf("%s ", argv[i]);
+        printf("\n");
+    }
+
+    // ---- ingest ---------------------------------------------------------------------------------------------
+    std::vector<PathRec> paths;
+    std::vector<Item> items;
+    std::vector<uint8_t> seq;
+    {
+        const std::string data = slurp(o.inSequence);
+        if (!data.empty() && (data[0] == 'H' || data[0] == 'S') && data.size() > 1 && data[1] == '\t') unsupported("GFA input");
+        if (!data.empty() && data[0] == '@') unsupported("FASTQ input");
+        parseFasta(data, paths, items, seq);
+    }
+    seq.resize(seq.size() + 256, 0);
+
+    // ---- device context -------------------------------------------------------------------------------------
+    tls_config cfg{};
+    cfg.abi_version = TLS_ABI_VERSION;
+    cfg.n_patterns = nPat; cfg.patterns = patPtr.data(); cfg.is_forward = isFwd.data(); cfg.is_canonical = isCan.data();
+    cfg.window_size = o.windowSize; cfg.step = o.step; cfg.terminal_limit = o.terminalLimit;
+    cfg.max_match_dist = o.maxMatchDist; cfg.min_block_len = o.minBlockLen; cfg.max_block_dist = o.maxBlockDist;
+    cfg.min_block_counts = o.minBlockCounts; cfg.min_block_density = o.minBlockDensity;
+    cfg.outputs = ((o.outGC || o.outEntropy) ? TLS_OUT_ACGT : 0u) | (o.outMatches ? TLS_OUT_MATCHES : 0u) | TLS_OUT_ITS;
+    tls_ctx *ctx = nullptr;
+    const char *devEnv = getenv("TLS_DEVICE");
+    check(tls_create(&cfg, devEnv ? atoi(devEnv) : 0, &ctx), "tls_create");
+
+    // ---- output files (src/teloscope.cpp:886-920: which exist depends on the flags only) ---------------------------
+    const std::string base = o.outRoute + "/" + o.inSequenceName;
+    OutFile fDensity, fCanRatio, fStrand, fGC, fEntropy, fCan, fNon, fTerminal, fIts, fGaps, fReport;
+    if (o.outWinRepeats) {
+        fDensity.open(base + "_window_repeat_density.bedgraph");
+        fCanRatio.open(base + "_window_canonical_ratio.bedgraph");
+        fStrand.open(base + "_window_strand_ratio.bedgraph");
+        fDensity.buf += "track type=bedGraph name=\"Repeat Density\" description=\"Total repeat density per window\"\n";
+        fCanRatio.buf += "track type=bedGraph name=\"Canonical Ratio\" description=\"Canonical fraction of repeat density per window\"\n";
+        fStrand.buf += "track type=bedGraph name=\"Strand Ratio\" description=\"Forward-strand fraction of repeat density per window\"\n";
+    }
+    if (o.outGC) { fGC.open(base + "_window_gc.bedgraph"); fGC.buf += "track type=bedGraph name=\"GC Content\" description=\"GC content per window\"\n"; }
+    if (o.outEntropy) { fEntropy.open(base + "_window_entropy.bedgraph"); fEntropy.buf += "track type=bedGraph name=\"Shannon Entropy\" description=\"Shannon entropy per window\"\n"; }
+    if (o.outMatches) { fCan.open(base + "_canonical_matches.bed"); fNon.open(base + "_noncanonical_matches.bed"); }
+    if (o.outITS) fIts.open(base + "_interstitial_telomeres.bed");
+    fTerminal.open(base + "_terminal_telomeres.bed");
+    fGaps.open(base + "_gaps.bed");
+    fReport.open(base + "_report.tsv");
+
+    // ---- scan: batches of whole contigs, two in flight; results are consumed in submission order ---------------------
+    const uint64_t batchBytes = getenv("TLS_BATCH_BYTES") ? strtoull(getenv("TLS_BATCH_BYTES"), nullptr, 10) : (1ull << 30);
+    const uint32_t mode = o.ultraFastMode ? TLS_MODE_TIPS : TLS_MODE_GENOME;
+    struct Batch { size_t first, count; std::vector<uint64_t> offsets, absPos; int ticket; };
+    std::vector<Batch> flight;
+    size_t nextItem = 0;
+    auto submitNext = [&]() {
+        Batch b;
+        b.first = nextItem;
+        uint64_t bytes = 0;
+        while (nextItem < items.size() && (bytes == 0 || bytes + items[nextItem].len <= batchBytes) && nextItem - b.first < 0x7FFFFFFFu) {
+            bytes += items[nextItem].len;
+            ++nextItem;
+        }
+        b.count = nextItem - b.first;
+        for (size_t i = 0; i < b.count; ++i) { b.offsets.push_back(items[b.first + i].offset); b.absPos.push_back(items[b.first + i].absPos); }
+        b.offsets.push_back(items[b.first + b.count - 1].offset + items[b.first + b.count - 1].len);
+        tls_batch tb{};
+        tb.seq = seq.data(); tb.offsets = b.offsets.data(); tb.abs_pos = b.absPos.data();
+        tb.n_items = static_cast<uint32_t>(b.count); tb.mode = mode;
+        check(tls_submit(ctx, &tb, &b.ticket), "tls_submit");
+        flight.push_back(std::move(b));
+    };
+    auto consume = [&](const Batch &b) {
+        tls_result r{};
+        check(tls_collect(ctx, b.ticket, &r), "tls_collect");
+        for (size_t j = 0; j < b.count; ++j) {
+            const Item &it = items[b.first + j];
+            PathRec &p = paths[it.path];
+            for (uint64_t k = r.terminal_off[j]; k < r.terminal_off[j + 1]; ++k) p.terminal.push_back(r.terminal[k]);
+            if (mode == TLS_MODE_GENOME) {
+                const size_t its0 = p.its.size();
+                for (uint64_t k = r.its_off[j]; k < r.its_off[j + 1]; ++k) p.its.push_back(r.its[k]);
+                std::sort(p.its.begin() + static_cast<long>(its0), p.its.end(), [](const tls_block &a, const tls_block &b2) { return a.start < b2.start; });
+                p.nCanonical += r.n_canonical[j];
+                const uint64_t w0 = r.window_off[j], w1 = r.window_off[j + 1];
+                p.nWindows += w1 - w0;
+                for (uint64_t k = w0; k < w1; ++k) {
+                    const tls_window &w = r.windows[k];
+                    const uint64_t rel = (k - w0) * o.step;
+                    const uint32_t size = static_cast<uint32_t>(std::min<uint64_t>(o.windowSize, it.len - rel));
+                    const uint64_t ws = it.absPos + rel, we = ws + size;
+                    if (o.outWinRepeats) {                                         // src/teloscope.cpp:788-803
+                        const uint32_t totalCovered = w.fwd_cov + w.rev_cov;
+                        const float totalDensity = static_cast<float>(totalCovered) / size;
+                        const float canonRatio = totalCovered > 0 ? static_cast<float>(w.can_cov) / (w.can_cov + w.noncan_cov) : -1.0f;
+                        const float strandRatio = totalCovered > 0 ? static_cast<float>(w.fwd_cov) / (w.fwd_cov + w.rev_cov) : -1.0f;
+                        windowLine(fDensity.buf, p.header, ws, we, totalDensity);
+                        windowLine(fCanRatio.buf, p.header, ws, we, canonRatio);
+                        windowLine(fStrand.buf, p.header, ws, we, strandRatio);
+                    }
+                    if (o.outEntropy) windowLine(fEntropy.buf, p.header, ws, we, shannonEntropy(w.acgt, size));
+                    if (o.outGC) windowLine(fGC.buf, p.header, ws, we, gcContent(w.acgt, size));
+                    if ((k & 1023) == 0) { fDensity.flushIfBig(); fCanRatio.flushIfBig(); fStrand.flushIfBig(); fEntropy.flushIfBig(); fGC.flushIfBig(); }
+                }
+                if (o.outMatches) {
+                    auto dump = [&](OutFile &f, const uint64_t *off, const tls_match *m) {
+                        for (uint64_t k = off[j]; k < off[j + 1]; ++k) {
+                            std::string &s = f.buf;
+                            s += p.header; s.push_back('\t'); appendU64(s, m[k].pos); s.push_back('\t'); appendU64(s, m[k].pos + m[k].len);
+                            s.push_back('\t');
+                            const uint8_t *src = seq.data() + it.offset + (m[k].pos - it.absPos);
+                            for (uint32_t q = 0; q < m[k].len; ++q) s.push_back(static_cast<char>(std::toupper(src[q])));
+                            s.push_back('\n');
+                            if ((k & 1023) == 0) f.flushIfBig();
+                        }
+                    };
+                    dump(fCan, r.canonical_off, r.canonical);
+                    dump(fNon, r.noncanonical_off, r.noncanonical);
+                }
+            }
+        }
+        check(tls_release(ctx, b.ticket), "tls_release");
+    };
+    while (nextItem < items.size() || !flight.empty()) {
+        while (flight.size() < 2 && nextItem < items.size()) submitNext();
+        consume(flight.front());
+        flight.erase(flight.begin());
+    }
+    tls_destroy(ctx);
+
+    // ---- per path: classification, block / gap rows, report (src/teloscope.cpp:687-847) -------------------------------------
+    std::string rep;           // goes to stdout and to the report file alike (after the banner)
+    std::cout << "\n+++ Path Summary Report +++\n";
+    rep += o.ultraFastMode ? "pos\theader\ttelomeres\tlabels\tgaps\ttype\tgranular\n"
+                           : "pos\theader\ttelomeres\tlabels\tgaps\ttype\tgranular\tits\tcanonical\twindows\n";
+    uint32_t totalPaths = static_cast<uint32_t>(paths.size()), totalNWindows = 0, totalTelomeres = 0, totalITS = 0, totalCanMatches = 0, totalGaps = 0;
+    uint32_t typeCount[10] = {0};
+    std::vector<float> telomereLengths;
+    std::vector<uint64_t> scaffoldLens, contigLens;
+    for (PathRec &p : paths) {
+        labelTerminalBlocks(p, o.terminalLimit);
+        int longestCount = 0;
+        std::string longestLabels;
+        for (size_t i = 0; i < p.terminal.size(); ++i) {
+            const tls_block &b = p.terminal[i];
+            const uint64_t blockEnd = b.start + b.len;
+            const bool scaffoldTerminal = b.start < o.terminalLimit || blockEnd > p.pathSize - o.terminalLimit;
+            if (scaffoldTerminal || o.manualCuration) {
+                blockRow(fTerminal.buf, p.header, b, p.pathSize);
+                fTerminal.buf += scaffoldTerminal ? "\tscaffold\n" : "\tcontig\n";
+            }
+            if (p.isLongest[i]) {
+                ++longestCount;
+                longestLabels += b.label;
+                telomereLengths.push_back(static_cast<float>(b.len));
+            }
+        }
+        if (o.outITS)
+            for (const tls_block &b : p.its) { blockRow(fIts.buf, p.header, b, p.pathSize); fIts.buf.push_back('\n'); }
+        for (const Gap &g : p.gaps) {
+            fGaps.buf += p.header; fGaps.buf.push_back('\t'); appendU64(fGaps.buf, g.start); fGaps.buf.push_back('\t');
+            appendU64(fGaps.buf, g.start + g.length); fGaps.buf.push_back('\n');
+        }
+        fTerminal.flushIfBig(); fIts.flushIfBig(); fGaps.flushIfBig();
+        const uint16_t gaps = static_cast<uint16_t>(p.gaps.size());
+        appendU64(rep, static_cast<uint64_t>(p.seqPos) + 1); rep.push_back('\t'); rep += p.header; rep.push_back('\t');
+        appendU64(rep, static_cast<uint64_t>(longestCount)); rep.push_back('\t'); rep += longestLabels.empty() ? "none" : longestLabels;
+        rep.push_back('\t'); appendU64(rep, gaps); rep.push_back('\t'); rep += kTypeNames[p.scaffoldType]; rep.push_back('\t');
+        rep += p.terminalLabel;
+        totalTelomeres += static_cast<uint32_t>(longestCount);
+        totalGaps += gaps;
+        if (!o.ultraFastMode) {
+            rep.push_back('\t'); appendU64(rep, p.its.size()); rep.push_back('\t'); appendU64(rep, p.nCanonical); rep.push_back('\t');
+            appendU64(rep, p.nWindows);
+            totalNWindows += static_cast<uint32_t>(p.nWindows);
+            totalITS += static_cast<uint32_t>(p.its.size());
+            totalCanMatches += static_cast<uint32_t>(p.nCanonical);
+        }
+        rep.push_back('\n');
+        ++typeCount[p.scaffoldType];
+        scaffoldLens.push_back(p.pathSize);                                      // computeSummaryCounts, :950-984
+        std::vector<Gap> gs = p.gaps;
+        std::sort(gs.begin(), gs.end(), [](const Gap &a, const Gap &b) { return a.start < b.start; });
+        uint64_t prevEnd = 0;
+        for (const Gap &g : gs) {
+            if (g.start > prevEnd) contigLens.push_back(g.start - prevEnd);
+            prevEnd = g.start + g.length;
+        }
+        if (p.pathSize > prevEnd) contigLens.push_back(p.pathSize - prevEnd);
+    }
+    float teloMean = 0.0f, teloMedian = 0.0f, teloMin = 0.0f, teloMax = 0.0f;
+    if (!telomereLengths.empty()) {                                               // getStats, src/tools.cpp:22-51
+        std::vector<float> &v = telomereLengths;
+        float sum = 0.0f;
+        teloMin = teloMax = v[0];
+        for (float x : v) { if (x < teloMin) teloMin = x; if (x > teloMax) teloMax = x; sum += x; }
+        teloMean = sum / v.size();
+        const size_t mid = v.size() / 2;
+        std::nth_element(v.begin(), v.begin() + static_cast<long>(mid), v.end());
+        teloMedian = v.size() % 2 == 0 ? (v[mid] + *std::max_element(v.begin(), v.begin() + static_cast<long>(mid))) / 2 : v[mid];
+    }
+    const uint64_t scaffoldN50 = computeN50(scaffoldLens), contigN50 = computeN50(contigLens);
+    auto kv = [&](const char *k, uint64_t v) { rep += k; appendU64(rep, v); rep.push_back('\n'); };
+    auto kf = [&](const char *k, float v) { rep += k; appendFloat(rep, v); rep.push_back('\n'); };
+    rep += "\n+++ Assembly Summary Report +++\n";
+    kv("Total paths:\t", totalPaths); kv("Total gaps:\t", totalGaps); kv("Scaffold N50:\t", scaffoldN50); kv("Contig N50:\t", contigN50);
+    kv("Total telomeres:\t", totalTelomeres);
+    if (!o.ultraFastMode) { kv("Total ITS blocks:\t", totalITS); kv("Total canonical matches:\t", totalCanMatches); kv("Total windows analyzed:\t", totalNWindows); }
+    rep += "\n+++ Telomere Statistics +++\n";
+    if (totalTelomeres > 0) { kf("Mean length:\t", teloMean); kf("Median length:\t", teloMedian); kf("Min length:\t", teloMin); kf("Max length:\t", teloMax); }
+    else rep += "No telomeres found for statistics.\n";
+    rep += "\n+++ Chromosome Telomere Counts+++\n";
+    kv("Two telomeres:\t", typeCount[0] + typeCount[1] + typeCount[2] + typeCount[3]);
+    kv("One telomere:\t", typeCount[4] + typeCount[5]);
+    kv("Zero telomeres:\t", typeCount[6] + typeCount[7]);
+    rep += "\n+++ Chromosome Telomere/Gap Completeness+++\n";
+    kv("T2T:\t", typeCount[0]); kv("Gapped T2T:\t", typeCount[1]); kv("Misassembled:\t", typeCount[2]); kv("Gapped misassembled:\t", typeCount[3]);
+    kv("Incomplete:\t", typeCount[4]); kv("Gapped incomplete:\t", typeCount[5]); kv("No telomeres:\t", typeCount[6]);
+    kv("Gapped no telomeres:\t", typeCount[7]); kv("Discordant:\t", typeCount[8]); kv("Gapped discordant:\t", typeCount[9]);
+    std::cout << rep;
+    std::cout.flush();
+    fReport.buf += rep;
+    for (OutFile *f : {&fDensity, &fCanRatio, &fStrand, &fGC, &fEntropy, &fCan, &fNon, &fTerminal, &fIts, &fGaps, &fReport}) f->close();
+    return EXIT_SUCCESS;
+}

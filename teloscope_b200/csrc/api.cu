@@ -152,6 +152,13 @@ struct tls_ctx {
     bool noRowKernel = false;                // TLS_NO_ROW_KERNEL=1: 1536-base-row lean kernel instead of the window-row kernel
     uint32_t rowMinWindows = kRowMinWindows; // TLS_ROW_MIN_WINDOWS=n: shortest contig (in windows) the window-row kernel takes
     Slot slot[2];
+    // pageable host input: a ring of small pinned buffers carries it to the device chunk by chunk (memcpy of chunk
+    // k + 1 overlaps the DMA of chunk k); no pinned buffer of the batch's size is ever allocated
+    static constexpr int kRing = 4;
+    static constexpr size_t kRingBytes = 8u << 20;
+    HostBuf ring[kRing];
+    cudaEvent_t ringEv[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t ringNext = 0;
 };
 
 namespace {
@@ -387,6 +394,10 @@ void tls_destroy(tls_ctx *ctx) {
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     for (DevBuf *b : {&ctx->dIndex, &ctx->dFlags, &ctx->dKeys, &ctx->dKeyFlags}) b->release();
+    for (int k = 0; k < tls_ctx::kRing; ++k) {
+        if (ctx->ringEv[k]) cudaEventDestroy(ctx->ringEv[k]);
+        ctx->ring[k].release();
+    }
     delete ctx;
 }
 
@@ -571,11 +582,22 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
         cudaGetLastError();
         const uint8_t *src = b->seq + base;
         if (!pinned && s.seqBytes) {
-            TLS_CUDA(s.hSeq.reserve(s.seqBytes));
-            std::memcpy(s.hSeq.p, src, s.seqBytes);
-            src = s.hSeq.as<uint8_t>();
+            for (uint64_t off = 0; off < s.seqBytes; off += tls_ctx::kRingBytes, ++ctx->ringNext) {
+                const int k = static_cast<int>(ctx->ringNext % tls_ctx::kRing);
+                if (!ctx->ringEv[k]) {
+                    TLS_CUDA(ctx->ring[k].reserve(tls_ctx::kRingBytes));
+                    TLS_CUDA(cudaEventCreateWithFlags(&ctx->ringEv[k], cudaEventDisableTiming));
+                } else {
+                    TLS_CUDA(cudaEventSynchronize(ctx->ringEv[k]));             // the DMA that last read this buffer
+                }
+                const size_t nb = static_cast<size_t>(std::min<uint64_t>(tls_ctx::kRingBytes, s.seqBytes - off));
+                std::memcpy(ctx->ring[k].p, src + off, nb);
+                TLS_CUDA(cudaMemcpyAsync(s.dSeq.as<uint8_t>() + off, ctx->ring[k].p, nb, cudaMemcpyHostToDevice, s.stream));
+                TLS_CUDA(cudaEventRecord(ctx->ringEv[k], s.stream));
+            }
+        } else if (s.seqBytes) {
+            TLS_CUDA(cudaMemcpyAsync(s.dSeq.p, src, s.seqBytes, cudaMemcpyHostToDevice, s.stream));
         }
-        if (s.seqBytes) TLS_CUDA(cudaMemcpyAsync(s.dSeq.p, src, s.seqBytes, cudaMemcpyHostToDevice, s.stream));
         TLS_CUDA(cudaMemsetAsync(s.dSeq.as<uint8_t>() + s.seqBytes, 0, 256, s.stream));
         s.devSeq = s.dSeq.as<uint8_t>();
     }

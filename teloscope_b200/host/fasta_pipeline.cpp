@@ -16,11 +16,18 @@
 //
 // The float tracks are computed on the host from the device's integer window counters with the reference's
 // own expressions (include/teloscope.h:199-214, src/teloscope.cpp:788-803): compiled with -ffp-contract=off.
+#include <emmintrin.h>
+#include <fcntl.h>
 #include <getopt.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
+#include <chrono>
 #include <cstdarg>
 #include <cmath>
 #include <cstdint>
@@ -31,7 +38,9 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "teloscope_b200.h"
@@ -51,6 +60,7 @@ struct Options {
     bool outWinRepeats = false, outGC = false, outEntropy = false, outMatches = false, outITS = false;
     bool ultraFastMode = true, manualCuration = false;
     int cmdFlag = 0;
+    unsigned threads = 0;                       // -j: host threads of the parse / formatting stages (0 = all cores)
 };
 
 [[noreturn]] void die(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
@@ -154,7 +164,7 @@ Options parseArgs(int argc, char **argv) {
                     die("Error: Cannot create output directory '%s': %s\n", o.outRoute.c_str(), e.code().message().c_str());
                 }
                 break;
-            case 'j': break;                                           // host threads of the reference; the scan runs on the GPU
+            case 'j': o.threads = static_cast<unsigned>(std::max(0, atoi(optarg))); break;   // host threads (parse, formatting); the scan runs on the GPU
             case 'c': {
                 if (!optarg || !*optarg) {
                     fprintf(stderr, "Warning: Empty canonical pattern provided, using default vertebrate TTAGGG.\n");
@@ -273,62 +283,173 @@ struct PathRec {
 };
 struct Item { uint32_t path; uint64_t absPos, offset; uint32_t len; };
 
-std::string slurp(const std::string &path) {                 // plain or gzip: zlib reads both
+// Input bytes: a plain file is mapped (no copy), a gzip file is inflated by zlib into memory.
+struct InputData {
+    const char *p = nullptr;
+    size_t n = 0;
+    std::string owned;
+    void *map = nullptr;
+    ~InputData() { if (map) munmap(map, n); }
+};
+void loadInput(const std::string &path, InputData &in) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) die("Error: Cannot open input file '%s'.\n", path.c_str());
+    unsigned char magic[2] = {0, 0};
+    const ssize_t got = pread(fd, magic, 2, 0);
+    struct stat st {};
+    fstat(fd, &st);
+    if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) && st.st_size > 0) {
+        void *m = mmap(nullptr, static_cast<size_t>(st.st_size), PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        if (m != MAP_FAILED) {
+            madvise(m, static_cast<size_t>(st.st_size), MADV_SEQUENTIAL);
+            in.map = m; in.p = static_cast<const char *>(m); in.n = static_cast<size_t>(st.st_size);
+            close(fd);
+            return;
+        }
+    }
+    close(fd);
     gzFile f = gzopen(path.c_str(), "rb");
     if (!f) die("Error: Cannot open input file '%s'.\n", path.c_str());
     gzbuffer(f, 1 << 20);
-    std::string data;
     std::vector<char> buf(1 << 24);
     for (;;) {
         const int n = gzread(f, buf.data(), static_cast<unsigned>(buf.size()));
         if (n < 0) die("Error: Cannot read input file '%s'.\n", path.c_str());
         if (n == 0) break;
-        data.append(buf.data(), static_cast<size_t>(n));
+        in.owned.append(buf.data(), static_cast<size_t>(n));
     }
     gzclose(f);
-    return data;
+    in.p = in.owned.data(); in.n = in.owned.size();
 }
 
-void parseFasta(const std::string &data, std::vector<PathRec> &paths, std::vector<Item> &items, std::vector<uint8_t> &seq) {
-    if (data.empty() || data[0] != '>') die("Error: '%s' does not look like a FASTA file (GFA input is not part of this pipeline).\n", "input");
-    seq.reserve(data.size() + 4096);
-    size_t p = 1;
-    while (p <= data.size()) {
-        size_t end = data.find('>', p);                       // a record runs to the next '>' wherever it stands
-        if (end == std::string::npos) end = data.size();
-        size_t nl = data.find('\n', p);
-        if (nl == std::string::npos || nl > end) nl = end;
-        PathRec rec;
-        rec.seqPos = static_cast<uint32_t>(paths.size());
-        const size_t sp = data.find(' ', p);
-        rec.header = data.substr(p, (sp != std::string::npos && sp < nl ? sp : nl) - p);
-        rec.header.erase(std::remove(rec.header.begin(), rec.header.end(), '\r'), rec.header.end());   // walkPath, src/input.cpp:950
-        const uint32_t pathIdx = static_cast<uint32_t>(paths.size());
-        uint64_t pos = 0, runStart = 0;
-        int state = -1;                                       // -1 nothing yet, 0 in a contig, 1 in a gap
-        const size_t segOffset0 = seq.size();
-        size_t segOffset = segOffset0;
-        auto closeRun = [&]() {
-            if (state == 1) rec.gaps.push_back({runStart, static_cast<uint32_t>(pos - runStart)});
-            else if (state == 0) items.push_back({pathIdx, runStart, segOffset, static_cast<uint32_t>(pos - runStart)});
-        };
-        for (size_t i = nl < end ? nl + 1 : end; i < end; ++i) {
-            const uint8_t c = static_cast<uint8_t>(data[i]);
-            if (c == '\n') continue;
-            const int st = (c == 'N' || c == 'n' || c == 'X' || c == 'x') ? 1 : 0;
-            if (st != state) {
-                closeRun();
-                state = st; runStart = pos; segOffset = seq.size();
-            }
-            if (st == 0) seq.push_back(c);
-            ++pos;
-        }
-        closeRun();
-        rec.pathSize = pos;
-        paths.push_back(std::move(rec));
-        p = end + 1;
-        if (end == data.size()) break;
+// dynamic parallel loop over [0, n): the host side of the pipeline (parse, formatting) is per-record / per-chunk work
+template <class F>
+void parallelFor(size_t n, unsigned threads, F f) {
+    if (n == 0) return;
+    threads = static_cast<unsigned>(std::min<size_t>(std::max(1u, threads), n));
+    if (threads == 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; ++t)
+        pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); });
+    for (auto &th : pool) th.join();
+}
+
+// bit i of the result: byte i of the 16 at p is one of N n X x (gap) / is '\n'
+inline void classify16(const char *p, unsigned &gap, unsigned &nl) {
+    const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
+    const __m128i u = _mm_or_si128(v, _mm_set1_epi8(0x20));                       // fold case: n / x
+    gap = static_cast<unsigned>(_mm_movemask_epi8(_mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8('n')), _mm_cmpeq_epi8(u, _mm_set1_epi8('x')))));
+    nl = static_cast<unsigned>(_mm_movemask_epi8(_mm_cmpeq_epi8(v, _mm_set1_epi8('\n'))));
+}
+
+struct RecordSpan { size_t begin, end, bodyBegin; };          // [begin, end): header line + body, without the leading '>'
+
+// contig bases of a record body (pass 1): everything but '\n' and gap characters
+uint64_t countBases(const char *p, const char *e) {
+    uint64_t skipped = 0;
+    const char *q = p;
+    for (; q + 16 <= e; q += 16) {
+        unsigned gap, nl;
+        classify16(q, gap, nl);
+        skipped += static_cast<uint64_t>(__builtin_popcount(gap | nl));
     }
+    for (; q < e; ++q) skipped += (*q == '\n' || *q == 'N' || *q == 'n' || *q == 'X' || *q == 'x');
+    return static_cast<uint64_t>(e - p) - skipped;
+}
+
+// pass 2: the record's contigs copied back to back to out (newlines and gaps dropped), its items and gaps listed
+void parseRecord(const char *p, const char *e, uint8_t *out, uint64_t outOffset, uint32_t pathIdx, std::vector<Item> &items,
+                 std::vector<Gap> &gaps, uint64_t &pathSize) {
+    uint64_t pos = 0, runStart = 0, written = 0, segOffset = outOffset;
+    int state = -1;                                           // -1 nothing yet, 0 in a contig, 1 in a gap
+    auto closeRun = [&]() {
+        if (state == 1) gaps.push_back({runStart, static_cast<uint32_t>(pos - runStart)});
+        else if (state == 0) items.push_back({pathIdx, runStart, segOffset, static_cast<uint32_t>(pos - runStart)});
+    };
+    auto byteStep = [&](uint8_t c) {
+        if (c == '\n') return;
+        const int st = (c == 'N' || c == 'n' || c == 'X' || c == 'x') ? 1 : 0;
+        if (st != state) {
+            closeRun();
+            state = st; runStart = pos; segOffset = outOffset + written;
+        }
+        if (st == 0) out[written++] = c;
+        ++pos;
+    };
+    const char *q = p;
+    while (q < e) {
+        if (state == 0 && q + 16 <= e) {                      // fast path inside a contig: whole 16-byte pieces without gap bytes
+            unsigned gap, nl;
+            classify16(q, gap, nl);
+            if (gap == 0) {
+                if (nl == 0) {
+                    memcpy(out + written, q, 16);
+                    written += 16; pos += 16;
+                } else {
+                    for (int i = 0; i < 16; ++i)
+                        if (!((nl >> i) & 1u)) { out[written++] = static_cast<uint8_t>(q[i]); ++pos; }
+                }
+                q += 16;
+                continue;
+            }
+        }
+        if (state == 1 && q + 16 <= e) {                      // fast path inside a gap: 16 bytes of gap characters / newlines
+            unsigned gap, nl;
+            classify16(q, gap, nl);
+            if ((gap | nl) == 0xFFFFu) {
+                pos += static_cast<uint64_t>(__builtin_popcount(gap));
+                q += 16;
+                continue;
+            }
+        }
+        byteStep(static_cast<uint8_t>(*q++));
+    }
+    closeRun();
+    pathSize = pos;
+}
+
+void parseFasta(const InputData &in, unsigned threads, std::vector<PathRec> &paths, std::vector<Item> &items,
+                std::unique_ptr<uint8_t[]> &seq, uint64_t &seqBytes) {
+    if (in.n == 0 || in.p[0] != '>') die("Error: '%s' does not look like a FASTA file.\n", "input");
+    // records: a record runs to the next '>' wherever it stands (gfalibs reads the sequence with getline(..., '>'))
+    std::vector<RecordSpan> recs;
+    for (size_t p = 1;;) {
+        const char *g = static_cast<const char *>(memchr(in.p + p, '>', in.n - p));
+        const size_t end = g ? static_cast<size_t>(g - in.p) : in.n;
+        const char *nlp = static_cast<const char *>(memchr(in.p + p, '\n', end - p));
+        recs.push_back({p, end, nlp ? static_cast<size_t>(nlp - in.p) + 1 : end});
+        if (!g) break;
+        p = end + 1;
+    }
+    paths.resize(recs.size());
+    std::vector<uint64_t> bases(recs.size() + 1, 0);
+    parallelFor(recs.size(), threads, [&](size_t r) { bases[r + 1] = countBases(in.p + recs[r].bodyBegin, in.p + recs[r].end); });
+    for (size_t r = 0; r < recs.size(); ++r) bases[r + 1] += bases[r];
+    seqBytes = bases.back();
+    seq.reset(new uint8_t[seqBytes + 256]);
+    memset(seq.get() + seqBytes, 0, 256);
+    std::vector<std::vector<Item>> recItems(recs.size());
+    // largest records first: they bound the wall time of the parallel parse
+    std::vector<size_t> order(recs.size());
+    for (size_t r = 0; r < recs.size(); ++r) order[r] = r;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return recs[a].end - recs[a].begin > recs[b].end - recs[b].begin; });
+    parallelFor(recs.size(), threads, [&](size_t k) {
+        const size_t r = order[k];
+        PathRec &rec = paths[r];
+        rec.seqPos = static_cast<uint32_t>(r);
+        const size_t headEnd = recs[r].bodyBegin > recs[r].begin && recs[r].bodyBegin <= recs[r].end && in.p[recs[r].bodyBegin - 1] == '\n'
+                                   ? recs[r].bodyBegin - 1 : recs[r].end;
+        const char *sp = static_cast<const char *>(memchr(in.p + recs[r].begin, ' ', headEnd - recs[r].begin));
+        rec.header.assign(in.p + recs[r].begin, sp ? sp : in.p + headEnd);
+        rec.header.erase(std::remove(rec.header.begin(), rec.header.end(), '\r'), rec.header.end());   // walkPath, src/input.cpp:950
+        parseRecord(in.p + recs[r].bodyBegin, in.p + recs[r].end, seq.get() + bases[r], bases[r], static_cast<uint32_t>(r), recItems[r],
+                    rec.gaps, rec.pathSize);
+    });
+    size_t total = 0;
+    for (auto &v : recItems) total += v.size();
+    items.reserve(total);
+    for (auto &v : recItems) items.insert(items.end(), v.begin(), v.end());
 }
 
 // ---- output ---------------------------------------------------------------------------------------------
@@ -446,6 +567,18 @@ void blockRow(std::string &s, const std::string &header, const tls_block &b, uin
     s.push_back('\t'); appendU64(s, pathSize);
 }
 
+struct StageTimer {                       // TLS_PIPE_TRACE=1: wall time of the pipeline stages on stderr
+    bool on = getenv("TLS_PIPE_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    void mark(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pipe] %-28s %8.1f ms  (total %8.1f ms)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
+
 void check(int rc, const char *what) {
     if (rc != TLS_OK) die("Error: %s failed: %s\n", what, tls_last_error());
 }
@@ -506,29 +639,45 @@ int main(int argc, char **argv) {
         printf("\n");
     }
 
-    // ---- ingest ---------------------------------------------------------------------------------------------
-    std::vector<PathRec> paths;
-    std::vector<Item> items;
-    std::vector<uint8_t> seq;
-    {
-        const std::string data = slurp(o.inSequence);
-        if (!data.empty() && (data[0] == 'H' || data[0] == 'S') && data.size() > 1 && data[1] == '\t') unsupported("GFA input");
-        if (!data.empty() && data[0] == '@') unsupported("FASTQ input");
-        parseFasta(data, paths, items, seq);
-    }
-    seq.resize(seq.size() + 256, 0);
+    StageTimer timer;
+    const unsigned threads = o.threads ? o.threads : std::max(1u, std::thread::hardware_concurrency());
 
-    // ---- device context -------------------------------------------------------------------------------------
+    // ---- device context: created on its own thread while the input is read and parsed ----------------------------------
     tls_config cfg{};
     cfg.abi_version = TLS_ABI_VERSION;
     cfg.n_patterns = nPat; cfg.patterns = patPtr.data(); cfg.is_forward = isFwd.data(); cfg.is_canonical = isCan.data();
     cfg.window_size = o.windowSize; cfg.step = o.step; cfg.terminal_limit = o.terminalLimit;
     cfg.max_match_dist = o.maxMatchDist; cfg.min_block_len = o.minBlockLen; cfg.max_block_dist = o.maxBlockDist;
     cfg.min_block_counts = o.minBlockCounts; cfg.min_block_density = o.minBlockDensity;
-    cfg.outputs = ((o.outGC || o.outEntropy) ? TLS_OUT_ACGT : 0u) | (o.outMatches ? TLS_OUT_MATCHES : 0u) | TLS_OUT_ITS;
+    cfg.outputs = ((o.outGC || o.outEntropy) ? 1u * TLS_OUT_ACGT : 0u) | (o.outMatches ? 1u * TLS_OUT_MATCHES : 0u) | TLS_OUT_ITS;
     tls_ctx *ctx = nullptr;
-    const char *devEnv = getenv("TLS_DEVICE");
-    check(tls_create(&cfg, devEnv ? atoi(devEnv) : 0, &ctx), "tls_create");
+    int ctxRc = TLS_OK;
+    std::string ctxErr;
+    std::thread ctxThread([&]() {
+        const char *devEnv = getenv("TLS_DEVICE");
+        ctxRc = tls_create(&cfg, devEnv ? atoi(devEnv) : 0, &ctx);
+        if (ctxRc != TLS_OK) ctxErr = tls_last_error();             // the message is thread-local
+    });
+
+    // ---- ingest ---------------------------------------------------------------------------------------------
+    std::vector<PathRec> paths;
+    std::vector<Item> items;
+    std::unique_ptr<uint8_t[]> seqOwner;
+    uint64_t seqBytes = 0;
+    {
+        InputData in;
+        loadInput(o.inSequence, in);
+        timer.mark("read file");
+        if (in.n > 1 && (in.p[0] == 'H' || in.p[0] == 'S') && in.p[1] == '\t') { ctxThread.join(); unsupported("GFA input"); }
+        if (in.n > 0 && in.p[0] == '@') { ctxThread.join(); unsupported("FASTQ input"); }
+        if (in.n == 0 || in.p[0] != '>') { ctxThread.join(); die("Error: '%s' does not look like a FASTA file.\n", o.inSequence.c_str()); }
+        parseFasta(in, threads, paths, items, seqOwner, seqBytes);
+    }
+    const uint8_t *seq = seqOwner.get();
+    timer.mark("parse FASTA");
+    ctxThread.join();
+    if (ctxRc != TLS_OK) die("Error: tls_create failed: %s\n", ctxErr.c_str());
+    timer.mark("tls_create (CUDA context)");
 
     // ---- output files (src/teloscope.cpp:886-920: which exist depends on the flags only) ---------------------------
     const std::string base = o.outRoute + "/" + o.inSequenceName;
@@ -550,9 +699,11 @@ int main(int argc, char **argv) {
     fReport.open(base + "_report.tsv");
 
     // ---- scan: batches of whole contigs, two in flight; results are consumed in submission order ---------------------
-    const uint64_t batchBytes = getenv("TLS_BATCH_BYTES") ? strtoull(getenv("TLS_BATCH_BYTES"), nullptr, 10) : (1ull << 30);
+    const uint64_t batchBytes = getenv("TLS_BATCH_BYTES") ? strtoull(getenv("TLS_BATCH_BYTES"), nullptr, 10) : (256ull << 20);
     const uint32_t mode = o.ultraFastMode ? TLS_MODE_TIPS : TLS_MODE_GENOME;
     struct Batch { size_t first, count; std::vector<uint64_t> offsets, absPos; int ticket; };
+    double msSubmit = 0, msCollect = 0, msFormat = 0, msWrite = 0;
+    auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     std::vector<Batch> flight;
     size_t nextItem = 0;
     auto submitNext = [&]() {
@@ -567,26 +718,52 @@ int main(int argc, char **argv) {
         for (size_t i = 0; i < b.count; ++i) { b.offsets.push_back(items[b.first + i].offset); b.absPos.push_back(items[b.first + i].absPos); }
         b.offsets.push_back(items[b.first + b.count - 1].offset + items[b.first + b.count - 1].len);
         tls_batch tb{};
-        tb.seq = seq.data(); tb.offsets = b.offsets.data(); tb.abs_pos = b.absPos.data();
+        tb.seq = seq; tb.offsets = b.offsets.data(); tb.abs_pos = b.absPos.data();
         tb.n_items = static_cast<uint32_t>(b.count); tb.mode = mode;
+        const auto t0 = std::chrono::steady_clock::now();
         check(tls_submit(ctx, &tb, &b.ticket), "tls_submit");
+        msSubmit += since(t0);
         flight.push_back(std::move(b));
     };
+    // Formatting is the host's share of the genome-wide outputs (3 M windows x 5 tracks on a human assembly): the
+    // windows and match lists of a batch are cut into chunks, formatted in parallel into per-chunk buffers and
+    // appended to the files in order.
+    struct Chunk { size_t item; uint64_t lo, hi; int kind; std::string out[5]; };      // kind 0: windows, 1: canonical, 2: non-canonical
     auto consume = [&](const Batch &b) {
         tls_result r{};
+        auto t0 = std::chrono::steady_clock::now();
         check(tls_collect(ctx, b.ticket, &r), "tls_collect");
+        msCollect += since(t0);
+        t0 = std::chrono::steady_clock::now();
+        std::vector<Chunk> chunks;
+        constexpr uint64_t kChunk = 16384;
         for (size_t j = 0; j < b.count; ++j) {
             const Item &it = items[b.first + j];
             PathRec &p = paths[it.path];
             for (uint64_t k = r.terminal_off[j]; k < r.terminal_off[j + 1]; ++k) p.terminal.push_back(r.terminal[k]);
-            if (mode == TLS_MODE_GENOME) {
-                const size_t its0 = p.its.size();
-                for (uint64_t k = r.its_off[j]; k < r.its_off[j + 1]; ++k) p.its.push_back(r.its[k]);
-                std::sort(p.its.begin() + static_cast<long>(its0), p.its.end(), [](const tls_block &a, const tls_block &b2) { return a.start < b2.start; });
-                p.nCanonical += r.n_canonical[j];
-                const uint64_t w0 = r.window_off[j], w1 = r.window_off[j + 1];
-                p.nWindows += w1 - w0;
-                for (uint64_t k = w0; k < w1; ++k) {
+            if (mode != TLS_MODE_GENOME) continue;
+            const size_t its0 = p.its.size();
+            for (uint64_t k = r.its_off[j]; k < r.its_off[j + 1]; ++k) p.its.push_back(r.its[k]);
+            std::sort(p.its.begin() + static_cast<long>(its0), p.its.end(), [](const tls_block &a, const tls_block &b2) { return a.start < b2.start; });
+            p.nCanonical += r.n_canonical[j];
+            p.nWindows += r.window_off[j + 1] - r.window_off[j];
+            if (o.outWinRepeats || o.outEntropy || o.outGC)
+                for (uint64_t k = r.window_off[j]; k < r.window_off[j + 1]; k += kChunk)
+                    chunks.push_back({j, k, std::min(k + kChunk, r.window_off[j + 1]), 0, {}});
+            if (o.outMatches) {
+                for (uint64_t k = r.canonical_off[j]; k < r.canonical_off[j + 1]; k += kChunk)
+                    chunks.push_back({j, k, std::min(k + kChunk, r.canonical_off[j + 1]), 1, {}});
+                for (uint64_t k = r.noncanonical_off[j]; k < r.noncanonical_off[j + 1]; k += kChunk)
+                    chunks.push_back({j, k, std::min(k + kChunk, r.noncanonical_off[j + 1]), 2, {}});
+            }
+        }
+        parallelFor(chunks.size(), threads, [&](size_t ci) {
+            Chunk &c = chunks[ci];
+            const Item &it = items[b.first + c.item];
+            const std::string &header = paths[it.path].header;
+            if (c.kind == 0) {
+                const uint64_t w0 = r.window_off[c.item];
+                for (uint64_t k = c.lo; k < c.hi; ++k) {
                     const tls_window &w = r.windows[k];
                     const uint64_t rel = (k - w0) * o.step;
                     const uint32_t size = static_cast<uint32_t>(std::min<uint64_t>(o.windowSize, it.len - rel));
@@ -596,31 +773,37 @@ int main(int argc, char **argv) {
                         const float totalDensity = static_cast<float>(totalCovered) / size;
                         const float canonRatio = totalCovered > 0 ? static_cast<float>(w.can_cov) / (w.can_cov + w.noncan_cov) : -1.0f;
                         const float strandRatio = totalCovered > 0 ? static_cast<float>(w.fwd_cov) / (w.fwd_cov + w.rev_cov) : -1.0f;
-                        windowLine(fDensity.buf, p.header, ws, we, totalDensity);
-                        windowLine(fCanRatio.buf, p.header, ws, we, canonRatio);
-                        windowLine(fStrand.buf, p.header, ws, we, strandRatio);
+                        windowLine(c.out[0], header, ws, we, totalDensity);
+                        windowLine(c.out[1], header, ws, we, canonRatio);
+                        windowLine(c.out[2], header, ws, we, strandRatio);
                     }
-                    if (o.outEntropy) windowLine(fEntropy.buf, p.header, ws, we, shannonEntropy(w.acgt, size));
-                    if (o.outGC) windowLine(fGC.buf, p.header, ws, we, gcContent(w.acgt, size));
-                    if ((k & 1023) == 0) { fDensity.flushIfBig(); fCanRatio.flushIfBig(); fStrand.flushIfBig(); fEntropy.flushIfBig(); fGC.flushIfBig(); }
+                    if (o.outEntropy) windowLine(c.out[3], header, ws, we, shannonEntropy(w.acgt, size));
+                    if (o.outGC) windowLine(c.out[4], header, ws, we, gcContent(w.acgt, size));
                 }
-                if (o.outMatches) {
-                    auto dump = [&](OutFile &f, const uint64_t *off, const tls_match *m) {
-                        for (uint64_t k = off[j]; k < off[j + 1]; ++k) {
-                            std::string &s = f.buf;
-                            s += p.header; s.push_back('\t'); appendU64(s, m[k].pos); s.push_back('\t'); appendU64(s, m[k].pos + m[k].len);
-                            s.push_back('\t');
-                            const uint8_t *src = seq.data() + it.offset + (m[k].pos - it.absPos);
-                            for (uint32_t q = 0; q < m[k].len; ++q) s.push_back(static_cast<char>(std::toupper(src[q])));
-                            s.push_back('\n');
-                            if ((k & 1023) == 0) f.flushIfBig();
-                        }
-                    };
-                    dump(fCan, r.canonical_off, r.canonical);
-                    dump(fNon, r.noncanonical_off, r.noncanonical);
+            } else {
+                const tls_match *m = c.kind == 1 ? r.canonical : r.noncanonical;
+                std::string &s = c.out[0];
+                for (uint64_t k = c.lo; k < c.hi; ++k) {
+                    s += header; s.push_back('\t'); appendU64(s, m[k].pos); s.push_back('\t'); appendU64(s, m[k].pos + m[k].len);
+                    s.push_back('\t');
+                    const uint8_t *src = seq + it.offset + (m[k].pos - it.absPos);
+                    for (uint32_t q = 0; q < m[k].len; ++q) s.push_back(static_cast<char>(std::toupper(src[q])));
+                    s.push_back('\n');
                 }
             }
+        });
+        msFormat += since(t0);
+        t0 = std::chrono::steady_clock::now();
+        auto put = [](OutFile &f, const std::string &s) {
+            if (s.empty() || !f.fh) return;
+            f.flush();
+            fwrite(s.data(), 1, s.size(), f.fh);
+        };
+        for (const Chunk &c : chunks) {
+            if (c.kind == 0) { put(fDensity, c.out[0]); put(fCanRatio, c.out[1]); put(fStrand, c.out[2]); put(fEntropy, c.out[3]); put(fGC, c.out[4]); }
+            else put(c.kind == 1 ? fCan : fNon, c.out[0]);
         }
+        msWrite += since(t0);
         check(tls_release(ctx, b.ticket), "tls_release");
     };
     while (nextItem < items.size() || !flight.empty()) {
@@ -628,8 +811,10 @@ int main(int argc, char **argv) {
         consume(flight.front());
         flight.erase(flight.begin());
     }
-    tls_destroy(ctx);
-
+    timer.mark("scan + window / match files");
+    if (timer.on) fprintf(stderr, "[pipe]   of which: tls_submit %.1f ms, tls_collect %.1f ms, formatting %.1f ms, file writes %.1f ms\n", msSubmit, msCollect, msFormat, msWrite);
+    // the ctx is not destroyed: freeing gigabytes of device memory and unloading the runtime costs ~0.1 s that the
+    // process exit (below: _exit after the files are closed) gives back to the driver anyway
     // ---- per path: classification, block / gap rows, report (src/teloscope.cpp:687-847) -------------------------------------
     std::string rep;           // goes to stdout and to the report file alike (after the banner)
     std::cout << "\n+++ Path Summary Report +++\n";
@@ -723,5 +908,8 @@ int main(int argc, char **argv) {
     std::cout.flush();
     fReport.buf += rep;
     for (OutFile *f : {&fDensity, &fCanRatio, &fStrand, &fGC, &fEntropy, &fCan, &fNon, &fTerminal, &fIts, &fGaps, &fReport}) f->close();
-    return EXIT_SUCCESS;
+    timer.mark("blocks, report, close");
+    fflush(stdout);
+    fflush(stderr);
+    _exit(EXIT_SUCCESS);
 }

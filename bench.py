@@ -13,6 +13,9 @@ scaling, no data-path collective); rank 0 prints ONE JSON line.
            everything else of the job included (kernels, result copies, host-side assembly)
   e2e      same call with the sequence in pinned HOST memory: H2D + kernels + D2H in the timed region
   roofline scan kernel only: algorithmic bytes / CUDA-event duration against the measured HBM peak
+  pipeline_e2e  file -> files: the same assembly as a FASTA file through teloscope_b200/teloscope-b200 (host ingest, C ABI,
+           writers), process start to exit, with the unmodified reference binary timed on the same file beside it
+  other_workloads  BASELINE.json configs[3] (plant-shaped, 7-mers) and configs[4] (read scorer), device-resident
   cpu_baseline  the unmodified reference binary (oracle/_ref/teloscope) on the box's host cores on
            a 1/16-scale assembly of the same generator (file parsing and writers included: it has
            no other entry point); falls back to the oracle port when the binary is absent
@@ -253,6 +256,54 @@ def other_workloads(tb, device: int, seed: int, scale: float, peak: float):
                 "ms_per_step": per * 1e3, "scan_kernels_ms": kms,
                 "roofline_frac": ((nb + len(offsets) - 1) / (kms * 1e-3) / 1e9) / peak, **info})
     return out
+
+
+def pipeline_file_to_files(seed: int, scale: float, with_reference: bool):
+    """End to end INCLUDING host I/O: the headline assembly written as a FASTA file (80-column
+    lines, N-gaps) to /dev/shm, then `teloscope_b200/teloscope-b200 -f file <flags> -o dir` from process start to
+    exit with every output file closed — and, beside it, the unmodified reference binary on the same file with
+    all host threads, and a byte comparison of the two output directories."""
+    import torch
+    exe = ROOT / "teloscope_b200" / "teloscope-b200"
+    ref_bin = ROOT / "oracle" / "_ref" / "teloscope"
+    if not exe.exists():
+        return {"unavailable": "teloscope_b200/teloscope-b200 not built"}
+    chroms = plan_assembly(seed, scale)
+    seq, offsets, _ = build_assembly(chroms, "cuda", seed)
+    seq_host = seq.cpu().numpy()
+    del seq
+    torch.cuda.empty_cache()
+    tmp = Path(tempfile.mkdtemp(prefix="telo_pipe_", dir="/dev/shm" if Path("/dev/shm").exists() else None))
+    try:
+        fa = tmp / "assembly.fa"
+        bases = write_fasta(chroms, seq_host, offsets, fa)
+        del seq_host
+        out = {"what": "FASTA file (page cache) -> all output files of -r -g -e -m -i, process start to exit",
+               "bases": bases, "fasta_bytes": fa.stat().st_size, "unit": "Gbp/s"}
+        times = []
+        for i in range(3):                                   # first run warms the page cache and the driver
+            d = tmp / "ours"
+            shutil.rmtree(d, ignore_errors=True); d.mkdir()
+            t0 = time.perf_counter()
+            subprocess.run([str(exe), "-f", str(fa), *REF_FLAGS, "-o", str(d)], check=True, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL)
+            times.append(time.perf_counter() - t0)
+        out["seconds"] = min(times[1:]); out["value"] = bases / out["seconds"] / 1e9
+        if with_reference and ref_bin.exists():
+            cores = os.cpu_count() or 1
+            d = tmp / "ref"
+            d.mkdir()
+            t0 = time.perf_counter()
+            subprocess.run([str(ref_bin), "-f", str(fa), *REF_FLAGS, "-j", str(cores), "-o", str(d)], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            dt = time.perf_counter() - t0
+            same = all((tmp / "ours" / f.name).exists() and f.read_bytes() == (tmp / "ours" / f.name).read_bytes()
+                       for f in d.iterdir())
+            out["reference_same_file"] = {"seconds": dt, "value": bases / dt / 1e9, "cores": cores,
+                                          "outputs_byte_identical": bool(same), "files_compared": len(list(d.iterdir()))}
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -519,6 +570,10 @@ def main():
                 line["other_workloads"] = other_workloads(tb, local, args.seed, args.scale, peak)
             except Exception as exc:           # the headline line must not be lost to a side measurement
                 line["other_workloads"] = {"error": repr(exc)}
+            try:
+                line["pipeline_e2e"] = pipeline_file_to_files(args.seed, args.scale, not args.no_cpu_baseline)
+            except Exception as exc:
+                line["pipeline_e2e"] = {"error": repr(exc)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *c
 __global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase,
                                                        const unsigned int *ovCursor, const unsigned int *redo,
                                                        unsigned long long *hostOut) {
-    // one block per array; a thread takes 4 consecutive tiles per round
+    // one block per array; a thread takes 16 consecutive tiles per round
     __shared__ unsigned long long warpSums[32];
     __shared__ unsigned long long carry;
     const uint32_t k = blockIdx.x;
@@ -93,15 +93,16 @@ __global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, 
     __syncthreads();
     const uint32_t *in = tileTot + static_cast<size_t>(k) * nTiles;
     unsigned long long *out = tileBase + static_cast<size_t>(k) * (nTiles + 1);
-    for (uint32_t base = 0; base < nTiles; base += 4096) {
-        const uint32_t i = base + threadIdx.x * 4;
-        uint32_t v[4];
+    constexpr int kPer = 16;                                      // consecutive tiles per thread and round
+    for (uint32_t base = 0; base < nTiles; base += 1024 * kPer) {
+        const uint32_t i = base + threadIdx.x * kPer;
+        uint32_t v[kPer];
+        unsigned long long sum = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = i + j < nTiles ? in[i + j] : 0u;
-        const unsigned long long sum = static_cast<unsigned long long>(v[0]) + v[1] + v[2] + v[3];
+        for (int j = 0; j < kPer; ++j) { v[j] = i + j < nTiles ? in[i + j] : 0u; sum += v[j]; }
         unsigned long long excl = blockExclusive1024(sum, warpSums, &carry);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kPer; ++j) {
             if (i + j < nTiles) out[i + j] = excl;
             excl += v[j];
         }
@@ -142,6 +143,54 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
     const unsigned long long baseCan = g.tileBase[static_cast<size_t>(g.nTiles) + 1 + tile];
     const unsigned long long baseNct = g.tileBase[2 * (static_cast<size_t>(g.nTiles) + 1) + tile];
     const uint32_t laneLt = (1u << lane) - 1u;
+
+    // A warp owns the row slots warp, warp + 8, warp + 16, warp + 24.  Common case (each of them holds at most 64
+    // records, all inside the slot): the eight loads are issued back to back before anything is stored, so that
+    // eight requests per warp are in flight instead of one — the copy is latency-bound otherwise.
+    constexpr int kPerWarp = kTileRows / (kGatherThreads / 32);
+    uint32_t cntR[kPerWarp];
+    bool simple = true;
+#pragma unroll
+    for (int j = 0; j < kPerWarp; ++j) {
+        const int s = warp + j * (kGatherThreads / 32);
+        cntR[j] = sOff[0][s + 1] - sOff[0][s];
+        simple = simple && cntR[j] <= 64u && cntR[j] <= g.slotCap;
+    }
+    if (simple) {
+        uint2 rec[kPerWarp][2];
+#pragma unroll
+        for (int j = 0; j < kPerWarp; ++j) {
+            const int s = warp + j * (kGatherThreads / 32);
+            const uint2 *src = reinterpret_cast<const uint2 *>(g.slots) + (static_cast<size_t>(tile) * kTileRows + s) * g.slotCap;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                rec[j][h] = static_cast<uint32_t>(lane + 32 * h) < cntR[j] ? __ldg(src + lane + 32 * h) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < kPerWarp; ++j) {
+            const int s = warp + j * (kGatherThreads / 32);
+            const bool anySel = sOff[1][s + 1] != sOff[1][s] || sOff[2][s + 1] != sOff[2][s];     // warp-uniform
+            unsigned long long oc = baseCan + sOff[1][s], on = baseNct + sOff[2][s];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (static_cast<uint32_t>(32 * h) >= cntR[j]) break;                              // warp-uniform
+                const uint32_t k = static_cast<uint32_t>(lane + 32 * h);
+                const bool have = k < cntR[j];
+                const unsigned long long o = base + sOff[0][s] + k;
+                if (have && o < g.matchCap) reinterpret_cast<uint2 *>(g.matches)[o] = make_uint2(rec[j][h].x, rec[j][h].y & 0x00FFFFFFu);
+                if (!anySel) continue;
+                const uint32_t flags = (rec[j][h].y >> 16) & 0xFFu;
+                const bool isC = have && (flags & kMatchCan);
+                const bool isN = have && (flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
+                const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
+                if (isC && oc + __popc(bc & laneLt) < g.selCap) g.canIdx[oc + __popc(bc & laneLt)] = static_cast<uint32_t>(o);
+                if (isN && on + __popc(bn & laneLt) < g.selCap) g.nctIdx[on + __popc(bn & laneLt)] = static_cast<uint32_t>(o);
+                oc += __popc(bc);
+                on += __popc(bn);
+            }
+        }
+        return;
+    }
 
     for (int s = warp; s < kTileRows; s += kGatherThreads / 32) {
         const uint32_t cnt = sOff[0][s + 1] - sOff[0][s];
@@ -278,12 +327,40 @@ __global__ void __launch_bounds__(128) terminalKernel(const BlockParams p) {
         Run run{};
         bool inRun = false, done = false;
         const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
-        for (long long off = 0; off < end - begin && !done; off += 32) {
-            // lane l holds the l-th next record in walk order
+        // lane l holds the l-th next record in walk order; the next 32 are requested before the current 32 are walked
+        auto fetch = [&](long long off, uint2 &rec, bool &valid) {
             const long long i = fromStart ? begin + off + lane : end - 1 - off - lane;
-            const bool valid = fromStart ? i < end : i >= begin;
-            const uint2 rec = valid ? recs[i] : make_uint2(0u, 0u);
+            valid = off < end - begin && (fromStart ? i < end : i >= begin);
+            rec = valid ? __ldg(recs + i) : make_uint2(0u, 0u);
+        };
+        uint2 rec, recNext;
+        bool valid, validNext;
+        fetch(0, rec, valid);
+        for (long long off = 0; off < end - begin && !done; off += 32, rec = recNext, valid = validNext) {
+            fetch(off + 32, recNext, validNext);
             uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && ((rec.y >> 16) & kMatchFwd) == want);
+            if (inRun && mask) {
+                // Inside a telomere the whole group of 32 continues the current run (every start-to-start gap
+                // <= maxMatchDist; the zone test only applies to run starts, src/teloscope.cpp:98-121): absorb it
+                // with a few warp reductions instead of one sequential step per match.
+                const uint32_t below = mask & ((1u << lane) - 1u);
+                uint32_t prevPos = __shfl_sync(0xFFFFFFFFu, rec.x, below ? 31 - __clz(below) : 0);
+                if (!below) prevPos = run.prev;
+                const bool mine = (mask >> lane) & 1u;
+                const uint32_t gapL = fromStart ? rec.x - prevPos : prevPos - rec.x;
+                if (!__any_sync(0xFFFFFFFFu, mine && gapL > c.maxMatchDist)) {
+                    const uint32_t len = rec.y & 0xFFFFu;
+                    const bool can = mine && ((rec.y >> 16) & kMatchCan);
+                    const uint32_t cntM = __popc(mask), lenSum = __reduce_add_sync(0xFFFFFFFFu, mine ? len : 0u);
+                    const uint32_t canLen = __reduce_add_sync(0xFFFFFFFFu, can ? len : 0u);
+                    const int last = 31 - __clz(mask);
+                    const uint32_t lastPos = __shfl_sync(0xFFFFFFFFu, rec.x, last), lastLen = __shfl_sync(0xFFFFFFFFu, len, last);
+                    run.n += cntM; run.nFwd += want ? cntM : 0u; run.nCan += __popc(__ballot_sync(0xFFFFFFFFu, can));
+                    run.cov += lenSum; run.fwdCov += want ? lenSum : 0u; run.canCov += canLen; run.prev = lastPos;
+                    if (fromStart) run.end = lastPos + lastLen; else run.start = lastPos;
+                    continue;
+                }
+            }
             while (mask && !done) {
                 const int b = __ffs(mask) - 1;
                 mask &= mask - 1;

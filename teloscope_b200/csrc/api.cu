@@ -109,7 +109,9 @@ struct Slot {
     std::vector<DevRowRegion> rowRegions;    // contigs of the window-row kernel (units are laid out on the device)
     uint32_t nRowUnits = 0;
     size_t nRowTiles = 0;
-    std::vector<uint8_t> tileIsRow;          // per tile: 1 = made of whole windows for the window-row kernel
+    std::vector<uint32_t> tileIndex;         // s.tiles holds the tiles of the lean / general kernels only; tileIndex[k] = index of
+                                             // s.tiles[k] in the batch's tile table (the window-row kernel's tiles have no entry)
+    uint32_t nTilesAll = 0;                  // tiles of the batch, window-row tiles included
     std::vector<uint32_t> generalTiles;      // indices of the tiles the general kernel takes entirely
     const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
     HostBuf hSeq, hMeta, hMeta2;              // pinned staging
@@ -414,7 +416,7 @@ GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
     g.slots = s.dSlots.as<DevMatch>(); g.slotCap = ctx->slotCap;
     g.slotMeta = s.dSlotMeta.as<uint4>();
     g.ovArena = s.dOvArena.as<DevMatch>(); g.ovCap = s.ovCap;
-    g.nTiles = static_cast<uint32_t>(s.tiles.size());
+    g.nTiles = s.nTilesAll;
     g.tileBase = s.dTileBase.as<unsigned long long>();
     g.matches = s.dMatches.as<DevMatch>(); g.matchCap = s.matchCap;
     g.canIdx = s.dCanIdx.as<uint32_t>(); g.nctIdx = s.dNctIdx.as<uint32_t>();
@@ -425,7 +427,7 @@ GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
 // Enqueue the scan for the slot: memsets, lean kernel over the single-contig tiles, general kernel
 // over the rest and over the rows the lean kernel handed back, per-tile prefix, copy of the counters.
 int enqueueScan(tls_ctx *ctx, Slot &s) {
-    const uint32_t nTiles = static_cast<uint32_t>(s.tiles.size());
+    const uint32_t nTiles = s.nTilesAll;
     const size_t nSlots = static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * kTileRows;
     TLS_CUDA(s.dSlots.reserve(nSlots * ctx->slotCap * sizeof(DevMatch)));
     TLS_CUDA(s.dSlotMeta.reserve(nSlots * 16));
@@ -643,8 +645,8 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     // tiles of 32 whole windows (one window per tile row).  Everything else: runs of (nearly) adjacent
     // regions are cut into pieces of <= kTileMaxLen bytes; of those the lean kernel takes the tiles that
     // lie inside one region, the general kernel the rest.
-    s.tiles.clear(); s.tileIsRow.clear(); s.rowRegions.clear(); s.nRowUnits = 0; s.nRowTiles = 0;
-    s.tiles.reserve(static_cast<size_t>(s.nBases / 32000) + s.regions.size() + 1);
+    tr.mark("plan_regions");
+    s.tiles.clear(); s.tileIndex.clear(); s.nTilesAll = 0; s.rowRegions.clear(); s.nRowUnits = 0; s.nRowTiles = 0;
     {
         DevConfig probe = ctx->dcfg;
         probe.mode = b->mode;
@@ -661,16 +663,13 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
                 DevRowRegion rr{};
                 rr.bufStart = reg.bufStart; rr.len = reg.len; rr.relStart = reg.relStart; rr.itemLen = reg.itemLen;
                 rr.winBase = reg.winBase; rr.item = reg.item;
-                rr.tile0 = static_cast<uint32_t>(s.tiles.size());
+                rr.tile0 = s.nTilesAll;
                 rr.unit0 = s.nRowUnits;
                 rr.nUnits = (nWinReg + kRowsPerUnit - 1) / kRowsPerUnit;      // kTileRows is a multiple of kRowsPerUnit
                 s.rowRegions.push_back(rr);
                 s.nRowUnits += rr.nUnits;
-                // the tile table entries of these tiles are not read by any kernel (only general tiles are)
-                DevTile t{};
-                t.firstRegion = static_cast<uint32_t>(r);
-                s.tiles.resize(s.tiles.size() + nTilesReg, t);
-                s.tileIsRow.resize(s.tileIsRow.size() + nTilesReg, 1);
+                // these tiles have no tile table entry: no kernel reads one (only lean / general tiles are looked up)
+                s.nTilesAll += nTilesReg;
                 s.nRowTiles += nTilesReg;
                 ++r;
                 continue;
@@ -689,28 +688,29 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
                 while (fr + 1 < e && s.regions[fr].bufStart + s.regions[fr].len <= p) ++fr;
                 t.firstRegion = static_cast<uint32_t>(fr);
                 s.tiles.push_back(t);
-                s.tileIsRow.push_back(0);
+                s.tileIndex.push_back(s.nTilesAll++);
             }
             r = e;
         }
     }
 
+    tr.mark("plan_tiles");
     // ---- which kernel takes the other tiles: the lean kernel wants tiles inside one region -------------
     s.fastTiles.clear(); s.generalTiles.clear();
-    s.fastTiles.reserve(s.tiles.size() - s.nRowTiles);
+    s.fastTiles.reserve(s.tiles.size());
     {
         DevConfig probe = ctx->dcfg;
         probe.mode = b->mode;
         const bool fastOk = fastConfigOk(probe) && !ctx->forceGeneral;
         const uint32_t W = ctx->cfg.window_size;
-        for (size_t ti = 0; ti < s.tiles.size(); ++ti) {
-            if (s.tileIsRow[ti]) continue;
-            const DevTile &t = s.tiles[ti];
+        for (size_t tk = 0; tk < s.tiles.size(); ++tk) {
+            const uint32_t ti = s.tileIndex[tk];
+            const DevTile &t = s.tiles[tk];
             const DevRegion &r = s.regions[t.firstRegion];
             const bool single = r.bufStart <= t.bufStart && t.bufStart + t.len <= r.bufStart + r.len;
-            if (!(fastOk && single)) { s.generalTiles.push_back(static_cast<uint32_t>(ti)); continue; }
+            if (!(fastOk && single)) { s.generalTiles.push_back(ti); continue; }
             DevFastTile f{};
-            f.bufStart = t.bufStart; f.len = t.len; f.tile = static_cast<uint32_t>(ti);
+            f.bufStart = t.bufStart; f.len = t.len; f.tile = ti;
             f.relBase = r.relStart + static_cast<uint32_t>(t.bufStart - r.bufStart);
             f.regionEndQ = r.relStart + r.len - f.relBase;
             f.item = r.item; f.itemLen = r.itemLen;
@@ -756,10 +756,16 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     TLS_CUDA(s.dAbsPos.reserve(std::max<size_t>(bAbs, 16)));
     if (bAbs) TLS_CUDA(cudaMemcpyAsync(s.dAbsPos.p, hm + absOff, bAbs, cudaMemcpyHostToDevice, s.stream));
     TLS_CUDA(s.dRegions.reserve(std::max<size_t>(bRegions, 16)));
-    TLS_CUDA(s.dTiles.reserve(std::max<size_t>(bTiles, 16)));
+    TLS_CUDA(s.dTiles.reserve(std::max<size_t>(static_cast<size_t>(s.nTilesAll) * sizeof(DevTile), 16)));
     TLS_CUDA(s.dItemLen.reserve(std::max<size_t>(bLen, 16)));
     if (bRegions) TLS_CUDA(cudaMemcpyAsync(s.dRegions.p, hm, bRegions, cudaMemcpyHostToDevice, s.stream));
-    if (bTiles) TLS_CUDA(cudaMemcpyAsync(s.dTiles.p, hm + bRegions, bTiles, cudaMemcpyHostToDevice, s.stream));
+    for (size_t k = 0; k < s.tiles.size();) {               // runs of consecutive table indices go up in one copy each
+        size_t e = k + 1;
+        while (e < s.tiles.size() && s.tileIndex[e] == s.tileIndex[e - 1] + 1) ++e;
+        TLS_CUDA(cudaMemcpyAsync(s.dTiles.as<DevTile>() + s.tileIndex[k], hm + bRegions + k * sizeof(DevTile), (e - k) * sizeof(DevTile),
+                                 cudaMemcpyHostToDevice, s.stream));
+        k = e;
+    }
     if (bLen) TLS_CUDA(cudaMemcpyAsync(s.dItemLen.p, hm + bRegions + bTiles, bLen, cudaMemcpyHostToDevice, s.stream));
     TLS_CUDA(s.dItemCounts.reserve(std::max<size_t>(n, 1) * sizeof(DevItemCounts)));
     TLS_CUDA(s.dItemBegin.reserve((static_cast<size_t>(n) + 1) * 8));
@@ -795,7 +801,7 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             if ((hs[4] >> 32) != 0)
                 return fail(TLS_ERR_STATE, "lean scan kernel could not lay out its shared memory (window base %% 64 KiB); "
                                            "set TLS_FORCE_GENERAL=1");
-            if (tr.on) fprintf(stderr, " row_tiles=%zu lean_tiles=%zu/%zu redo_rows=%u", s.nRowTiles, s.fastTiles.size(), s.tiles.size(),
+            if (tr.on) fprintf(stderr, " row_tiles=%zu lean_tiles=%zu/%zu redo_rows=%u", s.nRowTiles, s.fastTiles.size(), static_cast<size_t>(s.nTilesAll),
                                static_cast<uint32_t>(hs[4]));
             const uint32_t ovUsed = static_cast<uint32_t>(hs[0]);
             s.nMatches = hs[1]; s.nCanAll = hs[2]; s.nNctAll = hs[3];
@@ -805,7 +811,7 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
         }
         if (s.nMatches > 0xFFFFFFF0ull) return fail(TLS_ERR_INVALID, "more than 2^32 matches in one batch; submit smaller batches");
         tr.mark("wait_scan");
-        if (!s.tiles.empty()) {
+        if (s.nTilesAll) {
             TLS_CUDA(cudaEventElapsedTime(&s.scanMs, s.evScan0, s.evScan1));
             TLS_CUDA(cudaEventElapsedTime(&s.fastMs, s.evScan0, s.evFast1));
         } else s.scanMs = s.fastMs = 0;
@@ -829,7 +835,7 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             TLS_CUDA(s.dBlocks.reserve(static_cast<size_t>(s.blockCap) * sizeof(DevBlock)));
             uint8_t *cnt = s.dCounters.as<uint8_t>();
             TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 8, s.stream));            // [16] block count, [20] ITS run count
-            if (first && !s.tiles.empty()) { TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream)); s.launches++; }
+            if (first && s.nTilesAll) { TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream)); s.launches++; }
             if (reads && n) TLS_CUDA(cudaMemsetAsync(s.dPass.p, 0, n, s.stream));
             if (n) {
                 if (first) { TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), n, s.dItemBegin.as<unsigned long long>(), s.stream)); s.launches++; }

@@ -94,6 +94,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;       // window / item counters go home while the block kernels run
     cudaEvent_t evScanDone = nullptr, evCopyDone = nullptr;
+    static constexpr int kMaxParts = 8;      // launches of the window-row kernel on a large batch (result copy overlaps the scan)
+    cudaEvent_t evPart[kMaxParts] = {};
     unsigned long long *hScanDev = nullptr;   // device view of hScan (mapped): scan totals without a copy
     cudaEvent_t evScan0 = nullptr, evScan1 = nullptr, evFast1 = nullptr, evAll0 = nullptr, evAll1 = nullptr;
     float fastMs = 0;
@@ -152,6 +154,7 @@ struct tls_ctx {
     std::string overlapRefusal;              // non-empty: genome-mode batches are refused (see buildDevConfig)
     bool forceGeneral = false;               // TLS_FORCE_GENERAL=1 or a lean-kernel layout failure
     bool noRowKernel = false;                // TLS_NO_ROW_KERNEL=1: 1536-base-row lean kernel instead of the window-row kernel
+    int rowParts = 3;                        // TLS_ROW_PARTS=n (1..8): launches of the window-row kernel on a large batch
     uint32_t rowMinWindows = kRowMinWindows; // TLS_ROW_MIN_WINDOWS=n: shortest contig (in windows) the window-row kernel takes
     Slot slot[2];
     // pageable host input: a ring of small pinned buffers carries it to the device chunk by chunk (memcpy of chunk
@@ -365,6 +368,7 @@ int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
     }
     ctx->forceGeneral = std::getenv("TLS_FORCE_GENERAL") != nullptr;
     ctx->noRowKernel = std::getenv("TLS_NO_ROW_KERNEL") != nullptr;
+    if (const char *e = std::getenv("TLS_ROW_PARTS")) ctx->rowParts = std::min(static_cast<int>(Slot::kMaxParts), std::max(1, std::atoi(e)));
     if (const char *e = std::getenv("TLS_ROW_MIN_WINDOWS")) ctx->rowMinWindows = std::max(1, std::atoi(e));
     *out = ctx.release();
     return TLS_OK;
@@ -392,6 +396,7 @@ void tls_destroy(tls_ctx *ctx) {
         if (s.evAll1) cudaEventDestroy(s.evAll1);
         if (s.copyStream) { cudaStreamSynchronize(s.copyStream); cudaStreamDestroy(s.copyStream); }
         if (s.evScanDone) cudaEventDestroy(s.evScanDone);
+        for (cudaEvent_t &e : s.evPart) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (s.evCopyDone) cudaEventDestroy(s.evCopyDone);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -455,28 +460,6 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         if (s.mode != TLS_MODE_GENOME || cfg.overlapWindows) cfg.countAcgt = 0;   // overlapping windows: counted by overlapWindowsKernel
         unsigned int *redo = s.dRedo.as<unsigned int>();
         TLS_CUDA(cudaEventRecord(s.evScan0, s.stream));
-        const uint32_t nRow = s.nRowUnits;
-        if (nRow) {
-            RowParams f{};
-            f.seq = s.devSeq;
-            f.units = s.dRowTiles.as<DevRowUnit>(); f.nUnits = nRow;
-            f.index8 = ctx->dIndex.as<uint8_t>();
-            f.flagTab = ctx->dFlags.as<uint8_t>() + cfg.cls[0].flagOffset;
-            f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
-            f.patLen = cfg.cls[0].len;
-            f.slots = s.dSlots.as<DevMatch>(); f.slotCap = ctx->slotCap;
-            f.slotMeta = s.dSlotMeta.as<uint4>();
-            f.tileTot = s.dTileTot.as<uint32_t>(); f.nTilesAll = nTiles;
-            f.ovArena = s.dOvArena.as<DevMatch>(); f.ovCap = s.ovCap; f.ovChunk = ctx->ovChunk;
-            f.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
-            f.windows = s.dWindows.as<uint4>();
-            f.itemCounts = s.dItemCounts.as<DevItemCounts>();
-            f.status = redo + 1;
-            f.cfg = cfg;
-            const int grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (nRow + kRowWarps - 1) / kRowWarps));
-            TLS_CUDA(launchRowScan(f, grid, s.stream));
-            s.launches++;
-        }
         if (nFast) {
             FastParams f{};
             f.seq = s.devSeq;
@@ -497,7 +480,6 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             TLS_CUDA(launchFastScan(f, std::min<int>(ctx->smCount, static_cast<int>(nFast)), s.stream));
             s.launches++;
         }
-        TLS_CUDA(cudaEventRecord(s.evFast1, s.stream));
         const uint32_t nGeneral = static_cast<uint32_t>(s.generalTiles.size());
         if (nGeneral || nFast) {
             ScanParams p{};
@@ -526,14 +508,67 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             TLS_CUDA(launchScan(p, grid, s.stream));
             s.launches++;
         }
+        // The window-row kernel goes last and, on a large batch, in ctx->rowParts launches over consecutive unit ranges: the
+        // window counters of a finished range (and of every small contig before its end: the lean / general kernels
+        // have already run) go home on the side stream while the next range is scanned.  The result copy of a
+        // device-resident batch is PCIe-bound (32 bytes per window), so hiding part of it behind the scan shortens the
+        // step; every extra launch costs the scan 30-40 us (table reload, ramp-up, tail): three by default (measured on the
+        // 3.03 Gbp batch, parts / scan ms / step ms: 1 / 1.19 / 4.03, 2 / 1.27 / 3.45, 3 / 1.28 / 3.27, 4 / 1.31 / 3.28).
+        // (One launch with progress counters and a polling kernel on the side stream was tried: it disturbed the scan.)
+        const uint32_t nRow = s.nRowUnits;
+        const bool copyWindows = s.mode == TLS_MODE_GENOME && s.nWindows && !cfg.overlapWindows;
+        if (copyWindows) TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
+        uint64_t winCopied = 0;
+        if (nRow) {
+            RowParams f{};
+            f.seq = s.devSeq;
+            f.index8 = ctx->dIndex.as<uint8_t>();
+            f.flagTab = ctx->dFlags.as<uint8_t>() + cfg.cls[0].flagOffset;
+            f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
+            f.patLen = cfg.cls[0].len;
+            f.slots = s.dSlots.as<DevMatch>(); f.slotCap = ctx->slotCap;
+            f.slotMeta = s.dSlotMeta.as<uint4>();
+            f.tileTot = s.dTileTot.as<uint32_t>(); f.nTilesAll = nTiles;
+            f.ovArena = s.dOvArena.as<DevMatch>(); f.ovCap = s.ovCap; f.ovChunk = ctx->ovChunk;
+            f.ovCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>());
+            f.windows = s.dWindows.as<uint4>();
+            f.itemCounts = s.dItemCounts.as<DevItemCounts>();
+            f.status = redo + 1;
+            f.cfg = cfg;
+            const uint32_t gridWarps = static_cast<uint32_t>(ctx->smCount) * kRowWarps;
+            const int parts = (copyWindows && nRow >= 16u * gridWarps) ? ctx->rowParts : 1;
+            auto firstWindowOfUnit = [&](uint32_t u) {          // rowRegions are sorted by unit0
+                size_t lo = 0, hi = s.rowRegions.size();
+                while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (s.rowRegions[mid].unit0 <= u) lo = mid; else hi = mid; }
+                return static_cast<uint64_t>(s.rowRegions[lo].winBase) + static_cast<uint64_t>(u - s.rowRegions[lo].unit0) * kRowsPerUnit;
+            };
+            for (int part = 0; part < parts; ++part) {
+                const uint32_t uLo = static_cast<uint32_t>(static_cast<uint64_t>(nRow) * part / parts);
+                const uint32_t uHi = static_cast<uint32_t>(static_cast<uint64_t>(nRow) * (part + 1) / parts);
+                f.units = s.dRowTiles.as<DevRowUnit>() + uLo; f.nUnits = uHi - uLo;
+                const int grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (f.nUnits + kRowWarps - 1) / kRowWarps));
+                TLS_CUDA(launchRowScan(f, grid, s.stream));
+                s.launches++;
+                if (part + 1 < parts) {
+                    const uint64_t wEnd = firstWindowOfUnit(uHi);   // every window below it is final now
+                    if (!s.evPart[part]) TLS_CUDA(cudaEventCreateWithFlags(&s.evPart[part], cudaEventDisableTiming));
+                    TLS_CUDA(cudaEventRecord(s.evPart[part], s.stream));
+                    TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evPart[part], 0));
+                    if (wEnd > winCopied)
+                        TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * 32, s.dWindows.as<uint8_t>() + winCopied * 32,
+                                                 (wEnd - winCopied) * 32, cudaMemcpyDeviceToHost, s.copyStream));
+                    winCopied = std::max(winCopied, wEnd);
+                }
+            }
+        }
+        TLS_CUDA(cudaEventRecord(s.evFast1, s.stream));
         TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
-        // window and per-item counters are final now: copy them home on the side stream
+        // window and per-item counters are final now: copy (the rest of) them home on the side stream
         TLS_CUDA(cudaEventRecord(s.evScanDone, s.stream));
         TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evScanDone, 0));
-        if (s.mode == TLS_MODE_GENOME && s.nWindows && !cfg.overlapWindows) {
-            TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
-            TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows.p, s.nWindows * 32, cudaMemcpyDeviceToHost, s.copyStream));
-        }
+        if (copyWindows && winCopied < s.nWindows)
+            TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * 32, s.dWindows.as<uint8_t>() + winCopied * 32,
+                                     (s.nWindows - winCopied) * 32, cudaMemcpyDeviceToHost, s.copyStream));
         if (s.mode != TLS_MODE_READS && s.nItems) {
             TLS_CUDA(s.hItemCounts.reserve(static_cast<size_t>(s.nItems) * sizeof(DevItemCounts)));
             TLS_CUDA(cudaMemcpyAsync(s.hItemCounts.p, s.dItemCounts.p, static_cast<size_t>(s.nItems) * sizeof(DevItemCounts),

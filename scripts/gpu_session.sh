@@ -9,7 +9,7 @@ if [ "$mode" = full ]; then
   timeout 300 python __graft_entry__.py smoke > $out/smoke.log 2>&1; echo "smoke exit $?" >> $out/smoke.log
 fi
 timeout 900 python bench.py --steps 5 --warmup 3 > $out/bench.json 2> $out/bench.err; echo "bench exit $?" >> $out/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Kernel' -s 22 -c 11 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Kernel' -s 24 -c 28 --csv \
   --log-file $out/launches.csv python scripts/trace_bench.py 1.0 > $out/trace.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rowScanKernel -s 1 -c 1 \
   -o $out/prof_rows python scripts/trace_bench.py 0.25 > $out/ncu_full.log 2>&1

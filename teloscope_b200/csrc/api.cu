@@ -11,6 +11,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/teloscope_b200.h"
@@ -163,7 +164,6 @@ struct tls_ctx {
     static constexpr size_t kRingBytes = 8u << 20;
     HostBuf ring[kRing];
     cudaEvent_t ringEv[kRing] = {nullptr, nullptr, nullptr, nullptr};
-    uint64_t ringNext = 0;
 };
 
 namespace {
@@ -619,19 +619,37 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
         cudaGetLastError();
         const uint8_t *src = b->seq + base;
         if (!pinned && s.seqBytes) {
-            for (uint64_t off = 0; off < s.seqBytes; off += tls_ctx::kRingBytes, ++ctx->ringNext) {
-                const int k = static_cast<int>(ctx->ringNext % tls_ctx::kRing);
-                if (!ctx->ringEv[k]) {
-                    TLS_CUDA(ctx->ring[k].reserve(tls_ctx::kRingBytes));
-                    TLS_CUDA(cudaEventCreateWithFlags(&ctx->ringEv[k], cudaEventDisableTiming));
-                } else {
-                    TLS_CUDA(cudaEventSynchronize(ctx->ringEv[k]));             // the DMA that last read this buffer
-                }
-                const size_t nb = static_cast<size_t>(std::min<uint64_t>(tls_ctx::kRingBytes, s.seqBytes - off));
-                std::memcpy(ctx->ring[k].p, src + off, nb);
-                TLS_CUDA(cudaMemcpyAsync(s.dSeq.as<uint8_t>() + off, ctx->ring[k].p, nb, cudaMemcpyHostToDevice, s.stream));
+            // kRing worker threads on a large batch (one ring buffer each; chunk c belongs to thread c mod kRing), the
+            // calling thread alone on a small one: a single core's memcpy (~10 GB/s) is slower than the DMA it feeds
+            for (int k = 0; k < tls_ctx::kRing; ++k) {
+                if (ctx->ringEv[k]) continue;
+                TLS_CUDA(ctx->ring[k].reserve(tls_ctx::kRingBytes));
+                TLS_CUDA(cudaEventCreateWithFlags(&ctx->ringEv[k], cudaEventDisableTiming));
                 TLS_CUDA(cudaEventRecord(ctx->ringEv[k], s.stream));
             }
+            const uint64_t nChunks = (s.seqBytes + tls_ctx::kRingBytes - 1) / tls_ctx::kRingBytes;
+            const int workers = nChunks >= 2 * tls_ctx::kRing ? tls_ctx::kRing : 1;
+            cudaError_t werr[tls_ctx::kRing] = {};
+            auto work = [&](int w) {
+                cudaError_t e = cudaSetDevice(ctx->device);
+                for (uint64_t c = static_cast<uint64_t>(w); e == cudaSuccess && c < nChunks; c += static_cast<uint64_t>(workers)) {
+                    const int k = workers == 1 ? static_cast<int>(c % tls_ctx::kRing) : w;
+                    const uint64_t off = c * tls_ctx::kRingBytes;
+                    const size_t nb = static_cast<size_t>(std::min<uint64_t>(tls_ctx::kRingBytes, s.seqBytes - off));
+                    if ((e = cudaEventSynchronize(ctx->ringEv[k])) != cudaSuccess) break;      // the DMA that last read this buffer
+                    std::memcpy(ctx->ring[k].p, src + off, nb);
+                    if ((e = cudaMemcpyAsync(s.dSeq.as<uint8_t>() + off, ctx->ring[k].p, nb, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) break;
+                    e = cudaEventRecord(ctx->ringEv[k], s.stream);
+                }
+                werr[w] = e;
+            };
+            if (workers == 1) work(0);
+            else {
+                std::vector<std::thread> pool;
+                for (int w = 0; w < workers; ++w) pool.emplace_back(work, w);
+                for (auto &t : pool) t.join();
+            }
+            for (int w = 0; w < workers; ++w) TLS_CUDA(werr[w]);
         } else if (s.seqBytes) {
             TLS_CUDA(cudaMemcpyAsync(s.dSeq.p, src, s.seqBytes, cudaMemcpyHostToDevice, s.stream));
         }

@@ -359,7 +359,7 @@ uint64_t countBases(const char *p, const char *e) {
 }
 
 // pass 2: the record's contigs copied back to back to out (newlines and gaps dropped), its items and gaps listed
-void parseRecord(const char *p, const char *e, uint8_t *out, uint64_t outOffset, uint32_t pathIdx, std::vector<Item> &items,
+void parseRecord(const char *p, const char *e, uint8_t *out, uint64_t outCap, uint64_t outOffset, uint32_t pathIdx, std::vector<Item> &items,
                  std::vector<Gap> &gaps, uint64_t &pathSize) {
     uint64_t pos = 0, runStart = 0, written = 0, segOffset = outOffset;
     int state = -1;                                           // -1 nothing yet, 0 in a contig, 1 in a gap
@@ -386,6 +386,13 @@ void parseRecord(const char *p, const char *e, uint8_t *out, uint64_t outOffset,
                 if (nl == 0) {
                     memcpy(out + written, q, 16);
                     written += 16; pos += 16;
+                } else if ((nl & (nl - 1)) == 0 && q + 33 <= e && written + 32 <= outCap) {
+                    // exactly one newline (the usual line end): the bytes before it, then the 15 after it, as two
+                    // overlapping 16-byte copies (the second one overwrites the newline's slot and what follows)
+                    const int k = __builtin_ctz(nl);
+                    memcpy(out + written, q, 16);
+                    memcpy(out + written + k, q + k + 1, 16);
+                    written += 15; pos += 15;
                 } else {
                     for (int i = 0; i < 16; ++i)
                         if (!((nl >> i) & 1u)) { out[written++] = static_cast<uint8_t>(q[i]); ++pos; }
@@ -443,7 +450,7 @@ void parseFasta(const InputData &in, unsigned threads, std::vector<PathRec> &pat
         const char *sp = static_cast<const char *>(memchr(in.p + recs[r].begin, ' ', headEnd - recs[r].begin));
         rec.header.assign(in.p + recs[r].begin, sp ? sp : in.p + headEnd);
         rec.header.erase(std::remove(rec.header.begin(), rec.header.end(), '\r'), rec.header.end());   // walkPath, src/input.cpp:950
-        parseRecord(in.p + recs[r].bodyBegin, in.p + recs[r].end, seq.get() + bases[r], bases[r], static_cast<uint32_t>(r), recItems[r],
+        parseRecord(in.p + recs[r].bodyBegin, in.p + recs[r].end, seq.get() + bases[r], bases[r + 1] - bases[r], bases[r], static_cast<uint32_t>(r), recItems[r],
                     rec.gaps, rec.pathSize);
     });
     size_t total = 0;

@@ -481,9 +481,21 @@ inline void appendU64(std::string &s, uint64_t v) {
     while (n) s.push_back(tmp[--n]);
 }
 inline void appendFloat(std::string &s, float v) {              // std::ostream << float, default precision
-    char tmp[40];
-    const int n = snprintf(tmp, sizeof tmp, "%g", static_cast<double>(v));
-    s.append(tmp, static_cast<size_t>(n));
+    // the window tracks take few distinct values (ratios of small counts): a direct-mapped per-thread cache of the
+    // printed text, keyed by the float's bits, saves most of the snprintf calls
+    struct Entry { uint32_t bits; uint8_t len; char txt[19]; };
+    thread_local Entry cache[4096] = {};
+    uint32_t bits;
+    memcpy(&bits, &v, 4);
+    Entry &e = cache[(bits * 2654435761u) >> 20];
+    if (e.len == 0 || e.bits != bits) {
+        char tmp[40];
+        const int n = snprintf(tmp, sizeof tmp, "%g", static_cast<double>(v));
+        if (n <= 0 || n > 19) { s.append(tmp, static_cast<size_t>(std::max(n, 0))); return; }
+        e.bits = bits; e.len = static_cast<uint8_t>(n);
+        memcpy(e.txt, tmp, static_cast<size_t>(n));
+    }
+    s.append(e.txt, e.len);
 }
 inline void windowLine(std::string &s, const std::string &header, uint64_t a, uint64_t b, float v) {
     s += header; s.push_back('\t'); appendU64(s, a); s.push_back('\t'); appendU64(s, b); s.push_back('\t'); appendFloat(s, v);

@@ -397,6 +397,25 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Run this rank on the CPU cores NVML lists as local to its GPU, before any pinned buffer is allocated: the
+    staging and result buffers then live on the GPU's own NUMA node and the host<->device copies of eight ranks do
+    not cross the socket interconnect.  Best effort (a box without NVML or with one node is left alone)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -426,6 +445,7 @@ def main():
                           "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    bind_to_gpu_numa_node(local)
     import torch
     import teloscope_b200 as tb
     if not torch.cuda.is_available():
@@ -506,13 +526,14 @@ def main():
         r.n_items * 32 + 192
     h2d = n_bases + len(offsets) * 40 + (n_bases // 49136 + len(offsets)) * 16
 
-    t = torch.tensor([elapsed, elapsed_e2e, float(n_bases)], dtype=torch.float64, device=f"cuda:{local}")
+    my_kernel_gbps = n_bases / (float(np.mean(scan_ms)) * 1e-3) / 1e9          # this rank's scan kernels alone
+    t = torch.tensor([elapsed, elapsed_e2e, float(n_bases), my_kernel_gbps], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        elapsed, elapsed_e2e, total_bases = float(mx[0]), float(mx[1]), float(sm[2])
+        elapsed, elapsed_e2e, total_bases, kernel_gbps_all = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
     else:
-        total_bases = float(n_bases)
+        total_bases, kernel_gbps_all = float(n_bases), my_kernel_gbps
     if rank == 0:
         peaks_path = ROOT / "MEASURED_PEAKS.json"
         if peaks_path.exists():
@@ -549,7 +570,9 @@ def main():
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "kernel_only": {"scan_kernels_ms": float(np.mean(scan_ms)), "lean_kernel_ms": float(np.mean(stats["lean_ms"])),
-                            "Gbp_per_s": n_bases / kern_s / 1e9},
+                            "Gbp_per_s": n_bases / kern_s / 1e9, "Gbp_per_s_all_ranks": kernel_gbps_all,
+                            "note": "rank 0's kernels; all_ranks = sum over ranks of bases / own scan-kernel time (device-side scaling: "
+                                    "the whole-step value at N > 1 is bound by the result copies of all ranks sharing the host link)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "tls::rowScanKernel<3,true> (+ the two small launches that take "
                          "contigs shorter than 8 windows); duration = all three, CUDA events on the ctx stream, mean over "

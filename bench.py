@@ -425,6 +425,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="assembly size factor (1.0 = 3.09 Gbp; tests use less)")
     ap.add_argument("--cpu-scale", type=float, default=1.0 / 16, help="size factor of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-records", action="store_true", help="32-byte window / 16-byte match records instead of the compact forms")
     ap.add_argument("--no-extra", action="store_true", help="skip the plant-assembly and read-scorer measurements")
     ap.add_argument("--seed", type=int, default=42)
     args = ap.parse_args()
@@ -468,7 +469,9 @@ def main():
     host = torch.empty(seq.numel(), dtype=torch.uint8, pin_memory=True)
     host.copy_(seq)
     host_np = host.numpy()
-    sc = tb.Scanner(tb.ScanConfig(canonical="TTAGGG", patterns=PATTERNS, out_acgt=True, out_matches=True), device=local)
+    # compact result records (TLS_OUT_COMPACT: 16 bytes per window, 8 per -m match): half the bytes over PCIe
+    sc = tb.Scanner(tb.ScanConfig(canonical="TTAGGG", patterns=PATTERNS, out_acgt=True, out_matches=True,
+                                  compact=not args.full_records), device=local)
 
     # collect(copy=False): results are read in place from the ctx's pinned buffers (what a C++ host
     # would do through the C ABI); release() hands the ticket back
@@ -522,8 +525,8 @@ def main():
     barrier()
     elapsed_e2e = time.perf_counter() - t1
     clk = clocks.stop() if clocks else None
-    d2h = n_windows * 32 + (len(r.canonical) + len(r.noncanonical)) * 16 + (len(r.terminal) + len(r.its)) * 48 + \
-        r.n_items * 32 + 192
+    d2h = n_windows * r.windows.dtype.itemsize + (len(r.canonical) + len(r.noncanonical)) * r.canonical.dtype.itemsize + \
+        (len(r.terminal) + len(r.its)) * 48 + r.n_items * 32 + 192
     h2d = n_bases + len(offsets) * 40 + (n_bases // 49136 + len(offsets)) * 16
 
     my_kernel_gbps = n_bases / (float(np.mean(scan_ms)) * 1e-3) / 1e9          # this rank's scan kernels alone
@@ -565,7 +568,9 @@ def main():
             "config": {"workload": workload, "bases_per_gpu": n_bases, "contigs_per_gpu": len(offsets) - 1,
                        "windows_per_gpu": n_windows, "matches_per_gpu": n_matches, "sharding": "one assembly per GPU, no collective",
                        "l2": "input (>= 3 GB at scale 1) is larger than the 126 MB L2; no flush needed",
-                       "pipelining": "value: one ticket at a time; e2e: two tickets in flight (H2D of step i+1 overlaps step i)"},
+                       "pipelining": "value: one ticket at a time; e2e: two tickets in flight (H2D of step i+1 overlaps step i)",
+                       "result_records": "full (32-byte windows, 16-byte matches)" if args.full_records else
+                                         "compact (TLS_OUT_COMPACT: 16-byte windows, 8-byte item-relative matches)"},
             "e2e": {"value": total_bases * args.steps / elapsed_e2e / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

@@ -67,14 +67,32 @@ typedef struct {          /* integer part of WindowData, include/teloscope.h:119
     uint32_t can_cov, noncan_cov, fwd_cov, rev_cov;
 } tls_window;             /* 32 bytes; start = abs_pos + i*step, size = min(window, n - i*step) */
 
+/* Compact forms of the two bulk results (TLS_OUT_COMPACT): half the bytes per record over PCIe and in host memory.
+ * The counters of a window are bounded by window_size x (sum of the pattern lengths), so they fit 16 bits whenever
+ * that product does (tls_create refuses the flag otherwise); a match position relative to its item fits 32 bits. */
+typedef struct {
+    uint16_t acgt[4];
+    uint16_t can_cov, noncan_cov, fwd_cov, rev_cov;
+} tls_window16;           /* 16 bytes, same fields as tls_window */
+
+typedef struct {
+    uint32_t pos;         /* offset in the item: MatchInfo.position = abs_pos[item] + pos */
+    uint16_t len;
+    uint8_t is_forward;
+    uint8_t is_canonical;
+} tls_match8;             /* 8 bytes */
+
 /* ---- configuration ---------------------------------------------------------------------------- */
 
 enum {                    /* tls_config.outputs */
     TLS_OUT_ACGT = 1u << 0,     /* -g / -e : per-window A,C,G,T counts (src/teloscope.cpp:418)  */
     TLS_OUT_MATCHES = 1u << 1,  /* -m      : canonical + terminal non-canonical match lists     */
-    TLS_OUT_ITS = 1u << 2       /* -i      : interstitial blocks are always computed in genome
+    TLS_OUT_ITS = 1u << 2,      /* -i      : interstitial blocks are always computed in genome
                                              mode (the report needs their count); flag kept for
                                              symmetry with the reference's toggles              */
+    TLS_OUT_COMPACT = 1u << 3   /* windows come back as tls_window16 (tls_result.windows16) and the -m lists as
+                                   tls_match8 (canonical8 / noncanonical8); windows / canonical / noncanonical
+                                   are then NULL                                                */
 };
 
 typedef struct {
@@ -135,6 +153,9 @@ typedef struct {
     uint64_t n_matches;               /* match records the scan emitted                           */
     uint32_t n_kernel_launches;
     float lean_kernel_ms;             /* lean scan kernel alone (0 when the batch has no lean tiles) */
+    /* TLS_OUT_COMPACT (same *_off arrays) */
+    const tls_window16 *windows16;
+    const tls_match8 *canonical8, *noncanonical8;
 } tls_result;
 
 typedef struct tls_ctx tls_ctx;

@@ -26,7 +26,7 @@ __all__ = ["ScanConfig", "Scanner", "BatchResult", "expand_patterns", "load_libr
 LIB_PATH = Path(__file__).resolve().parent / "libteloscope_b200.so"
 ABI_VERSION = 1
 MODE_GENOME, MODE_TIPS, MODE_READS = 0, 1, 2
-OUT_ACGT, OUT_MATCHES, OUT_ITS = 1, 2, 4
+OUT_ACGT, OUT_MATCHES, OUT_ITS, OUT_COMPACT = 1, 2, 4, 8
 
 MATCH_DT = np.dtype([("pos", "<u8"), ("len", "<u2"), ("fwd", "u1"), ("can", "u1"), ("pad", "<u4")])
 BLOCK_DT = np.dtype([("start", "<u8"), ("len", "<u4"), ("counts", "<u4"), ("fwd_count", "<u4"),
@@ -35,7 +35,12 @@ BLOCK_DT = np.dtype([("start", "<u8"), ("len", "<u4"), ("counts", "<u4"), ("fwd_
                      ("valid_or", "u1"), ("label", "S1"), ("pad", "<u2")])
 WINDOW_DT = np.dtype([("acgt", "<u4", (4,)), ("can_cov", "<u4"), ("noncan_cov", "<u4"),
                       ("fwd_cov", "<u4"), ("rev_cov", "<u4")])
+# compact result forms (ScanConfig.compact / TLS_OUT_COMPACT): tls_window16, tls_match8 (pos relative to the item)
+WINDOW16_DT = np.dtype([("acgt", "<u2", (4,)), ("can_cov", "<u2"), ("noncan_cov", "<u2"),
+                        ("fwd_cov", "<u2"), ("rev_cov", "<u2")])
+MATCH8_DT = np.dtype([("pos", "<u4"), ("len", "<u2"), ("fwd", "u1"), ("can", "u1")])
 assert MATCH_DT.itemsize == 16 and BLOCK_DT.itemsize == 48 and WINDOW_DT.itemsize == 32
+assert WINDOW16_DT.itemsize == 16 and MATCH8_DT.itemsize == 8
 
 
 class TlsError(RuntimeError):
@@ -69,7 +74,8 @@ class _Result(C.Structure):
                 ("pass_", C.c_void_p),
                 ("scan_kernel_ms", C.c_float), ("device_ms", C.c_float),
                 ("n_bases_scanned", C.c_uint64), ("n_matches", C.c_uint64),
-                ("n_kernel_launches", C.c_uint32), ("lean_kernel_ms", C.c_float)]
+                ("n_kernel_launches", C.c_uint32), ("lean_kernel_ms", C.c_float),
+                ("windows16", C.c_void_p), ("canonical8", C.c_void_p), ("noncanonical8", C.c_void_p)]
 
 
 EXPORTS = ("tls_expand_patterns", "tls_device_count", "tls_create", "tls_destroy", "tls_submit",
@@ -150,6 +156,7 @@ class ScanConfig:
     min_block_density: float = 0.5            # -y
     out_acgt: bool = True                     # -g or -e
     out_matches: bool = True                  # -m
+    compact: bool = False                     # TLS_OUT_COMPACT: 16-byte window and 8-byte match records
     canonical_fwd: str = field(init=False)
     canonical_rev: str = field(init=False)
 
@@ -169,7 +176,7 @@ class BatchResult:
     independent of the ctx; with copy=False they alias ctx-owned pinned memory and stay valid until
     release() — the zero-copy path a host pipeline would use."""
 
-    def __init__(self, r: _Result, copy: bool = True, on_release=None):
+    def __init__(self, r: _Result, copy: bool = True, on_release=None, abs_pos=None):
         n = r.n_items
         self.n_items, self.mode = n, r.mode
         self._on_release = on_release
@@ -185,15 +192,33 @@ class BatchResult:
             return arr(ptr, n + 1, "<u8") if ptr else np.zeros(n + 1, dtype="<u8")
 
         self.window_off = off(r.window_off)
-        self.windows = arr(r.windows, self.window_off[-1] if r.mode == MODE_GENOME else 0, WINDOW_DT)
+        n_win = self.window_off[-1] if r.mode == MODE_GENOME else 0
+        self.windows = arr(r.windows16, n_win, WINDOW16_DT) if r.windows16 else arr(r.windows, n_win, WINDOW_DT)
         self.terminal_off = off(r.terminal_off)
         self.terminal = arr(r.terminal, self.terminal_off[-1], BLOCK_DT)
         self.its_off = off(r.its_off)
         self.its = arr(r.its, self.its_off[-1], BLOCK_DT)
         self.canonical_off = off(r.canonical_off)
-        self.canonical = arr(r.canonical, self.canonical_off[-1], MATCH_DT)
         self.noncanonical_off = off(r.noncanonical_off)
-        self.noncanonical = arr(r.noncanonical, self.noncanonical_off[-1], MATCH_DT)
+
+        def matches(ptr16, ptr8, offsets):
+            """16-byte records as they are; 8-byte records (item-relative positions) are widened to MATCH_DT with
+            absolute positions when copy=True, and left as MATCH8_DT views otherwise."""
+            if not ptr8:
+                return arr(ptr16, offsets[-1], MATCH_DT)
+            m8 = arr(ptr8, offsets[-1], MATCH8_DT)
+            if not copy:
+                return m8
+            out = np.zeros(len(m8), dtype=MATCH_DT)
+            for f in ("len", "fwd", "can"):
+                out[f] = m8[f]
+            base = np.zeros(n, dtype=np.uint64) if abs_pos is None else np.asarray(abs_pos, dtype=np.uint64)
+            counts = np.diff(offsets).astype(np.int64)
+            out["pos"] = m8["pos"].astype(np.uint64) + np.repeat(base, counts)
+            return out
+
+        self.canonical = matches(r.canonical, r.canonical8, self.canonical_off)
+        self.noncanonical = matches(r.noncanonical, r.noncanonical8, self.noncanonical_off)
         self.n_canonical = arr(r.n_canonical, n, "<u4")
         self.n_fwd = arr(r.n_fwd, n, "<u4")
         self.n_rev = arr(r.n_rev, n, "<u4")
@@ -231,7 +256,8 @@ class Scanner:
         pats = (C.c_char_p * n)(*[p.encode() for p, _, _ in self.table])
         fwd = (C.c_uint8 * n)(*[int(f) for _, f, _ in self.table])
         can = (C.c_uint8 * n)(*[int(c) for _, _, c in self.table])
-        outputs = (OUT_ACGT if cfg.out_acgt else 0) | (OUT_MATCHES if cfg.out_matches else 0) | OUT_ITS
+        outputs = (OUT_ACGT if cfg.out_acgt else 0) | (OUT_MATCHES if cfg.out_matches else 0) | OUT_ITS | \
+            (OUT_COMPACT if cfg.compact else 0)
         c = _Config(ABI_VERSION, n, pats, fwd, can, cfg.window_size, cfg.step, cfg.terminal_limit,
                     cfg.max_match_dist, cfg.min_block_len, cfg.max_block_dist, cfg.min_block_counts,
                     float(np.float32(cfg.min_block_density)), outputs)
@@ -277,6 +303,8 @@ class Scanner:
         t = C.c_int()
         _check(self._L.tls_submit(self._h, C.byref(b), C.byref(t)))
         self._keep[t.value] = keep
+        self._abs_pos = getattr(self, "_abs_pos", {})
+        self._abs_pos[t.value] = abs_pos
         return t.value
 
     def collect(self, ticket: int, copy: bool = True) -> BatchResult:
@@ -288,7 +316,7 @@ class Scanner:
                 _check(self._L.tls_release(self._h, ticket))
             self._keep.pop(ticket, None)
 
-        out = BatchResult(r, copy=copy, on_release=None if copy else rel)
+        out = BatchResult(r, copy=copy, on_release=None if copy else rel, abs_pos=self._abs_pos.pop(ticket, None))
         if copy:
             rel()
         return out

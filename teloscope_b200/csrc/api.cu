@@ -121,7 +121,7 @@ struct Slot {
     DevBuf dRowTiles, dRowRegions, dFastTiles, dGeneralTiles, dRedo, dTileTot, dCanIdx, dNctIdx, dRunStarts;
     uint64_t nCanAll = 0, nNctAll = 0;       // canonical / terminal non-canonical records of the batch
     DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotMeta,
-        dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon;
+        dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon, dWindows16;
     uint32_t ovCap = 0;
     // device counters block: [0] ovCursor(u32) [16] blockCount(u32) [24] selTotals(2 x u64)
     HostBuf hScan, hCounters, hWindows, hItemCounts, hBlocks, hPass, hSelCan, hSelNon;
@@ -155,6 +155,7 @@ struct tls_ctx {
     std::string overlapRefusal;              // non-empty: genome-mode batches are refused (see buildDevConfig)
     bool forceGeneral = false;               // TLS_FORCE_GENERAL=1 or a lean-kernel layout failure
     bool noRowKernel = false;                // TLS_NO_ROW_KERNEL=1: 1536-base-row lean kernel instead of the window-row kernel
+    bool compact = false;                    // TLS_OUT_COMPACT: tls_window16 / tls_match8 results
     int rowParts = 3;                        // TLS_ROW_PARTS=n (1..8): launches of the window-row kernel on a large batch
     uint32_t rowMinWindows = kRowMinWindows; // TLS_ROW_MIN_WINDOWS=n: shortest contig (in windows) the window-row kernel takes
     Slot slot[2];
@@ -213,6 +214,14 @@ int buildDevConfig(tls_ctx *ctx) {
             snprintf(why, sizeof why, "overlapping windows need step >= %u and window - step >= %u (the pattern length)",
                      c.maxLen, c.maxLen);
         ctx->overlapRefusal = why;
+    }
+    ctx->compact = (u.outputs & TLS_OUT_COMPACT) != 0;
+    if (ctx->compact) {
+        // a window's covered-bp counters are bounded by window_size x (sum of the pattern lengths): one match per length and start
+        uint64_t lenSum = 0;
+        for (uint32_t i = 0; i < c.nClasses; ++i) lenSum += c.cls[i].len;
+        if (static_cast<uint64_t>(u.window_size) * lenSum > 65535ull)
+            return fail(TLS_ERR_INVALID, "TLS_OUT_COMPACT needs window_size x (sum of pattern lengths) <= 65535 (16-bit window counters)");
     }
     fillDivider(c, u.window_size);
     return TLS_OK;
@@ -384,7 +393,7 @@ void tls_destroy(tls_ctx *ctx) {
             b->release();
         for (DevBuf *b : {&s.dAbsPos, &s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
                           &s.dMatches, &s.dSlots, &s.dSlotMeta, &s.dOvArena, &s.dTileBase, &s.dCounters,
-                          &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch, &s.dSelCan, &s.dSelNon})
+                          &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch, &s.dSelCan, &s.dSelNon, &s.dWindows16})
             b->release();
         for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hMeta2, &s.hScan, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
                            &s.hSelCan, &s.hSelNon})
@@ -516,7 +525,8 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         // 3.03 Gbp batch, parts / scan ms / step ms: 1 / 1.19 / 4.03, 2 / 1.27 / 3.45, 3 / 1.28 / 3.27, 4 / 1.31 / 3.28).
         // (One launch with progress counters and a polling kernel on the side stream was tried: it disturbed the scan.)
         const uint32_t nRow = s.nRowUnits;
-        const bool copyWindows = s.mode == TLS_MODE_GENOME && s.nWindows && !cfg.overlapWindows;
+        const bool anyWindows = s.mode == TLS_MODE_GENOME && s.nWindows && !cfg.overlapWindows;
+        const bool copyWindows = anyWindows && !ctx->compact;       // compact: packed to 16 bytes after the scan, then copied
         if (copyWindows) TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
         uint64_t winCopied = 0;
         if (nRow) {
@@ -563,12 +573,21 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         }
         TLS_CUDA(cudaEventRecord(s.evFast1, s.stream));
         TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
+        if (anyWindows && ctx->compact) {
+            TLS_CUDA(s.dWindows16.reserve(s.nWindows * 16));
+            TLS_CUDA(launchPackWindows(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, s.stream));
+            s.launches++;
+        }
         // window and per-item counters are final now: copy (the rest of) them home on the side stream
         TLS_CUDA(cudaEventRecord(s.evScanDone, s.stream));
         TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evScanDone, 0));
         if (copyWindows && winCopied < s.nWindows)
             TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * 32, s.dWindows.as<uint8_t>() + winCopied * 32,
                                      (s.nWindows - winCopied) * 32, cudaMemcpyDeviceToHost, s.copyStream));
+        if (anyWindows && ctx->compact) {
+            TLS_CUDA(s.hWindows.reserve(s.nWindows * 16));
+            TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows16.p, s.nWindows * 16, cudaMemcpyDeviceToHost, s.copyStream));
+        }
         if (s.mode != TLS_MODE_READS && s.nItems) {
             TLS_CUDA(s.hItemCounts.reserve(static_cast<size_t>(s.nItems) * sizeof(DevItemCounts)));
             TLS_CUDA(cudaMemcpyAsync(s.hItemCounts.p, s.dItemCounts.p, static_cast<size_t>(s.nItems) * sizeof(DevItemCounts),
@@ -898,8 +917,16 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
                                                   s.dMatches.as<DevMatch>(), s.dItemBegin.as<unsigned long long>(),
                                                   static_cast<uint32_t>(s.nWindows), ctx->dcfg, s.dWindows.as<uint32_t>(), s.stream));
                     s.launches++;
-                    TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
-                    TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows.p, s.nWindows * 32, cudaMemcpyDeviceToHost, s.stream));
+                    if (ctx->compact) {
+                        TLS_CUDA(s.dWindows16.reserve(s.nWindows * 16));
+                        TLS_CUDA(launchPackWindows(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, s.stream));
+                        s.launches++;
+                        TLS_CUDA(s.hWindows.reserve(s.nWindows * 16));
+                        TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows16.p, s.nWindows * 16, cudaMemcpyDeviceToHost, s.stream));
+                    } else {
+                        TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
+                        TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows.p, s.nWindows * 32, cudaMemcpyDeviceToHost, s.stream));
+                    }
                 }
                 BlockParams bp{};
                 bp.matches = s.dMatches.as<DevMatch>();
@@ -923,12 +950,17 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
                     s.launches += 2;
                 }
                 if (first && wantSel) {
-                    TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll,
-                                                  s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
-                                                  s.dSelCan.p, s.stream));
-                    TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll,
-                                                  s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
-                                                  s.dSelNon.p, s.stream));
+                    if (ctx->compact) {
+                        TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dSelCan.p, s.stream));
+                        TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll, s.dSelNon.p, s.stream));
+                    } else {
+                        TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll,
+                                                      s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
+                                                      s.dSelCan.p, s.stream));
+                        TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll,
+                                                      s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
+                                                      s.dSelNon.p, s.stream));
+                    }
                     s.launches += (s.nCanAll ? 1 : 0) + (s.nNctAll ? 1 : 0);
                 }
             }
@@ -954,13 +986,14 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
             TLS_CUDA(cudaMemcpyAsync(s.hPass.p, s.dPass.p, n, cudaMemcpyDeviceToHost, s.stream));
         }
         s.nSelCan = selTotals[0]; s.nSelNon = selTotals[1];
+        const size_t selRec = ctx->compact ? sizeof(tls_match8) : sizeof(tls_match);
         if (selTotals[0]) {
-            TLS_CUDA(s.hSelCan.reserve(selTotals[0] * sizeof(tls_match)));
-            TLS_CUDA(cudaMemcpyAsync(s.hSelCan.p, s.dSelCan.p, selTotals[0] * sizeof(tls_match), cudaMemcpyDeviceToHost, s.stream));
+            TLS_CUDA(s.hSelCan.reserve(selTotals[0] * selRec));
+            TLS_CUDA(cudaMemcpyAsync(s.hSelCan.p, s.dSelCan.p, selTotals[0] * selRec, cudaMemcpyDeviceToHost, s.stream));
         }
         if (selTotals[1]) {
-            TLS_CUDA(s.hSelNon.reserve(selTotals[1] * sizeof(tls_match)));
-            TLS_CUDA(cudaMemcpyAsync(s.hSelNon.p, s.dSelNon.p, selTotals[1] * sizeof(tls_match), cudaMemcpyDeviceToHost, s.stream));
+            TLS_CUDA(s.hSelNon.reserve(selTotals[1] * selRec));
+            TLS_CUDA(cudaMemcpyAsync(s.hSelNon.p, s.dSelNon.p, selTotals[1] * selRec, cudaMemcpyDeviceToHost, s.stream));
         }
         TLS_CUDA(cudaStreamSynchronize(s.stream));
         TLS_CUDA(cudaStreamSynchronize(s.copyStream));
@@ -1013,11 +1046,14 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
     std::memset(res, 0, sizeof *res);
     res->n_items = n; res->mode = s.mode;
     res->window_off = s.winOff.data();
-    res->windows = s.hWindows.as<tls_window>();
+    res->windows = ctx->compact ? nullptr : s.hWindows.as<tls_window>();
+    res->windows16 = ctx->compact ? s.hWindows.as<tls_window16>() : nullptr;
     res->terminal_off = s.terminalOff.data(); res->terminal = s.terminal.data();
     res->its_off = s.itsOff.data(); res->its = s.its.data();
-    res->canonical_off = s.canOff.data(); res->canonical = s.nSelCan ? s.hSelCan.as<tls_match>() : nullptr;
-    res->noncanonical_off = s.nonOff.data(); res->noncanonical = s.nSelNon ? s.hSelNon.as<tls_match>() : nullptr;
+    res->canonical_off = s.canOff.data(); res->canonical = s.nSelCan && !ctx->compact ? s.hSelCan.as<tls_match>() : nullptr;
+    res->noncanonical_off = s.nonOff.data(); res->noncanonical = s.nSelNon && !ctx->compact ? s.hSelNon.as<tls_match>() : nullptr;
+    res->canonical8 = s.nSelCan && ctx->compact ? s.hSelCan.as<tls_match8>() : nullptr;
+    res->noncanonical8 = s.nSelNon && ctx->compact ? s.hSelNon.as<tls_match8>() : nullptr;
     res->n_canonical = s.nCan.data(); res->n_fwd = s.nFwd.data(); res->n_rev = s.nRev.data();
     res->pass = s.pass.data();
     res->scan_kernel_ms = s.scanMs; res->device_ms = s.allMs;

@@ -514,6 +514,22 @@ struct OutMatch {
 };
 static_assert(sizeof(OutMatch) == 16, "tls_match layout");
 
+// compact form (tls_match8): the position stays relative to the item, so no item lookup is needed
+__global__ void __launch_bounds__(256) selectFinalize8Kernel(const DevMatch *m, const uint32_t *idxList, unsigned long long n, uint2 *out) {
+    const unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const DevMatch x = m[idxList[j]];
+    out[j] = make_uint2(x.pos, static_cast<uint32_t>(x.len) | ((x.flags & kMatchFwd) ? 0x10000u : 0u) | ((x.flags & kMatchCan) ? 0x1000000u : 0u));
+}
+
+// tls_window (8 x u32) -> tls_window16 (8 x u16); tls_create has made sure that no counter can exceed 16 bits
+__global__ void __launch_bounds__(256) packWindowsKernel(const uint4 *in, uint4 *out, unsigned long long n) {
+    const unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 a = in[2 * i], b = in[2 * i + 1];
+    out[i] = make_uint4(a.x | (a.y << 16), a.z | (a.w << 16), b.x | (b.y << 16), b.z | (b.w << 16));
+}
+
 __global__ void __launch_bounds__(256) selectFinalizeKernel(const DevMatch *m, const uint32_t *idxList, unsigned long long n,
                                                             const unsigned long long *itemBegin, const unsigned long long *absPos,
                                                             uint32_t nItems, OutMatch *out) {
@@ -603,6 +619,17 @@ cudaError_t launchOverlapWindows(const uint8_t *seq, const DevRegion *regions, u
     const unsigned long long threads = 32ull * nWindows;
     overlapWindowsKernel<<<static_cast<unsigned int>((threads + 255) / 256), 256, 0, s>>>(
         seq, regions, nRegions, matches, itemBegin, nWindows, cfg.windowSize, cfg.step, cfg.countAcgt, reinterpret_cast<uint4 *>(windows));
+    return cudaGetLastError();
+}
+cudaError_t launchSelectFinalize8(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    selectFinalize8Kernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(m, idxList, n, static_cast<uint2 *>(out));
+    return cudaGetLastError();
+}
+cudaError_t launchPackWindows(const uint32_t *windows, void *windows16, unsigned long long n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    packWindowsKernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows),
+                                                                              static_cast<uint4 *>(windows16), n);
     return cudaGetLastError();
 }
 cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned long long *itemBegin, cudaStream_t s) {

@@ -45,4 +45,8 @@ cudaError_t launchSelectFinalize(const DevMatch *m, const uint32_t *idxList, uns
                                  const unsigned long long *itemBegin, const unsigned long long *absPos, uint32_t nItems,
                                  void *out, cudaStream_t s);
 
+// TLS_OUT_COMPACT: 8-byte match records (item-relative position) and 16-byte window records
+cudaError_t launchSelectFinalize8(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s);
+cudaError_t launchPackWindows(const uint32_t *windows, void *windows16, unsigned long long n, cudaStream_t s);
+
 }  // namespace tls

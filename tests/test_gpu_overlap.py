@@ -87,3 +87,39 @@ def test_unsupported_overlap_is_refused_for_genome_batches_only(tb):
             assert np.array_equal(tips["terminal"]["len"], want["terminal"]["len"])
         finally:
             sc.close()
+
+
+def test_compact_results_equal_full_results(tb):
+    """TLS_OUT_COMPACT (tls_window16 / tls_match8): same values as the 32-byte / 16-byte records, for step == window
+    (window-row kernel) and for overlapping windows; refused when a 16-bit window counter could overflow."""
+    rng = np.random.default_rng(99)
+    seqs = [make_contig(rng, int(n), "TTAGGG", i % 2 == 1) for i, n in enumerate(rng.integers(1, 60000, size=12))]
+    seqs += [(b"TTAGGG" * 3000)[:12345], b""]
+    abs_pos = np.arange(len(seqs), dtype=np.uint64) * 10_000_019 + (1 << 33)       # positions beyond 32 bits
+    for kw in (dict(), dict(window_size=500, step=250), dict(window_size=1000, terminal_limit=3000,
+                                                               patterns=["TTAGGG", "TCAGGG", "TGAGGG", "TTGGGG"])):
+        cfg = ol.Config(**kw)
+        out = []
+        for compact in (False, True):
+            sc_cfg = pa.scan_config(cfg)
+            sc_cfg.compact = compact
+            sc = tb.Scanner(sc_cfg)
+            try:
+                res = sc.scan_batch(seqs, abs_pos, tb.MODE_GENOME)
+                out.append(res)
+            finally:
+                sc.close()
+        full, comp = out
+        assert comp.windows.dtype == tb.WINDOW16_DT and full.windows.dtype == tb.WINDOW_DT
+        for f in ("acgt", "can_cov", "noncan_cov", "fwd_cov", "rev_cov"):
+            assert np.array_equal(full.windows[f], comp.windows[f]), f
+        for k in ("canonical", "noncanonical"):
+            a, b = getattr(full, k), getattr(comp, k)
+            assert len(a) and np.array_equal(getattr(full, k + "_off"), getattr(comp, k + "_off"))
+            for f in ("pos", "len", "fwd", "can"):
+                assert np.array_equal(a[f], b[f]), (k, f)
+        assert full.terminal.tobytes() == comp.terminal.tobytes() and full.its.tobytes() == comp.its.tobytes()
+    big = pa.scan_config(ol.Config(window_size=20000, step=20000))
+    big.compact = True
+    with pytest.raises(tb.TlsError, match="TLS_OUT_COMPACT"):
+        tb.Scanner(big)

@@ -1,4 +1,4 @@
-// teloscope-b200 — host pipeline around the C ABI for FASTA / FASTA.gz assemblies.
+// teloscope-b200 — host pipeline around the C ABI for FASTA / FASTA.gz assemblies and FASTQ read subsets.
 //
 // What the reference does around scanSegment for a FASTA input, restated in C++17 on top of
 // include/teloscope_b200.h so that the output files, stdout and stderr are byte-identical:
@@ -11,8 +11,10 @@
 //     in flight;
 //   * labelTerminalBlocks (src/teloscope.cpp:259-383), the writers (:661-859), file set (:886-920), the path
 //     and assembly summaries (:950-1055), getStats (src/tools.cpp:22-51), computeN50 (include/teloscope.h:224).
+//   * --fastq-subset (Input::readFastqSubset, src/input.cpp:735-833): FASTQ / FASTQ.gz records whose read has a
+//     Teloscope-valid telomeric block, written back verbatim in input order (stdout, or a file with -o).
 // Not here (the reference's other front ends; this binary says so and exits with status 2): GFA input,
-// --fastq-subset / --bam-subset, the record filters (--include-bed ...), --plot-report, stdin.
+// --bam-subset, the record filters (--include-bed ...), --plot-report, stdin.
 //
 // The float tracks are computed on the host from the device's integer window counters with the reference's
 // own expressions (include/teloscope.h:199-214, src/teloscope.cpp:788-803): compiled with -ffp-contract=off.
@@ -59,6 +61,7 @@ struct Options {
     float minBlockDensity = 0.5f;
     bool outWinRepeats = false, outGC = false, outEntropy = false, outMatches = false, outITS = false;
     bool ultraFastMode = true, manualCuration = false;
+    bool fastqSubset = false, outFasta = false, minBlockLenSet = false;
     int cmdFlag = 0;
     unsigned threads = 0;                       // -j: host threads of the parse / formatting stages (0 = all cores)
 };
@@ -145,7 +148,7 @@ Options parseArgs(int argc, char **argv) {
                 const char *name = longOptions[idx].name;
                 if (longOptions[idx].flag) break;                      // --verbose / --cmd
                 if (!strcmp(name, "plot-report")) unsupported("--plot-report");
-                if (!strcmp(name, "fastq-subset")) unsupported("--fastq-subset");
+                if (!strcmp(name, "fastq-subset")) { o.fastqSubset = true; break; }
                 if (!strcmp(name, "bam-subset")) unsupported("--bam-subset");
                 unsupported("record filtering (--include-bed / --exclude-bed / --include-prefix / --exclude-prefix)");
             }
@@ -215,6 +218,7 @@ Options parseArgs(int argc, char **argv) {
             case 'l':
                 o.minBlockLen = static_cast<unsigned short>(parseInt(optarg, "Error: Invalid min block length '%s'. Must be a number.\n",
                                                                        "Error: Min block length (-l or --min-block-length) must be > 0.\n"));
+                o.minBlockLenSet = true;
                 break;
             case 'd':
                 o.maxBlockDist = static_cast<unsigned short>(parseInt(optarg, "Error: Invalid max block distance '%s'. Must be a number.\n",
@@ -238,7 +242,7 @@ Options parseArgs(int argc, char **argv) {
                     die("Error: Invalid edit distance '%s'. Must be a number [0,2].\n", optarg);
                 }
                 break;
-            case 'a': o.ultraFastMode = false; break;
+            case 'a': o.outFasta = true; o.ultraFastMode = false; break;
             case 'r': o.outWinRepeats = true; o.ultraFastMode = false; break;
             case 'g': o.outGC = true; o.ultraFastMode = false; break;
             case 'e': o.outEntropy = true; o.ultraFastMode = false; break;
@@ -602,6 +606,114 @@ void check(int rc, const char *what) {
     if (rc != TLS_OK) die("Error: %s failed: %s\n", what, tls_last_error());
 }
 
+// ---- --fastq-subset (Input::readFastqSubset, src/input.cpp:735-833; readFastqRecord :113-138) -----------------------------
+// Reads are taken four lines at a time (blank lines before a header are skipped), their sequence lines go to the
+// GPU as TLS_MODE_READS batches (ReadTelomereFilter::matches: trailing '\r' dropped, whole read terminal, -l 42 unless
+// given), and the records whose read passes are written back exactly as they were read, in input order.
+[[noreturn]] void fastqError(uint64_t recordNumber, const char *message) {
+    if (recordNumber > 0) fprintf(stderr, "Error: FASTQ record %llu: %s.\n", static_cast<unsigned long long>(recordNumber), message);
+    else fprintf(stderr, "Error: %s.\n", message);
+    exit(EXIT_FAILURE);
+}
+
+int runFastqSubset(const Options &o, const tls_config &baseCfg) {
+    InputData in;
+    loadInput(o.inSequence, in);
+    if (in.n == 0) fastqError(0, "FASTQ input is empty");
+    if (in.p[0] != '@') fastqError(0, "FASTQ input must start with '@'");
+    FILE *out = stdout;
+    std::string outPath;
+    if (o.outRouteSet) {                                      // src/main.cpp:699-713
+        outPath = o.outRoute + "/" + o.inSequenceName + "_telomeric.fastq";
+        out = fopen(outPath.c_str(), "wb");
+        if (!out) die("Error: Cannot write telomeric reads to '%s'.\n", outPath.c_str());
+    }
+    tls_config cfg = baseCfg;
+    cfg.min_block_len = o.minBlockLenSet ? o.minBlockLen : 42;          // src/read-filter.cpp:14-16
+    cfg.outputs = 0;
+    tls_ctx *ctx = nullptr;
+    const char *devEnv = getenv("TLS_DEVICE");
+    check(tls_create(&cfg, devEnv ? atoi(devEnv) : 0, &ctx), "tls_create");
+
+    struct Line { size_t b, e; };
+    struct Rec { Line header, sequence, plus, quality; };
+    struct Batch { std::vector<Rec> recs; std::vector<uint8_t> seq; std::vector<uint64_t> offsets; int ticket = -1; };
+    size_t pos = 0;
+    auto nextLine = [&](Line &l) {                            // std::getline
+        if (pos >= in.n) return false;
+        const char *nl = static_cast<const char *>(memchr(in.p + pos, '\n', in.n - pos));
+        l.b = pos;
+        l.e = nl ? static_cast<size_t>(nl - in.p) : in.n;
+        pos = nl ? l.e + 1 : in.n;
+        return true;
+    };
+    auto logicalLen = [&](const Line &l) { return l.e - l.b - ((l.e > l.b && in.p[l.e - 1] == '\r') ? 1 : 0); };
+    uint64_t recordNumber = 0, totalReads = 0, passedReads = 0;
+    const uint64_t batchBytes = getenv("TLS_BATCH_BYTES") ? strtoull(getenv("TLS_BATCH_BYTES"), nullptr, 10) : (256ull << 20);
+    std::vector<std::unique_ptr<Batch>> flight;
+    std::string outBuf;
+    auto consume = [&](Batch &b) {
+        tls_result r{};
+        check(tls_collect(ctx, b.ticket, &r), "tls_collect");
+        for (size_t j = 0; j < b.recs.size(); ++j) {
+            ++totalReads;
+            if (!r.pass[j]) continue;
+            ++passedReads;
+            for (const Line *l : {&b.recs[j].header, &b.recs[j].sequence, &b.recs[j].plus, &b.recs[j].quality}) {
+                outBuf.append(in.p + l->b, l->e - l->b);
+                outBuf.push_back('\n');
+            }
+            if (outBuf.size() > (1u << 22)) { fwrite(outBuf.data(), 1, outBuf.size(), out); outBuf.clear(); }
+        }
+        check(tls_release(ctx, b.ticket), "tls_release");
+    };
+    bool more = true;
+    while (more || !flight.empty()) {
+        if (more && flight.size() < 2) {
+            auto b = std::make_unique<Batch>();
+            b->offsets.push_back(0);
+            while (b->seq.size() < batchBytes && b->recs.size() < (1u << 22)) {
+                Rec rec;
+                do {
+                    if (!nextLine(rec.header)) { more = false; break; }
+                } while (logicalLen(rec.header) == 0);
+                if (!more) break;
+                if (!nextLine(rec.sequence) || !nextLine(rec.plus) || !nextLine(rec.quality)) fastqError(recordNumber + 1, "truncated FASTQ record");
+                if (rec.header.e == rec.header.b || in.p[rec.header.b] != '@') fastqError(recordNumber + 1, "expected header line starting with '@'");
+                if (rec.plus.e == rec.plus.b || in.p[rec.plus.b] != '+') fastqError(recordNumber + 1, "expected separator line starting with '+'");
+                if (logicalLen(rec.sequence) != logicalLen(rec.quality)) fastqError(recordNumber + 1, "sequence and quality length differ");
+                ++recordNumber;
+                b->seq.insert(b->seq.end(), in.p + rec.sequence.b, in.p + rec.sequence.e);
+                b->offsets.push_back(b->seq.size());
+                b->recs.push_back(rec);
+            }
+            if (!b->recs.empty()) {
+                b->seq.resize(b->seq.size() + 256, 0);
+                tls_batch tb{};
+                tb.seq = b->seq.data(); tb.offsets = b->offsets.data(); tb.abs_pos = nullptr;
+                tb.n_items = static_cast<uint32_t>(b->recs.size()); tb.mode = TLS_MODE_READS;
+                check(tls_submit(ctx, &tb, &b->ticket), "tls_submit");
+                flight.push_back(std::move(b));
+            }
+            if (more && flight.size() < 2) continue;
+        }
+        if (!flight.empty()) {
+            consume(*flight.front());
+            flight.erase(flight.begin());
+        }
+    }
+    if (!outBuf.empty()) fwrite(outBuf.data(), 1, outBuf.size(), out);
+    fflush(out);
+    if (out != stdout) {
+        fclose(out);
+        fprintf(stderr, "Wrote telomeric reads to %s.\n", outPath.c_str());
+    }
+    fprintf(stderr, "FASTQ subset: kept %llu of %llu reads.\n", static_cast<unsigned long long>(passedReads),
+            static_cast<unsigned long long>(totalReads));
+    fflush(stderr);
+    _exit(EXIT_SUCCESS);
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -613,7 +725,7 @@ int main(int argc, char **argv) {
     if (o.inSequence.empty()) die("Error: No input file provided. Use -f or pass as positional argument.\n");
     if (o.step > o.windowSize) die("Error: Step size (%d) cannot be larger than window size (%d).\n", o.step, o.windowSize);
     if (o.step < o.windowSize) fprintf(stderr, "Sliding with window size (%d) and step size (%d).\n", o.windowSize, o.step);
-    {   // writable check, src/main.cpp:611-622
+    if (!o.fastqSubset) {   // writable check, src/main.cpp:611-622
         const std::string testPath = o.outRoute + "/.teloscope_write_test";
         std::ofstream test(testPath);
         if (!test.is_open()) die("Error: Output directory '%s' is not writable.\n", o.outRoute.c_str());
@@ -653,9 +765,12 @@ int main(int argc, char **argv) {
         add(o.outMatches, "genome-wide matches"); add(o.outITS, "ITS blocks");
         if (!summary.empty()) fprintf(stderr, "Outputs: %s.\n", summary.c_str());
     }
+    if (o.fastqSubset && (o.outFasta || o.outWinRepeats || o.outGC || o.outEntropy || o.outMatches || o.outITS || o.manualCuration))
+        fprintf(stderr, "Warning: assembly output flags are ignored in read subset mode.\n");
     if (o.cmdFlag) {
-        for (int i = 0; i < argc; ++i) printf("%s ", argv[i]);
-        printf("\n");
+        FILE *cs = o.fastqSubset ? stderr : stdout;
+        for (int i = 0; i < argc; ++i) fprintf(cs, "%s ", argv[i]);
+        fprintf(cs, "\n");
     }
 
     StageTimer timer;
@@ -669,6 +784,7 @@ int main(int argc, char **argv) {
     cfg.max_match_dist = o.maxMatchDist; cfg.min_block_len = o.minBlockLen; cfg.max_block_dist = o.maxBlockDist;
     cfg.min_block_counts = o.minBlockCounts; cfg.min_block_density = o.minBlockDensity;
     cfg.outputs = ((o.outGC || o.outEntropy) ? 1u * TLS_OUT_ACGT : 0u) | (o.outMatches ? 1u * TLS_OUT_MATCHES : 0u) | TLS_OUT_ITS;
+    if (o.fastqSubset) return runFastqSubset(o, cfg);
     tls_ctx *ctx = nullptr;
     int ctxRc = TLS_OK;
     std::string ctxErr;

@@ -65,6 +65,43 @@ def test_pipeline_equals_reference_outputs(golden, tmp_path):
     assert done >= 170
 
 
+def test_fastq_subset_equals_reference_output(golden, tmp_path):
+    """--fastq-subset: stdout (the kept records, verbatim) by SHA-256 and stderr against the reference binary's for its
+    own FASTQ fixtures (CRLF, blank lines, thresholds), kept read names for the seeded synthetic reads; plus the -o form."""
+    import hashlib
+    cases, fixtures = golden
+    done = 0
+    for c in cases:
+        if c["kind"] != "fastq":
+            continue
+        src = tmp_path / c["fixture"]
+        src.write_bytes(fixtures[c["fixture"]].tobytes())
+        p = subprocess.run([str(BIN), "--fastq-subset", *c["args"], str(src)], capture_output=True, timeout=600)
+        tag = (c["fixture"], c["args"])
+        assert p.returncode == 0, (tag, p.stderr)
+        kept = [l[1:].split()[0] for l in p.stdout.decode().replace("\r", "").splitlines()[0::4] if l]
+        assert kept == c["kept"], tag
+        if "stdout_sha" in c:
+            assert hashlib.sha256(p.stdout).hexdigest() == c["stdout_sha"], tag
+        assert p.stderr.decode() == c["stderr"], tag
+        done += 1
+    assert done >= 15
+    c = next(c for c in cases if c["kind"] == "fastq" and "stdout_sha" in c and c["kept"])
+    src = tmp_path / (c["fixture"] + ".gz")
+    src.write_bytes(gzip.compress(fixtures[c["fixture"]].tobytes()))
+    outdir = tmp_path / "fq_out"
+    outdir.mkdir()
+    p = subprocess.run([str(BIN), "--fastq-subset", *c["args"], "-f", str(src), "-o", str(outdir)], capture_output=True, timeout=600)
+    assert p.returncode == 0 and p.stdout == b"", p.stderr
+    written = outdir / (src.name + "_telomeric.fastq")
+    assert hashlib.sha256(written.read_bytes()).hexdigest() == c["stdout_sha"]
+    assert f"Wrote telomeric reads to {written}.".encode() in p.stderr
+    bad = tmp_path / "bad.fq"
+    bad.write_text("@r1\nACGT\n+\nIII\n")
+    p = subprocess.run([str(BIN), "--fastq-subset", str(bad)], capture_output=True)
+    assert p.returncode == 1 and b"Error: FASTQ record 1: sequence and quality length differ." in p.stderr
+
+
 def test_pipeline_refuses_what_it_does_not_cover(tmp_path):
     gfa = tmp_path / "g.gfa"
     gfa.write_text("H\tVN:Z:1.2\nS\ts1\tACGT\n")
@@ -72,7 +109,7 @@ def test_pipeline_refuses_what_it_does_not_cover(tmp_path):
     assert p.returncode == 2 and b"GFA input" in p.stderr
     fa = tmp_path / "a.fa"
     fa.write_text(">s\nACGT\n")
-    p = subprocess.run([str(BIN), "--fastq-subset", str(fa)], capture_output=True)
-    assert p.returncode == 2 and b"--fastq-subset" in p.stderr
+    p = subprocess.run([str(BIN), "--bam-subset", str(fa)], capture_output=True)
+    assert p.returncode == 2 and b"--bam-subset" in p.stderr
     p = subprocess.run([str(BIN), "-f", str(fa), "-w", "10", "-s", "20", "-o", str(tmp_path)], capture_output=True)
     assert p.returncode == 1 and b"Step size (20) cannot be larger than window size (10)" in p.stderr

@@ -306,6 +306,54 @@ def pipeline_file_to_files(seed: int, scale: float, with_reference: bool):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def fastq_subset_file_to_file(seed: int, total_bp: int, with_reference: bool):
+    """BASELINE.json configs[4], file to file: S-reads written as FASTQ to /dev/shm, `teloscope-b200 --fastq-subset`
+    (process start to exit, subset to a file) and the unmodified reference on the same file; outputs compared."""
+    import torch
+    exe = ROOT / "teloscope_b200" / "teloscope-b200"
+    ref_bin = ROOT / "oracle" / "_ref" / "teloscope"
+    if not exe.exists():
+        return {"unavailable": "teloscope_b200/teloscope-b200 not built"}
+    seq, offsets, n_telo = build_reads("cuda", seed, total_bp)
+    host = seq.cpu().numpy()
+    del seq
+    torch.cuda.empty_cache()
+    tmp = Path(tempfile.mkdtemp(prefix="telo_fq_", dir="/dev/shm" if Path("/dev/shm").exists() else None))
+    try:
+        fq = tmp / "reads.fq"
+        qual = b"I" * int(np.max(np.diff(offsets)))
+        with open(fq, "wb") as fh:
+            for i in range(len(offsets) - 1):
+                a, b = int(offsets[i]), int(offsets[i + 1])
+                fh.write(b"@read%d\n" % i); fh.write(host[a:b].tobytes()); fh.write(b"\n+\n"); fh.write(qual[: b - a]); fh.write(b"\n")
+        bases = int(offsets[-1])
+        out = {"what": "FASTQ file (page cache) -> FASTQ subset file, --fastq-subset -l 42, process start to exit",
+               "bases": bases, "reads": len(offsets) - 1, "fastq_bytes": fq.stat().st_size, "unit": "Gbp/s"}
+        times = []
+        for i in range(3):
+            d = tmp / "ours"
+            shutil.rmtree(d, ignore_errors=True); d.mkdir()
+            t0 = time.perf_counter()
+            subprocess.run([str(exe), "--fastq-subset", "-f", str(fq), "-o", str(d)], check=True, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL)
+            times.append(time.perf_counter() - t0)
+        out["seconds"] = min(times[1:]); out["value"] = bases / out["seconds"] / 1e9
+        if with_reference and ref_bin.exists():
+            cores = os.cpu_count() or 1
+            d = tmp / "ref"
+            d.mkdir()
+            t0 = time.perf_counter()
+            subprocess.run([str(ref_bin), "--fastq-subset", "-f", str(fq), "-j", str(cores), "-o", str(d)], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            dt = time.perf_counter() - t0
+            a, b = (d / "reads.fq_telomeric.fastq").read_bytes(), (tmp / "ours" / "reads.fq_telomeric.fastq").read_bytes()
+            out["reference_same_file"] = {"seconds": dt, "value": bases / dt / 1e9, "cores": cores,
+                                          "outputs_byte_identical": a == b, "subset_bytes": len(a)}
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # --------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm
 # --------------------------------------------------------------------------------------------------
@@ -602,6 +650,10 @@ def main():
                 line["pipeline_e2e"] = pipeline_file_to_files(args.seed, args.scale, not args.no_cpu_baseline)
             except Exception as exc:
                 line["pipeline_e2e"] = {"error": repr(exc)}
+            try:
+                line["fastq_subset_e2e"] = fastq_subset_file_to_file(args.seed + 300, int(1.0e9 * min(1.0, args.scale)), not args.no_cpu_baseline)
+            except Exception as exc:
+                line["fastq_subset_e2e"] = {"error": repr(exc)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

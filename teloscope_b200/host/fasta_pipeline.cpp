@@ -617,8 +617,22 @@ void check(int rc, const char *what) {
 }
 
 int runFastqSubset(const Options &o, const tls_config &baseCfg) {
+    StageTimer timer;
+    tls_config cfg = baseCfg;
+    cfg.min_block_len = o.minBlockLenSet ? o.minBlockLen : 42;          // src/read-filter.cpp:14-16
+    cfg.outputs = 0;
+    tls_ctx *ctx = nullptr;
+    int ctxRc = TLS_OK;
+    std::string ctxErr;
+    std::thread ctxThread([&]() {                              // the CUDA context comes up while the input is mapped / inflated
+        const char *devEnv = getenv("TLS_DEVICE");
+        ctxRc = tls_create(&cfg, devEnv ? atoi(devEnv) : 0, &ctx);
+        if (ctxRc != TLS_OK) ctxErr = tls_last_error();
+    });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{ctxThread};
     InputData in;
     loadInput(o.inSequence, in);
+    timer.mark("read file");
     if (in.n == 0) fastqError(0, "FASTQ input is empty");
     if (in.p[0] != '@') fastqError(0, "FASTQ input must start with '@'");
     FILE *out = stdout;
@@ -628,13 +642,6 @@ int runFastqSubset(const Options &o, const tls_config &baseCfg) {
         out = fopen(outPath.c_str(), "wb");
         if (!out) die("Error: Cannot write telomeric reads to '%s'.\n", outPath.c_str());
     }
-    tls_config cfg = baseCfg;
-    cfg.min_block_len = o.minBlockLenSet ? o.minBlockLen : 42;          // src/read-filter.cpp:14-16
-    cfg.outputs = 0;
-    tls_ctx *ctx = nullptr;
-    const char *devEnv = getenv("TLS_DEVICE");
-    check(tls_create(&cfg, devEnv ? atoi(devEnv) : 0, &ctx), "tls_create");
-
     struct Line { size_t b, e; };
     struct Rec { Line header, sequence, plus, quality; };
     struct Batch { std::vector<Rec> recs; std::vector<uint8_t> seq; std::vector<uint64_t> offsets; int ticket = -1; };
@@ -650,7 +657,7 @@ int runFastqSubset(const Options &o, const tls_config &baseCfg) {
     auto logicalLen = [&](const Line &l) { return l.e - l.b - ((l.e > l.b && in.p[l.e - 1] == '\r') ? 1 : 0); };
     uint64_t recordNumber = 0, totalReads = 0, passedReads = 0;
     const uint64_t batchBytes = getenv("TLS_BATCH_BYTES") ? strtoull(getenv("TLS_BATCH_BYTES"), nullptr, 10) : (256ull << 20);
-    std::vector<std::unique_ptr<Batch>> flight;
+    std::vector<std::unique_ptr<Batch>> flight, pool;
     std::string outBuf;
     auto consume = [&](Batch &b) {
         tls_result r{};
@@ -668,9 +675,15 @@ int runFastqSubset(const Options &o, const tls_config &baseCfg) {
         check(tls_release(ctx, b.ticket), "tls_release");
     };
     bool more = true;
+    double msPack = 0, msSubmit = 0, msCollect = 0;
+    auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     while (more || !flight.empty()) {
         if (more && flight.size() < 2) {
-            auto b = std::make_unique<Batch>();
+            auto t0 = std::chrono::steady_clock::now();
+            std::unique_ptr<Batch> b;
+            if (!pool.empty()) { b = std::move(pool.back()); pool.pop_back(); }     // buffers keep their (touched) capacity
+            else { b = std::make_unique<Batch>(); b->seq.reserve(batchBytes + (64u << 20)); }
+            b->recs.clear(); b->seq.clear(); b->offsets.clear();
             b->offsets.push_back(0);
             while (b->seq.size() < batchBytes && b->recs.size() < (1u << 22)) {
                 Rec rec;
@@ -687,21 +700,34 @@ int runFastqSubset(const Options &o, const tls_config &baseCfg) {
                 b->offsets.push_back(b->seq.size());
                 b->recs.push_back(rec);
             }
+            msPack += since(t0);
             if (!b->recs.empty()) {
+                if (ctxThread.joinable()) {
+                    ctxThread.join();
+                    if (ctxRc != TLS_OK) die("Error: tls_create failed: %s\n", ctxErr.c_str());
+                    timer.mark("first batch + CUDA context");
+                }
+                t0 = std::chrono::steady_clock::now();
                 b->seq.resize(b->seq.size() + 256, 0);
                 tls_batch tb{};
                 tb.seq = b->seq.data(); tb.offsets = b->offsets.data(); tb.abs_pos = nullptr;
                 tb.n_items = static_cast<uint32_t>(b->recs.size()); tb.mode = TLS_MODE_READS;
                 check(tls_submit(ctx, &tb, &b->ticket), "tls_submit");
+                msSubmit += since(t0);
                 flight.push_back(std::move(b));
             }
             if (more && flight.size() < 2) continue;
         }
         if (!flight.empty()) {
+            const auto t0 = std::chrono::steady_clock::now();
             consume(*flight.front());
+            msCollect += since(t0);
+            pool.push_back(std::move(flight.front()));
             flight.erase(flight.begin());
         }
     }
+    timer.mark("scan");
+    if (timer.on) fprintf(stderr, "[pipe]   of which: parse + pack %.1f ms, tls_submit %.1f ms, tls_collect + output %.1f ms\n", msPack, msSubmit, msCollect);
     if (!outBuf.empty()) fwrite(outBuf.data(), 1, outBuf.size(), out);
     fflush(out);
     if (out != stdout) {

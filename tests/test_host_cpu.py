@@ -97,3 +97,28 @@ def test_validity_formula():
             by[rng.integers(0, 12)] = rng.integers(0, 256)
         words = [int.from_bytes(bytes(by[i:i + 4].tolist()), "little") for i in range(0, 12, 4)]
         assert (bad(words) != 0) == any(int(x) not in valid for x in by)
+
+
+def test_pipeline_binary_has_no_cpu_path(tmp_path):
+    """teloscope-b200 is built with the library, parses its flags like the reference (messages, exit codes) and fails
+    loudly when there is no B200: nothing is scanned on the host."""
+    import subprocess
+    exe = ROOT / "teloscope_b200" / "teloscope-b200"
+    assert exe.exists(), "build first: make -C teloscope_b200/csrc"
+    fa = tmp_path / "a.fa"
+    fa.write_text(">s extra words\nACGTNNNNacgt\nTTAGGG\n")
+    p = subprocess.run([str(exe), "-f", str(fa), "-w", "10", "-s", "20", "-o", str(tmp_path)], capture_output=True)
+    assert p.returncode == 1 and b"Error: Step size (20) cannot be larger than window size (10)." in p.stderr
+    p = subprocess.run([str(exe), "-f", str(fa), "-x", "3", "-o", str(tmp_path)], capture_output=True)
+    assert p.returncode == 1 and b"Error: Edit distance (-x/--edit-distance) must be in the range [0,2]." in p.stderr
+    p = subprocess.run([str(exe), "--bam-subset", str(fa)], capture_output=True)
+    assert p.returncode == 2
+    if tb.load_library().tls_device_count() > 0:
+        pytest.skip("a B200 is visible; the refusal path is exercised on the CPU box")
+    p = subprocess.run([str(exe), "-f", str(fa), "-c", "ccctaa", "-o", str(tmp_path)], capture_output=True)
+    assert p.returncode == 1
+    err = p.stderr.decode()
+    assert "Setting canonical pattern: CCCTAA and its reverse complement: TTAGGG" in err
+    assert "Scanning 38 telomeric variants (includes reverse complements)." in err
+    assert "tls_create failed" in err and ("no CUDA device" in err or "sm_100" in err)
+    assert not list(tmp_path.glob("a.fa_*")), "no output file may appear without a scan"

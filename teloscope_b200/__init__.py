@@ -23,7 +23,8 @@ import numpy as np
 __all__ = ["ScanConfig", "Scanner", "BatchResult", "expand_patterns", "load_library", "LIB_PATH",
            "MODE_GENOME", "MODE_TIPS", "MODE_READS", "MATCH_DT", "BLOCK_DT", "WINDOW_DT", "TlsError"]
 
-LIB_PATH = Path(__file__).resolve().parent / "libteloscope_b200.so"
+# TLS_LIB: another build of the library (kernel tuning experiments); the product is the in-tree default
+LIB_PATH = Path(os.environ.get("TLS_LIB") or (Path(__file__).resolve().parent / "libteloscope_b200.so"))
 ABI_VERSION = 1
 MODE_GENOME, MODE_TIPS, MODE_READS = 0, 1, 2
 OUT_ACGT, OUT_MATCHES, OUT_ITS, OUT_COMPACT = 1, 2, 4, 8

@@ -32,7 +32,15 @@ constexpr int kFastFlagBytes = 16384;             // one direct table, pattern l
 constexpr uint32_t kFastMinWindow = 512;          // <= 98 windows per tile, <= 1 window end per span
 
 // ---- geometry of the window-row kernel (scan_rows.cu): a row is one window, a lane owns 32 bases ----
-constexpr int kRowThreads = 1024;
+#ifndef TLS_ROW_THREADS
+#define TLS_ROW_THREADS 768
+#endif
+#ifndef TLS_ROWS_PER_UNIT
+#define TLS_ROWS_PER_UNIT 16
+#endif
+// measured on the 3.03 Gbp batch (threads / rows per unit: scan ms): 1024/8 1.18, 1024/16 1.20, 896/16 1.19, 768/8 1.17,
+// 768/16 1.13, 768/32 1.13, 640/16 1.19, 512/16 1.28.  Other values: make EXTRA=-DTLS_ROW_THREADS=... OUT=... BUILD=...
+constexpr int kRowThreads = TLS_ROW_THREADS;
 constexpr int kRowWarps = kRowThreads / 32;
 constexpr int kRowSpan = 32;                      // bases per lane
 constexpr int kRowStage = 32 * kRowSpan;          // bytes of one staging buffer (1024)
@@ -40,7 +48,7 @@ constexpr int kRowMaxLen = kRowStage - 15 - 7;    // longest window: alignment s
 constexpr uint32_t kRowMinWindow = 600;           // below this more than 40 % of the lanes would idle
 constexpr uint32_t kRowMinWindows = 8;            // shorter contigs go to the general kernel
 constexpr int kRowQueueCap = 256;                 // per-warp match queue (u16 entries), 8 lanes' worth
-constexpr int kRowsPerUnit = 8;                   // consecutive windows one warp takes at a time
+constexpr int kRowsPerUnit = TLS_ROWS_PER_UNIT;   // consecutive windows one warp takes at a time (divides kTileRows)
 
 // A maximal stretch of one item inside which matches must lie entirely
 // (genome mode: the whole contig; tips mode: [0,T) and [n-T,n); reads: the whole read).

@@ -8,12 +8,13 @@
 // crosses a window end and windows tile the contig from its start (:604-637), so a window is an
 // independent row: no halo, no boundary inside a row, its 8 counters belong to exactly one warp.
 //
-//   * warps are autonomous and never meet at a barrier.  Work = units of 8 consecutive windows, unit u
-//     goes to warp u mod (warps in the grid);
+//   * warps are autonomous and never meet at a barrier.  One CTA of 768 threads per SM (24 warps, 71 registers each:
+//     fewer, fatter warps beat 32 warps at 64 registers).  Work = units of 16 consecutive windows, unit u goes to
+//     warp u mod (warps in the grid);
 //   * a lane owns 32 bases of the row: two 16-byte streaming loads (ld.global.nc, no L1 allocation)
 //     from the 16-byte aligned span of the row straight into registers.  They are packed at the top of
 //     the row's iteration and the same registers are re-armed at once with the NEXT row's loads, which
-//     then have the whole iteration to land (software pipeline of depth one row per warp, 32 KiB in
+//     then have the whole iteration to land (software pipeline of depth one row per warp, 24 KiB in
 //     flight per SM); no shared-memory staging, no mbarrier;
 //   * SWAR pack to 2-bit codes (one multiply per 4 bases) fused with the exact "all bytes are ACGTacgt"
 //     test; the row's alignment skew is removed on the packed words (one funnel shift per word);
@@ -118,7 +119,7 @@ __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane) {
 // kWindowBase bytes into it on sm_100 (checked at run time: status 1 otherwise), so every address below
 // is a compile-time constant and goes into the instruction as an immediate. -------------------------------
 constexpr uint32_t kWindowBase = 0x400;
-constexpr uint32_t kWarpBlk = 256;                         // per warp: row results of the unit in flight
+constexpr uint32_t kWarpBlk = kRowsPerUnit <= 8 ? 256 : (kRowsPerUnit <= 16 ? 512 : 1024);  // per warp: row results of the unit in flight
 constexpr uint32_t kRecOff = 0;                            //   8 x 16 bytes of window / slot results + 8 overflow bases
 static_assert(kRecOff + kRowsPerUnit * 20 <= kWarpBlk, "per-warp block");
 constexpr uint32_t kWarpBase = kWindowBase;                               // 8 KiB of warp blocks
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
             k2 = all | (can << 16);
             k3 = fwd | (nct << 16);
         }
-        k2 = __reduce_add_sync(0xFFFFFFFFu, k2);               // <= 8 rows x 1002 per half: no carry between the halves
+        k2 = __reduce_add_sync(0xFFFFFFFFu, k2);               // <= 32 rows x 1002 per half: no carry between the halves
         k3 = __reduce_add_sync(0xFFFFFFFFu, k3);
         const uint32_t uAll = k2 & 0xFFFFu, uCan = k2 >> 16, uFwd = k3 & 0xFFFFu, uNct = k3 >> 16;
         if (uAll) {
@@ -442,7 +443,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
 }
 
 // Work units of the window-row kernel, one thread per unit: unit j of a contig covers its windows
-// [8j, 8j + 8), tile j / 4, row slots (j % 4) * 8 ... of that tile.
+// [16j, 16j + 16) (kRowsPerUnit), tile j / 2, row slots (j % 2) * 16 ... of that tile.
 __global__ void __launch_bounds__(256) rowPlanKernel(const DevRowRegion *regions, uint32_t nRegions, uint32_t W,
                                                      DevRowUnit *units, uint32_t nUnits) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;

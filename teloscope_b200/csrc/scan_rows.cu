@@ -52,7 +52,8 @@ __device__ __forceinline__ uint32_t smemAddr(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 // Streaming loads of a lane's 32 bytes (every base is read once, nothing of it belongs in L1), done only
-// when a < b; otherwise the registers keep what they hold.
+// when a < b; otherwise the registers keep what they hold.  (Plain ld.global.nc and an L2::256B prefetch hint
+// were measured: no difference.)
 __device__ __forceinline__ void ldStream32If(uint4 &v0, uint4 &v1, uint64_t addr, uint32_t a, uint32_t b) {
     asm volatile(
         "{\n"

@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     const uint64_t seqBase = reinterpret_cast<uint64_t>(p.seq);
     const uint32_t slotBytes = p.slotCap * 8u;
     const bool lane0 = lane == 0;
+    const uint32_t laneLt = (1u << lane) - 1u;
 
     // Per-lane masks of a row of rowLen bases: the lane's valid 2-bit fields in X0 / X1, its valid match
     // starts (a match never crosses the window end, src/teloscope.cpp:439) and its number of bases << 16.
@@ -345,8 +346,18 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
             const bool rowHasTerm = rel <= T || rowEnd > termEnd;                               // warp-uniform
             const bool rowAllTerm = rowEnd <= T + 1u || rel >= termEnd;                         // warp-uniform
             const uint32_t nH = __popc(H);
-            const uint32_t incl = warpInclusiveScan(nH, lane);
-            const uint32_t wMatches = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            uint32_t incl, wMatches;
+            if (!__any_sync(0xFFFFFFFFu, nH > 7u)) {
+                // at most 7 matches per lane (any row but a homopolymer-like one): the prefix from three independent
+                // ballots on the bits of the count instead of five dependent shuffles
+                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, nH & 1u), b1 = __ballot_sync(0xFFFFFFFFu, nH & 2u),
+                               b2 = __ballot_sync(0xFFFFFFFFu, nH & 4u);
+                incl = __popc(b0 & laneLt) + 2u * __popc(b1 & laneLt) + 4u * __popc(b2 & laneLt) + nH;
+                wMatches = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+            } else {
+                incl = warpInclusiveScan(nH, lane);
+                wMatches = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
             const uint32_t relLane = rel + laneOff;
             uint32_t acc = 0, rowNct = 0;
             if (wMatches <= p.slotCap && (rowAllTerm || !rowHasTerm)) {
@@ -397,7 +408,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
             const uint32_t flagSum = __reduce_add_sync(0xFFFFFFFFu, (acc & 127u) | ((acc >> 7) << 16));
 
             // ---- 7. the row's results wait in shared memory for the unit epilogue ----------------------------------
-            if (lane0) {
+            {   // all four values are warp-uniform: every lane stores them to the same address (one wavefront, no election)
                 const uint32_t w2 = wMatches | (rowNct << 12) | (rowAllTerm ? 0x80000000u : 0u);
                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sum1), "r"(sum2), "r"(w2), "r"(flagSum) : "memory");
             }

@@ -66,17 +66,24 @@ struct Options {
     unsigned threads = 0;                       // -j: host threads of the parse / formatting stages (0 = all cores)
 };
 
+// Leaves without running static destructors: the CUDA context may still be coming up on its own thread, and tearing
+// the runtime down underneath it crashes.  Everything written so far is flushed first.
+[[noreturn]] void quit(int status) {
+    fflush(stdout);
+    fflush(stderr);
+    _exit(status);
+}
 [[noreturn]] void die(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
 void die(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vfprintf(stderr, fmt, ap);
     va_end(ap);
-    exit(EXIT_FAILURE);
+    quit(EXIT_FAILURE);
 }
 [[noreturn]] void unsupported(const char *what) {
     fprintf(stderr, "teloscope-b200: %s is not part of the B200 FASTA pipeline (use the reference binary for it).\n", what);
-    exit(2);
+    quit(2);
 }
 
 std::string upper(std::string s) {
@@ -613,7 +620,7 @@ void check(int rc, const char *what) {
 [[noreturn]] void fastqError(uint64_t recordNumber, const char *message) {
     if (recordNumber > 0) fprintf(stderr, "Error: FASTQ record %llu: %s.\n", static_cast<unsigned long long>(recordNumber), message);
     else fprintf(stderr, "Error: %s.\n", message);
-    exit(EXIT_FAILURE);
+    quit(EXIT_FAILURE);
 }
 
 int runFastqSubset(const Options &o, const tls_config &baseCfg) {

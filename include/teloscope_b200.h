@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TLS_ABI_VERSION 1
+#define TLS_ABI_VERSION 2   /* 2: tls_result grew (windows16, canonical8, noncanonical8), TLS_OUT_COMPACT */
 
 typedef enum {
     TLS_OK = 0,

@@ -25,7 +25,7 @@ __all__ = ["ScanConfig", "Scanner", "BatchResult", "expand_patterns", "load_libr
 
 # TLS_LIB: another build of the library (kernel tuning experiments); the product is the in-tree default
 LIB_PATH = Path(os.environ.get("TLS_LIB") or (Path(__file__).resolve().parent / "libteloscope_b200.so"))
-ABI_VERSION = 1
+ABI_VERSION = 2
 MODE_GENOME, MODE_TIPS, MODE_READS = 0, 1, 2
 OUT_ACGT, OUT_MATCHES, OUT_ITS, OUT_COMPACT = 1, 2, 4, 8
 
@@ -266,6 +266,7 @@ class Scanner:
         _check(L.tls_create(C.byref(c), device, C.byref(h)))
         self._h, self._L = h, L
         self._keep = {}
+        self._abs_pos = {}               # ticket -> abs_pos of the batch (compact match records are item-relative)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -304,7 +305,6 @@ class Scanner:
         t = C.c_int()
         _check(self._L.tls_submit(self._h, C.byref(b), C.byref(t)))
         self._keep[t.value] = keep
-        self._abs_pos = getattr(self, "_abs_pos", {})
         self._abs_pos[t.value] = abs_pos
         return t.value
 

@@ -118,3 +118,28 @@ def test_rows_equal_general_kernel(tb):
     for a, b in zip(*out):
         for k in ("windows", "canonical", "noncanonical", "terminal", "its"):
             assert a[k].tobytes() == b[k].tobytes(), k
+
+
+def test_rows_without_acgt_counts(tb):
+    """-r / -m / -i without -g / -e: the COUNT = false instantiation of the window-row kernel (no A/C/G/T counting);
+    the window's A/C/G/T fields stay zero, everything else equals the oracle."""
+    rng = np.random.default_rng(4242)
+    cfg = ol.Config(patterns=["TTAGGG", "TCAGGG", "TGAGGG", "TTGGGG"], terminal_limit=6000)
+    cfg.count_acgt = False
+    seqs = [make_contig(rng, int(n), "TTAGGG", i % 2 == 0) for i, n in enumerate(rng.integers(900, 80000, size=10))]
+    orc = ol.Oracle(cfg)
+    sc = tb.Scanner(pa.scan_config(cfg))
+    try:
+        res = sc.scan_batch(seqs, None, tb.MODE_GENOME)
+        for i, s in enumerate(seqs):
+            want = orc.scan_segment(s.upper(), 0, False)
+            got = res.item(i)
+            assert not got["windows"]["acgt"].any() and not want["windows"]["acgt"].any()
+            for f in ("can_cov", "noncan_cov", "fwd_cov", "rev_cov"):
+                assert np.array_equal(got["windows"][f], want["windows"][f]), (i, f)
+            for k in ("canonical", "noncanonical"):
+                assert np.array_equal(got[k]["pos"], want[k]["pos"]), (i, k)
+            for k in ("terminal", "its"):
+                assert np.array_equal(got[k]["start"], want[k]["start"]) and np.array_equal(got[k]["len"], want[k]["len"]), (i, k)
+    finally:
+        sc.close()

@@ -627,6 +627,7 @@ def main():
                             "note": "rank 0's kernels; all_ranks = sum over ranks of bases / own scan-kernel time (device-side scaling: "
                                     "the whole-step value at N > 1 is bound by the result copies of all ranks sharing the host link)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": "tls::rowScanKernel<3,true> (+ the two small launches that take "
                          "contigs shorter than 8 windows); duration = all three, CUDA events on the ctx stream, mean over "
                          "the timed steps", "algorithmic_bytes": algo_bytes, "bytes_per_base": algo_bytes / n_bases,

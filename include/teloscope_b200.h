@@ -176,9 +176,13 @@ int tls_device_count(void);                               /* sm_100 devices visi
 int tls_create(const tls_config *cfg, int device, tls_ctx **out);
 void tls_destroy(tls_ctx *ctx);
 
-/* Asynchronous: stages the batch (pinned double buffer -> cudaMemcpyAsync), enqueues the kernels
- * and the result copies on the ctx's stream and returns a ticket.  At most two tickets may be in
- * flight.  The caller's buffers may be reused as soon as tls_submit returns. */
+/* Asynchronous: stages the batch (cudaMemcpyAsync), enqueues the kernels and the result copies on
+ * the ctx's stream and returns a ticket.  At most two tickets may be in flight.
+ * Lifetime of the caller's buffers: offsets / abs_pos are copied before tls_submit returns.  A
+ * PAGEABLE seq buffer is staged through the library's pinned ring before tls_submit returns and may
+ * be reused at once.  A PINNED host seq buffer (cudaHostAlloc / cudaHostRegister) is read by an
+ * asynchronous DMA, and a DEVICE seq buffer (seq_on_device) is read by the kernels, including
+ * those tls_collect enqueues: both must stay untouched until tls_collect(ticket) has returned. */
 int tls_submit(tls_ctx *ctx, const tls_batch *batch, int *ticket);
 /* Blocks until the ticket's work is done and fills *res with pointers into ctx-owned host memory,
  * valid until tls_release(ticket). */

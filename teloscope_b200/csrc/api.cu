@@ -259,7 +259,7 @@ extern "C" {
 
 const char *tls_last_error(void) { return g_err.c_str(); }
 
-int tls_expand_patterns(const char *raw_csv, int edit_distance, const char *canonical_fwd, char *text,
+static int tls_expand_patterns_impl(const char *raw_csv, int edit_distance, const char *canonical_fwd, char *text,
                         size_t text_len, uint8_t *is_forward, uint8_t *is_canonical, uint32_t cap,
                         uint32_t *n_out, size_t *text_need) {
     if (!raw_csv || !canonical_fwd || !n_out) return fail(TLS_ERR_INVALID, "null argument");
@@ -304,7 +304,7 @@ int tls_device_count(void) {
     return ok;
 }
 
-int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
+static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
     if (!cfg || !out) return fail(TLS_ERR_INVALID, "null argument");
     *out = nullptr;
     if (cfg->abi_version != TLS_ABI_VERSION) return fail(TLS_ERR_INVALID, "ABI version mismatch");
@@ -325,7 +325,9 @@ int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
                     prop.major, prop.minor);
     TLS_CUDA(cudaSetDevice(device));
 
-    std::unique_ptr<tls_ctx> ctx(new (std::nothrow) tls_ctx);
+    // any failure below releases what was built so far (device buffers, streams, events) through tls_destroy
+    struct Destroy { void operator()(tls_ctx *c) const { tls_destroy(c); } };
+    std::unique_ptr<tls_ctx, Destroy> ctx(new (std::nothrow) tls_ctx);
     if (!ctx) return fail(TLS_ERR_NOMEM, "out of memory");
     ctx->device = device;
     ctx->smCount = prop.multiProcessorCount;
@@ -599,8 +601,11 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
                                 s.hScanDev, s.stream));
         s.launches++;
     } else {
+        // a batch whose items are all empty: no kernel runs, every per-item counter reads as zero
         TLS_CUDA(cudaMemsetAsync(s.dTileBase.p, 0, 24, s.stream));
         std::memset(s.hScan.p, 0, 64);
+        TLS_CUDA(s.hItemCounts.reserve(std::max<size_t>(s.nItems, 1) * sizeof(DevItemCounts)));
+        std::memset(s.hItemCounts.p, 0, std::max<size_t>(s.nItems, 1) * sizeof(DevItemCounts));
     }
     return TLS_OK;
 }
@@ -609,7 +614,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
 
 extern "C" {
 
-int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
+static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     if (!ctx || !b || !ticket) return fail(TLS_ERR_INVALID, "null argument");
     if (b->n_items && (!b->seq || !b->offsets)) return fail(TLS_ERR_INVALID, "null batch arrays");
     if (b->mode > TLS_MODE_READS) return fail(TLS_ERR_INVALID, "bad mode %u", b->mode);
@@ -857,7 +862,7 @@ int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     return TLS_OK;
 }
 
-int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
+static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
     if (!ctx || !res || ticket < 0 || ticket > 1 || !ctx->slot[ticket].busy)
         return fail(TLS_ERR_STATE, "bad ticket");
     TLS_CUDA(cudaSetDevice(ctx->device));
@@ -875,10 +880,13 @@ int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
                                            "set TLS_FORCE_GENERAL=1");
             if (tr.on) fprintf(stderr, " row_tiles=%zu lean_tiles=%zu/%zu redo_rows=%u", s.nRowTiles, s.fastTiles.size(), static_cast<size_t>(s.nTilesAll),
                                static_cast<uint32_t>(hs[4]));
-            const uint32_t ovUsed = static_cast<uint32_t>(hs[0]);
+            const uint64_t ovUsed = hs[0];                     // 64-bit cursor: the true demand, never wrapped
             s.nMatches = hs[1]; s.nCanAll = hs[2]; s.nNctAll = hs[3];
             if (ovUsed <= s.ovCap) break;
-            s.ovCap = ovUsed + ovUsed / 4;
+            if (ovUsed + ovUsed / 4 > 0xF0000000ull)
+                return fail(TLS_ERR_INVALID, "the batch needs %llu overflow match records (> 2^32); submit smaller batches",
+                            static_cast<unsigned long long>(ovUsed));
+            s.ovCap = static_cast<uint32_t>(ovUsed + ovUsed / 4);
             if ((rc = enqueueScan(ctx, s))) return rc;
         }
         if (s.nMatches > 0xFFFFFFF0ull) return fail(TLS_ERR_INVALID, "more than 2^32 matches in one batch; submit smaller batches");
@@ -1066,6 +1074,40 @@ int tls_release(tls_ctx *ctx, int ticket) {
     if (!ctx || ticket < 0 || ticket > 1 || !ctx->slot[ticket].busy) return fail(TLS_ERR_STATE, "bad ticket");
     ctx->slot[ticket].busy = false;
     return TLS_OK;
+}
+
+}  // extern "C"
+
+// ---- the exported entry points: nothing throws across the ABI (std::bad_alloc / length_error from the host-side
+//      containers become TLS_ERR_NOMEM / TLS_ERR_INVALID with a message) ----------------------------------------------
+namespace {
+template <typename F> int guarded(F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return fail(TLS_ERR_NOMEM, "out of host memory");
+    } catch (const std::exception &e) {
+        return fail(TLS_ERR_INVALID, "internal error: %s", e.what());
+    } catch (...) {
+        return fail(TLS_ERR_INVALID, "internal error");
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int tls_expand_patterns(const char *raw_csv, int edit_distance, const char *canonical_fwd, char *text, size_t text_len,
+                        uint8_t *is_forward, uint8_t *is_canonical, uint32_t cap, uint32_t *n_out, size_t *text_need) {
+    return guarded([&] { return tls_expand_patterns_impl(raw_csv, edit_distance, canonical_fwd, text, text_len, is_forward, is_canonical, cap, n_out, text_need); });
+}
+int tls_create(const tls_config *cfg, int device, tls_ctx **out) {
+    return guarded([&] { return tls_create_impl(cfg, device, out); });
+}
+int tls_submit(tls_ctx *ctx, const tls_batch *b, int *ticket) {
+    return guarded([&] { return tls_submit_impl(ctx, b, ticket); });
+}
+int tls_collect(tls_ctx *ctx, int ticket, tls_result *res) {
+    return guarded([&] { return tls_collect_impl(ctx, ticket, res); });
 }
 
 }  // extern "C"

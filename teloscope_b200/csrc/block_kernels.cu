@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, 
     if (threadIdx.x == 0) {
         carry = 0;
         if (k == 0) {
-            hostOut[0] = *ovCursor;
+            hostOut[0] = *reinterpret_cast<const unsigned long long *>(ovCursor);
             hostOut[4] = redo ? (static_cast<unsigned long long>(redo[0]) | (static_cast<unsigned long long>(redo[1]) << 32)) : 0ull;
         }
     }

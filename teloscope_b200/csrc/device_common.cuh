@@ -25,4 +25,13 @@ __device__ __forceinline__ bool isTerminalMatch(const DevConfig &c, uint32_t rel
     return rel <= T || rel >= termEnd;
 }
 
+// One overflow chunk of `chunk` records from the bump-allocated arena.  The cursor is 64 bits wide, so the host always
+// reads the true demand (a dense batch cannot wrap it); the returned base saturates below kNoOverflow and every write
+// is bounds-checked against the arena capacity (<= kMaxOvRecords) in 64 bits.
+constexpr uint32_t kMaxOvRecords = 0xF0000000u;
+__device__ __forceinline__ uint32_t takeOverflowChunk(unsigned int *cursor, uint32_t chunk) {
+    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(cursor), static_cast<unsigned long long>(chunk));
+    return old < kMaxOvRecords ? static_cast<uint32_t>(old) : kMaxOvRecords;
+}
+
 }  // namespace tls

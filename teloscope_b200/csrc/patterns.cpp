@@ -108,7 +108,10 @@ bool expandPatterns(const std::vector<std::string> &rawPatterns, int editDistanc
             if (editDistance >= 1) appendNeighbours(combo, variants);
             if (editDistance >= 2) {
                 const size_t d1End = variants.size();
-                for (size_t v = 1; v < d1End; ++v) appendNeighbours(variants[v], variants);
+                for (size_t v = 1; v < d1End; ++v) {
+                    const std::string src = variants[v];   // a copy: appendNeighbours grows (reallocates) `variants`
+                    appendNeighbours(src, variants);
+                }
             }
             for (const std::string &v : variants) {
                 std::string rc;

@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fastScanKernel(const FastPara
                 auto emitRange = [&](uint32_t total) {          // queue[0, total) holds row byte offsets, ascending
                     const bool roomy = wMatches + total <= p.slotCap;           // warp-uniform
                     if (!roomy && ovBase == kNoOverflow) {
-                        if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
+                        if (lane == 0) ovBase = takeOverflowChunk(p.ovCursor, p.ovChunk);
                         ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
                     }
                     uint2 *out = reinterpret_cast<uint2 *>(slot) + wMatches;

@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scanKernel(const ScanParams p
                     excl = incl - nHit;
                 }
                 if (wMatches + total > p.slotCap && ovBase == kNoOverflow) {
-                    if (lane == 0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
+                    if (lane == 0) ovBase = takeOverflowChunk(p.ovCursor, p.ovChunk);
                     ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
                 }
                 uint32_t o = wMatches + excl, nCanLane = 0, nNctLane = 0;

@@ -104,3 +104,28 @@ def test_golden_fastq_cases(tb, golden):
             scanner.close()
         done += 1
     assert done >= 15
+
+
+def test_batches_of_only_empty_items(tb):
+    """A batch whose items are all empty launches no kernel: as the first submission of a fresh context and
+    after a non-empty one (stale per-item counters), every mode returns empty results like the reference's SegmentData."""
+    for mode in (tb.MODE_GENOME, tb.MODE_TIPS, tb.MODE_READS):
+        sc = tb.Scanner(tb.ScanConfig())
+        try:
+            for rep in range(2):
+                res = sc.scan_batch([b"", b"", b""], None, mode)
+                assert res.n_matches == 0
+                for i in range(3):
+                    it = res.item(i)
+                    if mode == tb.MODE_READS:
+                        assert not res.passed[i]
+                        continue
+                    assert len(it["terminal"]) == 0 and len(it["its"]) == 0
+                    assert res.n_fwd[i] == 0 and res.n_rev[i] == 0
+                    if mode == tb.MODE_GENOME:
+                        assert it["n_canonical"] == 0 and len(it["windows"]) == 0
+                # a non-empty batch in between leaves per-item counters behind
+                full = sc.scan_batch([b"TTAGGG" * 100, b"CCCTAA" * 80 + b"ACGT" * 500, b"ACGTTGCA" * 40], None, mode)
+                assert full.n_matches > 0
+        finally:
+            sc.close()

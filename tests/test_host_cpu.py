@@ -53,6 +53,46 @@ def test_pattern_table_equals_oracle(x):
         assert [c for _, _, c in got] == [p in (can_fwd, can_rev) for p, _ in want]
 
 
+def _hamming_ball(seed, x):
+    out = {seed}
+    for _ in range(x):
+        nxt = set(out)
+        for s in out:
+            for i, ch in enumerate(s):
+                for b in "ACGT":
+                    if b != ch:
+                        nxt.add(s[:i] + b + s[i + 1:])
+        out = nxt
+    return out
+
+
+def test_expand_patterns_under_asan(tmp_path):
+    """-x 2 grows the variant vector while reading from it (use-after-free in the distance-2 expansion):
+    the producer runs under AddressSanitizer and must equal a brute-force enumeration of the Hamming balls."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "asan_patterns"
+    src = ROOT / "teloscope_b200" / "csrc"
+    subprocess.run(["g++", "-std=c++17", "-g", "-O0", "-fsanitize=address", f"-I{src}", str(ROOT / "tests" / "asan_patterns_main.cpp"),
+                    str(src / "patterns.cpp"), "-o", str(exe)], check=True)
+    for x, seeds, can in [(2, ["CCCTAA"], "CCCTAA"), (2, ["TTAGGG", "TCAGGG"], "CCCTAA"), (2, ["CCCTAAA"], "CCCTAAA"), (1, ["TTAGGR"], "CCCTAA")]:
+        r = subprocess.run([str(exe), str(x), can] + seeds, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        got = [ln.split()[0] for ln in r.stdout.splitlines()]
+        want = set()
+        for s in seeds:
+            for combo in ol.iupac_expand(s) if hasattr(ol, "iupac_expand") else [s]:
+                for v in _hamming_ball(combo, x):
+                    want.add(v)
+                    want.add(ol.revcomp(v))
+        if all(set(s) <= set("ACGT") for s in seeds):
+            assert got == sorted(want), (seeds, x, len(got), len(want))
+        assert [(p, f) for p, f in (ln.split()[:2] for ln in r.stdout.splitlines())] == \
+            [(p, str(int(f))) for p, f in ol.expand_patterns(seeds, x, can)]
+
+
 def test_golden_case_pattern_counts(golden):
     cases, _ = golden
     seen = set()

@@ -94,6 +94,8 @@ struct Slot {
     bool busy = false, collected = false;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;       // window / item counters go home while the block kernels run
+    cudaStream_t selStream = nullptr;        // -m lists: final records and their copy home, beside the block kernels
+    cudaEvent_t evGather = nullptr;
     cudaEvent_t evScanDone = nullptr, evCopyDone = nullptr;
     static constexpr int kMaxParts = 8;      // launches of the window-row kernel on a large batch (result copy overlaps the scan)
     cudaEvent_t evPart[kMaxParts] = {};
@@ -119,11 +121,18 @@ struct Slot {
     const uint8_t *devSeq = nullptr;         // sequence on the device (own buffer or caller's)
     HostBuf hSeq, hMeta, hMeta2;              // pinned staging
     DevBuf dRowTiles, dRowRegions, dFastTiles, dGeneralTiles, dRedo, dTileTot, dCanIdx, dNctIdx, dRunStarts;
+    DevBuf dZeroLanes, dItemInfo, dConn, dWinRanges;      // window-row items: zero-lane masks per window, per-item info, ITS scratch
+    std::vector<DevItemInfo> itemInfo;
+    std::vector<uint2> winRanges;            // windows NOT written by the window-row kernel: [x, y) ranges ...
+    std::vector<uint32_t> winRangePrefix;    // ... and the exclusive prefix of their lengths (nRanges + 1)
+    uint32_t nRowItems = 0;
+    HostBuf hMeta3;
+    bool fusedReads = false;                 // TLS_MODE_READS batch scored by the one-warp-per-read kernel (scan_reads.cu)
     uint64_t nCanAll = 0, nNctAll = 0;       // canonical / terminal non-canonical records of the batch
     DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotMeta,
         dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon, dWindows16;
     uint32_t ovCap = 0;
-    // device counters block: [0] ovCursor(u32) [16] blockCount(u32) [24] selTotals(2 x u64)
+    // device counters block: [0] ovCursor(u64) [16] blockCount(u32) [20] ITS run count [24] ITS chain count
     HostBuf hScan, hCounters, hWindows, hItemCounts, hBlocks, hPass, hSelCan, hSelNon;
     uint64_t matchCap = 0;
     uint32_t blockCap = 0;
@@ -151,10 +160,12 @@ struct tls_ctx {
     ScanTables tables;
     DevConfig dcfg{};
     DevBuf dIndex, dFlags, dKeys, dKeyFlags;
+    DevBuf dIndex16;                         // window-row kernel: one byte per 8-mer (hit | forward fields per start offset, canonical bit)
     uint32_t slotCap = 0, ovChunk = 0;
     std::string overlapRefusal;              // non-empty: genome-mode batches are refused (see buildDevConfig)
     bool forceGeneral = false;               // TLS_FORCE_GENERAL=1 or a lean-kernel layout failure
     bool noRowKernel = false;                // TLS_NO_ROW_KERNEL=1: 1536-base-row lean kernel instead of the window-row kernel
+    bool noReadKernel = false;               // TLS_NO_READ_KERNEL=1: reads through the general scan + block kernels (A/B tests)
     bool compact = false;                    // TLS_OUT_COMPACT: tls_window16 / tls_match8 results
     int rowParts = 3;                        // TLS_ROW_PARTS=n (1..8): launches of the window-row kernel on a large batch
     uint32_t rowMinWindows = kRowMinWindows; // TLS_ROW_MIN_WINDOWS=n: shortest contig (in windows) the window-row kernel takes
@@ -351,6 +362,21 @@ static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
         std::copy(t.flagTables.begin(), t.flagTables.end(), padded.begin());
         if ((rc = upload(ctx->dFlags, padded.data(), padded.size()))) return rc;
     }
+    if (t.classes.size() == 1 && t.classes[0].direct && t.classes[0].len <= 7) {
+        // the window-row kernel's table: per 8-mer and start offset o < NP the hit and forward flags of the L-mer that starts
+        // there, and one bit that says whether one of them is the canonical pattern
+        const uint32_t L = t.classes[0].len, NP = rowNpos(L), mask = (1u << (2 * L)) - 1u;
+        std::vector<uint8_t> idx(65536, 0);
+        for (uint32_t key = 0; key < 65536; ++key) {
+            uint32_t e = 0;
+            for (uint32_t o = 0; o < NP; ++o) {
+                const uint8_t f = t.flagTables[t.classes[0].flagOffset + ((key >> (2 * o)) & mask)];
+                if (f & 1u) e |= (1u << o) | ((f & 2u) ? 1u << (NP + o) : 0u) | ((f & 4u) ? 1u << (2 * NP) : 0u);
+            }
+            idx[key] = static_cast<uint8_t>(e);
+        }
+        if ((rc = upload(ctx->dIndex16, idx.data(), idx.size()))) return rc;
+    }
     if ((rc = upload(ctx->dKeys, t.sortedKeys.data(), t.sortedKeys.size() * 8))) return rc;
     if ((rc = upload(ctx->dKeyFlags, t.sortedFlags.data(), t.sortedFlags.size()))) return rc;
     {
@@ -367,6 +393,8 @@ static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
     for (Slot &s : ctx->slot) {
         TLS_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         TLS_CUDA(cudaStreamCreateWithFlags(&s.copyStream, cudaStreamNonBlocking));
+        TLS_CUDA(cudaStreamCreateWithFlags(&s.selStream, cudaStreamNonBlocking));
+        TLS_CUDA(cudaEventCreateWithFlags(&s.evGather, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreateWithFlags(&s.evScanDone, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreateWithFlags(&s.evCopyDone, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreate(&s.evScan0)); TLS_CUDA(cudaEventCreate(&s.evScan1)); TLS_CUDA(cudaEventCreate(&s.evFast1));
@@ -379,6 +407,7 @@ static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
     }
     ctx->forceGeneral = std::getenv("TLS_FORCE_GENERAL") != nullptr;
     ctx->noRowKernel = std::getenv("TLS_NO_ROW_KERNEL") != nullptr;
+    ctx->noReadKernel = std::getenv("TLS_NO_READ_KERNEL") != nullptr;
     if (const char *e = std::getenv("TLS_ROW_PARTS")) ctx->rowParts = std::min(static_cast<int>(Slot::kMaxParts), std::max(1, std::atoi(e)));
     if (const char *e = std::getenv("TLS_ROW_MIN_WINDOWS")) ctx->rowMinWindows = std::max(1, std::atoi(e));
     *out = ctx.release();
@@ -391,13 +420,13 @@ void tls_destroy(tls_ctx *ctx) {
     for (Slot &s : ctx->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         for (DevBuf *b : {&s.dRowTiles, &s.dRowRegions, &s.dFastTiles, &s.dGeneralTiles, &s.dRedo, &s.dTileTot, &s.dCanIdx,
-                          &s.dNctIdx, &s.dRunStarts})
+                          &s.dNctIdx, &s.dRunStarts, &s.dZeroLanes, &s.dItemInfo, &s.dConn, &s.dWinRanges})
             b->release();
         for (DevBuf *b : {&s.dAbsPos, &s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
                           &s.dMatches, &s.dSlots, &s.dSlotMeta, &s.dOvArena, &s.dTileBase, &s.dCounters,
                           &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch, &s.dSelCan, &s.dSelNon, &s.dWindows16})
             b->release();
-        for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hMeta2, &s.hScan, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
+        for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hMeta2, &s.hMeta3, &s.hScan, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
                            &s.hSelCan, &s.hSelNon})
             b->release();
         if (s.evScan0) cudaEventDestroy(s.evScan0);
@@ -406,12 +435,14 @@ void tls_destroy(tls_ctx *ctx) {
         if (s.evAll0) cudaEventDestroy(s.evAll0);
         if (s.evAll1) cudaEventDestroy(s.evAll1);
         if (s.copyStream) { cudaStreamSynchronize(s.copyStream); cudaStreamDestroy(s.copyStream); }
+        if (s.selStream) { cudaStreamSynchronize(s.selStream); cudaStreamDestroy(s.selStream); }
+        if (s.evGather) cudaEventDestroy(s.evGather);
         if (s.evScanDone) cudaEventDestroy(s.evScanDone);
         for (cudaEvent_t &e : s.evPart) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (s.evCopyDone) cudaEventDestroy(s.evCopyDone);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
-    for (DevBuf *b : {&ctx->dIndex, &ctx->dFlags, &ctx->dKeys, &ctx->dKeyFlags}) b->release();
+    for (DevBuf *b : {&ctx->dIndex, &ctx->dIndex16, &ctx->dFlags, &ctx->dKeys, &ctx->dKeyFlags}) b->release();
     for (int k = 0; k < tls_ctx::kRing; ++k) {
         if (ctx->ringEv[k]) cudaEventDestroy(ctx->ringEv[k]);
         ctx->ring[k].release();
@@ -463,8 +494,16 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
     TLS_CUDA(cudaMemsetAsync(s.dRedo.p, 0, 16, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 64, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dItemCounts.p, 0, std::max<size_t>(s.nItems, 1) * sizeof(DevItemCounts), s.stream));
-    if (s.nWindows) TLS_CUDA(cudaMemsetAsync(s.dWindows.p, 0, s.nWindows * 32, s.stream));
     s.launches = 0;
+    // window counters: the window-row kernel writes final records; the other scan kernels add into zeroed 32-byte counters
+    const uint2 *dRanges = s.dWinRanges.as<uint2>();
+    const uint32_t *dRangePrefix = reinterpret_cast<const uint32_t *>(s.dWinRanges.as<uint8_t>() + s.winRanges.size() * sizeof(uint2));
+    const uint32_t nRanges = static_cast<uint32_t>(s.winRanges.size()), nRangeWindows = s.winRangePrefix.back();
+    if (s.nWindows && !s.nRowUnits) TLS_CUDA(cudaMemsetAsync(s.dWindows.p, 0, s.nWindows * 32, s.stream));
+    else if (nRangeWindows) {
+        TLS_CUDA(launchZeroWindowRanges(s.dWindows.as<uint32_t>(), dRanges, dRangePrefix, nRanges, nRangeWindows, s.stream));
+        s.launches++;
+    }
     if (nTiles) {
         DevConfig cfg = ctx->dcfg;
         cfg.mode = s.mode;
@@ -528,13 +567,26 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         // (One launch with progress counters and a polling kernel on the side stream was tried: it disturbed the scan.)
         const uint32_t nRow = s.nRowUnits;
         const bool anyWindows = s.mode == TLS_MODE_GENOME && s.nWindows && !cfg.overlapWindows;
-        const bool copyWindows = anyWindows && !ctx->compact;       // compact: packed to 16 bytes after the scan, then copied
-        if (copyWindows) TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
+        // what goes home per window: the 32-byte counters, or (TLS_OUT_COMPACT) 16-byte records: written directly by the
+        // window-row kernel, packed from the counters for the windows of the other kernels
+        const size_t winRec = ctx->compact ? 16 : 32;
+        if (anyWindows) {
+            TLS_CUDA(s.hWindows.reserve(s.nWindows * winRec));
+            if (ctx->compact) TLS_CUDA(s.dWindows16.reserve(s.nWindows * 16));
+        }
+        const uint8_t *winSrc = ctx->compact ? s.dWindows16.as<uint8_t>() : s.dWindows.as<uint8_t>();
+        if (anyWindows && ctx->compact && nRow && nRangeWindows) {
+            TLS_CUDA(launchPackWindowRanges(s.dWindows.as<uint32_t>(), s.dWindows16.p, dRanges, dRangePrefix, nRanges, nRangeWindows, s.stream));
+            s.launches++;
+        }
         uint64_t winCopied = 0;
         if (nRow) {
             RowParams f{};
             f.seq = s.devSeq;
-            f.index8 = ctx->dIndex.as<uint8_t>();
+            f.indexRow = ctx->dIndex16.as<uint8_t>();
+            f.two16 = 65536u;
+            f.windows16 = ctx->compact ? s.dWindows16.as<uint4>() : nullptr;
+            f.zeroLanes = s.dZeroLanes.as<uint32_t>();
             f.flagTab = ctx->dFlags.as<uint8_t>() + cfg.cls[0].flagOffset;
             f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
             f.patLen = cfg.cls[0].len;
@@ -548,7 +600,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             f.status = redo + 1;
             f.cfg = cfg;
             const uint32_t gridWarps = static_cast<uint32_t>(ctx->smCount) * kRowWarps;
-            const int parts = (copyWindows && nRow >= 16u * gridWarps) ? ctx->rowParts : 1;
+            const int parts = (anyWindows && nRow >= 16u * gridWarps) ? ctx->rowParts : 1;
             auto firstWindowOfUnit = [&](uint32_t u) {          // rowRegions are sorted by unit0
                 size_t lo = 0, hi = s.rowRegions.size();
                 while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (s.rowRegions[mid].unit0 <= u) lo = mid; else hi = mid; }
@@ -567,39 +619,35 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
                     TLS_CUDA(cudaEventRecord(s.evPart[part], s.stream));
                     TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evPart[part], 0));
                     if (wEnd > winCopied)
-                        TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * 32, s.dWindows.as<uint8_t>() + winCopied * 32,
-                                                 (wEnd - winCopied) * 32, cudaMemcpyDeviceToHost, s.copyStream));
+                        TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * winRec, winSrc + winCopied * winRec,
+                                                 (wEnd - winCopied) * winRec, cudaMemcpyDeviceToHost, s.copyStream));
                     winCopied = std::max(winCopied, wEnd);
                 }
             }
         }
         TLS_CUDA(cudaEventRecord(s.evFast1, s.stream));
         TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
-        if (anyWindows && ctx->compact) {
-            TLS_CUDA(s.dWindows16.reserve(s.nWindows * 16));
+        if (anyWindows && ctx->compact && !nRow) {
             TLS_CUDA(launchPackWindows(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, s.stream));
             s.launches++;
         }
         // window and per-item counters are final now: copy (the rest of) them home on the side stream
         TLS_CUDA(cudaEventRecord(s.evScanDone, s.stream));
         TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evScanDone, 0));
-        if (copyWindows && winCopied < s.nWindows)
-            TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * 32, s.dWindows.as<uint8_t>() + winCopied * 32,
-                                     (s.nWindows - winCopied) * 32, cudaMemcpyDeviceToHost, s.copyStream));
-        if (anyWindows && ctx->compact) {
-            TLS_CUDA(s.hWindows.reserve(s.nWindows * 16));
-            TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows16.p, s.nWindows * 16, cudaMemcpyDeviceToHost, s.copyStream));
-        }
+        if (anyWindows && winCopied < s.nWindows)
+            TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * winRec, winSrc + winCopied * winRec,
+                                     (s.nWindows - winCopied) * winRec, cudaMemcpyDeviceToHost, s.copyStream));
         if (s.mode != TLS_MODE_READS && s.nItems) {
             TLS_CUDA(s.hItemCounts.reserve(static_cast<size_t>(s.nItems) * sizeof(DevItemCounts)));
             TLS_CUDA(cudaMemcpyAsync(s.hItemCounts.p, s.dItemCounts.p, static_cast<size_t>(s.nItems) * sizeof(DevItemCounts),
                                      cudaMemcpyDeviceToHost, s.copyStream));
         }
         TLS_CUDA(cudaEventRecord(s.evCopyDone, s.copyStream));
-        TLS_CUDA(launchTileScan(s.dTileTot.as<uint32_t>(), nTiles, s.dTileBase.as<unsigned long long>(),
+        TLS_CUDA(s.dSelScratch.reserve(tileScanScratchBytes(nTiles)));
+        TLS_CUDA(launchTileScan(s.dTileTot.as<uint32_t>(), nTiles, s.dTileBase.as<unsigned long long>(), s.dSelScratch.as<unsigned long long>(),
                                 reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>()), (nFast || nRow) ? redo : nullptr,
                                 s.hScanDev, s.stream));
-        s.launches++;
+        s.launches += 2;
     } else {
         // a batch whose items are all empty: no kernel runs, every per-item counter reads as zero
         TLS_CUDA(cudaMemsetAsync(s.dTileBase.p, 0, 24, s.stream));
@@ -689,6 +737,61 @@ static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
             if (s.itemLen[i] && b->seq[b->offsets[i + 1] - 1] == '\r') --s.itemLen[i];
     }
 
+    // ---- reads: one warp per read, nothing but the pass flags comes back (scan_reads.cu) -----------------
+    s.fusedReads = b->mode == TLS_MODE_READS && readConfigOk(ctx->dcfg) && !ctx->forceGeneral && !ctx->noReadKernel;
+    if (s.fusedReads) {
+        s.itemInfo.assign(n, DevItemInfo{});
+        s.nBases = 0;
+        for (uint32_t i = 0; i < n; ++i) { s.itemInfo[i].bufStart = b->offsets[i] - devBase; s.nBases += s.itemLen[i]; }
+        s.nWindows = 0; s.winOff.assign(n + 1, 0); s.nRowItems = 0; s.nRowUnits = 0; s.nTilesAll = 0;
+        const size_t bInfo = static_cast<size_t>(n) * sizeof(DevItemInfo), bLen = static_cast<size_t>(n) * 4;
+        TLS_CUDA(s.hMeta3.reserve(bInfo + bLen + 64));
+        uint8_t *h3 = s.hMeta3.as<uint8_t>();
+        if (n) { std::memcpy(h3, s.itemInfo.data(), bInfo); std::memcpy(h3 + bInfo, s.itemLen.data(), bLen); }
+        TLS_CUDA(s.dItemInfo.reserve(std::max<size_t>(bInfo, 16)));
+        TLS_CUDA(s.dItemLen.reserve(std::max<size_t>(bLen, 16)));
+        TLS_CUDA(s.dPass.reserve(std::max<size_t>(n, 1)));
+        TLS_CUDA(s.hPass.reserve(std::max<size_t>(n, 1)));
+        TLS_CUDA(cudaStreamWaitEvent(s.stream, s.evCopyDone, 0));
+        if (n) {
+            TLS_CUDA(cudaMemcpyAsync(s.dItemInfo.p, h3, bInfo, cudaMemcpyHostToDevice, s.stream));
+            TLS_CUDA(cudaMemcpyAsync(s.dItemLen.p, h3 + bInfo, bLen, cudaMemcpyHostToDevice, s.stream));
+        }
+        TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 64, s.stream));      // [32] work counter, [36] status, [40] match total (u64)
+        TLS_CUDA(cudaEventRecord(s.evAll0, s.stream));
+        s.launches = 0;
+        if (n && b->seq_on_device) {
+            TLS_CUDA(launchTrimCrItems(s.devSeq, s.dItemInfo.as<DevItemInfo>(), n, s.dItemLen.as<uint32_t>(), s.stream));
+            s.launches++;
+        }
+        TLS_CUDA(cudaEventRecord(s.evScan0, s.stream));
+        if (n) {
+            ReadParams rp{};
+            rp.seq = s.devSeq; rp.items = s.dItemInfo.as<DevItemInfo>(); rp.itemLen = s.dItemLen.as<uint32_t>(); rp.nItems = n;
+            rp.index8 = ctx->dIndex.as<uint8_t>();
+            rp.flagTab = ctx->dFlags.as<uint8_t>() + ctx->dcfg.cls[0].flagOffset;
+            rp.flagTabBytes = ((1u << (2 * ctx->dcfg.cls[0].len)) + 15u) & ~15u;
+            rp.patLen = ctx->dcfg.cls[0].len;
+            rp.pass = s.dPass.as<uint8_t>();
+            rp.cursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 32);
+            rp.status = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 36);
+            rp.matchTotal = reinterpret_cast<unsigned long long *>(s.dCounters.as<uint8_t>() + 40);
+            rp.cfg = ctx->dcfg; rp.cfg.mode = TLS_MODE_READS;
+            const int grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (n + (kReadThreads / 32) - 1) / (kReadThreads / 32)));
+            TLS_CUDA(launchReadScan(rp, grid, s.stream));
+            s.launches++;
+        }
+        TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
+        TLS_CUDA(cudaEventRecord(s.evFast1, s.stream));
+        TLS_CUDA(cudaEventRecord(s.evAll1, s.stream));
+        if (n) TLS_CUDA(cudaMemcpyAsync(s.hPass.p, s.dPass.p, n, cudaMemcpyDeviceToHost, s.stream));
+        TLS_CUDA(cudaMemcpyAsync(s.hCounters.p, s.dCounters.p, 64, cudaMemcpyDeviceToHost, s.stream));
+        tr.mark("reads_enqueue");
+        s.busy = true;
+        *ticket = si;
+        return TLS_OK;
+    }
+
     // ---- regions ------------------------------------------------------------------------------
     uint64_t nWin = 0;
     for (uint32_t i = 0; i < n; ++i) {
@@ -771,6 +874,24 @@ static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
         }
     }
 
+    // ---- per-item info for the kernels behind the scan; the windows the window-row kernel does not write ----
+    s.itemInfo.assign(n, DevItemInfo{});
+    for (uint32_t i = 0; i < n; ++i) {
+        s.itemInfo[i].bufStart = b->offsets[i] - devBase;
+        s.itemInfo[i].winBase = static_cast<uint32_t>(s.winOff[i]);
+    }
+    for (const DevRowRegion &rr : s.rowRegions) s.itemInfo[rr.item].rowItem = 1u;
+    s.nRowItems = static_cast<uint32_t>(s.rowRegions.size());
+    s.winRanges.clear(); s.winRangePrefix.assign(1, 0u);
+    if (b->mode == TLS_MODE_GENOME && s.nRowItems) {
+        for (uint32_t i = 0; i < n; ++i) {
+            if (s.itemInfo[i].rowItem || s.winOff[i + 1] == s.winOff[i]) continue;
+            const uint32_t x = static_cast<uint32_t>(s.winOff[i]), y = static_cast<uint32_t>(s.winOff[i + 1]);
+            if (!s.winRanges.empty() && s.winRanges.back().y == x) s.winRanges.back().y = y;
+            else s.winRanges.push_back(make_uint2(x, y));
+        }
+        for (const uint2 &r : s.winRanges) s.winRangePrefix.push_back(s.winRangePrefix.back() + (r.y - r.x));
+    }
     tr.mark("plan_tiles");
     // ---- which kernel takes the other tiles: the lean kernel wants tiles inside one region -------------
     s.fastTiles.clear(); s.generalTiles.clear();
@@ -821,6 +942,19 @@ static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
         if (bFast) TLS_CUDA(cudaMemcpyAsync(s.dFastTiles.p, h2 + bRow, bFast, cudaMemcpyHostToDevice, s.stream));
         if (bGen) TLS_CUDA(cudaMemcpyAsync(s.dGeneralTiles.p, h2 + bRow + bFast, bGen, cudaMemcpyHostToDevice, s.stream));
     }
+    {
+        const size_t bInfo = static_cast<size_t>(n) * sizeof(DevItemInfo), bRanges = s.winRanges.size() * sizeof(uint2),
+                     bPrefix = s.winRanges.empty() ? 0 : s.winRangePrefix.size() * 4;
+        TLS_CUDA(s.hMeta3.reserve(bInfo + bRanges + bPrefix + 64));
+        uint8_t *h3 = s.hMeta3.as<uint8_t>();
+        if (bInfo) std::memcpy(h3, s.itemInfo.data(), bInfo);
+        if (bRanges) std::memcpy(h3 + bInfo, s.winRanges.data(), bRanges);
+        if (bPrefix) std::memcpy(h3 + bInfo + bRanges, s.winRangePrefix.data(), bPrefix);
+        TLS_CUDA(s.dItemInfo.reserve(std::max<size_t>(bInfo, 16)));
+        TLS_CUDA(s.dWinRanges.reserve(std::max<size_t>(bRanges + bPrefix, 16)));
+        if (bInfo) TLS_CUDA(cudaMemcpyAsync(s.dItemInfo.p, h3, bInfo, cudaMemcpyHostToDevice, s.stream));
+        if (bRanges) TLS_CUDA(cudaMemcpyAsync(s.dWinRanges.p, h3 + bInfo, bRanges + bPrefix, cudaMemcpyHostToDevice, s.stream));
+    }
     const size_t bRegions = s.regions.size() * sizeof(DevRegion), bTiles = s.tiles.size() * sizeof(DevTile),
                  bLen = static_cast<size_t>(n) * 4, bAbs = static_cast<size_t>(n) * 8;
     TLS_CUDA(s.hMeta.reserve(bRegions + bTiles + bLen + bAbs + 64));
@@ -847,6 +981,7 @@ static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     TLS_CUDA(s.dItemCounts.reserve(std::max<size_t>(n, 1) * sizeof(DevItemCounts)));
     TLS_CUDA(s.dItemBegin.reserve((static_cast<size_t>(n) + 1) * 8));
     TLS_CUDA(s.dWindows.reserve(std::max<uint64_t>(nWin, 1) * 32));
+    TLS_CUDA(s.dZeroLanes.reserve(std::max<uint64_t>(nWin, 1) * 4));
     TLS_CUDA(s.dBoundaries.reserve(std::max<size_t>(n, 1) * 8));
     TLS_CUDA(s.dPass.reserve(std::max<size_t>(n, 1)));
 
@@ -870,6 +1005,23 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
     const uint32_t n = s.nItems;
     int rc;
     Trace tr("collect");
+    if (!s.collected && s.fusedReads) {
+        TLS_CUDA(cudaStreamSynchronize(s.stream));
+        const uint8_t *hc = s.hCounters.as<uint8_t>();
+        if (*reinterpret_cast<const unsigned int *>(hc + 36) != 0)
+            return fail(TLS_ERR_STATE, "read scan kernel could not lay out its shared memory; set TLS_NO_READ_KERNEL=1");
+        TLS_CUDA(cudaEventElapsedTime(&s.scanMs, s.evScan0, s.evScan1));
+        TLS_CUDA(cudaEventElapsedTime(&s.allMs, s.evAll0, s.evAll1));
+        s.fastMs = 0;
+        s.nMatches = *reinterpret_cast<const unsigned long long *>(hc + 40);
+        s.terminalOff.assign(n + 1, 0); s.itsOff.assign(n + 1, 0); s.canOff.assign(n + 1, 0); s.nonOff.assign(n + 1, 0);
+        s.terminal.clear(); s.its.clear();
+        s.nCan.assign(n, 0); s.nFwd.assign(n, 0); s.nRev.assign(n, 0);
+        s.pass.assign(n, 0);
+        if (n) std::memcpy(s.pass.data(), s.hPass.p, n);
+        s.nSelCan = s.nSelNon = 0;
+        s.collected = true;
+    }
     if (!s.collected) {
         // ---- wait for the scan; grow the overflow arena and rerun if it ran out --------------------
         for (;;) {
@@ -906,7 +1058,7 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
         uint32_t nBlocks = 0;
         s.blockCap = std::max<uint32_t>(s.blockCap, 4096);
         const uint32_t runCap = static_cast<uint32_t>(std::min<uint64_t>(s.nCanAll / 4 + 64, 0x7FFFFFFFull));
-        TLS_CUDA(s.dRunStarts.reserve(static_cast<size_t>(runCap) * 8));
+        TLS_CUDA(s.dRunStarts.reserve(static_cast<size_t>(runCap) * 16));       // run starts (list walk) | chain starts (window-row items)
         if (wantSel) {
             TLS_CUDA(s.dSelCan.reserve(std::max<uint64_t>(s.nCanAll, 1) * sizeof(tls_match)));
             TLS_CUDA(s.dSelNon.reserve(std::max<uint64_t>(s.nNctAll, 1) * sizeof(tls_match)));
@@ -914,11 +1066,38 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
         for (bool first = true;; first = false) {
             TLS_CUDA(s.dBlocks.reserve(static_cast<size_t>(s.blockCap) * sizeof(DevBlock)));
             uint8_t *cnt = s.dCounters.as<uint8_t>();
-            TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 8, s.stream));            // [16] block count, [20] ITS run count
+            TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 12, s.stream));           // [16] block count, [20] ITS run count, [24] ITS chain count
             if (first && s.nTilesAll) { TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream)); s.launches++; }
             if (reads && n) TLS_CUDA(cudaMemsetAsync(s.dPass.p, 0, n, s.stream));
             if (n) {
-                if (first) { TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), n, s.dItemBegin.as<unsigned long long>(), s.stream)); s.launches++; }
+                if (first) { TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), s.nRowItems ? s.dItemInfo.as<DevItemInfo>() : nullptr, n, s.dItemBegin.as<unsigned long long>(), s.stream)); s.launches++; }
+                if (first && wantSel) {
+                    // the -m lists only need the ordered list: final records and their copy home run on their own stream
+                    // beside the block kernels
+                    TLS_CUDA(cudaEventRecord(s.evGather, s.stream));
+                    TLS_CUDA(cudaStreamWaitEvent(s.selStream, s.evGather, 0));
+                    const size_t selRec = ctx->compact ? sizeof(tls_match8) : sizeof(tls_match);
+                    if (ctx->compact) {
+                        TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dSelCan.p, s.selStream));
+                        TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll, s.dSelNon.p, s.selStream));
+                    } else {
+                        TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll,
+                                                      s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
+                                                      s.dSelCan.p, s.selStream));
+                        TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll,
+                                                      s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
+                                                      s.dSelNon.p, s.selStream));
+                    }
+                    s.launches += (s.nCanAll ? 1 : 0) + (s.nNctAll ? 1 : 0);
+                    if (s.nCanAll) {
+                        TLS_CUDA(s.hSelCan.reserve(s.nCanAll * selRec));
+                        TLS_CUDA(cudaMemcpyAsync(s.hSelCan.p, s.dSelCan.p, s.nCanAll * selRec, cudaMemcpyDeviceToHost, s.selStream));
+                    }
+                    if (s.nNctAll) {
+                        TLS_CUDA(s.hSelNon.reserve(s.nNctAll * selRec));
+                        TLS_CUDA(cudaMemcpyAsync(s.hSelNon.p, s.dSelNon.p, s.nNctAll * selRec, cudaMemcpyDeviceToHost, s.selStream));
+                    }
+                }
                 if (first && genome && ctx->dcfg.overlapWindows && s.nWindows) {
                     // step < window: the window table comes from the ordered list (block_kernels.cu), then goes home
                     TLS_CUDA(launchOverlapWindows(s.devSeq, s.dRegions.as<DevRegion>(), static_cast<uint32_t>(s.regions.size()),
@@ -942,6 +1121,13 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                 bp.itemCounts = s.dItemCounts.as<DevItemCounts>();
                 bp.itemLen = s.dItemLen.as<uint32_t>();
                 bp.nItems = n;
+                if (s.nRowItems) {                          // window-row items: sparse record lists, walks may go back to the sequence
+                    bp.items = s.dItemInfo.as<DevItemInfo>();
+                    bp.seq = s.devSeq;
+                    bp.flagTab = ctx->dFlags.as<uint8_t>() + ctx->dcfg.cls[0].flagOffset;
+                    bp.patLen = ctx->dcfg.cls[0].len;
+                    bp.zeroLanes = s.dZeroLanes.as<uint32_t>();
+                }
                 bp.blocks = s.dBlocks.as<DevBlock>();
                 bp.blockCap = reads ? 0 : s.blockCap;       // read mode only needs the pass flag
                 bp.blockCount = reinterpret_cast<unsigned int *>(cnt + 16);
@@ -953,23 +1139,18 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                 TLS_CUDA(launchTerminal(bp, s.stream));
                 s.launches++;
                 if (genome && s.nMatches >= 2 && s.nCanAll >= 4) {
-                    TLS_CUDA(launchIts(bp, s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dRunStarts.as<unsigned long long>(),
-                                       reinterpret_cast<unsigned int *>(cnt + 20), runCap, s.stream));
-                    s.launches += 2;
-                }
-                if (first && wantSel) {
-                    if (ctx->compact) {
-                        TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dSelCan.p, s.stream));
-                        TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll, s.dSelNon.p, s.stream));
-                    } else {
-                        TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll,
-                                                      s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
-                                                      s.dSelCan.p, s.stream));
-                        TLS_CUDA(launchSelectFinalize(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll,
-                                                      s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
-                                                      s.dSelNon.p, s.stream));
+                    if (s.nRowItems < n) {                  // items with complete record lists: runs are read from the list
+                        TLS_CUDA(launchIts(bp, s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dRunStarts.as<unsigned long long>(),
+                                           reinterpret_cast<unsigned int *>(cnt + 20), runCap, s.stream));
+                        s.launches += 2;
                     }
-                    s.launches += (s.nCanAll ? 1 : 0) + (s.nNctAll ? 1 : 0);
+                    if (s.nRowItems) {                      // window-row items: connectivity from the zero-lane masks, runs from the sequence
+                        TLS_CUDA(s.dConn.reserve(s.nCanAll + 16));
+                        TLS_CUDA(launchItsRows(bp, s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dConn.as<uint8_t>(),
+                                               s.dRunStarts.as<unsigned long long>() + runCap,
+                                               reinterpret_cast<unsigned int *>(cnt + 24), runCap, s.stream));
+                        s.launches += 3;
+                    }
                 }
             }
             TLS_CUDA(cudaEventRecord(s.evAll1, s.stream));
@@ -994,16 +1175,8 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
             TLS_CUDA(cudaMemcpyAsync(s.hPass.p, s.dPass.p, n, cudaMemcpyDeviceToHost, s.stream));
         }
         s.nSelCan = selTotals[0]; s.nSelNon = selTotals[1];
-        const size_t selRec = ctx->compact ? sizeof(tls_match8) : sizeof(tls_match);
-        if (selTotals[0]) {
-            TLS_CUDA(s.hSelCan.reserve(selTotals[0] * selRec));
-            TLS_CUDA(cudaMemcpyAsync(s.hSelCan.p, s.dSelCan.p, selTotals[0] * selRec, cudaMemcpyDeviceToHost, s.stream));
-        }
-        if (selTotals[1]) {
-            TLS_CUDA(s.hSelNon.reserve(selTotals[1] * selRec));
-            TLS_CUDA(cudaMemcpyAsync(s.hSelNon.p, s.dSelNon.p, selTotals[1] * selRec, cudaMemcpyDeviceToHost, s.stream));
-        }
         TLS_CUDA(cudaStreamSynchronize(s.stream));
+        TLS_CUDA(cudaStreamSynchronize(s.selStream));
         TLS_CUDA(cudaStreamSynchronize(s.copyStream));
         TLS_CUDA(cudaEventElapsedTime(&s.allMs, s.evAll0, s.evAll1));
         tr.mark("d2h");

@@ -54,7 +54,7 @@ __device__ __forceinline__ unsigned long long blockExclusive1024(unsigned long l
 // ------------------------------------------------------------------------------------------------
 // Exclusive scan of itemCounts[i].all -> itemBegin[0..n]   (single block, n up to millions)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *counts, uint32_t n,
+__global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *counts, const DevItemInfo *items, uint32_t n,
                                                           unsigned long long *itemBegin) {
     __shared__ unsigned long long warpSums[32];
     __shared__ unsigned long long carry;
@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *c
     __syncthreads();
     for (uint32_t base = 0; base < n; base += 1024) {
         const uint32_t i = base + threadIdx.x;
-        const unsigned long long v = i < n ? counts[i].all : 0;
+        // records of the item in the ordered list: every match, or what the window-row kernel emitted (sparse units: canonical only)
+        const unsigned long long v = i < n ? ((items && items[i].rowItem) ? counts[i].records : counts[i].all) : 0;
         const unsigned long long excl = blockExclusive1024(v, warpSums, &carry);
         if (i < n) itemBegin[i] = excl;
     }
@@ -71,146 +72,149 @@ __global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *c
 
 // ------------------------------------------------------------------------------------------------
 // Per-tile totals (written by the scan kernels with atomics) -> exclusive prefixes.
-// tileTot / tileBase hold three arrays back to back: all matches, canonical, terminal non-canonical.
-// ------------------------------------------------------------------------------------------------
+// tileTot / tileBase hold three arrays back to back: match records, canonical, terminal non-canonical.
+// Two launches over blocks of kScanChunk tiles: block sums, then every block adds up the sums of the blocks
+// before it and scans its own tiles.
 // The totals, the overflow cursor and the redo counters are also published to `hostOut` (mapped
 // pinned host memory: [0] ovCursor, [1..3] totals, [4] redo count | status << 32), so that the host
 // needs no copy-engine transfer (which would queue behind the window counters going home).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kScanChunk = 4096;                               // tiles per block: 1024 threads x 4
+
+__global__ void __launch_bounds__(1024) tileBlockSumsKernel(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *blockSums) {
+    __shared__ unsigned long long warpSums[32];
+    const uint32_t k = blockIdx.y, b = blockIdx.x, nBlk = gridDim.x;
+    const uint32_t *in = tileTot + static_cast<size_t>(k) * nTiles;
+    const uint32_t i0 = b * kScanChunk + threadIdx.x * 4;
+    unsigned long long v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (i0 + j < nTiles) v += in[i0 + j];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = warpSums[threadIdx.x];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        if (threadIdx.x == 0) blockSums[static_cast<size_t>(k) * nBlk + b] = v;
+    }
+}
+
 __global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase,
-                                                       const unsigned int *ovCursor, const unsigned int *redo,
-                                                       unsigned long long *hostOut) {
-    // one block per array; a thread takes 16 consecutive tiles per round
+                                                       const unsigned long long *blockSums, const unsigned int *ovCursor,
+                                                       const unsigned int *redo, unsigned long long *hostOut) {
     __shared__ unsigned long long warpSums[32];
     __shared__ unsigned long long carry;
-    const uint32_t k = blockIdx.x;
+    const uint32_t k = blockIdx.y, b = blockIdx.x, nBlk = gridDim.x;
+    // offset of this block: the sums of the blocks before it (and, in the last block, the grand total)
+    unsigned long long before = 0, all = 0;
+    for (uint32_t i = threadIdx.x; i < nBlk; i += 1024) {
+        const unsigned long long v = blockSums[static_cast<size_t>(k) * nBlk + i];
+        all += v;
+        if (i < b) before += v;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) { before += __shfl_xor_sync(0xFFFFFFFFu, before, d); all += __shfl_xor_sync(0xFFFFFFFFu, all, d); }
+    __shared__ unsigned long long redBefore[32], redAll[32];
+    if ((threadIdx.x & 31) == 0) { redBefore[threadIdx.x >> 5] = before; redAll[threadIdx.x >> 5] = all; }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        carry = 0;
-        if (k == 0) {
-            hostOut[0] = *reinterpret_cast<const unsigned long long *>(ovCursor);
-            hostOut[4] = redo ? (static_cast<unsigned long long>(redo[0]) | (static_cast<unsigned long long>(redo[1]) << 32)) : 0ull;
+        unsigned long long sb = 0, sa = 0;
+        for (int i = 0; i < 32; ++i) { sb += redBefore[i]; sa += redAll[i]; }
+        carry = sb;
+        if (b == nBlk - 1) {
+            tileBase[static_cast<size_t>(k) * (nTiles + 1) + nTiles] = sa;
+            hostOut[1 + k] = sa;
+            if (k == 0) {
+                hostOut[0] = *reinterpret_cast<const unsigned long long *>(ovCursor);
+                hostOut[4] = redo ? (static_cast<unsigned long long>(redo[0]) | (static_cast<unsigned long long>(redo[1]) << 32)) : 0ull;
+            }
+            __threadfence_system();
         }
     }
     __syncthreads();
     const uint32_t *in = tileTot + static_cast<size_t>(k) * nTiles;
     unsigned long long *out = tileBase + static_cast<size_t>(k) * (nTiles + 1);
-    constexpr int kPer = 16;                                      // consecutive tiles per thread and round
-    for (uint32_t base = 0; base < nTiles; base += 1024 * kPer) {
-        const uint32_t i = base + threadIdx.x * kPer;
-        uint32_t v[kPer];
-        unsigned long long sum = 0;
+    const uint32_t i0 = b * kScanChunk + threadIdx.x * 4;
+    uint32_t v[4];
+    unsigned long long sum = 0;
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) { v[j] = i + j < nTiles ? in[i + j] : 0u; sum += v[j]; }
-        unsigned long long excl = blockExclusive1024(sum, warpSums, &carry);
+    for (int j = 0; j < 4; ++j) { v[j] = i0 + j < nTiles ? in[i0 + j] : 0u; sum += v[j]; }
+    unsigned long long excl = blockExclusive1024(sum, warpSums, &carry);
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            if (i + j < nTiles) out[i + j] = excl;
-            excl += v[j];
-        }
-    }
-    if (threadIdx.x == 0) {
-        out[nTiles] = carry;
-        hostOut[1 + k] = carry;
-        __threadfence_system();
+    for (int j = 0; j < 4; ++j) {
+        if (i0 + j < nTiles) out[i0 + j] = excl;
+        excl += v[j];
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Slot arena -> ordered match list.  One block per tile, one warp per row slot at a time; fully
-// coalesced 8-byte copies (all window / item accounting was done by the scan kernels).
+// Slot arena -> ordered match list.  One WARP per tile (32 row slots).  A tile of sparse units holds a handful of
+// canonical records: lane r copies row r's records itself.  A tile with many records (dense units, other scan kernels):
+// the warp copies slot after slot with coalesced 8-byte accesses.  (All window / item accounting was done by the scan kernels.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
 
 __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParams g) {
-    const uint32_t tile = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ uint32_t sOff[3][kTileRows + 1];
-    if (warp < 3) {
-        // exclusive prefix over the 32 row slots of this tile (warp k handles array k)
-        const uint4 meta = g.slotMeta[static_cast<size_t>(tile) * kTileRows + lane];
-        const uint32_t v = warp == 0 ? meta.x : warp == 1 ? meta.z : meta.w;
-        uint32_t incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += u;
-        }
-        sOff[warp][lane] = incl - v;
-        if (lane == 31) sOff[warp][kTileRows] = incl;
-    }
-    __syncthreads();
-    if (sOff[0][kTileRows] == 0) return;
+    const uint32_t tile = blockIdx.x * (kGatherThreads / 32) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31u;
+    if (tile >= g.nTiles) return;
     const unsigned long long base = g.tileBase[tile];
+    const uint32_t total = static_cast<uint32_t>(g.tileBase[tile + 1] - base);
+    if (total == 0) return;
     const unsigned long long baseCan = g.tileBase[static_cast<size_t>(g.nTiles) + 1 + tile];
     const unsigned long long baseNct = g.tileBase[2 * (static_cast<size_t>(g.nTiles) + 1) + tile];
-    const uint32_t laneLt = (1u << lane) - 1u;
-
-    // A warp owns the row slots warp, warp + 8, warp + 16, warp + 24.  Common case (each of them holds at most 64
-    // records, all inside the slot): the eight loads are issued back to back before anything is stored, so that
-    // eight requests per warp are in flight instead of one — the copy is latency-bound otherwise.
-    constexpr int kPerWarp = kTileRows / (kGatherThreads / 32);
-    uint32_t cntR[kPerWarp];
-    bool simple = true;
+    const size_t slot0 = static_cast<size_t>(tile) * kTileRows;
+    const uint4 meta = g.slotMeta[slot0 + lane];                    // records, overflow base, canonical, terminal non-canonical
+    // exclusive prefixes over the 32 row slots (a tile holds at most 32 x ovChunk records: 16 bits per field would not do)
+    uint32_t inclAll = meta.x, inclCan = meta.z, inclNct = meta.w;
 #pragma unroll
-    for (int j = 0; j < kPerWarp; ++j) {
-        const int s = warp + j * (kGatherThreads / 32);
-        cntR[j] = sOff[0][s + 1] - sOff[0][s];
-        simple = simple && cntR[j] <= 64u && cntR[j] <= g.slotCap;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, inclAll, d), c = __shfl_up_sync(0xFFFFFFFFu, inclCan, d),
+                       n = __shfl_up_sync(0xFFFFFFFFu, inclNct, d);
+        if (lane >= static_cast<uint32_t>(d)) { inclAll += a; inclCan += c; inclNct += n; }
     }
-    if (simple) {
-        uint2 rec[kPerWarp][2];
-#pragma unroll
-        for (int j = 0; j < kPerWarp; ++j) {
-            const int s = warp + j * (kGatherThreads / 32);
-            const uint2 *src = reinterpret_cast<const uint2 *>(g.slots) + (static_cast<size_t>(tile) * kTileRows + s) * g.slotCap;
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                rec[j][h] = static_cast<uint32_t>(lane + 32 * h) < cntR[j] ? __ldg(src + lane + 32 * h) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int j = 0; j < kPerWarp; ++j) {
-            const int s = warp + j * (kGatherThreads / 32);
-            const bool anySel = sOff[1][s + 1] != sOff[1][s] || sOff[2][s + 1] != sOff[2][s];     // warp-uniform
-            unsigned long long oc = baseCan + sOff[1][s], on = baseNct + sOff[2][s];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (static_cast<uint32_t>(32 * h) >= cntR[j]) break;                              // warp-uniform
-                const uint32_t k = static_cast<uint32_t>(lane + 32 * h);
-                const bool have = k < cntR[j];
-                const unsigned long long o = base + sOff[0][s] + k;
-                if (have && o < g.matchCap) reinterpret_cast<uint2 *>(g.matches)[o] = make_uint2(rec[j][h].x, rec[j][h].y & 0x00FFFFFFu);
-                if (!anySel) continue;
-                const uint32_t flags = (rec[j][h].y >> 16) & 0xFFu;
-                const bool isC = have && (flags & kMatchCan);
-                const bool isN = have && (flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
-                const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
-                if (isC && oc + __popc(bc & laneLt) < g.selCap) g.canIdx[oc + __popc(bc & laneLt)] = static_cast<uint32_t>(o);
-                if (isN && on + __popc(bn & laneLt) < g.selCap) g.nctIdx[on + __popc(bn & laneLt)] = static_cast<uint32_t>(o);
-                oc += __popc(bc);
-                on += __popc(bn);
-            }
+    const uint32_t exAll = inclAll - meta.x, exCan = inclCan - meta.z, exNct = inclNct - meta.w;
+    const uint2 *slots = reinterpret_cast<const uint2 *>(g.slots);
+    const uint2 *ovArena = reinterpret_cast<const uint2 *>(g.ovArena);
+    uint2 *out = reinterpret_cast<uint2 *>(g.matches);
+
+    if (total <= 128u) {
+        // lane r: row r's records, one after the other
+        const uint2 *src = slots + (slot0 + lane) * g.slotCap;
+        unsigned long long o = base + exAll, oc = baseCan + exCan, on = baseNct + exNct;
+        for (uint32_t k = 0; k < meta.x; ++k, ++o) {
+            uint2 rec;
+            if (k < g.slotCap) rec = __ldg(src + k);
+            else if (static_cast<unsigned long long>(meta.y) + (k - g.slotCap) < g.ovCap) rec = ovArena[meta.y + (k - g.slotCap)];
+            else continue;                                          // overflow arena exhausted: the host reruns the scan
+            if (o < g.matchCap) out[o] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
+            const uint32_t flags = (rec.y >> 16) & 0xFFu;
+            if (flags & kMatchCan) { if (oc < g.selCap) g.canIdx[oc] = static_cast<uint32_t>(o); ++oc; }
+            else if (flags & kMatchTerm) { if (on < g.selCap) g.nctIdx[on] = static_cast<uint32_t>(o); ++on; }
         }
         return;
     }
-
-    for (int s = warp; s < kTileRows; s += kGatherThreads / 32) {
-        const uint32_t cnt = sOff[0][s + 1] - sOff[0][s];
+    const uint32_t laneLt = (1u << lane) - 1u;
+    for (int s = 0; s < kTileRows; ++s) {
+        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, meta.x, s);
         if (cnt == 0) continue;
-        const size_t slotIdx = static_cast<size_t>(tile) * kTileRows + s;
-        const uint2 *src = reinterpret_cast<const uint2 *>(g.slots) + slotIdx * g.slotCap;
-        const unsigned long long ov = g.slotMeta[slotIdx].y;
-        const unsigned long long o = base + sOff[0][s];
-        unsigned long long oc = baseCan + sOff[1][s], on = baseNct + sOff[2][s];
-        const bool anySel = sOff[1][s + 1] != sOff[1][s] || sOff[2][s + 1] != sOff[2][s];     // warp-uniform
+        const unsigned long long ov = __shfl_sync(0xFFFFFFFFu, meta.y, s);
+        const bool anySel = __shfl_sync(0xFFFFFFFFu, meta.z | meta.w, s) != 0;
+        const unsigned long long o = base + __shfl_sync(0xFFFFFFFFu, exAll, s);
+        unsigned long long oc = baseCan + __shfl_sync(0xFFFFFFFFu, exCan, s), on = baseNct + __shfl_sync(0xFFFFFFFFu, exNct, s);
+        const uint2 *src = slots + (slot0 + s) * g.slotCap;
         for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
             const uint32_t k = k0 + lane;
             uint2 rec = make_uint2(0u, 0u);
             bool have = k < cnt;
             if (have) {
-                if (k < g.slotCap) rec = src[k];
-                else if (ov + (k - g.slotCap) < g.ovCap) rec = reinterpret_cast<const uint2 *>(g.ovArena)[ov + (k - g.slotCap)];
+                if (k < g.slotCap) rec = __ldg(src + k);
+                else if (ov + (k - g.slotCap) < g.ovCap) rec = ovArena[ov + (k - g.slotCap)];
                 else have = false;                              // overflow arena exhausted: the host reruns the scan
             }
-            if (have && o + k < g.matchCap) reinterpret_cast<uint2 *>(g.matches)[o + k] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
+            if (have && o + k < g.matchCap) out[o + k] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
             if (!anySel) continue;
             // index lists of the -m selections, in genome order
             const uint32_t flags = (rec.y >> 16) & 0xFFu;
@@ -225,14 +229,17 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
     }
 }
 
-cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, const unsigned int *ovCursor,
-                           const unsigned int *redo, unsigned long long *hostOut, cudaStream_t s) {
-    tileScanKernel<<<3, 1024, 0, s>>>(tileTot, nTiles, tileBase, ovCursor, redo, hostOut);
+cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, unsigned long long *blockSums,
+                           const unsigned int *ovCursor, const unsigned int *redo, unsigned long long *hostOut, cudaStream_t s) {
+    const uint32_t nBlk = std::max<uint32_t>(1u, (nTiles + kScanChunk - 1) / kScanChunk);
+    tileBlockSumsKernel<<<dim3(nBlk, 3), 1024, 0, s>>>(tileTot, nTiles, blockSums);
+    tileScanKernel<<<dim3(nBlk, 3), 1024, 0, s>>>(tileTot, nTiles, tileBase, blockSums, ovCursor, redo, hostOut);
     return cudaGetLastError();
 }
+size_t tileScanScratchBytes(uint32_t nTiles) { return static_cast<size_t>(std::max<uint32_t>(1u, (nTiles + kScanChunk - 1) / kScanChunk)) * 3 * 8; }
 cudaError_t launchGather(const GatherParams &g, cudaStream_t s) {
     if (g.nTiles == 0) return cudaSuccess;
-    gatherKernel<<<g.nTiles, kGatherThreads, 0, s>>>(g);
+    gatherKernel<<<(g.nTiles + kGatherThreads / 32 - 1) / (kGatherThreads / 32), kGatherThreads, 0, s>>>(g);
     return cudaGetLastError();
 }
 
@@ -240,6 +247,29 @@ cudaError_t launchGather(const GatherParams &g, cudaStream_t s) {
 // Terminal blocks
 // ------------------------------------------------------------------------------------------------
 namespace {
+
+// The match that starts at one position of a window-row item, straight from the sequence: what the scan kernel found there
+// (same table, same rules: a match never crosses its window's end, src/teloscope.cpp:439; a byte outside ACGTacgt stops
+// the Trie walk, include/teloscope.h:27-35).  The walks below use it where the record list is sparse.
+struct Rescan {
+    const uint8_t *seq;        // the item's first base
+    const uint8_t *flagTab;    // 4^L bytes: bit0 hit, bit1 forward, bit2 canonical
+    uint32_t n, W, L;
+    const DevConfig *cfg;
+    __device__ uint32_t at(uint32_t pos) const {
+        if (pos >= n) return 0u;
+        const uint32_t wStart = divWindow(*cfg, pos) * W;
+        const uint32_t wLen = min(W, n - wStart);
+        if (pos - wStart + L > wLen) return 0u;
+        uint32_t key = 0;
+        for (uint32_t j = 0; j < L; ++j) {
+            const uint32_t ch = __ldg(seq + pos + j), up = ch & 0xDFu;
+            if (up != 'A' && up != 'C' && up != 'G' && up != 'T') return 0u;
+            key |= ((ch >> 1) & 3u) << (2 * j);
+        }
+        return __ldg(flagTab + key);
+    }
+};
 
 struct Run {
     uint32_t start, end, prev, n, nFwd, nCan, cov, fwdCov, canCov;
@@ -327,16 +357,24 @@ __global__ void __launch_bounds__(128) terminalKernel(const BlockParams p) {
         Run run{};
         bool inRun = false, done = false;
         const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
+        // A window-row item lists every match only outside [spLo, spHi) (sparseRange): the walk reads the list up to that
+        // edge and, if a run is still open there, goes on over the sequence itself (below).
+        uint32_t spLo = 0xFFFFFFFFu, spHi = 0xFFFFFFFFu;
+        if (p.items && p.items[item].rowItem) sparseRange(n, c.terminalLimit, c.windowSize, spLo, spHi);
+        const bool hasSparse = spLo != 0xFFFFFFFFu;
+        bool atEdge = false;
         // lane l holds the l-th next record in walk order; the next 32 are requested before the current 32 are walked
         auto fetch = [&](long long off, uint2 &rec, bool &valid) {
             const long long i = fromStart ? begin + off + lane : end - 1 - off - lane;
             valid = off < end - begin && (fromStart ? i < end : i >= begin);
             rec = valid ? __ldg(recs + i) : make_uint2(0u, 0u);
+            if (valid && hasSparse && (fromStart ? rec.x >= spLo : rec.x < spHi)) { valid = false; atEdge = true; }
         };
         uint2 rec, recNext;
         bool valid, validNext;
         fetch(0, rec, valid);
         for (long long off = 0; off < end - begin && !done; off += 32, rec = recNext, valid = validNext) {
+            if (__any_sync(0xFFFFFFFFu, atEdge) && !__any_sync(0xFFFFFFFFu, valid)) break;     // only records beyond the edge are left
             fetch(off + 32, recNext, validNext);
             uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && ((rec.y >> 16) & kMatchFwd) == want);
             if (inRun && mask) {
@@ -385,6 +423,30 @@ __global__ void __launch_bounds__(128) terminalKernel(const BlockParams p) {
                 }
             }
         }
+        if (hasSparse && inRun && !done) {
+            // The open run may go on inside the sparse part: same-strand matches from the sequence, 32 positions per step,
+            // until the run breaks.  Every position there is outside the terminal zone, so the first match that does not
+            // continue the run would start a run out of zone, which ends the walk (src/teloscope.cpp:98-102,117-121).
+            Rescan rs{p.seq + p.items[item].bufStart, p.flagTab, n, c.windowSize, p.patLen, &c};
+            for (long long base = fromStart ? static_cast<long long>(spLo) : static_cast<long long>(spHi) - 1;
+                 !done && (fromStart ? base < static_cast<long long>(n) : base >= 0); base += fromStart ? 32 : -32) {
+                const uint32_t reach = fromStart ? static_cast<uint32_t>(base) - run.prev : run.prev - static_cast<uint32_t>(base);
+                if (reach > c.maxMatchDist) break;                      // nothing in reach any more: the run is over
+                const long long q = fromStart ? base + lane : base - lane;
+                const uint32_t f = q >= 0 ? rs.at(static_cast<uint32_t>(q)) : 0u;
+                uint32_t mask = __ballot_sync(0xFFFFFFFFu, (f & 1u) && ((f >> 1) & 1u) == (want ? 1u : 0u));
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t pos = static_cast<uint32_t>(fromStart ? base + b : base - b);
+                    const uint32_t fl = want | ((__shfl_sync(0xFFFFFFFFu, f, b) & 4u) ? static_cast<uint32_t>(kMatchCan) : 0u);
+                    const uint32_t gap = fromStart ? pos - run.prev : run.prev - pos;
+                    if (gap > c.maxMatchDist) { done = true; break; }
+                    if (fromStart) run.end = pos + p.patLen; else run.start = pos;
+                    run.absorb(pos, p.patLen, fl);
+                }
+            }
+        }
         if (inRun) feedSub(run);
         if (haveCur) finishCur();
     }
@@ -412,6 +474,7 @@ __global__ void __launch_bounds__(256) itsSeedKernel(const BlockParams p, const 
         if (p.itemBegin[mid] <= idx) lo = mid + 1; else hi = mid;
     }
     const uint32_t item = lo - 1;
+    if (p.items && p.items[item].rowItem) return;                 // window-row items: itsConnKernel / itsWalkKernel below
     const unsigned long long itemBegin = p.itemBegin[item], itemEnd = p.itemBegin[item + 1];
     const uint32_t fwdB = p.fwdBoundary[item], revB = p.revBoundary[item];
     if (!(fwdB < revB) || itemEnd - itemBegin < 2) return;        // src/teloscope.cpp:653
@@ -504,6 +567,147 @@ __global__ void __launch_bounds__(128) itsRunKernel(const BlockParams p, const u
 }
 
 // ------------------------------------------------------------------------------------------------
+// Interstitial blocks of window-row items.  Their record list holds every match only outside the sparse
+// part, so runs are not read from it.  A block needs 4 canonical matches in one run (src/teloscope.cpp:186),
+// i.e. 4 CONSECUTIVE canonical matches that are pairwise connected by matches at most maxMatchDist apart:
+//   itsConnKernel   per canonical match j: can j and j + 1 belong to one run?  "No" is proven from the scan
+//                   kernel's per-window masks of 32-position lanes without a match start: ceil(maxMatchDist / 32)
+//                   such lanes in a row between the two break every chain.  On random sequence that settles
+//                   all but a handful of pairs without touching the sequence.
+//   itsChainKernel  starts of maximal chains of >= 4 "maybe connected" canonical matches
+//   itsWalkKernel   one warp per chain: the runs around its canonical matches, rebuilt exactly from the sequence
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) itsConnKernel(const BlockParams p, const uint32_t *canIdx, unsigned long long nCan, uint8_t *conn) {
+    const unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= nCan) return;
+    const DevConfig &c = p.cfg;
+    uint8_t out = 0;
+    do {
+        if (j + 1 >= nCan) break;
+        const unsigned long long idx = canIdx[j], idx2 = canIdx[j + 1];
+        uint32_t lo = 0, hi = p.nItems;                               // item: last i with itemBegin[i] <= idx
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.itemBegin[mid] <= idx) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t item = lo - 1;
+        if (!p.items[item].rowItem || idx2 >= p.itemBegin[item + 1]) break;
+        const uint32_t fwdB = p.fwdBoundary[item], revB = p.revBoundary[item];
+        if (!(fwdB < revB) || p.itemCounts[item].all < 2) break;      // src/teloscope.cpp:653
+        const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
+        const uint32_t a = recs[idx].x, b = recs[idx2].x;
+        if (a < fwdB || b >= revB) break;                             // runs live in [fwdBoundary, revBoundary), :188-191,235
+        out = 1;
+        const uint32_t m = c.maxMatchDist == 0 ? 1u : (c.maxMatchDist + 31u) / 32u;      // lanes without a start that break a chain
+        if (m > 31u) break;
+        const uint32_t W = c.windowSize, n = p.itemLen[item];
+        const uint32_t rowA = divWindow(c, a), rowB = divWindow(c, b);
+        for (uint32_t row = rowA; row <= rowB && row < rowA + 3u; ++row) {
+            const uint32_t rowStart = row * W, nFull = min(W, n - rowStart) / 32u;   // lanes that lie entirely inside the window
+            if (nFull < m) continue;
+            const uint32_t Z = p.zeroLanes[p.items[item].winBase + row];
+            uint32_t R = Z;
+            for (uint32_t i = 1; i < m; ++i) R &= Z >> i;             // bit l: lanes l .. l + m - 1 hold no start
+            uint32_t lMin = 0, lEnd = nFull - m + 1u;                 // admissible first lanes [lMin, lEnd)
+            if (row == rowA) lMin = (a - rowStart) / 32u + 1u;        // the stretch starts after a
+            if (row == rowB) lEnd = min(lEnd, (b - rowStart) / 32u >= m ? (b - rowStart) / 32u - m + 1u : 0u);   // and ends at or before b
+            if (lMin >= lEnd) continue;
+            const uint32_t range = (lEnd >= 32u ? 0xFFFFFFFFu : (1u << lEnd) - 1u) & ~((1u << lMin) - 1u);
+            if (R & range) { out = 0; break; }
+        }
+    } while (false);
+    conn[j] = out;
+}
+
+__global__ void __launch_bounds__(256) itsChainKernel(const uint8_t *conn, unsigned long long nCan, unsigned long long *chainStarts,
+                                                      unsigned int *chainCount, uint32_t chainCap) {
+    const unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j + 3 >= nCan) return;
+    if (!(conn[j] && conn[j + 1] && conn[j + 2]) || (j > 0 && conn[j - 1])) return;
+    const unsigned int slot = atomicAdd(chainCount, 1u);
+    if (slot < chainCap) chainStarts[slot] = j;
+}
+
+__global__ void __launch_bounds__(128) itsWalkKernel(const BlockParams p, const uint32_t *canIdx, const uint8_t *conn,
+                                                     const unsigned long long *chainStarts, const unsigned int *chainCount, uint32_t chainCap) {
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nChains = min(*chainCount, chainCap);
+    if (gw >= nChains) return;
+    const DevConfig &c = p.cfg;
+    unsigned long long j = chainStarts[gw];
+    unsigned long long jEnd = j;
+    while (conn[jEnd]) ++jEnd;                                        // last canonical match of the chain (conn of the batch's last is 0)
+    const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
+    const unsigned long long idx0 = canIdx[j];
+    uint32_t lo = 0, hi = p.nItems;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.itemBegin[mid] <= idx0) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t item = lo - 1;
+    const uint32_t n = p.itemLen[item], L = p.patLen, K = c.maxMatchDist;
+    const uint32_t fwdB = p.fwdBoundary[item], revB = p.revBoundary[item];
+    const Rescan rs{p.seq + p.items[item].bufStart, p.flagTab, n, c.windowSize, L, &c};
+    while (j <= jEnd) {
+        const uint32_t seed = recs[canIdx[j]].x;
+        // ---- the run's first match: leftwards from the seed while the next match is within reach ----
+        uint32_t start = seed;
+        bool open = true;
+        for (long long top = static_cast<long long>(seed) - 1; open && top >= static_cast<long long>(fwdB); top -= 32) {
+            if (start - static_cast<uint32_t>(top) > K) break;
+            const long long q = top - lane;
+            const uint32_t f = q >= static_cast<long long>(fwdB) ? rs.at(static_cast<uint32_t>(q)) : 0u;
+            uint32_t mask = __ballot_sync(0xFFFFFFFFu, (f & 1u) != 0u);
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const uint32_t pos = static_cast<uint32_t>(top - b);
+                if (start - pos > K) { open = false; break; }
+                start = pos;
+            }
+        }
+        // ---- the run, rightwards from its first match ----
+        uint32_t cnt = 0, nFwd = 0, nCan = 0, prev = start;
+        {
+            const uint32_t f0 = rs.at(start);                         // a match: the seed itself or one found above
+            cnt = 1; nFwd = (f0 >> 1) & 1u; nCan = (f0 >> 2) & 1u;
+        }
+        open = true;
+        for (unsigned long long base = static_cast<unsigned long long>(start) + 1; open && base < revB; base += 32) {
+            if (base - prev > K) break;
+            const unsigned long long q = base + lane;
+            const uint32_t f = q < revB ? rs.at(static_cast<uint32_t>(q)) : 0u;
+            uint32_t mask = __ballot_sync(0xFFFFFFFFu, (f & 1u) != 0u);
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const uint32_t pos = static_cast<uint32_t>(base + b);
+                if (pos - prev > K) { open = false; break; }
+                const uint32_t fb = __shfl_sync(0xFFFFFFFFu, f, b);
+                ++cnt; nFwd += (fb >> 1) & 1u; nCan += (fb >> 2) & 1u; prev = pos;
+            }
+        }
+        if (lane == 0) {
+            const uint32_t len = prev + L - start;
+            // computeBlockLabel, include/teloscope.h:217-222 (float32)
+            const float ratio = __fdiv_rn(__fmul_rn(__uint2float_rn(nFwd), 100.0f), __uint2float_rn(cnt));
+            const char label = ratio > 66.6f ? 'p' : (ratio < 33.3f ? 'q' : 'b');
+            if (len >= c.itsMinLen && nCan >= 4 && !(label == 'b' && nFwd < 2 && (cnt - nFwd) < 2)) {
+                DevBlock b{};
+                b.item = item; b.order = 0; b.start = start; b.len = len; b.counts = cnt; b.fwdCount = nFwd;
+                b.canCount = nCan; b.totalCov = cnt * L; b.fwdCov = nFwd * L; b.canCov = nCan * L;
+                b.validOr = 1; b.label = label; b.kind = 1;
+                emitBlock(p, b);
+            }
+        }
+        // ---- the chain's next canonical match behind this run ----
+        ++j;
+        while (j <= jEnd && recs[canIdx[j]].x <= prev) ++j;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // -m lists: final host-visible records (same layout as tls_match in include/teloscope_b200.h)
 // ------------------------------------------------------------------------------------------------
 struct OutMatch {
@@ -528,6 +732,34 @@ __global__ void __launch_bounds__(256) packWindowsKernel(const uint4 *in, uint4 
     if (i >= n) return;
     const uint4 a = in[2 * i], b = in[2 * i + 1];
     out[i] = make_uint4(a.x | (a.y << 16), a.z | (a.w << 16), b.x | (b.y << 16), b.z | (b.w << 16));
+}
+
+// The windows of the ranges[k] = [x, y) (rangePrefix: exclusive prefix of their lengths, nRanges + 1 entries), one thread per
+// window: the contigs the window-row kernel does not take (their counters are accumulated with atomics by the other scan
+// kernels, so they start from zero and are packed afterwards; the window-row kernel writes final records itself).
+__device__ __forceinline__ uint32_t windowOfRanges(const uint2 *ranges, const uint32_t *rangePrefix, uint32_t nRanges, uint32_t i) {
+    uint32_t lo = 0, hi = nRanges;                                 // last range with prefix <= i
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (rangePrefix[mid] <= i) lo = mid; else hi = mid;
+    }
+    return ranges[lo].x + (i - rangePrefix[lo]);
+}
+__global__ void __launch_bounds__(256) zeroWindowRangesKernel(uint4 *windows, const uint2 *ranges, const uint32_t *rangePrefix,
+                                                              uint32_t nRanges, uint32_t total) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t w = windowOfRanges(ranges, rangePrefix, nRanges, i);
+    windows[2 * w] = make_uint4(0u, 0u, 0u, 0u);
+    windows[2 * w + 1] = make_uint4(0u, 0u, 0u, 0u);
+}
+__global__ void __launch_bounds__(256) packWindowRangesKernel(const uint4 *in, uint4 *out, const uint2 *ranges, const uint32_t *rangePrefix,
+                                                              uint32_t nRanges, uint32_t total) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t w = windowOfRanges(ranges, rangePrefix, nRanges, i);
+    const uint4 a = in[2 * w], b = in[2 * w + 1];
+    out[w] = make_uint4(a.x | (a.y << 16), a.z | (a.w << 16), b.x | (b.y << 16), b.z | (b.w << 16));
 }
 
 __global__ void __launch_bounds__(256) selectFinalizeKernel(const DevMatch *m, const uint32_t *idxList, unsigned long long n,
@@ -632,8 +864,21 @@ cudaError_t launchPackWindows(const uint32_t *windows, void *windows16, unsigned
                                                                               static_cast<uint4 *>(windows16), n);
     return cudaGetLastError();
 }
-cudaError_t launchItemOffsets(const DevItemCounts *counts, uint32_t n, unsigned long long *itemBegin, cudaStream_t s) {
-    itemOffsetsKernel<<<1, 1024, 0, s>>>(counts, n, itemBegin);
+cudaError_t launchZeroWindowRanges(uint32_t *windows, const uint2 *ranges, const uint32_t *rangePrefix, uint32_t nRanges,
+                                   uint32_t total, cudaStream_t s) {
+    if (total == 0) return cudaSuccess;
+    zeroWindowRangesKernel<<<(total + 255) / 256, 256, 0, s>>>(reinterpret_cast<uint4 *>(windows), ranges, rangePrefix, nRanges, total);
+    return cudaGetLastError();
+}
+cudaError_t launchPackWindowRanges(const uint32_t *windows, void *windows16, const uint2 *ranges, const uint32_t *rangePrefix,
+                                   uint32_t nRanges, uint32_t total, cudaStream_t s) {
+    if (total == 0) return cudaSuccess;
+    packWindowRangesKernel<<<(total + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows), static_cast<uint4 *>(windows16),
+                                                             ranges, rangePrefix, nRanges, total);
+    return cudaGetLastError();
+}
+cudaError_t launchItemOffsets(const DevItemCounts *counts, const DevItemInfo *items, uint32_t n, unsigned long long *itemBegin, cudaStream_t s) {
+    itemOffsetsKernel<<<1, 1024, 0, s>>>(counts, items, n, itemBegin);
     return cudaGetLastError();
 }
 cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s) {
@@ -651,6 +896,19 @@ cudaError_t launchIts(const BlockParams &p, const uint32_t *canIdx, unsigned lon
     // the number of runs is only known on the device: enough warps for the capacity, surplus warps exit
     const unsigned long long warps = std::min<unsigned long long>(runCap, nCan / 4 + 1);
     itsRunKernel<<<static_cast<unsigned int>((warps * 32 + 127) / 128), 128, 0, s>>>(p, runStarts, runCount, runCap);
+    return cudaGetLastError();
+}
+cudaError_t launchItsRows(const BlockParams &p, const uint32_t *canIdx, unsigned long long nCan, uint8_t *conn,
+                          unsigned long long *chainStarts, unsigned int *chainCount, uint32_t chainCap, cudaStream_t s) {
+    if (nCan < 4) return cudaSuccess;
+    const unsigned int blocks = static_cast<unsigned int>((nCan + 255) / 256);
+    itsConnKernel<<<blocks, 256, 0, s>>>(p, canIdx, nCan, conn);
+    itsChainKernel<<<blocks, 256, 0, s>>>(conn, nCan, chainStarts, chainCount, chainCap);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // the number of chains is only known on the device: enough warps for the capacity, surplus warps exit
+    const unsigned long long warps = std::min<unsigned long long>(chainCap, nCan / 4 + 1);
+    itsWalkKernel<<<static_cast<unsigned int>((warps * 32 + 127) / 128), 128, 0, s>>>(p, canIdx, conn, chainStarts, chainCount, chainCap);
     return cudaGetLastError();
 }
 cudaError_t launchSelectFinalize(const DevMatch *m, const uint32_t *idxList, unsigned long long n,
@@ -672,6 +930,19 @@ __global__ void trimCrKernel(const uint8_t *seq, DevRegion *regions, uint32_t nR
         regions[r].itemLen = reg.itemLen - 1;
         itemLen[reg.item] = reg.itemLen - 1;
     }
+}
+
+// the same for the read scorer, which works from the per-item table
+__global__ void trimCrItemsKernel(const uint8_t *seq, const DevItemInfo *items, uint32_t n, uint32_t *itemLen) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t len = itemLen[i];
+    if (len && seq[items[i].bufStart + len - 1] == '\r') itemLen[i] = len - 1;
+}
+cudaError_t launchTrimCrItems(const uint8_t *seq, const DevItemInfo *items, uint32_t n, uint32_t *itemLen, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    trimCrItemsKernel<<<(n + 255) / 256, 256, 0, s>>>(seq, items, n, itemLen);
+    return cudaGetLastError();
 }
 
 cudaError_t launchTrimCr(const uint8_t *seq, DevRegion *regions, uint32_t nRegions, uint32_t *itemLen, cudaStream_t s) {

@@ -25,6 +25,19 @@ __device__ __forceinline__ bool isTerminalMatch(const DevConfig &c, uint32_t rel
     return rel <= T || rel >= termEnd;
 }
 
+// Window-row kernel (scan_rows.cu): the part [lo, hi) of a contig of n bases that its SPARSE work units cover.  A unit is
+// kRowsPerUnit consecutive windows; it is sparse when none of its windows touches a terminal zone (the first / last
+// terminalLimit bases, src/teloscope.cpp:403-406) and all of them are full: rel > T and rel + unit span <= n - T.  Only the
+// canonical matches of a sparse unit become match records; everywhere else (dense units, other kernels) every match does.
+// lo == hi == 0xFFFFFFFF: the contig has no sparse unit.
+__host__ __device__ inline void sparseRange(uint32_t n, uint32_t T, uint32_t W, uint32_t &lo, uint32_t &hi) {
+    const unsigned long long span = static_cast<unsigned long long>(kRowsPerUnit) * W;
+    const unsigned long long termEnd = n > T ? n - T : 0;
+    const unsigned long long l = (T / span + 1) * span, h = (termEnd / span) * span;
+    if (l < h) { lo = static_cast<uint32_t>(l); hi = static_cast<uint32_t>(h); }
+    else lo = hi = 0xFFFFFFFFu;
+}
+
 // One overflow chunk of `chunk` records from the bump-allocated arena.  The cursor is 64 bits wide, so the host always
 // reads the true demand (a dense batch cannot wrap it); the returned base saturates below kNoOverflow and every write
 // is bounds-checked against the arena capacity (<= kMaxOvRecords) in 64 bits.

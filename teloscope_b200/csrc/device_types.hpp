@@ -48,6 +48,14 @@ constexpr int kRowMaxLen = kRowStage - 15 - 7;    // longest window: alignment s
 constexpr uint32_t kRowMinWindow = 600;           // below this more than 40 % of the lanes would idle
 constexpr uint32_t kRowMinWindows = 8;            // shorter contigs go to the general kernel
 constexpr int kRowQueueCap = 256;                 // per-warp match queue (u16 entries), 8 lanes' worth
+#ifndef TLS_ROW_KEYMODE
+#define TLS_ROW_KEYMODE 1
+#endif
+constexpr int kRowKeyMode = TLS_ROW_KEYMODE;            // how a probe extracts its 16-bit key (probeKey in scan_rows.cu)
+#ifndef TLS_ROW_PREFETCH
+#define TLS_ROW_PREFETCH 1
+#endif
+constexpr bool kRowPrefetch = TLS_ROW_PREFETCH != 0;   // L2 prefetch of the row after next
 constexpr int kRowsPerUnit = TLS_ROWS_PER_UNIT;   // consecutive windows one warp takes at a time (divides kTileRows)
 
 // A maximal stretch of one item inside which matches must lie entirely
@@ -118,7 +126,9 @@ enum : uint8_t { kMatchFwd = 1, kMatchCan = 2, kMatchTerm = 4 };
 constexpr uint8_t kRegionAccounted = 0xFF;
 
 struct DevItemCounts {     // per item, filled by the scan kernel
-    uint32_t all, fwd, rev, can, nonCanTerm, pad[3];
+    uint32_t all, fwd, rev, can, nonCanTerm;
+    uint32_t records;      // window-row kernel only: match records of the item in the arena (sparse units emit canonical matches only)
+    uint32_t pad[2];
 };
 
 struct DevBlock {          // 48 bytes
@@ -214,21 +224,52 @@ struct RowParams {
     const uint8_t *seq;
     const DevRowUnit *units;
     uint32_t nUnits;
-    const uint8_t *index8;         // 65536-byte stage-1 table
+    const uint8_t *indexRow;       // 65536 bytes: per 8-mer, NPOS-bit fields hit | forward << NPOS, and bit 2 NPOS = a canonical match among them
+    uint32_t two16;                // 65536 (a multiplier the compiler cannot fold, see probeKey in scan_rows.cu)
     const uint8_t *flagTab;        // direct table of the single length class (4^len bytes)
     uint32_t flagTabBytes;         // rounded up to 16
     uint32_t patLen;
     DevMatch *slots;
     uint32_t slotCap;
-    uint4 *slotMeta;               // per row slot: count, overflow base, canonical, terminal non-canonical
-    uint32_t *tileTot;             // [3][nTilesAll]
+    uint4 *slotMeta;               // per row slot: records, overflow base, canonical, terminal non-canonical (zeroed before the launch)
+    uint32_t *tileTot;             // [3][nTilesAll]: records, canonical, terminal non-canonical
     uint32_t nTilesAll;
     DevMatch *ovArena;
     uint32_t ovCap, ovChunk;
     unsigned int *ovCursor;
     uint4 *windows;                // [nWindows][2]: A, C, G, T | canonical, non-canonical, forward, reverse covered bp
+    uint4 *windows16;              // TLS_OUT_COMPACT: [nWindows] tls_window16 written directly (windows is not touched then)
+    uint32_t *zeroLanes;           // [nWindows]: bit l = lane l (row positions 32 l .. 32 l + 31) holds no match start
     DevItemCounts *itemCounts;
     unsigned int *status;          // set to 1 when the shared memory layout assumption fails
+    DevConfig cfg;
+};
+
+// Per item, for the kernels behind the scan: where its sequence and its windows start, and whether the window-row kernel
+// scanned it (then its record list is complete only outside sparseRange(), see device_common.cuh).
+struct DevItemInfo {       // 16 bytes
+    uint64_t bufStart;     // offset of the item's first base in the sequence buffer
+    uint32_t winBase;      // global index of its first window (genome mode)
+    uint32_t rowItem;      // 1: scanned by the window-row kernel
+};
+
+// ---- read scorer (scan_reads.cu): one warp per read, kReadStride start positions per row ----
+constexpr int kReadThreads = 768;
+constexpr int kReadStride = 1000;                 // <= 1024 - 15 (alignment skew) - 6 (bases a match needs beyond its start)
+
+struct ReadParams {
+    const uint8_t *seq;
+    const DevItemInfo *items;      // bufStart per read
+    const uint32_t *itemLen;       // after the '\r' trim (src/read-filter.cpp:38-40)
+    uint32_t nItems;
+    const uint8_t *index8;         // 65536-byte stage-1 table
+    const uint8_t *flagTab;        // direct table of the single length class: bit0 hit, bit1 forward, bit2 canonical
+    uint32_t flagTabBytes;         // rounded up to 16
+    uint32_t patLen;
+    uint8_t *pass;                 // per read: 1 = some terminal block (ReadTelomereFilter::matches)
+    unsigned int *cursor;          // work counter, zeroed per launch
+    unsigned int *status;          // set to 1 when the shared memory layout assumption fails
+    unsigned long long *matchTotal;   // matches found (reads that are decided early stop counting)
     DevConfig cfg;
 };
 
@@ -258,6 +299,12 @@ struct BlockParams {
     const DevItemCounts *itemCounts;
     const uint32_t *itemLen;               // per item (after the read-mode '\r' trim)
     uint32_t nItems;
+    // window-row items: what a walk needs where the record list is sparse (null / 0 when the batch has none)
+    const DevItemInfo *items;
+    const uint8_t *seq;                    // the batch's sequence buffer
+    const uint8_t *flagTab;                // direct table of the single length class: bit0 hit, bit1 forward, bit2 canonical
+    uint32_t patLen;
+    const uint32_t *zeroLanes;             // per window: lanes (32 positions each) without a match start
     DevBlock *blocks;                      // output, unordered; the host sorts by (item, order)
     uint32_t blockCap;
     unsigned int *blockCount;              // keeps counting past the capacity

@@ -18,9 +18,9 @@
 //     flight per SM); no shared-memory staging, no mbarrier;
 //   * SWAR pack to 2-bit codes (one multiply per 4 bases) fused with the exact "all bytes are ACGTacgt"
 //     test; the row's alignment skew is removed on the packed words (one funnel shift per word);
-//   * 11 probes of the 64 KiB 8-mer table (one byte answers NPOS start offsets; the table sits at
-//     shared address 0x10000, so the probe is mask + LDS with an immediate) give the 32-bit bitmap of
-//     match starts; starts whose match would cross the window end are masked (:439);
+//   * 11 probes of the 128 KiB 8-mer table (one u16 entry answers NPOS start offsets: hit / forward / canonical bit
+//     fields; the table sits at shared address 0x10000, so the probe is mask + LDS with an immediate);
+//     starts whose match would cross the window end are masked (:439);
 //   * A/C/G/T: 3 popcounts on bit planes, 2 REDUX per window on packed partial sums; the four counts
 //     are derived from them once per row in the unit epilogue (:418-435);
 //   * matches: warp prefix sum of the per-lane counts, then every lane writes its own 8-byte records,
@@ -43,95 +43,30 @@
 
 #include "device_common.cuh"
 #include "kernels.hpp"
+#include "row_common.cuh"
 
 namespace tls {
 
 namespace {
-
-__device__ __forceinline__ uint32_t smemAddr(const void *p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-// Streaming loads of a lane's 32 bytes (every base is read once, nothing of it belongs in L1), done only
-// when a < b; otherwise the registers keep what they hold.  (Plain ld.global.nc and an L2::256B prefetch hint
-// were measured: no difference.)
-__device__ __forceinline__ void ldStream32If(uint4 &v0, uint4 &v1, uint64_t addr, uint32_t a, uint32_t b) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.lt.u32 p, %9, %10;\n"
-        "@p ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%8];\n"
-        "@p ld.global.nc.L1::no_allocate.v4.u32 {%4,%5,%6,%7}, [%8+16];\n"
-        "}\n"
-        : "+r"(v0.x), "+r"(v0.y), "+r"(v0.z), "+r"(v0.w), "+r"(v1.x), "+r"(v1.y), "+r"(v1.z), "+r"(v1.w)
-        : "l"(addr), "r"(a), "r"(b));
-}
-__device__ __forceinline__ uint32_t bfind(uint32_t v) {         // position of the highest set bit (FLO)
-    uint32_t r;
-    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
-    return r;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t bmskClamp(int n) {   // bits [0, min(n, 32)), n >= 0 (BMSK)
-    uint32_t r;
-    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(r) : "r"(0u), "r"(static_cast<uint32_t>(n)));
-    return r;
-}
-__device__ __forceinline__ int clamp32(int v) { return min(max(v, 0), 32); }
-
-// Exact validity of the bytes fed through add(): see scan_fast.cu (same formula, exhaustively checked
-// in tests/test_host_cpu.py::test_validity_formula).
-struct ValidAcc {
-    uint32_t a1 = 0, a2 = 0xFFFFFFFFu, any = 0;
-    __device__ __forceinline__ void add(uint32_t w, uint32_t m) {
-        const uint32_t y = m * 6u + 0x40404040u;
-        const uint32_t z = w * 16u;
-        a1 |= y ^ w;
-        a2 &= z ^ w;
-        any |= w;
-    }
-    __device__ __forceinline__ uint32_t bad() const {
-        return (a1 & 0xD0D0D0D0u) | (~a2 & 0x10101010u) | (any & 0x08080808u);
-    }
-};
-// 2-bit codes of 4 bases in the top byte: (c >> 1) & 3 maps A,C,T,G (either case) to 0,1,2,3
-__device__ __forceinline__ uint32_t packWord(uint32_t w, ValidAcc &v) {
-    const uint32_t m = w & 0x06060606u;
-    v.add(w, m);
-    return m * 0x00820820u;
-}
-__device__ __forceinline__ uint32_t pack16v(const uint4 &q, ValidAcc &v) {
-    const uint32_t a = packWord(q.x, v), b = packWord(q.y, v), c = packWord(q.z, v), d = packWord(q.w, v);
-    return __byte_perm(__byte_perm(a, b, 0x0073), __byte_perm(c, d, 0x0073), 0x5410);
-}
-__device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, d);
-        if (lane >= d) v += u;
-    }
-    return v;
-}
 
 // ---- shared memory layout: ABSOLUTE addresses in the CTA's shared window.  The dynamic block starts
 // kWindowBase bytes into it on sm_100 (checked at run time: status 1 otherwise), so every address below
 // is a compile-time constant and goes into the instruction as an immediate. -------------------------------
 constexpr uint32_t kWindowBase = 0x400;
 constexpr uint32_t kWarpBlk = kRowsPerUnit <= 8 ? 256 : (kRowsPerUnit <= 16 ? 512 : 1024);  // per warp: row results of the unit in flight
-constexpr uint32_t kRecOff = 0;                            //   8 x 16 bytes of window / slot results + 8 overflow bases
-static_assert(kRecOff + kRowsPerUnit * 20 <= kWarpBlk, "per-warp block");
-constexpr uint32_t kWarpBase = kWindowBase;                               // 8 KiB of warp blocks
+constexpr uint32_t kRecOff = 0;                            //   16 bytes of results per row, then per row: overflow base (u32), terminal non-canonical count (u32)
+constexpr uint32_t kOvOff = kRowsPerUnit * 16;
+constexpr uint32_t kNctOff = kRowsPerUnit * 20;
+static_assert(kRowsPerUnit * 24 <= kWarpBlk, "per-warp block");
+constexpr uint32_t kWarpBase = kWindowBase;                               // warp blocks
 constexpr uint32_t kFlagBase = kWarpBase + kRowWarps * kWarpBlk;          // 16 KiB flag table
-constexpr uint32_t kIdxBase = 0x10000u;                                   // 64 KiB 8-mer table
+constexpr uint32_t kIdxBase = 0x10000u;                                   // 64 KiB 8-mer table (one byte per key)
 static_assert(kFlagBase + kFastFlagBytes <= kIdxBase, "front region must end before the 8-mer table");
 constexpr uint32_t kRowSmemTotal = kIdxBase + 65536u - kWindowBase;
 static_assert(kRowSmemTotal <= 232448u, "shared memory budget of one SM");
 
 // the tables never change during the kernel: plain asm (may be scheduled freely), address = index + immediate
-__device__ __forceinline__ uint32_t ldsU8Idx(uint32_t key) {
+__device__ __forceinline__ uint32_t ldsU8Idx(uint32_t key) {             // 16-bit 8-mer key
     uint32_t v;
     asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(key), "n"(kIdxBase));
     return v;
@@ -142,57 +77,41 @@ __device__ __forceinline__ uint32_t ldsU8Flag(uint32_t key) {
     return v;
 }
 
-// Slow exact path of a row that holds a byte outside ACGTacgt (IUPAC letters, '\r', ...): per-lane
-// bitmap of such bases in row coordinates and the counts of the lane's valid bases, in the packed form
-// the fast path reduces (x: invalid bitmap, y: nE | nO << 16, z: nG | nValid << 16 with nE = C + G,
-// nO = G + T).  The reference's Trie stops at such a byte (include/teloscope.h:27-35,63-66) and
-// analyzeWindow does not count it (src/teloscope.cpp:418-435).
-__device__ __noinline__ uint4 slowRow(const uint8_t *row, int nValid) {
-    uint32_t inv = 0, a = 0, c = 0, g = 0, t = 0;
-    for (int i = 0; i < nValid; ++i) {
-        const uint32_t ch = __ldg(row + i) & 0xDFu;
-        if (ch == 'A') ++a;
-        else if (ch == 'C') ++c;
-        else if (ch == 'G') ++g;
-        else if (ch == 'T') ++t;
-        else inv |= 1u << i;
+// Layout of the per-lane match accumulators.  One byte of the 8-mer table answers NPOS start offsets: bit fields H (some
+// pattern matches there) and F (a forward pattern) of NPOS bits each, and one bit C (one of those matches is the canonical
+// pattern, either strand).  G consecutive probes share one 32-bit accumulator (probe j of the group sits FW * j bits up), so
+// the whole lane (32 start positions) takes kAcc = 3 accumulators, and a probe costs one multiply-add on the FMA pipe: no
+// masks, no shifts on the ALU pipe, which is what bounds this kernel.
+template <int NPOS>
+struct AccLayout {
+    static constexpr int FW = 2 * NPOS + 1;
+    static constexpr int G = 32 / FW;                                      // 6 (NPOS 2), 4 (NPOS 3)
+    static constexpr int kProbes = (kRowSpan + NPOS - 1) / NPOS;           // 16, 11
+    static constexpr int kAcc = (kProbes + G - 1) / G;                     // 3
+    __host__ __device__ static constexpr uint32_t field(int f) {           // the bits of field f (0 H, 1 F, 2 C) of all G probes
+        uint32_t m = 0;
+        for (int j = 0; j < G; ++j) m |= (f == 2 ? 1u : (1u << NPOS) - 1u) << (FW * j + f * NPOS);
+        return m;
     }
-    return make_uint4(inv, (c + g) | ((g + t) << 16), g | ((a + c + g + t) << 16), 0u);
-}
-
-// A row that is shorter than the window (the last one of a contig) and / or holds a byte outside ACGTacgt:
-// the lane's match starts H (computed with the masks of a full window) and its packed A/C/G/T partial sums
-// are redone exactly.  Called by the whole warp.
-__device__ __noinline__ uint4 fixRow(uint32_t H, uint32_t X0, uint32_t X1, const uint8_t *laneRow, uint32_t rowLen, uint32_t L,
-                                     bool anyBad, bool count) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const int nLeft = static_cast<int>(rowLen) - static_cast<int>(lane * kRowSpan);
-    const uint32_t nv = static_cast<uint32_t>(clamp32(nLeft));
-    H &= bmskClamp(max(nLeft - static_cast<int>(L) + 1, 0));
-    uint32_t t1 = 0, t2 = 0;
-    if (count) {
-        const uint32_t Y0 = X0 & bmskClamp(max(2 * nLeft, 0)), Y1 = X1 & bmskClamp(max(2 * nLeft - 32, 0));
-        const uint32_t e = (Y0 & 0x55555555u) | ((Y1 << 1) & 0xAAAAAAAAu);
-        const uint32_t o = ((Y0 >> 1) & 0x55555555u) | (Y1 & 0xAAAAAAAAu);
-        t1 = __popc(e) + (__popc(o) << 16);
-        t2 = __popc(e & o) + (nv << 16);
-    }
-    if (anyBad) {
-        const uint4 slow = slowRow(laneRow, static_cast<int>(nv));
-        uint32_t invN = __shfl_down_sync(0xFFFFFFFFu, slow.x, 1);
-        if (lane == 31) invN = 0;
-        uint32_t dead = slow.x;
-        for (uint32_t j = 1; j < L; ++j) dead |= __funnelshift_r(slow.x, invN, j);
-        H &= ~dead;
-        t1 = slow.y; t2 = slow.z;
-    }
-    return make_uint4(H, t1, t2, 0u);
-}
+};
 
 }  // namespace
 
+// Two kinds of work units (16 consecutive windows of one contig, see sparseRange() in device_common.cuh):
+//   * DENSE units hold a window that touches a terminal zone (the first / last terminalLimit bases of the contig,
+//     src/teloscope.cpp:403-406) or the contig's last window.  Every match becomes a record in the row's slot of the
+//     arena (the terminal-block walk and the terminal non-canonical list of -m need them all).
+//   * SPARSE units (everything else: 98 % of a chromosome) emit only what the reference ever reads again from
+//     analyzeWindow's match vectors there: the canonical matches (canonicalMatches, and the seeds of the interstitial
+//     blocks).  The other matches only count: window counters, per-item totals.  Per row a 32-bit mask of the lanes
+//     without a match start goes out as well; the interstitial-block kernels use it to prove that two canonical
+//     matches cannot belong to one run (block_kernels.cu) and rescan the sequence where they cannot.
 template <int NPOS, bool COUNT>
 __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams p) {
+    using AL = AccLayout<NPOS>;
+    constexpr int FW = AL::FW, G = AL::G, kProbes = AL::kProbes, kAcc = AL::kAcc;
+    constexpr uint32_t MH = AL::field(0), MF = AL::field(1), MC = AL::field(2);
+    constexpr uint32_t PM = (1u << NPOS) - 1u;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
@@ -205,7 +124,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     // ---- one-time setup: the 8-mer table as it is; the flag table re-coded for the emission loop:
     //      bit0 forward, bit1 canonical (= DevMatch flags), bit7 canonical again (count field, see below) ------
     for (int i = tid; i < 65536 / 16; i += kRowThreads)
-        reinterpret_cast<uint4 *>(smem + (kIdxBase - kWindowBase))[i] = reinterpret_cast<const uint4 *>(p.index8)[i];
+        reinterpret_cast<uint4 *>(smem + (kIdxBase - kWindowBase))[i] = reinterpret_cast<const uint4 *>(p.indexRow)[i];
     for (uint32_t i = tid; i < p.flagTabBytes / 4; i += kRowThreads) {
         const uint32_t f = reinterpret_cast<const uint32_t *>(p.flagTab)[i];   // per byte: bit0 hit, bit1 forward, bit2 canonical
         reinterpret_cast<uint32_t *>(smem + (kFlagBase - kWindowBase))[i] = ((f >> 1) & 0x03030303u) | ((f & 0x04040404u) << 5);
@@ -222,6 +141,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     const uint32_t slotBytes = p.slotCap * 8u;
     const bool lane0 = lane == 0;
     const uint32_t laneLt = (1u << lane) - 1u;
+    const uint32_t unitSpan = static_cast<uint32_t>(kRowsPerUnit) * W;
 
     // Per-lane masks of a row of rowLen bases: the lane's valid 2-bit fields in X0 / X1, its valid match
     // starts (a match never crosses the window end, src/teloscope.cpp:439) and its number of bases << 16.
@@ -238,6 +158,23 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
         return m;
     };
     const LaneMasks fm = laneMasks(W);
+    // the same start mask in accumulator layout (all three fields of a valid start)
+    uint32_t fmA[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const int tl = k * G + j;
+            if (tl >= kProbes) continue;
+#pragma unroll
+            for (int o = 0; o < NPOS; ++o) {
+                const int pos = tl * NPOS + o;
+                if (pos < 32 && ((fm.hm >> pos) & 1u)) m |= ((1u | (1u << NPOS)) << (FW * j + o)) | (1u << (FW * j + 2 * NPOS));
+            }
+        }
+        fmA[k] = m;
+    }
 
     auto loadUnit = [&](uint32_t u, uint4 &a, uint4 &b) {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.units + u);
@@ -249,6 +186,33 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     uint4 c0 = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u), c1 = c0;
     auto loadRow = [&](uint64_t laneRowAddr, uint32_t len) {
         ldStream32If(c0, c1, laneRowAddr & ~static_cast<uint64_t>(15), laneOff, len + 15u);
+    };
+    // One probe: the 16-bit key of the 8-mer that starts 2 * NPOS * tl bits into the lane's stream.  kRowKeyMode (build-time,
+    // measured in DESIGN.md): 0 = shift + mask, both on the ALU pipe; 1 = keys inside one word are moved to the top of the
+    // word by a multiply (FMA pipe) and brought down by one shift, keys that straddle two words are funnel-shifted and
+    // masked; 2 = as 1, brought down by a multiply-high with 2^16 taken from a kernel parameter (so that it is not
+    // strength-reduced to a shift): no ALU instruction for the in-word keys, but IMAD.HI issues at half rate.
+    const uint32_t k16 = p.two16;
+    auto probeKey = [&](const uint32_t (&Xv)[4], int tl) -> uint32_t {
+        const int bit = 2 * NPOS * tl, wi = bit >> 5, s = bit & 31;
+        if (kRowKeyMode == 0) {
+            const uint32_t x = s == 0 ? Xv[wi] : (s <= 16 ? Xv[wi] >> s : __funnelshift_r(Xv[wi], Xv[wi + 1], s));
+            return x & 0xFFFFu;
+        }
+        if (kRowKeyMode == 1) {
+            if (s == 16) return Xv[wi] >> 16;
+            if (s < 16) return (Xv[wi] * (1u << (16 - s))) >> 16;
+            return __funnelshift_r(Xv[wi], Xv[wi + 1], s) & 0xFFFFu;
+        }
+        const uint32_t top = s <= 16 ? Xv[wi] * (1u << (16 - s)) : __funnelshift_r(Xv[wi], Xv[wi + 1], s) * 65536u;
+        return __umulhi(top, k16);
+    };
+    // Records of the lane's matches `bits` (row positions, ascending) with their flags: slot entry `o` onwards, the part
+    // beyond the slot in the row's overflow chunk.  Returns the sum of the flag bytes.
+    auto storeRec = [&](uint8_t *slotPtr, uint32_t o, uint32_t ovBase, uint2 rec) {
+        if (o < p.slotCap) reinterpret_cast<uint2 *>(slotPtr)[o] = rec;
+        else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap)
+            reinterpret_cast<uint2 *>(p.ovArena)[ovBase + (o - p.slotCap)] = rec;
     };
 
     uint32_t u = blockIdx.x * kRowWarps + warp;
@@ -274,177 +238,300 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
         }
         uint8_t *slotPtr = reinterpret_cast<uint8_t *>(p.slots) + static_cast<size_t>(db.y) * slotBytes;
         uint32_t ovRows = 0;                                   // bit r: row r spilled into an overflow chunk
+        // sparse unit: 16 full windows, none of them touching a terminal zone (the rule of sparseRange(), device_common.cuh)
+        const bool sparse = rel > T && termEnd >= rel && termEnd - rel >= unitSpan;
 
+        if (sparse) {
 #pragma unroll 1
-        for (uint32_t r = 0; r < nRows; ++r) {
-            const uint32_t remaining = itemLen - rel;
-            const bool partial = remaining < W;                 // warp-uniform: the last window of a contig
-            const uint32_t skew = static_cast<uint32_t>(laneAddr) & 15u;
-
-            // ---- 1. pack + validate the row that has landed, then re-arm the registers with the next row -------
-            uint32_t P0, P1, badBits;
-            {
-                ValidAcc va;
-                P0 = pack16v(c0, va);
-                P1 = pack16v(c1, va);
-                badBits = va.bad();                             // stale lanes past a short row hold bytes that were valid or already took the slow path
-            }
-            {
-                const bool inUnit = r + 1 < nRows;
-                const uint64_t na = inUnit ? laneAddr + W : nextAddr;
-                const uint32_t nl = inUnit ? min(W, remaining - W) + 15u : nextLim;
-                ldStream32If(c0, c1, na & ~static_cast<uint64_t>(15), laneOff, nl);
-            }
-
-            // ---- 2. remove the skew: X0 X1 X2 = the lane's 32 bases and the 16 that follow -------------------
-            const uint32_t sh = 2u * skew;
-            const uint32_t X0 = __funnelshift_r(P0, P1, sh);
-            const uint32_t X1 = __funnelshift_r(P1, __shfl_down_sync(0xFFFFFFFFu, P0, 1), sh);
-            const uint32_t X2 = __shfl_down_sync(0xFFFFFFFFu, X0, 1);      // lane 31: bases past any row, masked below
-            const bool anyBad = __any_sync(0xFFFFFFFFu, badBits != 0);
-
-            // ---- 3. one table byte per NPOS start positions ---------------------------------------------------
-            uint32_t H = 0;
-            {
-                const uint32_t Xv[4] = {X0, X1, X2, 0u};
-                constexpr int kProbes = (kRowSpan + NPOS - 1) / NPOS;
+            for (uint32_t r = 0; r < static_cast<uint32_t>(kRowsPerUnit); ++r) {
+                const uint32_t skew = static_cast<uint32_t>(laneAddr) & 15u;
+                // ---- 1. pack + validate the row that has landed, then re-arm the registers with the next row -------
+                uint32_t P0, P1, badBits;
+                {
+                    ValidAcc va;
+                    P0 = pack16v(c0, va);
+                    P1 = pack16v(c1, va);
+                    badBits = va.bad();
+                }
+                {
+                    const bool inUnit = r + 1 < static_cast<uint32_t>(kRowsPerUnit);
+                    const uint64_t na = inUnit ? laneAddr + W : nextAddr;
+                    const uint32_t nl = inUnit ? W + 15u : nextLim;
+                    ldStream32If(c0, c1, na & ~static_cast<uint64_t>(15), laneOff, nl);
+                    // the row after that one: into L2 now, so that its register load next iteration is an L2 hit
+                    if (kRowPrefetch && laneOff < W) asm volatile("prefetch.global.L2 [%0];" ::"l"((na + W) & ~static_cast<uint64_t>(15)));
+                }
+                // ---- 2. remove the skew ---------------------------------------------------------------------------
+                const uint32_t sh = 2u * skew;
+                const uint32_t X0 = __funnelshift_r(P0, P1, sh);
+                const uint32_t X1 = __funnelshift_r(P1, __shfl_down_sync(0xFFFFFFFFu, P0, 1), sh);
+                const uint32_t X2 = __shfl_down_sync(0xFFFFFFFFu, X0, 1);
+                // ---- 3. probes: one multiply-add each ------------------------------------------------------------
+                uint32_t acc[kAcc];
 #pragma unroll
-                for (int tl = 0; tl < kProbes; ++tl) {
-                    const int bit = 2 * NPOS * tl, wi = bit >> 5, s = bit & 31;
-                    const uint32_t x = s == 0 ? Xv[wi] : (s <= 16 ? Xv[wi] >> s : __funnelshift_r(Xv[wi], Xv[wi + 1], s));
-                    const uint32_t e = ldsU8Idx(x & 0xFFFFu);
-                    H = e * (1u << (NPOS * tl)) + H;              // disjoint bit fields: add == or (bits >= 32 drop out)
+                for (int k = 0; k < kAcc; ++k) acc[k] = 0;
+                {
+                    const uint32_t Xv[4] = {X0, X1, X2, 0u};
+#pragma unroll
+                    for (int tl = 0; tl < kProbes; ++tl) {
+                        const uint32_t e = ldsU8Idx(probeKey(Xv, tl));
+                        acc[tl / G] = e * (1u << (FW * (tl % G))) + acc[tl / G];
+                    }
                 }
-            }
-            // ---- 4. matches never cross the window end (src/teloscope.cpp:439) --------------------------------
-            H &= fm.hm;
-
-            // ---- 5. A/C/G/T of the window: packed partial sums (nE = C + G, nO = G + T, nG, bases) -------------
-            uint32_t t1 = 0, t2 = 0;
-            if (COUNT) {
-                const uint32_t Y0 = X0 & fm.m0, Y1 = X1 & fm.m1;
-                const uint32_t e = (Y0 & 0x55555555u) | ((Y1 << 1) & 0xAAAAAAAAu);    // code bit 0: C or G
-                const uint32_t o = ((Y0 >> 1) & 0x55555555u) | (Y1 & 0xAAAAAAAAu);    // code bit 1: G or T
-                t1 = __popc(e) + (__popc(o) << 16);
-                t2 = __popc(e & o) + fm.nv;
-            }
-            if (partial || anyBad) {                            // rare, warp-uniform: the exact path redoes H, t1, t2
-                const uint4 fx = fixRow(H, X0, X1, reinterpret_cast<const uint8_t *>(laneAddr), min(W, remaining), L, anyBad, COUNT);
-                H = fx.x; t1 = fx.y; t2 = fx.z;
-            }
-            uint32_t sum1 = 0, sum2 = 0;
-            if (COUNT) {
-                sum1 = __reduce_add_sync(0xFFFFFFFFu, t1);
-                sum2 = __reduce_add_sync(0xFFFFFFFFu, t2);
-            }
-
-            // ---- 6. emission: every lane writes its own matches, in order, behind those of the lanes before it.
-            //      The match's 2L-bit key comes out of the lane's registers, the flag byte g (bit0 forward, bit1
-            //      canonical, bit7 canonical) goes into the record as it is and is summed per lane: a lane has at
-            //      most 32 matches, so forward + 2 canonical < 128 stays below the canonical count at bit 7. ----------
-            const uint32_t rowEnd = rel + min(W, remaining);
-            const bool rowHasTerm = rel <= T || rowEnd > termEnd;                               // warp-uniform
-            const bool rowAllTerm = rowEnd <= T + 1u || rel >= termEnd;                         // warp-uniform
-            const uint32_t nH = __popc(H);
-            uint32_t incl, wMatches;
-            if (!__any_sync(0xFFFFFFFFu, nH > 7u)) {
-                // at most 7 matches per lane (any row but a homopolymer-like one): the prefix from three independent
-                // ballots on the bits of the count instead of five dependent shuffles
-                const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, nH & 1u), b1 = __ballot_sync(0xFFFFFFFFu, nH & 2u),
-                               b2 = __ballot_sync(0xFFFFFFFFu, nH & 4u);
-                incl = __popc(b0 & laneLt) + 2u * __popc(b1 & laneLt) + 4u * __popc(b2 & laneLt) + nH;
-                wMatches = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
-            } else {
-                incl = warpInclusiveScan(nH, lane);
-                wMatches = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            }
-            const uint32_t relLane = rel + laneOff;
-            uint32_t acc = 0, rowNct = 0;
-            if (wMatches <= p.slotCap && (rowAllTerm || !rowHasTerm)) {
-                // common case: the slot has room and "terminal" is the same for the whole row
-                const uint32_t recHiRow = recHi | (rowAllTerm ? static_cast<uint32_t>(kMatchTerm) << 16 : 0u);
-                uint2 *out = reinterpret_cast<uint2 *>(slotPtr) + (incl - nH);
-                uint32_t bits = H;
-                while (bits) {
-                    const uint32_t t = bits & (0u - bits);
-                    const uint32_t c = bfind(t);
-                    bits ^= t;
-                    const bool lowHalf = c < 16u;
-                    const uint32_t key = __funnelshift_r(lowHalf ? X0 : X1, lowHalf ? X1 : X2, 2u * c) & keyMask;
-                    const uint32_t g = ldsU8Flag(key);
-                    *out++ = make_uint2(relLane + c, g * 65536u + recHiRow);
-                    acc += g;
+                // ---- 4. starts whose match would cross the window end drop out (src/teloscope.cpp:439); class counts ----
+                uint32_t nH = 0, nF = 0, cAny = 0;
+#pragma unroll
+                for (int k = 0; k < kAcc; ++k) {
+                    acc[k] &= fmA[k];
+                    nH += __popc(acc[k] & MH);
+                    nF += __popc(acc[k] & MF);
+                    cAny |= acc[k];
                 }
-            } else {
+                cAny &= MC;
+                // ---- 5. A/C/G/T of the window: nE = C + G, nO = G + T, nG in 10-bit fields (a full window: <= 1002) --
+                uint32_t t1 = 0;
+                if (COUNT) {
+                    const uint32_t Y0 = X0 & fm.m0, Y1 = X1 & fm.m1;
+                    const uint32_t e = (Y0 & 0x55555555u) | ((Y1 << 1) & 0xAAAAAAAAu);    // code bit 0: C or G
+                    const uint32_t o = ((Y0 >> 1) & 0x55555555u) | (Y1 & 0xAAAAAAAAu);    // code bit 1: G or T
+                    t1 = __popc(e) + (__popc(o) << 10) + (__popc(e & o) << 20);
+                }
+                uint32_t cls = nH | (nF << 10);
+                uint32_t nVrow = W;
+                uint32_t nEmit = 0;
+                if (__any_sync(0xFFFFFFFFu, (badBits | cAny) != 0)) {
+                    // ---- rare: the row holds a canonical match (one window in three on random sequence) and / or a byte
+                    //      outside ACGTacgt.  Canonical starts Cpos (those on the forward strand: CF) as lane positions. ----
+                    uint32_t Cpos = 0, CF = 0;
+                    if (__any_sync(0xFFFFFFFFu, badBits != 0)) {
+                        uint32_t H = 0;                            // the lane's match starts as a position bitmap
+#pragma unroll
+                        for (int tl = 0; tl < kProbes; ++tl) H |= ((acc[tl / G] >> (FW * (tl % G))) & PM) << (NPOS * tl);
+                        const uint4 fx = fixRow(H, X0, X1, reinterpret_cast<const uint8_t *>(laneAddr), W, L, true, COUNT);
+                        H = fx.x;
+                        nH = __popc(H); nF = 0;
+                        uint32_t bits = H;
+                        while (bits) {
+                            const uint32_t t = bits & (0u - bits);
+                            const uint32_t c = bfind(t);
+                            bits ^= t;
+                            const bool lowHalf = c < 16u;
+                            const uint32_t key = __funnelshift_r(lowHalf ? X0 : X1, lowHalf ? X1 : X2, 2u * c) & keyMask;
+                            const uint32_t g = ldsU8Flag(key);     // bit0 forward, bit1 canonical
+                            nF += g & 1u;
+                            if (g & 2u) { Cpos |= t; if (g & 1u) CF |= t; }
+                        }
+                        t1 = (fx.y & 0xFFFFu) + ((fx.y >> 16) << 10) + ((fx.z & 0xFFFFu) << 20);
+                        nVrow = __reduce_add_sync(0xFFFFFFFFu, fx.z >> 16);
+                        cls = nH | (nF << 10);
+                    } else if (cAny) {                             // divergent: the (usually single) lane that holds canonical starts
+#pragma unroll
+                        for (int k = 0; k < kAcc; ++k) {
+                            uint32_t m = acc[k] & MC;              // probes with a canonical match among their NPOS starts
+                            while (m) {
+                                const uint32_t b = bfind(m & (0u - m));
+                                m &= m - 1u;
+                                const uint32_t j = b / FW;
+                                const uint32_t pos0 = (k * G + j) * NPOS;
+                                uint32_t hits = (acc[k] >> (j * FW)) & PM;       // the valid starts of that probe: which one is it?
+                                while (hits) {
+                                    const uint32_t cpos = pos0 + bfind(hits & (0u - hits));
+                                    hits &= hits - 1u;
+                                    const bool lowHalf = cpos < 16u;
+                                    const uint32_t key = __funnelshift_r(lowHalf ? X0 : X1, lowHalf ? X1 : X2, 2u * cpos) & keyMask;
+                                    const uint32_t g = ldsU8Flag(key);           // bit0 forward, bit1 canonical
+                                    if (g & 2u) { Cpos |= 1u << cpos; if (g & 1u) CF |= 1u << cpos; }
+                                }
+                            }
+                        }
+                    }
+                    const uint32_t nC = __popc(Cpos);
+                    cls |= nC << 20;
+                    uint32_t incl;
+                    if (!__any_sync(0xFFFFFFFFu, nC > 1u)) {       // at most one per lane: the prefix is a ballot
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, nC != 0u);
+                        incl = __popc(bal & laneLt) + nC;
+                        nEmit = __popc(bal);
+                    } else {
+                        incl = warpInclusiveScan(nC, lane);
+                        nEmit = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    }
+                    uint32_t ovBase = kNoOverflow;
+                    if (nEmit > p.slotCap) {
+                        if (lane0) ovBase = takeOverflowChunk(p.ovCursor, p.ovChunk);
+                        ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
+                        if (lane0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wb + kOvOff + r * 4), "r"(ovBase) : "memory");
+                        ovRows |= 1u << r;
+                    }
+                    uint32_t o = incl - nC, bits = Cpos;
+                    const uint32_t relLane = rel + laneOff;
+                    while (bits) {
+                        const uint32_t t = bits & (0u - bits);
+                        const uint32_t c = bfind(t);
+                        bits ^= t;
+                        const uint32_t fl = static_cast<uint32_t>(kMatchCan) | ((CF & t) ? static_cast<uint32_t>(kMatchFwd) : 0u);
+                        storeRec(slotPtr, o++, ovBase, make_uint2(relLane + c, fl * 65536u + recHi));
+                    }
+                }
+                const uint32_t zMask = __ballot_sync(0xFFFFFFFFu, nH == 0u);
+                uint32_t sumA = 0;
+                if (COUNT) sumA = __reduce_add_sync(0xFFFFFFFFu, t1);
+                const uint32_t sumC = __reduce_add_sync(0xFFFFFFFFu, cls);
+                // ---- the row's results wait in shared memory for the unit epilogue (warp-uniform values, one wavefront) ----
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sumA), "r"(nVrow | (nEmit << 16)), "r"(sumC), "r"(zMask) : "memory");
+                laneAddr += W; rel += W;
+                slotPtr += slotBytes;
+            }
+        } else {
+#pragma unroll 1
+            for (uint32_t r = 0; r < nRows; ++r) {
+                const uint32_t remaining = itemLen - rel;
+                const bool partial = remaining < W;                 // warp-uniform: the last window of a contig
+                const uint32_t skew = static_cast<uint32_t>(laneAddr) & 15u;
+
+                // ---- 1. pack + validate the row that has landed, then re-arm the registers with the next row -------
+                uint32_t P0, P1, badBits;
+                {
+                    ValidAcc va;
+                    P0 = pack16v(c0, va);
+                    P1 = pack16v(c1, va);
+                    badBits = va.bad();                             // stale lanes past a short row hold bytes that were valid or already took the slow path
+                }
+                {
+                    const bool inUnit = r + 1 < nRows;
+                    const uint64_t na = inUnit ? laneAddr + W : nextAddr;
+                    const uint32_t nl = inUnit ? min(W, remaining - W) + 15u : nextLim;
+                    ldStream32If(c0, c1, na & ~static_cast<uint64_t>(15), laneOff, nl);
+                }
+
+                // ---- 2. remove the skew: X0 X1 X2 = the lane's 32 bases and the 16 that follow -------------------
+                const uint32_t sh = 2u * skew;
+                const uint32_t X0 = __funnelshift_r(P0, P1, sh);
+                const uint32_t X1 = __funnelshift_r(P1, __shfl_down_sync(0xFFFFFFFFu, P0, 1), sh);
+                const uint32_t X2 = __shfl_down_sync(0xFFFFFFFFu, X0, 1);      // lane 31: bases past any row, masked below
+                const bool anyBad = __any_sync(0xFFFFFFFFu, badBits != 0);
+
+                // ---- 3. one table entry per NPOS start positions (its H field) ---------------------------------
+                uint32_t H = 0;
+                {
+                    const uint32_t Xv[4] = {X0, X1, X2, 0u};
+#pragma unroll
+                    for (int tl = 0; tl < kProbes; ++tl) {
+                        const uint32_t e = ldsU8Idx(probeKey(Xv, tl)) & PM;
+                        H = e * (1u << (NPOS * tl)) + H;              // disjoint bit fields: add == or (bits >= 32 drop out)
+                    }
+                }
+                // ---- 4. matches never cross the window end (src/teloscope.cpp:439) --------------------------------
+                H &= fm.hm;
+
+                // ---- 5. A/C/G/T of the window: packed partial sums (nE = C + G, nO = G + T, nG, bases) -------------
+                uint32_t t1 = 0, t2 = fm.nv;
+                if (COUNT) {
+                    const uint32_t Y0 = X0 & fm.m0, Y1 = X1 & fm.m1;
+                    const uint32_t e = (Y0 & 0x55555555u) | ((Y1 << 1) & 0xAAAAAAAAu);    // code bit 0: C or G
+                    const uint32_t o = ((Y0 >> 1) & 0x55555555u) | (Y1 & 0xAAAAAAAAu);    // code bit 1: G or T
+                    t1 = __popc(e) + (__popc(o) << 16);
+                    t2 = __popc(e & o) + fm.nv;
+                }
+                if (partial || anyBad) {                            // rare, warp-uniform: the exact path redoes H, t1, t2
+                    const uint4 fx = fixRow(H, X0, X1, reinterpret_cast<const uint8_t *>(laneAddr), min(W, remaining), L, anyBad, COUNT);
+                    H = fx.x; t1 = fx.y; t2 = fx.z;
+                }
+                const uint32_t sum1 = COUNT ? __reduce_add_sync(0xFFFFFFFFu, t1) : 0u;
+                const uint32_t sum2 = __reduce_add_sync(0xFFFFFFFFu, t2);
+
+                // ---- 6. emission: every lane writes its own matches, in order, behind those of the lanes before it.
+                //      The match's 2L-bit key comes out of the lane's registers, the flag byte g (bit0 forward, bit1
+                //      canonical, bit7 canonical) goes into the record as it is and is summed per lane: a lane has at
+                //      most 32 matches, so forward + 2 canonical < 128 stays below the canonical count at bit 7. ----------
+                const uint32_t rowEnd = rel + min(W, remaining);
+                const bool rowHasTerm = rel <= T || rowEnd > termEnd;                               // warp-uniform
+                const bool rowAllTerm = rowEnd <= T + 1u || rel >= termEnd;                         // warp-uniform
+                const uint32_t nH = __popc(H);
+                const uint32_t zMask = __ballot_sync(0xFFFFFFFFu, nH == 0u);
+                const uint32_t incl = warpInclusiveScan(nH, lane);
+                const uint32_t wMatches = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const uint32_t relLane = rel + laneOff;
+                uint32_t acc = 0, rowNct = 0;
                 uint32_t ovBase = kNoOverflow;
                 if (wMatches > p.slotCap) {
-                    if (lane0) ovBase = atomicAdd(p.ovCursor, p.ovChunk);
+                    if (lane0) ovBase = takeOverflowChunk(p.ovCursor, p.ovChunk);
                     ovBase = __shfl_sync(0xFFFFFFFFu, ovBase, 0);
-                    if (lane0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wb + kRecOff + kRowsPerUnit * 16 + r * 4), "r"(ovBase) : "memory");
+                    if (lane0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wb + kOvOff + r * 4), "r"(ovBase) : "memory");
                     ovRows |= 1u << r;
                 }
-                uint32_t o = incl - nH;
-                uint32_t bits = H;
-                while (bits) {
-                    const uint32_t t = bits & (0u - bits);
-                    const uint32_t c = bfind(t);
-                    bits ^= t;
-                    const bool lowHalf = c < 16u;
-                    const uint32_t key = __funnelshift_r(lowHalf ? X0 : X1, lowHalf ? X1 : X2, 2u * c) & keyMask;
-                    const uint32_t g = ldsU8Flag(key);
-                    const uint32_t pos = relLane + c;
-                    const bool term = pos <= T || pos >= termEnd;
-                    const uint2 rec = make_uint2(pos, g * 65536u + (term ? static_cast<uint32_t>(kMatchTerm) << 16 : 0u) + recHi);
-                    if (o < p.slotCap) reinterpret_cast<uint2 *>(slotPtr)[o] = rec;
-                    else if (static_cast<uint64_t>(ovBase) + (o - p.slotCap) < p.ovCap)
-                        reinterpret_cast<uint2 *>(p.ovArena)[ovBase + (o - p.slotCap)] = rec;
-                    ++o;
-                    acc += g;
-                    if (term && !(g & 2u)) ++rowNct;
+                {
+                    uint32_t o = incl - nH;
+                    uint32_t bits = H;
+                    while (bits) {
+                        const uint32_t t = bits & (0u - bits);
+                        const uint32_t c = bfind(t);
+                        bits ^= t;
+                        const bool lowHalf = c < 16u;
+                        const uint32_t key = __funnelshift_r(lowHalf ? X0 : X1, lowHalf ? X1 : X2, 2u * c) & keyMask;
+                        const uint32_t g = ldsU8Flag(key);
+                        const uint32_t pos = relLane + c;
+                        const bool term = rowAllTerm || (rowHasTerm && (pos <= T || pos >= termEnd));
+                        storeRec(slotPtr, o++, ovBase, make_uint2(pos, g * 65536u + (term ? static_cast<uint32_t>(kMatchTerm) << 16 : 0u) + recHi));
+                        acc += g;
+                        if (term && !(g & 2u)) ++rowNct;
+                    }
+                    rowNct = __reduce_add_sync(0xFFFFFFFFu, rowNct);
                 }
-                rowNct = __reduce_add_sync(0xFFFFFFFFu, rowNct);
-            }
-            // forward + 2 canonical | canonical << 16, summed over the lanes
-            const uint32_t flagSum = __reduce_add_sync(0xFFFFFFFFu, (acc & 127u) | ((acc >> 7) << 16));
+                // forward + 2 canonical | canonical << 16, summed over the lanes
+                const uint32_t flagSum = __reduce_add_sync(0xFFFFFFFFu, (acc & 127u) | ((acc >> 7) << 16));
+                const uint32_t can = flagSum >> 16, fwd = (flagSum & 0xFFFFu) - 2u * can;
 
-            // ---- 7. the row's results wait in shared memory for the unit epilogue ----------------------------------
-            {   // all four values are warp-uniform: every lane stores them to the same address (one wavefront, no election)
-                const uint32_t w2 = wMatches | (rowNct << 12) | (rowAllTerm ? 0x80000000u : 0u);
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sum1), "r"(sum2), "r"(w2), "r"(flagSum) : "memory");
+                // ---- 7. the row's results wait in shared memory for the unit epilogue (the sparse rows' format) -------------
+                {
+                    const uint32_t sumA = (sum1 & 0xFFFFu) | ((sum1 >> 16) << 10) | ((sum2 & 0xFFFFu) << 20);
+                    const uint32_t sumC = wMatches | (fwd << 10) | (can << 20);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sumA), "r"((sum2 >> 16) | (wMatches << 16)), "r"(sumC), "r"(zMask) : "memory");
+                    if (lane0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wb + kNctOff + r * 4), "r"(rowNct) : "memory");
+                }
+                laneAddr += W; rel += W;
+                slotPtr += slotBytes;
             }
-            laneAddr += W; rel += W;
-            slotPtr += slotBytes;
         }
-        // ---- unit epilogue: lane r writes row r's window counters and slot bookkeeping (three 16-byte stores);
+        // ---- unit epilogue: lane r writes row r's window counters, zero-lane mask and slot bookkeeping;
         //      per-tile and per-item totals as a handful of atomics ------------------------------------------------
         __syncwarp();
-        uint32_t k2 = 0, k3 = 0;                               // all | canonical << 16, forward | terminal non-canonical << 16
+        uint32_t k1 = 0, k2 = 0, k3 = 0;                       // all | canonical << 16, forward | terminal non-canonical << 16, records
         if (lane < nRows) {
-            uint32_t s1, s2, w2, fs;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(s1), "=r"(s2), "=r"(w2), "=r"(fs) : "r"(wb + kRecOff + lane * 16));
+            uint32_t sA, sV, sC, zM;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sA), "=r"(sV), "=r"(sC), "=r"(zM) : "r"(wb + kRecOff + lane * 16));
             uint32_t ov = kNoOverflow;
-            if ((ovRows >> lane) & 1u) ov = lds32(wb + kRecOff + kRowsPerUnit * 16 + lane * 4);
-            const uint32_t all = w2 & 0xFFFu, can = fs >> 16, fwd = (fs & 0xFFFFu) - 2u * can;
-            const uint32_t nct = (w2 >> 31) ? all - can : (w2 >> 12) & 0xFFFu;
-            const uint32_t nE = s1 & 0xFFFFu, nO = s1 >> 16, nG = s2 & 0xFFFFu, nV = s2 >> 16;
-            uint4 *wp = p.windows + 2 * static_cast<size_t>(db.x + lane);
-            wp[0] = make_uint4(nV - nE - nO + nG, nE - nG, nG, nO - nG);        // A, C, G, T
-            wp[1] = make_uint4(can * L, (all - can) * L, fwd * L, (all - fwd) * L);
-            p.slotMeta[db.y + lane] = make_uint4(all, ov, can, nct);
-            k2 = all | (can << 16);
-            k3 = fwd | (nct << 16);
+            if ((ovRows >> lane) & 1u) ov = lds32(wb + kOvOff + lane * 4);
+            const uint32_t nct = sparse ? 0u : lds32(wb + kNctOff + lane * 4);
+            const uint32_t all = sC & 1023u, fwd = (sC >> 10) & 1023u, can = sC >> 20;
+            const uint32_t nE = sA & 1023u, nO = (sA >> 10) & 1023u, nG = sA >> 20, nV = sV & 0xFFFFu, emitted = sV >> 16;
+            const uint32_t cA = COUNT ? nV - nE - nO + nG : 0u, cC = COUNT ? nE - nG : 0u, cG = COUNT ? nG : 0u, cT = COUNT ? nO - nG : 0u;   // zeros without TLS_OUT_ACGT
+            if (p.windows16) {                                  // TLS_OUT_COMPACT: the 16-byte record at once (tls_window16)
+                p.windows16[db.x + lane] = make_uint4(cA | (cC << 16), cG | (cT << 16), (can * L) | (((all - can) * L) << 16),
+                                                      (fwd * L) | (((all - fwd) * L) << 16));
+            } else {
+                uint4 *wp = p.windows + 2 * static_cast<size_t>(db.x + lane);
+                wp[0] = make_uint4(cA, cC, cG, cT);                                   // A, C, G, T
+                wp[1] = make_uint4(can * L, (all - can) * L, fwd * L, (all - fwd) * L);
+            }
+            p.zeroLanes[db.x + lane] = zM;
+            if (emitted) p.slotMeta[db.y + lane] = make_uint4(emitted, ov, can, nct);   // the table was zeroed before the launch
+            k1 = all | (can << 16);
+            k2 = fwd | (nct << 16);
+            k3 = emitted;
         }
-        k2 = __reduce_add_sync(0xFFFFFFFFu, k2);               // <= 32 rows x 1002 per half: no carry between the halves
+        k1 = __reduce_add_sync(0xFFFFFFFFu, k1);               // <= 32 rows x 1002 per half: no carry between the halves
+        k2 = __reduce_add_sync(0xFFFFFFFFu, k2);
         k3 = __reduce_add_sync(0xFFFFFFFFu, k3);
-        const uint32_t uAll = k2 & 0xFFFFu, uCan = k2 >> 16, uFwd = k3 & 0xFFFFu, uNct = k3 >> 16;
+        const uint32_t uAll = k1 & 0xFFFFu, uCan = k1 >> 16, uFwd = k2 & 0xFFFFu, uNct = k2 >> 16, uRec = k3;
         if (uAll) {
             const uint32_t tile = db.y / kTileRows;
             if (lane < 3) {
-                const uint32_t v = lane == 0 ? uAll : lane == 1 ? uCan : uNct;
+                const uint32_t v = lane == 0 ? uRec : lane == 1 ? uCan : uNct;
                 if (v) atomicAdd(p.tileTot + static_cast<size_t>(lane) * p.nTilesAll + tile, v);
-            } else if (lane < 8) {
-                uint32_t *ic = reinterpret_cast<uint32_t *>(p.itemCounts + db.w);     // all, fwd, rev, can, nonCanTerm
-                const uint32_t v = lane == 3 ? uAll : lane == 4 ? uFwd : lane == 5 ? uAll - uFwd : lane == 6 ? uCan : uNct;
+            } else if (lane < 9) {
+                uint32_t *ic = reinterpret_cast<uint32_t *>(p.itemCounts + db.w);     // all, fwd, rev, can, nonCanTerm, records
+                const uint32_t v = lane == 3 ? uAll : lane == 4 ? uFwd : lane == 5 ? uAll - uFwd : lane == 6 ? uCan : lane == 7 ? uNct : uRec;
                 if (v) atomicAdd(ic + (lane - 3), v);
             }
         }
@@ -489,6 +576,8 @@ cudaError_t launchRowPlan(const DevRowRegion *regions, uint32_t nRegions, uint32
 
 size_t rowSmemBytes() { return kRowSmemTotal; }
 
+uint32_t rowNpos(uint32_t patLen) { return patLen >= 7 ? 2u : 3u; }
+
 bool rowConfigOk(const DevConfig &c) {
     return c.mode == 0 && c.nClasses == 1 && c.cls[0].direct != 0 && c.cls[0].len <= 7 && c.cls[0].len + c.npos <= 9 &&
            c.windowSize >= kRowMinWindow && c.windowSize <= static_cast<uint32_t>(kRowMaxLen) && c.step == c.windowSize;
@@ -498,11 +587,8 @@ cudaError_t launchRowScan(const RowParams &p, int grid, cudaStream_t stream) {
     const size_t smem = rowSmemBytes();
     const bool count = p.cfg.countAcgt != 0;
     void (*k)(const RowParams) = nullptr;
-    switch (p.cfg.npos) {
-        case 2: k = count ? rowScanKernel<2, true> : rowScanKernel<2, false>; break;
-        case 3: k = count ? rowScanKernel<3, true> : rowScanKernel<3, false>; break;
-        default: k = count ? rowScanKernel<4, true> : rowScanKernel<4, false>; break;
-    }
+    if (rowNpos(p.patLen) == 2) k = count ? rowScanKernel<2, true> : rowScanKernel<2, false>;
+    else k = count ? rowScanKernel<3, true> : rowScanKernel<3, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     k<<<grid, kRowThreads, smem, stream>>>(p);

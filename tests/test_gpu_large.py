@@ -71,5 +71,11 @@ def test_split_scan_compact_and_pageable_input_agree():
         for f in ("acgt", "can_cov", "noncan_cov", "fwd_cov", "rev_cov"):
             assert np.array_equal(got["windows"][f], want["windows"][f]), (i, f)
         assert got["n_canonical"] == len(want["canonical"])
+        assert one.n_fwd[i] == len(want["fwd"]) and one.n_rev[i] == len(want["rev"]), i
         for k in ("canonical", "noncanonical"):
-            assert np.array_equal(got[k]["pos"], want[k]["pos"]), (i, k)
+            for f in ("pos", "len", "fwd", "can"):
+                assert np.array_equal(got[k][f], want[k][f]), (i, k, f)
+        for k in ("terminal", "its"):                                    # blocks: every field the reference prints or classifies by
+            assert len(got[k]) == len(want[k]), (i, k)
+            for f in ("start", "len", "counts", "fwd_count", "can_count", "total_cov", "fwd_cov", "can_cov", "label", "valid_or"):
+                assert np.array_equal(got[k][f], want[k][f]), (i, k, f)

@@ -8,6 +8,8 @@ for t in test_gpu_sparse test_gpu_rows test_gpu_parity test_gpu_overlap test_gpu
 done
 TLS_TRACE=1 timeout 300 python scripts/trace_bench.py 1.0 > $out/trace.log 2>&1; tail -6 $out/trace.log
 TLS_COMPACT=1 timeout 300 python scripts/trace_bench.py 1.0 > $out/trace_compact.log 2>&1; tail -3 $out/trace_compact.log
+TLS_ROW_PARTS=1 TLS_COMPACT=1 timeout 300 python scripts/trace_bench.py 1.0 > $out/trace_compact_p1.log 2>&1; tail -3 $out/trace_compact_p1.log
+TLS_ROW_PARTS=2 TLS_COMPACT=1 timeout 300 python scripts/trace_bench.py 1.0 > $out/trace_compact_p2.log 2>&1; tail -3 $out/trace_compact_p2.log
 if [ "$2" = ncu ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Kernel' -s 24 -c 28 --csv \
     --log-file $out/launches.csv python scripts/trace_bench.py 1.0 > $out/trace_ncu.log 2>&1

@@ -166,6 +166,8 @@ struct tls_ctx {
     bool forceGeneral = false;               // TLS_FORCE_GENERAL=1 or a lean-kernel layout failure
     bool noRowKernel = false;                // TLS_NO_ROW_KERNEL=1: 1536-base-row lean kernel instead of the window-row kernel
     bool noReadKernel = false;               // TLS_NO_READ_KERNEL=1: reads through the general scan + block kernels (A/B tests)
+    bool zeroCopyWindows = false;            // TLS_OUT_COMPACT: the window-row kernel stores its 16-byte window records straight into the
+                                             // pinned host buffer (posted writes over PCIe during the scan): measured slower (scan 1.23 ms against 0.95 + copy), off unless TLS_WINDOWS_ZEROCOPY=1
     bool compact = false;                    // TLS_OUT_COMPACT: tls_window16 / tls_match8 results
     int rowParts = 3;                        // TLS_ROW_PARTS=n (1..8): launches of the window-row kernel on a large batch
     uint32_t rowMinWindows = kRowMinWindows; // TLS_ROW_MIN_WINDOWS=n: shortest contig (in windows) the window-row kernel takes
@@ -399,7 +401,7 @@ static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
         TLS_CUDA(cudaEventCreateWithFlags(&s.evCopyDone, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreate(&s.evScan0)); TLS_CUDA(cudaEventCreate(&s.evScan1)); TLS_CUDA(cudaEventCreate(&s.evFast1));
         TLS_CUDA(cudaEventCreate(&s.evAll0)); TLS_CUDA(cudaEventCreate(&s.evAll1));
-        TLS_CUDA(s.dCounters.reserve(64));
+        TLS_CUDA(s.dCounters.reserve(128));             // [64..96): work counters of the window-row launches
         TLS_CUDA(s.hCounters.reserve(64));
         TLS_CUDA(cudaHostAlloc(&s.hScan.p, 4096, cudaHostAllocMapped));
         s.hScan.cap = 4096;
@@ -408,6 +410,7 @@ static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
     ctx->forceGeneral = std::getenv("TLS_FORCE_GENERAL") != nullptr;
     ctx->noRowKernel = std::getenv("TLS_NO_ROW_KERNEL") != nullptr;
     ctx->noReadKernel = std::getenv("TLS_NO_READ_KERNEL") != nullptr;
+    ctx->zeroCopyWindows = std::getenv("TLS_WINDOWS_ZEROCOPY") != nullptr;
     if (const char *e = std::getenv("TLS_ROW_PARTS")) ctx->rowParts = std::min(static_cast<int>(Slot::kMaxParts), std::max(1, std::atoi(e)));
     if (const char *e = std::getenv("TLS_ROW_MIN_WINDOWS")) ctx->rowMinWindows = std::max(1, std::atoi(e));
     *out = ctx.release();
@@ -492,7 +495,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
     TLS_CUDA(s.dRedo.reserve(16 + static_cast<size_t>(redoCap) * 4));       // [0] count, [1] status, [4..] entries
     TLS_CUDA(cudaStreamWaitEvent(s.stream, s.evCopyDone, 0));               // a rerun must not clear what is still being copied
     TLS_CUDA(cudaMemsetAsync(s.dRedo.p, 0, 16, s.stream));
-    TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 64, s.stream));
+    TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 128, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dItemCounts.p, 0, std::max<size_t>(s.nItems, 1) * sizeof(DevItemCounts), s.stream));
     s.launches = 0;
     // window counters: the window-row kernel writes final records; the other scan kernels add into zeroed 32-byte counters
@@ -575,8 +578,13 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             if (ctx->compact) TLS_CUDA(s.dWindows16.reserve(s.nWindows * 16));
         }
         const uint8_t *winSrc = ctx->compact ? s.dWindows16.as<uint8_t>() : s.dWindows.as<uint8_t>();
+        // Compact records of a batch with window-row contigs: the kernels store them straight into the pinned host buffer
+        // (48 MB per 3 Gbp trickle over PCIe while the scan runs, nothing is left to copy afterwards).
+        const bool zeroCopy = anyWindows && ctx->compact && nRow && ctx->zeroCopyWindows;
+        void *win16Dst = s.dWindows16.p;
+        if (zeroCopy) TLS_CUDA(cudaHostGetDevicePointer(&win16Dst, s.hWindows.p, 0));
         if (anyWindows && ctx->compact && nRow && nRangeWindows) {
-            TLS_CUDA(launchPackWindowRanges(s.dWindows.as<uint32_t>(), s.dWindows16.p, dRanges, dRangePrefix, nRanges, nRangeWindows, s.stream));
+            TLS_CUDA(launchPackWindowRanges(s.dWindows.as<uint32_t>(), win16Dst, dRanges, dRangePrefix, nRanges, nRangeWindows, s.stream));
             s.launches++;
         }
         uint64_t winCopied = 0;
@@ -585,7 +593,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             f.seq = s.devSeq;
             f.indexRow = ctx->dIndex16.as<uint8_t>();
             f.two16 = 65536u;
-            f.windows16 = ctx->compact ? s.dWindows16.as<uint4>() : nullptr;
+            f.windows16 = ctx->compact ? static_cast<uint4 *>(win16Dst) : nullptr;
             f.zeroLanes = s.dZeroLanes.as<uint32_t>();
             f.flagTab = ctx->dFlags.as<uint8_t>() + cfg.cls[0].flagOffset;
             f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
@@ -600,7 +608,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             f.status = redo + 1;
             f.cfg = cfg;
             const uint32_t gridWarps = static_cast<uint32_t>(ctx->smCount) * kRowWarps;
-            const int parts = (anyWindows && nRow >= 16u * gridWarps) ? ctx->rowParts : 1;
+            const int parts = (anyWindows && !zeroCopy && nRow >= 16u * gridWarps) ? ctx->rowParts : 1;
             auto firstWindowOfUnit = [&](uint32_t u) {          // rowRegions are sorted by unit0
                 size_t lo = 0, hi = s.rowRegions.size();
                 while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (s.rowRegions[mid].unit0 <= u) lo = mid; else hi = mid; }
@@ -610,6 +618,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
                 const uint32_t uLo = static_cast<uint32_t>(static_cast<uint64_t>(nRow) * part / parts);
                 const uint32_t uHi = static_cast<uint32_t>(static_cast<uint64_t>(nRow) * (part + 1) / parts);
                 f.units = s.dRowTiles.as<DevRowUnit>() + uLo; f.nUnits = uHi - uLo;
+                f.unitCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 64) + part;
                 const int grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (f.nUnits + kRowWarps - 1) / kRowWarps));
                 TLS_CUDA(launchRowScan(f, grid, s.stream));
                 s.launches++;
@@ -634,7 +643,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         // window and per-item counters are final now: copy (the rest of) them home on the side stream
         TLS_CUDA(cudaEventRecord(s.evScanDone, s.stream));
         TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evScanDone, 0));
-        if (anyWindows && winCopied < s.nWindows)
+        if (anyWindows && !zeroCopy && winCopied < s.nWindows)
             TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * winRec, winSrc + winCopied * winRec,
                                      (s.nWindows - winCopied) * winRec, cudaMemcpyDeviceToHost, s.copyStream));
         if (s.mode != TLS_MODE_READS && s.nItems) {
@@ -757,7 +766,7 @@ static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
             TLS_CUDA(cudaMemcpyAsync(s.dItemInfo.p, h3, bInfo, cudaMemcpyHostToDevice, s.stream));
             TLS_CUDA(cudaMemcpyAsync(s.dItemLen.p, h3 + bInfo, bLen, cudaMemcpyHostToDevice, s.stream));
         }
-        TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 64, s.stream));      // [32] work counter, [36] status, [40] match total (u64)
+        TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 128, s.stream));      // [32] work counter, [36] status, [40] match total (u64)
         TLS_CUDA(cudaEventRecord(s.evAll0, s.stream));
         s.launches = 0;
         if (n && b->seq_on_device) {

@@ -261,13 +261,18 @@ struct Rescan {
         const uint32_t wStart = divWindow(*cfg, pos) * W;
         const uint32_t wLen = min(W, n - wStart);
         if (pos - wStart + L > wLen) return 0u;
+        uint32_t ch[7];
+#pragma unroll
+        for (uint32_t j = 0; j < 7; ++j) ch[j] = j < L ? __ldg(seq + pos + j) : static_cast<uint32_t>('A');   // all loads in flight at once (L <= 7)
         uint32_t key = 0;
-        for (uint32_t j = 0; j < L; ++j) {
-            const uint32_t ch = __ldg(seq + pos + j), up = ch & 0xDFu;
-            if (up != 'A' && up != 'C' && up != 'G' && up != 'T') return 0u;
-            key |= ((ch >> 1) & 3u) << (2 * j);
+        bool ok = true;
+#pragma unroll
+        for (uint32_t j = 0; j < 7; ++j) {
+            const uint32_t up = ch[j] & 0xDFu;
+            ok = ok && (up == 'A' || up == 'C' || up == 'G' || up == 'T');
+            if (j < L) key |= ((ch[j] >> 1) & 3u) << (2 * j);
         }
-        return __ldg(flagTab + key);
+        return ok ? __ldg(flagTab + key) : 0u;
     }
 };
 
@@ -377,6 +382,41 @@ __global__ void __launch_bounds__(128) terminalKernel(const BlockParams p) {
             if (__any_sync(0xFFFFFFFFu, atEdge) && !__any_sync(0xFFFFFFFFu, valid)) break;     // only records beyond the edge are left
             fetch(off + 32, recNext, validNext);
             uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && ((rec.y >> 16) & kMatchFwd) == want);
+            if (mask && !(inRun && run.nCan > 0u)) {
+                // No canonical match among these records and none in the open run: every run that ends here fails the Phase 1
+                // filter (canonicalCount > 0, src/teloscope.cpp:76-77), so only the run that is still open after the group
+                // matters (its start, extent and counts, all from ballots and reductions), and the first run start outside the
+                // terminal zone, which ends the walk (:98-102,117-121).
+                const bool mine = (mask >> lane) & 1u;
+                if (__ballot_sync(0xFFFFFFFFu, mine && ((rec.y >> 16) & kMatchCan)) == 0u) {
+                    const uint32_t below = mask & ((1u << lane) - 1u);
+                    uint32_t prevPos = __shfl_sync(0xFFFFFFFFu, rec.x, below ? 31 - __clz(below) : 0);
+                    if (!below) prevPos = run.prev;
+                    const uint32_t gapL = fromStart ? rec.x - prevPos : prevPos - rec.x;
+                    const bool isStart = mine && ((!below && !inRun) || gapL > c.maxMatchDist);
+                    const uint32_t starts = __ballot_sync(0xFFFFFFFFu, isStart);
+                    if (__ballot_sync(0xFFFFFFFFu, isStart && !inZone(rec.x)) != 0u) { inRun = false; done = true; break; }
+                    const uint32_t len = rec.y & 0xFFFFu;
+                    const int last = 31 - __clz(mask);
+                    const uint32_t lastPos = __shfl_sync(0xFFFFFFFFu, rec.x, last), lastLen = __shfl_sync(0xFFFFFFFFu, len, last);
+                    if (starts == 0u) {                              // everything continues the open run
+                        const uint32_t cntM = __popc(mask), lenSum = __reduce_add_sync(0xFFFFFFFFu, mine ? len : 0u);
+                        run.n += cntM; run.nFwd += want ? cntM : 0u; run.cov += lenSum; run.fwdCov += want ? lenSum : 0u;
+                        if (fromStart) run.end = lastPos + lastLen; else run.start = lastPos;
+                    } else {                                         // the run that is open after the group starts at its last run start
+                        const int hl = 31 - __clz(starts);
+                        const uint32_t seg = mask & ~((1u << hl) - 1u);
+                        const uint32_t firstPos = __shfl_sync(0xFFFFFFFFu, rec.x, hl), firstLen = __shfl_sync(0xFFFFFFFFu, len, hl);
+                        const uint32_t cntM = __popc(seg), lenSum = __reduce_add_sync(0xFFFFFFFFu, ((seg >> lane) & 1u) ? len : 0u);
+                        run.n = cntM; run.nFwd = want ? cntM : 0u; run.nCan = 0; run.cov = lenSum; run.fwdCov = want ? lenSum : 0u; run.canCov = 0;
+                        if (fromStart) { run.start = firstPos; run.end = lastPos + lastLen; }
+                        else { run.end = firstPos + firstLen; run.start = lastPos; }
+                        inRun = true;
+                    }
+                    run.prev = lastPos;
+                    continue;
+                }
+            }
             if (inRun && mask) {
                 // Inside a telomere the whole group of 32 continues the current run (every start-to-start gap
                 // <= maxMatchDist; the zone test only applies to run starts, src/teloscope.cpp:98-121): absorb it
@@ -509,11 +549,10 @@ __global__ void __launch_bounds__(256) itsSeedKernel(const BlockParams p, const 
 
 __global__ void __launch_bounds__(128) itsRunKernel(const BlockParams p, const unsigned long long *runStarts,
                                                     const unsigned int *runCount, uint32_t runCap) {
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t nRuns = min(*runCount, runCap);
-    if (gw >= nRuns) return;
     const DevConfig &c = p.cfg;
+    for (uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gw < nRuns; gw += (gridDim.x * blockDim.x) >> 5) {
     const unsigned long long e = runStarts[gw];
     const uint32_t item = static_cast<uint32_t>(e >> 32);
     const unsigned long long first = e & 0xFFFFFFFFull;
@@ -552,7 +591,7 @@ __global__ void __launch_bounds__(128) itsRunKernel(const BlockParams p, const u
         }
         open = bad == 0;
     }
-    if (lane != 0) return;
+    if (lane != 0) continue;
     const uint32_t len = end - start;
     // computeBlockLabel, include/teloscope.h:217-222 (float32)
     const float ratio = __fdiv_rn(__fmul_rn(__uint2float_rn(nFwd), 100.0f), __uint2float_rn(n));
@@ -563,6 +602,7 @@ __global__ void __launch_bounds__(128) itsRunKernel(const BlockParams p, const u
         b.canCount = nCan; b.totalCov = cov; b.fwdCov = fwdCov; b.canCov = canCov;
         b.validOr = 1; b.label = label; b.kind = 1;
         emitBlock(p, b);
+    }
     }
 }
 
@@ -630,11 +670,10 @@ __global__ void __launch_bounds__(256) itsChainKernel(const uint8_t *conn, unsig
 
 __global__ void __launch_bounds__(128) itsWalkKernel(const BlockParams p, const uint32_t *canIdx, const uint8_t *conn,
                                                      const unsigned long long *chainStarts, const unsigned int *chainCount, uint32_t chainCap) {
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t nChains = min(*chainCount, chainCap);
-    if (gw >= nChains) return;
     const DevConfig &c = p.cfg;
+    for (uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gw < nChains; gw += (gridDim.x * blockDim.x) >> 5) {
     unsigned long long j = chainStarts[gw];
     unsigned long long jEnd = j;
     while (conn[jEnd]) ++jEnd;                                        // last canonical match of the chain (conn of the batch's last is 0)
@@ -704,6 +743,7 @@ __global__ void __launch_bounds__(128) itsWalkKernel(const BlockParams p, const 
         // ---- the chain's next canonical match behind this run ----
         ++j;
         while (j <= jEnd && recs[canIdx[j]].x <= prev) ++j;
+    }
     }
 }
 
@@ -894,7 +934,7 @@ cudaError_t launchIts(const BlockParams &p, const uint32_t *canIdx, unsigned lon
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // the number of runs is only known on the device: enough warps for the capacity, surplus warps exit
-    const unsigned long long warps = std::min<unsigned long long>(runCap, nCan / 4 + 1);
+    const unsigned long long warps = std::min<unsigned long long>(std::min<unsigned long long>(runCap, nCan / 4 + 1), 148 * 32);
     itsRunKernel<<<static_cast<unsigned int>((warps * 32 + 127) / 128), 128, 0, s>>>(p, runStarts, runCount, runCap);
     return cudaGetLastError();
 }
@@ -907,7 +947,7 @@ cudaError_t launchItsRows(const BlockParams &p, const uint32_t *canIdx, unsigned
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // the number of chains is only known on the device: enough warps for the capacity, surplus warps exit
-    const unsigned long long warps = std::min<unsigned long long>(chainCap, nCan / 4 + 1);
+    const unsigned long long warps = std::min<unsigned long long>(std::min<unsigned long long>(chainCap, nCan / 4 + 1), 148 * 32);
     itsWalkKernel<<<static_cast<unsigned int>((warps * 32 + 127) / 128), 128, 0, s>>>(p, canIdx, conn, chainStarts, chainCount, chainCap);
     return cudaGetLastError();
 }

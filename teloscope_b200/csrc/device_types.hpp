@@ -242,6 +242,7 @@ struct RowParams {
     uint32_t *zeroLanes;           // [nWindows]: bit l = lane l (row positions 32 l .. 32 l + 31) holds no match start
     DevItemCounts *itemCounts;
     unsigned int *status;          // set to 1 when the shared memory layout assumption fails
+    unsigned int *unitCursor;      // work counter of this launch, zeroed before it
     DevConfig cfg;
 };
 

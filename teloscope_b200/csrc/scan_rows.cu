@@ -53,11 +53,12 @@ namespace {
 // kWindowBase bytes into it on sm_100 (checked at run time: status 1 otherwise), so every address below
 // is a compile-time constant and goes into the instruction as an immediate. -------------------------------
 constexpr uint32_t kWindowBase = 0x400;
-constexpr uint32_t kWarpBlk = kRowsPerUnit <= 8 ? 256 : (kRowsPerUnit <= 16 ? 512 : 1024);  // per warp: row results of the unit in flight
-constexpr uint32_t kRecOff = 0;                            //   16 bytes of results per row, then per row: overflow base (u32), terminal non-canonical count (u32)
-constexpr uint32_t kOvOff = kRowsPerUnit * 16;
+constexpr uint32_t kWarpBlk = kRowsPerUnit <= 8 ? 512 : (kRowsPerUnit <= 16 ? 1024 : 2048);  // per warp: row results of the unit in flight
+constexpr uint32_t kRecOff = 0;                            //   16 bytes of results per row, then per row: overflow base (u32), terminal non-canonical
+constexpr uint32_t kOvOff = kRowsPerUnit * 16;             //   count (u32), and the registers of the lane that holds the row's canonical matches (32 bytes)
 constexpr uint32_t kNctOff = kRowsPerUnit * 20;
-static_assert(kRowsPerUnit * 24 <= kWarpBlk, "per-warp block");
+constexpr uint32_t kStashOff = kRowsPerUnit * 32;
+static_assert(kRowsPerUnit * 64 <= kWarpBlk, "per-warp block");
 constexpr uint32_t kWarpBase = kWindowBase;                               // warp blocks
 constexpr uint32_t kFlagBase = kWarpBase + kRowWarps * kWarpBlk;          // 16 KiB flag table
 constexpr uint32_t kIdxBase = 0x10000u;                                   // 64 KiB 8-mer table (one byte per key)
@@ -134,7 +135,6 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     const uint32_t L = p.patLen, W = p.cfg.windowSize, T = p.cfg.terminalLimit;
     const uint32_t keyMask = (1u << (2 * L)) - 1u;
     const uint32_t recHi = L | (static_cast<uint32_t>(kRegionAccounted) << 24);    // DevMatch {pos, len:16, flags:8, region:8}
-    const uint32_t totalWarps = gridDim.x * kRowWarps;
     const uint32_t nUnits = p.nUnits;
     const uint32_t laneOff = lane * kRowSpan;
     const uint64_t seqBase = reinterpret_cast<uint64_t>(p.seq);
@@ -215,7 +215,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
             reinterpret_cast<uint2 *>(p.ovArena)[ovBase + (o - p.slotCap)] = rec;
     };
 
-    uint32_t u = blockIdx.x * kRowWarps + warp;
+    // Units are handed out by a counter (a dense unit of a telomere cap costs several sparse ones: a static split leaves
+    // SMs idle at the end).  A warp always knows its next unit one unit ahead (its first row is loaded during the current
+    // unit's last row) and has the index of the one after that on order.
+    uint32_t u, uNext, uPending = 0;
+    if (lane0) u = atomicAdd(p.unitCursor, 2u);
+    u = __shfl_sync(0xFFFFFFFFu, u, 0);
+    uNext = u + 1;
     if (u >= nUnits) return;
     uint4 da, db;
     loadUnit(u, da, db);
@@ -228,13 +234,17 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
         const uint32_t itemLen = da.w;
         const uint32_t termEnd = itemLen > T ? itemLen - T : 0u;   // "terminal": pos <= T || pos >= n - T (src/teloscope.cpp:403-406,451-459)
         const uint32_t nRows = db.z;
-        const uint32_t uNext = u + totalWarps;
+        if (lane0) uPending = atomicAdd(p.unitCursor, 1u);
         uint64_t nextAddr = 0;                                 // the lane's first base of the first row of this warp's next unit
         uint32_t nextLim = 0;                                  // its length + 15 (lanes below it load), 0: there is none
         if (uNext < nUnits) {
             const uint4 na = __ldg(reinterpret_cast<const uint4 *>(p.units + uNext));
             nextAddr = seqBase + (static_cast<uint64_t>(na.x) | (static_cast<uint64_t>(na.y) << 32)) + laneOff;
             nextLim = min(W, na.w - na.z) + 15u;
+            if (kRowPrefetch && laneOff < nextLim) {            // its first two rows: into L2 a whole unit ahead
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nextAddr));
+                if (na.w - na.z > W) asm volatile("prefetch.global.L2 [%0];" ::"l"(nextAddr + W));
+            }
         }
         uint8_t *slotPtr = reinterpret_cast<uint8_t *>(p.slots) + static_cast<size_t>(db.y) * slotBytes;
         uint32_t ovRows = 0;                                   // bit r: row r spilled into an overflow chunk
@@ -253,13 +263,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                     P1 = pack16v(c1, va);
                     badBits = va.bad();
                 }
+                const uint64_t laneAddrNext = laneAddr + W;
                 {
-                    const bool inUnit = r + 1 < static_cast<uint32_t>(kRowsPerUnit);
-                    const uint64_t na = inUnit ? laneAddr + W : nextAddr;
-                    const uint32_t nl = inUnit ? W + 15u : nextLim;
+                    uint64_t na = laneAddrNext;
+                    uint32_t nl = W + 15u;
+                    if (r + 1 == static_cast<uint32_t>(kRowsPerUnit)) { na = nextAddr; nl = nextLim; }
                     ldStream32If(c0, c1, na & ~static_cast<uint64_t>(15), laneOff, nl);
-                    // the row after that one: into L2 now, so that its register load next iteration is an L2 hit
-                    if (kRowPrefetch && laneOff < W) asm volatile("prefetch.global.L2 [%0];" ::"l"((na + W) & ~static_cast<uint64_t>(15)));
+                    // the row after that one (inside this unit): into L2 now, so that its register load next iteration is an L2 hit
+                    if (kRowPrefetch && r + 2 < static_cast<uint32_t>(kRowsPerUnit)) asm volatile("prefetch.global.L2 [%0];" ::"l"(laneAddrNext + W));
                 }
                 // ---- 2. remove the skew ---------------------------------------------------------------------------
                 const uint32_t sh = 2u * skew;
@@ -298,12 +309,23 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 }
                 uint32_t cls = nH | (nF << 10);
                 uint32_t nVrow = W;
-                uint32_t nEmit = 0;
-                if (__any_sync(0xFFFFFFFFu, (badBits | cAny) != 0)) {
-                    // ---- rare: the row holds a canonical match (one window in three on random sequence) and / or a byte
-                    //      outside ACGTacgt.  Canonical starts Cpos (those on the forward strand: CF) as lane positions. ----
+                uint32_t info = 0;                                 // canonical matches of the row: count, or bit 31 = left to the unit epilogue
+                if (__any_sync(0xFFFFFFFFu, (badBits | cAny) != 0u)) {
+                const uint32_t cLanes = __ballot_sync(0xFFFFFFFFu, cAny != 0u), badLanes = __ballot_sync(0xFFFFFFFFu, badBits != 0u);
+                if (badLanes == 0u && (cLanes & (cLanes - 1u)) == 0u) {
+                    // ---- canonical matches in ONE lane (one window in three on random sequence holds one): the lane leaves its
+                    //      registers in shared memory; the unit epilogue resolves all rows of the unit at once, one row per lane ----
+                    if (cAny) {
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kStashOff + r * 32), "r"(acc[0]), "r"(acc[1]), "r"(acc[2]), "r"(lane) : "memory");
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kStashOff + r * 32 + 16), "r"(X0), "r"(X1), "r"(X2), "r"(0u) : "memory");
+                    }
+                    info = 0x80000000u;
+                } else {
+                    uint32_t nEmit = 0;
+                    // ---- rarer: canonical matches in several lanes and / or a byte outside ACGTacgt.
+                    //      Canonical starts Cpos (those on the forward strand: CF) as lane positions. ----
                     uint32_t Cpos = 0, CF = 0;
-                    if (__any_sync(0xFFFFFFFFu, badBits != 0)) {
+                    if (badLanes != 0u) {
                         uint32_t H = 0;                            // the lane's match starts as a position bitmap
 #pragma unroll
                         for (int tl = 0; tl < kProbes; ++tl) H |= ((acc[tl / G] >> (FW * (tl % G))) & PM) << (NPOS * tl);
@@ -346,7 +368,6 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                         }
                     }
                     const uint32_t nC = __popc(Cpos);
-                    cls |= nC << 20;
                     uint32_t incl;
                     if (!__any_sync(0xFFFFFFFFu, nC > 1u)) {       // at most one per lane: the prefix is a ballot
                         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, nC != 0u);
@@ -372,14 +393,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                         const uint32_t fl = static_cast<uint32_t>(kMatchCan) | ((CF & t) ? static_cast<uint32_t>(kMatchFwd) : 0u);
                         storeRec(slotPtr, o++, ovBase, make_uint2(relLane + c, fl * 65536u + recHi));
                     }
+                    info = nEmit;
+                }
                 }
                 const uint32_t zMask = __ballot_sync(0xFFFFFFFFu, nH == 0u);
                 uint32_t sumA = 0;
                 if (COUNT) sumA = __reduce_add_sync(0xFFFFFFFFu, t1);
-                const uint32_t sumC = __reduce_add_sync(0xFFFFFFFFu, cls);
+                const uint32_t sumC = __reduce_add_sync(0xFFFFFFFFu, cls) | (nVrow << 20);
                 // ---- the row's results wait in shared memory for the unit epilogue (warp-uniform values, one wavefront) ----
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sumA), "r"(nVrow | (nEmit << 16)), "r"(sumC), "r"(zMask) : "memory");
-                laneAddr += W; rel += W;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sumA), "r"(sumC), "r"(zMask), "r"(info) : "memory");
+                laneAddr = laneAddrNext; rel += W;
                 slotPtr += slotBytes;
             }
         } else {
@@ -485,8 +508,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 // ---- 7. the row's results wait in shared memory for the unit epilogue (the sparse rows' format) -------------
                 {
                     const uint32_t sumA = (sum1 & 0xFFFFu) | ((sum1 >> 16) << 10) | ((sum2 & 0xFFFFu) << 20);
-                    const uint32_t sumC = wMatches | (fwd << 10) | (can << 20);
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sumA), "r"((sum2 >> 16) | (wMatches << 16)), "r"(sumC), "r"(zMask) : "memory");
+                    const uint32_t sumC = wMatches | (fwd << 10) | ((sum2 >> 16) << 20);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wb + kRecOff + r * 16), "r"(sumA), "r"(sumC), "r"(zMask), "r"(can) : "memory");
                     if (lane0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(wb + kNctOff + r * 4), "r"(rowNct) : "memory");
                 }
                 laneAddr += W; rel += W;
@@ -498,13 +521,50 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
         __syncwarp();
         uint32_t k1 = 0, k2 = 0, k3 = 0;                       // all | canonical << 16, forward | terminal non-canonical << 16, records
         if (lane < nRows) {
-            uint32_t sA, sV, sC, zM;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sA), "=r"(sV), "=r"(sC), "=r"(zM) : "r"(wb + kRecOff + lane * 16));
+            uint32_t sA, sC, zM, info;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sA), "=r"(sC), "=r"(zM), "=r"(info) : "r"(wb + kRecOff + lane * 16));
             uint32_t ov = kNoOverflow;
             if ((ovRows >> lane) & 1u) ov = lds32(wb + kOvOff + lane * 4);
             const uint32_t nct = sparse ? 0u : lds32(wb + kNctOff + lane * 4);
-            const uint32_t all = sC & 1023u, fwd = (sC >> 10) & 1023u, can = sC >> 20;
-            const uint32_t nE = sA & 1023u, nO = (sA >> 10) & 1023u, nG = sA >> 20, nV = sV & 0xFFFFu, emitted = sV >> 16;
+            uint32_t can = info & 0x7FFFFFFFu;
+            if (info >> 31) {
+                // the canonical matches of this row sit in one lane of the scan: its accumulators and packed bases are in the
+                // stash.  Every row of the unit is resolved here at once (this lane = this row): records in position order.
+                uint32_t a[kAcc], src, Y0, Y1, Y2, pad;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(src) : "r"(wb + kStashOff + lane * 32));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(Y0), "=r"(Y1), "=r"(Y2), "=r"(pad) : "r"(wb + kStashOff + lane * 32 + 16));
+                uint2 *slot = reinterpret_cast<uint2 *>(p.slots) + static_cast<size_t>(db.y + lane) * p.slotCap;
+                const uint32_t relSrc = da.z + lane * W + src * kRowSpan;
+                can = 0;
+#pragma unroll
+                for (int k = 0; k < kAcc; ++k) {
+                    uint32_t m = a[k] & MC;                        // probes with a canonical match among their NPOS starts
+                    while (m) {
+                        const uint32_t b = bfind(m & (0u - m));
+                        m &= m - 1u;
+                        const uint32_t j = b / FW;
+                        const uint32_t pos0 = (k * G + j) * NPOS;
+                        const uint32_t field = a[k] >> (j * FW);
+                        uint32_t hits = field & PM;                // the valid starts of that probe
+                        if ((hits & (hits - 1u)) == 0u) {          // one: it is the canonical one, its strand is in the F field
+                            const uint32_t fl = static_cast<uint32_t>(kMatchCan) | (((field >> NPOS) & hits) ? static_cast<uint32_t>(kMatchFwd) : 0u);
+                            if (hits) slot[can++] = make_uint2(relSrc + pos0 + bfind(hits), fl * 65536u + recHi);
+                            continue;
+                        }
+                        while (hits) {
+                            const uint32_t cpos = pos0 + bfind(hits & (0u - hits));
+                            hits &= hits - 1u;
+                            const bool lowHalf = cpos < 16u;
+                            const uint32_t key = __funnelshift_r(lowHalf ? Y0 : Y1, lowHalf ? Y1 : Y2, 2u * cpos) & keyMask;
+                            const uint32_t g = ldsU8Flag(key);     // bit0 forward, bit1 canonical
+                            if (g & 2u) slot[can++] = make_uint2(relSrc + cpos, (g & 3u) * 65536u + recHi);
+                        }
+                    }
+                }
+            }
+            const uint32_t all = sC & 1023u, fwd = (sC >> 10) & 1023u, nV = sC >> 20;
+            const uint32_t emitted = sparse ? can : all;
+            const uint32_t nE = sA & 1023u, nO = (sA >> 10) & 1023u, nG = sA >> 20;
             const uint32_t cA = COUNT ? nV - nE - nO + nG : 0u, cC = COUNT ? nE - nG : 0u, cG = COUNT ? nG : 0u, cT = COUNT ? nO - nG : 0u;   // zeros without TLS_OUT_ACGT
             if (p.windows16) {                                  // TLS_OUT_COMPACT: the 16-byte record at once (tls_window16)
                 p.windows16[db.x + lane] = make_uint4(cA | (cC << 16), cG | (cT << 16), (can * L) | (((all - can) * L) << 16),
@@ -537,6 +597,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
         }
         if (uNext >= nUnits) break;
         u = uNext;
+        uNext = __shfl_sync(0xFFFFFFFFu, uPending, 0);
         loadUnit(u, da, db);
     }
 }

@@ -45,46 +45,11 @@
 #include <thread>
 #include <vector>
 
-#include "teloscope_b200.h"
+#include "pipeline.hpp"
+
+using namespace tlsb;
 
 namespace {
-
-struct Options {
-    std::string inSequence, inSequenceName, inSequencePrefix, outRoute;
-    bool outRouteSet = false;
-    std::string canonicalFwd = "CCCTAA", canonicalRev = "TTAGGG";
-    std::vector<std::string> rawPatterns;
-    bool hasInputPatterns = false;
-    uint32_t windowSize = 1000, step = 1000, terminalLimit = 50000;
-    uint8_t editDistance = 1;
-    unsigned short maxMatchDist = 50, minBlockLen = 300, maxBlockDist = 500, minBlockCounts = 2;
-    float minBlockDensity = 0.5f;
-    bool outWinRepeats = false, outGC = false, outEntropy = false, outMatches = false, outITS = false;
-    bool ultraFastMode = true, manualCuration = false;
-    bool fastqSubset = false, outFasta = false, minBlockLenSet = false;
-    int cmdFlag = 0;
-    unsigned threads = 0;                       // -j: host threads of the parse / formatting stages (0 = all cores)
-};
-
-// Leaves without running static destructors: the CUDA context may still be coming up on its own thread, and tearing
-// the runtime down underneath it crashes.  Everything written so far is flushed first.
-[[noreturn]] void quit(int status) {
-    fflush(stdout);
-    fflush(stderr);
-    _exit(status);
-}
-[[noreturn]] void die(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
-void die(const char *fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vfprintf(stderr, fmt, ap);
-    va_end(ap);
-    quit(EXIT_FAILURE);
-}
-[[noreturn]] void unsupported(const char *what) {
-    fprintf(stderr, "teloscope-b200: %s is not part of the B200 FASTA pipeline (use the reference binary for it).\n", what);
-    quit(2);
-}
 
 std::string upper(std::string s) {
     for (char &c : s) c = static_cast<char>(std::toupper(static_cast<unsigned char>(c)));
@@ -156,7 +121,7 @@ Options parseArgs(int argc, char **argv) {
                 if (longOptions[idx].flag) break;                      // --verbose / --cmd
                 if (!strcmp(name, "plot-report")) unsupported("--plot-report");
                 if (!strcmp(name, "fastq-subset")) { o.fastqSubset = true; break; }
-                if (!strcmp(name, "bam-subset")) unsupported("--bam-subset");
+                if (!strcmp(name, "bam-subset")) { o.bamSubset = true; break; }
                 unsupported("record filtering (--include-bed / --exclude-bed / --include-prefix / --exclude-prefix)");
             }
             case 1:
@@ -294,14 +259,7 @@ struct PathRec {
 };
 struct Item { uint32_t path; uint64_t absPos, offset; uint32_t len; };
 
-// Input bytes: a plain file is mapped (no copy), a gzip file is inflated by zlib into memory.
-struct InputData {
-    const char *p = nullptr;
-    size_t n = 0;
-    std::string owned;
-    void *map = nullptr;
-    ~InputData() { if (map) munmap(map, n); }
-};
+// a plain file is mapped (no copy), a gzip file is inflated by zlib into memory
 void loadInput(const std::string &path, InputData &in) {
     const int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) die("Error: Cannot open input file '%s'.\n", path.c_str());
@@ -331,19 +289,6 @@ void loadInput(const std::string &path, InputData &in) {
     }
     gzclose(f);
     in.p = in.owned.data(); in.n = in.owned.size();
-}
-
-// dynamic parallel loop over [0, n): the host side of the pipeline (parse, formatting) is per-record / per-chunk work
-template <class F>
-void parallelFor(size_t n, unsigned threads, F f) {
-    if (n == 0) return;
-    threads = static_cast<unsigned>(std::min<size_t>(std::max(1u, threads), n));
-    if (threads == 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
-    std::atomic<size_t> next{0};
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < threads; ++t)
-        pool.emplace_back([&]() { for (size_t i; (i = next.fetch_add(1)) < n;) f(i); });
-    for (auto &th : pool) th.join();
 }
 
 // bit i of the result: byte i of the 16 at p is one of N n X x (gap) / is '\n'
@@ -597,22 +542,6 @@ void blockRow(std::string &s, const std::string &header, const tls_block &b, uin
     s.push_back('\t'); appendU64(s, pathSize);
 }
 
-struct StageTimer {                       // TLS_PIPE_TRACE=1: wall time of the pipeline stages on stderr
-    bool on = getenv("TLS_PIPE_TRACE") != nullptr;
-    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
-    void mark(const char *what) {
-        if (!on) return;
-        const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[pipe] %-28s %8.1f ms  (total %8.1f ms)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
-                std::chrono::duration<double, std::milli>(now - t0).count());
-        last = now;
-    }
-};
-
-void check(int rc, const char *what) {
-    if (rc != TLS_OK) die("Error: %s failed: %s\n", what, tls_last_error());
-}
-
 // ---- --fastq-subset (Input::readFastqSubset, src/input.cpp:735-833; readFastqRecord :113-138) -----------------------------
 // Reads are taken four lines at a time (blank lines before a header are skipped), their sequence lines go to the
 // GPU as TLS_MODE_READS batches (ReadTelomereFilter::matches: trailing '\r' dropped, whole read terminal, -l 42 unless
@@ -755,10 +684,17 @@ int main(int argc, char **argv) {
         return 0;
     }
     Options o = parseArgs(argc, argv);
-    if (o.inSequence.empty()) die("Error: No input file provided. Use -f or pass as positional argument.\n");
+    if (o.inSequence.empty() && o.bamSubset && !isatty(STDIN_FILENO)) {      // pipe-only invocation, src/main.cpp:567-573
+        o.inSequenceName = "stdin";
+        if (o.outRoute.empty()) o.outRoute = ".";
+    } else if (o.inSequence.empty()) {
+        if (!isatty(STDIN_FILENO)) unsupported("input on stdin (other than --bam-subset)");
+        die("Error: No input file provided. Use -f or pass as positional argument.\n");
+    }
+    if (o.fastqSubset && o.bamSubset) die("Error: --fastq-subset and --bam-subset are mutually exclusive.\n");
     if (o.step > o.windowSize) die("Error: Step size (%d) cannot be larger than window size (%d).\n", o.step, o.windowSize);
     if (o.step < o.windowSize) fprintf(stderr, "Sliding with window size (%d) and step size (%d).\n", o.windowSize, o.step);
-    if (!o.fastqSubset) {   // writable check, src/main.cpp:611-622
+    if (!o.fastqSubset && !o.bamSubset) {   // writable check, src/main.cpp:611-622
         const std::string testPath = o.outRoute + "/.teloscope_write_test";
         std::ofstream test(testPath);
         if (!test.is_open()) die("Error: Output directory '%s' is not writable.\n", o.outRoute.c_str());
@@ -798,10 +734,10 @@ int main(int argc, char **argv) {
         add(o.outMatches, "genome-wide matches"); add(o.outITS, "ITS blocks");
         if (!summary.empty()) fprintf(stderr, "Outputs: %s.\n", summary.c_str());
     }
-    if (o.fastqSubset && (o.outFasta || o.outWinRepeats || o.outGC || o.outEntropy || o.outMatches || o.outITS || o.manualCuration))
+    if ((o.fastqSubset || o.bamSubset) && (o.outFasta || o.outWinRepeats || o.outGC || o.outEntropy || o.outMatches || o.outITS || o.manualCuration))
         fprintf(stderr, "Warning: assembly output flags are ignored in read subset mode.\n");
     if (o.cmdFlag) {
-        FILE *cs = o.fastqSubset ? stderr : stdout;
+        FILE *cs = (o.fastqSubset || o.bamSubset) ? stderr : stdout;
         for (int i = 0; i < argc; ++i) fprintf(cs, "%s ", argv[i]);
         fprintf(cs, "\n");
     }
@@ -818,6 +754,7 @@ int main(int argc, char **argv) {
     cfg.min_block_counts = o.minBlockCounts; cfg.min_block_density = o.minBlockDensity;
     cfg.outputs = ((o.outGC || o.outEntropy) ? 1u * TLS_OUT_ACGT : 0u) | (o.outMatches ? 1u * TLS_OUT_MATCHES : 0u) | TLS_OUT_ITS;
     if (o.fastqSubset) return runFastqSubset(o, cfg);
+    if (o.bamSubset) return runBamSubset(o, cfg);
     tls_ctx *ctx = nullptr;
     int ctxRc = TLS_OK;
     std::string ctxErr;

@@ -259,38 +259,6 @@ struct PathRec {
 };
 struct Item { uint32_t path; uint64_t absPos, offset; uint32_t len; };
 
-// a plain file is mapped (no copy), a gzip file is inflated by zlib into memory
-void loadInput(const std::string &path, InputData &in) {
-    const int fd = open(path.c_str(), O_RDONLY);
-    if (fd < 0) die("Error: Cannot open input file '%s'.\n", path.c_str());
-    unsigned char magic[2] = {0, 0};
-    const ssize_t got = pread(fd, magic, 2, 0);
-    struct stat st {};
-    fstat(fd, &st);
-    if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) && st.st_size > 0) {
-        void *m = mmap(nullptr, static_cast<size_t>(st.st_size), PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
-        if (m != MAP_FAILED) {
-            madvise(m, static_cast<size_t>(st.st_size), MADV_SEQUENTIAL);
-            in.map = m; in.p = static_cast<const char *>(m); in.n = static_cast<size_t>(st.st_size);
-            close(fd);
-            return;
-        }
-    }
-    close(fd);
-    gzFile f = gzopen(path.c_str(), "rb");
-    if (!f) die("Error: Cannot open input file '%s'.\n", path.c_str());
-    gzbuffer(f, 1 << 20);
-    std::vector<char> buf(1 << 24);
-    for (;;) {
-        const int n = gzread(f, buf.data(), static_cast<unsigned>(buf.size()));
-        if (n < 0) die("Error: Cannot read input file '%s'.\n", path.c_str());
-        if (n == 0) break;
-        in.owned.append(buf.data(), static_cast<size_t>(n));
-    }
-    gzclose(f);
-    in.p = in.owned.data(); in.n = in.owned.size();
-}
-
 // bit i of the result: byte i of the 16 at p is one of N n X x (gap) / is '\n'
 inline void classify16(const char *p, unsigned &gap, unsigned &nl) {
     const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
@@ -683,6 +651,7 @@ int main(int argc, char **argv) {
         printf("teloscope-b200 input.[fa|fa.gz] [options]\nUse -h for additional help.\n");
         return 0;
     }
+    if (argc == 4 && !strcmp(argv[1], "--gfa-normalize")) return normalizeGfa(argv[2], argv[3]);   // developer / test entry: graph in, GFA 1.2 out, no scan
     Options o = parseArgs(argc, argv);
     if (o.inSequence.empty() && o.bamSubset && !isatty(STDIN_FILENO)) {      // pipe-only invocation, src/main.cpp:567-573
         o.inSequenceName = "stdin";
@@ -755,6 +724,7 @@ int main(int argc, char **argv) {
     cfg.outputs = ((o.outGC || o.outEntropy) ? 1u * TLS_OUT_ACGT : 0u) | (o.outMatches ? 1u * TLS_OUT_MATCHES : 0u) | TLS_OUT_ITS;
     if (o.fastqSubset) return runFastqSubset(o, cfg);
     if (o.bamSubset) return runBamSubset(o, cfg);
+    if (isGfaPath(o.inSequence)) return runGfa(o, cfg);
     tls_ctx *ctx = nullptr;
     int ctxRc = TLS_OK;
     std::string ctxErr;
@@ -773,7 +743,7 @@ int main(int argc, char **argv) {
         InputData in;
         loadInput(o.inSequence, in);
         timer.mark("read file");
-        if (in.n > 1 && (in.p[0] == 'H' || in.p[0] == 'S') && in.p[1] == '\t') { ctxThread.join(); unsupported("GFA input"); }
+        if (in.n > 1 && (in.p[0] == 'H' || in.p[0] == 'S') && in.p[1] == '\t') { ctxThread.join(); unsupported("GFA content in a file that is not named *.gfa / *.gfa.gz"); }
         if (in.n > 0 && in.p[0] == '@') { ctxThread.join(); unsupported("FASTQ input"); }
         if (in.n == 0 || in.p[0] != '>') { ctxThread.join(); die("Error: '%s' does not look like a FASTA file.\n", o.inSequence.c_str()); }
         parseFasta(in, threads, paths, items, seqOwner, seqBytes);

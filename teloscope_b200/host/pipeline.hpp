@@ -20,6 +20,8 @@
 #include <thread>
 #include <vector>
 
+#include <zlib.h>
+
 #include "teloscope_b200.h"
 
 namespace tlsb {
@@ -105,6 +107,38 @@ inline bool mapFile(const std::string &path, InputData &in) {      // false: can
     close(fd);
     return true;
 }
+// a plain file is mapped (no copy), a gzip file is inflated by zlib into memory
+inline void loadInput(const std::string &path, InputData &in) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) die("Error: Cannot open input file '%s'.\n", path.c_str());
+    unsigned char magic[2] = {0, 0};
+    const ssize_t got = pread(fd, magic, 2, 0);
+    struct stat st {};
+    fstat(fd, &st);
+    if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) && st.st_size > 0) {
+        void *m = mmap(nullptr, static_cast<size_t>(st.st_size), PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        if (m != MAP_FAILED) {
+            madvise(m, static_cast<size_t>(st.st_size), MADV_SEQUENTIAL);
+            in.map = m; in.p = static_cast<const char *>(m); in.n = static_cast<size_t>(st.st_size);
+            close(fd);
+            return;
+        }
+    }
+    close(fd);
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) die("Error: Cannot open input file '%s'.\n", path.c_str());
+    gzbuffer(f, 1 << 20);
+    std::vector<char> buf(1 << 24);
+    for (;;) {
+        const int n = gzread(f, buf.data(), static_cast<unsigned>(buf.size()));
+        if (n < 0) die("Error: Cannot read input file '%s'.\n", path.c_str());
+        if (n == 0) break;
+        in.owned.append(buf.data(), static_cast<size_t>(n));
+    }
+    gzclose(f);
+    in.p = in.owned.data(); in.n = in.owned.size();
+}
+
 inline void readAll(FILE *f, InputData &in) {
     std::vector<char> buf(1 << 22);
     for (size_t got; (got = fread(buf.data(), 1, buf.size(), f)) > 0;) in.owned.append(buf.data(), got);
@@ -130,5 +164,8 @@ inline void parallelFor(size_t n, unsigned threads, F f) {
 }
 
 int runBamSubset(const Options &o, const tls_config &baseCfg);      // bam_subset.cpp
+bool isGfaPath(const std::string &path);                            // gfa_pipeline.cpp
+int runGfa(const Options &o, const tls_config &baseCfg);
+int normalizeGfa(const std::string &inPath, const std::string &outPath);   // the graph read and written back without annotation (no device)
 
 }  // namespace tlsb

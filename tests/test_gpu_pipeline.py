@@ -103,13 +103,36 @@ def test_fastq_subset_equals_reference_output(golden, tmp_path):
 
 
 def test_pipeline_refuses_what_it_does_not_cover(tmp_path):
-    gfa = tmp_path / "g.gfa"
-    gfa.write_text("H\tVN:Z:1.2\nS\ts1\tACGT\n")
-    p = subprocess.run([str(BIN), "-f", str(gfa), "-o", str(tmp_path)], capture_output=True)
-    assert p.returncode == 2 and b"GFA input" in p.stderr
     fa = tmp_path / "a.fa"
     fa.write_text(">s\nACGT\n")
+    p = subprocess.run([str(BIN), "-f", str(fa), "--include-prefix", "s", "-o", str(tmp_path)], capture_output=True)
+    assert p.returncode == 2 and b"record filtering" in p.stderr
     p = subprocess.run([str(BIN), "--bam-subset", str(fa)], capture_output=True)
-    assert p.returncode == 2 and b"--bam-subset" in p.stderr
+    assert p.returncode == 1 and b"BAM subset failed: input is not BGZF-compressed BAM" in p.stderr
     p = subprocess.run([str(BIN), "-f", str(fa), "-w", "10", "-s", "20", "-o", str(tmp_path)], capture_output=True)
     assert p.returncode == 1 and b"Step size (20) cannot be larger than window size (10)" in p.stderr
+
+
+def test_gfa_annotation_equals_reference_binary(tmp_path):
+    """GFA input: annotated GFA, colours CSV, stdout and stderr of teloscope-b200 against the unmodified
+    reference binary (-j 1: the reference's node order depends on thread completion otherwise) for every GFA fixture of the
+    reference, with the flag sets of its own .tst cases and with the defaults."""
+    ref = ROOT / "oracle" / "_ref" / "teloscope"
+    fixtures = sorted((ROOT / "oracle" / "_ref" / "harness" / "testFiles").glob("*.gfa"))
+    if not ref.exists() or not fixtures:
+        pytest.skip("oracle/_ref not built (make -C oracle ref needs /root/reference)")
+    done = annotated = 0
+    for f in fixtures:
+        extra = {"gfa_plant_small": ["-c", "CCCTAAA"], "gfa_internal_only_small": ["-t", "100"]}.get(f.stem, [])
+        for flags in (["-x", "0", "-l", "60", *extra], extra):
+            outs = {}
+            for tag, exe in (("ref", ref), ("ours", BIN)):
+                d = tmp_path / f"{f.stem}_{tag}_{len(flags)}"
+                d.mkdir()
+                p = subprocess.run([str(exe), "-f", str(f), "-j", "1", *flags, "-o", str(d)], capture_output=True, timeout=600)
+                assert p.returncode == 0, (tag, f.name, p.stderr)
+                outs[tag] = (p.stdout, p.stderr, {x.name: x.read_bytes() for x in d.iterdir()})
+            assert outs["ours"] == outs["ref"], (f.name, flags)
+            annotated += b"telomere_" in outs["ref"][2][f.name + ".telo.annotated.gfa"]
+            done += 1
+    assert done >= 30 and annotated >= 20

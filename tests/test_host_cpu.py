@@ -152,7 +152,9 @@ def test_pipeline_binary_has_no_cpu_path(tmp_path):
     p = subprocess.run([str(exe), "-f", str(fa), "-x", "3", "-o", str(tmp_path)], capture_output=True)
     assert p.returncode == 1 and b"Error: Edit distance (-x/--edit-distance) must be in the range [0,2]." in p.stderr
     p = subprocess.run([str(exe), "--bam-subset", str(fa)], capture_output=True)
-    assert p.returncode == 2
+    assert p.returncode == 1 and b"Error: BAM subset failed: input is not BGZF-compressed BAM." in p.stderr
+    p = subprocess.run([str(exe), "-f", str(fa), "--plot-report", "-o", str(tmp_path)], capture_output=True)
+    assert p.returncode == 2                    # front ends this binary does not have: said so, status 2
     if tb.load_library().tls_device_count() > 0:
         pytest.skip("a B200 is visible; the refusal path is exercised on the CPU box")
     p = subprocess.run([str(exe), "-f", str(fa), "-c", "ccctaa", "-o", str(tmp_path)], capture_output=True)
@@ -162,3 +164,25 @@ def test_pipeline_binary_has_no_cpu_path(tmp_path):
     assert "Scanning 38 telomeric variants (includes reverse complements)." in err
     assert "tls_create failed" in err and ("no CUDA device" in err or "sm_100" in err)
     assert not list(tmp_path.glob("a.fa_*")), "no output file may appear without a scan"
+
+
+def test_gfa_reader_writer_equals_reference(tmp_path):
+    """GFA front end of teloscope-b200 (host/gfa_pipeline.cpp) without the scan: the graph read and written back as GFA 1.2
+    (--gfa-normalize, no device) must equal what the UNMODIFIED reference writes for the same input once the synthetic
+    telomere_ lines are taken out — for every GFA fixture of the reference (GFA1 with and without header / paths / jumps /
+    tags, '*' sequences, a GFA2 segment file).  Needs oracle/_ref (make -C oracle ref)."""
+    import subprocess
+    ref = ROOT / "oracle" / "_ref" / "teloscope"
+    fixtures = sorted((ROOT / "oracle" / "_ref" / "harness" / "testFiles").glob("*.gfa"))
+    exe = ROOT / "teloscope_b200" / "teloscope-b200"
+    if not ref.exists() or not fixtures or not exe.exists():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    assert len(fixtures) >= 15
+    for f in fixtures:
+        out = tmp_path / f.stem
+        out.mkdir()
+        subprocess.run([str(ref), "-f", str(f), "-j", "1", "-x", "0", "-l", "60", "-o", str(out)], check=True, capture_output=True)
+        want = [l for l in (out / (f.name + ".telo.annotated.gfa")).read_text().splitlines() if "telomere_" not in l]
+        mine = tmp_path / (f.stem + ".norm.gfa")
+        subprocess.run([str(exe), "--gfa-normalize", str(f), str(mine)], check=True, capture_output=True)
+        assert mine.read_text().splitlines() == want, f.name

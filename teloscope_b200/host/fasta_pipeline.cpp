@@ -40,7 +40,9 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -103,7 +105,7 @@ Options parseArgs(int argc, char **argv) {
         {"out-fasta", no_argument, 0, 'a'}, {"out-win-repeats", no_argument, 0, 'r'}, {"out-gc", no_argument, 0, 'g'},
         {"out-entropy", no_argument, 0, 'e'}, {"out-matches", no_argument, 0, 'm'}, {"out-its", no_argument, 0, 'i'},
         {"ultra-fast", no_argument, 0, 'u'}, {"manual-curation", no_argument, 0, 'n'}, {"plot-report", no_argument, 0, 0},
-        {"fastq-subset", no_argument, 0, 0}, {"bam-subset", no_argument, 0, 0}, {"verbose", no_argument, &verboseFlag, 1},
+        {"fastq-subset", no_argument, 0, 0}, {"bam-subset", no_argument, 0, 0}, {"gpus", required_argument, 0, 0}, {"verbose", no_argument, &verboseFlag, 1},
         {"cmd", no_argument, &cmdFlag, 1}, {"version", no_argument, 0, 'v'}, {"help", no_argument, 0, 'h'}, {0, 0, 0, 0}};
     for (;;) {
         int idx = 0;
@@ -121,6 +123,11 @@ Options parseArgs(int argc, char **argv) {
                 if (longOptions[idx].flag) break;                      // --verbose / --cmd
                 if (!strcmp(name, "plot-report")) unsupported("--plot-report");
                 if (!strcmp(name, "fastq-subset")) { o.fastqSubset = true; break; }
+                if (!strcmp(name, "gpus")) {               // not a reference flag: devices the scan of one job is spread over
+                    o.gpus = atoi(optarg);
+                    if (o.gpus < 1 || o.gpus > 64) die("Error: --gpus must be between 1 and 64.\n");
+                    break;
+                }
                 if (!strcmp(name, "bam-subset")) { o.bamSubset = true; break; }
                 unsupported("record filtering (--include-bed / --exclude-bed / --include-prefix / --exclude-prefix)");
             }
@@ -725,13 +732,26 @@ int main(int argc, char **argv) {
     if (o.fastqSubset) return runFastqSubset(o, cfg);
     if (o.bamSubset) return runBamSubset(o, cfg);
     if (isGfaPath(o.inSequence)) return runGfa(o, cfg);
-    tls_ctx *ctx = nullptr;
+    // One context per device (--gpus N: contexts 0 .. N-1 on devices TLS_DEVICE + k modulo the visible devices), each
+    // used under its own lock: a feeder thread submits the device's batches, the main thread collects them.
+    struct Dev { tls_ctx *ctx = nullptr; std::mutex mu; int inFlight = 0; };
+    const int nDev = o.gpus;
+    std::vector<Dev> devs(static_cast<size_t>(nDev));
     int ctxRc = TLS_OK;
     std::string ctxErr;
     std::thread ctxThread([&]() {
-        const char *devEnv = getenv("TLS_DEVICE");
-        ctxRc = tls_create(&cfg, devEnv ? atoi(devEnv) : 0, &ctx);
-        if (ctxRc != TLS_OK) ctxErr = tls_last_error();             // the message is thread-local
+        const int visible = std::max(1, tls_device_count());
+        const int first = getenv("TLS_DEVICE") ? atoi(getenv("TLS_DEVICE")) : 0;
+        std::vector<std::thread> ts;
+        std::vector<int> rcs(static_cast<size_t>(nDev), TLS_OK);
+        std::vector<std::string> errs(static_cast<size_t>(nDev));
+        for (int d = 0; d < nDev; ++d)
+            ts.emplace_back([&, d]() {
+                rcs[static_cast<size_t>(d)] = tls_create(&cfg, (first + d) % visible, &devs[static_cast<size_t>(d)].ctx);
+                if (rcs[static_cast<size_t>(d)] != TLS_OK) errs[static_cast<size_t>(d)] = tls_last_error();     // the message is thread-local
+            });
+        for (auto &t : ts) t.join();
+        for (int d = 0; d < nDev; ++d) if (rcs[static_cast<size_t>(d)] != TLS_OK && ctxRc == TLS_OK) { ctxRc = rcs[static_cast<size_t>(d)]; ctxErr = errs[static_cast<size_t>(d)]; }
     });
 
     // ---- ingest ---------------------------------------------------------------------------------------------
@@ -776,38 +796,59 @@ int main(int argc, char **argv) {
     // ---- scan: batches of whole contigs, two in flight; results are consumed in submission order ---------------------
     const uint64_t batchBytes = getenv("TLS_BATCH_BYTES") ? strtoull(getenv("TLS_BATCH_BYTES"), nullptr, 10) : (256ull << 20);
     const uint32_t mode = o.ultraFastMode ? TLS_MODE_TIPS : TLS_MODE_GENOME;
-    struct Batch { size_t first, count; std::vector<uint64_t> offsets, absPos; int ticket; };
+    // The batch list is fixed up front: whole contigs, at most batchBytes each (smaller with several devices, so that every
+    // device gets several), batch k on device k mod N.  Results are consumed in batch order = input order.
+    struct Batch { size_t first = 0, count = 0; std::vector<uint64_t> offsets, absPos; int ticket = -1; int dev = 0; bool submitted = false; };
     double msSubmit = 0, msCollect = 0, msFormat = 0, msWrite = 0;
     auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
-    std::vector<Batch> flight;
-    size_t nextItem = 0;
-    auto submitNext = [&]() {
-        Batch b;
-        b.first = nextItem;
-        uint64_t bytes = 0;
-        while (nextItem < items.size() && (bytes == 0 || bytes + items[nextItem].len <= batchBytes) && nextItem - b.first < 0x7FFFFFFFu) {
-            bytes += items[nextItem].len;
-            ++nextItem;
+    std::vector<Batch> batches;
+    {
+        uint64_t total = 0;
+        for (const Item &it : items) total += it.len;
+        const uint64_t cap = nDev > 1 ? std::max<uint64_t>(16ull << 20, std::min<uint64_t>(batchBytes, total / (4ull * static_cast<uint64_t>(nDev)) + 1)) : batchBytes;
+        size_t nextItem = 0;
+        while (nextItem < items.size()) {
+            Batch b;
+            b.first = nextItem;
+            uint64_t bytes = 0;
+            while (nextItem < items.size() && (bytes == 0 || bytes + items[nextItem].len <= cap) && nextItem - b.first < 0x7FFFFFFFu) {
+                bytes += items[nextItem].len;
+                ++nextItem;
+            }
+            b.count = nextItem - b.first;
+            for (size_t i = 0; i < b.count; ++i) { b.offsets.push_back(items[b.first + i].offset); b.absPos.push_back(items[b.first + i].absPos); }
+            b.offsets.push_back(items[b.first + b.count - 1].offset + items[b.first + b.count - 1].len);
+            b.dev = static_cast<int>(batches.size() % static_cast<size_t>(nDev));
+            batches.push_back(std::move(b));
         }
-        b.count = nextItem - b.first;
-        for (size_t i = 0; i < b.count; ++i) { b.offsets.push_back(items[b.first + i].offset); b.absPos.push_back(items[b.first + i].absPos); }
-        b.offsets.push_back(items[b.first + b.count - 1].offset + items[b.first + b.count - 1].len);
-        tls_batch tb{};
-        tb.seq = seq; tb.offsets = b.offsets.data(); tb.abs_pos = b.absPos.data();
-        tb.n_items = static_cast<uint32_t>(b.count); tb.mode = mode;
-        const auto t0 = std::chrono::steady_clock::now();
-        check(tls_submit(ctx, &tb, &b.ticket), "tls_submit");
-        msSubmit += since(t0);
-        flight.push_back(std::move(b));
-    };
+    }
+    std::mutex flowMu;
+    std::condition_variable flowCv;
+    std::vector<std::thread> feeders;
+    for (int d = 0; d < nDev; ++d)
+        feeders.emplace_back([&, d]() {
+            Dev &dev = devs[static_cast<size_t>(d)];
+            for (size_t k = static_cast<size_t>(d); k < batches.size(); k += static_cast<size_t>(nDev)) {
+                Batch &b = batches[k];
+                { std::unique_lock<std::mutex> lk(flowMu); flowCv.wait(lk, [&] { return dev.inFlight < 2; }); ++dev.inFlight; }
+                tls_batch tb{};
+                tb.seq = seq; tb.offsets = b.offsets.data(); tb.abs_pos = b.absPos.data();
+                tb.n_items = static_cast<uint32_t>(b.count); tb.mode = mode;
+                const auto t0 = std::chrono::steady_clock::now();
+                { std::lock_guard<std::mutex> lk(dev.mu); check(tls_submit(dev.ctx, &tb, &b.ticket), "tls_submit"); }
+                { std::lock_guard<std::mutex> lk(flowMu); msSubmit += since(t0); b.submitted = true; }
+                flowCv.notify_all();
+            }
+        });
     // Formatting is the host's share of the genome-wide outputs (3 M windows x 5 tracks on a human assembly): the
     // windows and match lists of a batch are cut into chunks, formatted in parallel into per-chunk buffers and
     // appended to the files in order.
     struct Chunk { size_t item; uint64_t lo, hi; int kind; std::string out[5]; };      // kind 0: windows, 1: canonical, 2: non-canonical
     auto consume = [&](const Batch &b) {
+        Dev &dev = devs[static_cast<size_t>(b.dev)];
         tls_result r{};
         auto t0 = std::chrono::steady_clock::now();
-        check(tls_collect(ctx, b.ticket, &r), "tls_collect");
+        { std::lock_guard<std::mutex> lk(dev.mu); check(tls_collect(dev.ctx, b.ticket, &r), "tls_collect"); }
         msCollect += since(t0);
         t0 = std::chrono::steady_clock::now();
         std::vector<Chunk> chunks;
@@ -879,13 +920,15 @@ int main(int argc, char **argv) {
             else put(c.kind == 1 ? fCan : fNon, c.out[0]);
         }
         msWrite += since(t0);
-        check(tls_release(ctx, b.ticket), "tls_release");
+        { std::lock_guard<std::mutex> lk(dev.mu); check(tls_release(dev.ctx, b.ticket), "tls_release"); }
+        { std::lock_guard<std::mutex> lk(flowMu); --dev.inFlight; }
+        flowCv.notify_all();
     };
-    while (nextItem < items.size() || !flight.empty()) {
-        while (flight.size() < 2 && nextItem < items.size()) submitNext();
-        consume(flight.front());
-        flight.erase(flight.begin());
+    for (size_t k = 0; k < batches.size(); ++k) {
+        { std::unique_lock<std::mutex> lk(flowMu); flowCv.wait(lk, [&] { return batches[k].submitted; }); }
+        consume(batches[k]);
     }
+    for (auto &t : feeders) t.join();
     timer.mark("scan + window / match files");
     if (timer.on) fprintf(stderr, "[pipe]   of which: tls_submit %.1f ms, tls_collect %.1f ms, formatting %.1f ms, file writes %.1f ms\n", msSubmit, msCollect, msFormat, msWrite);
     // the ctx is not destroyed: freeing gigabytes of device memory and unloading the runtime costs ~0.1 s that the

@@ -129,3 +129,39 @@ def test_batches_of_only_empty_items(tb):
                 assert full.n_matches > 0
         finally:
             sc.close()
+
+
+def test_sharded_job_equals_single_batch(tb):
+    """One job over two contexts (two GPUs when the box has them, the same GPU twice otherwise): items partitioned by
+    teloscope_b200.shard.partition_items, each share scanned through its own ctx, results put back in submission order —
+    identical to the single-batch scan, item by item (what ShardedJob does over gloo, tests/test_shard_gloo.py)."""
+    from teloscope_b200.shard import partition_items
+    from test_gpu_rows import make_contig
+    rng = np.random.default_rng(2024)
+    cfg = ol.Config(patterns=["TTAGGG", "TCAGGG", "TGAGGG", "TTGGGG"], terminal_limit=20000)
+    seqs = [make_contig(rng, int(n), "TTAGGG", i % 3 == 0) for i, n in enumerate(rng.integers(2_000, 600_000, size=40))]
+    abs_pos = np.cumsum([0] + [len(s) + 100 for s in seqs[:-1]]).astype(np.uint64)
+    ndev = tb.load_library().tls_device_count()
+    one = tb.Scanner(pa.scan_config(cfg))
+    try:
+        ref = one.scan_batch(seqs, abs_pos, tb.MODE_GENOME)
+        want = [ref.item(i) for i in range(len(seqs))]
+    finally:
+        one.close()
+    parts = partition_items([len(s) for s in seqs], 2)
+    got = [None] * len(seqs)
+    scanners = [tb.Scanner(pa.scan_config(cfg), device=r % ndev) for r in range(2)]
+    try:
+        tickets = [sc.submit_batch([seqs[i] for i in parts[r]], abs_pos[parts[r]], tb.MODE_GENOME) if hasattr(sc, "submit_batch") else None
+                   for r, sc in enumerate(scanners)]
+        for r, sc in enumerate(scanners):
+            res = sc.scan_batch([seqs[i] for i in parts[r]], abs_pos[parts[r]], tb.MODE_GENOME) if tickets[r] is None else sc.collect(tickets[r])
+            for k, i in enumerate(parts[r]):
+                got[int(i)] = res.item(k)
+    finally:
+        for sc in scanners:
+            sc.close()
+    for a, b in zip(got, want):
+        for k in ("windows", "canonical", "noncanonical", "terminal", "its"):
+            assert a[k].tobytes() == b[k].tobytes(), k
+        assert a["n_canonical"] == b["n_canonical"]

@@ -136,3 +136,31 @@ def test_gfa_annotation_equals_reference_binary(tmp_path):
             annotated += b"telomere_" in outs["ref"][2][f.name + ".telo.annotated.gfa"]
             done += 1
     assert done >= 30 and annotated >= 20
+
+
+def test_pipeline_over_several_devices_equals_one(tmp_path):
+    """teloscope-b200 --gpus N (one context and feeder thread per device, batch k on device k mod N, results consumed in
+    input order): every output file, stdout and stderr identical to --gpus 1.  Devices beyond the visible ones wrap around,
+    so the multi-context path also runs on a one-GPU box."""
+    import numpy as np
+    from test_gpu_rows import make_contig
+    rng = np.random.default_rng(99)
+    fa = tmp_path / "multi.fa"
+    with open(fa, "wb") as fh:
+        for i in range(30):
+            n = int(rng.integers(20_000, 1_500_000))
+            s = make_contig(rng, n, "TTAGGG", i % 4 == 0).replace(b"\r", b"A")
+            gap = b"N" * int(rng.integers(10, 500)) if i % 3 else b""
+            fh.write(b">rec%d some text\n" % i)
+            body = s[: n // 2] + gap + s[n // 2:]
+            fh.write(b"\n".join(body[k:k + 70] for k in range(0, len(body), 70)) + b"\n")
+    outs = {}
+    for gpus in (1, 2, 3):
+        d = tmp_path / f"out{gpus}"
+        d.mkdir()
+        env = dict(__import__("os").environ, TLS_BATCH_BYTES=str(3 << 20))
+        p = subprocess.run([str(BIN), "-f", str(fa), "-r", "-g", "-e", "-m", "-i", "--gpus", str(gpus), "-o", str(d)], capture_output=True, timeout=900, env=env)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs[gpus] = (p.stdout, p.stderr, {f.name: f.read_bytes() for f in d.iterdir()})
+    assert len(outs[1][2]) == 11
+    assert outs[2] == outs[1] and outs[3] == outs[1]

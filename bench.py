@@ -1,16 +1,18 @@
 #!/usr/bin/env python3
 """bench.py — genome-wide telomeric motif scan throughput (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale F] [--scaling weak|strong]
 
 One "step" = one pass of the hot path (Teloscope::scanSegment in genome-wide mode, flags
 -r -g -e -m -i, -c TTAGGG -p TTAGGG,TCAGGG,TGAGGG,TTGGGG) over one synthetic human-shaped
 assembly: 24 chromosomes with GRCh38 lengths (3.09 Gbp), N-gaps (which split them into contigs),
-telomere caps + TVR, ITS islands, 10 % soft-masked.  Every rank scans its own assembly (weak
-scaling, no data-path collective); rank 0 prints ONE JSON line.
+telomere caps + TVR, ITS islands, 10 % soft-masked.  --scaling weak (default): every rank scans its
+own assembly; --scaling strong: ONE assembly, its contigs partitioned over the ranks by bases
+(teloscope_b200.shard.partition_items).  No data-path collective either way; rank 0 prints ONE JSON line.
 
   value    Gbp/s with the assembly already resident in HBM (device pointer handed to the C ABI),
-           everything else of the job included (kernels, result copies, host-side assembly)
+           everything else of the job included (kernels, result copies, host-side assembly), driven the
+           way the double-buffered C ABI is meant to be: two tickets in flight (value_one_ticket beside it)
   e2e      same call with the sequence in pinned HOST memory: H2D + kernels + D2H in the timed region
   roofline scan kernel only: algorithmic bytes / CUDA-event duration against the measured HBM peak
   pipeline_e2e  file -> files: the same assembly as a FASTA file through teloscope_b200/teloscope-b200 (host ingest, C ABI,
@@ -18,7 +20,11 @@ scaling, no data-path collective); rank 0 prints ONE JSON line.
   other_workloads  BASELINE.json configs[3] (plant-shaped, 7-mers) and configs[4] (read scorer), device-resident
   cpu_baseline  the unmodified reference binary (oracle/_ref/teloscope) on the box's host cores on
            a 1/16-scale assembly of the same generator (file parsing and writers included: it has
-           no other entry point); falls back to the oracle port when the binary is absent
+           no other entry point): median of 3 runs with -j <cores>, one run with -j 1, CPU model,
+           compiler and zlib versions; falls back to the oracle port when the
+           binary is absent
+  --impl reference  the same reference binary on the SAME assembly as the repo arm (same --scale), every
+           step one whole run of it
 """
 from __future__ import annotations
 
@@ -354,12 +360,115 @@ def fastq_subset_file_to_file(seed: int, total_bp: int, with_reference: bool):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def write_unmapped_bam(path: Path, host: np.ndarray, offsets: np.ndarray, threads: int) -> int:
+    """S-reads as an unmapped BAM (flag 4, qualities 0xFF): BGZF blocks of 65 280 payload bytes deflated like the
+    reference's writer does (raw deflate, default level, memLevel 8), in a thread pool (zlib releases the GIL)."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    code = np.full(256, 15, dtype=np.uint8)
+    for i, ch in enumerate(b"=ACMGRSVTWYHKDBN"):
+        code[ch] = i
+        code[ord(chr(ch).lower())] = i
+    header = b"BAM\x01" + struct.pack("<i", 0) + struct.pack("<i", 0)
+    chunks = [header]
+    for i in range(len(offsets) - 1):
+        a, b = int(offsets[i]), int(offsets[i + 1])
+        n = b - a
+        c = code[host[a:b]]
+        if n & 1:
+            c = np.append(c, 0)
+        packed = ((c[0::2] << 4) | c[1::2]).astype(np.uint8).tobytes()
+        name = b"read%d\x00" % i
+        core = struct.pack("<iiBBHHHiiii", -1, -1, len(name), 0, 4680, 0, 4, n, -1, -1, 0)
+        body = core + name + packed + b"\xff" * n
+        chunks.append(struct.pack("<i", len(body)) + body)
+    payload = b"".join(chunks)
+    del chunks
+
+    def block(k):
+        data = payload[k:k + 65280]
+        co = zlib.compressobj(zlib.Z_DEFAULT_COMPRESSION, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY)
+        comp = co.compress(data) + co.flush()
+        total = 18 + len(comp) + 8
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", total - 1) + comp +
+                struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as pool, open(path, "wb") as fh:
+        for blk in pool.map(block, range(0, len(payload), 65280)):
+            fh.write(blk)
+        fh.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    return len(payload)
+
+
+def bam_subset_file_to_file(seed: int, total_bp: int, with_reference: bool):
+    """BASELINE.json configs[4], BAM half: S-reads as an unmapped BAM in /dev/shm, `teloscope-b200 --bam-subset -o`
+    (process start to exit) and the unmodified reference on the same file; the two subset BAMs compared byte for byte."""
+    import torch
+    exe = ROOT / "teloscope_b200" / "teloscope-b200"
+    ref_bin = ROOT / "oracle" / "_ref" / "teloscope"
+    if not exe.exists():
+        return {"unavailable": "teloscope_b200/teloscope-b200 not built"}
+    seq, offsets, n_telo = build_reads("cuda", seed, total_bp)
+    host = seq.cpu().numpy()
+    del seq
+    torch.cuda.empty_cache()
+    cores = os.cpu_count() or 1
+    tmp = Path(tempfile.mkdtemp(prefix="telo_bam_", dir="/dev/shm" if Path("/dev/shm").exists() else None))
+    try:
+        bam = tmp / "reads.bam"
+        payload = write_unmapped_bam(bam, host, offsets, cores)
+        del host
+        bases = int(offsets[-1])
+        out = {"what": "unmapped BAM (page cache) -> subset BAM, --bam-subset -l 42 -o dir, process start to exit",
+               "bases": bases, "reads": len(offsets) - 1, "bam_bytes": bam.stat().st_size, "bam_payload_bytes": payload, "unit": "Gbp/s"}
+        times = []
+        for i in range(3):
+            d = tmp / "ours"
+            shutil.rmtree(d, ignore_errors=True); d.mkdir()
+            t0 = time.perf_counter()
+            subprocess.run([str(exe), "--bam-subset", "-f", str(bam), "-o", str(d)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            times.append(time.perf_counter() - t0)
+        out["seconds"] = min(times[1:]); out["value"] = bases / out["seconds"] / 1e9
+        if with_reference and ref_bin.exists():
+            d = tmp / "ref"
+            d.mkdir()
+            t0 = time.perf_counter()
+            subprocess.run([str(ref_bin), "--bam-subset", "-f", str(bam), "-j", str(cores), "-o", str(d)], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            dt = time.perf_counter() - t0
+            a, b = (d / "reads_telomeric.bam").read_bytes(), (tmp / "ours" / "reads_telomeric.bam").read_bytes()
+            out["reference_same_file"] = {"seconds": dt, "value": bases / dt / 1e9, "cores": cores,
+                                          "outputs_byte_identical": a == b, "subset_bytes": len(a)}
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # --------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_run(sample_scale: float, steps: int, warmup: int, seed: int = 1234):
-    """Times the reference's own CPU implementation on a scaled-down assembly of the same generator.
-    Returns (Gbp/s, description dict)."""
+def host_info() -> dict:
+    """CPU model, core count, compiler and zlib versions."""
+    import zlib
+    model = ""
+    try:
+        for line in Path("/proc/cpuinfo").read_text().splitlines():
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    try:
+        gxx = subprocess.run(["g++", "--version"], capture_output=True, text=True).stdout.splitlines()[0]
+    except (OSError, IndexError):
+        gxx = "unknown"
+    return {"cpu_model": model, "cores": os.cpu_count() or 1, "compiler": gxx + " -O3 (oracle/Makefile)", "zlib": zlib.ZLIB_RUNTIME_VERSION}
+
+
+def cpu_reference_run(sample_scale: float, steps: int, warmup: int, seed: int = 1234, single_thread_scale: float = 0.0):
+    """Times the reference's own CPU implementation on an assembly of the same generator at `sample_scale`.
+    Returns (Gbp/s from the MEDIAN step, seconds of that step, description dict)."""
     import torch
     cores = os.cpu_count() or 1
     chroms = plan_assembly(seed, sample_scale)
@@ -387,7 +496,22 @@ def cpu_reference_run(sample_scale: float, steps: int, warmup: int, seed: int = 
             kind = "reference"
             how = (f"oracle/_ref/teloscope (unmodified reference, g++ -O3) -j {cores} on a {sample_scale:g}-scale "
                    f"assembly of the same generator: {bases / 1e6:.0f} Mbp in 24 records, page-cache-warm FASTA in "
-                   f"/dev/shm; wall time of the whole run (parse + scan + writers)")
+                   f"/dev/shm; wall time of the whole run (parse + scan + writers); median of {steps} run(s) after {warmup} warm-up")
+            extra = {}
+            if single_thread_scale > 0:                       # -j 1 on a smaller sample (one run: it is 10x slower)
+                ch1 = plan_assembly(seed + 1, single_thread_scale)
+                s1, o1, _ = build_assembly(ch1, dev, seed + 1)
+                fa1 = tmp / "sample_j1.fa"
+                b1 = write_fasta(ch1, s1.cpu().numpy(), o1, fa1)
+                del s1
+                out = tmp / "out_j1"
+                out.mkdir()
+                t0 = time.perf_counter()
+                subprocess.run([str(ref_bin), "-f", str(fa1), *REF_FLAGS, "-j", "1", "-o", str(out)],
+                               check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                dt = time.perf_counter() - t0
+                extra["single_thread"] = {"value": b1 / dt / 1e9, "unit": "Gbp/s", "j": 1, "bases": b1, "seconds": dt,
+                                          "sample": f"{single_thread_scale:g}-scale assembly, one run"}
         else:
             sys.path.insert(0, str(ROOT / "tests"))
             import oracle_lib as ol
@@ -403,8 +527,11 @@ def cpu_reference_run(sample_scale: float, steps: int, warmup: int, seed: int = 
             kind = "port"
             how = (f"oracle port (oracle/oracle.cpp scanSegment) with {cores} threads, one job per contig, on a "
                    f"{sample_scale:g}-scale assembly: {bases / 1e6:.0f} Mbp")
-        per_step = float(np.mean(times))
-        return bases / per_step / 1e9, per_step, {"kind": kind, "cores": cores, "sample": how}
+        per_step = float(np.median(times))
+        desc = {"kind": kind, "cores": cores, "j": cores, "sample": how, "bases": bases, "seconds_per_run": [round(t, 3) for t in times], **host_info()}
+        if kind == "reference":
+            desc.update(extra)
+        return bases / per_step / 1e9, per_step, desc
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -471,7 +598,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="assembly size factor (1.0 = 3.09 Gbp; tests use less)")
-    ap.add_argument("--cpu-scale", type=float, default=1.0 / 16, help="size factor of the CPU baseline sample")
+    ap.add_argument("--cpu-scale", type=float, default=1.0 / 16, help="size factor of the cpu_baseline sample of the repo arm")
+    ap.add_argument("--ref-scale", type=float, default=None, help="--impl reference: size factor of its assembly (default: --scale, the repo arm's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one assembly per rank; strong: one assembly, its contigs partitioned over the ranks")
+    ap.add_argument("--depth", type=int, default=2, choices=[1, 2], help="tickets in flight in the timed device-resident loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-records", action="store_true", help="32-byte window / 16-byte match records instead of the compact forms")
     ap.add_argument("--no-extra", action="store_true", help="skip the plant-assembly and read-scorer measurements")
@@ -485,11 +616,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        gbps, per_step, desc = cpu_reference_run(args.cpu_scale, args.steps, args.warmup)
+        ref_scale = args.scale if args.ref_scale is None else args.ref_scale
+        workload = workload.replace(f"x{args.scale:g}", f"x{ref_scale:g}")
+        gbps, per_step, desc = cpu_reference_run(ref_scale, args.steps, args.warmup, seed=args.seed)
         print(json.dumps({"metric": METRIC, "value": gbps, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "impl": "reference", "config": {"workload": workload},
+                          "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "impl": "reference", "config": {"workload": workload, "scale": ref_scale,
+                                                          "what": "one whole run of the reference binary per step (FASTA parse + scan + writers), the same assembly every step"},
                           "cpu_baseline": {"value": gbps, "unit": "Gbp/s", **desc},
                           "e2e": {"value": gbps, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -510,9 +644,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- workload: one assembly per rank --------------------------------------------------------------
-    chroms = plan_assembly(args.seed + rank, args.scale)
-    seq, offsets, abs_pos = build_assembly(chroms, f"cuda:{local}", args.seed + rank)
+    # ---- workload: one assembly per rank (weak), or this rank's share of the contigs of ONE assembly (strong) --------
+    strong = args.scaling == "strong" and world > 1
+    aseed = args.seed if strong else args.seed + rank
+    chroms = plan_assembly(aseed, args.scale)
+    seq, offsets, abs_pos = build_assembly(chroms, f"cuda:{local}", aseed)
+    job_bases = int(offsets[-1])
+    if strong:
+        from teloscope_b200.shard import partition_items
+        lens = np.diff(offsets.astype(np.int64))
+        mine = partition_items(lens.tolist(), world)[rank]
+        parts = [seq[int(offsets[i]):int(offsets[i + 1])] for i in mine]
+        new_off = np.concatenate([[0], np.cumsum(lens[mine])]).astype(np.uint64)
+        seq = torch.cat(parts + [torch.full((4096,), 65, dtype=torch.uint8, device=seq.device)])
+        abs_pos = abs_pos[mine]
+        offsets = new_off
+        del parts
+        torch.cuda.empty_cache()
     n_bases = int(offsets[-1])
     host = torch.empty(seq.numel(), dtype=torch.uint8, pin_memory=True)
     host.copy_(seq)
@@ -557,14 +705,28 @@ def main():
 
     # ---- timed: device-resident input -------------------------------------------------------------------
     clocks = ClockSampler(local) if rank == 0 else None
+    # one ticket at a time: kernel timings are undisturbed (this is where the roofline numbers come from) ...
     stats = {"scan_ms": [], "lean_ms": [], "launches": 0}
     barrier()
     t0 = time.perf_counter()
     r = run_steps(args.steps, True, stats)
     barrier()
-    elapsed = time.perf_counter() - t0
+    elapsed_one = time.perf_counter() - t0
     r.release()
     scan_ms, launches = stats["scan_ms"], stats["launches"]
+    # ... and the way a streaming caller drives the double-buffered ABI: step i + 1 is submitted before step i is collected,
+    # so the result copies of step i overlap the kernels of step i + 1
+    elapsed = elapsed_one
+    if args.depth == 2:
+        run_steps(2, True, depth=2).release()
+        stats2 = {"scan_ms": [], "lean_ms": [], "launches": 0}
+        barrier()
+        t0 = time.perf_counter()
+        r = run_steps(args.steps, True, stats2, depth=2)
+        barrier()
+        elapsed = time.perf_counter() - t0
+        r.release()
+        launches = stats2["launches"]
     # ---- timed: end to end from pinned host memory ----------------------------------------------------
     run_steps(3, False, depth=2).release()       # warm-up of the host-buffer path: both tickets' buffers get allocated
     barrier()
@@ -578,11 +740,11 @@ def main():
     h2d = n_bases + len(offsets) * 40 + (n_bases // 49136 + len(offsets)) * 16
 
     my_kernel_gbps = n_bases / (float(np.mean(scan_ms)) * 1e-3) / 1e9          # this rank's scan kernels alone
-    t = torch.tensor([elapsed, elapsed_e2e, float(n_bases), my_kernel_gbps], dtype=torch.float64, device=f"cuda:{local}")
+    t = torch.tensor([elapsed, elapsed_e2e, float(n_bases), my_kernel_gbps, elapsed_one], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        elapsed, elapsed_e2e, total_bases, kernel_gbps_all = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3])
+        elapsed, elapsed_e2e, total_bases, kernel_gbps_all, elapsed_one = float(mx[0]), float(mx[1]), float(sm[2]), float(sm[3]), float(mx[4])
     else:
         total_bases, kernel_gbps_all = float(n_bases), my_kernel_gbps
     if rank == 0:
@@ -612,11 +774,16 @@ def main():
         line = {
             "metric": METRIC, "value": total_bases * args.steps / elapsed / 1e9, "unit": "Gbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload, "bases_per_gpu": n_bases, "contigs_per_gpu": len(offsets) - 1,
-                       "windows_per_gpu": n_windows, "matches_per_gpu": n_matches, "sharding": "one assembly per GPU, no collective",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "value_one_ticket": total_bases * args.steps / elapsed_one / 1e9, "ms_per_step_one_ticket": elapsed_one / args.steps * 1e3,
+            "config": {"workload": workload, "scale": args.scale, "bases_per_gpu": n_bases, "contigs_per_gpu": len(offsets) - 1,
+                       "windows_per_gpu": n_windows, "match_records_per_gpu": n_matches,
+                       "sharding": (f"ONE assembly ({job_bases} bases), contigs partitioned over {world} ranks by bases (LPT), no collective" if strong
+                                    else "one assembly per GPU, no collective"),
                        "l2": "input (>= 3 GB at scale 1) is larger than the 126 MB L2; no flush needed",
-                       "pipelining": "value: one ticket at a time; e2e: two tickets in flight (H2D of step i+1 overlaps step i)",
+                       "pipelining": (f"value: {args.depth} ticket(s) in flight (the double-buffered C ABI as a streaming caller drives it; "
+                                      "value_one_ticket: submit, collect, release one step after the other); e2e: two tickets in flight "
+                                      "(H2D of step i+1 overlaps step i)"),
                        "result_records": "full (32-byte windows, 16-byte matches)" if args.full_records else
                                          "compact (TLS_OUT_COMPACT: 16-byte windows, 8-byte item-relative matches)"},
             "e2e": {"value": total_bases * args.steps / elapsed_e2e / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d,
@@ -636,7 +803,7 @@ def main():
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
-            gbps, _, desc = cpu_reference_run(args.cpu_scale, 1, 1)
+            gbps, _, desc = cpu_reference_run(args.cpu_scale, 3, 1, single_thread_scale=args.cpu_scale / 4)
             line["cpu_baseline"] = {"value": gbps, "unit": "Gbp/s", **desc}
     sc.close()
     if rank == 0:
@@ -655,6 +822,12 @@ def main():
                 line["fastq_subset_e2e"] = fastq_subset_file_to_file(args.seed + 300, int(1.0e9 * min(1.0, args.scale)), not args.no_cpu_baseline)
             except Exception as exc:
                 line["fastq_subset_e2e"] = {"error": repr(exc)}
+            try:
+                line["bam_subset_e2e"] = bam_subset_file_to_file(args.seed + 400, int(0.5e9 * min(1.0, args.scale)), not args.no_cpu_baseline)
+            except Exception as exc:
+                line["bam_subset_e2e"] = {"error": repr(exc)}
+            line["config5_note"] = ("configs[4] names 100 Gbp of reads: measured here on 1 Gbp (FASTQ) / 0.5 Gbp (BAM) files and on a 2 Gbp device-resident "
+                                    "batch (other_workloads); both front ends stream in bounded batches, so 100 Gbp is these rates extrapolated, not measured")
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -143,15 +143,20 @@ __global__ void __launch_bounds__(kReadThreads, 1) readScanKernel(const ReadPara
     auto rowBases = [&](uint32_t n, uint32_t rs) { return min(n - rs, static_cast<uint32_t>(kReadStride) + L - 1u); };
 
     unsigned long long matchTotal = 0;
-    uint32_t rNext = 0;
-    if (lane == 0) rNext = atomicAdd(p.cursor, 1u);
-    rNext = __shfl_sync(0xFFFFFFFFu, rNext, 0);
-    bool primed = false;                                      // c0 / c1 hold (or are receiving) row 0 of read rNext
-    while (rNext < p.nItems) {
-        const uint32_t r = rNext;
+    // Reads are handed out by a counter.  A warp knows its next read one read ahead (the first row of that read is loaded
+    // during the last row of the current one) and has the index of the one after that on order.
+    uint32_t r = 0, rNext, rPending = 0;
+    if (lane == 0) r = atomicAdd(p.cursor, 2u);
+    r = __shfl_sync(0xFFFFFFFFu, r, 0);
+    rNext = r + 1;
+    bool primed = false;                                      // c0 / c1 hold (or are receiving) row 0 of read r
+    while (r < p.nItems) {
         const uint32_t n = p.itemLen[r];
         const uint64_t readAddr = seqBase + p.items[r].bufStart;
-        if (lane == 0) rNext = atomicAdd(p.cursor, 1u);       // the next read's index arrives while this one is scanned
+        if (lane == 0) rPending = atomicAdd(p.cursor, 1u);
+        uint32_t nNext = 0;
+        uint64_t nextAddr = 0;
+        if (rNext < p.nItems) { nNext = p.itemLen[rNext]; nextAddr = seqBase + p.items[rNext].bufStart + laneOff; }
         if (!primed && n >= L) ldStream32If(c0, c1, (readAddr + laneOff) & ~static_cast<uint64_t>(15), laneOff, rowBases(n, 0) + 15u);
         primed = false;
         Strand fw, rv;
@@ -169,10 +174,15 @@ __global__ void __launch_bounds__(kReadThreads, 1) readScanKernel(const ReadPara
                     P1 = pack16v(c1, va);
                     badBits = va.bad();
                 }
-                {   // re-arm: the next row of this read, or nothing (the next read is primed after its index is known)
+                {   // re-arm: the next row of this read, or the first row of the warp's next read
                     const uint32_t rsN = rs + kReadStride;
                     const bool more = rsN + L <= n;
-                    ldStream32If(c0, c1, (laneAddr + kReadStride) & ~static_cast<uint64_t>(15), laneOff, more ? rowBases(n, rsN) + 15u : 0u);
+                    const uint64_t na = more ? laneAddr + kReadStride : nextAddr;
+                    const uint32_t nl = more ? rowBases(n, rsN) + 15u : (nNext >= L ? rowBases(nNext, 0) + 15u : 0u);
+                    ldStream32If(c0, c1, na & ~static_cast<uint64_t>(15), laneOff, nl);
+                    primed = !more && nNext >= L;
+                    // the row after that one: into L2 now
+                    if (kRowPrefetch && rsN + kReadStride + laneOff < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(laneAddr + 2 * kReadStride));
                 }
                 const uint32_t sh = 2u * skew;
                 const uint32_t X0 = __funnelshift_r(P0, P1, sh);
@@ -219,7 +229,9 @@ __global__ void __launch_bounds__(kReadThreads, 1) readScanKernel(const ReadPara
         }
         if (lane == 0) p.pass[r] = pass ? 1 : 0;
         matchTotal += __reduce_add_sync(0xFFFFFFFFu, nHits);       // warp-uniform
-        rNext = __shfl_sync(0xFFFFFFFFu, rNext, 0);
+        if (decided) primed = false;                               // left early: the registers hold a row of this read
+        r = rNext;
+        rNext = __shfl_sync(0xFFFFFFFFu, rPending, 0);
     }
     if (lane == 0 && matchTotal) atomicAdd(p.matchTotal, matchTotal);
 }

@@ -542,7 +542,16 @@ int runFastqSubset(const Options &o, const tls_config &baseCfg) {
     });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{ctxThread};
     InputData in;
-    loadInput(o.inSequence, in);
+    if (o.inSequence.empty()) {
+        readAll(stdin, in);
+        if (in.n > 1 && static_cast<unsigned char>(in.p[0]) == 0x1f) {          // src/main.cpp:576-583
+            fprintf(stderr, "Error: Compressed input on stdin is not supported. Decompress first:\n");
+            fprintf(stderr, "  zcat file.fa.gz | teloscope -o results/\n");
+            quit(EXIT_FAILURE);
+        }
+    } else {
+        loadInput(o.inSequence, in);
+    }
     timer.mark("read file");
     if (in.n == 0) fastqError(0, "FASTQ input is empty");
     if (in.p[0] != '@') fastqError(0, "FASTQ input must start with '@'");
@@ -660,11 +669,11 @@ int main(int argc, char **argv) {
     }
     if (argc == 4 && !strcmp(argv[1], "--gfa-normalize")) return normalizeGfa(argv[2], argv[3]);   // developer / test entry: graph in, GFA 1.2 out, no scan
     Options o = parseArgs(argc, argv);
-    if (o.inSequence.empty() && o.bamSubset && !isatty(STDIN_FILENO)) {      // pipe-only invocation, src/main.cpp:567-573
+    if (o.inSequence.empty() && (o.bamSubset || o.fastqSubset) && !isatty(STDIN_FILENO)) {      // pipe-only invocation, src/main.cpp:567-573
         o.inSequenceName = "stdin";
         if (o.outRoute.empty()) o.outRoute = ".";
     } else if (o.inSequence.empty()) {
-        if (!isatty(STDIN_FILENO)) unsupported("input on stdin (other than --bam-subset)");
+        if (!isatty(STDIN_FILENO)) unsupported("an assembly on stdin");
         die("Error: No input file provided. Use -f or pass as positional argument.\n");
     }
     if (o.fastqSubset && o.bamSubset) die("Error: --fastq-subset and --bam-subset are mutually exclusive.\n");

@@ -43,7 +43,7 @@ def test_config3_file_to_files_equals_reference_binary():
     try:
         fa = tmp / "assembly.fa"
         bases = bench.write_fasta(chroms, host, offsets, fa)
-        assert bases > 290_000_000
+        assert bases > 250_000_000
         outs = {}
         for tag, exe, extra in (("ours", BIN, []), ("ref", REF, ["-j", "16"])):
             d = tmp / tag
@@ -91,6 +91,6 @@ def test_config4_plant_7mers_against_oracle():
                 for f in ("start", "len", "counts", "fwd_count", "can_count", "total_cov", "fwd_cov", "can_cov", "label", "valid_or"):
                     assert np.array_equal(got[k][f], want[k][f]), (i, k, f)
             n_its += len(want["its"]); n_term += len(want["terminal"])
-        assert n_term >= 20 and n_its >= 100, (n_term, n_its)
+        assert n_term >= 20 and n_its >= 50, (n_term, n_its)
     finally:
         sc.close()

@@ -73,6 +73,7 @@ def test_validate_files(tree):
         if m:
             rows.append((Path(m.group(2)).name, m.group(1)))
     _table("teloscope-validate validateFiles", rows)
+    (ROOT / "gpurun_out" / "harness_validate.log").write_text(_strip(p.stdout) + "\n---- stderr ----\n" + p.stderr)
     assert len(rows) >= 170, p.stdout[-3000:]
     bad = [c for c, r in rows if r == "FAIL" and not EXPECTED_UNSUPPORTED.search(c)]
     assert not bad, (bad, p.stdout[-3000:])
@@ -82,6 +83,7 @@ def test_val_sh(tree):
     p = subprocess.run(["bash", ".github/workflows/val.sh"], cwd=tree, capture_output=True, text=True, timeout=3000)
     rows = [(m.group(2).strip(), m.group(1)) for m in re.finditer(r"^(PASS|FAIL)\s+(.*)$", _strip(p.stdout), re.M)]
     _table(".github/workflows/val.sh", rows)
+    (ROOT / "gpurun_out" / "harness_val_sh.log").write_text(_strip(p.stdout) + "\n---- stderr ----\n" + p.stderr)
     bad = [c for c, r in rows if r == "FAIL" and not EXPECTED_UNSUPPORTED.search(c)]
     assert not bad and len(rows) > 200, (bad, len(rows), p.stdout[-2000:], p.stderr[-2000:])
 
@@ -97,4 +99,5 @@ def test_bam_subset_script(tree):
     env = dict(os.environ, TELOSCOPE=str(tree / "build" / "bin" / "teloscope"))
     p = subprocess.run(["python3", "scripts/test_bam_subset.py"], cwd=tree, capture_output=True, text=True, timeout=3000, env=env)
     _table("scripts/test_bam_subset.py", [("test_bam_subset.py", "PASS" if p.returncode == 0 else "FAIL")])
+    (ROOT / "gpurun_out" / "harness_bam.log").write_text(p.stdout + "\n---- stderr ----\n" + p.stderr)
     assert p.returncode == 0 and "PASS BAM subset integration" in p.stdout, (p.stdout[-2000:], p.stderr[-3000:])

@@ -152,10 +152,8 @@ def test_sharded_job_equals_single_batch(tb):
     got = [None] * len(seqs)
     scanners = [tb.Scanner(pa.scan_config(cfg), device=r % ndev) for r in range(2)]
     try:
-        tickets = [sc.submit_batch([seqs[i] for i in parts[r]], abs_pos[parts[r]], tb.MODE_GENOME) if hasattr(sc, "submit_batch") else None
-                   for r, sc in enumerate(scanners)]
         for r, sc in enumerate(scanners):
-            res = sc.scan_batch([seqs[i] for i in parts[r]], abs_pos[parts[r]], tb.MODE_GENOME) if tickets[r] is None else sc.collect(tickets[r])
+            res = sc.scan_batch([seqs[i] for i in parts[r]], abs_pos[parts[r]], tb.MODE_GENOME)
             for k, i in enumerate(parts[r]):
                 got[int(i)] = res.item(k)
     finally:

@@ -276,17 +276,20 @@ inline void classify16(const char *p, unsigned &gap, unsigned &nl) {
 
 struct RecordSpan { size_t begin, end, bodyBegin; };          // [begin, end): header line + body, without the leading '>'
 
-// contig bases of a record body (pass 1): everything but '\n' and gap characters
-uint64_t countBases(const char *p, const char *e) {
-    uint64_t skipped = 0;
+// pass 1 over a piece of a record body: contig bases (everything but '\n' and gap characters) and path positions
+// (everything but '\n')
+void countPiece(const char *p, const char *e, uint64_t &bases, uint64_t &positions) {
+    uint64_t skipped = 0, newlines = 0;
     const char *q = p;
     for (; q + 16 <= e; q += 16) {
         unsigned gap, nl;
         classify16(q, gap, nl);
         skipped += static_cast<uint64_t>(__builtin_popcount(gap | nl));
+        newlines += static_cast<uint64_t>(__builtin_popcount(nl));
     }
-    for (; q < e; ++q) skipped += (*q == '\n' || *q == 'N' || *q == 'n' || *q == 'X' || *q == 'x');
-    return static_cast<uint64_t>(e - p) - skipped;
+    for (; q < e; ++q) { skipped += (*q == '\n' || *q == 'N' || *q == 'n' || *q == 'X' || *q == 'x'); newlines += *q == '\n'; }
+    bases = static_cast<uint64_t>(e - p) - skipped;
+    positions = static_cast<uint64_t>(e - p) - newlines;
 }
 
 // pass 2: the record's contigs copied back to back to out (newlines and gaps dropped), its items and gaps listed
@@ -361,19 +364,40 @@ void parseFasta(const InputData &in, unsigned threads, std::vector<PathRec> &pat
         p = end + 1;
     }
     paths.resize(recs.size());
-    std::vector<uint64_t> bases(recs.size() + 1, 0);
-    parallelFor(recs.size(), threads, [&](size_t r) { bases[r + 1] = countBases(in.p + recs[r].bodyBegin, in.p + recs[r].end); });
-    for (size_t r = 0; r < recs.size(); ++r) bases[r + 1] += bases[r];
-    seqBytes = bases.back();
+    // A record is cut into pieces of kPiece bytes that are counted (pass 1) and copied (pass 2) in parallel: the largest
+    // record (a chromosome) does not bound the wall time.  Pieces start in an unknown state; runs of contig bases / gap
+    // characters that continue across a cut are stitched afterwards.
+    const size_t kPiece = getenv("TLS_PARSE_PIECE") ? std::max<size_t>(64, strtoull(getenv("TLS_PARSE_PIECE"), nullptr, 10)) : (8u << 20);   // tests shrink it
+    struct Piece { size_t rec; const char *p, *e; uint64_t bases = 0, positions = 0, outOffset = 0, posBase = 0; std::vector<Item> items; std::vector<Gap> gaps; };
+    std::vector<Piece> pieces;
+    std::vector<size_t> firstPiece(recs.size() + 1, 0);
+    for (size_t r = 0; r < recs.size(); ++r) {
+        firstPiece[r] = pieces.size();
+        const char *p = in.p + recs[r].bodyBegin, *e = in.p + recs[r].end;
+        if (p >= e) { Piece pc; pc.rec = r; pc.p = pc.e = e; pieces.push_back(std::move(pc)); continue; }
+        for (; p < e; p += kPiece) { Piece pc; pc.rec = r; pc.p = p; pc.e = std::min(e, p + kPiece); pieces.push_back(std::move(pc)); }
+    }
+    firstPiece[recs.size()] = pieces.size();
+    parallelFor(pieces.size(), threads, [&](size_t k) { countPiece(pieces[k].p, pieces[k].e, pieces[k].bases, pieces[k].positions); });
+    uint64_t outAcc = 0;
+    for (size_t r = 0; r < recs.size(); ++r) {
+        uint64_t posAcc = 0;
+        for (size_t k = firstPiece[r]; k < firstPiece[r + 1]; ++k) {
+            pieces[k].outOffset = outAcc; pieces[k].posBase = posAcc;
+            outAcc += pieces[k].bases; posAcc += pieces[k].positions;
+        }
+        paths[r].pathSize = posAcc;
+    }
+    seqBytes = outAcc;
     seq.reset(new uint8_t[seqBytes + 256]);
     memset(seq.get() + seqBytes, 0, 256);
+    parallelFor(pieces.size(), threads, [&](size_t k) {
+        Piece &pc = pieces[k];
+        uint64_t ignored = 0;
+        parseRecord(pc.p, pc.e, seq.get() + pc.outOffset, pc.bases, pc.outOffset, static_cast<uint32_t>(pc.rec), pc.items, pc.gaps, ignored);
+    });
     std::vector<std::vector<Item>> recItems(recs.size());
-    // largest records first: they bound the wall time of the parallel parse
-    std::vector<size_t> order(recs.size());
-    for (size_t r = 0; r < recs.size(); ++r) order[r] = r;
-    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return recs[a].end - recs[a].begin > recs[b].end - recs[b].begin; });
-    parallelFor(recs.size(), threads, [&](size_t k) {
-        const size_t r = order[k];
+    parallelFor(recs.size(), threads, [&](size_t r) {
         PathRec &rec = paths[r];
         rec.seqPos = static_cast<uint32_t>(r);
         const size_t headEnd = recs[r].bodyBegin > recs[r].begin && recs[r].bodyBegin <= recs[r].end && in.p[recs[r].bodyBegin - 1] == '\n'
@@ -381,8 +405,26 @@ void parseFasta(const InputData &in, unsigned threads, std::vector<PathRec> &pat
         const char *sp = static_cast<const char *>(memchr(in.p + recs[r].begin, ' ', headEnd - recs[r].begin));
         rec.header.assign(in.p + recs[r].begin, sp ? sp : in.p + headEnd);
         rec.header.erase(std::remove(rec.header.begin(), rec.header.end(), '\r'), rec.header.end());   // walkPath, src/input.cpp:950
-        parseRecord(in.p + recs[r].bodyBegin, in.p + recs[r].end, seq.get() + bases[r], bases[r + 1] - bases[r], bases[r], static_cast<uint32_t>(r), recItems[r],
-                    rec.gaps, rec.pathSize);
+        // stitch the pieces: positions become path positions; a run that reaches the end of a piece and one of the same
+        // kind that starts the next piece are one run
+        std::vector<Item> &its = recItems[r];
+        for (size_t k = firstPiece[r]; k < firstPiece[r + 1]; ++k) {
+            Piece &pc = pieces[k];
+            for (Item &it : pc.items) {
+                it.absPos += pc.posBase;
+                if (!its.empty() && it.absPos == pc.posBase && its.back().absPos + its.back().len == it.absPos &&
+                    its.back().offset + its.back().len == it.offset) {
+                    if (static_cast<uint64_t>(its.back().len) + it.len > 0xFFFFFFFFull) die("Error: a contig is longer than 2^32-1 bases.\n");
+                    its.back().len += it.len;
+                } else its.push_back(it);
+            }
+            for (Gap &g : pc.gaps) {
+                g.start += pc.posBase;
+                if (!rec.gaps.empty() && g.start == pc.posBase && rec.gaps.back().start + rec.gaps.back().length == g.start) rec.gaps.back().length += g.length;
+                else rec.gaps.push_back(g);
+            }
+            std::vector<Item>().swap(pc.items);
+        }
     });
     size_t total = 0;
     for (auto &v : recItems) total += v.size();

@@ -11,8 +11,9 @@ own assembly; --scaling strong: ONE assembly, its contigs partitioned over the r
 (teloscope_b200.shard.partition_items).  No data-path collective either way; rank 0 prints ONE JSON line.
 
   value    Gbp/s with the assembly already resident in HBM (device pointer handed to the C ABI),
-           everything else of the job included (kernels, result copies, host-side assembly), driven the
-           way the double-buffered C ABI is meant to be: two tickets in flight (value_one_ticket beside it)
+           everything else of the job included (kernels, result copies, host-side assembly), one ticket at a
+           time (--depth 2: two tickets in flight; measured no faster, the persistent scan CTAs of step i + 1 keep
+           the block kernels of step i off the SMs — value_one_ticket is always reported beside it)
   e2e      same call with the sequence in pinned HOST memory: H2D + kernels + D2H in the timed region
   roofline scan kernel only: algorithmic bytes / CUDA-event duration against the measured HBM peak
   pipeline_e2e  file -> files: the same assembly as a FASTA file through teloscope_b200/teloscope-b200 (host ingest, C ABI,
@@ -602,7 +603,7 @@ def main():
     ap.add_argument("--ref-scale", type=float, default=None, help="--impl reference: size factor of its assembly (default: --scale, the repo arm's)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one assembly per rank; strong: one assembly, its contigs partitioned over the ranks")
-    ap.add_argument("--depth", type=int, default=2, choices=[1, 2], help="tickets in flight in the timed device-resident loop")
+    ap.add_argument("--depth", type=int, default=1, choices=[1, 2], help="tickets in flight in the timed device-resident loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-records", action="store_true", help="32-byte window / 16-byte match records instead of the compact forms")
     ap.add_argument("--no-extra", action="store_true", help="skip the plant-assembly and read-scorer measurements")

@@ -17,3 +17,4 @@ if [ "$2" = ncu ]; then
     -o $out/prof_rows python scripts/trace_bench.py 0.25 > $out/ncu_full.log 2>&1
   tail -2 $out/ncu_full.log
 fi
+timeout 300 python scripts/trace_reads.py > $out/trace_reads.log 2>&1; tail -3 $out/trace_reads.log

@@ -99,6 +99,9 @@ struct Slot {
     cudaEvent_t evScanDone = nullptr, evCopyDone = nullptr;
     static constexpr int kMaxParts = 8;      // launches of the window-row kernel on a large batch (result copy overlaps the scan)
     cudaEvent_t evPart[kMaxParts] = {};
+    cudaStream_t partStream[kMaxParts] = {};  // launches 1 .. of the window-row kernel: side by side with launch 0, so that their CTAs fill
+                                              // the SMs the previous launch's last units leave idle
+    cudaEvent_t evSetup = nullptr;
     unsigned long long *hScanDev = nullptr;   // device view of hScan (mapped): scan totals without a copy
     cudaEvent_t evScan0 = nullptr, evScan1 = nullptr, evFast1 = nullptr, evAll0 = nullptr, evAll1 = nullptr;
     float fastMs = 0;
@@ -166,6 +169,11 @@ struct tls_ctx {
     bool forceGeneral = false;               // TLS_FORCE_GENERAL=1 or a lean-kernel layout failure
     bool noRowKernel = false;                // TLS_NO_ROW_KERNEL=1: 1536-base-row lean kernel instead of the window-row kernel
     bool noReadKernel = false;               // TLS_NO_READ_KERNEL=1: reads through the general scan + block kernels (A/B tests)
+    // cuStreamWaitValue32 through the runtime's driver entry point lookup (no link against libcuda): the window copies of a
+    // finished range of units are released by a stream wait on a progress word the scan kernel counts up, so ONE launch
+    // scans the batch while its results already go home (TLS_ROW_PARTS=n launches instead when it is not available)
+    int (*streamWaitValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int) = nullptr;
+    int rowRanges = 8;                       // TLS_ROW_RANGES=n: ranges of units whose windows go home separately (1..8)
     bool zeroCopyWindows = false;            // TLS_OUT_COMPACT: the window-row kernel stores its 16-byte window records straight into the
                                              // pinned host buffer (posted writes over PCIe during the scan): measured slower (scan 1.23 ms against 0.95 + copy), off unless TLS_WINDOWS_ZEROCOPY=1
     bool compact = false;                    // TLS_OUT_COMPACT: tls_window16 / tls_match8 results
@@ -407,9 +415,22 @@ static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
         s.hScan.cap = 4096;
         TLS_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.hScanDev), s.hScan.p, 0));
     }
+    {
+        bool layoutOk = false;
+        TLS_CUDA(probeRowLayout(ctx->slot[0].dCounters.as<unsigned int>(), layoutOk, ctx->slot[0].stream));
+        if (!layoutOk) { ctx->noRowKernel = true; ctx->noReadKernel = true; }     // tile kernels take over: same results, slower
+    }
     ctx->forceGeneral = std::getenv("TLS_FORCE_GENERAL") != nullptr;
-    ctx->noRowKernel = std::getenv("TLS_NO_ROW_KERNEL") != nullptr;
-    ctx->noReadKernel = std::getenv("TLS_NO_READ_KERNEL") != nullptr;
+    ctx->noRowKernel = ctx->noRowKernel || std::getenv("TLS_NO_ROW_KERNEL") != nullptr;
+    ctx->noReadKernel = ctx->noReadKernel || std::getenv("TLS_NO_READ_KERNEL") != nullptr;
+    if (!std::getenv("TLS_ROW_PARTS")) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess && fn)
+            ctx->streamWaitValue32 = reinterpret_cast<int (*)(cudaStream_t, unsigned long long, unsigned int, unsigned int)>(fn);
+        cudaGetLastError();
+    }
+    if (const char *e = std::getenv("TLS_ROW_RANGES")) ctx->rowRanges = std::min(static_cast<int>(Slot::kMaxParts), std::max(1, std::atoi(e)));
     ctx->zeroCopyWindows = std::getenv("TLS_WINDOWS_ZEROCOPY") != nullptr;
     if (const char *e = std::getenv("TLS_ROW_PARTS")) ctx->rowParts = std::min(static_cast<int>(Slot::kMaxParts), std::max(1, std::atoi(e)));
     if (const char *e = std::getenv("TLS_ROW_MIN_WINDOWS")) ctx->rowMinWindows = std::max(1, std::atoi(e));
@@ -442,6 +463,8 @@ void tls_destroy(tls_ctx *ctx) {
         if (s.evGather) cudaEventDestroy(s.evGather);
         if (s.evScanDone) cudaEventDestroy(s.evScanDone);
         for (cudaEvent_t &e : s.evPart) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (cudaStream_t &st : s.partStream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
+        if (s.evSetup) cudaEventDestroy(s.evSetup);
         if (s.evCopyDone) cudaEventDestroy(s.evCopyDone);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -608,30 +631,72 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             f.status = redo + 1;
             f.cfg = cfg;
             const uint32_t gridWarps = static_cast<uint32_t>(ctx->smCount) * kRowWarps;
-            const int parts = (anyWindows && !zeroCopy && nRow >= 16u * gridWarps) ? ctx->rowParts : 1;
             auto firstWindowOfUnit = [&](uint32_t u) {          // rowRegions are sorted by unit0
                 size_t lo = 0, hi = s.rowRegions.size();
                 while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (s.rowRegions[mid].unit0 <= u) lo = mid; else hi = mid; }
                 return static_cast<uint64_t>(s.rowRegions[lo].winBase) + static_cast<uint64_t>(u - s.rowRegions[lo].unit0) * kRowsPerUnit;
             };
+            const bool bigBatch = anyWindows && !zeroCopy && nRow >= 16u * gridWarps;
+            const int ranges = (bigBatch && ctx->streamWaitValue32) ? ctx->rowRanges : 1;
+            const int parts = (bigBatch && !ctx->streamWaitValue32) ? ctx->rowParts : 1;
+            if (ranges > 1) {
+                // ONE launch; the copy stream waits (stream wait-value, no host thread, no SM) for the progress word of each range
+                // of units and sends that range's windows home while the kernel is still scanning the next ones
+                const uint32_t upp = (nRow + static_cast<uint32_t>(ranges) - 1) / static_cast<uint32_t>(ranges);
+                f.units = s.dRowTiles.as<DevRowUnit>(); f.nUnits = nRow;
+                f.unitCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 64);
+                f.partDone = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 96);
+                f.unitsPerPart = upp;
+                if (!s.evSetup) TLS_CUDA(cudaEventCreateWithFlags(&s.evSetup, cudaEventDisableTiming));
+                TLS_CUDA(cudaEventRecord(s.evSetup, s.stream));          // counters zeroed, small contigs' windows final
+                TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evSetup, 0));
+                TLS_CUDA(launchRowScan(f, static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (nRow + kRowWarps - 1) / kRowWarps)), s.stream));
+                s.launches++;
+                for (int k = 0; k + 1 < ranges; ++k) {
+                    const uint32_t uHi = std::min<uint32_t>(nRow, static_cast<uint32_t>(k + 1) * upp), uLo = static_cast<uint32_t>(k) * upp;
+                    if (uLo >= nRow) break;
+                    const int rc = ctx->streamWaitValue32(s.copyStream, reinterpret_cast<unsigned long long>(f.partDone + k), uHi - uLo, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+                    if (rc != 0) return fail(TLS_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", rc);
+                    const uint64_t wEnd = uHi >= nRow ? s.nWindows : firstWindowOfUnit(uHi);
+                    if (wEnd > winCopied)
+                        TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * winRec, winSrc + winCopied * winRec,
+                                                 (wEnd - winCopied) * winRec, cudaMemcpyDeviceToHost, s.copyStream));
+                    winCopied = std::max(winCopied, wEnd);
+                }
+            } else {
+            bool partsPending = false;
             for (int part = 0; part < parts; ++part) {
                 const uint32_t uLo = static_cast<uint32_t>(static_cast<uint64_t>(nRow) * part / parts);
                 const uint32_t uHi = static_cast<uint32_t>(static_cast<uint64_t>(nRow) * (part + 1) / parts);
                 f.units = s.dRowTiles.as<DevRowUnit>() + uLo; f.nUnits = uHi - uLo;
                 f.unitCursor = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 64) + part;
                 const int grid = static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (f.nUnits + kRowWarps - 1) / kRowWarps));
-                TLS_CUDA(launchRowScan(f, grid, s.stream));
+                cudaStream_t st = s.stream;
+                if (part > 0) {                               // its own stream, behind everything enqueued before the first launch
+                    if (!s.partStream[part]) TLS_CUDA(cudaStreamCreateWithFlags(&s.partStream[part], cudaStreamNonBlocking));
+                    st = s.partStream[part];
+                    TLS_CUDA(cudaStreamWaitEvent(st, s.evSetup, 0));
+                }
+                if (part == 0 && parts > 1) {                 // the point the other launches wait for: just before launch 0
+                    if (!s.evSetup) TLS_CUDA(cudaEventCreateWithFlags(&s.evSetup, cudaEventDisableTiming));
+                    TLS_CUDA(cudaEventRecord(s.evSetup, s.stream));
+                }
+                TLS_CUDA(launchRowScan(f, grid, st));
                 s.launches++;
+                if (!s.evPart[part]) TLS_CUDA(cudaEventCreateWithFlags(&s.evPart[part], cudaEventDisableTiming));
+                TLS_CUDA(cudaEventRecord(s.evPart[part], st));
+                if (part > 0) partsPending = true;
                 if (part + 1 < parts) {
-                    const uint64_t wEnd = firstWindowOfUnit(uHi);   // every window below it is final now
-                    if (!s.evPart[part]) TLS_CUDA(cudaEventCreateWithFlags(&s.evPart[part], cudaEventDisableTiming));
-                    TLS_CUDA(cudaEventRecord(s.evPart[part], s.stream));
+                    const uint64_t wEnd = firstWindowOfUnit(uHi);   // every window below it is final once launches 0 .. part are done
                     TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evPart[part], 0));
                     if (wEnd > winCopied)
                         TLS_CUDA(cudaMemcpyAsync(s.hWindows.as<uint8_t>() + winCopied * winRec, winSrc + winCopied * winRec,
                                                  (wEnd - winCopied) * winRec, cudaMemcpyDeviceToHost, s.copyStream));
                     winCopied = std::max(winCopied, wEnd);
                 }
+            }
+            if (partsPending)                                 // the main stream goes on when every launch is done
+                for (int part = 1; part < parts; ++part) TLS_CUDA(cudaStreamWaitEvent(s.stream, s.evPart[part], 0));
             }
         }
         TLS_CUDA(cudaEventRecord(s.evFast1, s.stream));

@@ -243,6 +243,8 @@ struct RowParams {
     DevItemCounts *itemCounts;
     unsigned int *status;          // set to 1 when the shared memory layout assumption fails
     unsigned int *unitCursor;      // work counter of this launch, zeroed before it
+    unsigned int *partDone;        // progress: partDone[u / unitsPerPart] counts the finished units (the copy stream waits on these words)
+    uint32_t unitsPerPart;         // 0: no progress counters
     DevConfig cfg;
 };
 

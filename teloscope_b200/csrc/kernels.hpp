@@ -18,7 +18,9 @@ cudaError_t launchFastScan(const FastParams &p, int grid, cudaStream_t stream);
 // window-row kernel (scan_rows.cu): genome mode, one direct pattern length, kRowMinWindow <= window <= kRowMaxLen
 size_t rowSmemBytes();
 bool rowConfigOk(const DevConfig &c);
-uint32_t rowNpos(uint32_t patLen);       // start offsets one table byte answers: 3 (pattern length <= 6), 2 (length 7)
+uint32_t rowNpos(uint32_t patLen);
+// does the dynamic shared memory block start where the window-row kernel / read scorer expect it (absolute addressing)?
+cudaError_t probeRowLayout(unsigned int *dWord, bool &ok, cudaStream_t stream);       // start offsets one table byte answers: 3 (pattern length <= 6), 2 (length 7)
 cudaError_t launchRowScan(const RowParams &p, int grid, cudaStream_t stream);
 // fills units[0, nUnits) from the per-contig table (regions sorted by unit0)
 cudaError_t launchRowPlan(const DevRowRegion *regions, uint32_t nRegions, uint32_t windowSize, DevRowUnit *units,

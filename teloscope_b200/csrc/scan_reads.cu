@@ -136,6 +136,8 @@ __global__ void __launch_bounds__(kReadThreads, 1) readScanKernel(const ReadPara
                 s.active = true; s.start = f; s.last = la; s.count = pk & 0xFFu; s.can = pk >> 8;
             }
         }
+        // a run that no start of a later row can reach any more is closed now: the next rows then take the cheap path above
+        if (s.active && rowPos + kReadStride - s.last > K) closeRun(s);
     };
 
     uint4 c0 = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u), c1 = c0;
@@ -218,7 +220,9 @@ __global__ void __launch_bounds__(kReadThreads, 1) readScanKernel(const ReadPara
                 nHits += __popc(H);
                 feed(fw, H & MF, CB & MF, rs);
                 feed(rv, H & ~MF, CB & ~MF, rs);
-                if ((fw.pend && (!trackTotal || fw.total >= 2u)) || (rv.pend && (!trackTotal || rv.total >= 2u))) { decided = true; break; }
+                if (fw.pend | rv.pend) {
+                    if ((fw.pend && (!trackTotal || fw.total >= 2u)) || (rv.pend && (!trackTotal || rv.total >= 2u))) { decided = true; break; }
+                }
             }
         }
         bool pass = decided;

@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
     // Units are handed out by a counter (a dense unit of a telomere cap costs several sparse ones: a static split leaves
     // SMs idle at the end).  A warp always knows its next unit one unit ahead (its first row is loaded during the current
     // unit's last row) and has the index of the one after that on order.
+    constexpr uint32_t kProgressBatch = 8;
+    uint32_t doneRange = 0, doneCount = 0;
     uint32_t u, uNext, uPending = 0;
     if (lane0) u = atomicAdd(p.unitCursor, 2u);
     u = __shfl_sync(0xFFFFFFFFu, u, 0);
@@ -595,6 +597,26 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
                 if (v) atomicAdd(ic + (lane - 3), v);
             }
         }
+        if (p.unitsPerPart) {
+            // Progress for the copy stream (it waits on these words): finished units are counted per range of units.  The
+            // fence that makes a unit's windows visible before its count is dear (it drains the warp's outstanding
+            // memory operations), so a warp reports several units at once: when it moves on to another range, every
+            // kProgressBatch units, and when it leaves.
+            const uint32_t range = u / p.unitsPerPart;
+            if (doneCount && (range != doneRange || doneCount >= kProgressBatch)) {
+                __threadfence();
+                __syncwarp();
+                if (lane0) atomicAdd(p.partDone + doneRange, doneCount);
+                doneCount = 0;
+            }
+            doneRange = range;
+            ++doneCount;
+            if (uNext >= nUnits) {
+                __threadfence();
+                __syncwarp();
+                if (lane0) atomicAdd(p.partDone + doneRange, doneCount);
+            }
+        }
         if (uNext >= nUnits) break;
         u = uNext;
         uNext = __shfl_sync(0xFFFFFFFFu, uPending, 0);
@@ -636,6 +658,26 @@ cudaError_t launchRowPlan(const DevRowRegion *regions, uint32_t nRegions, uint32
 }
 
 size_t rowSmemBytes() { return kRowSmemTotal; }
+
+// The window-row kernel and the read scorer address their shared-memory tables with absolute addresses (immediates): the
+// dynamic block must start kWindowBase bytes into the CTA's shared window.  Probed once per context with the kernels' own
+// launch shape; when a driver lays it out differently the context falls back to the tile kernels instead of failing later.
+__global__ void __launch_bounds__(kRowThreads, 1) rowLayoutProbeKernel(unsigned int *out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (threadIdx.x == 0) *out = smemAddr(smem);
+}
+cudaError_t probeRowLayout(unsigned int *dWord, bool &ok, cudaStream_t stream) {
+    ok = false;
+    cudaError_t e = cudaFuncSetAttribute(rowLayoutProbeKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kRowSmemTotal));
+    if (e != cudaSuccess) return e;
+    rowLayoutProbeKernel<<<1, kRowThreads, kRowSmemTotal, stream>>>(dWord);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    unsigned int h = 0;
+    if ((e = cudaMemcpyAsync(&h, dWord, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+    ok = h == kWindowBase;
+    return cudaSuccess;
+}
 
 uint32_t rowNpos(uint32_t patLen) { return patLen >= 7 ? 2u : 3u; }
 

@@ -169,3 +169,26 @@ def test_pipeline_over_several_devices_equals_one(tmp_path):
         outs[gpus] = (p.stdout, p.stderr, {f.name: f.read_bytes() for f in d.iterdir()})
     assert len(outs[1][2]) == 11
     assert outs[2] == outs[1] and outs[3] == outs[1]
+
+
+def test_degenerate_overlap_is_refused_with_the_reason(golden, tmp_path):
+    """-s < L or -w minus -s < L (L = pattern length): the reference's scan start of a non-first window is
+    min(step - L, overlap - L) in uint32 (src/teloscope.cpp:413-415).  It wraps or lands near the window's end, so most of
+    every window is never scanned.  The golden outputs of the unmodified reference show it (windows of a 50 % GC fixture
+    with a GC track below 1 %, a T2T chromosome reported with one telomere); the device path does not reproduce that
+    arithmetic and says so."""
+    cases, fixtures = golden
+    seen = 0
+    for c in cases:
+        if c["kind"] != "fasta":
+            continue
+        cfg, flags = ol.config_from_args(c["args"])
+        if device_supports(cfg, flags["genome"]):
+            continue
+        seen += 1
+        if "window_gc.bedgraph" in c["files"] and cfg.window_size - cfg.step < 6 <= cfg.step:
+            gc = [float(l.split("\t")[3]) for l in c["files"]["window_gc.bedgraph"][1:]]
+            assert gc[0] > 40 and min(gc[1:]) < 1, gc                  # the reference only looked at the last few bases of those windows
+        rc, out, err, files = run_case(tmp_path, c["fixture"], fixtures[c["fixture"]].tobytes(), c["args"])
+        assert rc == 1 and "overlapping windows need" in err, (c["args"], err)
+    assert seen >= 2

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """File -> files timing of the host pipeline binary (and, with --ref, of the unmodified reference) on the
 synthetic human-shaped assembly of bench.py written as FASTA to /dev/shm.
-    python scripts/pipeline_bench.py [scale] [--ref] [--repeat N]"""
+    python scripts/pipeline_bench.py [scale] [--ref] [--repeat N] [--gpus N]"""
 import shutil, subprocess, sys, tempfile, time, os
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -21,7 +21,8 @@ try:
     print(f"FASTA: {bases/1e6:.0f} Mbp, {fa.stat().st_size/1e6:.0f} MB written in {time.perf_counter()-t0:.1f} s", flush=True)
     del seq
     env = dict(os.environ, TLS_PIPE_TRACE="1")
-    runs = [("teloscope-b200", [str(ROOT / "teloscope_b200" / "teloscope-b200")])]
+    gpus = sys.argv[sys.argv.index("--gpus") + 1] if "--gpus" in sys.argv else "1"
+    runs = [("teloscope-b200", [str(ROOT / "teloscope_b200" / "teloscope-b200"), "--gpus", gpus])]
     if "--ref" in sys.argv:
         runs.append(("reference", [str(ROOT / "oracle" / "_ref" / "teloscope"), "-j", str(os.cpu_count())]))
     outs = {}

@@ -351,17 +351,31 @@ void parseRecord(const char *p, const char *e, uint8_t *out, uint64_t outCap, ui
 }
 
 void parseFasta(const InputData &in, unsigned threads, std::vector<PathRec> &paths, std::vector<Item> &items,
-                std::unique_ptr<uint8_t[]> &seq, uint64_t &seqBytes) {
+                uint8_t *&seq, uint64_t &seqBytes) {
     if (in.n == 0 || in.p[0] != '>') die("Error: '%s' does not look like a FASTA file.\n", "input");
     // records: a record runs to the next '>' wherever it stands (gfalibs reads the sequence with getline(..., '>'))
+    // the '>' bytes are looked for in parallel (a serial memchr over a 3 GB file costs 0.3 s)
     std::vector<RecordSpan> recs;
-    for (size_t p = 1;;) {
-        const char *g = static_cast<const char *>(memchr(in.p + p, '>', in.n - p));
-        const size_t end = g ? static_cast<size_t>(g - in.p) : in.n;
-        const char *nlp = static_cast<const char *>(memchr(in.p + p, '\n', end - p));
-        recs.push_back({p, end, nlp ? static_cast<size_t>(nlp - in.p) + 1 : end});
-        if (!g) break;
-        p = end + 1;
+    {
+        const size_t nChunks = std::max<size_t>(1, std::min<size_t>(threads * 4, in.n / (4u << 20) + 1)), chunk = (in.n + nChunks - 1) / nChunks;
+        std::vector<std::vector<size_t>> found(nChunks);
+        parallelFor(nChunks, threads, [&](size_t c) {
+            const size_t lo = std::max<size_t>(1, c * chunk), hi = std::min(in.n, (c + 1) * chunk);
+            for (size_t q = lo; q < hi;) {
+                const char *g = static_cast<const char *>(memchr(in.p + q, '>', hi - q));
+                if (!g) break;
+                found[c].push_back(static_cast<size_t>(g - in.p));
+                q = static_cast<size_t>(g - in.p) + 1;
+            }
+        });
+        size_t p = 1;
+        auto close = [&](size_t end) {
+            const char *nlp = static_cast<const char *>(memchr(in.p + p, '\n', end - p));
+            recs.push_back({p, end, nlp ? static_cast<size_t>(nlp - in.p) + 1 : end});
+            p = end + 1;
+        };
+        for (const auto &v : found) for (size_t g : v) close(g);
+        close(in.n);
     }
     paths.resize(recs.size());
     // A record is cut into pieces of kPiece bytes that are counted (pass 1) and copied (pass 2) in parallel: the largest
@@ -389,12 +403,18 @@ void parseFasta(const InputData &in, unsigned threads, std::vector<PathRec> &pat
         paths[r].pathSize = posAcc;
     }
     seqBytes = outAcc;
-    seq.reset(new uint8_t[seqBytes + 256]);
-    memset(seq.get() + seqBytes, 0, 256);
+    {   // the contig buffer: 2 MiB aligned and advised for huge pages (3 GB of first-touch faults otherwise); it lives until exit
+        const size_t cap = (static_cast<size_t>(seqBytes) + 256 + (2u << 20) - 1) & ~static_cast<size_t>((2u << 20) - 1);
+        void *mem = nullptr;
+        if (posix_memalign(&mem, 2u << 20, cap) != 0 || !mem) die("Error: out of memory (%zu bytes for the sequence).\n", cap);
+        madvise(mem, cap, MADV_HUGEPAGE);
+        seq = static_cast<uint8_t *>(mem);
+    }
+    memset(seq + seqBytes, 0, 256);
     parallelFor(pieces.size(), threads, [&](size_t k) {
         Piece &pc = pieces[k];
         uint64_t ignored = 0;
-        parseRecord(pc.p, pc.e, seq.get() + pc.outOffset, pc.bases, pc.outOffset, static_cast<uint32_t>(pc.rec), pc.items, pc.gaps, ignored);
+        parseRecord(pc.p, pc.e, seq + pc.outOffset, pc.bases, pc.outOffset, static_cast<uint32_t>(pc.rec), pc.items, pc.gaps, ignored);
     });
     std::vector<std::vector<Item>> recItems(recs.size());
     parallelFor(recs.size(), threads, [&](size_t r) {
@@ -808,7 +828,7 @@ int main(int argc, char **argv) {
     // ---- ingest ---------------------------------------------------------------------------------------------
     std::vector<PathRec> paths;
     std::vector<Item> items;
-    std::unique_ptr<uint8_t[]> seqOwner;
+    uint8_t *seqOwner = nullptr;
     uint64_t seqBytes = 0;
     {
         InputData in;
@@ -819,7 +839,7 @@ int main(int argc, char **argv) {
         if (in.n == 0 || in.p[0] != '>') { ctxThread.join(); die("Error: '%s' does not look like a FASTA file.\n", o.inSequence.c_str()); }
         parseFasta(in, threads, paths, items, seqOwner, seqBytes);
     }
-    const uint8_t *seq = seqOwner.get();
+    const uint8_t *seq = seqOwner;
     timer.mark("parse FASTA");
     ctxThread.join();
     if (ctxRc != TLS_OK) die("Error: tls_create failed: %s\n", ctxErr.c_str());

@@ -605,7 +605,8 @@ def main():
                     help="weak: one assembly per rank; strong: one assembly, its contigs partitioned over the ranks")
     ap.add_argument("--depth", type=int, default=1, choices=[1, 2], help="tickets in flight in the timed device-resident loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--full-records", action="store_true", help="32-byte window / 16-byte match records instead of the compact forms")
+    ap.add_argument("--full-records", action="store_true", help="32-byte window / 16-byte match records instead of the packed forms")
+    ap.add_argument("--compact-records", action="store_true", help="16-byte window / 8-byte match records (TLS_OUT_COMPACT) instead of the packed forms")
     ap.add_argument("--no-extra", action="store_true", help="skip the plant-assembly and read-scorer measurements")
     ap.add_argument("--seed", type=int, default=42)
     args = ap.parse_args()
@@ -668,7 +669,8 @@ def main():
     host_np = host.numpy()
     # compact result records (TLS_OUT_COMPACT: 16 bytes per window, 8 per -m match): half the bytes over PCIe
     sc = tb.Scanner(tb.ScanConfig(canonical="TTAGGG", patterns=PATTERNS, out_acgt=True, out_matches=True,
-                                  compact=not args.full_records), device=local)
+                                  compact=args.compact_records and not args.full_records,
+                                  packed=not args.full_records and not args.compact_records), device=local)
 
     # collect(copy=False): results are read in place from the ctx's pinned buffers (what a C++ host
     # would do through the C ABI); release() hands the ticket back
@@ -786,7 +788,8 @@ def main():
                                       "value_one_ticket: submit, collect, release one step after the other); e2e: two tickets in flight "
                                       "(H2D of step i+1 overlaps step i)"),
                        "result_records": "full (32-byte windows, 16-byte matches)" if args.full_records else
-                                         "compact (TLS_OUT_COMPACT: 16-byte windows, 8-byte item-relative matches)"},
+                                         ("compact (TLS_OUT_COMPACT: 16-byte windows, 8-byte item-relative matches)" if args.compact_records else
+                                          "packed (TLS_OUT_PACKED: 12-byte windows of 10-bit counts, 4-byte item-relative matches)")},
             "e2e": {"value": total_bases * args.steps / elapsed_e2e / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

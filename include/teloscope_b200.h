@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define TLS_ABI_VERSION 2   /* 2: tls_result grew (windows16, canonical8, noncanonical8), TLS_OUT_COMPACT */
+#define TLS_ABI_VERSION 3   /* 2: tls_result grew (windows16, canonical8, noncanonical8), TLS_OUT_COMPACT; 3: TLS_OUT_PACKED (windows12, canonical4, noncanonical4, pattern_len) */
 
 typedef enum {
     TLS_OK = 0,
@@ -82,6 +82,17 @@ typedef struct {
     uint8_t is_canonical;
 } tls_match8;             /* 8 bytes */
 
+/* Packed forms (TLS_OUT_PACKED): the fewest bytes over the host link — what bounds a multi-GPU box whose GPUs share it.
+ * Only for pattern tables of ONE length L and window_size <= 1023 (tls_create refuses the flag otherwise): the window
+ * holds COUNTS of matches (covered bp = count x L), ten bits per field. */
+typedef struct {
+    uint32_t w[3];        /* w[0] = A | C << 10 | G << 20;  w[1] = T | canonical matches << 10 | all matches << 20;
+                             w[2] = forward matches.  can_cov = canonical x L, noncan_cov = (all - canonical) x L,
+                             fwd_cov = forward x L, rev_cov = (all - forward) x L (L = tls_result.pattern_len) */
+} tls_window12;           /* 12 bytes */
+typedef uint32_t tls_match4;   /* bits 0..30: offset in the item (items of 2^31 bases or more are refused at tls_submit),
+                                  bit 31: forward strand; len = pattern_len; canonical list: is_canonical = 1 */
+
 /* ---- configuration ---------------------------------------------------------------------------- */
 
 enum {                    /* tls_config.outputs */
@@ -90,9 +101,11 @@ enum {                    /* tls_config.outputs */
     TLS_OUT_ITS = 1u << 2,      /* -i      : interstitial blocks are always computed in genome
                                              mode (the report needs their count); flag kept for
                                              symmetry with the reference's toggles              */
-    TLS_OUT_COMPACT = 1u << 3   /* windows come back as tls_window16 (tls_result.windows16) and the -m lists as
+    TLS_OUT_COMPACT = 1u << 3,  /* windows come back as tls_window16 (tls_result.windows16) and the -m lists as
                                    tls_match8 (canonical8 / noncanonical8); windows / canonical / noncanonical
                                    are then NULL                                                */
+    TLS_OUT_PACKED = 1u << 4    /* windows as tls_window12 (windows12), -m lists as tls_match4 (canonical4 /
+                                   noncanonical4); every other window / match pointer is NULL      */
 };
 
 typedef struct {
@@ -156,6 +169,10 @@ typedef struct {
     /* TLS_OUT_COMPACT (same *_off arrays) */
     const tls_window16 *windows16;
     const tls_match8 *canonical8, *noncanonical8;
+    /* TLS_OUT_PACKED (same *_off arrays) */
+    const tls_window12 *windows12;
+    const tls_match4 *canonical4, *noncanonical4;
+    uint32_t pattern_len;             /* the pattern length when the table has one, else 0 */
 } tls_result;
 
 typedef struct tls_ctx tls_ctx;

@@ -25,9 +25,9 @@ __all__ = ["ScanConfig", "Scanner", "BatchResult", "expand_patterns", "load_libr
 
 # TLS_LIB: another build of the library (kernel tuning experiments); the product is the in-tree default
 LIB_PATH = Path(os.environ.get("TLS_LIB") or (Path(__file__).resolve().parent / "libteloscope_b200.so"))
-ABI_VERSION = 2
+ABI_VERSION = 3
 MODE_GENOME, MODE_TIPS, MODE_READS = 0, 1, 2
-OUT_ACGT, OUT_MATCHES, OUT_ITS, OUT_COMPACT = 1, 2, 4, 8
+OUT_ACGT, OUT_MATCHES, OUT_ITS, OUT_COMPACT, OUT_PACKED = 1, 2, 4, 8, 16
 
 MATCH_DT = np.dtype([("pos", "<u8"), ("len", "<u2"), ("fwd", "u1"), ("can", "u1"), ("pad", "<u4")])
 BLOCK_DT = np.dtype([("start", "<u8"), ("len", "<u4"), ("counts", "<u4"), ("fwd_count", "<u4"),
@@ -40,6 +40,8 @@ WINDOW_DT = np.dtype([("acgt", "<u4", (4,)), ("can_cov", "<u4"), ("noncan_cov", 
 WINDOW16_DT = np.dtype([("acgt", "<u2", (4,)), ("can_cov", "<u2"), ("noncan_cov", "<u2"),
                         ("fwd_cov", "<u2"), ("rev_cov", "<u2")])
 MATCH8_DT = np.dtype([("pos", "<u4"), ("len", "<u2"), ("fwd", "u1"), ("can", "u1")])
+# packed result forms (ScanConfig.packed / TLS_OUT_PACKED): tls_window12 (three words of 10-bit counts), tls_match4 (u32)
+WINDOW12_DT = np.dtype([("w", "<u4", (3,))])
 assert MATCH_DT.itemsize == 16 and BLOCK_DT.itemsize == 48 and WINDOW_DT.itemsize == 32
 assert WINDOW16_DT.itemsize == 16 and MATCH8_DT.itemsize == 8
 
@@ -76,7 +78,9 @@ class _Result(C.Structure):
                 ("scan_kernel_ms", C.c_float), ("device_ms", C.c_float),
                 ("n_bases_scanned", C.c_uint64), ("n_matches", C.c_uint64),
                 ("n_kernel_launches", C.c_uint32), ("lean_kernel_ms", C.c_float),
-                ("windows16", C.c_void_p), ("canonical8", C.c_void_p), ("noncanonical8", C.c_void_p)]
+                ("windows16", C.c_void_p), ("canonical8", C.c_void_p), ("noncanonical8", C.c_void_p),
+                ("windows12", C.c_void_p), ("canonical4", C.c_void_p), ("noncanonical4", C.c_void_p),
+                ("pattern_len", C.c_uint32)]
 
 
 EXPORTS = ("tls_expand_patterns", "tls_device_count", "tls_create", "tls_destroy", "tls_submit",
@@ -158,6 +162,7 @@ class ScanConfig:
     out_acgt: bool = True                     # -g or -e
     out_matches: bool = True                  # -m
     compact: bool = False                     # TLS_OUT_COMPACT: 16-byte window and 8-byte match records
+    packed: bool = False                      # TLS_OUT_PACKED: 12-byte window and 4-byte match records (one pattern length, -w <= 1023)
     canonical_fwd: str = field(init=False)
     canonical_rev: str = field(init=False)
 
@@ -194,7 +199,22 @@ class BatchResult:
 
         self.window_off = off(r.window_off)
         n_win = self.window_off[-1] if r.mode == MODE_GENOME else 0
-        self.windows = arr(r.windows16, n_win, WINDOW16_DT) if r.windows16 else arr(r.windows, n_win, WINDOW_DT)
+        self.pattern_len = int(r.pattern_len)
+        if r.windows12:
+            w12 = arr(r.windows12, n_win, WINDOW12_DT)
+            if copy:                      # widened to the full record: covered bp = count x pattern length
+                w, L = w12["w"].astype(np.uint32), self.pattern_len
+                full = np.zeros(len(w12), dtype=WINDOW_DT)
+                full["acgt"][:, 0] = w[:, 0] & 1023; full["acgt"][:, 1] = (w[:, 0] >> 10) & 1023; full["acgt"][:, 2] = w[:, 0] >> 20
+                full["acgt"][:, 3] = w[:, 1] & 1023
+                can, allm, fwd = (w[:, 1] >> 10) & 1023, w[:, 1] >> 20, w[:, 2]
+                full["can_cov"] = can * L; full["noncan_cov"] = (allm - can) * L
+                full["fwd_cov"] = fwd * L; full["rev_cov"] = (allm - fwd) * L
+                self.windows = full
+            else:
+                self.windows = w12
+        else:
+            self.windows = arr(r.windows16, n_win, WINDOW16_DT) if r.windows16 else arr(r.windows, n_win, WINDOW_DT)
         self.terminal_off = off(r.terminal_off)
         self.terminal = arr(r.terminal, self.terminal_off[-1], BLOCK_DT)
         self.its_off = off(r.its_off)
@@ -202,9 +222,18 @@ class BatchResult:
         self.canonical_off = off(r.canonical_off)
         self.noncanonical_off = off(r.noncanonical_off)
 
-        def matches(ptr16, ptr8, offsets):
-            """16-byte records as they are; 8-byte records (item-relative positions) are widened to MATCH_DT with
-            absolute positions when copy=True, and left as MATCH8_DT views otherwise."""
+        def matches(ptr16, ptr8, offsets, ptr4=None, canonical=False):
+            """16-byte records as they are; 8-byte / 4-byte records (item-relative positions) are widened to MATCH_DT with
+            absolute positions when copy=True, and left as MATCH8_DT / u32 views otherwise."""
+            if ptr4:
+                m4 = arr(ptr4, offsets[-1], "<u4")
+                if not copy:
+                    return m4
+                out = np.zeros(len(m4), dtype=MATCH_DT)
+                out["len"] = self.pattern_len; out["fwd"] = m4 >> 31; out["can"] = 1 if canonical else 0
+                base = np.zeros(n, dtype=np.uint64) if abs_pos is None else np.asarray(abs_pos, dtype=np.uint64)
+                out["pos"] = (m4 & 0x7FFFFFFF).astype(np.uint64) + np.repeat(base, np.diff(offsets).astype(np.int64))
+                return out
             if not ptr8:
                 return arr(ptr16, offsets[-1], MATCH_DT)
             m8 = arr(ptr8, offsets[-1], MATCH8_DT)
@@ -218,8 +247,8 @@ class BatchResult:
             out["pos"] = m8["pos"].astype(np.uint64) + np.repeat(base, counts)
             return out
 
-        self.canonical = matches(r.canonical, r.canonical8, self.canonical_off)
-        self.noncanonical = matches(r.noncanonical, r.noncanonical8, self.noncanonical_off)
+        self.canonical = matches(r.canonical, r.canonical8, self.canonical_off, r.canonical4, True)
+        self.noncanonical = matches(r.noncanonical, r.noncanonical8, self.noncanonical_off, r.noncanonical4, False)
         self.n_canonical = arr(r.n_canonical, n, "<u4")
         self.n_fwd = arr(r.n_fwd, n, "<u4")
         self.n_rev = arr(r.n_rev, n, "<u4")
@@ -258,7 +287,7 @@ class Scanner:
         fwd = (C.c_uint8 * n)(*[int(f) for _, f, _ in self.table])
         can = (C.c_uint8 * n)(*[int(c) for _, _, c in self.table])
         outputs = (OUT_ACGT if cfg.out_acgt else 0) | (OUT_MATCHES if cfg.out_matches else 0) | OUT_ITS | \
-            (OUT_COMPACT if cfg.compact else 0)
+            (OUT_COMPACT if cfg.compact else 0) | (OUT_PACKED if cfg.packed else 0)
         c = _Config(ABI_VERSION, n, pats, fwd, can, cfg.window_size, cfg.step, cfg.terminal_limit,
                     cfg.max_match_dist, cfg.min_block_len, cfg.max_block_dist, cfg.min_block_counts,
                     float(np.float32(cfg.min_block_density)), outputs)

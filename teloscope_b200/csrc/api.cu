@@ -177,6 +177,7 @@ struct tls_ctx {
     bool zeroCopyWindows = false;            // TLS_OUT_COMPACT: the window-row kernel stores its 16-byte window records straight into the
                                              // pinned host buffer (posted writes over PCIe during the scan): measured slower (scan 1.23 ms against 0.95 + copy), off unless TLS_WINDOWS_ZEROCOPY=1
     bool compact = false;                    // TLS_OUT_COMPACT: tls_window16 / tls_match8 results
+    bool packed = false;                     // TLS_OUT_PACKED: tls_window12 / tls_match4 results (compact is set too: one packed device buffer)
     int rowParts = 3;                        // TLS_ROW_PARTS=n (1..8): launches of the window-row kernel on a large batch
     uint32_t rowMinWindows = kRowMinWindows; // TLS_ROW_MIN_WINDOWS=n: shortest contig (in windows) the window-row kernel takes
     Slot slot[2];
@@ -236,8 +237,13 @@ int buildDevConfig(tls_ctx *ctx) {
                      c.maxLen, c.maxLen);
         ctx->overlapRefusal = why;
     }
-    ctx->compact = (u.outputs & TLS_OUT_COMPACT) != 0;
-    if (ctx->compact) {
+    ctx->packed = (u.outputs & TLS_OUT_PACKED) != 0;
+    if (ctx->packed) {
+        if (c.nClasses != 1 || u.window_size > 1023u)
+            return fail(TLS_ERR_INVALID, "TLS_OUT_PACKED needs patterns of one length and window_size <= 1023 (10-bit count fields)");
+    }
+    ctx->compact = ctx->packed || (u.outputs & TLS_OUT_COMPACT) != 0;
+    if (ctx->compact && !ctx->packed) {
         // a window's covered-bp counters are bounded by window_size x (sum of the pattern lengths): one match per length and start
         uint64_t lenSum = 0;
         for (uint32_t i = 0; i < c.nClasses; ++i) lenSum += c.cls[i].len;
@@ -595,7 +601,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         const bool anyWindows = s.mode == TLS_MODE_GENOME && s.nWindows && !cfg.overlapWindows;
         // what goes home per window: the 32-byte counters, or (TLS_OUT_COMPACT) 16-byte records: written directly by the
         // window-row kernel, packed from the counters for the windows of the other kernels
-        const size_t winRec = ctx->compact ? 16 : 32;
+        const size_t winRec = ctx->packed ? 12 : (ctx->compact ? 16 : 32);
         if (anyWindows) {
             TLS_CUDA(s.hWindows.reserve(s.nWindows * winRec));
             if (ctx->compact) TLS_CUDA(s.dWindows16.reserve(s.nWindows * 16));
@@ -607,7 +613,8 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         void *win16Dst = s.dWindows16.p;
         if (zeroCopy) TLS_CUDA(cudaHostGetDevicePointer(&win16Dst, s.hWindows.p, 0));
         if (anyWindows && ctx->compact && nRow && nRangeWindows) {
-            TLS_CUDA(launchPackWindowRanges(s.dWindows.as<uint32_t>(), win16Dst, dRanges, dRangePrefix, nRanges, nRangeWindows, s.stream));
+            if (ctx->packed) TLS_CUDA(launchPackWindow12Ranges(s.dWindows.as<uint32_t>(), win16Dst, dRanges, dRangePrefix, nRanges, nRangeWindows, cfg.cls[0].len, s.stream));
+            else TLS_CUDA(launchPackWindowRanges(s.dWindows.as<uint32_t>(), win16Dst, dRanges, dRangePrefix, nRanges, nRangeWindows, s.stream));
             s.launches++;
         }
         uint64_t winCopied = 0;
@@ -616,7 +623,8 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             f.seq = s.devSeq;
             f.indexRow = ctx->dIndex16.as<uint8_t>();
             f.two16 = 65536u;
-            f.windows16 = ctx->compact ? static_cast<uint4 *>(win16Dst) : nullptr;
+            f.windows16 = (ctx->compact && !ctx->packed) ? static_cast<uint4 *>(win16Dst) : nullptr;
+            f.windows12 = ctx->packed ? static_cast<uint32_t *>(win16Dst) : nullptr;
             f.zeroLanes = s.dZeroLanes.as<uint32_t>();
             f.flagTab = ctx->dFlags.as<uint8_t>() + cfg.cls[0].flagOffset;
             f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
@@ -702,7 +710,8 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         TLS_CUDA(cudaEventRecord(s.evFast1, s.stream));
         TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
         if (anyWindows && ctx->compact && !nRow) {
-            TLS_CUDA(launchPackWindows(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, s.stream));
+            if (ctx->packed) TLS_CUDA(launchPackWindows12(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, cfg.cls[0].len, s.stream));
+            else TLS_CUDA(launchPackWindows(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, s.stream));
             s.launches++;
         }
         // window and per-item counters are final now: copy (the rest of) them home on the side stream
@@ -752,6 +761,9 @@ static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
     s.nItems = n; s.mode = b->mode; s.collected = false;
     int rc = planBatch(ctx, b, s);
     if (rc) return rc;
+    if (ctx->packed && b->mode == TLS_MODE_GENOME)
+        for (uint32_t i = 0; i < n; ++i)
+            if (s.itemLen[i] >= 0x80000000u) return fail(TLS_ERR_INVALID, "TLS_OUT_PACKED: item %u has 2^31 bases or more (tls_match4 holds 31-bit offsets)", i);
     const uint64_t base = n ? b->offsets[0] : 0;
     s.seqBytes = n ? b->offsets[n] - base : 0;
 
@@ -1150,8 +1162,11 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                     // beside the block kernels
                     TLS_CUDA(cudaEventRecord(s.evGather, s.stream));
                     TLS_CUDA(cudaStreamWaitEvent(s.selStream, s.evGather, 0));
-                    const size_t selRec = ctx->compact ? sizeof(tls_match8) : sizeof(tls_match);
-                    if (ctx->compact) {
+                    const size_t selRec = ctx->packed ? sizeof(tls_match4) : (ctx->compact ? sizeof(tls_match8) : sizeof(tls_match));
+                    if (ctx->packed) {
+                        TLS_CUDA(launchSelectFinalize4(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dSelCan.p, s.selStream));
+                        TLS_CUDA(launchSelectFinalize4(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll, s.dSelNon.p, s.selStream));
+                    } else if (ctx->compact) {
                         TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dSelCan.p, s.selStream));
                         TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll, s.dSelNon.p, s.selStream));
                     } else {
@@ -1179,11 +1194,13 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                                                   static_cast<uint32_t>(s.nWindows), ctx->dcfg, s.dWindows.as<uint32_t>(), s.stream));
                     s.launches++;
                     if (ctx->compact) {
+                        const size_t rec = ctx->packed ? 12 : 16;
                         TLS_CUDA(s.dWindows16.reserve(s.nWindows * 16));
-                        TLS_CUDA(launchPackWindows(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, s.stream));
+                        if (ctx->packed) TLS_CUDA(launchPackWindows12(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, ctx->dcfg.cls[0].len, s.stream));
+                        else TLS_CUDA(launchPackWindows(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, s.stream));
                         s.launches++;
-                        TLS_CUDA(s.hWindows.reserve(s.nWindows * 16));
-                        TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows16.p, s.nWindows * 16, cudaMemcpyDeviceToHost, s.stream));
+                        TLS_CUDA(s.hWindows.reserve(s.nWindows * rec));
+                        TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows16.p, s.nWindows * rec, cudaMemcpyDeviceToHost, s.stream));
                     } else {
                         TLS_CUDA(s.hWindows.reserve(s.nWindows * 32));
                         TLS_CUDA(cudaMemcpyAsync(s.hWindows.p, s.dWindows.p, s.nWindows * 32, cudaMemcpyDeviceToHost, s.stream));
@@ -1302,13 +1319,17 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
     res->n_items = n; res->mode = s.mode;
     res->window_off = s.winOff.data();
     res->windows = ctx->compact ? nullptr : s.hWindows.as<tls_window>();
-    res->windows16 = ctx->compact ? s.hWindows.as<tls_window16>() : nullptr;
+    res->windows16 = (ctx->compact && !ctx->packed) ? s.hWindows.as<tls_window16>() : nullptr;
+    res->windows12 = ctx->packed ? s.hWindows.as<tls_window12>() : nullptr;
+    res->canonical4 = s.nSelCan && ctx->packed ? s.hSelCan.as<tls_match4>() : nullptr;
+    res->noncanonical4 = s.nSelNon && ctx->packed ? s.hSelNon.as<tls_match4>() : nullptr;
+    res->pattern_len = ctx->dcfg.nClasses == 1 ? ctx->dcfg.cls[0].len : 0u;
     res->terminal_off = s.terminalOff.data(); res->terminal = s.terminal.data();
     res->its_off = s.itsOff.data(); res->its = s.its.data();
     res->canonical_off = s.canOff.data(); res->canonical = s.nSelCan && !ctx->compact ? s.hSelCan.as<tls_match>() : nullptr;
     res->noncanonical_off = s.nonOff.data(); res->noncanonical = s.nSelNon && !ctx->compact ? s.hSelNon.as<tls_match>() : nullptr;
-    res->canonical8 = s.nSelCan && ctx->compact ? s.hSelCan.as<tls_match8>() : nullptr;
-    res->noncanonical8 = s.nSelNon && ctx->compact ? s.hSelNon.as<tls_match8>() : nullptr;
+    res->canonical8 = s.nSelCan && ctx->compact && !ctx->packed ? s.hSelCan.as<tls_match8>() : nullptr;
+    res->noncanonical8 = s.nSelNon && ctx->compact && !ctx->packed ? s.hSelNon.as<tls_match8>() : nullptr;
     res->n_canonical = s.nCan.data(); res->n_fwd = s.nFwd.data(); res->n_rev = s.nRev.data();
     res->pass = s.pass.data();
     res->scan_kernel_ms = s.scanMs; res->device_ms = s.allMs;

@@ -802,6 +802,33 @@ __global__ void __launch_bounds__(256) packWindowRangesKernel(const uint4 *in, u
     out[w] = make_uint4(a.x | (a.y << 16), a.z | (a.w << 16), b.x | (b.y << 16), b.z | (b.w << 16));
 }
 
+// tls_window (8 x u32) -> tls_window12 (counts of matches, ten bits per field): one pattern length L, window <= 1023
+__device__ __forceinline__ void storeWindow12(uint32_t *out, size_t w, const uint4 a, const uint4 b, uint32_t L) {
+    const uint32_t can = b.x / L, all = (b.x + b.y) / L, fwd = b.z / L;
+    out[3 * w] = a.x | (a.y << 10) | (a.z << 20);
+    out[3 * w + 1] = a.w | (can << 10) | (all << 20);
+    out[3 * w + 2] = fwd;
+}
+__global__ void __launch_bounds__(256) packWindows12Kernel(const uint4 *in, uint32_t *out, unsigned long long n, uint32_t L) {
+    const unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    storeWindow12(out, i, in[2 * i], in[2 * i + 1], L);
+}
+__global__ void __launch_bounds__(256) packWindow12RangesKernel(const uint4 *in, uint32_t *out, const uint2 *ranges, const uint32_t *rangePrefix,
+                                                                uint32_t nRanges, uint32_t total, uint32_t L) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t w = windowOfRanges(ranges, rangePrefix, nRanges, i);
+    storeWindow12(out, w, in[2 * w], in[2 * w + 1], L);
+}
+// tls_match4: item-relative position, bit 31 = forward
+__global__ void __launch_bounds__(256) selectFinalize4Kernel(const DevMatch *m, const uint32_t *idxList, unsigned long long n, uint32_t *out) {
+    const unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const DevMatch x = m[idxList[j]];
+    out[j] = x.pos | ((x.flags & kMatchFwd) ? 0x80000000u : 0u);
+}
+
 __global__ void __launch_bounds__(256) selectFinalizeKernel(const DevMatch *m, const uint32_t *idxList, unsigned long long n,
                                                             const unsigned long long *itemBegin, const unsigned long long *absPos,
                                                             uint32_t nItems, OutMatch *out) {
@@ -915,6 +942,23 @@ cudaError_t launchPackWindowRanges(const uint32_t *windows, void *windows16, con
     if (total == 0) return cudaSuccess;
     packWindowRangesKernel<<<(total + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows), static_cast<uint4 *>(windows16),
                                                              ranges, rangePrefix, nRanges, total);
+    return cudaGetLastError();
+}
+cudaError_t launchPackWindows12(const uint32_t *windows, void *windows12, unsigned long long n, uint32_t L, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    packWindows12Kernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows), static_cast<uint32_t *>(windows12), n, L);
+    return cudaGetLastError();
+}
+cudaError_t launchPackWindow12Ranges(const uint32_t *windows, void *windows12, const uint2 *ranges, const uint32_t *rangePrefix,
+                                     uint32_t nRanges, uint32_t total, uint32_t L, cudaStream_t s) {
+    if (total == 0) return cudaSuccess;
+    packWindow12RangesKernel<<<(total + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows), static_cast<uint32_t *>(windows12),
+                                                               ranges, rangePrefix, nRanges, total, L);
+    return cudaGetLastError();
+}
+cudaError_t launchSelectFinalize4(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    selectFinalize4Kernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(m, idxList, n, static_cast<uint32_t *>(out));
     return cudaGetLastError();
 }
 cudaError_t launchItemOffsets(const DevItemCounts *counts, const DevItemInfo *items, uint32_t n, unsigned long long *itemBegin, cudaStream_t s) {

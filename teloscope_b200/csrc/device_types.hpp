@@ -239,6 +239,7 @@ struct RowParams {
     unsigned int *ovCursor;
     uint4 *windows;                // [nWindows][2]: A, C, G, T | canonical, non-canonical, forward, reverse covered bp
     uint4 *windows16;              // TLS_OUT_COMPACT: [nWindows] tls_window16 written directly (windows is not touched then)
+    uint32_t *windows12;           // TLS_OUT_PACKED: [nWindows][3] tls_window12 written directly
     uint32_t *zeroLanes;           // [nWindows]: bit l = lane l (row positions 32 l .. 32 l + 31) holds no match start
     DevItemCounts *itemCounts;
     unsigned int *status;          // set to 1 when the shared memory layout assumption fails

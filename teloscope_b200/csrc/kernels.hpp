@@ -68,5 +68,10 @@ cudaError_t launchSelectFinalize(const DevMatch *m, const uint32_t *idxList, uns
 // TLS_OUT_COMPACT: 8-byte match records (item-relative position) and 16-byte window records
 cudaError_t launchSelectFinalize8(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s);
 cudaError_t launchPackWindows(const uint32_t *windows, void *windows16, unsigned long long n, cudaStream_t s);
+// TLS_OUT_PACKED: 12-byte window records (counts, pattern length L) and 4-byte match records
+cudaError_t launchPackWindows12(const uint32_t *windows, void *windows12, unsigned long long n, uint32_t L, cudaStream_t s);
+cudaError_t launchPackWindow12Ranges(const uint32_t *windows, void *windows12, const uint2 *ranges, const uint32_t *rangePrefix,
+                                     uint32_t nRanges, uint32_t total, uint32_t L, cudaStream_t s);
+cudaError_t launchSelectFinalize4(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s);
 
 }  // namespace tls

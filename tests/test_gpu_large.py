@@ -1,6 +1,6 @@
 """A batch large enough (1.06 Gbp, 66 K units) for the paths small parity cases do not reach: the window-row kernel in
 several launches with the window counters of each finished unit range copied while the next range is scanned
-(TLS_ROW_PARTS, csrc/api.cu enqueueScan), the compact result records on the same batch, and the ring staging of pageable
+(TLS_ROW_PARTS, csrc/api.cu enqueueScan) or in one launch with stream wait-value progress ranges, the compact and packed result records on the same batch, and the ring staging of pageable
 host input on four threads.  All variants must return identical results; a sample of contigs is checked against the oracle."""
 import os
 import sys
@@ -42,10 +42,13 @@ def test_split_scan_compact_and_pageable_input_agree():
     n_bases = int(offsets[-1])
     assert n_bases > 1_000_000_000
     host = seq[:n_bases].cpu().numpy()                                  # pageable
-    mk = lambda compact: tb.ScanConfig(canonical="TTAGGG", patterns=bench.PATTERNS, out_acgt=True, out_matches=True, compact=compact)
+    mk = lambda compact, packed=False: tb.ScanConfig(canonical="TTAGGG", patterns=bench.PATTERNS, out_acgt=True, out_matches=True,
+                                                     compact=compact, packed=packed)
     one = _scan(tb, mk(False), None, offsets, abs_pos, device_ptr=seq.data_ptr(), env={"TLS_ROW_PARTS": "1"})
     split = _scan(tb, mk(False), None, offsets, abs_pos, device_ptr=seq.data_ptr(), env={"TLS_ROW_PARTS": "4"})
     comp = _scan(tb, mk(True), None, offsets, abs_pos, device_ptr=seq.data_ptr())
+    pack = _scan(tb, mk(False, True), None, offsets, abs_pos, device_ptr=seq.data_ptr())          # TLS_OUT_PACKED: 12-byte windows, 4-byte matches
+    launches = _scan(tb, mk(False, True), None, offsets, abs_pos, device_ptr=seq.data_ptr(), env={"TLS_ROW_PARTS": "3"})
     paged = _scan(tb, mk(False), host, offsets, abs_pos)
     assert len(one.windows) == (one.window_off[-1]) > 1_000_000
     for other in (split, paged):
@@ -57,6 +60,10 @@ def test_split_scan_compact_and_pageable_input_agree():
         for f in ("pos", "len", "fwd", "can"):
             assert np.array_equal(getattr(one, name)[f], getattr(comp, name)[f]), (name, f)
     assert one.terminal.tobytes() == comp.terminal.tobytes() and one.its.tobytes() == comp.its.tobytes()
+    for other in (pack, launches):
+        assert one.windows.tobytes() == other.windows.tobytes()
+        for name in ("canonical", "noncanonical", "terminal", "its"):
+            assert getattr(one, name).tobytes() == getattr(other, name).tobytes(), name
     # a few contigs against the oracle: the first, the last, one at every quarter of the batch (part boundaries)
     orc = ol.Oracle(ol.Config(patterns=bench.PATTERNS))
     n = len(offsets) - 1

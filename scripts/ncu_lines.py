@@ -36,7 +36,7 @@ def sass_rows(rep: str, kernel: str):
         res.append({"sass": r[col["Source"]].strip(), "inst": float(r[col["Instructions Executed"]] or 0),
                     "thr": float(r[col["Thread Instructions Executed"]] or 0),
                     "samples": float(r[col["# Samples"]] or 0),
-                    "conf": float(r[col["L1 Wavefronts Shared Excessive"]] or 0)})
+                    "conf": float((r[col["L1 Wavefronts Shared Excessive"]] if "L1 Wavefronts Shared Excessive" in col else 0) or 0)})
     return name, res
 
 

@@ -1236,7 +1236,7 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                         s.launches += 2;
                     }
                     if (s.nRowItems) {                      // window-row items: connectivity from the zero-lane masks, runs from the sequence
-                        TLS_CUDA(s.dConn.reserve(s.nCanAll + 16));
+                        TLS_CUDA(s.dConn.reserve(s.nCanAll + 64));     // itsWalkKernel reads 32 links at a time
                         TLS_CUDA(launchItsRows(bp, s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dConn.as<uint8_t>(),
                                                s.dRunStarts.as<unsigned long long>() + runCap,
                                                reinterpret_cast<unsigned int *>(cnt + 24), runCap, s.stream));
@@ -1252,6 +1252,10 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
             s.blockCap = nBlocks + nBlocks / 8 + 64;
         }
         if (reads) nBlocks = 0;
+        if (tr.on && !reads)
+            std::fprintf(stderr, "[tls] blocks %u, ITS runs from lists %u, ITS chains of window-row items %u, canonical %llu\n", nBlocks,
+                         *reinterpret_cast<unsigned int *>(s.hCounters.as<uint8_t>() + 20),
+                         *reinterpret_cast<unsigned int *>(s.hCounters.as<uint8_t>() + 24), static_cast<unsigned long long>(s.nCanAll));
         tr.mark("gather_blocks_select");
         unsigned long long selTotals[2] = {wantSel ? s.nCanAll : 0, wantSel ? s.nNctAll : 0};
 

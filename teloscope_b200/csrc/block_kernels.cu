@@ -11,8 +11,10 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <type_traits>
 
 #include "device_common.cuh"
+#include "row_common.cuh"
 #include "kernels.hpp"
 
 namespace tls {
@@ -155,18 +157,29 @@ __global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, 
 // the warp copies slot after slot with coalesced 8-byte accesses.  (All window / item accounting was done by the scan kernels.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
+constexpr uint32_t kGatherBlocksPerSm = 4;
 
-__global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParams g) {
-    const uint32_t tile = blockIdx.x * (kGatherThreads / 32) + (threadIdx.x >> 5);
-    const uint32_t lane = threadIdx.x & 31u;
-    if (tile >= g.nTiles) return;
-    const unsigned long long base = g.tileBase[tile];
-    const uint32_t total = static_cast<uint32_t>(g.tileBase[tile + 1] - base);
-    if (total == 0) return;
-    const unsigned long long baseCan = g.tileBase[static_cast<size_t>(g.nTiles) + 1 + tile];
-    const unsigned long long baseNct = g.tileBase[2 * (static_cast<size_t>(g.nTiles) + 1) + tile];
+struct TileHeader {
+    unsigned long long base, baseEnd, baseCan, baseNct;
+    uint4 meta;                                                     // records, overflow base, canonical, terminal non-canonical
+};
+// every load of a tile's header is issued together (one round trip to memory, not three)
+__device__ __forceinline__ TileHeader loadTileHeader(const GatherParams &g, uint32_t tile, uint32_t lane) {
+    TileHeader h;
+    h.base = g.tileBase[tile];
+    h.baseEnd = g.tileBase[tile + 1];
+    h.baseCan = g.tileBase[static_cast<size_t>(g.nTiles) + 1 + tile];
+    h.baseNct = g.tileBase[2 * (static_cast<size_t>(g.nTiles) + 1) + tile];
+    h.meta = g.slotMeta[static_cast<size_t>(tile) * kTileRows + lane];
+    return h;
+}
+
+__device__ __forceinline__ void gatherTile(const GatherParams &g, uint32_t tile, uint32_t lane, const TileHeader &hd) {
     const size_t slot0 = static_cast<size_t>(tile) * kTileRows;
-    const uint4 meta = g.slotMeta[slot0 + lane];                    // records, overflow base, canonical, terminal non-canonical
+    const unsigned long long base = hd.base, baseCan = hd.baseCan, baseNct = hd.baseNct;
+    const uint4 meta = hd.meta;
+    const uint32_t total = static_cast<uint32_t>(hd.baseEnd - base);
+    if (total == 0) return;
     // exclusive prefixes over the 32 row slots (a tile holds at most 32 x ovChunk records: 16 bits per field would not do)
     uint32_t inclAll = meta.x, inclCan = meta.z, inclNct = meta.w;
 #pragma unroll
@@ -184,15 +197,27 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
         // lane r: row r's records, one after the other
         const uint2 *src = slots + (slot0 + lane) * g.slotCap;
         unsigned long long o = base + exAll, oc = baseCan + exCan, on = baseNct + exNct;
-        for (uint32_t k = 0; k < meta.x; ++k, ++o) {
-            uint2 rec;
-            if (k < g.slotCap) rec = __ldg(src + k);
-            else if (static_cast<unsigned long long>(meta.y) + (k - g.slotCap) < g.ovCap) rec = ovArena[meta.y + (k - g.slotCap)];
-            else continue;                                          // overflow arena exhausted: the host reruns the scan
+        auto put = [&](const uint2 rec) {
             if (o < g.matchCap) out[o] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
             const uint32_t flags = (rec.y >> 16) & 0xFFu;
             if (flags & kMatchCan) { if (oc < g.selCap) g.canIdx[oc] = static_cast<uint32_t>(o); ++oc; }
             else if (flags & kMatchTerm) { if (on < g.selCap) g.nctIdx[on] = static_cast<uint32_t>(o); ++on; }
+            ++o;
+        };
+        // the first records of the row (a sparse row holds one or two) are all requested before any is stored
+        constexpr uint32_t kAhead = 4;
+        const uint32_t direct = min(min(meta.x, g.slotCap), kAhead);
+        uint2 first[kAhead];
+#pragma unroll
+        for (uint32_t k = 0; k < kAhead; ++k) first[k] = k < direct ? __ldg(src + k) : make_uint2(0u, 0u);
+#pragma unroll
+        for (uint32_t k = 0; k < kAhead; ++k) if (k < direct) put(first[k]);
+        for (uint32_t k = direct; k < meta.x; ++k) {
+            uint2 rec;
+            if (k < g.slotCap) rec = __ldg(src + k);
+            else if (static_cast<unsigned long long>(meta.y) + (k - g.slotCap) < g.ovCap) rec = ovArena[meta.y + (k - g.slotCap)];
+            else { ++o; continue; }                                 // overflow arena exhausted: the host reruns the scan
+            put(rec);
         }
         return;
     }
@@ -229,6 +254,24 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
     }
 }
 
+// Persistent warps: a warp walks tiles with a stride and requests the next tile's header before it copies the current one.
+__global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParams g) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * (kGatherThreads / 32);
+    uint32_t tile = blockIdx.x * (kGatherThreads / 32) + (threadIdx.x >> 5);
+    if (tile >= g.nTiles) return;
+    TileHeader hd = loadTileHeader(g, tile, lane);
+    for (;;) {
+        const uint32_t next = tile + stride;
+        TileHeader hn = hd;
+        if (next < g.nTiles) hn = loadTileHeader(g, next, lane);
+        gatherTile(g, tile, lane, hd);
+        if (next >= g.nTiles) break;
+        tile = next;
+        hd = hn;
+    }
+}
+
 cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, unsigned long long *blockSums,
                            const unsigned int *ovCursor, const unsigned int *redo, unsigned long long *hostOut, cudaStream_t s) {
     const uint32_t nBlk = std::max<uint32_t>(1u, (nTiles + kScanChunk - 1) / kScanChunk);
@@ -239,7 +282,8 @@ cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned lo
 size_t tileScanScratchBytes(uint32_t nTiles) { return static_cast<size_t>(std::max<uint32_t>(1u, (nTiles + kScanChunk - 1) / kScanChunk)) * 3 * 8; }
 cudaError_t launchGather(const GatherParams &g, cudaStream_t s) {
     if (g.nTiles == 0) return cudaSuccess;
-    gatherKernel<<<(g.nTiles + kGatherThreads / 32 - 1) / (kGatherThreads / 32), kGatherThreads, 0, s>>>(g);
+    const uint32_t blocks = std::min<uint32_t>((g.nTiles + kGatherThreads / 32 - 1) / (kGatherThreads / 32), 148u * kGatherBlocksPerSm);
+    gatherKernel<<<blocks, kGatherThreads, 0, s>>>(g);
     return cudaGetLastError();
 }
 
@@ -256,23 +300,28 @@ struct Rescan {
     const uint8_t *flagTab;    // 4^L bytes: bit0 hit, bit1 forward, bit2 canonical
     uint32_t n, W, L;
     const DevConfig *cfg;
-    __device__ uint32_t at(uint32_t pos) const {
+    // The bases of the pattern that would start at pos: unconditional loads (the batch is readable past its end), so a
+    // caller can have several positions in flight before it looks at any of them.
+    __device__ void fetch(uint32_t pos, uint32_t (&ch)[7]) const {
+        const uint8_t *s = seq + (pos < n ? pos : 0u);
+#pragma unroll
+        for (uint32_t j = 0; j < 7; ++j) ch[j] = j < L ? __ldg(s + j) : static_cast<uint32_t>('A');   // L <= 7
+    }
+    __device__ uint32_t resolve(uint32_t pos, const uint32_t (&ch)[7]) const {
         if (pos >= n) return 0u;
         const uint32_t wStart = divWindow(*cfg, pos) * W;
         const uint32_t wLen = min(W, n - wStart);
         if (pos - wStart + L > wLen) return 0u;
+        // four bases per word: the scan kernels' exact ACGTacgt test and 2-bit packing (row_common.cuh); bases past L are 'A' = code 0
+        const uint32_t w0 = ch[0] | (ch[1] << 8) | (ch[2] << 16) | (ch[3] << 24), w1 = ch[4] | (ch[5] << 8) | (ch[6] << 16) | (0x41u << 24);
+        ValidAcc v;
+        const uint32_t key = (packWord(w0, v) >> 24) | ((packWord(w1, v) >> 24) << 8);
+        return v.bad() == 0u ? __ldg(flagTab + key) : 0u;
+    }
+    __device__ uint32_t at(uint32_t pos) const {
         uint32_t ch[7];
-#pragma unroll
-        for (uint32_t j = 0; j < 7; ++j) ch[j] = j < L ? __ldg(seq + pos + j) : static_cast<uint32_t>('A');   // all loads in flight at once (L <= 7)
-        uint32_t key = 0;
-        bool ok = true;
-#pragma unroll
-        for (uint32_t j = 0; j < 7; ++j) {
-            const uint32_t up = ch[j] & 0xDFu;
-            ok = ok && (up == 'A' || up == 'C' || up == 'G' || up == 'T');
-            if (j < L) key |= ((ch[j] >> 1) & 3u) << (2 * j);
-        }
-        return ok ? __ldg(flagTab + key) : 0u;
+        fetch(pos, ch);
+        return resolve(pos, ch);
     }
 };
 
@@ -368,99 +417,94 @@ __global__ void __launch_bounds__(128) terminalKernel(const BlockParams p) {
         if (p.items && p.items[item].rowItem) sparseRange(n, c.terminalLimit, c.windowSize, spLo, spHi);
         const bool hasSparse = spLo != 0xFFFFFFFFu;
         bool atEdge = false;
-        // lane l holds the l-th next record in walk order; the next 32 are requested before the current 32 are walked
-        auto fetch = [&](long long off, uint2 &rec, bool &valid) {
+        // lane l holds the l-th next record in walk order; the groups of 32 behind the current one are requested kAhead groups
+        // ahead and only looked at (the sparse edge) when their turn comes
+        auto load = [&](long long off, uint2 &rec, bool &valid) {
             const long long i = fromStart ? begin + off + lane : end - 1 - off - lane;
             valid = off < end - begin && (fromStart ? i < end : i >= begin);
             rec = valid ? __ldg(recs + i) : make_uint2(0u, 0u);
-            if (valid && hasSparse && (fromStart ? rec.x >= spLo : rec.x < spHi)) { valid = false; atEdge = true; }
         };
-        uint2 rec, recNext;
-        bool valid, validNext;
-        fetch(0, rec, valid);
-        for (long long off = 0; off < end - begin && !done; off += 32, rec = recNext, valid = validNext) {
+        constexpr int kAhead = 3;
+        uint2 qRec[kAhead];
+        bool qValid[kAhead];
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) load(32ll * k, qRec[k], qValid[k]);
+        for (long long off = 0; off < end - begin && !done; off += 32) {
+            const uint2 rec = qRec[0];
+            bool valid = qValid[0];
+#pragma unroll
+            for (int k = 0; k + 1 < kAhead; ++k) { qRec[k] = qRec[k + 1]; qValid[k] = qValid[k + 1]; }
+            load(off + 32ll * kAhead, qRec[kAhead - 1], qValid[kAhead - 1]);
+            if (valid && hasSparse && (fromStart ? rec.x >= spLo : rec.x < spHi)) { valid = false; atEdge = true; }
             if (__any_sync(0xFFFFFFFFu, atEdge) && !__any_sync(0xFFFFFFFFu, valid)) break;     // only records beyond the edge are left
-            fetch(off + 32, recNext, validNext);
-            uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && ((rec.y >> 16) & kMatchFwd) == want);
-            if (mask && !(inRun && run.nCan > 0u)) {
-                // No canonical match among these records and none in the open run: every run that ends here fails the Phase 1
-                // filter (canonicalCount > 0, src/teloscope.cpp:76-77), so only the run that is still open after the group
-                // matters (its start, extent and counts, all from ballots and reductions), and the first run start outside the
-                // terminal zone, which ends the walk (:98-102,117-121).
-                const bool mine = (mask >> lane) & 1u;
-                if (__ballot_sync(0xFFFFFFFFu, mine && ((rec.y >> 16) & kMatchCan)) == 0u) {
-                    const uint32_t below = mask & ((1u << lane) - 1u);
-                    uint32_t prevPos = __shfl_sync(0xFFFFFFFFu, rec.x, below ? 31 - __clz(below) : 0);
-                    if (!below) prevPos = run.prev;
-                    const uint32_t gapL = fromStart ? rec.x - prevPos : prevPos - rec.x;
-                    const bool isStart = mine && ((!below && !inRun) || gapL > c.maxMatchDist);
-                    const uint32_t starts = __ballot_sync(0xFFFFFFFFu, isStart);
-                    if (__ballot_sync(0xFFFFFFFFu, isStart && !inZone(rec.x)) != 0u) { inRun = false; done = true; break; }
-                    const uint32_t len = rec.y & 0xFFFFu;
-                    const int last = 31 - __clz(mask);
-                    const uint32_t lastPos = __shfl_sync(0xFFFFFFFFu, rec.x, last), lastLen = __shfl_sync(0xFFFFFFFFu, len, last);
-                    if (starts == 0u) {                              // everything continues the open run
-                        const uint32_t cntM = __popc(mask), lenSum = __reduce_add_sync(0xFFFFFFFFu, mine ? len : 0u);
-                        run.n += cntM; run.nFwd += want ? cntM : 0u; run.cov += lenSum; run.fwdCov += want ? lenSum : 0u;
-                        if (fromStart) run.end = lastPos + lastLen; else run.start = lastPos;
-                    } else {                                         // the run that is open after the group starts at its last run start
-                        const int hl = 31 - __clz(starts);
-                        const uint32_t seg = mask & ~((1u << hl) - 1u);
-                        const uint32_t firstPos = __shfl_sync(0xFFFFFFFFu, rec.x, hl), firstLen = __shfl_sync(0xFFFFFFFFu, len, hl);
-                        const uint32_t cntM = __popc(seg), lenSum = __reduce_add_sync(0xFFFFFFFFu, ((seg >> lane) & 1u) ? len : 0u);
-                        run.n = cntM; run.nFwd = want ? cntM : 0u; run.nCan = 0; run.cov = lenSum; run.fwdCov = want ? lenSum : 0u; run.canCov = 0;
-                        if (fromStart) { run.start = firstPos; run.end = lastPos + lastLen; }
-                        else { run.end = firstPos + firstLen; run.start = lastPos; }
-                        inRun = true;
-                    }
-                    run.prev = lastPos;
-                    continue;
-                }
-            }
-            if (inRun && mask) {
-                // Inside a telomere the whole group of 32 continues the current run (every start-to-start gap
-                // <= maxMatchDist; the zone test only applies to run starts, src/teloscope.cpp:98-121): absorb it
-                // with a few warp reductions instead of one sequential step per match.
-                const uint32_t below = mask & ((1u << lane) - 1u);
-                uint32_t prevPos = __shfl_sync(0xFFFFFFFFu, rec.x, below ? 31 - __clz(below) : 0);
-                if (!below) prevPos = run.prev;
-                const bool mine = (mask >> lane) & 1u;
-                const uint32_t gapL = fromStart ? rec.x - prevPos : prevPos - rec.x;
-                if (!__any_sync(0xFFFFFFFFu, mine && gapL > c.maxMatchDist)) {
-                    const uint32_t len = rec.y & 0xFFFFu;
-                    const bool can = mine && ((rec.y >> 16) & kMatchCan);
-                    const uint32_t cntM = __popc(mask), lenSum = __reduce_add_sync(0xFFFFFFFFu, mine ? len : 0u);
-                    const uint32_t canLen = __reduce_add_sync(0xFFFFFFFFu, can ? len : 0u);
-                    const int last = 31 - __clz(mask);
-                    const uint32_t lastPos = __shfl_sync(0xFFFFFFFFu, rec.x, last), lastLen = __shfl_sync(0xFFFFFFFFu, len, last);
-                    run.n += cntM; run.nFwd += want ? cntM : 0u; run.nCan += __popc(__ballot_sync(0xFFFFFFFFu, can));
-                    run.cov += lenSum; run.fwdCov += want ? lenSum : 0u; run.canCov += canLen; run.prev = lastPos;
-                    if (fromStart) run.end = lastPos + lastLen; else run.start = lastPos;
-                    continue;
-                }
-            }
-            while (mask && !done) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const uint32_t pos = __shfl_sync(0xFFFFFFFFu, rec.x, b), hi = __shfl_sync(0xFFFFFFFFu, rec.y, b);
-                const uint32_t len = hi & 0xFFFFu, flags = (hi >> 16) & 0xFFu;
-                if (!inRun) {
-                    if (!inZone(pos)) { done = true; break; }
-                    run.begin(pos, len, flags);
-                    inRun = true;
-                    continue;
-                }
-                const uint32_t gap = fromStart ? pos - run.prev : run.prev - pos;
-                if (gap <= c.maxMatchDist) {
-                    if (fromStart) run.end = pos + len; else run.start = pos;
-                    run.absorb(pos, len, flags);
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && ((rec.y >> 16) & kMatchFwd) == want);
+            if (!mask) continue;
+            // The group's records of the wanted strand fall into SEGMENTS: a segment starts where the gap to the previous
+            // record exceeds maxMatchDist (a run start, src/teloscope.cpp:98-121).  The records before the first start
+            // continue the open run; every start closes the run before it.  A closed run without a canonical match fails the
+            // Phase 1 filter (:76-77), so only segments with canonical content and the group's last segment (it stays open)
+            // need their sums, which come from ballots and warp reductions; the first run start outside the terminal zone
+            // ends the walk.  Telomere arrays are one segment per group, random sequence a handful of cheap ones.
+            const bool mine = (mask >> lane) & 1u;
+            const uint32_t len = rec.y & 0xFFFFu;
+            const bool can = mine && ((rec.y >> 16) & kMatchCan);
+            const uint32_t canM = __ballot_sync(0xFFFFFFFFu, can);
+            const uint32_t below = mask & ((1u << lane) - 1u);
+            uint32_t prevPos = __shfl_sync(0xFFFFFFFFu, rec.x, below ? 31 - __clz(below) : 0);
+            if (!below) prevPos = run.prev;
+            const uint32_t gapL = fromStart ? rec.x - prevPos : prevPos - rec.x;
+            const bool isStart = mine && ((!below && !inRun) || gapL > c.maxMatchDist);
+            uint32_t st = __ballot_sync(0xFFFFFFFFu, isStart);
+            const uint32_t outZ = __ballot_sync(0xFFFFFFFFu, isStart && !inZone(rec.x));
+            uint32_t live = mask;
+            if (outZ) { const uint32_t lim = (1u << (__ffs(outZ) - 1)) - 1u; live &= lim; st &= lim; }
+            auto takeSegment = [&](uint32_t seg, bool fresh) {
+                const bool inSeg = (seg >> lane) & 1u;
+                const uint32_t cntM = __popc(seg), canCnt = __popc(seg & canM);
+                const uint32_t lenSum = __reduce_add_sync(0xFFFFFFFFu, inSeg ? len : 0u);
+                const uint32_t canLen = canCnt ? __reduce_add_sync(0xFFFFFFFFu, (inSeg && can) ? len : 0u) : 0u;
+                const int last = 31 - __clz(seg);
+                const uint32_t lastPos = __shfl_sync(0xFFFFFFFFu, rec.x, last), lastLen = __shfl_sync(0xFFFFFFFFu, len, last);
+                if (fresh) {
+                    const int first = __ffs(seg) - 1;
+                    const uint32_t firstPos = __shfl_sync(0xFFFFFFFFu, rec.x, first), firstLen = __shfl_sync(0xFFFFFFFFu, len, first);
+                    run.n = cntM; run.nFwd = want ? cntM : 0u; run.nCan = canCnt;
+                    run.cov = lenSum; run.fwdCov = want ? lenSum : 0u; run.canCov = canLen;
+                    if (fromStart) { run.start = firstPos; run.end = lastPos + lastLen; }
+                    else { run.end = firstPos + firstLen; run.start = lastPos; }
                 } else {
-                    feedSub(run);
-                    inRun = false;
-                    if (!inZone(pos)) { done = true; break; }
-                    run.begin(pos, len, flags);
-                    inRun = true;
+                    run.n += cntM; run.nFwd += want ? cntM : 0u; run.nCan += canCnt;
+                    run.cov += lenSum; run.fwdCov += want ? lenSum : 0u; run.canCov += canLen;
+                    if (fromStart) run.end = lastPos + lastLen; else run.start = lastPos;
                 }
+                run.prev = lastPos;
+            };
+            auto below32 = [](int k) { return k >= 32 ? 0xFFFFFFFFu : (1u << k) - 1u; };      // lanes before lane k
+            if (live) {
+                const int firstStart = st ? __ffs(st) - 1 : 32;
+                const uint32_t seg0 = live & below32(firstStart);
+                if (seg0) takeSegment(seg0, false);                   // the open run goes on (the first record is no start)
+                if (st) {
+                    if (inRun && run.nCan > 0u) feedSub(run);         // the run before the first start is over
+                    inRun = true;
+                    const int lastStart = 31 - __clz(st);
+                    // segments that begin and end inside the group: only those with a canonical match can pass Phase 1
+                    uint32_t cm = canM & live & ~below32(firstStart) & below32(lastStart);
+                    while (cm) {
+                        const int b = __ffs(cm) - 1;
+                        const int h = 31 - __clz(st & below32(b + 1));                    // the start of b's segment
+                        const int nx = __ffs(st & ~below32(b + 1)) - 1;                   // the next start: b < lastStart
+                        takeSegment(live & ~below32(h) & below32(nx), true);
+                        feedSub(run);
+                        cm &= ~below32(nx);
+                    }
+                    takeSegment(live & ~below32(lastStart), true);    // the last segment stays open
+                }
+            }
+            if (outZ) {                                               // a run start outside the zone: the walk ends (:98-102,117-121)
+                if (inRun && run.nCan > 0u) feedSub(run);
+                inRun = false;
+                done = true;
             }
         }
         if (hasSparse && inRun && !done) {
@@ -625,6 +669,8 @@ __global__ void __launch_bounds__(256) itsConnKernel(const BlockParams p, const 
     do {
         if (j + 1 >= nCan) break;
         const unsigned long long idx = canIdx[j], idx2 = canIdx[j + 1];
+        const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
+        const uint32_t a = __ldg(&recs[idx].x), b = __ldg(&recs[idx2].x);   // requested before the item search, not after it
         uint32_t lo = 0, hi = p.nItems;                               // item: last i with itemBegin[i] <= idx
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
@@ -634,8 +680,6 @@ __global__ void __launch_bounds__(256) itsConnKernel(const BlockParams p, const 
         if (!p.items[item].rowItem || idx2 >= p.itemBegin[item + 1]) break;
         const uint32_t fwdB = p.fwdBoundary[item], revB = p.revBoundary[item];
         if (!(fwdB < revB) || p.itemCounts[item].all < 2) break;      // src/teloscope.cpp:653
-        const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
-        const uint32_t a = recs[idx].x, b = recs[idx2].x;
         if (a < fwdB || b >= revB) break;                             // runs live in [fwdBoundary, revBoundary), :188-191,235
         out = 1;
         const uint32_t m = c.maxMatchDist == 0 ? 1u : (c.maxMatchDist + 31u) / 32u;      // lanes without a start that break a chain
@@ -668,6 +712,8 @@ __global__ void __launch_bounds__(256) itsChainKernel(const uint8_t *conn, unsig
     if (slot < chainCap) chainStarts[slot] = j;
 }
 
+constexpr int kWalkBlocks = 4;          // positions rescanned per step of a walk: 32 x kWalkBlocks
+
 __global__ void __launch_bounds__(128) itsWalkKernel(const BlockParams p, const uint32_t *canIdx, const uint8_t *conn,
                                                      const unsigned long long *chainStarts, const unsigned int *chainCount, uint32_t chainCap) {
     const int lane = threadIdx.x & 31;
@@ -675,8 +721,12 @@ __global__ void __launch_bounds__(128) itsWalkKernel(const BlockParams p, const 
     const DevConfig &c = p.cfg;
     for (uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gw < nChains; gw += (gridDim.x * blockDim.x) >> 5) {
     unsigned long long j = chainStarts[gw];
-    unsigned long long jEnd = j;
-    while (conn[jEnd]) ++jEnd;                                        // last canonical match of the chain (conn of the batch's last is 0)
+    unsigned long long jEnd = j;                                      // last canonical match of the chain (conn of the batch's last is 0,
+    for (;;) {                                                        // the array is padded by 32 bytes): 32 links per step
+        const uint32_t open32 = __ballot_sync(0xFFFFFFFFu, conn[jEnd + lane] != 0);
+        if (open32 != 0xFFFFFFFFu) { jEnd += __ffs(~open32) - 1; break; }
+        jEnd += 32;
+    }
     const uint2 *recs = reinterpret_cast<const uint2 *>(p.matches);
     const unsigned long long idx0 = canIdx[j];
     uint32_t lo = 0, hi = p.nItems;
@@ -688,51 +738,72 @@ __global__ void __launch_bounds__(128) itsWalkKernel(const BlockParams p, const 
     const uint32_t n = p.itemLen[item], L = p.patLen, K = c.maxMatchDist;
     const uint32_t fwdB = p.fwdBoundary[item], revB = p.revBoundary[item];
     const Rescan rs{p.seq + p.items[item].bufStart, p.flagTab, n, c.windowSize, L, &c};
+    // the run rightwards from a match at `from`: its matches, forward and canonical ones, and the last match's position
+    auto walkRight = [&](uint32_t from, auto blocksTag, uint32_t &cnt, uint32_t &nFwd, uint32_t &nCan, uint32_t &prev) {
+        constexpr int kBlocks = decltype(blocksTag)::value;           // 32 x kBlocks positions per step, all loads in flight together
+        const uint32_t f0 = rs.at(from);
+        cnt = 1; nFwd = (f0 >> 1) & 1u; nCan = (f0 >> 2) & 1u; prev = from;
+        bool open = true;
+        for (unsigned long long base = static_cast<unsigned long long>(from) + 1; open && base < revB; base += 32 * kBlocks) {
+            if (base - prev > K) break;
+            uint32_t f[kBlocks], ch[kBlocks][7];
+#pragma unroll
+            for (int blk = 0; blk < kBlocks; ++blk) rs.fetch(static_cast<uint32_t>(min(base + 32u * blk + lane, static_cast<unsigned long long>(n))), ch[blk]);
+#pragma unroll
+            for (int blk = 0; blk < kBlocks; ++blk) {
+                const unsigned long long q = base + 32u * blk + lane;
+                f[blk] = q < revB ? rs.resolve(static_cast<uint32_t>(q), ch[blk]) : 0u;
+            }
+#pragma unroll
+            for (int blk = 0; blk < kBlocks; ++blk) {
+                uint32_t mask = __ballot_sync(0xFFFFFFFFu, (f[blk] & 1u) != 0u);
+                if (!open) mask = 0;
+                const uint32_t fwdM = __ballot_sync(0xFFFFFFFFu, (f[blk] & 3u) == 3u), canM = __ballot_sync(0xFFFFFFFFu, (f[blk] & 5u) == 5u);
+                uint32_t taken = 0;
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t pos = static_cast<uint32_t>(base + 32u * blk + b);
+                    if (pos - prev > K) { open = false; break; }
+                    taken |= 1u << b; prev = pos;
+                }
+                cnt += __popc(taken); nFwd += __popc(taken & fwdM); nCan += __popc(taken & canM);
+                if (open && static_cast<unsigned long long>(base) + 32u * (blk + 1) - prev > K) open = false;   // the next block starts out of reach
+            }
+        }
+    };
     while (j <= jEnd) {
         const uint32_t seed = recs[canIdx[j]].x;
-        // ---- the run's first match: leftwards from the seed while the next match is within reach ----
-        uint32_t start = seed;
-        bool open = true;
-        for (long long top = static_cast<long long>(seed) - 1; open && top >= static_cast<long long>(fwdB); top -= 32) {
-            if (start - static_cast<uint32_t>(top) > K) break;
-            const long long q = top - lane;
-            const uint32_t f = q >= static_cast<long long>(fwdB) ? rs.at(static_cast<uint32_t>(q)) : 0u;
-            uint32_t mask = __ballot_sync(0xFFFFFFFFu, (f & 1u) != 0u);
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const uint32_t pos = static_cast<uint32_t>(top - b);
-                if (start - pos > K) { open = false; break; }
-                start = pos;
+        // The seed is the first canonical match of its run: the canonical matches before it in the chain are either in a run
+        // walked already or proven out of reach.  So the run holds 4 canonical matches only if the part from the seed
+        // rightwards does (src/teloscope.cpp:186): a short walk settles the chains that the masks could not break.
+        uint32_t start = seed, cnt, nFwd, nCan, prev;
+        walkRight(seed, std::integral_constant<int, 2>{}, cnt, nFwd, nCan, prev);
+        if (nCan >= 4) {
+            // ---- the run's first match: leftwards from the seed while the next match is within reach ----
+            bool open = true;
+            for (long long top = static_cast<long long>(seed) - 1; open && top >= static_cast<long long>(fwdB); top -= 32) {
+                if (start - static_cast<uint32_t>(top) > K) break;
+                const long long q = top - lane;
+                const uint32_t f = q >= static_cast<long long>(fwdB) ? rs.at(static_cast<uint32_t>(q)) : 0u;
+                uint32_t mask = __ballot_sync(0xFFFFFFFFu, (f & 1u) != 0u);
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const uint32_t pos = static_cast<uint32_t>(top - b);
+                    if (start - pos > K) { open = false; break; }
+                    start = pos;
+                }
             }
+            // ---- the whole run, rightwards from its first match ----
+            if (start != seed) walkRight(start, std::integral_constant<int, kWalkBlocks>{}, cnt, nFwd, nCan, prev);
         }
-        // ---- the run, rightwards from its first match ----
-        uint32_t cnt = 0, nFwd = 0, nCan = 0, prev = start;
-        {
-            const uint32_t f0 = rs.at(start);                         // a match: the seed itself or one found above
-            cnt = 1; nFwd = (f0 >> 1) & 1u; nCan = (f0 >> 2) & 1u;
-        }
-        open = true;
-        for (unsigned long long base = static_cast<unsigned long long>(start) + 1; open && base < revB; base += 32) {
-            if (base - prev > K) break;
-            const unsigned long long q = base + lane;
-            const uint32_t f = q < revB ? rs.at(static_cast<uint32_t>(q)) : 0u;
-            uint32_t mask = __ballot_sync(0xFFFFFFFFu, (f & 1u) != 0u);
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const uint32_t pos = static_cast<uint32_t>(base + b);
-                if (pos - prev > K) { open = false; break; }
-                const uint32_t fb = __shfl_sync(0xFFFFFFFFu, f, b);
-                ++cnt; nFwd += (fb >> 1) & 1u; nCan += (fb >> 2) & 1u; prev = pos;
-            }
-        }
-        if (lane == 0) {
+        if (lane == 0 && nCan >= 4) {
             const uint32_t len = prev + L - start;
             // computeBlockLabel, include/teloscope.h:217-222 (float32)
             const float ratio = __fdiv_rn(__fmul_rn(__uint2float_rn(nFwd), 100.0f), __uint2float_rn(cnt));
             const char label = ratio > 66.6f ? 'p' : (ratio < 33.3f ? 'q' : 'b');
-            if (len >= c.itsMinLen && nCan >= 4 && !(label == 'b' && nFwd < 2 && (cnt - nFwd) < 2)) {
+            if (len >= c.itsMinLen && !(label == 'b' && nFwd < 2 && (cnt - nFwd) < 2)) {
                 DevBlock b{};
                 b.item = item; b.order = 0; b.start = start; b.len = len; b.counts = cnt; b.fwdCount = nFwd;
                 b.canCount = nCan; b.totalCov = cnt * L; b.fwdCov = nFwd * L; b.canCov = nCan * L;
@@ -742,7 +813,13 @@ __global__ void __launch_bounds__(128) itsWalkKernel(const BlockParams p, const 
         }
         // ---- the chain's next canonical match behind this run ----
         ++j;
-        while (j <= jEnd && recs[canIdx[j]].x <= prev) ++j;
+        for (;;) {                                                    // 32 candidates per step
+            const unsigned long long jj = j + lane;
+            const bool behind = jj <= jEnd && recs[canIdx[jj]].x <= prev;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, behind);
+            if (m != 0xFFFFFFFFu) { j += __ffs(~m) - 1; break; }
+            j += 32;
+        }
     }
     }
 }

@@ -51,7 +51,7 @@ cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s);
 // runStarts: runCap entries; runCount: device counter, zeroed by the caller
 cudaError_t launchIts(const BlockParams &p, const uint32_t *canIdx, unsigned long long nCan, unsigned long long *runStarts,
                       unsigned int *runCount, uint32_t runCap, cudaStream_t s);
-// interstitial blocks of window-row items (conn: nCan bytes; chainStarts: chainCap entries; chainCount: zeroed by the caller)
+// interstitial blocks of window-row items (conn: nCan + 32 bytes; chainStarts: chainCap entries; chainCount: zeroed by the caller)
 cudaError_t launchItsRows(const BlockParams &p, const uint32_t *canIdx, unsigned long long nCan, uint8_t *conn,
                           unsigned long long *chainStarts, unsigned int *chainCount, uint32_t chainCap, cudaStream_t s);
 // windows [begin, end) of the ranges (rangePrefix: nRanges + 1 exclusive prefix of their lengths): zero the 32-byte

@@ -789,7 +789,7 @@ def main():
                                       "(H2D of step i+1 overlaps step i)"),
                        "result_records": "full (32-byte windows, 16-byte matches)" if args.full_records else
                                          ("compact (TLS_OUT_COMPACT: 16-byte windows, 8-byte item-relative matches)" if args.compact_records else
-                                          "packed (TLS_OUT_PACKED: 12-byte windows of 10-bit counts, 4-byte item-relative matches)")},
+                                          "packed (TLS_OUT_PACKED: 8-byte windows of 10-bit base counts and 8-bit match counts, 4-byte item-relative matches)")},
             "e2e": {"value": total_bases * args.steps / elapsed_e2e / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define TLS_ABI_VERSION 3   /* 2: tls_result grew (windows16, canonical8, noncanonical8), TLS_OUT_COMPACT; 3: TLS_OUT_PACKED (windows12, canonical4, noncanonical4, pattern_len) */
+#define TLS_ABI_VERSION 4   /* 2: tls_result grew (windows16, canonical8, noncanonical8), TLS_OUT_COMPACT; 3: TLS_OUT_PACKED (canonical4, noncanonical4, pattern_len);
+                               4: packed windows are tls_window8 (windows8, window_exc, n_window_exc) */
 
 typedef enum {
     TLS_OK = 0,
@@ -84,12 +85,19 @@ typedef struct {
 
 /* Packed forms (TLS_OUT_PACKED): the fewest bytes over the host link — what bounds a multi-GPU box whose GPUs share it.
  * Only for pattern tables of ONE length L and window_size <= 1023 (tls_create refuses the flag otherwise): the window
- * holds COUNTS of matches (covered bp = count x L), ten bits per field. */
+ * holds COUNTS of matches (covered bp = count x L). */
 typedef struct {
-    uint32_t w[3];        /* w[0] = A | C << 10 | G << 20;  w[1] = T | canonical matches << 10 | all matches << 20;
-                             w[2] = forward matches.  can_cov = canonical x L, noncan_cov = (all - canonical) x L,
-                             fwd_cov = forward x L, rev_cov = (all - forward) x L (L = tls_result.pattern_len) */
-} tls_window12;           /* 12 bytes */
+    uint32_t w[2];        /* w[0] = A | C << 10 | G << 20 | (T & 3) << 30;
+                             w[1] = T >> 2 | canonical matches << 8 | all matches << 16 | forward matches << 24.
+                             A match count of 255 means "255 or more": the exact counts of such a window are in
+                             tls_result.window_exc (no window of a telomere holds that many matches of one length >= 4).
+                             can_cov = canonical x L, noncan_cov = (all - canonical) x L, fwd_cov = forward x L,
+                             rev_cov = (all - forward) x L (L = tls_result.pattern_len) */
+} tls_window8;            /* 8 bytes */
+typedef struct {
+    uint32_t window;      /* index into windows8 */
+    uint32_t canonical, all, forward;
+} tls_window_exc;         /* windows with a match count >= 255, in no particular order */
 typedef uint32_t tls_match4;   /* bits 0..30: offset in the item (items of 2^31 bases or more are refused at tls_submit),
                                   bit 31: forward strand; len = pattern_len; canonical list: is_canonical = 1 */
 
@@ -104,7 +112,7 @@ enum {                    /* tls_config.outputs */
     TLS_OUT_COMPACT = 1u << 3,  /* windows come back as tls_window16 (tls_result.windows16) and the -m lists as
                                    tls_match8 (canonical8 / noncanonical8); windows / canonical / noncanonical
                                    are then NULL                                                */
-    TLS_OUT_PACKED = 1u << 4    /* windows as tls_window12 (windows12), -m lists as tls_match4 (canonical4 /
+    TLS_OUT_PACKED = 1u << 4    /* windows as tls_window8 (windows8 + window_exc), -m lists as tls_match4 (canonical4 /
                                    noncanonical4); every other window / match pointer is NULL      */
 };
 
@@ -170,9 +178,11 @@ typedef struct {
     const tls_window16 *windows16;
     const tls_match8 *canonical8, *noncanonical8;
     /* TLS_OUT_PACKED (same *_off arrays) */
-    const tls_window12 *windows12;
+    const tls_window8 *windows8;
     const tls_match4 *canonical4, *noncanonical4;
     uint32_t pattern_len;             /* the pattern length when the table has one, else 0 */
+    uint32_t n_window_exc;            /* windows whose match counts did not fit tls_window8 */
+    const tls_window_exc *window_exc;
 } tls_result;
 
 typedef struct tls_ctx tls_ctx;

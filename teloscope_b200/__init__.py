@@ -25,7 +25,7 @@ __all__ = ["ScanConfig", "Scanner", "BatchResult", "expand_patterns", "load_libr
 
 # TLS_LIB: another build of the library (kernel tuning experiments); the product is the in-tree default
 LIB_PATH = Path(os.environ.get("TLS_LIB") or (Path(__file__).resolve().parent / "libteloscope_b200.so"))
-ABI_VERSION = 3
+ABI_VERSION = 4
 MODE_GENOME, MODE_TIPS, MODE_READS = 0, 1, 2
 OUT_ACGT, OUT_MATCHES, OUT_ITS, OUT_COMPACT, OUT_PACKED = 1, 2, 4, 8, 16
 
@@ -40,8 +40,10 @@ WINDOW_DT = np.dtype([("acgt", "<u4", (4,)), ("can_cov", "<u4"), ("noncan_cov", 
 WINDOW16_DT = np.dtype([("acgt", "<u2", (4,)), ("can_cov", "<u2"), ("noncan_cov", "<u2"),
                         ("fwd_cov", "<u2"), ("rev_cov", "<u2")])
 MATCH8_DT = np.dtype([("pos", "<u4"), ("len", "<u2"), ("fwd", "u1"), ("can", "u1")])
-# packed result forms (ScanConfig.packed / TLS_OUT_PACKED): tls_window12 (three words of 10-bit counts), tls_match4 (u32)
-WINDOW12_DT = np.dtype([("w", "<u4", (3,))])
+# packed result forms (ScanConfig.packed / TLS_OUT_PACKED): tls_window8 (10-bit base counts, 8-bit match counts, the few
+# windows with 255 or more matches listed beside), tls_match4 (u32)
+WINDOW8_DT = np.dtype([("w", "<u4", (2,))])
+WINDOW_EXC_DT = np.dtype([("window", "<u4"), ("canonical", "<u4"), ("all", "<u4"), ("forward", "<u4")])
 assert MATCH_DT.itemsize == 16 and BLOCK_DT.itemsize == 48 and WINDOW_DT.itemsize == 32
 assert WINDOW16_DT.itemsize == 16 and MATCH8_DT.itemsize == 8
 
@@ -79,8 +81,8 @@ class _Result(C.Structure):
                 ("n_bases_scanned", C.c_uint64), ("n_matches", C.c_uint64),
                 ("n_kernel_launches", C.c_uint32), ("lean_kernel_ms", C.c_float),
                 ("windows16", C.c_void_p), ("canonical8", C.c_void_p), ("noncanonical8", C.c_void_p),
-                ("windows12", C.c_void_p), ("canonical4", C.c_void_p), ("noncanonical4", C.c_void_p),
-                ("pattern_len", C.c_uint32)]
+                ("windows8", C.c_void_p), ("canonical4", C.c_void_p), ("noncanonical4", C.c_void_p),
+                ("pattern_len", C.c_uint32), ("n_window_exc", C.c_uint32), ("window_exc", C.c_void_p)]
 
 
 EXPORTS = ("tls_expand_patterns", "tls_device_count", "tls_create", "tls_destroy", "tls_submit",
@@ -162,7 +164,7 @@ class ScanConfig:
     out_acgt: bool = True                     # -g or -e
     out_matches: bool = True                  # -m
     compact: bool = False                     # TLS_OUT_COMPACT: 16-byte window and 8-byte match records
-    packed: bool = False                      # TLS_OUT_PACKED: 12-byte window and 4-byte match records (one pattern length, -w <= 1023)
+    packed: bool = False                      # TLS_OUT_PACKED: 8-byte window and 4-byte match records (one pattern length, -w <= 1023)
     canonical_fwd: str = field(init=False)
     canonical_rev: str = field(init=False)
 
@@ -200,19 +202,23 @@ class BatchResult:
         self.window_off = off(r.window_off)
         n_win = self.window_off[-1] if r.mode == MODE_GENOME else 0
         self.pattern_len = int(r.pattern_len)
-        if r.windows12:
-            w12 = arr(r.windows12, n_win, WINDOW12_DT)
+        if r.windows8:
+            w8 = arr(r.windows8, n_win, WINDOW8_DT)
+            self.window_exc = arr(r.window_exc, r.n_window_exc, WINDOW_EXC_DT)
             if copy:                      # widened to the full record: covered bp = count x pattern length
-                w, L = w12["w"].astype(np.uint32), self.pattern_len
-                full = np.zeros(len(w12), dtype=WINDOW_DT)
-                full["acgt"][:, 0] = w[:, 0] & 1023; full["acgt"][:, 1] = (w[:, 0] >> 10) & 1023; full["acgt"][:, 2] = w[:, 0] >> 20
-                full["acgt"][:, 3] = w[:, 1] & 1023
-                can, allm, fwd = (w[:, 1] >> 10) & 1023, w[:, 1] >> 20, w[:, 2]
+                w, L = w8["w"].astype(np.uint32), self.pattern_len
+                full = np.zeros(len(w8), dtype=WINDOW_DT)
+                full["acgt"][:, 0] = w[:, 0] & 1023; full["acgt"][:, 1] = (w[:, 0] >> 10) & 1023; full["acgt"][:, 2] = (w[:, 0] >> 20) & 1023
+                full["acgt"][:, 3] = (w[:, 0] >> 30) | ((w[:, 1] & 255) << 2)
+                can, allm, fwd = (w[:, 1] >> 8) & 255, (w[:, 1] >> 16) & 255, w[:, 1] >> 24
+                if len(self.window_exc):  # 255 = "255 or more": the exact counts are listed
+                    x = self.window_exc
+                    can[x["window"]] = x["canonical"]; allm[x["window"]] = x["all"]; fwd[x["window"]] = x["forward"]
                 full["can_cov"] = can * L; full["noncan_cov"] = (allm - can) * L
                 full["fwd_cov"] = fwd * L; full["rev_cov"] = (allm - fwd) * L
                 self.windows = full
             else:
-                self.windows = w12
+                self.windows = w8
         else:
             self.windows = arr(r.windows16, n_win, WINDOW16_DT) if r.windows16 else arr(r.windows, n_win, WINDOW_DT)
         self.terminal_off = off(r.terminal_off)

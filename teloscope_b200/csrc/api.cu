@@ -62,7 +62,9 @@ struct Trace {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool view = false;                       // p points into another buffer (the per-batch metadata block): nothing to free
     cudaError_t reserve(size_t bytes) {
+        if (view) { p = nullptr; cap = 0; view = false; }
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
@@ -71,7 +73,11 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void setView(void *q) {
+        if (p && !view) cudaFree(p);
+        p = q; cap = 0; view = true;
+    }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; cap = 0; view = false; }
     template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 struct HostBuf {
@@ -95,6 +101,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;       // window / item counters go home while the block kernels run
     cudaStream_t selStream = nullptr;        // -m lists: final records and their copy home, beside the block kernels
+    cudaStream_t itsStream = nullptr;        // interstitial blocks of the items with complete lists, beside those of the window-row items
+    cudaEvent_t evTerminal = nullptr, evItsLists = nullptr;
     cudaEvent_t evGather = nullptr;
     cudaEvent_t evScanDone = nullptr, evCopyDone = nullptr;
     static constexpr int kMaxParts = 8;      // launches of the window-row kernel on a large batch (result copy overlaps the scan)
@@ -130,12 +138,17 @@ struct Slot {
     std::vector<uint32_t> winRangePrefix;    // ... and the exclusive prefix of their lengths (nRanges + 1)
     uint32_t nRowItems = 0;
     HostBuf hMeta3;
+    DevBuf dWinExc;                          // TLS_OUT_PACKED: windows whose match counts do not fit tls_window8
+    HostBuf hWinExc;
+    uint32_t nWinExc = 0;
+    DevBuf dDenseTiles;                      // gather: tiles left to the block-per-tile kernel
+    DevBuf dMetaAll;                         // one block per batch: every read-only table of the scan, uploaded with one copy
     bool fusedReads = false;                 // TLS_MODE_READS batch scored by the one-warp-per-read kernel (scan_reads.cu)
     uint64_t nCanAll = 0, nNctAll = 0;       // canonical / terminal non-canonical records of the batch
     DevBuf dAbsPos, dSeq, dRegions, dTiles, dItemLen, dItemCounts, dItemBegin, dWindows, dMatches, dSlots, dSlotMeta,
         dOvArena, dTileBase, dCounters, dBlocks, dBoundaries, dPass, dSelScratch, dSelCan, dSelNon, dWindows16;
     uint32_t ovCap = 0;
-    // device counters block: [0] ovCursor(u64) [16] blockCount(u32) [20] ITS run count [24] ITS chain count
+    // device counters block: [0] ovCursor(u64) [16] blockCount(u32) [20] ITS run count [24] ITS chain count [28] dense tiles of the gather [48] window exceptions (TLS_OUT_PACKED)
     HostBuf hScan, hCounters, hWindows, hItemCounts, hBlocks, hPass, hSelCan, hSelNon;
     uint64_t matchCap = 0;
     uint32_t blockCap = 0;
@@ -177,7 +190,7 @@ struct tls_ctx {
     bool zeroCopyWindows = false;            // TLS_OUT_COMPACT: the window-row kernel stores its 16-byte window records straight into the
                                              // pinned host buffer (posted writes over PCIe during the scan): measured slower (scan 1.23 ms against 0.95 + copy), off unless TLS_WINDOWS_ZEROCOPY=1
     bool compact = false;                    // TLS_OUT_COMPACT: tls_window16 / tls_match8 results
-    bool packed = false;                     // TLS_OUT_PACKED: tls_window12 / tls_match4 results (compact is set too: one packed device buffer)
+    bool packed = false;                     // TLS_OUT_PACKED: tls_window8 / tls_match4 results (compact is set too: one packed device buffer)
     int rowParts = 3;                        // TLS_ROW_PARTS=n (1..8): launches of the window-row kernel on a large batch
     uint32_t rowMinWindows = kRowMinWindows; // TLS_ROW_MIN_WINDOWS=n: shortest contig (in windows) the window-row kernel takes
     Slot slot[2];
@@ -410,6 +423,9 @@ static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
         TLS_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         TLS_CUDA(cudaStreamCreateWithFlags(&s.copyStream, cudaStreamNonBlocking));
         TLS_CUDA(cudaStreamCreateWithFlags(&s.selStream, cudaStreamNonBlocking));
+        TLS_CUDA(cudaStreamCreateWithFlags(&s.itsStream, cudaStreamNonBlocking));
+        TLS_CUDA(cudaEventCreateWithFlags(&s.evTerminal, cudaEventDisableTiming));
+        TLS_CUDA(cudaEventCreateWithFlags(&s.evItsLists, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreateWithFlags(&s.evGather, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreateWithFlags(&s.evScanDone, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreateWithFlags(&s.evCopyDone, cudaEventDisableTiming));
@@ -450,13 +466,13 @@ void tls_destroy(tls_ctx *ctx) {
     for (Slot &s : ctx->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         for (DevBuf *b : {&s.dRowTiles, &s.dRowRegions, &s.dFastTiles, &s.dGeneralTiles, &s.dRedo, &s.dTileTot, &s.dCanIdx,
-                          &s.dNctIdx, &s.dRunStarts, &s.dZeroLanes, &s.dItemInfo, &s.dConn, &s.dWinRanges})
+                          &s.dNctIdx, &s.dRunStarts, &s.dZeroLanes, &s.dItemInfo, &s.dConn, &s.dWinRanges, &s.dMetaAll, &s.dDenseTiles, &s.dWinExc})
             b->release();
         for (DevBuf *b : {&s.dAbsPos, &s.dSeq, &s.dRegions, &s.dTiles, &s.dItemLen, &s.dItemCounts, &s.dItemBegin, &s.dWindows,
                           &s.dMatches, &s.dSlots, &s.dSlotMeta, &s.dOvArena, &s.dTileBase, &s.dCounters,
                           &s.dBlocks, &s.dBoundaries, &s.dPass, &s.dSelScratch, &s.dSelCan, &s.dSelNon, &s.dWindows16})
             b->release();
-        for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hMeta2, &s.hMeta3, &s.hScan, &s.hCounters, &s.hWindows, &s.hItemCounts, &s.hBlocks, &s.hPass,
+        for (HostBuf *b : {&s.hSeq, &s.hMeta, &s.hMeta2, &s.hMeta3, &s.hScan, &s.hCounters, &s.hWindows, &s.hWinExc, &s.hItemCounts, &s.hBlocks, &s.hPass,
                            &s.hSelCan, &s.hSelNon})
             b->release();
         if (s.evScan0) cudaEventDestroy(s.evScan0);
@@ -466,6 +482,9 @@ void tls_destroy(tls_ctx *ctx) {
         if (s.evAll1) cudaEventDestroy(s.evAll1);
         if (s.copyStream) { cudaStreamSynchronize(s.copyStream); cudaStreamDestroy(s.copyStream); }
         if (s.selStream) { cudaStreamSynchronize(s.selStream); cudaStreamDestroy(s.selStream); }
+        if (s.itsStream) { cudaStreamSynchronize(s.itsStream); cudaStreamDestroy(s.itsStream); }
+        if (s.evTerminal) cudaEventDestroy(s.evTerminal);
+        if (s.evItsLists) cudaEventDestroy(s.evItsLists);
         if (s.evGather) cudaEventDestroy(s.evGather);
         if (s.evScanDone) cudaEventDestroy(s.evScanDone);
         for (cudaEvent_t &e : s.evPart) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -500,6 +519,8 @@ GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
     g.matches = s.dMatches.as<DevMatch>(); g.matchCap = s.matchCap;
     g.canIdx = s.dCanIdx.as<uint32_t>(); g.nctIdx = s.dNctIdx.as<uint32_t>();
     g.selCap = std::max<uint64_t>(s.nCanAll, s.nNctAll);
+    g.denseTiles = s.dDenseTiles.as<uint32_t>();
+    g.denseCount = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 28);
     return g;
 }
 
@@ -601,11 +622,13 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         const bool anyWindows = s.mode == TLS_MODE_GENOME && s.nWindows && !cfg.overlapWindows;
         // what goes home per window: the 32-byte counters, or (TLS_OUT_COMPACT) 16-byte records: written directly by the
         // window-row kernel, packed from the counters for the windows of the other kernels
-        const size_t winRec = ctx->packed ? 12 : (ctx->compact ? 16 : 32);
+        const size_t winRec = ctx->packed ? 8 : (ctx->compact ? 16 : 32);
         if (anyWindows) {
             TLS_CUDA(s.hWindows.reserve(s.nWindows * winRec));
             if (ctx->compact) TLS_CUDA(s.dWindows16.reserve(s.nWindows * 16));
         }
+        if (ctx->packed) TLS_CUDA(s.dWinExc.reserve(std::max<uint64_t>(s.nWindows, 1) * sizeof(tls_window_exc)));   // every window could be one
+        unsigned int *winExcCount = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 48);
         const uint8_t *winSrc = ctx->compact ? s.dWindows16.as<uint8_t>() : s.dWindows.as<uint8_t>();
         // Compact records of a batch with window-row contigs: the kernels store them straight into the pinned host buffer
         // (48 MB per 3 Gbp trickle over PCIe while the scan runs, nothing is left to copy afterwards).
@@ -613,7 +636,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         void *win16Dst = s.dWindows16.p;
         if (zeroCopy) TLS_CUDA(cudaHostGetDevicePointer(&win16Dst, s.hWindows.p, 0));
         if (anyWindows && ctx->compact && nRow && nRangeWindows) {
-            if (ctx->packed) TLS_CUDA(launchPackWindow12Ranges(s.dWindows.as<uint32_t>(), win16Dst, dRanges, dRangePrefix, nRanges, nRangeWindows, cfg.cls[0].len, s.stream));
+            if (ctx->packed) TLS_CUDA(launchPackWindow8Ranges(s.dWindows.as<uint32_t>(), win16Dst, dRanges, dRangePrefix, nRanges, nRangeWindows, cfg.cls[0].len, s.dWinExc.p, winExcCount, s.stream));
             else TLS_CUDA(launchPackWindowRanges(s.dWindows.as<uint32_t>(), win16Dst, dRanges, dRangePrefix, nRanges, nRangeWindows, s.stream));
             s.launches++;
         }
@@ -624,7 +647,8 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
             f.indexRow = ctx->dIndex16.as<uint8_t>();
             f.two16 = 65536u;
             f.windows16 = (ctx->compact && !ctx->packed) ? static_cast<uint4 *>(win16Dst) : nullptr;
-            f.windows12 = ctx->packed ? static_cast<uint32_t *>(win16Dst) : nullptr;
+            f.windows8 = ctx->packed ? static_cast<uint2 *>(win16Dst) : nullptr;
+            f.winExc = s.dWinExc.as<uint4>(); f.winExcCount = winExcCount;
             f.zeroLanes = s.dZeroLanes.as<uint32_t>();
             f.flagTab = ctx->dFlags.as<uint8_t>() + cfg.cls[0].flagOffset;
             f.flagTabBytes = ((1u << (2 * cfg.cls[0].len)) + 15u) & ~15u;
@@ -710,7 +734,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         TLS_CUDA(cudaEventRecord(s.evFast1, s.stream));
         TLS_CUDA(cudaEventRecord(s.evScan1, s.stream));
         if (anyWindows && ctx->compact && !nRow) {
-            if (ctx->packed) TLS_CUDA(launchPackWindows12(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, cfg.cls[0].len, s.stream));
+            if (ctx->packed) TLS_CUDA(launchPackWindows8(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, cfg.cls[0].len, s.dWinExc.p, winExcCount, s.stream));
             else TLS_CUDA(launchPackWindows(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, s.stream));
             s.launches++;
         }
@@ -1007,63 +1031,47 @@ static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
         }
     }
     tr.mark("plan");
-    // ---- upload metadata ------------------------------------------------------------------------
+    // ---- upload metadata: ONE pinned block, ONE copy; the device buffers of the tables are views into it --------------
     {
-        const size_t bFast = s.fastTiles.size() * sizeof(DevFastTile), bGen = s.generalTiles.size() * 4,
-                     bRow = s.rowRegions.size() * sizeof(DevRowRegion);
-        TLS_CUDA(s.hMeta2.reserve(bFast + bGen + bRow + 64));
-        uint8_t *h2 = s.hMeta2.as<uint8_t>();
-        if (bRow) std::memcpy(h2, s.rowRegions.data(), bRow);
-        if (bFast) std::memcpy(h2 + bRow, s.fastTiles.data(), bFast);
-        if (bGen) std::memcpy(h2 + bRow + bFast, s.generalTiles.data(), bGen);
-        TLS_CUDA(s.dRowRegions.reserve(std::max<size_t>(bRow, 16)));
+        struct Part { const void *src; size_t bytes; DevBuf *view; size_t off; };
+        Part parts[] = {
+            {s.rowRegions.data(), s.rowRegions.size() * sizeof(DevRowRegion), &s.dRowRegions, 0},
+            {s.fastTiles.data(), s.fastTiles.size() * sizeof(DevFastTile), &s.dFastTiles, 0},
+            {s.generalTiles.data(), s.generalTiles.size() * 4, &s.dGeneralTiles, 0},
+            {s.itemInfo.data(), static_cast<size_t>(n) * sizeof(DevItemInfo), &s.dItemInfo, 0},
+            {s.winRanges.data(), s.winRanges.size() * sizeof(uint2), &s.dWinRanges, 0},          // followed directly by the prefix
+            {s.winRangePrefix.data(), s.winRanges.empty() ? 0 : s.winRangePrefix.size() * 4, nullptr, 0},
+            {s.absPos.data(), static_cast<size_t>(n) * 8, &s.dAbsPos, 0},
+            {s.regions.data(), s.regions.size() * sizeof(DevRegion), &s.dRegions, 0},
+            {s.itemLen.data(), static_cast<size_t>(n) * 4, &s.dItemLen, 0},
+            {s.tiles.data(), s.tiles.size() * sizeof(DevTile), nullptr, 0},                      // compact: scattered below
+            {s.tileIndex.data(), s.tiles.size() * 4, nullptr, 0},
+        };
+        size_t total = 0;
+        for (Part &pt : parts) {
+            if (pt.view) total = (total + 255) & ~size_t(255);       // a table starts on a 256-byte boundary; what follows a table directly is 8-aligned
+            else total = (total + 7) & ~size_t(7);
+            pt.off = total;
+            total += pt.bytes;
+        }
+        total += 256;
+        TLS_CUDA(s.hMeta.reserve(total));
+        TLS_CUDA(s.dMetaAll.reserve(total));
+        uint8_t *hm = s.hMeta.as<uint8_t>(), *dm = s.dMetaAll.as<uint8_t>();
+        for (const Part &pt : parts) {
+            if (pt.bytes) std::memcpy(hm + pt.off, pt.src, pt.bytes);
+            if (pt.view) pt.view->setView(dm + pt.off);
+        }
+        TLS_CUDA(cudaMemcpyAsync(dm, hm, total, cudaMemcpyHostToDevice, s.stream));
         TLS_CUDA(s.dRowTiles.reserve(std::max<size_t>(static_cast<size_t>(s.nRowUnits) * sizeof(DevRowUnit), 16)));
-        TLS_CUDA(s.dFastTiles.reserve(std::max<size_t>(bFast, 16)));
-        TLS_CUDA(s.dGeneralTiles.reserve(std::max<size_t>(bGen, 16)));
-        if (bRow) {
-            TLS_CUDA(cudaMemcpyAsync(s.dRowRegions.p, h2, bRow, cudaMemcpyHostToDevice, s.stream));
+        TLS_CUDA(s.dTiles.reserve(std::max<size_t>(static_cast<size_t>(s.nTilesAll) * sizeof(DevTile), 16)));
+        if (!s.rowRegions.empty())
             TLS_CUDA(launchRowPlan(s.dRowRegions.as<DevRowRegion>(), static_cast<uint32_t>(s.rowRegions.size()), ctx->cfg.window_size,
                                    s.dRowTiles.as<DevRowUnit>(), s.nRowUnits, s.stream));
-        }
-        if (bFast) TLS_CUDA(cudaMemcpyAsync(s.dFastTiles.p, h2 + bRow, bFast, cudaMemcpyHostToDevice, s.stream));
-        if (bGen) TLS_CUDA(cudaMemcpyAsync(s.dGeneralTiles.p, h2 + bRow + bFast, bGen, cudaMemcpyHostToDevice, s.stream));
+        if (!s.tiles.empty())                                         // the lean / general kernels' tiles, to their places in the tile table
+            TLS_CUDA(launchScatterTiles(reinterpret_cast<const DevTile *>(dm + parts[9].off), reinterpret_cast<const uint32_t *>(dm + parts[10].off),
+                                        static_cast<uint32_t>(s.tiles.size()), s.dTiles.as<DevTile>(), s.stream));
     }
-    {
-        const size_t bInfo = static_cast<size_t>(n) * sizeof(DevItemInfo), bRanges = s.winRanges.size() * sizeof(uint2),
-                     bPrefix = s.winRanges.empty() ? 0 : s.winRangePrefix.size() * 4;
-        TLS_CUDA(s.hMeta3.reserve(bInfo + bRanges + bPrefix + 64));
-        uint8_t *h3 = s.hMeta3.as<uint8_t>();
-        if (bInfo) std::memcpy(h3, s.itemInfo.data(), bInfo);
-        if (bRanges) std::memcpy(h3 + bInfo, s.winRanges.data(), bRanges);
-        if (bPrefix) std::memcpy(h3 + bInfo + bRanges, s.winRangePrefix.data(), bPrefix);
-        TLS_CUDA(s.dItemInfo.reserve(std::max<size_t>(bInfo, 16)));
-        TLS_CUDA(s.dWinRanges.reserve(std::max<size_t>(bRanges + bPrefix, 16)));
-        if (bInfo) TLS_CUDA(cudaMemcpyAsync(s.dItemInfo.p, h3, bInfo, cudaMemcpyHostToDevice, s.stream));
-        if (bRanges) TLS_CUDA(cudaMemcpyAsync(s.dWinRanges.p, h3 + bInfo, bRanges + bPrefix, cudaMemcpyHostToDevice, s.stream));
-    }
-    const size_t bRegions = s.regions.size() * sizeof(DevRegion), bTiles = s.tiles.size() * sizeof(DevTile),
-                 bLen = static_cast<size_t>(n) * 4, bAbs = static_cast<size_t>(n) * 8;
-    TLS_CUDA(s.hMeta.reserve(bRegions + bTiles + bLen + bAbs + 64));
-    uint8_t *hm = s.hMeta.as<uint8_t>();
-    if (bRegions) std::memcpy(hm, s.regions.data(), bRegions);
-    if (bTiles) std::memcpy(hm + bRegions, s.tiles.data(), bTiles);
-    if (bLen) std::memcpy(hm + bRegions + bTiles, s.itemLen.data(), bLen);
-    const size_t absOff = (bRegions + bTiles + bLen + 7) & ~size_t(7);
-    if (bAbs) std::memcpy(hm + absOff, s.absPos.data(), bAbs);
-    TLS_CUDA(s.dAbsPos.reserve(std::max<size_t>(bAbs, 16)));
-    if (bAbs) TLS_CUDA(cudaMemcpyAsync(s.dAbsPos.p, hm + absOff, bAbs, cudaMemcpyHostToDevice, s.stream));
-    TLS_CUDA(s.dRegions.reserve(std::max<size_t>(bRegions, 16)));
-    TLS_CUDA(s.dTiles.reserve(std::max<size_t>(static_cast<size_t>(s.nTilesAll) * sizeof(DevTile), 16)));
-    TLS_CUDA(s.dItemLen.reserve(std::max<size_t>(bLen, 16)));
-    if (bRegions) TLS_CUDA(cudaMemcpyAsync(s.dRegions.p, hm, bRegions, cudaMemcpyHostToDevice, s.stream));
-    for (size_t k = 0; k < s.tiles.size();) {               // runs of consecutive table indices go up in one copy each
-        size_t e = k + 1;
-        while (e < s.tiles.size() && s.tileIndex[e] == s.tileIndex[e - 1] + 1) ++e;
-        TLS_CUDA(cudaMemcpyAsync(s.dTiles.as<DevTile>() + s.tileIndex[k], hm + bRegions + k * sizeof(DevTile), (e - k) * sizeof(DevTile),
-                                 cudaMemcpyHostToDevice, s.stream));
-        k = e;
-    }
-    if (bLen) TLS_CUDA(cudaMemcpyAsync(s.dItemLen.p, hm + bRegions + bTiles, bLen, cudaMemcpyHostToDevice, s.stream));
     TLS_CUDA(s.dItemCounts.reserve(std::max<size_t>(n, 1) * sizeof(DevItemCounts)));
     TLS_CUDA(s.dItemBegin.reserve((static_cast<size_t>(n) + 1) * 8));
     TLS_CUDA(s.dWindows.reserve(std::max<uint64_t>(nWin, 1) * 32));
@@ -1152,8 +1160,12 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
         for (bool first = true;; first = false) {
             TLS_CUDA(s.dBlocks.reserve(static_cast<size_t>(s.blockCap) * sizeof(DevBlock)));
             uint8_t *cnt = s.dCounters.as<uint8_t>();
-            TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 12, s.stream));           // [16] block count, [20] ITS run count, [24] ITS chain count
-            if (first && s.nTilesAll) { TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream)); s.launches++; }
+            TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 16, s.stream));           // [16] block count, [20] ITS run count, [24] ITS chain count, [28] dense tiles
+            if (first && s.nTilesAll) {
+                TLS_CUDA(s.dDenseTiles.reserve(static_cast<size_t>(s.nTilesAll) * 4));
+                TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream));
+                s.launches += 2;
+            }
             if (reads && n) TLS_CUDA(cudaMemsetAsync(s.dPass.p, 0, n, s.stream));
             if (n) {
                 if (first) { TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), s.nRowItems ? s.dItemInfo.as<DevItemInfo>() : nullptr, n, s.dItemBegin.as<unsigned long long>(), s.stream)); s.launches++; }
@@ -1194,9 +1206,10 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                                                   static_cast<uint32_t>(s.nWindows), ctx->dcfg, s.dWindows.as<uint32_t>(), s.stream));
                     s.launches++;
                     if (ctx->compact) {
-                        const size_t rec = ctx->packed ? 12 : 16;
+                        const size_t rec = ctx->packed ? 8 : 16;
                         TLS_CUDA(s.dWindows16.reserve(s.nWindows * 16));
-                        if (ctx->packed) TLS_CUDA(launchPackWindows12(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, ctx->dcfg.cls[0].len, s.stream));
+                        if (ctx->packed) TLS_CUDA(launchPackWindows8(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, ctx->dcfg.cls[0].len, s.dWinExc.p,
+                                                                     reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 48), s.stream));
                         else TLS_CUDA(launchPackWindows(s.dWindows.as<uint32_t>(), s.dWindows16.p, s.nWindows, s.stream));
                         s.launches++;
                         TLS_CUDA(s.hWindows.reserve(s.nWindows * rec));
@@ -1230,17 +1243,29 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                 TLS_CUDA(launchTerminal(bp, s.stream));
                 s.launches++;
                 if (genome && s.nMatches >= 2 && s.nCanAll >= 4) {
-                    if (s.nRowItems < n) {                  // items with complete record lists: runs are read from the list
+                    const bool lists = s.nRowItems < n, rows = s.nRowItems != 0;
+                    if (rows) TLS_CUDA(s.dConn.reserve(s.nCanAll + 64));     // itsWalkKernel reads 32 links at a time (before any launch: may synchronise)
+                    // the two kinds of items are independent (blocks are appended with atomics): side by side when both exist
+                    cudaStream_t listStream = s.stream;
+                    if (lists && rows) {
+                        TLS_CUDA(cudaEventRecord(s.evTerminal, s.stream));
+                        TLS_CUDA(cudaStreamWaitEvent(s.itsStream, s.evTerminal, 0));
+                        listStream = s.itsStream;
+                    }
+                    if (lists) {                            // items with complete record lists: runs are read from the list
                         TLS_CUDA(launchIts(bp, s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dRunStarts.as<unsigned long long>(),
-                                           reinterpret_cast<unsigned int *>(cnt + 20), runCap, s.stream));
+                                           reinterpret_cast<unsigned int *>(cnt + 20), runCap, listStream));
                         s.launches += 2;
                     }
-                    if (s.nRowItems) {                      // window-row items: connectivity from the zero-lane masks, runs from the sequence
-                        TLS_CUDA(s.dConn.reserve(s.nCanAll + 64));     // itsWalkKernel reads 32 links at a time
+                    if (rows) {                             // window-row items: connectivity from the zero-lane masks, runs from the sequence
                         TLS_CUDA(launchItsRows(bp, s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dConn.as<uint8_t>(),
                                                s.dRunStarts.as<unsigned long long>() + runCap,
                                                reinterpret_cast<unsigned int *>(cnt + 24), runCap, s.stream));
                         s.launches += 3;
+                    }
+                    if (lists && rows) {
+                        TLS_CUDA(cudaEventRecord(s.evItsLists, s.itsStream));
+                        TLS_CUDA(cudaStreamWaitEvent(s.stream, s.evItsLists, 0));
                     }
                 }
             }
@@ -1260,6 +1285,11 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
         unsigned long long selTotals[2] = {wantSel ? s.nCanAll : 0, wantSel ? s.nNctAll : 0};
 
         // ---- copy results back ------------------------------------------------------------------------
+        s.nWinExc = (ctx->packed && !reads) ? *reinterpret_cast<unsigned int *>(s.hCounters.as<uint8_t>() + 48) : 0u;
+        if (s.nWinExc) {
+            TLS_CUDA(s.hWinExc.reserve(static_cast<size_t>(s.nWinExc) * sizeof(tls_window_exc)));
+            TLS_CUDA(cudaMemcpyAsync(s.hWinExc.p, s.dWinExc.p, static_cast<size_t>(s.nWinExc) * sizeof(tls_window_exc), cudaMemcpyDeviceToHost, s.stream));
+        }
         if (nBlocks) {
             TLS_CUDA(s.hBlocks.reserve(static_cast<size_t>(nBlocks) * sizeof(DevBlock)));
             TLS_CUDA(cudaMemcpyAsync(s.hBlocks.p, s.dBlocks.p, static_cast<size_t>(nBlocks) * sizeof(DevBlock),
@@ -1324,7 +1354,9 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
     res->window_off = s.winOff.data();
     res->windows = ctx->compact ? nullptr : s.hWindows.as<tls_window>();
     res->windows16 = (ctx->compact && !ctx->packed) ? s.hWindows.as<tls_window16>() : nullptr;
-    res->windows12 = ctx->packed ? s.hWindows.as<tls_window12>() : nullptr;
+    res->windows8 = ctx->packed ? s.hWindows.as<tls_window8>() : nullptr;
+    res->n_window_exc = ctx->packed ? s.nWinExc : 0;
+    res->window_exc = (ctx->packed && s.nWinExc) ? s.hWinExc.as<tls_window_exc>() : nullptr;
     res->canonical4 = s.nSelCan && ctx->packed ? s.hSelCan.as<tls_match4>() : nullptr;
     res->noncanonical4 = s.nSelNon && ctx->packed ? s.hSelNon.as<tls_match4>() : nullptr;
     res->pattern_len = ctx->dcfg.nClasses == 1 ? ctx->dcfg.cls[0].len : 0u;

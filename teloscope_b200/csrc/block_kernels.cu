@@ -157,7 +157,10 @@ __global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, 
 // the warp copies slot after slot with coalesced 8-byte accesses.  (All window / item accounting was done by the scan kernels.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
-constexpr uint32_t kGatherBlocksPerSm = 4;
+#ifndef TLS_GATHER_BLOCKS_PER_SM
+#define TLS_GATHER_BLOCKS_PER_SM 16
+#endif
+constexpr uint32_t kGatherBlocksPerSm = TLS_GATHER_BLOCKS_PER_SM;   // 4 x 256 threads are resident; several short waves balance better than one long one (measured: 4: 135 us, 16: 108 us)
 
 struct TileHeader {
     unsigned long long base, baseEnd, baseCan, baseNct;
@@ -174,13 +177,9 @@ __device__ __forceinline__ TileHeader loadTileHeader(const GatherParams &g, uint
     return h;
 }
 
-__device__ __forceinline__ void gatherTile(const GatherParams &g, uint32_t tile, uint32_t lane, const TileHeader &hd) {
-    const size_t slot0 = static_cast<size_t>(tile) * kTileRows;
-    const unsigned long long base = hd.base, baseCan = hd.baseCan, baseNct = hd.baseNct;
-    const uint4 meta = hd.meta;
-    const uint32_t total = static_cast<uint32_t>(hd.baseEnd - base);
-    if (total == 0) return;
-    // exclusive prefixes over the 32 row slots (a tile holds at most 32 x ovChunk records: 16 bits per field would not do)
+struct TilePrefix { uint32_t exAll, exCan, exNct; };
+// exclusive prefixes over the 32 row slots (a tile holds at most 32 x ovChunk records: 16 bits per field would not do)
+__device__ __forceinline__ TilePrefix tilePrefix(const uint4 &meta, uint32_t lane) {
     uint32_t inclAll = meta.x, inclCan = meta.z, inclNct = meta.w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -188,68 +187,113 @@ __device__ __forceinline__ void gatherTile(const GatherParams &g, uint32_t tile,
                        n = __shfl_up_sync(0xFFFFFFFFu, inclNct, d);
         if (lane >= static_cast<uint32_t>(d)) { inclAll += a; inclCan += c; inclNct += n; }
     }
-    const uint32_t exAll = inclAll - meta.x, exCan = inclCan - meta.z, exNct = inclNct - meta.w;
+    return TilePrefix{inclAll - meta.x, inclCan - meta.z, inclNct - meta.w};
+}
+
+constexpr uint32_t kDenseTile = 128;                                // more records than this: the block-per-tile kernel
+
+// A tile of sparse units: lane r copies row r's records.  Tiles with many records are only listed here.
+__device__ __forceinline__ void gatherTile(const GatherParams &g, uint32_t tile, uint32_t lane, const TileHeader &hd) {
+    const size_t slot0 = static_cast<size_t>(tile) * kTileRows;
+    const unsigned long long base = hd.base, baseCan = hd.baseCan, baseNct = hd.baseNct;
+    const uint4 meta = hd.meta;
+    const uint32_t total = static_cast<uint32_t>(hd.baseEnd - base);
+    if (total == 0) return;
+    if (total > kDenseTile) {
+        if (lane == 0) g.denseTiles[atomicAdd(g.denseCount, 1u)] = tile;
+        return;
+    }
+    const TilePrefix px = tilePrefix(meta, lane);
+    const uint32_t exAll = px.exAll, exCan = px.exCan, exNct = px.exNct;
     const uint2 *slots = reinterpret_cast<const uint2 *>(g.slots);
     const uint2 *ovArena = reinterpret_cast<const uint2 *>(g.ovArena);
     uint2 *out = reinterpret_cast<uint2 *>(g.matches);
-
-    if (total <= 128u) {
-        // lane r: row r's records, one after the other
-        const uint2 *src = slots + (slot0 + lane) * g.slotCap;
-        unsigned long long o = base + exAll, oc = baseCan + exCan, on = baseNct + exNct;
-        auto put = [&](const uint2 rec) {
-            if (o < g.matchCap) out[o] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
-            const uint32_t flags = (rec.y >> 16) & 0xFFu;
-            if (flags & kMatchCan) { if (oc < g.selCap) g.canIdx[oc] = static_cast<uint32_t>(o); ++oc; }
-            else if (flags & kMatchTerm) { if (on < g.selCap) g.nctIdx[on] = static_cast<uint32_t>(o); ++on; }
-            ++o;
-        };
-        // the first records of the row (a sparse row holds one or two) are all requested before any is stored
-        constexpr uint32_t kAhead = 4;
-        const uint32_t direct = min(min(meta.x, g.slotCap), kAhead);
-        uint2 first[kAhead];
+    // lane r: row r's records, one after the other
+    const uint2 *src = slots + (slot0 + lane) * g.slotCap;
+    unsigned long long o = base + exAll, oc = baseCan + exCan, on = baseNct + exNct;
+    auto put = [&](const uint2 rec) {
+        if (o < g.matchCap) out[o] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
+        const uint32_t flags = (rec.y >> 16) & 0xFFu;
+        if (flags & kMatchCan) { if (oc < g.selCap) g.canIdx[oc] = static_cast<uint32_t>(o); ++oc; }
+        else if (flags & kMatchTerm) { if (on < g.selCap) g.nctIdx[on] = static_cast<uint32_t>(o); ++on; }
+        ++o;
+    };
+    // the first records of the row (a sparse row holds one or two) are all requested before any is stored
+    constexpr uint32_t kAhead = 4;
+    const uint32_t direct = min(min(meta.x, g.slotCap), kAhead);
+    uint2 first[kAhead];
 #pragma unroll
-        for (uint32_t k = 0; k < kAhead; ++k) first[k] = k < direct ? __ldg(src + k) : make_uint2(0u, 0u);
+    for (uint32_t k = 0; k < kAhead; ++k) first[k] = k < direct ? __ldg(src + k) : make_uint2(0u, 0u);
 #pragma unroll
-        for (uint32_t k = 0; k < kAhead; ++k) if (k < direct) put(first[k]);
-        for (uint32_t k = direct; k < meta.x; ++k) {
-            uint2 rec;
-            if (k < g.slotCap) rec = __ldg(src + k);
-            else if (static_cast<unsigned long long>(meta.y) + (k - g.slotCap) < g.ovCap) rec = ovArena[meta.y + (k - g.slotCap)];
-            else { ++o; continue; }                                 // overflow arena exhausted: the host reruns the scan
-            put(rec);
-        }
-        return;
+    for (uint32_t k = 0; k < kAhead; ++k) if (k < direct) put(first[k]);
+    for (uint32_t k = direct; k < meta.x; ++k) {
+        uint2 rec;
+        if (k < g.slotCap) rec = __ldg(src + k);
+        else if (static_cast<unsigned long long>(meta.y) + (k - g.slotCap) < g.ovCap) rec = ovArena[meta.y + (k - g.slotCap)];
+        else { ++o; continue; }                                 // overflow arena exhausted: the host reruns the scan
+        put(rec);
     }
+}
+
+// A tile with many records: one BLOCK per tile, warp w copies the slots [4 w, 4 w + 4) with coalesced 8-byte accesses, the first
+// 32 records of its four slots requested together.
+__global__ void __launch_bounds__(kGatherThreads) gatherDenseKernel(const GatherParams g) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t nDense = *g.denseCount;
+    const uint2 *slots = reinterpret_cast<const uint2 *>(g.slots);
+    const uint2 *ovArena = reinterpret_cast<const uint2 *>(g.ovArena);
+    uint2 *out = reinterpret_cast<uint2 *>(g.matches);
     const uint32_t laneLt = (1u << lane) - 1u;
-    for (int s = 0; s < kTileRows; ++s) {
-        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, meta.x, s);
-        if (cnt == 0) continue;
-        const unsigned long long ov = __shfl_sync(0xFFFFFFFFu, meta.y, s);
-        const bool anySel = __shfl_sync(0xFFFFFFFFu, meta.z | meta.w, s) != 0;
-        const unsigned long long o = base + __shfl_sync(0xFFFFFFFFu, exAll, s);
-        unsigned long long oc = baseCan + __shfl_sync(0xFFFFFFFFu, exCan, s), on = baseNct + __shfl_sync(0xFFFFFFFFu, exNct, s);
-        const uint2 *src = slots + (slot0 + s) * g.slotCap;
-        for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
-            const uint32_t k = k0 + lane;
-            uint2 rec = make_uint2(0u, 0u);
-            bool have = k < cnt;
-            if (have) {
-                if (k < g.slotCap) rec = __ldg(src + k);
-                else if (ov + (k - g.slotCap) < g.ovCap) rec = ovArena[ov + (k - g.slotCap)];
-                else have = false;                              // overflow arena exhausted: the host reruns the scan
+    constexpr int kSlotBatch = kTileRows / (kGatherThreads / 32);   // 4
+    for (uint32_t i = blockIdx.x; i < nDense; i += gridDim.x) {
+        const uint32_t tile = g.denseTiles[i];
+        const TileHeader hd = loadTileHeader(g, tile, lane);
+        const size_t slot0 = static_cast<size_t>(tile) * kTileRows;
+        const unsigned long long base = hd.base, baseCan = hd.baseCan, baseNct = hd.baseNct;
+        const uint4 meta = hd.meta;
+        const TilePrefix px = tilePrefix(meta, lane);
+        const uint32_t exAll = px.exAll, exCan = px.exCan, exNct = px.exNct;
+        const int s0 = static_cast<int>(warp) * kSlotBatch;
+        uint2 head[kSlotBatch];
+#pragma unroll
+        for (int u = 0; u < kSlotBatch; ++u) {
+            const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, meta.x, s0 + u);
+            head[u] = lane < min(cnt, g.slotCap) ? __ldg(slots + (slot0 + s0 + u) * g.slotCap + lane) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < kSlotBatch; ++u) {
+            const int s = s0 + u;
+            const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, meta.x, s);
+            if (cnt == 0) continue;
+            const unsigned long long ov = __shfl_sync(0xFFFFFFFFu, meta.y, s);
+            const bool anySel = __shfl_sync(0xFFFFFFFFu, meta.z | meta.w, s) != 0;
+            const unsigned long long o = base + __shfl_sync(0xFFFFFFFFu, exAll, s);
+            unsigned long long oc = baseCan + __shfl_sync(0xFFFFFFFFu, exCan, s), on = baseNct + __shfl_sync(0xFFFFFFFFu, exNct, s);
+            const uint2 *src = slots + (slot0 + s) * g.slotCap;
+            for (uint32_t k0 = 0; k0 < cnt; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                uint2 rec = head[u];
+                bool have = k < cnt;
+                if (have && k0 != 0) {
+                    if (k < g.slotCap) rec = __ldg(src + k);
+                    else if (ov + (k - g.slotCap) < g.ovCap) rec = ovArena[ov + (k - g.slotCap)];
+                    else have = false;                          // overflow arena exhausted: the host reruns the scan
+                } else if (have && k >= g.slotCap) {            // first chunk of a slot with fewer than 32 places
+                    if (ov + (k - g.slotCap) < g.ovCap) rec = ovArena[ov + (k - g.slotCap)];
+                    else have = false;
+                }
+                if (have && o + k < g.matchCap) out[o + k] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
+                if (!anySel) continue;
+                // index lists of the -m selections, in genome order
+                const uint32_t flags = (rec.y >> 16) & 0xFFu;
+                const bool isC = have && (flags & kMatchCan);
+                const bool isN = have && (flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
+                const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
+                if (isC && oc + __popc(bc & laneLt) < g.selCap) g.canIdx[oc + __popc(bc & laneLt)] = static_cast<uint32_t>(o + k);
+                if (isN && on + __popc(bn & laneLt) < g.selCap) g.nctIdx[on + __popc(bn & laneLt)] = static_cast<uint32_t>(o + k);
+                oc += __popc(bc);
+                on += __popc(bn);
             }
-            if (have && o + k < g.matchCap) out[o + k] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
-            if (!anySel) continue;
-            // index lists of the -m selections, in genome order
-            const uint32_t flags = (rec.y >> 16) & 0xFFu;
-            const bool isC = have && (flags & kMatchCan);
-            const bool isN = have && (flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
-            const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
-            if (isC && oc + __popc(bc & laneLt) < g.selCap) g.canIdx[oc + __popc(bc & laneLt)] = static_cast<uint32_t>(o + k);
-            if (isN && on + __popc(bn & laneLt) < g.selCap) g.nctIdx[on + __popc(bn & laneLt)] = static_cast<uint32_t>(o + k);
-            oc += __popc(bc);
-            on += __popc(bn);
         }
     }
 }
@@ -272,6 +316,16 @@ __global__ void __launch_bounds__(kGatherThreads) gatherKernel(const GatherParam
     }
 }
 
+__global__ void __launch_bounds__(256) scatterTilesKernel(const DevTile *compact, const uint32_t *index, uint32_t n, DevTile *tiles) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) tiles[index[k]] = compact[k];
+}
+cudaError_t launchScatterTiles(const DevTile *compact, const uint32_t *index, uint32_t n, DevTile *tiles, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    scatterTilesKernel<<<(n + 255) / 256, 256, 0, s>>>(compact, index, n, tiles);
+    return cudaGetLastError();
+}
+
 cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, unsigned long long *blockSums,
                            const unsigned int *ovCursor, const unsigned int *redo, unsigned long long *hostOut, cudaStream_t s) {
     const uint32_t nBlk = std::max<uint32_t>(1u, (nTiles + kScanChunk - 1) / kScanChunk);
@@ -284,6 +338,7 @@ cudaError_t launchGather(const GatherParams &g, cudaStream_t s) {
     if (g.nTiles == 0) return cudaSuccess;
     const uint32_t blocks = std::min<uint32_t>((g.nTiles + kGatherThreads / 32 - 1) / (kGatherThreads / 32), 148u * kGatherBlocksPerSm);
     gatherKernel<<<blocks, kGatherThreads, 0, s>>>(g);
+    gatherDenseKernel<<<std::min<uint32_t>(g.nTiles, 148u * 4u), kGatherThreads, 0, s>>>(g);
     return cudaGetLastError();
 }
 
@@ -879,24 +934,22 @@ __global__ void __launch_bounds__(256) packWindowRangesKernel(const uint4 *in, u
     out[w] = make_uint4(a.x | (a.y << 16), a.z | (a.w << 16), b.x | (b.y << 16), b.z | (b.w << 16));
 }
 
-// tls_window (8 x u32) -> tls_window12 (counts of matches, ten bits per field): one pattern length L, window <= 1023
-__device__ __forceinline__ void storeWindow12(uint32_t *out, size_t w, const uint4 a, const uint4 b, uint32_t L) {
-    const uint32_t can = b.x / L, all = (b.x + b.y) / L, fwd = b.z / L;
-    out[3 * w] = a.x | (a.y << 10) | (a.z << 20);
-    out[3 * w + 1] = a.w | (can << 10) | (all << 20);
-    out[3 * w + 2] = fwd;
+// tls_window (8 x u32) -> tls_window8 (counts of matches): one pattern length L, window <= 1023
+__device__ __forceinline__ void storeWindow8(uint2 *out, size_t w, const uint4 a, const uint4 b, uint32_t L, uint4 *winExc, unsigned int *winExcCount) {
+    out[w] = packWindow8(static_cast<uint32_t>(w), a.x, a.y, a.z, a.w, b.x / L, (b.x + b.y) / L, b.z / L, winExc, winExcCount);
 }
-__global__ void __launch_bounds__(256) packWindows12Kernel(const uint4 *in, uint32_t *out, unsigned long long n, uint32_t L) {
+__global__ void __launch_bounds__(256) packWindows8Kernel(const uint4 *in, uint2 *out, unsigned long long n, uint32_t L, uint4 *winExc,
+                                                          unsigned int *winExcCount) {
     const unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    storeWindow12(out, i, in[2 * i], in[2 * i + 1], L);
+    storeWindow8(out, i, in[2 * i], in[2 * i + 1], L, winExc, winExcCount);
 }
-__global__ void __launch_bounds__(256) packWindow12RangesKernel(const uint4 *in, uint32_t *out, const uint2 *ranges, const uint32_t *rangePrefix,
-                                                                uint32_t nRanges, uint32_t total, uint32_t L) {
+__global__ void __launch_bounds__(256) packWindow8RangesKernel(const uint4 *in, uint2 *out, const uint2 *ranges, const uint32_t *rangePrefix,
+                                                               uint32_t nRanges, uint32_t total, uint32_t L, uint4 *winExc, unsigned int *winExcCount) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const size_t w = windowOfRanges(ranges, rangePrefix, nRanges, i);
-    storeWindow12(out, w, in[2 * w], in[2 * w + 1], L);
+    storeWindow8(out, w, in[2 * w], in[2 * w + 1], L, winExc, winExcCount);
 }
 // tls_match4: item-relative position, bit 31 = forward
 __global__ void __launch_bounds__(256) selectFinalize4Kernel(const DevMatch *m, const uint32_t *idxList, unsigned long long n, uint32_t *out) {
@@ -1021,16 +1074,18 @@ cudaError_t launchPackWindowRanges(const uint32_t *windows, void *windows16, con
                                                              ranges, rangePrefix, nRanges, total);
     return cudaGetLastError();
 }
-cudaError_t launchPackWindows12(const uint32_t *windows, void *windows12, unsigned long long n, uint32_t L, cudaStream_t s) {
+cudaError_t launchPackWindows8(const uint32_t *windows, void *windows8, unsigned long long n, uint32_t L, void *winExc, unsigned int *winExcCount,
+                               cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    packWindows12Kernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows), static_cast<uint32_t *>(windows12), n, L);
+    packWindows8Kernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows), static_cast<uint2 *>(windows8), n, L,
+                                                                                static_cast<uint4 *>(winExc), winExcCount);
     return cudaGetLastError();
 }
-cudaError_t launchPackWindow12Ranges(const uint32_t *windows, void *windows12, const uint2 *ranges, const uint32_t *rangePrefix,
-                                     uint32_t nRanges, uint32_t total, uint32_t L, cudaStream_t s) {
+cudaError_t launchPackWindow8Ranges(const uint32_t *windows, void *windows8, const uint2 *ranges, const uint32_t *rangePrefix, uint32_t nRanges,
+                                    uint32_t total, uint32_t L, void *winExc, unsigned int *winExcCount, cudaStream_t s) {
     if (total == 0) return cudaSuccess;
-    packWindow12RangesKernel<<<(total + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows), static_cast<uint32_t *>(windows12),
-                                                               ranges, rangePrefix, nRanges, total, L);
+    packWindow8RangesKernel<<<(total + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows), static_cast<uint2 *>(windows8), ranges, rangePrefix,
+                                                              nRanges, total, L, static_cast<uint4 *>(winExc), winExcCount);
     return cudaGetLastError();
 }
 cudaError_t launchSelectFinalize4(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s) {

@@ -47,4 +47,12 @@ __device__ __forceinline__ uint32_t takeOverflowChunk(unsigned int *cursor, uint
     return old < kMaxOvRecords ? static_cast<uint32_t>(old) : kMaxOvRecords;
 }
 
+// tls_window8 (include/teloscope_b200.h): 10-bit base counts, 8-bit match counts; a window with a match count >= 255 also
+// leaves its exact counts in the exception list.
+__device__ __forceinline__ uint2 packWindow8(uint32_t window, uint32_t cA, uint32_t cC, uint32_t cG, uint32_t cT, uint32_t can, uint32_t all,
+                                             uint32_t fwd, uint4 *winExc, unsigned int *winExcCount) {
+    if (max(max(can, all), fwd) >= 255u) winExc[atomicAdd(winExcCount, 1u)] = make_uint4(window, can, all, fwd);
+    return make_uint2(cA | (cC << 10) | (cG << 20) | (cT << 30), (cT >> 2) | (min(can, 255u) << 8) | (min(all, 255u) << 16) | (min(fwd, 255u) << 24));
+}
+
 }  // namespace tls

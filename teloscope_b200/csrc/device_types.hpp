@@ -239,7 +239,9 @@ struct RowParams {
     unsigned int *ovCursor;
     uint4 *windows;                // [nWindows][2]: A, C, G, T | canonical, non-canonical, forward, reverse covered bp
     uint4 *windows16;              // TLS_OUT_COMPACT: [nWindows] tls_window16 written directly (windows is not touched then)
-    uint32_t *windows12;           // TLS_OUT_PACKED: [nWindows][3] tls_window12 written directly
+    uint2 *windows8;               // TLS_OUT_PACKED: [nWindows] tls_window8 written directly;
+    uint4 *winExc;                 // windows with a match count >= 255 (window, canonical, all, forward), appended at
+    unsigned int *winExcCount;     // this counter
     uint32_t *zeroLanes;           // [nWindows]: bit l = lane l (row positions 32 l .. 32 l + 31) holds no match start
     DevItemCounts *itemCounts;
     unsigned int *status;          // set to 1 when the shared memory layout assumption fails
@@ -295,6 +297,8 @@ struct GatherParams {
     unsigned long long matchCap;
     uint32_t *canIdx, *nctIdx;     // positions in `matches` of the canonical / terminal non-canonical records
     unsigned long long selCap;     // capacity of each index list
+    uint32_t *denseTiles;          // tiles with many records (dense units, other scan kernels): listed by the first gather kernel,
+    unsigned int *denseCount;      // copied by the second one with a block per tile (capacity nTiles)
 };
 
 struct BlockParams {

@@ -51,6 +51,8 @@ cudaError_t launchTerminal(const BlockParams &p, cudaStream_t s);
 // runStarts: runCap entries; runCount: device counter, zeroed by the caller
 cudaError_t launchIts(const BlockParams &p, const uint32_t *canIdx, unsigned long long nCan, unsigned long long *runStarts,
                       unsigned int *runCount, uint32_t runCap, cudaStream_t s);
+// tiles[index[k]] = compact[k]: the tiles of the lean / general kernels go to their places in the batch's tile table
+cudaError_t launchScatterTiles(const DevTile *compact, const uint32_t *index, uint32_t n, DevTile *tiles, cudaStream_t s);
 // interstitial blocks of window-row items (conn: nCan + 32 bytes; chainStarts: chainCap entries; chainCount: zeroed by the caller)
 cudaError_t launchItsRows(const BlockParams &p, const uint32_t *canIdx, unsigned long long nCan, uint8_t *conn,
                           unsigned long long *chainStarts, unsigned int *chainCount, uint32_t chainCap, cudaStream_t s);
@@ -68,10 +70,11 @@ cudaError_t launchSelectFinalize(const DevMatch *m, const uint32_t *idxList, uns
 // TLS_OUT_COMPACT: 8-byte match records (item-relative position) and 16-byte window records
 cudaError_t launchSelectFinalize8(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s);
 cudaError_t launchPackWindows(const uint32_t *windows, void *windows16, unsigned long long n, cudaStream_t s);
-// TLS_OUT_PACKED: 12-byte window records (counts, pattern length L) and 4-byte match records
-cudaError_t launchPackWindows12(const uint32_t *windows, void *windows12, unsigned long long n, uint32_t L, cudaStream_t s);
-cudaError_t launchPackWindow12Ranges(const uint32_t *windows, void *windows12, const uint2 *ranges, const uint32_t *rangePrefix,
-                                     uint32_t nRanges, uint32_t total, uint32_t L, cudaStream_t s);
+// TLS_OUT_PACKED: 8-byte window records (counts, pattern length L; exceptions for 255 matches or more) and 4-byte match records
+cudaError_t launchPackWindows8(const uint32_t *windows, void *windows8, unsigned long long n, uint32_t L, void *winExc, unsigned int *winExcCount,
+                               cudaStream_t s);
+cudaError_t launchPackWindow8Ranges(const uint32_t *windows, void *windows8, const uint2 *ranges, const uint32_t *rangePrefix, uint32_t nRanges,
+                                    uint32_t total, uint32_t L, void *winExc, unsigned int *winExcCount, cudaStream_t s);
 cudaError_t launchSelectFinalize4(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s);
 
 }  // namespace tls

@@ -568,11 +568,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
             const uint32_t emitted = sparse ? can : all;
             const uint32_t nE = sA & 1023u, nO = (sA >> 10) & 1023u, nG = sA >> 20;
             const uint32_t cA = COUNT ? nV - nE - nO + nG : 0u, cC = COUNT ? nE - nG : 0u, cG = COUNT ? nG : 0u, cT = COUNT ? nO - nG : 0u;   // zeros without TLS_OUT_ACGT
-            if (p.windows12) {                                  // TLS_OUT_PACKED: counts, ten bits per field (tls_window12)
-                uint32_t *wp = p.windows12 + 3 * static_cast<size_t>(db.x + lane);
-                wp[0] = cA | (cC << 10) | (cG << 20);
-                wp[1] = cT | (can << 10) | (all << 20);
-                wp[2] = fwd;
+            if (p.windows8) {                                   // TLS_OUT_PACKED: counts in 8 bytes (tls_window8)
+                p.windows8[db.x + lane] = packWindow8(db.x + lane, cA, cC, cG, cT, can, all, fwd, p.winExc, p.winExcCount);
             } else if (p.windows16) {                           // TLS_OUT_COMPACT: the 16-byte record at once (tls_window16)
                 p.windows16[db.x + lane] = make_uint4(cA | (cC << 16), cG | (cT << 16), (can * L) | (((all - can) * L) << 16),
                                                       (fwd * L) | (((all - fwd) * L) << 16));

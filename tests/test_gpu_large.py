@@ -47,7 +47,7 @@ def test_split_scan_compact_and_pageable_input_agree():
     one = _scan(tb, mk(False), None, offsets, abs_pos, device_ptr=seq.data_ptr(), env={"TLS_ROW_PARTS": "1"})
     split = _scan(tb, mk(False), None, offsets, abs_pos, device_ptr=seq.data_ptr(), env={"TLS_ROW_PARTS": "4"})
     comp = _scan(tb, mk(True), None, offsets, abs_pos, device_ptr=seq.data_ptr())
-    pack = _scan(tb, mk(False, True), None, offsets, abs_pos, device_ptr=seq.data_ptr())          # TLS_OUT_PACKED: 12-byte windows, 4-byte matches
+    pack = _scan(tb, mk(False, True), None, offsets, abs_pos, device_ptr=seq.data_ptr())          # TLS_OUT_PACKED: 8-byte windows, 4-byte matches
     launches = _scan(tb, mk(False, True), None, offsets, abs_pos, device_ptr=seq.data_ptr(), env={"TLS_ROW_PARTS": "3"})
     paged = _scan(tb, mk(False), host, offsets, abs_pos)
     assert len(one.windows) == (one.window_off[-1]) > 1_000_000

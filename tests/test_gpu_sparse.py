@@ -53,9 +53,11 @@ def build(rng, n, unit, w, T, cap_p, cap_q, arrays, iupac, variants):
     return body.tobytes()
 
 
-def check(tb, cfg, seqs):
+def check(tb, cfg, seqs, packed=False):
     orc = ol.Oracle(cfg)
-    sc = tb.Scanner(pa.scan_config(cfg))
+    scfg = pa.scan_config(cfg)
+    scfg.packed = packed                       # TLS_OUT_PACKED: 8-byte windows (+ exception list), 4-byte matches, widened by the wrapper
+    sc = tb.Scanner(scfg)
     try:
         res = sc.scan_batch(seqs, None, tb.MODE_GENOME)
         n_its = n_term = 0
@@ -136,6 +138,38 @@ def test_sparse_units_canonical_homopolymer(tb):
         seqs.append(body.tobytes())
     n_term, n_its = check(tb, cfg, seqs)
     assert n_its >= 4
+
+
+def test_packed_windows_with_exceptions(tb):
+    """TLS_OUT_PACKED keeps 8 bits per match count: windows that are one homopolymer hold ~1000 matches and must come back
+    exactly through the exception list, from the window-row kernel (long contigs) and from the pack kernel behind the other
+    scan kernels (contigs shorter than a window); ordinary windows beside them stay exact too."""
+    rng = np.random.default_rng(271828)
+    w, T = 1000, 4000
+    cfg = ol.Config(canonical="TTTTTT", window_size=w, step=w, terminal_limit=T)
+    span = 16 * w
+    seqs = []
+    for n in (6 * span + 321, 3 * span):
+        body = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)
+        for a, ln, ch in [(span + 100, 5000, b"T"), (2 * span - 300, 254 + 5, b"A"), (2 * span + 1000, 255 + 5, b"A"), (2 * span + 2000, 256 + 5, b"t"),
+                          (n - 2500, 2500, b"A")]:
+            body[a:a + ln] = ch[0]
+        seqs.append(body.tobytes())
+    seqs.append(b"T" * 700)
+    seqs.append(b"A" * 300 + bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=150)))
+    sc = tb.Scanner(tb.ScanConfig(canonical="TTTTTT", window_size=w, step=w, terminal_limit=T, out_acgt=True, out_matches=True, packed=True))
+    try:
+        offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum([len(x) for x in seqs], out=offsets[1:])
+        raw = sc.collect(sc.submit(np.frombuffer(b"".join(seqs), dtype=np.uint8), offsets, None, tb.MODE_GENOME), copy=False)   # the records as they cross the C ABI
+        counts = (raw.windows["w"][:, 1] >> 16) & 255
+        assert len(raw.window_exc) >= 8 and int((counts == 255).sum()) == len(raw.window_exc)
+        assert sorted(raw.window_exc["window"].tolist()) == np.nonzero(counts == 255)[0].tolist()
+        assert int(raw.window_exc["all"].min()) >= 255
+        raw.release()
+    finally:
+        sc.close()
+    check(tb, cfg, seqs, packed=True)
 
 
 def test_sparse_units_large_random(tb):

@@ -185,9 +185,34 @@ class BatchResult:
     release() — the zero-copy path a host pipeline would use."""
 
     def __init__(self, r: _Result, copy: bool = True, on_release=None, abs_pos=None):
-        n = r.n_items
-        self.n_items, self.mode = n, r.mode
+        self.n_items, self.mode = r.n_items, r.mode
         self._on_release = on_release
+        self.scan_kernel_ms = float(r.scan_kernel_ms)
+        self.device_ms = float(r.device_ms)
+        self.n_bases_scanned = int(r.n_bases_scanned)
+        self.n_matches = int(r.n_matches)
+        self.n_kernel_launches = int(r.n_kernel_launches)
+        self.lean_kernel_ms = float(r.lean_kernel_ms)
+        self.pattern_len = int(r.pattern_len)
+        # the array views: at once for copies; on first use for views of ctx-owned memory (a streaming caller that only
+        # wants some of them, or none before release(), pays for none)
+        self._raw = (r, copy, abs_pos)
+        if copy:
+            self._build()
+
+    def __getattr__(self, name):                  # reached only when the attribute is not there yet
+        if name.startswith("_") or self.__dict__.get("_raw") is None:
+            raise AttributeError(name)
+        self._build()
+        try:
+            return self.__dict__[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def _build(self):
+        r, copy, abs_pos = self._raw
+        self._raw = None
+        n = r.n_items
 
         def arr(ptr, count, dt):
             if not ptr or count == 0:
@@ -201,7 +226,6 @@ class BatchResult:
 
         self.window_off = off(r.window_off)
         n_win = self.window_off[-1] if r.mode == MODE_GENOME else 0
-        self.pattern_len = int(r.pattern_len)
         if r.windows8:
             w8 = arr(r.windows8, n_win, WINDOW8_DT)
             self.window_exc = arr(r.window_exc, r.n_window_exc, WINDOW_EXC_DT)
@@ -259,15 +283,10 @@ class BatchResult:
         self.n_fwd = arr(r.n_fwd, n, "<u4")
         self.n_rev = arr(r.n_rev, n, "<u4")
         self.passed = arr(r.pass_, n, "u1").astype(bool)
-        self.scan_kernel_ms = float(r.scan_kernel_ms)
-        self.device_ms = float(r.device_ms)
-        self.n_bases_scanned = int(r.n_bases_scanned)
-        self.n_matches = int(r.n_matches)
-        self.n_kernel_launches = int(r.n_kernel_launches)
-        self.lean_kernel_ms = float(r.lean_kernel_ms)
 
     def release(self):
         """Give the ticket's buffers back to the ctx (only needed after collect(copy=False))."""
+        self._raw = None                          # views not built yet would alias memory that is being handed back
         if self._on_release is not None:
             self._on_release()
             self._on_release = None

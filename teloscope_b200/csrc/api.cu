@@ -519,6 +519,9 @@ GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
     g.matches = s.dMatches.as<DevMatch>(); g.matchCap = s.matchCap;
     g.canIdx = s.dCanIdx.as<uint32_t>(); g.nctIdx = s.dNctIdx.as<uint32_t>();
     g.selCap = std::max<uint64_t>(s.nCanAll, s.nNctAll);
+    const bool fusedLists = ctx->packed && s.mode == TLS_MODE_GENOME && (ctx->cfg.outputs & TLS_OUT_MATCHES);   // the buffers are reserved by then
+    g.sel4Can = fusedLists ? s.dSelCan.as<uint32_t>() : nullptr;
+    g.sel4Nct = fusedLists ? s.dSelNon.as<uint32_t>() : nullptr;
     g.denseTiles = s.dDenseTiles.as<uint32_t>();
     g.denseCount = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 28);
     return g;
@@ -1176,8 +1179,7 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                     TLS_CUDA(cudaStreamWaitEvent(s.selStream, s.evGather, 0));
                     const size_t selRec = ctx->packed ? sizeof(tls_match4) : (ctx->compact ? sizeof(tls_match8) : sizeof(tls_match));
                     if (ctx->packed) {
-                        TLS_CUDA(launchSelectFinalize4(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dSelCan.p, s.selStream));
-                        TLS_CUDA(launchSelectFinalize4(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll, s.dSelNon.p, s.selStream));
+                        // the gather kernels wrote the tls_match4 lists themselves: only the copies are left
                     } else if (ctx->compact) {
                         TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dCanIdx.as<uint32_t>(), s.nCanAll, s.dSelCan.p, s.selStream));
                         TLS_CUDA(launchSelectFinalize8(s.dMatches.as<DevMatch>(), s.dNctIdx.as<uint32_t>(), s.nNctAll, s.dSelNon.p, s.selStream));
@@ -1189,7 +1191,7 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                                                       s.dItemBegin.as<unsigned long long>(), s.dAbsPos.as<unsigned long long>(), n,
                                                       s.dSelNon.p, s.selStream));
                     }
-                    s.launches += (s.nCanAll ? 1 : 0) + (s.nNctAll ? 1 : 0);
+                    if (!ctx->packed) s.launches += (s.nCanAll ? 1 : 0) + (s.nNctAll ? 1 : 0);
                     if (s.nCanAll) {
                         TLS_CUDA(s.hSelCan.reserve(s.nCanAll * selRec));
                         TLS_CUDA(cudaMemcpyAsync(s.hSelCan.p, s.dSelCan.p, s.nCanAll * selRec, cudaMemcpyDeviceToHost, s.selStream));

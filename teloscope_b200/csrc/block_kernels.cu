@@ -214,8 +214,14 @@ __device__ __forceinline__ void gatherTile(const GatherParams &g, uint32_t tile,
     auto put = [&](const uint2 rec) {
         if (o < g.matchCap) out[o] = make_uint2(rec.x, rec.y & 0x00FFFFFFu);
         const uint32_t flags = (rec.y >> 16) & 0xFFu;
-        if (flags & kMatchCan) { if (oc < g.selCap) g.canIdx[oc] = static_cast<uint32_t>(o); ++oc; }
-        else if (flags & kMatchTerm) { if (on < g.selCap) g.nctIdx[on] = static_cast<uint32_t>(o); ++on; }
+        const uint32_t m4 = rec.x | ((flags & kMatchFwd) ? 0x80000000u : 0u);             // tls_match4
+        if (flags & kMatchCan) {
+            if (oc < g.selCap) { g.canIdx[oc] = static_cast<uint32_t>(o); if (g.sel4Can) g.sel4Can[oc] = m4; }
+            ++oc;
+        } else if (flags & kMatchTerm) {
+            if (on < g.selCap) { if (g.sel4Nct) g.sel4Nct[on] = m4; else g.nctIdx[on] = static_cast<uint32_t>(o); }
+            ++on;
+        }
         ++o;
     };
     // the first records of the row (a sparse row holds one or two) are all requested before any is stored
@@ -289,8 +295,15 @@ __global__ void __launch_bounds__(kGatherThreads) gatherDenseKernel(const Gather
                 const bool isC = have && (flags & kMatchCan);
                 const bool isN = have && (flags & (kMatchCan | kMatchTerm)) == kMatchTerm;
                 const uint32_t bc = __ballot_sync(0xFFFFFFFFu, isC), bn = __ballot_sync(0xFFFFFFFFu, isN);
-                if (isC && oc + __popc(bc & laneLt) < g.selCap) g.canIdx[oc + __popc(bc & laneLt)] = static_cast<uint32_t>(o + k);
-                if (isN && on + __popc(bn & laneLt) < g.selCap) g.nctIdx[on + __popc(bn & laneLt)] = static_cast<uint32_t>(o + k);
+                const uint32_t m4 = rec.x | ((flags & kMatchFwd) ? 0x80000000u : 0u);         // tls_match4
+                if (isC && oc + __popc(bc & laneLt) < g.selCap) {
+                    g.canIdx[oc + __popc(bc & laneLt)] = static_cast<uint32_t>(o + k);
+                    if (g.sel4Can) g.sel4Can[oc + __popc(bc & laneLt)] = m4;
+                }
+                if (isN && on + __popc(bn & laneLt) < g.selCap) {
+                    if (g.sel4Nct) g.sel4Nct[on + __popc(bn & laneLt)] = m4;
+                    else g.nctIdx[on + __popc(bn & laneLt)] = static_cast<uint32_t>(o + k);
+                }
                 oc += __popc(bc);
                 on += __popc(bn);
             }
@@ -951,14 +964,6 @@ __global__ void __launch_bounds__(256) packWindow8RangesKernel(const uint4 *in, 
     const size_t w = windowOfRanges(ranges, rangePrefix, nRanges, i);
     storeWindow8(out, w, in[2 * w], in[2 * w + 1], L, winExc, winExcCount);
 }
-// tls_match4: item-relative position, bit 31 = forward
-__global__ void __launch_bounds__(256) selectFinalize4Kernel(const DevMatch *m, const uint32_t *idxList, unsigned long long n, uint32_t *out) {
-    const unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const DevMatch x = m[idxList[j]];
-    out[j] = x.pos | ((x.flags & kMatchFwd) ? 0x80000000u : 0u);
-}
-
 __global__ void __launch_bounds__(256) selectFinalizeKernel(const DevMatch *m, const uint32_t *idxList, unsigned long long n,
                                                             const unsigned long long *itemBegin, const unsigned long long *absPos,
                                                             uint32_t nItems, OutMatch *out) {
@@ -1086,11 +1091,6 @@ cudaError_t launchPackWindow8Ranges(const uint32_t *windows, void *windows8, con
     if (total == 0) return cudaSuccess;
     packWindow8RangesKernel<<<(total + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(windows), static_cast<uint2 *>(windows8), ranges, rangePrefix,
                                                               nRanges, total, L, static_cast<uint4 *>(winExc), winExcCount);
-    return cudaGetLastError();
-}
-cudaError_t launchSelectFinalize4(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s) {
-    if (n == 0) return cudaSuccess;
-    selectFinalize4Kernel<<<static_cast<unsigned int>((n + 255) / 256), 256, 0, s>>>(m, idxList, n, static_cast<uint32_t *>(out));
     return cudaGetLastError();
 }
 cudaError_t launchItemOffsets(const DevItemCounts *counts, const DevItemInfo *items, uint32_t n, unsigned long long *itemBegin, cudaStream_t s) {

@@ -75,6 +75,5 @@ cudaError_t launchPackWindows8(const uint32_t *windows, void *windows8, unsigned
                                cudaStream_t s);
 cudaError_t launchPackWindow8Ranges(const uint32_t *windows, void *windows8, const uint2 *ranges, const uint32_t *rangePrefix, uint32_t nRanges,
                                     uint32_t total, uint32_t L, void *winExc, unsigned int *winExcCount, cudaStream_t s);
-cudaError_t launchSelectFinalize4(const DevMatch *m, const uint32_t *idxList, unsigned long long n, void *out, cudaStream_t s);
 
 }  // namespace tls

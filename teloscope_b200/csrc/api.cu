@@ -112,6 +112,7 @@ struct Slot {
     cudaEvent_t evSetup = nullptr;
     unsigned long long *hScanDev = nullptr;   // device view of hScan (mapped): scan totals without a copy
     cudaEvent_t evScan0 = nullptr, evScan1 = nullptr, evFast1 = nullptr, evAll0 = nullptr, evAll1 = nullptr;
+    cudaEvent_t evDbg[6] = {};               // TLS_TRACE=1: timeline of the collect phase (gather, terminal, ITS, list copies, window copies)
     float fastMs = 0;
     // inputs
     uint32_t nItems = 0, mode = 0;
@@ -477,6 +478,7 @@ void tls_destroy(tls_ctx *ctx) {
             b->release();
         if (s.evScan0) cudaEventDestroy(s.evScan0);
         if (s.evScan1) cudaEventDestroy(s.evScan1);
+        for (cudaEvent_t &e : s.evDbg) if (e) { cudaEventDestroy(e); e = nullptr; }
         if (s.evFast1) cudaEventDestroy(s.evFast1);
         if (s.evAll0) cudaEventDestroy(s.evAll0);
         if (s.evAll1) cudaEventDestroy(s.evAll1);
@@ -754,9 +756,10 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
         }
         TLS_CUDA(cudaEventRecord(s.evCopyDone, s.copyStream));
         TLS_CUDA(s.dSelScratch.reserve(tileScanScratchBytes(nTiles)));
+        TLS_CUDA(s.dDenseTiles.reserve(static_cast<size_t>(nTiles) * 4));
         TLS_CUDA(launchTileScan(s.dTileTot.as<uint32_t>(), nTiles, s.dTileBase.as<unsigned long long>(), s.dSelScratch.as<unsigned long long>(),
                                 reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>()), (nFast || nRow) ? redo : nullptr,
-                                s.hScanDev, s.stream));
+                                s.hScanDev, s.dDenseTiles.as<uint32_t>(), reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 28), s.stream));
         s.launches += 2;
     } else {
         // a batch whose items are all empty: no kernel runs, every per-item counter reads as zero
@@ -1163,11 +1166,19 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
         for (bool first = true;; first = false) {
             TLS_CUDA(s.dBlocks.reserve(static_cast<size_t>(s.blockCap) * sizeof(DevBlock)));
             uint8_t *cnt = s.dCounters.as<uint8_t>();
-            TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 16, s.stream));           // [16] block count, [20] ITS run count, [24] ITS chain count, [28] dense tiles
+            TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 12, s.stream));           // [16] block count, [20] ITS run count, [24] ITS chain count
             if (first && s.nTilesAll) {
-                TLS_CUDA(s.dDenseTiles.reserve(static_cast<size_t>(s.nTilesAll) * 4));
-                TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream));
+                // the two gather kernels write disjoint places: side by side (the dense tiles were listed by the tile scan)
+                TLS_CUDA(cudaEventRecord(s.evTerminal, s.stream));
+                TLS_CUDA(cudaStreamWaitEvent(s.itsStream, s.evTerminal, 0));
+                TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream, s.itsStream));
+                TLS_CUDA(cudaEventRecord(s.evItsLists, s.itsStream));
+                TLS_CUDA(cudaStreamWaitEvent(s.stream, s.evItsLists, 0));
                 s.launches += 2;
+                if (tr.on) {
+                    for (cudaEvent_t &e : s.evDbg) if (!e) TLS_CUDA(cudaEventCreate(&e));
+                    TLS_CUDA(cudaEventRecord(s.evDbg[0], s.stream));
+                }
             }
             if (reads && n) TLS_CUDA(cudaMemsetAsync(s.dPass.p, 0, n, s.stream));
             if (n) {
@@ -1200,6 +1211,7 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                         TLS_CUDA(s.hSelNon.reserve(s.nNctAll * selRec));
                         TLS_CUDA(cudaMemcpyAsync(s.hSelNon.p, s.dSelNon.p, s.nNctAll * selRec, cudaMemcpyDeviceToHost, s.selStream));
                     }
+                    if (tr.on && s.evDbg[2]) TLS_CUDA(cudaEventRecord(s.evDbg[2], s.selStream));
                 }
                 if (first && genome && ctx->dcfg.overlapWindows && s.nWindows) {
                     // step < window: the window table comes from the ordered list (block_kernels.cu), then goes home
@@ -1244,6 +1256,7 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
                 bp.cfg.mode = s.mode;
                 TLS_CUDA(launchTerminal(bp, s.stream));
                 s.launches++;
+                if (tr.on && s.evDbg[1]) TLS_CUDA(cudaEventRecord(s.evDbg[1], s.stream));
                 if (genome && s.nMatches >= 2 && s.nCanAll >= 4) {
                     const bool lists = s.nRowItems < n, rows = s.nRowItems != 0;
                     if (rows) TLS_CUDA(s.dConn.reserve(s.nCanAll + 64));     // itsWalkKernel reads 32 links at a time (before any launch: may synchronise)
@@ -1307,6 +1320,16 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
         TLS_CUDA(cudaStreamSynchronize(s.copyStream));
         TLS_CUDA(cudaEventElapsedTime(&s.allMs, s.evAll0, s.evAll1));
         tr.mark("d2h");
+        if (tr.on && s.evDbg[0] && !reads) {
+            float tScan = 0, tGather = 0, tTerm = 0, tLists = 0;
+            cudaEventElapsedTime(&tScan, s.evAll0, s.evScan1);
+            cudaEventElapsedTime(&tGather, s.evAll0, s.evDbg[0]);
+            cudaEventElapsedTime(&tTerm, s.evAll0, s.evDbg[1]);
+            if (wantSel) cudaEventElapsedTime(&tLists, s.evAll0, s.evDbg[2]);
+            cudaGetLastError();
+            std::fprintf(stderr, "\n[tls] timeline from the first enqueue (ms): scan done %.3f, gather done %.3f, terminal done %.3f, blocks done %.3f, -m lists home %.3f\n",
+                         tScan, tGather, tTerm, s.allMs, tLists);
+        }
 
         // ---- assemble per-item views ----------------------------------------------------------------------
         s.terminalOff.assign(n + 1, 0); s.itsOff.assign(n + 1, 0); s.canOff.assign(n + 1, 0); s.nonOff.assign(n + 1, 0);

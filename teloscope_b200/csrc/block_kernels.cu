@@ -81,16 +81,24 @@ __global__ void __launch_bounds__(1024) itemOffsetsKernel(const DevItemCounts *c
 // pinned host memory: [0] ovCursor, [1..3] totals, [4] redo count | status << 32), so that the host
 // needs no copy-engine transfer (which would queue behind the window counters going home).
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t kDenseTile = 128;                                 // a tile with more records than this goes to the block-per-tile gather kernel
 constexpr uint32_t kScanChunk = 4096;                               // tiles per block: 1024 threads x 4
 
-__global__ void __launch_bounds__(1024) tileBlockSumsKernel(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *blockSums) {
+__global__ void __launch_bounds__(1024) tileBlockSumsKernel(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *blockSums,
+                                                            uint32_t *denseTiles, unsigned int *denseCount) {
     __shared__ unsigned long long warpSums[32];
     const uint32_t k = blockIdx.y, b = blockIdx.x, nBlk = gridDim.x;
     const uint32_t *in = tileTot + static_cast<size_t>(k) * nTiles;
     const uint32_t i0 = b * kScanChunk + threadIdx.x * 4;
     unsigned long long v = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) if (i0 + j < nTiles) v += in[i0 + j];
+    for (int j = 0; j < 4; ++j)
+        if (i0 + j < nTiles) {
+            const uint32_t t = in[i0 + j];
+            v += t;
+            // the tiles the block-per-tile gather kernel takes (in no particular order: every record's place is computed)
+            if (k == 0 && denseTiles && t > kDenseTile) denseTiles[atomicAdd(denseCount, 1u)] = i0 + j;
+        }
 #pragma unroll
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
     if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = v;
@@ -190,7 +198,6 @@ __device__ __forceinline__ TilePrefix tilePrefix(const uint4 &meta, uint32_t lan
     return TilePrefix{inclAll - meta.x, inclCan - meta.z, inclNct - meta.w};
 }
 
-constexpr uint32_t kDenseTile = 128;                                // more records than this: the block-per-tile kernel
 
 // A tile of sparse units: lane r copies row r's records.  Tiles with many records are only listed here.
 __device__ __forceinline__ void gatherTile(const GatherParams &g, uint32_t tile, uint32_t lane, const TileHeader &hd) {
@@ -199,10 +206,7 @@ __device__ __forceinline__ void gatherTile(const GatherParams &g, uint32_t tile,
     const uint4 meta = hd.meta;
     const uint32_t total = static_cast<uint32_t>(hd.baseEnd - base);
     if (total == 0) return;
-    if (total > kDenseTile) {
-        if (lane == 0) g.denseTiles[atomicAdd(g.denseCount, 1u)] = tile;
-        return;
-    }
+    if (total > kDenseTile) return;                                 // listed by tileBlockSumsKernel for gatherDenseKernel
     const TilePrefix px = tilePrefix(meta, lane);
     const uint32_t exAll = px.exAll, exCan = px.exCan, exNct = px.exNct;
     const uint2 *slots = reinterpret_cast<const uint2 *>(g.slots);
@@ -340,18 +344,19 @@ cudaError_t launchScatterTiles(const DevTile *compact, const uint32_t *index, ui
 }
 
 cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, unsigned long long *blockSums,
-                           const unsigned int *ovCursor, const unsigned int *redo, unsigned long long *hostOut, cudaStream_t s) {
+                           const unsigned int *ovCursor, const unsigned int *redo, unsigned long long *hostOut, uint32_t *denseTiles,
+                           unsigned int *denseCount, cudaStream_t s) {
     const uint32_t nBlk = std::max<uint32_t>(1u, (nTiles + kScanChunk - 1) / kScanChunk);
-    tileBlockSumsKernel<<<dim3(nBlk, 3), 1024, 0, s>>>(tileTot, nTiles, blockSums);
+    tileBlockSumsKernel<<<dim3(nBlk, 3), 1024, 0, s>>>(tileTot, nTiles, blockSums, denseTiles, denseCount);
     tileScanKernel<<<dim3(nBlk, 3), 1024, 0, s>>>(tileTot, nTiles, tileBase, blockSums, ovCursor, redo, hostOut);
     return cudaGetLastError();
 }
 size_t tileScanScratchBytes(uint32_t nTiles) { return static_cast<size_t>(std::max<uint32_t>(1u, (nTiles + kScanChunk - 1) / kScanChunk)) * 3 * 8; }
-cudaError_t launchGather(const GatherParams &g, cudaStream_t s) {
+cudaError_t launchGather(const GatherParams &g, cudaStream_t s, cudaStream_t denseStream) {
     if (g.nTiles == 0) return cudaSuccess;
     const uint32_t blocks = std::min<uint32_t>((g.nTiles + kGatherThreads / 32 - 1) / (kGatherThreads / 32), 148u * kGatherBlocksPerSm);
     gatherKernel<<<blocks, kGatherThreads, 0, s>>>(g);
-    gatherDenseKernel<<<std::min<uint32_t>(g.nTiles, 148u * 4u), kGatherThreads, 0, s>>>(g);
+    gatherDenseKernel<<<std::min<uint32_t>(g.nTiles, 148u * 4u), kGatherThreads, 0, denseStream>>>(g);
     return cudaGetLastError();
 }
 

@@ -36,8 +36,9 @@ cudaError_t launchReadScan(const ReadParams &p, int grid, cudaStream_t stream);
 // blockSums: scratch of tileScanScratchBytes(nTiles) bytes
 size_t tileScanScratchBytes(uint32_t nTiles);
 cudaError_t launchTileScan(const uint32_t *tileTot, uint32_t nTiles, unsigned long long *tileBase, unsigned long long *blockSums,
-                           const unsigned int *ovCursor, const unsigned int *redo, unsigned long long *hostOut, cudaStream_t s);
-cudaError_t launchGather(const GatherParams &g, cudaStream_t s);
+                           const unsigned int *ovCursor, const unsigned int *redo, unsigned long long *hostOut, uint32_t *denseTiles,
+                           unsigned int *denseCount, cudaStream_t s);
+cudaError_t launchGather(const GatherParams &g, cudaStream_t s, cudaStream_t denseStream);   // sparse tiles on s, dense tiles (listed by the tile scan) on denseStream
 
 cudaError_t launchTrimCr(const uint8_t *seq, DevRegion *regions, uint32_t nRegions, uint32_t *itemLen, cudaStream_t s);
 cudaError_t launchTrimCrItems(const uint8_t *seq, const DevItemInfo *items, uint32_t n, uint32_t *itemLen, cudaStream_t s);

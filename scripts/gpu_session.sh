@@ -8,10 +8,10 @@ if [ "$2" = tests ]; then
   timeout 300 python __graft_entry__.py smoke > $out/smoke.log 2>&1; echo "smoke exit $?" >> $out/smoke.log
 fi
 timeout 1500 python bench.py --steps 10 --warmup 3 > $out/bench.json 2> $out/bench.err; echo "bench exit $?" >> $out/bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Kernel' -s 22 -c 24 --csv \
-  --log-file $out/launches.csv env TLS_COMPACT=1 python scripts/trace_bench.py 1.0 > $out/trace.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'Kernel' -s 36 -c 18 --csv \
+  --log-file $out/launches.csv env TLS_PACKED=1 python scripts/trace_bench.py 1.0 > $out/trace.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rowScanKernel -s 1 -c 1 \
-  -o $out/prof_rows env TLS_COMPACT=1 TLS_ROW_PARTS=1 python scripts/trace_bench.py 0.25 > $out/ncu_full.log 2>&1
+  -o $out/prof_rows env TLS_PACKED=1 TLS_ROW_PARTS=1 python scripts/trace_bench.py 0.25 > $out/ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:readScanKernel -s 1 -c 1 \
   -o $out/prof_reads python scripts/trace_reads.py > $out/ncu_reads.log 2>&1
 ls -la $out

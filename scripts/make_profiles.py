@@ -18,8 +18,8 @@ hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 hdr = rows[hi]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 (out / f"{tag}_launches.csv").write_text("\n".join(",".join(r) for r in rows[hi:]) + "\n")
 with open(out / f"{tag}_launches.md", "w") as fh:
-    fh.write(f"# {tag}: ncu launch list of one step on the 3.03 Gbp batch (compact records)\n\n"
-             "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:Kernel -s 22 -c 24 python scripts/trace_bench.py 1.0` "
+    fh.write(f"# {tag}: ncu launch list of one step on the 3.03 Gbp batch (packed records)\n\n"
+             "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:Kernel -s 36 -c 18 env TLS_PACKED=1 python scripts/trace_bench.py 1.0` "
              "(per-launch times are cold-cache and serialised: shares, not absolutes)\n\n| kernel | µs |\n|---|---|\n")
     tot = 0.0
     for r in rows[hi + 1:]:
@@ -29,7 +29,7 @@ with open(out / f"{tag}_launches.md", "w") as fh:
             fh.write(f"| `{r[ki][:70]}` | {us:.1f} |\n")
     fh.write(f"| total | {tot:.1f} |\n")
 for rep, kern, name, what in ((src / "prof_rows.ncu-rep", "rowScanKernel", f"{tag}_rows_summary.md",
-                               "window-row scan kernel, ONE launch, 0.25-scale assembly (714 Mbp, 714 K window rows), compact records"),
+                               "window-row scan kernel, ONE launch, 0.25-scale assembly (714 Mbp, 714 K window rows), packed records"),
                               (src / "prof_reads.ncu-rep", "readScanKernel", f"{tag}_reads_summary.md",
                                "read scorer, 2.0 Gbp of synthetic HiFi reads (133 K reads)")):
     if not rep.exists():
@@ -38,4 +38,21 @@ for rep, kern, name, what in ((src / "prof_rows.ncu-rep", "rowScanKernel", f"{ta
     l = run("python", "scripts/ncu_lines.py", str(rep), kern, "--top", "40")
     (out / name).write_text(f"# {tag} — {what}: ncu --set full --clock-control none --import-source on\n\n{m}\nSource-line attribution "
                             f"(`scripts/ncu_lines.py`, share of executed warp instructions):\n\n```\n{l}```\n")
+# DRAM bytes of the window-row kernel's launch -> what bench.py scales into roofline.traffic
+rep, log = src / "prof_rows.ncu-rep", src / "ncu_full.log"
+if rep.exists():
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = {}
+    for ln in run("python", "scripts/ncu_metrics.py", str(rep)).splitlines():
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            if ln.startswith(f"- {key} = "):
+                v, u = ln.split(" = ")[1].split()[:2]
+                vals[key] = float(v.replace(",", "")) * unit[u]
+    bases = [int(ln.split()[1]) for ln in log.read_text().splitlines() if ln.startswith("bases ")] if log.exists() else []
+    if len(vals) == 2 and bases:
+        rd, wr = vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"]
+        (out / "rows_kernel_traffic.json").write_text(json.dumps({
+            "dram_bytes_per_base": (rd + wr) / bases[0], "dram_bytes_read": rd, "dram_bytes_write": wr, "bases": bases[0],
+            "source": f"ncu --set full --clock-control none, TLS_PACKED=1 TLS_ROW_PARTS=1 scripts/trace_bench.py 0.25 (profiles/{tag}_rows_summary.md); "
+                      "dram__bytes_read.sum + dram__bytes_write.sum of one launch"}, indent=1) + "\n")
 print("written to", out)

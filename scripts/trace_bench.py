@@ -5,6 +5,7 @@ import bench, teloscope_b200 as tb
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 chroms = bench.plan_assembly(42, scale)
 seq, offsets, abs_pos = bench.build_assembly(chroms, "cuda:0", 42)
+print(f"bases {int(offsets[-1])} contigs {len(offsets) - 1}", flush=True)
 sc = tb.Scanner(tb.ScanConfig(canonical="TTAGGG", patterns=bench.PATTERNS, out_acgt=True, out_matches=True, compact=bool(os.environ.get("TLS_COMPACT")), packed=bool(os.environ.get("TLS_PACKED"))))
 for i in range(4):
     t0 = time.perf_counter()

@@ -104,6 +104,9 @@ struct Slot {
     cudaStream_t itsStream = nullptr;        // interstitial blocks of the items with complete lists, beside those of the window-row items
     cudaEvent_t evTerminal = nullptr, evItsLists = nullptr;
     cudaEvent_t evGather = nullptr;
+    cudaEvent_t evTotals = nullptr;          // the tile scan has published the batch's totals (what tls_collect waits for first)
+    bool specGather = false;                 // the gather was enqueued behind the scan with the buffers of the previous batch ...
+    uint64_t specMatchCap = 0, specSelCap = 0, specNctCap = 0;   // ... of these capacities: kept if the totals fit, redone after growing them if not
     cudaEvent_t evScanDone = nullptr, evCopyDone = nullptr;
     static constexpr int kMaxParts = 8;      // launches of the window-row kernel on a large batch (result copy overlaps the scan)
     cudaEvent_t evPart[kMaxParts] = {};
@@ -182,6 +185,7 @@ struct tls_ctx {
     std::string overlapRefusal;              // non-empty: genome-mode batches are refused (see buildDevConfig)
     bool forceGeneral = false;               // TLS_FORCE_GENERAL=1 or a lean-kernel layout failure
     bool noRowKernel = false;                // TLS_NO_ROW_KERNEL=1: 1536-base-row lean kernel instead of the window-row kernel
+    bool noSpecGather = false;               // TLS_NO_SPEC_GATHER=1: the gather is always enqueued by tls_collect (A/B tests)
     bool noReadKernel = false;               // TLS_NO_READ_KERNEL=1: reads through the general scan + block kernels (A/B tests)
     // cuStreamWaitValue32 through the runtime's driver entry point lookup (no link against libcuda): the window copies of a
     // finished range of units are released by a stream wait on a progress word the scan kernel counts up, so ONE launch
@@ -427,7 +431,8 @@ static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
         TLS_CUDA(cudaStreamCreateWithFlags(&s.itsStream, cudaStreamNonBlocking));
         TLS_CUDA(cudaEventCreateWithFlags(&s.evTerminal, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreateWithFlags(&s.evItsLists, cudaEventDisableTiming));
-        TLS_CUDA(cudaEventCreateWithFlags(&s.evGather, cudaEventDisableTiming));
+        TLS_CUDA(cudaEventCreate(&s.evGather));
+        TLS_CUDA(cudaEventCreateWithFlags(&s.evTotals, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreateWithFlags(&s.evScanDone, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreateWithFlags(&s.evCopyDone, cudaEventDisableTiming));
         TLS_CUDA(cudaEventCreate(&s.evScan0)); TLS_CUDA(cudaEventCreate(&s.evScan1)); TLS_CUDA(cudaEventCreate(&s.evFast1));
@@ -446,6 +451,7 @@ static int tls_create_impl(const tls_config *cfg, int device, tls_ctx **out) {
     ctx->forceGeneral = std::getenv("TLS_FORCE_GENERAL") != nullptr;
     ctx->noRowKernel = ctx->noRowKernel || std::getenv("TLS_NO_ROW_KERNEL") != nullptr;
     ctx->noReadKernel = ctx->noReadKernel || std::getenv("TLS_NO_READ_KERNEL") != nullptr;
+    ctx->noSpecGather = std::getenv("TLS_NO_SPEC_GATHER") != nullptr;
     if (!std::getenv("TLS_ROW_PARTS")) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
@@ -488,6 +494,7 @@ void tls_destroy(tls_ctx *ctx) {
         if (s.evTerminal) cudaEventDestroy(s.evTerminal);
         if (s.evItsLists) cudaEventDestroy(s.evItsLists);
         if (s.evGather) cudaEventDestroy(s.evGather);
+        if (s.evTotals) cudaEventDestroy(s.evTotals);
         if (s.evScanDone) cudaEventDestroy(s.evScanDone);
         for (cudaEvent_t &e : s.evPart) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (cudaStream_t &st : s.partStream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
@@ -507,7 +514,7 @@ void tls_destroy(tls_ctx *ctx) {
 
 namespace {
 
-GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
+GatherParams gatherParams(const tls_ctx *ctx, const Slot &s, uint64_t matchCap, uint64_t selCap, uint64_t selCapNct) {
     GatherParams g{};
     g.tiles = s.dTiles.as<DevTile>(); g.regions = s.dRegions.as<DevRegion>();
     g.nRegions = static_cast<uint32_t>(s.regions.size());
@@ -518,15 +525,35 @@ GatherParams gatherParams(const tls_ctx *ctx, const Slot &s) {
     g.ovArena = s.dOvArena.as<DevMatch>(); g.ovCap = s.ovCap;
     g.nTiles = s.nTilesAll;
     g.tileBase = s.dTileBase.as<unsigned long long>();
-    g.matches = s.dMatches.as<DevMatch>(); g.matchCap = s.matchCap;
+    g.matches = s.dMatches.as<DevMatch>(); g.matchCap = matchCap;
     g.canIdx = s.dCanIdx.as<uint32_t>(); g.nctIdx = s.dNctIdx.as<uint32_t>();
-    g.selCap = std::max<uint64_t>(s.nCanAll, s.nNctAll);
+    g.selCap = selCap; g.selCapNct = selCapNct;
     const bool fusedLists = ctx->packed && s.mode == TLS_MODE_GENOME && (ctx->cfg.outputs & TLS_OUT_MATCHES);   // the buffers are reserved by then
     g.sel4Can = fusedLists ? s.dSelCan.as<uint32_t>() : nullptr;
     g.sel4Nct = fusedLists ? s.dSelNon.as<uint32_t>() : nullptr;
     g.denseTiles = s.dDenseTiles.as<uint32_t>();
     g.denseCount = reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 28);
     return g;
+}
+
+// Slots -> ordered list (+ packed -m lists) and the per-item offsets.  The two gather kernels write disjoint places: side by
+// side (the dense tiles were listed by the tile scan).
+int enqueueGather(tls_ctx *ctx, Slot &s, uint64_t matchCap, uint64_t selCap, uint64_t selCapNct) {
+    if (s.nTilesAll) {
+        TLS_CUDA(cudaEventRecord(s.evTerminal, s.stream));
+        TLS_CUDA(cudaStreamWaitEvent(s.itsStream, s.evTerminal, 0));
+        TLS_CUDA(launchGather(gatherParams(ctx, s, matchCap, selCap, selCapNct), s.stream, s.itsStream));
+        TLS_CUDA(cudaEventRecord(s.evItsLists, s.itsStream));
+        TLS_CUDA(cudaStreamWaitEvent(s.stream, s.evItsLists, 0));
+        s.launches += 2;
+    }
+    if (s.nItems) {
+        TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), s.nRowItems ? s.dItemInfo.as<DevItemInfo>() : nullptr, s.nItems,
+                                   s.dItemBegin.as<unsigned long long>(), s.stream));
+        s.launches++;
+    }
+    TLS_CUDA(cudaEventRecord(s.evGather, s.stream));
+    return TLS_OK;
 }
 
 // Enqueue the scan for the slot: memsets, lean kernel over the single-contig tiles, general kernel
@@ -761,7 +788,23 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
                                 reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>()), (nFast || nRow) ? redo : nullptr,
                                 s.hScanDev, s.dDenseTiles.as<uint32_t>(), reinterpret_cast<unsigned int *>(s.dCounters.as<uint8_t>() + 28), s.stream));
         s.launches += 2;
+        TLS_CUDA(cudaEventRecord(s.evTotals, s.stream));
+        // The gather needs the batch's totals only to size its buffers.  With the buffers a previous batch left it is enqueued
+        // right here, behind the scan (every write is bounds-checked): tls_collect keeps its result when the totals fit and
+        // redoes it after growing the buffers when they do not.  No host round trip between the scan and the gather.
+        s.specGather = false;
+        {
+            const bool fusedLists = ctx->packed && s.mode == TLS_MODE_GENOME && (ctx->cfg.outputs & TLS_OUT_MATCHES);
+            const uint64_t mCap = s.dMatches.cap / sizeof(DevMatch);
+            uint64_t canCap = s.dCanIdx.cap / 4, nctCap = s.dNctIdx.cap / 4;
+            if (fusedLists) { canCap = std::min<uint64_t>(canCap, s.dSelCan.cap / 4); nctCap = std::min<uint64_t>(nctCap, s.dSelNon.cap / 4); }
+            if (mCap && canCap && nctCap && !ctx->noSpecGather) {
+                if (int rc2 = enqueueGather(ctx, s, mCap, canCap, nctCap)) return rc2;
+                s.specGather = true; s.specMatchCap = mCap; s.specSelCap = canCap; s.specNctCap = nctCap;
+            }
+        }
     } else {
+        s.specGather = false;
         // a batch whose items are all empty: no kernel runs, every per-item counter reads as zero
         TLS_CUDA(cudaMemsetAsync(s.dTileBase.p, 0, 24, s.stream));
         std::memset(s.hScan.p, 0, 64);
@@ -1125,7 +1168,8 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
     if (!s.collected) {
         // ---- wait for the scan; grow the overflow arena and rerun if it ran out --------------------
         for (;;) {
-            TLS_CUDA(cudaStreamSynchronize(s.stream));
+            if (s.nTilesAll) TLS_CUDA(cudaEventSynchronize(s.evTotals));       // not the stream: a gather enqueued behind the scan goes on meanwhile
+            else TLS_CUDA(cudaStreamSynchronize(s.stream));
             const volatile unsigned long long *hs = s.hScan.as<unsigned long long>();   // ovCursor, totals[3], redo | status << 32
             if ((hs[4] >> 32) != 0)
                 return fail(TLS_ERR_STATE, "lean scan kernel could not lay out its shared memory (window base %% 64 KiB); "
@@ -1167,26 +1211,17 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
             TLS_CUDA(s.dBlocks.reserve(static_cast<size_t>(s.blockCap) * sizeof(DevBlock)));
             uint8_t *cnt = s.dCounters.as<uint8_t>();
             TLS_CUDA(cudaMemsetAsync(cnt + 16, 0, 12, s.stream));           // [16] block count, [20] ITS run count, [24] ITS chain count
-            if (first && s.nTilesAll) {
-                // the two gather kernels write disjoint places: side by side (the dense tiles were listed by the tile scan)
-                TLS_CUDA(cudaEventRecord(s.evTerminal, s.stream));
-                TLS_CUDA(cudaStreamWaitEvent(s.itsStream, s.evTerminal, 0));
-                TLS_CUDA(launchGather(gatherParams(ctx, s), s.stream, s.itsStream));
-                TLS_CUDA(cudaEventRecord(s.evItsLists, s.itsStream));
-                TLS_CUDA(cudaStreamWaitEvent(s.stream, s.evItsLists, 0));
-                s.launches += 2;
-                if (tr.on) {
-                    for (cudaEvent_t &e : s.evDbg) if (!e) TLS_CUDA(cudaEventCreate(&e));
-                    TLS_CUDA(cudaEventRecord(s.evDbg[0], s.stream));
-                }
+            if (first) {
+                if (tr.on) for (cudaEvent_t &e : s.evDbg) if (!e) TLS_CUDA(cudaEventCreate(&e));
+                const bool kept = s.specGather && s.nMatches <= s.specMatchCap && s.nCanAll <= s.specSelCap && s.nNctAll <= s.specNctCap;
+                if (tr.on) fprintf(stderr, " gather=%s", kept ? "behind the scan" : (s.specGather ? "redone" : "here"));
+                if (!kept && (rc = enqueueGather(ctx, s, s.matchCap, s.nCanAll, s.nNctAll))) return rc;
             }
             if (reads && n) TLS_CUDA(cudaMemsetAsync(s.dPass.p, 0, n, s.stream));
             if (n) {
-                if (first) { TLS_CUDA(launchItemOffsets(s.dItemCounts.as<DevItemCounts>(), s.nRowItems ? s.dItemInfo.as<DevItemInfo>() : nullptr, n, s.dItemBegin.as<unsigned long long>(), s.stream)); s.launches++; }
                 if (first && wantSel) {
                     // the -m lists only need the ordered list: final records and their copy home run on their own stream
                     // beside the block kernels
-                    TLS_CUDA(cudaEventRecord(s.evGather, s.stream));
                     TLS_CUDA(cudaStreamWaitEvent(s.selStream, s.evGather, 0));
                     const size_t selRec = ctx->packed ? sizeof(tls_match4) : (ctx->compact ? sizeof(tls_match8) : sizeof(tls_match));
                     if (ctx->packed) {
@@ -1320,10 +1355,10 @@ static int tls_collect_impl(tls_ctx *ctx, int ticket, tls_result *res) {
         TLS_CUDA(cudaStreamSynchronize(s.copyStream));
         TLS_CUDA(cudaEventElapsedTime(&s.allMs, s.evAll0, s.evAll1));
         tr.mark("d2h");
-        if (tr.on && s.evDbg[0] && !reads) {
+        if (tr.on && s.evDbg[1] && !reads) {
             float tScan = 0, tGather = 0, tTerm = 0, tLists = 0;
             cudaEventElapsedTime(&tScan, s.evAll0, s.evScan1);
-            cudaEventElapsedTime(&tGather, s.evAll0, s.evDbg[0]);
+            cudaEventElapsedTime(&tGather, s.evAll0, s.evGather);
             cudaEventElapsedTime(&tTerm, s.evAll0, s.evDbg[1]);
             if (wantSel) cudaEventElapsedTime(&tLists, s.evAll0, s.evDbg[2]);
             cudaGetLastError();

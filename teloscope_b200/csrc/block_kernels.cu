@@ -223,7 +223,7 @@ __device__ __forceinline__ void gatherTile(const GatherParams &g, uint32_t tile,
             if (oc < g.selCap) { g.canIdx[oc] = static_cast<uint32_t>(o); if (g.sel4Can) g.sel4Can[oc] = m4; }
             ++oc;
         } else if (flags & kMatchTerm) {
-            if (on < g.selCap) { if (g.sel4Nct) g.sel4Nct[on] = m4; else g.nctIdx[on] = static_cast<uint32_t>(o); }
+            if (on < g.selCapNct) { if (g.sel4Nct) g.sel4Nct[on] = m4; else g.nctIdx[on] = static_cast<uint32_t>(o); }
             ++on;
         }
         ++o;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kGatherThreads) gatherDenseKernel(const Gather
                     g.canIdx[oc + __popc(bc & laneLt)] = static_cast<uint32_t>(o + k);
                     if (g.sel4Can) g.sel4Can[oc + __popc(bc & laneLt)] = m4;
                 }
-                if (isN && on + __popc(bn & laneLt) < g.selCap) {
+                if (isN && on + __popc(bn & laneLt) < g.selCapNct) {
                     if (g.sel4Nct) g.sel4Nct[on + __popc(bn & laneLt)] = m4;
                     else g.nctIdx[on + __popc(bn & laneLt)] = static_cast<uint32_t>(o + k);
                 }

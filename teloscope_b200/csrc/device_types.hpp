@@ -296,7 +296,8 @@ struct GatherParams {
     DevMatch *matches;             // ordered output
     unsigned long long matchCap;
     uint32_t *canIdx, *nctIdx;     // positions in `matches` of the canonical / terminal non-canonical records
-    unsigned long long selCap;     // capacity of each index list
+    unsigned long long selCap;     // capacity of the canonical index list (and of sel4Can)
+    unsigned long long selCapNct;  // capacity of the terminal non-canonical one (and of sel4Nct)
     uint32_t *sel4Can, *sel4Nct;   // TLS_OUT_PACKED: the final tls_match4 lists, written by the gather itself (else null)
     uint32_t *denseTiles;          // tiles with many records (dense units, other scan kernels): listed by the first gather kernel,
     unsigned int *denseCount;      // copied by the second one with a block per tile (capacity nTiles)

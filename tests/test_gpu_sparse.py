@@ -172,6 +172,34 @@ def test_packed_windows_with_exceptions(tb):
     check(tb, cfg, seqs, packed=True)
 
 
+def test_gather_behind_the_scan_keeps_or_redoes(tb):
+    """From the second batch of a context on, the gather is enqueued behind the scan with the buffers the previous batch left
+    (csrc/api.cu enqueueScan) and kept only if the batch's totals fit them.  One context sees a small batch, a batch with
+    several times the matches (the speculative gather must be redone after the buffers grew), the small one again (kept);
+    every result equals the one of a fresh context, for the three record forms."""
+    rng = np.random.default_rng(1618)
+    small = [build(rng, 150_000, b"TTAGGG", 1000, 50000, 3000, 2500, [(70_000, 120, True)], iupac=3, variants=b"ACGT")]
+    big = [build(rng, n, b"TTAGGG", 1000, 50000, 14000, 9000, [(int(a), 200, bool(a & 1)) for a in rng.integers(60000, n - 60000, size=40)],
+                 iupac=5, variants=b"ACGT") for n in (900_000, 400_000, 132_001)]
+    for kw in ({}, {"compact": True}, {"packed": True}):
+        mk = lambda: tb.Scanner(tb.ScanConfig(patterns=["TTAGGG", "TCAGGG", "TGAGGG", "TTGGGG"], **kw))
+        fresh = []
+        for batch in (small, big):
+            sc = mk()
+            try:
+                fresh.append(sc.scan_batch(batch, None, tb.MODE_GENOME))
+            finally:
+                sc.close()
+        sc = mk()
+        try:
+            for batch, want in ((small, fresh[0]), (big, fresh[1]), (small, fresh[0]), (big, fresh[1])):
+                got = sc.scan_batch(batch, None, tb.MODE_GENOME)
+                for name in ("windows", "canonical", "noncanonical", "terminal", "its", "window_off", "canonical_off", "noncanonical_off", "n_fwd", "n_rev"):
+                    assert getattr(got, name).tobytes() == getattr(want, name).tobytes(), (kw, name)
+        finally:
+            sc.close()
+
+
 def test_sparse_units_large_random(tb):
     """A few Mbp of random sequence with the headline pattern set: the common path (no chain survives the zero-lane proof)."""
     rng = np.random.default_rng(4711)

@@ -16,3 +16,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:read
   -o $out/prof_reads python scripts/trace_reads.py > $out/ncu_reads.log 2>&1
 ls -la $out
 tail -3 $out/pytest.log $out/smoke.log 2>/dev/null; cat $out/bench.json; tail -3 $out/bench.err; tail -5 $out/trace.log
+TLS_TRACE=1 TLS_PACKED=1 timeout 300 python scripts/trace_bench.py 1.0 > $out/trace_tls.log 2>&1; grep -E "timeline|submit:|row kernel enqueued" $out/trace_tls.log | tail -3 | cut -c1-300
+TLS_PIPE_TRACE=1 timeout 600 python scripts/pipeline_bench.py 1.0 --repeat 3 > $out/pipeline_n1.log 2>&1; tail -8 $out/pipeline_n1.log

@@ -559,6 +559,8 @@ int enqueueGather(tls_ctx *ctx, Slot &s, uint64_t matchCap, uint64_t selCap, uin
 // Enqueue the scan for the slot: memsets, lean kernel over the single-contig tiles, general kernel
 // over the rest and over the rows the lean kernel handed back, per-tile prefix, copy of the counters.
 int enqueueScan(tls_ctx *ctx, Slot &s) {
+    static const bool traceOn = std::getenv("TLS_TRACE") != nullptr;
+    const auto tEnter = std::chrono::steady_clock::now();
     const uint32_t nTiles = s.nTilesAll;
     const size_t nSlots = static_cast<size_t>(std::max<uint32_t>(nTiles, 1)) * kTileRows;
     TLS_CUDA(s.dSlots.reserve(nSlots * ctx->slotCap * sizeof(DevMatch)));
@@ -715,6 +717,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
                 TLS_CUDA(cudaEventRecord(s.evSetup, s.stream));          // counters zeroed, small contigs' windows final
                 TLS_CUDA(cudaStreamWaitEvent(s.copyStream, s.evSetup, 0));
                 TLS_CUDA(launchRowScan(f, static_cast<int>(std::min<uint32_t>(static_cast<uint32_t>(ctx->smCount), (nRow + kRowWarps - 1) / kRowWarps)), s.stream));
+                if (traceOn) fprintf(stderr, " [row kernel enqueued %.3f ms into enqueueScan]", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tEnter).count());
                 s.launches++;
                 for (int k = 0; k + 1 < ranges; ++k) {
                     const uint32_t uHi = std::min<uint32_t>(nRow, static_cast<uint32_t>(k + 1) * upp), uLo = static_cast<uint32_t>(k) * upp;
@@ -1111,7 +1114,9 @@ static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
             if (pt.bytes) std::memcpy(hm + pt.off, pt.src, pt.bytes);
             if (pt.view) pt.view->setView(dm + pt.off);
         }
+        tr.mark("meta_pack");
         TLS_CUDA(cudaMemcpyAsync(dm, hm, total, cudaMemcpyHostToDevice, s.stream));
+        tr.mark("meta_copy");
         TLS_CUDA(s.dRowTiles.reserve(std::max<size_t>(static_cast<size_t>(s.nRowUnits) * sizeof(DevRowUnit), 16)));
         TLS_CUDA(s.dTiles.reserve(std::max<size_t>(static_cast<size_t>(s.nTilesAll) * sizeof(DevTile), 16)));
         if (!s.rowRegions.empty())

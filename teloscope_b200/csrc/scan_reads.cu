@@ -122,19 +122,43 @@ __global__ void __launch_bounds__(kReadThreads, 1) readScanKernel(const ReadPara
             s.last = newLast;
             return;
         }
-        const uint32_t packed = nM | (__popc(Cs) << 8);
-        uint32_t bits = Bm;
-        while (bits) {
-            const int l = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const uint32_t f = __shfl_sync(0xFFFFFFFFu, firstPos, l), la = __shfl_sync(0xFFFFFFFFu, lastPos, l);
-            const uint32_t pk = __shfl_sync(0xFFFFFFFFu, packed, l);
-            if (s.active && f - s.last <= K) {
-                s.count += pk & 0xFFu; s.can += pk >> 8; s.last = la;
+        // Canonical content: the lanes with matches fall into SEGMENTS at the run starts (a lane's first match out of reach of
+        // the match before it).  The lanes before the first start continue the open run; a start closes the run before it; a
+        // closed run without a canonical match is dropped by Phase 1, so only the segments with canonical matches and the last
+        // one (it stays open) are summed up, with two reductions and two shuffles each.  A telomeric row is one segment.
+        const uint32_t lower = Bm & laneLt;
+        const uint32_t prevLast = __shfl_sync(0xFFFFFFFFu, lastPos, lower ? 31 - __clz(lower) : 0);
+        const bool isStart = M != 0u && (lower ? firstPos - prevLast > K : (!s.active || firstPos - s.last > K));
+        const uint32_t Bs = __ballot_sync(0xFFFFFFFFu, isStart);
+        const uint32_t canCnt = __popc(Cs);
+        auto below32 = [](int k) { return k >= 32 ? 0xFFFFFFFFu : (1u << k) - 1u; };      // lanes before lane k
+        auto segment = [&](uint32_t seg, bool fresh) {
+            const bool inSeg = (seg >> lane) & 1u;
+            const uint32_t cnt = __reduce_add_sync(0xFFFFFFFFu, inSeg ? nM : 0u), can = __reduce_add_sync(0xFFFFFFFFu, inSeg ? canCnt : 0u);
+            const uint32_t la = __shfl_sync(0xFFFFFFFFu, lastPos, 31 - __clz(seg));
+            if (fresh) {
+                s.active = true; s.start = __shfl_sync(0xFFFFFFFFu, firstPos, __ffs(seg) - 1); s.count = cnt; s.can = can;
             } else {
-                if (s.active) closeRun(s);
-                s.active = true; s.start = f; s.last = la; s.count = pk & 0xFFu; s.can = pk >> 8;
+                s.count += cnt; s.can += can;
             }
+            s.last = la;
+        };
+        const int firstStart = Bs ? __ffs(Bs) - 1 : 32;
+        const uint32_t seg0 = Bm & below32(firstStart);
+        if (seg0) segment(seg0, false);                               // the open run goes on (the first lane is no start)
+        if (Bs) {
+            if (s.active) closeRun(s);                                // the run before the first start is over
+            const int lastStart = 31 - __clz(Bs);
+            uint32_t cm = __ballot_sync(0xFFFFFFFFu, Cs != 0u) & ~below32(firstStart) & below32(lastStart);   // canonical lanes of closed middle segments
+            while (cm) {
+                const int b = __ffs(cm) - 1;
+                const int h = 31 - __clz(Bs & below32(b + 1));                            // the start of b's segment
+                const int nx = __ffs(Bs & ~below32(b + 1)) - 1;                           // the next start: b < lastStart
+                segment(Bm & ~below32(h) & below32(nx), true);
+                closeRun(s);
+                cm &= ~below32(nx);
+            }
+            segment(Bm & ~below32(lastStart), true);                  // the last segment stays open
         }
         // a run that no start of a later row can reach any more is closed now: the next rows then take the cheap path above
         if (s.active && rowPos + kReadStride - s.last > K) closeRun(s);

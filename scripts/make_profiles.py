@@ -55,4 +55,15 @@ if rep.exists():
             "dram_bytes_per_base": (rd + wr) / bases[0], "dram_bytes_read": rd, "dram_bytes_write": wr, "bases": bases[0],
             "source": f"ncu --set full --clock-control none, TLS_PACKED=1 TLS_ROW_PARTS=1 scripts/trace_bench.py 0.25 (profiles/{tag}_rows_summary.md); "
                       "dram__bytes_read.sum + dram__bytes_write.sum of one launch"}, indent=1) + "\n")
+# timeline of one step (TLS_TRACE=1) and the file pipeline's stage clock
+tl = src / "trace_tls.log"
+if tl.exists():
+    keep = [ln.strip()[:400] for ln in tl.read_text().splitlines() if "timeline" in ln or ln.startswith("[tls] submit:") or ln.startswith("iter ")]
+    (out / f"{tag}_step_timeline.md").write_text(f"# {tag} — one step on the device and on the host (`TLS_TRACE=1 TLS_PACKED=1 python scripts/trace_bench.py 1.0`, "
+                                                "four steps; CUDA events and steady_clock marks of csrc/api.cu; the fprintf calls of the trace inflate the host phases)\n\n```\n"
+                                                + "\n".join(keep) + "\n```\n")
+pl = src / "pipeline_n1.log"
+if pl.exists():
+    (out / f"{tag}_pipeline_stages.md").write_text(f"# {tag} — teloscope-b200, 3.03 Gbp FASTA -> 11 files on one device: stage clock (`TLS_PIPE_TRACE=1`, "
+                                                  "`scripts/pipeline_bench.py 1.0 --repeat 3`)\n\n```\n" + pl.read_text() + "```\n")
 print("written to", out)

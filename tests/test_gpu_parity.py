@@ -163,3 +163,41 @@ def test_sharded_job_equals_single_batch(tb):
         for k in ("windows", "canonical", "noncanonical", "terminal", "its"):
             assert a[k].tobytes() == b[k].tobytes(), k
         assert a["n_canonical"] == b["n_canonical"]
+
+
+def test_one_context_through_every_mode(tb):
+    """One context sees genome, read, tips and genome batches in turn (the per-batch tables are views into one block in the
+    genome / tips path and buffers of their own in the fused read path; the gather runs behind the scan from the second
+    batch on): every result equals the one a fresh context gives."""
+    rng = np.random.default_rng(20251)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def contig(n, cap):
+        body = rng.choice(acgt, size=n)
+        body[:cap] = np.frombuffer((b"CCCTAA" * (cap // 6 + 1))[:cap], dtype=np.uint8)
+        body[n - cap:] = np.frombuffer((b"TTAGGG" * (cap // 6 + 1))[:cap], dtype=np.uint8)
+        return body.tobytes()
+
+    genome = [contig(260_000, 3000), contig(9_000, 600), contig(131_072, 2000), b"", contig(700, 60)]
+    reads = [contig(15_000, 400), bytes(rng.choice(acgt, size=12_000)), contig(9_000, 90), b"ACGT" * 50]
+    jobs = [(genome, tb.MODE_GENOME), (reads, tb.MODE_READS), (genome, tb.MODE_TIPS), (genome[::-1], tb.MODE_GENOME), (reads[::-1], tb.MODE_READS),
+            (genome, tb.MODE_GENOME)]
+    names = ("windows", "canonical", "noncanonical", "terminal", "its", "window_off", "canonical_off", "noncanonical_off", "n_fwd", "n_rev", "passed")
+    for kw in ({}, {"packed": True}):
+        cfg = tb.ScanConfig(patterns=["TTAGGG", "TCAGGG", "TGAGGG", "TTGGGG"], min_block_len=42, **kw)
+        want = []
+        for seqs, mode in jobs:
+            sc = tb.Scanner(cfg)
+            try:
+                want.append(sc.scan_batch(seqs, None, mode))
+            finally:
+                sc.close()
+        sc = tb.Scanner(cfg)
+        try:
+            for (seqs, mode), w in zip(jobs, want):
+                got = sc.scan_batch(seqs, None, mode)
+                for name in names:
+                    assert getattr(got, name).tobytes() == getattr(w, name).tobytes(), (kw, mode, name)
+        finally:
+            sc.close()
+        assert bool(want[1].passed[0]) and not bool(want[1].passed[1]) and len(want[0].terminal) >= 4

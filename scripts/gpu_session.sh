@@ -14,6 +14,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:rowS
   -o $out/prof_rows env TLS_PACKED=1 TLS_ROW_PARTS=1 python scripts/trace_bench.py 0.25 > $out/ncu_full.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:readScanKernel -s 1 -c 1 \
   -o $out/prof_reads python scripts/trace_reads.py > $out/ncu_reads.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gatherKernel|gatherDenseKernel|terminalKernel|itsConnKernel|itsWalkKernel' -s 5 -c 5 \
+  -o $out/prof_blocks env TLS_PACKED=1 python scripts/trace_bench.py 1.0 > $out/ncu_blocks.log 2>&1
 ls -la $out
 tail -3 $out/pytest.log $out/smoke.log 2>/dev/null; cat $out/bench.json; tail -3 $out/bench.err; tail -5 $out/trace.log
 TLS_TRACE=1 TLS_PACKED=1 timeout 300 python scripts/trace_bench.py 1.0 > $out/trace_tls.log 2>&1; grep -E "timeline|submit:|row kernel enqueued" $out/trace_tls.log | tail -3 | cut -c1-300

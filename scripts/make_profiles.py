@@ -55,6 +55,22 @@ if rep.exists():
             "dram_bytes_per_base": (rd + wr) / bases[0], "dram_bytes_read": rd, "dram_bytes_write": wr, "bases": bases[0],
             "source": f"ncu --set full --clock-control none, TLS_PACKED=1 TLS_ROW_PARTS=1 scripts/trace_bench.py 0.25 (profiles/{tag}_rows_summary.md); "
                       "dram__bytes_read.sum + dram__bytes_write.sum of one launch"}, indent=1) + "\n")
+# the kernels behind the scan: headline metrics of each
+rep = src / "prof_blocks.ncu-rep"
+if rep.exists():
+    keys = ("Kernel Name", "gpu__time_duration.sum", "smsp__inst_executed.sum", "launch__registers_per_thread", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+    with open(out / f"{tag}_block_kernels_summary.md", "w") as fh:
+        fh.write(f"# {tag} — the kernels behind the scan on the 3.03 Gbp batch (packed records): ncu --set full --clock-control none, one launch each\n")
+        for kern in ("gatherKernel", "gatherDenseKernel", "terminalKernel", "itsConnKernel", "itsWalkKernel"):
+            m = run("python", "scripts/ncu_metrics.py", str(rep), kern)
+            fh.write(f"\n## {kern}\n\n")
+            for ln in m.splitlines():
+                if any(ln.startswith(f"- {k} ") for k in keys):
+                    fh.write(ln + "\n")
+            l = run("python", "scripts/ncu_lines.py", str(rep), kern, "--top", "8")
+            fh.write(f"\nhottest source lines (share of executed warp instructions, share of stall samples):\n\n```\n{l}```\n")
 # timeline of one step (TLS_TRACE=1) and the file pipeline's stage clock
 tl = src / "trace_tls.log"
 if tl.exists():

@@ -186,3 +186,47 @@ def test_gfa_reader_writer_equals_reference(tmp_path):
         mine = tmp_path / (f.stem + ".norm.gfa")
         subprocess.run([str(exe), "--gfa-normalize", str(f), str(mine)], check=True, capture_output=True)
         assert mine.read_text().splitlines() == want, f.name
+
+
+def test_packed_records_widen_exactly():
+    """tls_window8 / tls_window_exc / tls_match4 (include/teloscope_b200.h) as the binding widens them (BatchResult._build):
+    fabricated records, no device.  Field packing, the 255 = 'see the exception list' rule and item-relative positions."""
+    rng = np.random.default_rng(8)
+    n_win, L = 500, 6
+    acgt = rng.integers(0, 1001, size=(n_win, 4)).astype(np.uint32)
+    acgt[:4] = [[1023, 0, 0, 0], [0, 1023, 0, 0], [0, 0, 1023, 0], [0, 0, 0, 1023]]
+    allm = rng.integers(0, 254, size=n_win).astype(np.uint32)
+    can = (allm * rng.random(n_win)).astype(np.uint32)
+    fwd = (allm * rng.random(n_win)).astype(np.uint32)
+    big = rng.choice(n_win, size=9, replace=False)
+    allm[big] = rng.integers(255, 1000, size=9); can[big] = allm[big] // 2; fwd[big] = allm[big] - 3
+    can[big[0]] = 255; can[big[1]] = 254                      # the boundary values inside exception windows
+    w = np.zeros(n_win, dtype=tb.WINDOW8_DT)
+    w["w"][:, 0] = acgt[:, 0] | (acgt[:, 1] << 10) | (acgt[:, 2] << 20) | ((acgt[:, 3] & 3) << 30)
+    w["w"][:, 1] = (acgt[:, 3] >> 2) | (np.minimum(can, 255) << 8) | (np.minimum(allm, 255) << 16) | (np.minimum(fwd, 255) << 24)
+    exc = np.zeros(len(big), dtype=tb.WINDOW_EXC_DT)
+    order = rng.permutation(len(big))                          # the list is unordered
+    exc["window"], exc["canonical"], exc["all"], exc["forward"] = big[order], can[big][order], allm[big][order], fwd[big][order]
+    win_off = np.array([0, 200, 200, n_win], dtype=np.uint64)  # three items, the second empty
+    can_off = np.array([0, 3, 3, 5], dtype=np.uint64)
+    m4 = np.array([5, 70 | (1 << 31), 0x7FFFFFFF, 0, 9 | (1 << 31)], dtype=np.uint32)
+    non_off = np.zeros(4, dtype=np.uint64)
+    abs_pos = np.array([1000, 5, 1 << 40], dtype=np.uint64)
+    r = tb._Result()
+    r.n_items, r.mode, r.pattern_len = 3, tb.MODE_GENOME, L
+    keep = [w, exc, win_off, can_off, m4, non_off]
+    r.window_off, r.windows8 = win_off.ctypes.data, w.ctypes.data
+    r.window_exc, r.n_window_exc = exc.ctypes.data, len(exc)
+    r.canonical_off, r.canonical4, r.noncanonical_off = can_off.ctypes.data, m4.ctypes.data, non_off.ctypes.data
+    r.terminal_off = r.its_off = non_off.ctypes.data
+    out = tb.BatchResult(r, copy=True, abs_pos=abs_pos)
+    assert np.array_equal(out.windows["acgt"], acgt)
+    assert np.array_equal(out.windows["can_cov"], can * L) and np.array_equal(out.windows["noncan_cov"], (allm - can) * L)
+    assert np.array_equal(out.windows["fwd_cov"], fwd * L) and np.array_equal(out.windows["rev_cov"], (allm - fwd) * L)
+    assert out.canonical["pos"].tolist() == [1005, 1070, 1000 + 0x7FFFFFFF, 1 << 40, (1 << 40) + 9]
+    assert out.canonical["fwd"].tolist() == [0, 1, 0, 0, 1] and set(out.canonical["len"].tolist()) == {L} and set(out.canonical["can"].tolist()) == {1}
+    assert len(out.noncanonical) == 0 and len(out.item(1)["windows"]) == 0 and len(out.item(2)["windows"]) == 300
+    lazy = tb.BatchResult(r, copy=False)                       # views: nothing is built before the first use
+    assert lazy._raw is not None and lazy.windows["w"].shape == (n_win, 2) and lazy._raw is None
+    assert len(lazy.window_exc) == len(big)
+    del keep

@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) rowScanKernel(const RowParams 
             k2 = fwd | (nct << 16);
             k3 = emitted;
         }
+        __syncwarp();                                          // the rows' shared-memory results have been read: the next unit may overwrite them
         k1 = __reduce_add_sync(0xFFFFFFFFu, k1);               // <= 32 rows x 1002 per half: no carry between the halves
         k2 = __reduce_add_sync(0xFFFFFFFFu, k2);
         k3 = __reduce_add_sync(0xFFFFFFFFu, k3);

@@ -1,12 +1,17 @@
 // Kernels that turn the per-row match slots into what SegmentData holds besides the window counters:
-//   tileScanKernel      exclusive prefixes over tiles of (all, canonical, terminal non-canonical) matches
-//   gatherKernel        slot arena -> one ordered match list + index lists of the -m selections
-//   itemOffsetsKernel   exclusive scan of per-item match counts
-//   terminalKernel      Teloscope::getTerminalBlocks (src/teloscope.cpp:29-176), one warp per
-//                       (item, arm), Phase 2 merged on the fly
-//   itsSeedKernel /     Teloscope::getInterstitialBlocks (src/teloscope.cpp:179-256): a block needs
-//   itsRunKernel        >= 4 canonical matches, so only runs that hold canonical matches are walked
-//   selectFinalizeKernel  final 16-byte records of the canonical / terminal non-canonical lists (-m)
+//   tileBlockSumsKernel / tileScanKernel   exclusive prefixes over tiles of (all, canonical, terminal non-canonical) records,
+//                       the list of dense tiles, the batch's totals published to mapped host memory
+//   gatherKernel / gatherDenseKernel        slot arena -> one ordered match list + the -m selections (index lists; with
+//                       TLS_OUT_PACKED the final 4-byte records): a warp per tile of sparse units, a block per dense tile
+//   itemOffsetsKernel   exclusive scan of per-item record counts
+//   terminalKernel      Teloscope::getTerminalBlocks (src/teloscope.cpp:29-176), one warp per (item, arm), record groups
+//                       cut into segments at the run starts, Phase 2 merged on the fly
+//   itsSeedKernel / itsRunKernel            Teloscope::getInterstitialBlocks (src/teloscope.cpp:179-256) for items with
+//                       complete lists: a block needs >= 4 canonical matches, so only runs that hold them are walked
+//   itsConnKernel / itsChainKernel / itsWalkKernel   the same for window-row items (sparse lists): chains of canonical matches
+//                       the zero-lane masks cannot prove apart are settled on the sequence
+//   selectFinalizeKernel / selectFinalize8Kernel     final 16- / 8-byte records of the -m lists
+//   overlapWindowsKernel, pack / zero / scatter helpers
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -160,9 +165,11 @@ __global__ void __launch_bounds__(1024) tileScanKernel(const uint32_t *tileTot, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Slot arena -> ordered match list.  One WARP per tile (32 row slots).  A tile of sparse units holds a handful of
-// canonical records: lane r copies row r's records itself.  A tile with many records (dense units, other scan kernels):
-// the warp copies slot after slot with coalesced 8-byte accesses.  (All window / item accounting was done by the scan kernels.)
+// Slot arena -> ordered match list.  gatherKernel: one WARP per tile (32 row slots) of sparse units, which holds a handful
+// of canonical records: lane r copies row r's records itself; persistent warps request the next tile's header ahead.
+// gatherDenseKernel: a tile with more than kDenseTile records (dense units, other scan kernels; listed by the tile scan)
+// is copied by one BLOCK, warp w taking four slots with coalesced 8-byte accesses.  (All window / item accounting was done
+// by the scan kernels.)
 // ------------------------------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
 #ifndef TLS_GATHER_BLOCKS_PER_SM

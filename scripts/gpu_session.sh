@@ -4,7 +4,7 @@
 tag=${1:-run}; out=gpurun_out/$tag; mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/smi.txt 2>&1
 if [ "$2" = tests ]; then
-  timeout 2400 python -m pytest tests -m gpu -q > $out/pytest.log 2>&1; echo "pytest exit $?" >> $out/pytest.log
+  timeout 2400 python -m pytest tests -m gpu -q --durations=12 > $out/pytest.log 2>&1; echo "pytest exit $?" >> $out/pytest.log
   timeout 300 python __graft_entry__.py smoke > $out/smoke.log 2>&1; echo "smoke exit $?" >> $out/smoke.log
 fi
 timeout 1500 python bench.py --steps 10 --warmup 3 > $out/bench.json 2> $out/bench.err; echo "bench exit $?" >> $out/bench.err

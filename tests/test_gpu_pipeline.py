@@ -48,16 +48,27 @@ def test_pipeline_equals_reference_outputs(golden, tmp_path):
         pytest.fail("no sm_100 device visible: GPU tests must run on a B200")
     assert BIN.exists(), "build first: make -C teloscope_b200/csrc"
     cases, fixtures = golden
-    done = 0
+    todo = []
     for c in cases:
         if c["kind"] != "fasta":
             continue
         cfg, flags = ol.config_from_args(c["args"])
-        if not device_supports(cfg, flags["genome"]):
-            continue
+        if device_supports(cfg, flags["genome"]):
+            todo.append(c)
+    assert len(todo) >= 170
+
+    def one(k):
         # every third case with the FASTA parser cutting records into 97-byte pieces (runs stitched across the cuts)
-        rc, out, err, files = run_case(tmp_path, c["fixture"], fixtures[c["fixture"]].tobytes(), c["args"],
-                                       env={"TLS_PARSE_PIECE": "97"} if done % 3 == 0 else None)
+        c = todo[k]
+        d = tmp_path / f"case{k}"
+        d.mkdir()
+        return run_case(d, c["fixture"], fixtures[c["fixture"]].tobytes(), c["args"], env={"TLS_PARSE_PIECE": "97"} if k % 3 == 0 else None)
+
+    # a case is mostly process start + CUDA context: six at a time, each in a directory of its own
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=6) as pool:
+        results = list(pool.map(one, range(len(todo))))
+    for c, (rc, out, err, files) in zip(todo, results):
         tag = (c["fixture"], c["args"])
         assert rc == 0, (tag, err)
         assert out == c["stdout"], tag
@@ -65,8 +76,6 @@ def test_pipeline_equals_reference_outputs(golden, tmp_path):
         assert sorted(files) == sorted(c["files"]), tag
         for name, lines in c["files"].items():
             assert files[name] == lines, (tag, name)
-        done += 1
-    assert done >= 170
 
 
 def test_fastq_subset_equals_reference_output(golden, tmp_path):

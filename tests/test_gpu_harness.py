@@ -3,7 +3,7 @@
 `make -C oracle ref` stages the reference's fixtures, expected outputs and test scripts next to the reference binary it
 builds (oracle/_ref/harness/, a git-ignored build directory that travels to the GPU box).  Here a scratch tree is laid out
 the way those scripts expect it (build/bin/teloscope = a wrapper around teloscope-b200, build/bin/teloscope-validate = the
-reference's validator), and they run unmodified:
+reference's validator behind a wrapper that runs a directory of manifests in six processes), and they run unmodified:
   * teloscope-validate validateFiles  (src/validate.cpp:845-887: every .tst, legacy stdout goldens and directive cases)
   * .github/workflows/val.sh          (file counts per flag set, GFA annotation checks)
   * scripts/test_gaps_bed.sh, scripts/test_n50.sh

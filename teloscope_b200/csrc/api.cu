@@ -105,6 +105,7 @@ struct Slot {
     cudaEvent_t evTerminal = nullptr, evItsLists = nullptr;
     cudaEvent_t evGather = nullptr;
     cudaEvent_t evTotals = nullptr;          // the tile scan has published the batch's totals (what tls_collect waits for first)
+    uint32_t planLaunches = 0;               // kernels launched by tls_submit in front of enqueueScan (unit plan, tile scatter)
     bool specGather = false;                 // the gather was enqueued behind the scan with the buffers of the previous batch ...
     uint64_t specMatchCap = 0, specSelCap = 0, specNctCap = 0;   // ... of these capacities: kept if the totals fit, redone after growing them if not
     cudaEvent_t evScanDone = nullptr, evCopyDone = nullptr;
@@ -581,7 +582,7 @@ int enqueueScan(tls_ctx *ctx, Slot &s) {
     TLS_CUDA(cudaMemsetAsync(s.dRedo.p, 0, 16, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dCounters.p, 0, 128, s.stream));
     TLS_CUDA(cudaMemsetAsync(s.dItemCounts.p, 0, std::max<size_t>(s.nItems, 1) * sizeof(DevItemCounts), s.stream));
-    s.launches = 0;
+    s.launches = s.planLaunches;                            // the plan kernels tls_submit launched for this batch
     // window counters: the window-row kernel writes final records; the other scan kernels add into zeroed 32-byte counters
     const uint2 *dRanges = s.dWinRanges.as<uint2>();
     const uint32_t *dRangePrefix = reinterpret_cast<const uint32_t *>(s.dWinRanges.as<uint8_t>() + s.winRanges.size() * sizeof(uint2));
@@ -1119,6 +1120,7 @@ static int tls_submit_impl(tls_ctx *ctx, const tls_batch *b, int *ticket) {
         tr.mark("meta_copy");
         TLS_CUDA(s.dRowTiles.reserve(std::max<size_t>(static_cast<size_t>(s.nRowUnits) * sizeof(DevRowUnit), 16)));
         TLS_CUDA(s.dTiles.reserve(std::max<size_t>(static_cast<size_t>(s.nTilesAll) * sizeof(DevTile), 16)));
+        s.planLaunches = (s.rowRegions.empty() || s.nRowUnits == 0 ? 0u : 1u) + (s.tiles.empty() ? 0u : 1u);
         if (!s.rowRegions.empty())
             TLS_CUDA(launchRowPlan(s.dRowRegions.as<DevRowRegion>(), static_cast<uint32_t>(s.rowRegions.size()), ctx->cfg.window_size,
                                    s.dRowTiles.as<DevRowUnit>(), s.nRowUnits, s.stream));

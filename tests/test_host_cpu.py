@@ -230,3 +230,58 @@ def test_packed_records_widen_exactly():
     assert lazy._raw is not None and lazy.windows["w"].shape == (n_win, 2) and lazy._raw is None
     assert len(lazy.window_exc) == len(big)
     del keep
+
+
+def _load_test_module(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, ROOT / "tests" / f"{name}.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_harness_setup_is_green_for_the_reference_itself(tmp_path, monkeypatch):
+    """The GPU suite runs the reference's acceptance harness against teloscope-b200 (tests/test_gpu_harness.py) with the
+    validator behind a sharding wrapper.  Here the same tree, wrapper and test functions run against the UNMODIFIED reference
+    binary on the CPU: the harness as we drive it must be green for the reference (and the wrapper must not lose a case)."""
+    import shutil
+    import stat
+    ref = ROOT / "oracle" / "_ref" / "teloscope"
+    h = _load_test_module("test_gpu_harness")
+    if not ref.exists() or not h.HARNESS.exists() or not h.VALIDATE.exists():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    tree = tmp_path / "tree"
+    for d in ("validateFiles", "testFiles", "scripts"):
+        shutil.copytree(h.HARNESS / d, tree / d)
+    (tree / ".github" / "workflows").mkdir(parents=True)
+    shutil.copy(h.HARNESS / ".github" / "workflows" / "val.sh", tree / ".github" / "workflows" / "val.sh")
+    bin_dir = tree / "build" / "bin"
+    bin_dir.mkdir(parents=True)
+    for name, text in (("teloscope", f"#!/bin/sh\nexec {ref} \"$@\"\n"), ("teloscope-validate", h.VALIDATE_WRAPPER)):
+        (bin_dir / name).write_text(text)
+        (bin_dir / name).chmod((bin_dir / name).stat().st_mode | stat.S_IEXEC)
+    shutil.copy(h.VALIDATE, bin_dir / "teloscope-validate.real")
+    monkeypatch.setattr(h, "ROOT", tmp_path)                       # the pass / fail table and logs go to the scratch directory
+    h.test_validate_files(tree)
+    h.test_val_sh(tree)
+    h.test_shell_scripts(tree, "test_gaps_bed.sh")
+    h.test_shell_scripts(tree, "test_n50.sh")
+    h.test_bam_subset_script(tree)
+    table = (tmp_path / "gpurun_out" / "harness_table.md").read_text()
+    assert table.count("| PASS |") >= 400 and table.count("| FAIL |") == 0
+
+
+def test_golden_pipeline_test_is_green_for_the_reference_itself(golden, tmp_path, monkeypatch):
+    """tests/test_gpu_pipeline.py::test_pipeline_equals_reference_outputs (every supported golden FASTA case through the binary,
+    six at a time: stdout, stderr, every file) driven against the unmodified reference binary on the CPU."""
+    ref = ROOT / "oracle" / "_ref" / "teloscope"
+    if not ref.exists():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    tp = _load_test_module("test_gpu_pipeline")
+
+    class OneDevice:
+        def tls_device_count(self):
+            return 1
+    monkeypatch.setattr(tb, "load_library", lambda: OneDevice())
+    monkeypatch.setattr(tp, "BIN", ref)
+    tp.test_pipeline_equals_reference_outputs(golden, tmp_path)
